@@ -1,0 +1,259 @@
+/*
+ * platypus_b200.h — C ABI of the B200 read-vs-haplotype likelihood engine.
+ *
+ * This is the drop-in boundary for ONE path of andyrimmer/Platypus: scoring reads
+ * against candidate haplotypes (banded affine-gap min-plus alignment + 7-mer anchor
+ * voting), turning scores into per-read log-likelihoods, and reducing those to
+ * genotype likelihoods, EM haplotype frequencies and variant posteriors.
+ *
+ * Every entry point below names the reference interface it replaces (paths relative
+ * to the reference checkout).  Plain pointers and sizes only; the caller owns every
+ * buffer; every function returns an int status (0 = PLB_OK, negative = error, text
+ * via plb_last_error()).  No entry point ever falls back to a CPU implementation:
+ * if no CUDA device / kernel image is available the call fails with PLB_ERR_CUDA.
+ */
+#ifndef PLATYPUS_B200_H
+#define PLATYPUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLB_ABI_VERSION 1
+
+/* status codes */
+#define PLB_OK              0
+#define PLB_ERR_ARG        -1   /* NULL pointer / inconsistent offsets                         */
+#define PLB_ERR_SHAPE      -2   /* limit exceeded (haplotype > 16384 bp, H > max_haps, ...)     */
+#define PLB_ERR_CUDA       -3   /* CUDA runtime error, no device, or kernel image missing       */
+#define PLB_ERR_UNSUPPORTED -4  /* option not implemented yet (flank score, HLA map-qual cap)   */
+#define PLB_ERR_NOMEM      -5
+
+/* limits inherited from the reference */
+#define PLB_MAX_HAP_LEN    16384  /* hash_size, src/cython/calign.pyx:25-27, chaplotype.pyx:180-183 */
+#define PLB_KMER           7      /* hash_nucs,  src/cython/calign.pyx:25                           */
+#define PLB_BAND           16     /* diagonals,  src/c/align.c:83-88                                */
+#define PLB_SCORE_NONE     1000000 /* "no alignment attempted" sentinel, calign.pyx:184            */
+#define PLB_LL_CAP         (-300.0) /* chaplotype.pyx:634                                           */
+
+/*
+ * Scoring options.  Mirrors the constants hard-wired in
+ * src/cython/chaplotype.pyx:606-608 (gapExtend=3, nucprior=2) and the run-time
+ * switches the hot path reads from `options`: HLATyping,
+ * calculateFlankScore, useEMLikelihoods; max_em_iters is the `maxIters` argument of
+ * Population.call (src/cython/variantcaller.pyx:141 passes 100).
+ */
+typedef struct PlbOptions {
+    int32_t gap_extend;         /* 3 */
+    int32_t nuc_prior;          /* 2 */
+    int32_t use_mapq_cap;       /* options.HLATyping; must be 0 (PLB_ERR_UNSUPPORTED otherwise) */
+    int32_t calc_flank_score;   /* options.calculateFlankScore; must be 0                       */
+    int32_t max_em_iters;       /* 100 */
+    int32_t use_em_likelihoods; /* options.useEMLikelihoods, cpopulation.pyx:654-657            */
+} PlbOptions;
+
+/*
+ * A batch of windows.  One window = what one call of callVariantsInWindow
+ * (src/cython/variantcaller.pyx:74-141) hands to Population.setup: a list of
+ * haplotypes sharing one [win_start, win_end) interval and one flank, and for every
+ * individual three read lists (good, bad, broken mates) in that order
+ * (src/cython/chaplotype.pyx:341-373).
+ *
+ * Reads live in a pool and windows refer to them by index (slot_read), which is the
+ * flat equivalent of the reference's cAlignedRead** window pointers
+ * (src/cython/cwindow.pyx:208-236): a read overlapping several windows is stored and
+ * copied to the GPU once.  Field meaning follows cAlignedRead
+ * (src/cython/htslibWrapper.pxd:187-201): seq = ASCII bases, qual = raw phred (no
+ * +33), pos/end = alignment start/end, mapq, QC-fail = bitFlag & 512.
+ *
+ * All pointers are HOST pointers for the *_host entry points and DEVICE pointers for
+ * the *_device entry points.
+ */
+typedef struct PlbWindowBatch {
+    int32_t n_windows;
+    int32_t n_individuals;      /* nInd, identical for all windows of the batch            */
+    int32_t n_haps;             /* total haplotypes = win_hap_off[n_windows]                */
+    int32_t n_reads;            /* reads in the pool                                        */
+    int64_t n_slots;            /* window-read slots = wi_slot_off[n_windows*n_individuals] */
+
+    /* per window */
+    const int32_t* win_hap_off; /* [n_windows+1] haplotype index range of each window       */
+    const int32_t* win_start;   /* [n_windows] Haplotype.startPos                           */
+    const int32_t* win_end;     /* [n_windows] Haplotype.endPos                             */
+    const int32_t* hap_start;   /* [n_windows] genomic position of base 0 of the window's
+                                   haplotype sequences = startPos - endBufferSize
+                                   (src/cython/chaplotype.pyx:604)                          */
+
+    /* per haplotype */
+    const int64_t* hap_seq_off; /* [n_haps+1] byte offsets into hap_seq                     */
+    const uint8_t* hap_seq;     /* ASCII, Haplotype.cHaplotypeSequence (flank+window+flank) */
+
+    /* per (window, individual), index w*n_individuals + i */
+    const int64_t* wi_slot_off; /* [n_windows*n_individuals+1] slot range, ordered good|bad|broken */
+    const int32_t* wi_n_good;   /* [n_windows*n_individuals] reads.windowEnd-windowStart    */
+    const int32_t* wi_n_bad;    /* [n_windows*n_individuals] badReads count                 */
+
+    /* per slot */
+    const int32_t* slot_read;   /* [n_slots] index into the read pool                       */
+
+    /* read pool */
+    const int64_t* read_seq_off;/* [n_reads+1] byte offsets into read_seq / read_qual       */
+    const uint8_t* read_seq;
+    const uint8_t* read_qual;
+    const int32_t* read_pos;    /* [n_reads] cAlignedRead.pos                               */
+    const int32_t* read_end;    /* [n_reads] cAlignedRead.end                               */
+    const uint8_t* read_mapq;   /* [n_reads]                                                */
+    const uint8_t* read_qcfail; /* [n_reads] nonzero = Read_IsQCFail                        */
+
+    /* variants, only read by plb_population_*; may be NULL / 0 when posteriors are not wanted */
+    int32_t max_variants;       /* stride of var_prior / var_phred, <= 64                   */
+    const int32_t* win_n_var;   /* [n_windows]                                              */
+    const uint64_t* hap_var_mask;/* [n_haps] bit v set iff window variant v is in hap.variants
+                                    (the `var not in vsf` test, cpopulation.pyx:509-516)    */
+    const double* var_prior;    /* [n_windows*max_variants] Variant.calculatePrior value    */
+} PlbWindowBatch;
+
+/*
+ * Per-read outputs of the scoring stage (seam S2): what
+ * Haplotype.alignReads (src/cython/chaplotype.pyx:306-377) leaves in
+ * likelihoodCache, for every haplotype of every window at once.
+ * Layout: for (w,i) the block starts at ll_off[w*nInd+i] and is [H_w][T_wi]
+ * (haplotype-major, reads in good|bad|broken order); no 999 sentinel.
+ */
+typedef struct PlbLoglikOut {
+    const int64_t* ll_off;      /* [n_windows*n_individuals+1], see plb_ll_offsets          */
+    double*  ll;                /* log-likelihoods; may be NULL                             */
+    int32_t* score;             /* best integer alignment score of mapAndAlignReadToHaplotype
+                                   (src/cython/calign.pyx:170-272); -1 where the read was
+                                   short-circuited to LL=0 (QC fail / overlap<7); may be NULL */
+} PlbLoglikOut;
+
+/*
+ * Per-window outputs of the population model (seam S3): the fields
+ * variantcaller.pyx:582 reads back from Population after setup()+call()
+ * (src/cython/cpopulation.pxd:15-35).  Fixed strides: Hmax = max_haps,
+ * Gmax = Hmax*(Hmax+1)/2, genotype order (i,j), i<=j, row-major
+ * (src/cython/cgenotype.pyx:193-218).  Any pointer may be NULL to skip that output.
+ */
+typedef struct PlbPopulationOut {
+    int32_t  max_haps;
+    double*  gl;                /* [W][nInd][Gmax] genotypeLikelihoods (rescaled, max = 1)  */
+    double*  gl_log_max;        /* [W][nInd]       maxLogLikelihoods                        */
+    double*  gof;               /* [W][Gmax][nInd] goodnessOfFitValues                      */
+    double*  hap_like;          /* [W][nInd][Hmax] sum_r log10(e)*LL  (DiploidGenotype.hap1Like) */
+    double*  freq;              /* [W][Hmax]       frequencies after EM                     */
+    double*  em_post;           /* [W][nInd][Gmax] EMLikelihoods                            */
+    int32_t* call;              /* [W][nInd]       index of called genotype, -1 = no reads  */
+    double*  var_phred;         /* [W][max_variants] calculatePosterior (phred, rounded)    */
+    int32_t* em_iters;          /* [W]             EM iterations performed                  */
+} PlbPopulationOut;
+
+typedef struct PlbContext PlbContext;
+
+/* -- context -------------------------------------------------------------------- */
+
+/* One context per GPU (and per host thread driving it).  `device` is the CUDA ordinal.
+ * `stream` is a cudaStream_t passed as void* (NULL = the context creates its own); with
+ * PyTorch pass torch.cuda.current_stream().cuda_stream so events recorded by torch see
+ * the kernels. */
+int  plb_context_create(int device, void* stream, PlbContext** out);
+void plb_context_destroy(PlbContext* ctx);
+const char* plb_last_error(void);
+int  plb_abi_version(void);
+/* number of kernel launches issued through this context since creation */
+int64_t plb_launch_count(const PlbContext* ctx);
+
+/* -- helpers (host only, no GPU work) ---------------------------------------------- */
+
+/* Fills ll_off[n_windows*n_individuals+1] for PlbLoglikOut from the HOST batch; returns
+ * total element count in *total. */
+int plb_ll_offsets(const PlbWindowBatch* host_batch, int64_t* ll_off, int64_t* total);
+/* Validates a HOST batch against the reference's limits (haplotype <= 16384 bp,
+ * hapLen >= readLen+15 for every scored read, H <= max_haps ...). */
+int plb_validate(const PlbWindowBatch* host_batch, const PlbOptions* opt, int32_t max_haps);
+
+/* -- S1: kernel seam ------------------------------------------------------------- */
+
+/*
+ * Replaces fastAlignmentRoutine (src/c/align.h:8-9, src/c/align.c:77-586) for the
+ * score (aln1/aln2/firstpos are accepted for signature compatibility and must be
+ * NULL: traceback is scope row N2).  Same argument meaning: seq1 = haplotype segment
+ * of len1 = len2+15 bases, seq2/qual2 = read, localgapopen >= len1 entries.  Host
+ * buffers; launches a 1-element batch.  Returns the score (>= 0) or a negative status.
+ */
+int plb_fast_align(PlbContext* ctx, const char* seq1, const char* seq2, const char* qual2,
+                   int len1, int len2, int gapextend, int nucprior,
+                   const char* localgapopen, char* aln1, char* aln2, int* firstpos);
+
+/*
+ * Batched S1: n explicit (read, haplotype segment) alignments.  Host buffers.
+ * hap_seg_off/read_off are [n+1] byte offsets; segment i must hold
+ * (read_len_i + 15) bases and gap_open the same number of entries.
+ */
+int plb_align_batch_host(PlbContext* ctx, int32_t n,
+                         const int64_t* hap_seg_off, const uint8_t* hap_seg, const uint8_t* gap_open,
+                         const int64_t* read_off, const uint8_t* read_seq, const uint8_t* read_qual,
+                         int gapextend, int nucprior, int32_t* scores_out);
+
+/*
+ * Replaces Haplotype.annotateWithGapOpen (src/cython/chaplotype.pyx:552-590) for a
+ * set of haplotypes.  out must hold hap_seq_off[n_haps] + n_haps bytes: haplotype h
+ * gets hapLen_h+1 entries starting at hap_seq_off[h] + h (the last one is 0).
+ */
+int plb_gap_open_host(PlbContext* ctx, int32_t n_haps, const int64_t* hap_seq_off,
+                      const uint8_t* hap_seq, uint8_t* out);
+
+/* -- S2: per-read scoring seam ----------------------------------------------------- */
+
+/*
+ * Replaces, for every (window, individual, haplotype) of the batch at once,
+ * Haplotype.alignReads / alignSingleRead (src/cython/chaplotype.pxd:44-45,
+ * chaplotype.pyx:306-384) and below them mapAndAlignReadToHaplotype
+ * (src/cython/calign.pxd:11) and alignReadToHaplotype (chaplotype.pyx:594-676).
+ */
+int plb_window_loglik_host(PlbContext* ctx, const PlbWindowBatch* host_batch,
+                           const PlbOptions* opt, PlbLoglikOut* host_out);
+
+/* -- S3: window model seam --------------------------------------------------------- */
+
+/*
+ * Replaces Population.setup + Population.call (src/cython/cpopulation.pxd:46-56,
+ * cpopulation.pyx:197-309, 678-720) for every window of the batch.  Host buffers in,
+ * host buffers out; H2D/D2H copies are part of the call.  `ll` may be NULL or a
+ * PlbLoglikOut whose buffers also receive the per-read values.
+ */
+int plb_population_run_host(PlbContext* ctx, const PlbWindowBatch* host_batch,
+                            const PlbOptions* opt, PlbPopulationOut* host_out,
+                            PlbLoglikOut* host_ll);
+
+/* -- device-resident variants (inputs already in HBM; used by the multi-GPU driver) -- */
+
+/* Copies a HOST batch into device memory owned by the context and returns an opaque
+ * handle; the handle stays valid until plb_batch_free. */
+typedef struct PlbDeviceBatch PlbDeviceBatch;
+int  plb_batch_upload(PlbContext* ctx, const PlbWindowBatch* host_batch, PlbDeviceBatch** out);
+void plb_batch_free(PlbContext* ctx, PlbDeviceBatch* b);
+
+/* Runs scoring (+ population model when pop_out != NULL) on a device-resident batch.
+ * All pointers inside dev_pop / dev_ll are DEVICE pointers (e.g. torch tensors'
+ * data_ptr()).  Asynchronous on the context's stream; no host synchronisation. */
+int plb_run_device(PlbContext* ctx, PlbDeviceBatch* batch, const PlbOptions* opt,
+                   PlbPopulationOut* dev_pop, PlbLoglikOut* dev_ll);
+
+/* Statistics of the last plb_run_device / *_host call on this context (after a stream
+ * synchronise): number of scored (read,haplotype) pairs, band-DP executions, and
+ * algorithmic cells = 16 * readLen summed over scored pairs. */
+typedef struct PlbRunStats {
+    int64_t n_pairs;
+    int64_t n_pairs_scored;
+    int64_t n_dp;
+    int64_t cells;
+} PlbRunStats;
+int plb_last_stats(PlbContext* ctx, PlbRunStats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLATYPUS_B200_H */

@@ -1,0 +1,611 @@
+/*
+ * platypus_oracle.c — CPU restatement of the Platypus read-vs-haplotype likelihood path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see platypus_oracle.h).  Written from the behaviour of the
+ * reference, function by function; every function cites the reference lines it follows
+ * (paths relative to the reference checkout).  Plain C, double arithmetic in the same
+ * order as the reference so that results can be compared tightly.
+ */
+#include "platypus_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define KMER 7
+#define HASH_SIZE 16384          /* 4^7, calign.pyx:25-27 */
+#define BAND 16
+#define BIG (1 << 28)
+
+static const double M_LTOT = -0.23025850929940459;  /* chaplotype.pyx / calign.pyx:31 */
+static const double LOG10E = 0.43429448190325182;    /* cgenotype.pyx:24 */
+static const double LOG_HALF = -0.69314718055994529; /* cgenotype.pyx:28 */
+
+static plo_align_fn g_align_fn = 0;
+static int g_align_traceback = 0;
+
+void plo_set_align_fn(plo_align_fn fn, int traceback) {
+    g_align_fn = fn;
+    g_align_traceback = traceback;
+}
+
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+/* ------------------------------------------------------------------------------------------
+ * L1 — banded affine-gap min-plus alignment, src/c/align.c:77-586.
+ *
+ * The reference walks anti-diagonals with 8 SSE lanes; restated here cell by cell.
+ * x indexes the haplotype segment (0 .. read_len+14), y the read, diagonal d = x - y in
+ * [0,15].  Per cell:
+ *   sub  = 0 if hap[x]=='N' or hap[x]==read[y], else qual[y]          (align.c:175-178,314-318)
+ *   M    = min(M,I,D)(x-1,y-1) + sub, with the y=-1 row treated as 0  (initmask, :244-250)
+ *   I    = min(I(x,y-1)+ext, M(x,y-1)+open[x]) + nucprior             (:331-335, 478-484)
+ *          at y=0 only even x see a zero M above them (the even-lane init of :244-250)
+ *   D    = min(D(x-1,y)+ext, min(M,I)(x-1,y)+open[x])                 (:320-329, 472-476)
+ * Result: min over the 16 band cells of the last read row (:261-288, 416-443, 520).
+ * -----------------------------------------------------------------------------------------*/
+int plo_band_align(const uint8_t* hap, const uint8_t* read, const uint8_t* qual, int read_len,
+                   int ext, int nuc, const uint8_t* open) {
+    int Mp[BAND], Ip[BAND], Dp[BAND], Mc[BAND], Ic[BAND], Dc[BAND];
+    for (int y = 0; y < read_len; ++y) {
+        for (int d = 0; d < BAND; ++d) {
+            int x = y + d;
+            int sub = (hap[x] == 'N' || hap[x] == read[y]) ? 0 : (int)qual[y];
+            int diag = (y == 0) ? 0 : imin(Mp[d], imin(Ip[d], Dp[d]));
+            int m = diag + sub;
+            int ins;
+            if (y == 0) {
+                ins = (x % 2 == 0) ? (int)open[x] + nuc : BIG;
+            } else if (d + 1 < BAND) {
+                ins = imin(Ip[d + 1] + ext, Mp[d + 1] + (int)open[x]) + nuc;
+            } else {
+                ins = BIG;
+            }
+            int del;
+            if (d >= 1) {
+                del = imin(Dc[d - 1] + ext, imin(Mc[d - 1], Ic[d - 1]) + (int)open[x]);
+            } else {
+                del = BIG;
+            }
+            Mc[d] = imin(m, BIG);
+            Ic[d] = imin(ins, BIG);
+            Dc[d] = imin(del, BIG);
+        }
+        memcpy(Mp, Mc, sizeof Mp);
+        memcpy(Ip, Ic, sizeof Ip);
+        memcpy(Dp, Dc, sizeof Dp);
+    }
+    int best = BIG;
+    for (int d = 0; d < BAND; ++d) best = imin(best, imin(Mp[d], imin(Ip[d], Dp[d])));
+    return best;
+}
+
+static int do_align(const uint8_t* hap_seg, const uint8_t* read, const uint8_t* qual, int read_len,
+                    int ext, int nuc, const uint8_t* open, char* aln1, char* aln2) {
+    if (g_align_fn) {
+        int firstpos = 0;
+        return g_align_fn((const char*)hap_seg, (const char*)read, (const char*)qual, read_len + 15,
+                          read_len, ext, nuc, (const char*)open,
+                          g_align_traceback ? aln1 : 0, g_align_traceback ? aln2 : 0, &firstpos);
+    }
+    return plo_band_align(hap_seg, read, qual, read_len, ext, nuc, open);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Homopolymer gap-open table, src/cython/chaplotype.pyx:64-67 evaluated:
+ *   per_base_indel_errors -> chr(int(33.5 + 10*log((idx+1)*q)/log(0.1))) - '!'
+ * (tests/test_oracle.py recomputes the table from that formula.)
+ * -----------------------------------------------------------------------------------------*/
+static const uint8_t HOMOPOL_Q[49] = {45, 42, 41, 39, 37, 32, 28, 23, 20, 19, 17, 16, 15, 14, 13, 12, 11,
+                                      11, 10, 9,  9,  8,  8,  7,  7,  7,  6,  6,  6,  5,  5,  5,  4,  4,
+                                      4,  3,  3,  3,  3,  2,  2,  2,  2,  2,  1,  1,  1,  1,  1};
+
+/* src/cython/chaplotype.pyx:552-590: scan right to left; the run length counts identical
+ * bases immediately to the right, saturates at the end of the table, and 'N' never
+ * continues a run. */
+void plo_gap_open(const uint8_t* hap, int hap_len, uint8_t* out) {
+    int homopol = -1, run = 0;
+    out[hap_len] = 0;
+    for (int i = hap_len - 1; i >= 0; --i) {
+        if ((int)hap[i] == homopol) {
+            if (run + 1 < 49) run += 1;
+        } else {
+            run = 0;
+        }
+        out[i] = HOMOPOL_Q[run];
+        homopol = hap[i];
+        if (homopol == 'N') homopol = 0;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * 7-mer hashing, src/cython/calign.pyx:61-90: c = ch & 7; 7 -> 2; two low bits.
+ * -----------------------------------------------------------------------------------------*/
+static inline uint32_t base_code(uint8_t ch) {
+    uint32_t c = ch & 7u;
+    if (c == 7u) c = 2u;
+    return c & 3u;
+}
+
+uint32_t plo_kmer_hash(const uint8_t* seq) {
+    uint32_t h = 0;
+    for (int i = 0; i < KMER; ++i) h = (h << 2) + base_code(seq[i]);
+    return h;
+}
+
+typedef struct {
+    int16_t* head; /* [HASH_SIZE]: 1 + first position with that hash, 0 = none */
+    int16_t* next; /* [hap_len+1]: indexed by 1+position */
+    int cap_next;
+} HapIndex;
+
+/* src/cython/calign.pyx:94-124: positions 0 .. hap_len-8 are indexed (range(len-7)). */
+static void hap_index_build(HapIndex* ix, const uint8_t* hap, int hap_len) {
+    memset(ix->head, 0, HASH_SIZE * sizeof(int16_t));
+    if (ix->cap_next < hap_len + 1) {
+        free(ix->next);
+        ix->cap_next = hap_len + 1;
+        ix->next = (int16_t*)malloc((size_t)ix->cap_next * sizeof(int16_t));
+    }
+    memset(ix->next, 0, (size_t)(hap_len + 1) * sizeof(int16_t));
+    if (hap_len < KMER) return;
+    for (int i = 0; i < hap_len - KMER; ++i) {
+        uint32_t h = plo_kmer_hash(hap + i);
+        int slot = i + 1;
+        if (ix->head[h] == 0) {
+            ix->head[h] = (int16_t)slot;
+        } else {
+            int j = ix->head[h];
+            while (ix->next[j] != 0) j = ix->next[j];
+            ix->next[j] = (int16_t)slot;
+        }
+    }
+}
+
+/* src/cython/calign.pyx:155-165: hashes of read k-mers 0 .. read_len-8. */
+static void read_hashes(const uint8_t* read, int read_len, int16_t* out) {
+    uint32_t h = plo_kmer_hash(read);
+    out[0] = (int16_t)h;
+    for (int i = 1; i < read_len - KMER; ++i) {
+        h = ((h << 2) & (HASH_SIZE - 1)) + base_code(read[i + KMER - 1]);
+        out[i] = (int16_t)h;
+    }
+}
+
+/* src/cython/calign.pyx:170-272 with prebuilt index / read hashes (the reference caches
+ * both: chaplotype.pyx:637-642).  counts: scratch of >= hap_len+read_len ints. */
+static int map_and_align(const uint8_t* read, const uint8_t* qual, const int16_t* rhash, int read_start,
+                         int hap_start, int read_len, int hap_len, const uint8_t* hap,
+                         const HapIndex* ix, const uint8_t* gap_open, int ext, int nuc, int* counts,
+                         char* aln1, char* aln2, int* n_dp) {
+    if (n_dp) *n_dp = 0;
+    if (read_len < KMER) return 0; /* :182-183 */
+    int maxcount = 0;
+    int best_pos = -1;
+    int best = PLB_SCORE_NONE;
+    /* :196 compares against haplotype-1 and never fires; dropped. */
+    memset(counts, 0, (size_t)(hap_len + read_len) * sizeof(int));
+    for (int i = 0; i < read_len - KMER; ++i) { /* :209-220 */
+        int hidx = ix->head[(uint16_t)rhash[i]];
+        while (hidx != 0) {
+            int pos = hidx - i - 1;
+            int c = ++counts[pos + read_len];
+            if (c > maxcount) maxcount = c;
+            hidx = ix->next[hidx];
+        }
+    }
+    if (maxcount > 0) { /* :222-247 */
+        for (int i = 0; i < hap_len + read_len; ++i) {
+            if (counts[i] != maxcount) continue;
+            int idx = i - read_len;
+            if (idx >= -read_len && idx + read_len + 15 < hap_len) {
+                int start = imax(0, idx - 8);
+                int s = do_align(hap + start, read, qual, read_len, ext, nuc, gap_open + start, aln1, aln2);
+                if (n_dp) ++*n_dp;
+                if (s < best) {
+                    best = s;
+                    best_pos = idx;
+                    if (best == 0) return 0;
+                }
+            }
+        }
+    }
+    /* :252-267 original mapping position, clamped so the segment ends inside the haplotype */
+    int idx0 = imin(read_start - hap_start, hap_len - read_len - 15);
+    if (idx0 != best_pos) {
+        int start = imax(0, idx0 - 8);
+        int s = do_align(hap + start, read, qual, read_len, ext, nuc, gap_open + start, aln1, aln2);
+        if (n_dp) ++*n_dp;
+        if (s < best) best = s;
+    }
+    return best;
+}
+
+int plo_map_and_align(const uint8_t* read, const uint8_t* qual, int read_start, int hap_start,
+                      int read_len, int hap_len, const uint8_t* hap, const uint8_t* gap_open,
+                      int ext, int nuc, int* n_dp) {
+    if (read_len < KMER) {
+        if (n_dp) *n_dp = 0;
+        return 0;
+    }
+    HapIndex ix;
+    ix.head = (int16_t*)malloc(HASH_SIZE * sizeof(int16_t));
+    ix.next = 0;
+    ix.cap_next = 0;
+    hap_index_build(&ix, hap, hap_len);
+    int16_t* rh = (int16_t*)malloc((size_t)(read_len + 1) * sizeof(int16_t));
+    read_hashes(read, read_len, rh);
+    int* counts = (int*)malloc((size_t)(hap_len + read_len + 1) * sizeof(int));
+    char* aln1 = (char*)malloc((size_t)(2 * read_len + 16));
+    char* aln2 = (char*)malloc((size_t)(2 * read_len + 16));
+    int s = map_and_align(read, qual, rh, read_start, hap_start, read_len, hap_len, hap, &ix, gap_open, ext,
+                          nuc, counts, aln1, aln2, n_dp);
+    free(aln1);
+    free(aln2);
+    free(counts);
+    free(rh);
+    free(ix.next);
+    free(ix.head);
+    return s;
+}
+
+/* src/cython/chaplotype.pyx:621-622, 634, 675-676 (useMapQualCap = 0):
+ * LL = max(-300, mLTOT*score + log(1 - exp(mLTOT*mapq))). */
+double plo_score_to_ll(int score, int mapq) {
+    double right = log(1.0 - exp(M_LTOT * (double)mapq));
+    double v = M_LTOT * (double)score + right;
+    return v > PLB_LL_CAP ? v : PLB_LL_CAP; /* NaN cannot occur: score, mapq finite */
+}
+
+/* src/cython/chaplotype.pyx:103-115 */
+int plo_overlap(int hap_start, int hap_end, int read_pos, int read_end) {
+    int s = imax(hap_start, read_pos);
+    int e = imin(hap_end, read_end);
+    return e > s ? e - s : -1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * S2 over a batch: Haplotype.alignReads, src/cython/chaplotype.pyx:306-377.
+ * -----------------------------------------------------------------------------------------*/
+static int check_opts(const PlbOptions* opt) {
+    if (!opt) return PLB_ERR_ARG;
+    if (opt->use_mapq_cap || opt->calc_flank_score) return PLB_ERR_UNSUPPORTED;
+    return PLB_OK;
+}
+
+int plo_window_loglik(const PlbWindowBatch* b, const PlbOptions* opt, PlbLoglikOut* out, int n_threads,
+                      PlbRunStats* stats) {
+    int rc = check_opts(opt);
+    if (rc) return rc;
+    if (!b || !out || !out->ll_off) return PLB_ERR_ARG;
+    const int nInd = b->n_individuals;
+    int64_t tot_pairs = 0, tot_scored = 0, tot_dp = 0, tot_cells = 0;
+    if (n_threads < 1) n_threads = 1;
+    int err = 0;
+#pragma omp parallel num_threads(n_threads) reduction(+ : tot_pairs, tot_scored, tot_dp, tot_cells)
+    {
+        HapIndex ix;
+        ix.head = (int16_t*)malloc(HASH_SIZE * sizeof(int16_t));
+        ix.next = 0;
+        ix.cap_next = 0;
+        int cap_counts = 0, cap_read = 0, cap_go = 0;
+        int* counts = 0;
+        int16_t* rh = 0;
+        char *aln1 = 0, *aln2 = 0;
+        uint8_t* go = 0;
+#pragma omp for schedule(dynamic, 16)
+        for (int w = 0; w < b->n_windows; ++w) {
+            for (int h = b->win_hap_off[w]; h < b->win_hap_off[w + 1]; ++h) {
+                const uint8_t* hap = b->hap_seq + b->hap_seq_off[h];
+                int hap_len = (int)(b->hap_seq_off[h + 1] - b->hap_seq_off[h]);
+                if (hap_len > PLB_MAX_HAP_LEN) { err = PLB_ERR_SHAPE; continue; }
+                int hloc = h - b->win_hap_off[w];
+                int H = b->win_hap_off[w + 1] - b->win_hap_off[w];
+                (void)H;
+                if (cap_go < hap_len + 1) {
+                    free(go);
+                    cap_go = hap_len + 1;
+                    go = (uint8_t*)malloc((size_t)cap_go);
+                }
+                int built = 0;
+                for (int i = 0; i < nInd; ++i) {
+                    int wi = w * nInd + i;
+                    int64_t s0 = b->wi_slot_off[wi];
+                    int T = (int)(b->wi_slot_off[wi + 1] - s0);
+                    int n_checked = b->wi_n_good[wi] + b->wi_n_bad[wi]; /* broken mates skip the overlap test */
+                    int64_t base = out->ll_off[wi] + (int64_t)hloc * T;
+                    for (int t = 0; t < T; ++t) {
+                        int r = b->slot_read[s0 + t];
+                        int rlen = (int)(b->read_seq_off[r + 1] - b->read_seq_off[r]);
+                        ++tot_pairs;
+                        int skip = 0;
+                        if (t < n_checked) { /* chaplotype.pyx:343-361 */
+                            int ov = plo_overlap(b->win_start[w], b->win_end[w], b->read_pos[r], b->read_end[r]);
+                            if (b->read_qcfail[r] || ov < KMER) skip = 1;
+                        }
+                        if (skip) {
+                            if (out->ll) out->ll[base + t] = 0.0;
+                            if (out->score) out->score[base + t] = -1;
+                            continue;
+                        }
+                        if (!built) { /* lazy, chaplotype.pyx:641-645 */
+                            hap_index_build(&ix, hap, hap_len);
+                            plo_gap_open(hap, hap_len, go);
+                            built = 1;
+                        }
+                        if (cap_read < rlen + 1) {
+                            free(rh); free(aln1); free(aln2);
+                            cap_read = rlen + 1;
+                            rh = (int16_t*)malloc((size_t)cap_read * sizeof(int16_t));
+                            aln1 = (char*)malloc((size_t)(2 * cap_read + 16));
+                            aln2 = (char*)malloc((size_t)(2 * cap_read + 16));
+                        }
+                        if (cap_counts < hap_len + rlen + 1) {
+                            free(counts);
+                            cap_counts = hap_len + rlen + 1;
+                            counts = (int*)malloc((size_t)cap_counts * sizeof(int));
+                        }
+                        const uint8_t* rs = b->read_seq + b->read_seq_off[r];
+                        const uint8_t* rq = b->read_qual + b->read_seq_off[r];
+                        if (rlen >= KMER) read_hashes(rs, rlen, rh);
+                        int ndp = 0;
+                        int sc = map_and_align(rs, rq, rh, b->read_pos[r], b->hap_start[w], rlen, hap_len, hap, &ix,
+                                               go, opt->gap_extend, opt->nuc_prior, counts, aln1, aln2, &ndp);
+                        ++tot_scored;
+                        tot_dp += ndp;
+                        tot_cells += 16 * (int64_t)rlen;
+                        if (out->ll) out->ll[base + t] = plo_score_to_ll(sc, b->read_mapq[r]);
+                        if (out->score) out->score[base + t] = sc;
+                    }
+                }
+            }
+        }
+        free(go); free(counts); free(rh); free(aln1); free(aln2);
+        free(ix.next); free(ix.head);
+    }
+    if (stats) {
+        stats->n_pairs = tot_pairs;
+        stats->n_pairs_scored = tot_scored;
+        stats->n_dp = tot_dp;
+        stats->cells = tot_cells;
+    }
+    return err;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * DiploidGenotype.calculateDataLikelihood, src/cython/cgenotype.pyx:131-189.
+ * ll1/ll2: n_total per-read log-likelihoods of the two haplotypes (good|bad|broken).
+ * -----------------------------------------------------------------------------------------*/
+double plo_genotype_loglik(const double* ll1, const double* ll2, int n_total, int n_good, int homozygous,
+                           double* gof, double* hap1_like, double* hap2_like) {
+    double likelihood = 0.0, gofsum = 0.0, h1 = 0.0, h2 = 0.0;
+    for (int r = 0; r < n_total; ++r) {
+        double a = ll1[r], c = ll2[r];
+        double la = LOG10E * a, lc = LOG10E * c;
+        h1 += la;
+        h2 += lc;
+        gofsum += la > lc ? la : lc;
+        if (homozygous) {
+            likelihood += a;                                  /* :164-165 arr1 == arr2 */
+        } else if (fabs(a - c) >= 3) {
+            likelihood += (LOG_HALF + (a > c ? a : c));       /* :168-169 */
+        } else if (fabs(a - c) <= 1e-3) {
+            likelihood += a;                                  /* :174-175 */
+        } else {
+            likelihood += log(0.5 * (exp(a) + exp(c)));       /* :178-179 */
+        }
+    }
+    if (gof) *gof = n_good > 0 ? (-10 * gofsum) / n_good : 0.0; /* :182-185 */
+    if (hap1_like) *hap1_like = h1;
+    if (hap2_like) *hap2_like = h2;
+    return likelihood;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Population.call EM loop + EMiteration, src/cython/cpopulation.pyx:678-703, 384-457.
+ * gl[i*gl_stride + g]; genotype g <-> (s,r) in the order of cgenotype.pyx:193-218.
+ * Returns the number of iterations.
+ * -----------------------------------------------------------------------------------------*/
+int plo_em(const double* gl, const int32_t* n_reads, int n_ind, int n_hap, int gl_stride, int max_iters,
+           double* freq, double* em_post) {
+    int G = n_hap * (n_hap + 1) / 2;
+    double eps = fmin(1e-3, 1.0 / (n_ind * 2 * 2));
+    double max_change = eps + 1;
+    double* newf = (double*)malloc((size_t)n_hap * sizeof(double));
+    for (int k = 0; k < n_hap; ++k) freq[k] = 1.0 / n_hap;
+    int iters = 0;
+    while (max_change > eps && iters < max_iters) {
+        int n_with = 0;
+        for (int i = 0; i < n_ind; ++i) {
+            if (n_reads[i] == 0) continue;
+            double* csr = em_post + (size_t)i * gl_stride;
+            double sum = 0.0;
+            ++n_with;
+            int g = 0;
+            for (int s = 0; s < n_hap; ++s)
+                for (int r = s; r < n_hap; ++r, ++g) {
+                    double v = gl[(size_t)i * gl_stride + g] * freq[s] * freq[r] * (1 + (r != s));
+                    csr[g] = v;
+                    sum += v;
+                }
+            if (sum > 0.0)
+                for (g = 0; g < G; ++g) csr[g] /= sum;
+        }
+        for (int k = 0; k < n_hap; ++k) newf[k] = 0.0;
+        for (int i = 0; i < n_ind; ++i) {
+            if (n_reads[i] == 0) continue;
+            const double* csr = em_post + (size_t)i * gl_stride;
+            int g = 0;
+            for (int s = 0; s < n_hap; ++s)
+                for (int r = s; r < n_hap; ++r, ++g) {
+                    newf[s] += csr[g];
+                    newf[r] += csr[g];
+                }
+        }
+        max_change = 0.0;
+        for (int k = 0; k < n_hap; ++k) {
+            newf[k] = newf[k] / (2 * n_with);
+            double ch = fabs(freq[k] - newf[k]);
+            if (ch > max_change) max_change = ch;
+            freq[k] = newf[k];
+        }
+        ++iters;
+    }
+    free(newf);
+    return iters;
+}
+
+/* Population.calculatePosterior, src/cython/cpopulation.pyx:459-594. */
+double plo_posterior(const double* gl, const int32_t* n_reads, int n_ind, int n_hap, int gl_stride,
+                     const double* freq, const uint64_t* hap_var_mask, int var, double prior) {
+    double* fp = (double*)malloc((size_t)n_hap * sizeof(double));
+    double sumf = 0.0;
+    for (int i = 0; i < n_hap; ++i) {
+        if (!((hap_var_mask[i] >> var) & 1u)) {
+            fp[i] = freq[i];
+            sumf += freq[i];
+        } else {
+            fp[i] = 0.0;
+        }
+    }
+    if (sumf > 0)
+        for (int i = 0; i < n_hap; ++i) fp[i] /= sumf;
+    double slv = 0.0, sln = 0.0;
+    for (int i = 0; i < n_ind; ++i) {
+        if (n_reads[i] == 0) continue;
+        double pv = 0.0, pn = 0.0;
+        int g = 0;
+        for (int r = 0; r < n_hap; ++r)
+            for (int s = r; s < n_hap; ++s, ++g) {
+                double l = gl[(size_t)i * gl_stride + g];
+                double factor = (r != s) ? 2.0 : 1.0;
+                pv += (factor * freq[r] * freq[s] * l);
+                pn += (factor * fp[r] * fp[s] * l);
+            }
+        slv += pv > 0 ? log(pv) : -708;
+        sln += pn > 0 ? log(pn) : -708;
+    }
+    free(fp);
+    double ratio = fmax(1e-300, exp(sln - slv));
+    return round(-10.0 * (log10(ratio * (1.0 - prior)) - log10(prior + ratio * (1.0 - prior))));
+}
+
+/* ------------------------------------------------------------------------------------------
+ * S3 over a batch: Population.setup + call, src/cython/cpopulation.pyx:197-309, 678-720.
+ * -----------------------------------------------------------------------------------------*/
+int plo_population_run(const PlbWindowBatch* b, const PlbOptions* opt, PlbPopulationOut* out,
+                       PlbLoglikOut* ll_in, int n_threads, PlbRunStats* stats) {
+    int rc = check_opts(opt);
+    if (rc) return rc;
+    if (!b || !out) return PLB_ERR_ARG;
+    const int nInd = b->n_individuals;
+    const int Hmax = out->max_haps;
+    const int Gmax = Hmax * (Hmax + 1) / 2;
+    const int64_t nwi = (int64_t)b->n_windows * nInd;
+
+    PlbLoglikOut ll;
+    int64_t* off_own = 0;
+    double* ll_own = 0;
+    if (ll_in && ll_in->ll && ll_in->ll_off) {
+        ll = *ll_in;
+    } else {
+        off_own = (int64_t*)malloc((size_t)(nwi + 1) * sizeof(int64_t));
+        int64_t tot = 0;
+        for (int w = 0; w < b->n_windows; ++w)
+            for (int i = 0; i < nInd; ++i) {
+                int64_t wi = (int64_t)w * nInd + i;
+                off_own[wi] = tot;
+                tot += (int64_t)(b->win_hap_off[w + 1] - b->win_hap_off[w]) *
+                       (b->wi_slot_off[wi + 1] - b->wi_slot_off[wi]);
+            }
+        off_own[nwi] = tot;
+        ll_own = (double*)malloc((size_t)(tot > 0 ? tot : 1) * sizeof(double));
+        ll.ll_off = off_own;
+        ll.ll = ll_own;
+        ll.score = ll_in ? ll_in->score : 0;
+    }
+    rc = plo_window_loglik(b, opt, &ll, n_threads, stats);
+    if (rc) { free(off_own); free(ll_own); return rc; }
+
+    if (n_threads < 1) n_threads = 1;
+    int err = 0;
+#pragma omp parallel for num_threads(n_threads) schedule(dynamic, 64)
+    for (int w = 0; w < b->n_windows; ++w) {
+        int H = b->win_hap_off[w + 1] - b->win_hap_off[w];
+        if (H > Hmax || H < 1) { err = PLB_ERR_SHAPE; continue; }
+        int G = H * (H + 1) / 2;
+        double* gl = (double*)malloc((size_t)nInd * Gmax * sizeof(double));
+        double* emp = (double*)calloc((size_t)nInd * Gmax, sizeof(double));
+        int32_t* nreads = (int32_t*)malloc((size_t)nInd * sizeof(int32_t));
+        double* freq = (double*)calloc((size_t)Hmax, sizeof(double));
+        for (int i = 0; i < nInd; ++i) {
+            int64_t wi = (int64_t)w * nInd + i;
+            int T = (int)(b->wi_slot_off[wi + 1] - b->wi_slot_off[wi]);
+            int ngood = b->wi_n_good[wi];
+            nreads[i] = ngood;                               /* cpopulation.pyx:286-287 */
+            double maxll = -1e7;                             /* :288 */
+            const double* L = ll.ll + ll.ll_off[wi];
+            int g = 0;
+            for (int h1 = 0; h1 < H; ++h1) {
+                if (out->hap_like) {
+                    double s = 0.0;
+                    for (int t = 0; t < T; ++t) s += LOG10E * L[(size_t)h1 * T + t];
+                    out->hap_like[((size_t)w * nInd + i) * Hmax + h1] = s;
+                }
+                for (int h2 = h1; h2 < H; ++h2, ++g) {
+                    if (ngood == 0) {                        /* :293-294 */
+                        gl[(size_t)i * Gmax + g] = 1.0;
+                        if (out->gof) out->gof[((size_t)w * Gmax + g) * nInd + i] = 0.0;
+                        continue;
+                    }
+                    double gof = 0.0;
+                    double v = plo_genotype_loglik(L + (size_t)h1 * T, L + (size_t)h2 * T, T, ngood, h1 == h2, &gof,
+                                                   0, 0);
+                    if (v > maxll) maxll = v;
+                    gl[(size_t)i * Gmax + g] = v;
+                    if (out->gof) out->gof[((size_t)w * Gmax + g) * nInd + i] = gof;
+                }
+            }
+            for (g = 0; g < G; ++g) {                        /* :304-309 */
+                double* p = &gl[(size_t)i * Gmax + g];
+                *p = (ngood != 0) ? fmax(1e-300, exp(*p - maxll)) : 1.0;
+            }
+            for (g = G; g < Gmax; ++g) gl[(size_t)i * Gmax + g] = 0.0;
+            if (out->gl_log_max) out->gl_log_max[(size_t)w * nInd + i] = maxll;
+        }
+        int iters = plo_em(gl, nreads, nInd, H, Gmax, opt->max_em_iters, freq, emp);
+        if (out->gl) memcpy(out->gl + (size_t)w * nInd * Gmax, gl, (size_t)nInd * Gmax * sizeof(double));
+        if (out->em_post) memcpy(out->em_post + (size_t)w * nInd * Gmax, emp, (size_t)nInd * Gmax * sizeof(double));
+        if (out->freq) memcpy(out->freq + (size_t)w * Hmax, freq, (size_t)Hmax * sizeof(double));
+        if (out->em_iters) out->em_iters[w] = iters;
+        if (out->call) {                                     /* callGenotypes, :623-676 */
+            for (int i = 0; i < nInd; ++i) {
+                int bestg = -1;
+                double bestv = 0.0;
+                if (nreads[i] != 0) {
+                    const double* src = (opt->use_em_likelihoods == 1 ? emp : gl) + (size_t)i * Gmax;
+                    for (int g = 0; g < G; ++g)
+                        if (bestg == -1 || src[g] > bestv) { bestv = src[g]; bestg = g; }
+                }
+                out->call[(size_t)w * nInd + i] = bestg;
+            }
+        }
+        if (out->var_phred && b->max_variants > 0 && b->win_n_var) {
+            for (int v = 0; v < b->max_variants; ++v) {
+                double ph = 0.0;
+                if (v < b->win_n_var[w])
+                    ph = plo_posterior(gl, nreads, nInd, H, Gmax, freq, b->hap_var_mask + b->win_hap_off[w], v,
+                                       b->var_prior[(size_t)w * b->max_variants + v]);
+                out->var_phred[(size_t)w * b->max_variants + v] = ph;
+            }
+        }
+        free(gl); free(emp); free(nreads); free(freq);
+    }
+    free(off_own);
+    free(ll_own);
+    return err;
+}

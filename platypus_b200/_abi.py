@@ -1,0 +1,112 @@
+"""ctypes mirror of include/platypus_b200.h (structs only; no library is loaded here)."""
+import ctypes as C
+
+import numpy as np
+
+PLB_OK = 0
+PLB_ERR_ARG = -1
+PLB_ERR_SHAPE = -2
+PLB_ERR_CUDA = -3
+PLB_ERR_UNSUPPORTED = -4
+PLB_ERR_NOMEM = -5
+PLB_SCORE_NONE = 1000000
+PLB_LL_CAP = -300.0
+PLB_MAX_HAP_LEN = 16384
+
+_p = C.c_void_p
+
+
+class PlbOptions(C.Structure):
+    _fields_ = [("gap_extend", C.c_int32), ("nuc_prior", C.c_int32), ("use_mapq_cap", C.c_int32),
+                ("calc_flank_score", C.c_int32), ("max_em_iters", C.c_int32), ("use_em_likelihoods", C.c_int32)]
+
+    @classmethod
+    def default(cls, **kw):
+        o = cls(3, 2, 0, 0, 100, 0)
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+
+class PlbWindowBatch(C.Structure):
+    _fields_ = [("n_windows", C.c_int32), ("n_individuals", C.c_int32), ("n_haps", C.c_int32),
+                ("n_reads", C.c_int32), ("n_slots", C.c_int64),
+                ("win_hap_off", _p), ("win_start", _p), ("win_end", _p), ("hap_start", _p),
+                ("hap_seq_off", _p), ("hap_seq", _p),
+                ("wi_slot_off", _p), ("wi_n_good", _p), ("wi_n_bad", _p),
+                ("slot_read", _p),
+                ("read_seq_off", _p), ("read_seq", _p), ("read_qual", _p), ("read_pos", _p), ("read_end", _p),
+                ("read_mapq", _p), ("read_qcfail", _p),
+                ("max_variants", C.c_int32), ("win_n_var", _p), ("hap_var_mask", _p), ("var_prior", _p)]
+
+
+class PlbLoglikOut(C.Structure):
+    _fields_ = [("ll_off", _p), ("ll", _p), ("score", _p)]
+
+
+class PlbPopulationOut(C.Structure):
+    _fields_ = [("max_haps", C.c_int32), ("gl", _p), ("gl_log_max", _p), ("gof", _p), ("hap_like", _p),
+                ("freq", _p), ("em_post", _p), ("call", _p), ("var_phred", _p), ("em_iters", _p)]
+
+
+class PlbRunStats(C.Structure):
+    _fields_ = [("n_pairs", C.c_int64), ("n_pairs_scored", C.c_int64), ("n_dp", C.c_int64), ("cells", C.c_int64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+def ptr(a):
+    """Host pointer of a C-contiguous numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"], "need a C-contiguous numpy array"
+    return a.ctypes.data
+
+
+def declare(lib):
+    """Attach argtypes/restypes for every symbol of include/platypus_b200.h."""
+    P = C.POINTER
+    lib.plb_context_create.argtypes = [C.c_int, _p, P(_p)]
+    lib.plb_context_create.restype = C.c_int
+    lib.plb_context_destroy.argtypes = [_p]
+    lib.plb_context_destroy.restype = None
+    lib.plb_last_error.argtypes = []
+    lib.plb_last_error.restype = C.c_char_p
+    lib.plb_abi_version.argtypes = []
+    lib.plb_abi_version.restype = C.c_int
+    lib.plb_launch_count.argtypes = [_p]
+    lib.plb_launch_count.restype = C.c_int64
+    lib.plb_ll_offsets.argtypes = [P(PlbWindowBatch), _p, P(C.c_int64)]
+    lib.plb_ll_offsets.restype = C.c_int
+    lib.plb_validate.argtypes = [P(PlbWindowBatch), P(PlbOptions), C.c_int32]
+    lib.plb_validate.restype = C.c_int
+    lib.plb_fast_align.argtypes = [_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_char_p, _p, _p, _p]
+    lib.plb_fast_align.restype = C.c_int
+    lib.plb_align_batch_host.argtypes = [_p, C.c_int32, _p, _p, _p, _p, _p, _p, C.c_int, C.c_int, _p]
+    lib.plb_align_batch_host.restype = C.c_int
+    lib.plb_gap_open_host.argtypes = [_p, C.c_int32, _p, _p, _p]
+    lib.plb_gap_open_host.restype = C.c_int
+    lib.plb_window_loglik_host.argtypes = [_p, P(PlbWindowBatch), P(PlbOptions), P(PlbLoglikOut)]
+    lib.plb_window_loglik_host.restype = C.c_int
+    lib.plb_population_run_host.argtypes = [_p, P(PlbWindowBatch), P(PlbOptions), P(PlbPopulationOut), P(PlbLoglikOut)]
+    lib.plb_population_run_host.restype = C.c_int
+    lib.plb_batch_upload.argtypes = [_p, P(PlbWindowBatch), P(_p)]
+    lib.plb_batch_upload.restype = C.c_int
+    lib.plb_batch_free.argtypes = [_p, _p]
+    lib.plb_batch_free.restype = None
+    lib.plb_run_device.argtypes = [_p, _p, P(PlbOptions), P(PlbPopulationOut), P(PlbLoglikOut)]
+    lib.plb_run_device.restype = C.c_int
+    lib.plb_last_stats.argtypes = [_p, P(PlbRunStats)]
+    lib.plb_last_stats.restype = C.c_int
+    return lib
+
+
+# every symbol the header declares; tests check the built library exports all of them
+EXPORTED_SYMBOLS = [
+    "plb_context_create", "plb_context_destroy", "plb_last_error", "plb_abi_version", "plb_launch_count",
+    "plb_ll_offsets", "plb_validate", "plb_fast_align", "plb_align_batch_host", "plb_gap_open_host",
+    "plb_window_loglik_host", "plb_population_run_host", "plb_batch_upload", "plb_batch_free",
+    "plb_run_device", "plb_last_stats",
+]

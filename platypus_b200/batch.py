@@ -1,0 +1,258 @@
+"""
+Host-side container for a batch of windows: the flat (CSR) equivalent of what
+callVariantsInWindow hands to Population.setup one window at a time
+(reference: src/cython/variantcaller.pyx:74-141, src/cython/cpopulation.pyx:197-309).
+
+The arrays are exactly the fields of PlbWindowBatch in include/platypus_b200.h.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+
+
+@dataclass
+class Read:
+    """The fields of cAlignedRead the likelihood path touches
+    (reference: src/cython/htslibWrapper.pxd:187-201)."""
+    seq: bytes
+    qual: bytes          # raw phred, not +33
+    pos: int
+    end: int
+    mapq: int = 60
+    qcfail: bool = False
+
+    @property
+    def rlen(self):
+        return len(self.seq)
+
+
+@dataclass
+class Window:
+    """One window: haplotype sequences sharing an interval + per-individual read lists."""
+    start: int                       # Haplotype.startPos
+    end: int                         # Haplotype.endPos
+    hap_start: int                   # startPos - endBufferSize (chaplotype.pyx:604)
+    haplotypes: List[bytes]
+    # per individual: (good, bad, broken) lists of Read
+    reads: List[Sequence[Sequence[Read]]]
+    hap_var_mask: Optional[List[int]] = None   # per haplotype bit mask of contained variants
+    var_prior: Optional[List[float]] = None    # per variant prior
+
+
+@dataclass
+class WindowBatch:
+    n_windows: int
+    n_individuals: int
+    win_hap_off: np.ndarray
+    win_start: np.ndarray
+    win_end: np.ndarray
+    hap_start: np.ndarray
+    hap_seq_off: np.ndarray
+    hap_seq: np.ndarray
+    wi_slot_off: np.ndarray
+    wi_n_good: np.ndarray
+    wi_n_bad: np.ndarray
+    slot_read: np.ndarray
+    read_seq_off: np.ndarray
+    read_seq: np.ndarray
+    read_qual: np.ndarray
+    read_pos: np.ndarray
+    read_end: np.ndarray
+    read_mapq: np.ndarray
+    read_qcfail: np.ndarray
+    max_variants: int = 0
+    win_n_var: Optional[np.ndarray] = None
+    hap_var_mask: Optional[np.ndarray] = None
+    var_prior: Optional[np.ndarray] = None
+    _keep: list = field(default_factory=list, repr=False)
+
+    # ---- construction -------------------------------------------------------------------
+    @classmethod
+    def from_windows(cls, windows: Sequence[Window], n_individuals: int, dedupe_reads: bool = True):
+        """Pack Window objects.  Read objects shared between windows (same Python object) are
+        stored once in the pool, like the reference's shared cAlignedRead pointers."""
+        W = len(windows)
+        win_hap_off = np.zeros(W + 1, np.int32)
+        hap_chunks, hap_lens = [], []
+        pool, pool_ix = [], {}
+        slot_read, wi_off, n_good, n_bad = [], [0], [], []
+        max_var = 0
+        for w, win in enumerate(windows):
+            assert len(win.reads) == n_individuals, "every window needs one read-list triple per individual"
+            for h in win.haplotypes:
+                hap_chunks.append(np.frombuffer(h, np.uint8))
+                hap_lens.append(len(h))
+            win_hap_off[w + 1] = win_hap_off[w] + len(win.haplotypes)
+            for i in range(n_individuals):
+                good, bad, broken = win.reads[i]
+                for r in list(good) + list(bad) + list(broken):
+                    key = id(r) if dedupe_reads else len(pool)
+                    j = pool_ix.get(key)
+                    if j is None:
+                        j = len(pool)
+                        pool_ix[key] = j
+                        pool.append(r)
+                    slot_read.append(j)
+                n_good.append(len(good))
+                n_bad.append(len(bad))
+                wi_off.append(len(slot_read))
+            if win.var_prior is not None:
+                max_var = max(max_var, len(win.var_prior))
+        hap_seq_off = np.zeros(len(hap_lens) + 1, np.int64)
+        np.cumsum(hap_lens, out=hap_seq_off[1:])
+        read_lens = [len(r.seq) for r in pool]
+        read_seq_off = np.zeros(len(pool) + 1, np.int64)
+        np.cumsum(read_lens, out=read_seq_off[1:])
+        for r in pool:
+            assert len(r.seq) == len(r.qual), "seq/qual length mismatch"
+        b = cls(
+            n_windows=W, n_individuals=n_individuals,
+            win_hap_off=win_hap_off,
+            win_start=np.array([w.start for w in windows], np.int32),
+            win_end=np.array([w.end for w in windows], np.int32),
+            hap_start=np.array([w.hap_start for w in windows], np.int32),
+            hap_seq_off=hap_seq_off,
+            hap_seq=np.concatenate(hap_chunks) if hap_chunks else np.zeros(0, np.uint8),
+            wi_slot_off=np.array(wi_off, np.int64),
+            wi_n_good=np.array(n_good, np.int32), wi_n_bad=np.array(n_bad, np.int32),
+            slot_read=np.array(slot_read, np.int32),
+            read_seq_off=read_seq_off,
+            read_seq=np.frombuffer(b"".join(r.seq for r in pool), np.uint8).copy() if pool else np.zeros(0, np.uint8),
+            read_qual=np.frombuffer(b"".join(r.qual for r in pool), np.uint8).copy() if pool else np.zeros(0, np.uint8),
+            read_pos=np.array([r.pos for r in pool], np.int32),
+            read_end=np.array([r.end for r in pool], np.int32),
+            read_mapq=np.array([r.mapq for r in pool], np.uint8),
+            read_qcfail=np.array([1 if r.qcfail else 0 for r in pool], np.uint8),
+        )
+        if max_var > 0:
+            b.max_variants = max_var
+            b.win_n_var = np.array([len(w.var_prior) if w.var_prior is not None else 0 for w in windows], np.int32)
+            masks = []
+            for w in windows:
+                masks += list(w.hap_var_mask) if w.hap_var_mask is not None else [0] * len(w.haplotypes)
+            b.hap_var_mask = np.array(masks, np.uint64)
+            pri = np.zeros((W, max_var), np.float64)
+            for i, w in enumerate(windows):
+                if w.var_prior is not None:
+                    pri[i, :len(w.var_prior)] = w.var_prior
+            b.var_prior = pri
+        return b
+
+    # ---- derived sizes ------------------------------------------------------------------
+    @property
+    def n_haps(self):
+        return int(self.win_hap_off[-1])
+
+    @property
+    def n_reads(self):
+        return int(len(self.read_pos))
+
+    @property
+    def n_slots(self):
+        return int(self.wi_slot_off[-1])
+
+    def haps_per_window(self):
+        return np.diff(self.win_hap_off)
+
+    def max_haps(self):
+        return int(self.haps_per_window().max()) if self.n_windows else 0
+
+    def ll_offsets(self):
+        """[W*nInd+1] offsets of the per-(window,individual) [H][T] blocks of PlbLoglikOut."""
+        H = np.repeat(self.haps_per_window().astype(np.int64), self.n_individuals)
+        T = np.diff(self.wi_slot_off)
+        off = np.zeros(self.n_windows * self.n_individuals + 1, np.int64)
+        np.cumsum(H * T, out=off[1:])
+        return off
+
+    def input_nbytes(self):
+        return sum(int(a.nbytes) for a in self._arrays() if a is not None)
+
+    def _arrays(self):
+        return [self.win_hap_off, self.win_start, self.win_end, self.hap_start, self.hap_seq_off, self.hap_seq,
+                self.wi_slot_off, self.wi_n_good, self.wi_n_bad, self.slot_read, self.read_seq_off, self.read_seq,
+                self.read_qual, self.read_pos, self.read_end, self.read_mapq, self.read_qcfail, self.win_n_var,
+                self.hap_var_mask, self.var_prior]
+
+    # ---- ABI ----------------------------------------------------------------------------
+    def as_struct(self):
+        """PlbWindowBatch with HOST pointers into this object's arrays (keep `self` alive)."""
+        def c(a, dt):
+            if a is None:
+                return None
+            a2 = np.ascontiguousarray(a, dtype=dt)
+            self._keep.append(a2)
+            return a2
+        s = _abi.PlbWindowBatch()
+        s.n_windows, s.n_individuals = self.n_windows, self.n_individuals
+        s.n_haps, s.n_reads, s.n_slots = self.n_haps, self.n_reads, self.n_slots
+        self._keep.clear()
+        for name, dt in (("win_hap_off", np.int32), ("win_start", np.int32), ("win_end", np.int32),
+                         ("hap_start", np.int32), ("hap_seq_off", np.int64), ("hap_seq", np.uint8),
+                         ("wi_slot_off", np.int64), ("wi_n_good", np.int32), ("wi_n_bad", np.int32),
+                         ("slot_read", np.int32), ("read_seq_off", np.int64), ("read_seq", np.uint8),
+                         ("read_qual", np.uint8), ("read_pos", np.int32), ("read_end", np.int32),
+                         ("read_mapq", np.uint8), ("read_qcfail", np.uint8), ("win_n_var", np.int32),
+                         ("hap_var_mask", np.uint64), ("var_prior", np.float64)):
+            setattr(s, name, _abi.ptr(c(getattr(self, name), dt)))
+        s.max_variants = int(self.max_variants)
+        return s
+
+    # ---- sharding (contiguous blocks of windows per GPU) ---------------------
+    def slice_windows(self, lo: int, hi: int) -> "WindowBatch":
+        """Sub-batch with windows [lo, hi); the read pool is re-indexed to the reads the
+        shard touches (reads straddling a shard boundary are duplicated into both shards, as
+        the reference duplicates them across regions)."""
+        nI = self.n_individuals
+        h0, h1 = int(self.win_hap_off[lo]), int(self.win_hap_off[hi])
+        s0, s1 = int(self.wi_slot_off[lo * nI]), int(self.wi_slot_off[hi * nI])
+        slots = self.slot_read[s0:s1]
+        used, inv = np.unique(slots, return_inverse=True)
+        rlen = np.diff(self.read_seq_off)[used]
+        roff = np.zeros(len(used) + 1, np.int64)
+        np.cumsum(rlen, out=roff[1:])
+        if len(used):
+            idx = np.concatenate([np.arange(self.read_seq_off[r], self.read_seq_off[r + 1]) for r in used]) \
+                if len(used) < 4096 else _gather_index(self.read_seq_off, used)
+        else:
+            idx = np.zeros(0, np.int64)
+        hb0, hb1 = int(self.hap_seq_off[h0]), int(self.hap_seq_off[h1])
+        return WindowBatch(
+            n_windows=hi - lo, n_individuals=nI,
+            win_hap_off=(self.win_hap_off[lo:hi + 1] - h0).astype(np.int32),
+            win_start=self.win_start[lo:hi].copy(), win_end=self.win_end[lo:hi].copy(),
+            hap_start=self.hap_start[lo:hi].copy(),
+            hap_seq_off=(self.hap_seq_off[h0:h1 + 1] - hb0).astype(np.int64),
+            hap_seq=self.hap_seq[hb0:hb1].copy(),
+            wi_slot_off=(self.wi_slot_off[lo * nI:hi * nI + 1] - s0).astype(np.int64),
+            wi_n_good=self.wi_n_good[lo * nI:hi * nI].copy(), wi_n_bad=self.wi_n_bad[lo * nI:hi * nI].copy(),
+            slot_read=inv.astype(np.int32),
+            read_seq_off=roff, read_seq=self.read_seq[idx], read_qual=self.read_qual[idx],
+            read_pos=self.read_pos[used], read_end=self.read_end[used], read_mapq=self.read_mapq[used],
+            read_qcfail=self.read_qcfail[used],
+            max_variants=self.max_variants,
+            win_n_var=None if self.win_n_var is None else self.win_n_var[lo:hi].copy(),
+            hap_var_mask=None if self.hap_var_mask is None else self.hap_var_mask[h0:h1].copy(),
+            var_prior=None if self.var_prior is None else self.var_prior[lo:hi].copy(),
+        )
+
+
+def _gather_index(off, used):
+    """Vectorised concatenation of ranges [off[r], off[r+1]) for r in used."""
+    lens = (off[used + 1] - off[used]).astype(np.int64)
+    total = int(lens.sum())
+    starts = np.repeat(off[used], lens)
+    within = np.arange(total, dtype=np.int64) - np.repeat(np.cumsum(lens) - lens, lens)
+    return starts + within
+
+
+def shard_bounds(n_windows: int, world_size: int):
+    """Contiguous, near-equal window blocks per rank."""
+    base, rem = divmod(n_windows, world_size)
+    bounds = [0]
+    for r in range(world_size):
+        bounds.append(bounds[-1] + base + (1 if r < rem else 0))
+    return bounds
