@@ -293,23 +293,65 @@ int plo_window_loglik(const PlbWindowBatch* b, const PlbOptions* opt, PlbLoglikO
         ix.next = 0;
         ix.cap_next = 0;
         int cap_counts = 0, cap_read = 0, cap_go = 0;
+        int64_t cap_rh = 0, cap_slots = 0;
+        int64_t* rh_off = 0;
         int* counts = 0;
         int16_t* rh = 0;
         char *aln1 = 0, *aln2 = 0;
         uint8_t* go = 0;
 #pragma omp for schedule(dynamic, 16)
         for (int w = 0; w < b->n_windows; ++w) {
+            /* read k-mer hashes are computed once per read and window, as the reference caches
+             * them in read.hash (chaplotype.pyx:637-638) */
+            int64_t ws0 = b->wi_slot_off[(int64_t)w * nInd], ws1 = b->wi_slot_off[(int64_t)(w + 1) * nInd];
+            int64_t need = 0;
+            int max_rlen = 0;
+            for (int64_t s = ws0; s < ws1; ++s) {
+                int r = b->slot_read[s];
+                int rlen = (int)(b->read_seq_off[r + 1] - b->read_seq_off[r]);
+                need += rlen + 1;
+                if (rlen > max_rlen) max_rlen = rlen;
+            }
+            if (cap_rh < need) {
+                free(rh);
+                cap_rh = need;
+                rh = (int16_t*)malloc((size_t)cap_rh * sizeof(int16_t));
+            }
+            if (cap_slots < ws1 - ws0 + 1) {
+                free(rh_off);
+                cap_slots = ws1 - ws0 + 1;
+                rh_off = (int64_t*)malloc((size_t)cap_slots * sizeof(int64_t));
+            }
+            if (cap_read < max_rlen + 1) {
+                free(aln1); free(aln2);
+                cap_read = max_rlen + 1;
+                aln1 = (char*)malloc((size_t)(2 * cap_read + 16));
+                aln2 = (char*)malloc((size_t)(2 * cap_read + 16));
+            }
+            {
+                int64_t o = 0;
+                for (int64_t s = ws0; s < ws1; ++s) {
+                    int r = b->slot_read[s];
+                    int rlen = (int)(b->read_seq_off[r + 1] - b->read_seq_off[r]);
+                    rh_off[s - ws0] = o;
+                    if (rlen >= KMER) read_hashes(b->read_seq + b->read_seq_off[r], rlen, rh + o);
+                    o += rlen + 1;
+                }
+            }
             for (int h = b->win_hap_off[w]; h < b->win_hap_off[w + 1]; ++h) {
                 const uint8_t* hap = b->hap_seq + b->hap_seq_off[h];
                 int hap_len = (int)(b->hap_seq_off[h + 1] - b->hap_seq_off[h]);
                 if (hap_len > PLB_MAX_HAP_LEN) { err = PLB_ERR_SHAPE; continue; }
                 int hloc = h - b->win_hap_off[w];
-                int H = b->win_hap_off[w + 1] - b->win_hap_off[w];
-                (void)H;
                 if (cap_go < hap_len + 1) {
                     free(go);
                     cap_go = hap_len + 1;
                     go = (uint8_t*)malloc((size_t)cap_go);
+                }
+                if (cap_counts < hap_len + max_rlen + 1) {
+                    free(counts);
+                    cap_counts = hap_len + max_rlen + 1;
+                    counts = (int*)malloc((size_t)cap_counts * sizeof(int));
                 }
                 int built = 0;
                 for (int i = 0; i < nInd; ++i) {
@@ -337,24 +379,12 @@ int plo_window_loglik(const PlbWindowBatch* b, const PlbOptions* opt, PlbLoglikO
                             plo_gap_open(hap, hap_len, go);
                             built = 1;
                         }
-                        if (cap_read < rlen + 1) {
-                            free(rh); free(aln1); free(aln2);
-                            cap_read = rlen + 1;
-                            rh = (int16_t*)malloc((size_t)cap_read * sizeof(int16_t));
-                            aln1 = (char*)malloc((size_t)(2 * cap_read + 16));
-                            aln2 = (char*)malloc((size_t)(2 * cap_read + 16));
-                        }
-                        if (cap_counts < hap_len + rlen + 1) {
-                            free(counts);
-                            cap_counts = hap_len + rlen + 1;
-                            counts = (int*)malloc((size_t)cap_counts * sizeof(int));
-                        }
                         const uint8_t* rs = b->read_seq + b->read_seq_off[r];
                         const uint8_t* rq = b->read_qual + b->read_seq_off[r];
-                        if (rlen >= KMER) read_hashes(rs, rlen, rh);
                         int ndp = 0;
-                        int sc = map_and_align(rs, rq, rh, b->read_pos[r], b->hap_start[w], rlen, hap_len, hap, &ix,
-                                               go, opt->gap_extend, opt->nuc_prior, counts, aln1, aln2, &ndp);
+                        int sc = map_and_align(rs, rq, rh + rh_off[s0 + t - ws0], b->read_pos[r], b->hap_start[w], rlen,
+                                               hap_len, hap, &ix, go, opt->gap_extend, opt->nuc_prior, counts, aln1,
+                                               aln2, &ndp);
                         ++tot_scored;
                         tot_dp += ndp;
                         tot_cells += 16 * (int64_t)rlen;
@@ -364,7 +394,7 @@ int plo_window_loglik(const PlbWindowBatch* b, const PlbOptions* opt, PlbLoglikO
                 }
             }
         }
-        free(go); free(counts); free(rh); free(aln1); free(aln2);
+        free(go); free(counts); free(rh); free(rh_off); free(aln1); free(aln2);
         free(ix.next); free(ix.head);
     }
     if (stats) {

@@ -1,0 +1,944 @@
+// plb_api.cu — host side of the C ABI declared in include/platypus_b200.h.
+//
+// Owns device memory and launch planning; all arithmetic of the likelihood path runs in the
+// kernels of plb_kernels.cuh.  There is deliberately no CPU implementation behind these entry
+// points: without a usable CUDA device every call fails with PLB_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/platypus_b200.h"
+#include "plb_kernels.cuh"
+
+using namespace plb;
+
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return set_err(PLB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                           __LINE__);                                                              \
+    } while (0)
+
+struct Block {
+    void* p;
+    size_t cap;
+};
+
+struct PlbContext {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int64_t launches;
+    int n_sm;
+    int smem_optin;
+    std::vector<Block> cache;   // free device blocks, reused by size
+    Counters* d_ctr;
+    Counters* h_ctr;            // pinned
+    cudaEvent_t ev;
+};
+
+struct PlbDeviceBatch {
+    DevBatch d;
+    Block blk;
+    // plans
+    AnchorPlan aplan;
+    DpPlan dplan;
+    size_t a_smem, d_smem;
+    int a_grid, d_grid;
+    bool cnt16;
+    Queue q;
+    double* ll_scratch;
+    double* em_scratch;      // [W][nInd][Gmax_plan]
+    int32_t max_haps;        // largest H in the batch
+    size_t em_scratch_elems;
+    // host copies kept for output sizing
+    int64_t n_wi;
+};
+
+extern "C" const char* plb_last_error(void) { return g_err; }
+extern "C" int plb_abi_version(void) { return PLB_ABI_VERSION; }
+
+extern "C" int plb_context_create(int device, void* stream, PlbContext** out) {
+    if (!out) return set_err(PLB_ERR_ARG, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_err(PLB_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+                       e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return set_err(PLB_ERR_ARG, "device %d out of range (have %d)", device, n);
+    CU(cudaSetDevice(device));
+    PlbContext* c = new PlbContext();
+    c->device = device;
+    c->launches = 0;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+        c->own_stream = false;
+    } else {
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->n_sm = prop.multiProcessorCount;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (prop.major < 10)
+        return set_err(PLB_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", device,
+                       prop.major, prop.minor);
+    CU(cudaMalloc(&c->d_ctr, sizeof(Counters)));
+    CU(cudaMallocHost(&c->h_ctr, sizeof(Counters)));
+    memset(c->h_ctr, 0, sizeof(Counters));
+    CU(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
+    *out = c;
+    return PLB_OK;
+}
+
+extern "C" void plb_context_destroy(PlbContext* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& b : c->cache) cudaFree(b.p);
+    cudaFree(c->d_ctr);
+    cudaFreeHost(c->h_ctr);
+    cudaEventDestroy(c->ev);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int64_t plb_launch_count(const PlbContext* c) { return c ? c->launches : 0; }
+
+static int block_get(PlbContext* c, size_t bytes, Block* out) {
+    int best = -1;
+    for (size_t i = 0; i < c->cache.size(); ++i)
+        if (c->cache[i].cap >= bytes && (best < 0 || c->cache[i].cap < c->cache[best].cap)) best = (int)i;
+    if (best >= 0) {
+        *out = c->cache[best];
+        c->cache.erase(c->cache.begin() + best);
+        return PLB_OK;
+    }
+    // drop smaller cached blocks before growing
+    for (auto& b : c->cache) cudaFree(b.p);
+    c->cache.clear();
+    size_t cap = bytes + bytes / 8 + (1 << 20);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e != cudaSuccess) return set_err(PLB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(e));
+    out->p = p;
+    out->cap = cap;
+    return PLB_OK;
+}
+
+static void block_put(PlbContext* c, Block b) {
+    if (b.p) c->cache.push_back(b);
+}
+
+// ---- host helpers -----------------------------------------------------------------------------
+
+extern "C" int plb_ll_offsets(const PlbWindowBatch* b, int64_t* ll_off, int64_t* total) {
+    if (!b || !ll_off) return set_err(PLB_ERR_ARG, "NULL argument");
+    int64_t tot = 0;
+    for (int w = 0; w < b->n_windows; ++w)
+        for (int i = 0; i < b->n_individuals; ++i) {
+            int64_t wi = (int64_t)w * b->n_individuals + i;
+            ll_off[wi] = tot;
+            tot += (int64_t)(b->win_hap_off[w + 1] - b->win_hap_off[w]) * (b->wi_slot_off[wi + 1] - b->wi_slot_off[wi]);
+        }
+    ll_off[(int64_t)b->n_windows * b->n_individuals] = tot;
+    if (total) *total = tot;
+    return PLB_OK;
+}
+
+static int check_options(const PlbOptions* o) {
+    if (!o) return set_err(PLB_ERR_ARG, "options is NULL");
+    if (o->use_mapq_cap) return set_err(PLB_ERR_UNSUPPORTED, "use_mapq_cap (HLATyping) is not implemented");
+    if (o->calc_flank_score) return set_err(PLB_ERR_UNSUPPORTED, "calc_flank_score is not implemented");
+    if (o->gap_extend < 0 || o->gap_extend > 64 || o->nuc_prior < 0 || o->nuc_prior > 64)
+        return set_err(PLB_ERR_ARG, "gap_extend / nuc_prior out of range");
+    return PLB_OK;
+}
+
+extern "C" int plb_validate(const PlbWindowBatch* b, const PlbOptions* opt, int32_t max_haps) {
+    if (!b) return set_err(PLB_ERR_ARG, "batch is NULL");
+    if (opt) {
+        int rc = check_options(opt);
+        if (rc) return rc;
+    }
+    if (b->n_windows < 0 || b->n_individuals < 1) return set_err(PLB_ERR_ARG, "bad n_windows / n_individuals");
+    if (b->n_windows == 0) return PLB_OK;
+    if (!b->win_hap_off || !b->win_start || !b->win_end || !b->hap_start || !b->hap_seq_off || !b->wi_slot_off ||
+        !b->wi_n_good || !b->wi_n_bad || !b->read_seq_off)
+        return set_err(PLB_ERR_ARG, "NULL array in batch");
+    if (b->win_hap_off[0] != 0 || b->win_hap_off[b->n_windows] != b->n_haps)
+        return set_err(PLB_ERR_ARG, "win_hap_off inconsistent with n_haps");
+    const int64_t nwi = (int64_t)b->n_windows * b->n_individuals;
+    if (b->wi_slot_off[0] != 0 || b->wi_slot_off[nwi] != b->n_slots)
+        return set_err(PLB_ERR_ARG, "wi_slot_off inconsistent with n_slots");
+    if (b->n_slots > 0 && (!b->slot_read || !b->read_seq || !b->read_qual || !b->read_pos || !b->read_end ||
+                           !b->read_mapq || !b->read_qcfail))
+        return set_err(PLB_ERR_ARG, "NULL read array in batch");
+    if (b->n_haps > 0 && !b->hap_seq) return set_err(PLB_ERR_ARG, "hap_seq is NULL");
+    for (int w = 0; w < b->n_windows; ++w) {
+        const int H = b->win_hap_off[w + 1] - b->win_hap_off[w];
+        if (H < 1) return set_err(PLB_ERR_SHAPE, "window %d has no haplotypes", w);
+        if (max_haps > 0 && H > max_haps)
+            return set_err(PLB_ERR_SHAPE, "window %d has %d haplotypes > max_haps %d (cpopulation.pyx:221)", w, H,
+                           max_haps);
+        int min_len = 1 << 30;
+        for (int h = b->win_hap_off[w]; h < b->win_hap_off[w + 1]; ++h) {
+            const int64_t len = b->hap_seq_off[h + 1] - b->hap_seq_off[h];
+            if (len < 0) return set_err(PLB_ERR_ARG, "hap_seq_off not monotone at %d", h);
+            if (len > PLB_MAX_HAP_LEN)
+                return set_err(PLB_ERR_SHAPE, "haplotype %d is %lld bp > %d (chaplotype.pyx:180)", h, (long long)len,
+                               PLB_MAX_HAP_LEN);
+            min_len = std::min<int>(min_len, (int)len);
+        }
+        for (int i = 0; i < b->n_individuals; ++i) {
+            const int64_t wi = (int64_t)w * b->n_individuals + i;
+            const int64_t T = b->wi_slot_off[wi + 1] - b->wi_slot_off[wi];
+            if (T < 0 || b->wi_n_good[wi] < 0 || b->wi_n_bad[wi] < 0 || b->wi_n_good[wi] + b->wi_n_bad[wi] > T)
+                return set_err(PLB_ERR_ARG, "read counts inconsistent for window %d individual %d", w, i);
+            for (int64_t s = b->wi_slot_off[wi]; s < b->wi_slot_off[wi + 1]; ++s) {
+                const int r = b->slot_read[s];
+                if (r < 0 || r >= b->n_reads) return set_err(PLB_ERR_ARG, "slot %lld: read index out of range", (long long)s);
+                const int64_t L = b->read_seq_off[r + 1] - b->read_seq_off[r];
+                if (L < 0 || L > 32767) return set_err(PLB_ERR_SHAPE, "read %d length %lld out of range", r, (long long)L);
+                // the reference would read past the haplotype (calign.pyx:256-259); refuse instead
+                if (L >= PLB_KMER && L + 15 > min_len)
+                    return set_err(PLB_ERR_SHAPE, "window %d: read %d (%lld bp) + 15 exceeds haplotype length %d", w, r,
+                                   (long long)L, min_len);
+            }
+        }
+    }
+    for (int64_t i = 0; i < b->read_seq_off[b->n_reads]; ++i)
+        if (b->read_qual[i] > 93) return set_err(PLB_ERR_ARG, "base quality %d > 93 at byte %lld", b->read_qual[i], (long long)i);
+    if (b->max_variants > 64) return set_err(PLB_ERR_SHAPE, "max_variants %d > 64", b->max_variants);
+    return PLB_OK;
+}
+
+// ---- upload + planning ----------------------------------------------------------------------
+
+namespace {
+
+struct Layout {  // bump allocator over one device block
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        size_t o = off;
+        off = (off + bytes + 255) & ~(size_t)255;
+        return o;
+    }
+};
+
+template <typename T>
+T* at(const Block& b, size_t off) {
+    return (T*)((uint8_t*)b.p + off);
+}
+
+struct TileLists {
+    std::vector<Tile> a, d;
+};
+
+constexpr size_t kAnchorTabBudget = 40 * 1024;   // tables + chains of one haplotype group
+constexpr size_t kAnchorHashBudget = 24 * 1024;  // read hashes of one tile
+constexpr size_t kAnchorCntBudget = 100 * 1024;  // vote arrays in shared memory if they fit
+constexpr int kAnchorMaxSlots = 256;
+constexpr size_t kDpRecBudget = 40 * 1024;
+constexpr size_t kDpProfBudget = 56 * 1024;
+constexpr int kDpMaxSlots = 128;
+constexpr int kDpMaxPairs = 4096;
+constexpr int kDpThreads = 256;
+
+int prof_row_words(int L) {
+    int n = dp_steps(L) + 4;
+    n = (n + 3) & ~3;
+    if (!((n >> 2) & 1)) n += 4;
+    return n;
+}
+
+int tab_bits(int len) {
+    int nk = len - kKmer;
+    if (nk < 1) nk = 1;
+    int bits = 6;
+    while ((1 << bits) < 2 * nk && bits < 14) ++bits;
+    return bits;
+}
+
+}  // namespace
+
+static int plan_tiles(const PlbWindowBatch* hb, TileLists& tl, AnchorPlan& ap, DpPlan& dp, int& max_read, int& max_hap,
+                      int& max_H) {
+    memset(&ap, 0, sizeof ap);
+    memset(&dp, 0, sizeof dp);
+    max_read = 0;
+    max_hap = 0;
+    max_H = 0;
+    const int nInd = hb->n_individuals;
+    std::vector<int> slot_len;
+    for (int w = 0; w < hb->n_windows; ++w) {
+        const int h0 = hb->win_hap_off[w], h1 = hb->win_hap_off[w + 1];
+        max_H = std::max(max_H, h1 - h0);
+        const int64_t s0 = hb->wi_slot_off[(int64_t)w * nInd], s1 = hb->wi_slot_off[(int64_t)(w + 1) * nInd];
+        slot_len.resize((size_t)(s1 - s0));
+        for (int64_t s = s0; s < s1; ++s) {
+            const int r = hb->slot_read[s];
+            slot_len[(size_t)(s - s0)] = (int)(hb->read_seq_off[r + 1] - hb->read_seq_off[r]);
+            max_read = std::max(max_read, slot_len[(size_t)(s - s0)]);
+        }
+        // ---- anchor tiles
+        std::vector<std::pair<int, int>> groups;
+        {
+            int g0 = h0;
+            size_t bytes = 0;
+            int tw = 0, nh_ = 0;
+            for (int h = h0; h < h1; ++h) {
+                const int len = (int)(hb->hap_seq_off[h + 1] - hb->hap_seq_off[h]);
+                max_hap = std::max(max_hap, len);
+                const size_t need = ((size_t)4 << tab_bits(len)) + 2 * (size_t)((len + 2) & ~1);
+                if (h > g0 && (bytes + need > kAnchorTabBudget || h - g0 >= 64)) {
+                    groups.push_back({g0, h});
+                    g0 = h;
+                    bytes = 0;
+                }
+                bytes += need;
+            }
+            groups.push_back({g0, h1});
+            for (auto& g : groups) {
+                tw = 0;
+                nh_ = 0;
+                for (int h = g.first; h < g.second; ++h) {
+                    const int len = (int)(hb->hap_seq_off[h + 1] - hb->hap_seq_off[h]);
+                    tw += 1 << tab_bits(len);
+                    nh_ += (len + 2) & ~1;
+                }
+                ap.tab_words = std::max(ap.tab_words, tw);
+                ap.next_halfs = std::max(ap.next_halfs, nh_);
+                ap.max_group = std::max(ap.max_group, g.second - g.first);
+            }
+        }
+        {
+            int64_t c0 = s0;
+            size_t halfs = 0;
+            auto flush = [&](int64_t c1) {
+                if (c1 <= c0) return;
+                for (auto& g : groups) tl.a.push_back(Tile{w, g.first, g.second, c0, c1});
+                ap.max_slots = std::max<int>(ap.max_slots, (int)(c1 - c0));
+                ap.rhash_halfs = std::max<int>(ap.rhash_halfs, (int)halfs);
+            };
+            for (int64_t s = s0; s < s1; ++s) {
+                const int nk = std::max(0, slot_len[(size_t)(s - s0)] - kKmer);
+                if (s > c0 && (2 * (halfs + nk) > kAnchorHashBudget || s - c0 >= kAnchorMaxSlots)) {
+                    flush(s);
+                    c0 = s;
+                    halfs = 0;
+                }
+                halfs += nk;
+            }
+            flush(s1);
+        }
+        // ---- dp tiles
+        std::vector<std::pair<int, int>> dgroups;
+        {
+            int g0 = h0;
+            size_t recs = 0;
+            for (int h = h0; h < h1; ++h) {
+                const size_t need = (size_t)(hb->hap_seq_off[h + 1] - hb->hap_seq_off[h]) + kRecPad;
+                if (h > g0 && ((recs + need) * sizeof(HapRec) > kDpRecBudget || h - g0 >= 64)) {
+                    dgroups.push_back({g0, h});
+                    g0 = h;
+                    recs = 0;
+                }
+                recs += need;
+            }
+            dgroups.push_back({g0, h1});
+            for (auto& g : dgroups) {
+                size_t r = 0;
+                for (int h = g.first; h < g.second; ++h) r += (size_t)(hb->hap_seq_off[h + 1] - hb->hap_seq_off[h]) + kRecPad;
+                dp.rec_count = std::max<int>(dp.rec_count, (int)r);
+                dp.max_group = std::max(dp.max_group, g.second - g.first);
+            }
+        }
+        {
+            int maxg = 1;
+            for (auto& g : dgroups) maxg = std::max(maxg, g.second - g.first);
+            int64_t c0 = s0;
+            size_t words = 0;
+            auto flush = [&](int64_t c1) {
+                if (c1 <= c0) return;
+                for (auto& g : dgroups) {
+                    tl.d.push_back(Tile{w, g.first, g.second, c0, c1});
+                    dp.max_pairs = std::max<int>(dp.max_pairs, (int)(c1 - c0) * (g.second - g.first));
+                }
+                dp.max_slots = std::max<int>(dp.max_slots, (int)(c1 - c0));
+                dp.prof_words = std::max<int>(dp.prof_words, (int)words);
+            };
+            for (int64_t s = s0; s < s1; ++s) {
+                const int L = slot_len[(size_t)(s - s0)];
+                const int wds = L >= kMinFastLen ? prof_row_words(L) : 0;
+                if (s > c0 && (4 * (words + wds) > kDpProfBudget || s - c0 >= kDpMaxSlots ||
+                               (s - c0 + 1) * maxg > kDpMaxPairs)) {
+                    flush(s);
+                    c0 = s;
+                    words = 0;
+                }
+                words += wds;
+            }
+            flush(s1);
+        }
+    }
+    ap.n_tiles = (int)tl.a.size();
+    dp.n_tiles = (int)tl.d.size();
+    ap.max_slots = std::max(ap.max_slots, 1);
+    ap.max_group = std::max(ap.max_group, 1);
+    dp.max_slots = std::max(dp.max_slots, 1);
+    dp.max_group = std::max(dp.max_group, 1);
+    dp.max_pairs = std::max(dp.max_pairs, 1);
+    return PLB_OK;
+}
+
+template <typename T>
+static int h2d(PlbContext* c, T* dst, const T* src, size_t n) {
+    if (n == 0 || !src) return PLB_OK;
+    CU(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return PLB_OK;
+}
+
+extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch** out) {
+    if (!c || !hb || !out) return set_err(PLB_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const int W = hb->n_windows, nInd = hb->n_individuals;
+    if (W < 0 || nInd < 1) return set_err(PLB_ERR_ARG, "bad n_windows / n_individuals");
+    const int64_t nwi = (int64_t)W * nInd;
+    const int64_t n_slots = hb->n_slots;
+    const int n_haps = hb->n_haps, n_reads = hb->n_reads;
+    const int64_t hap_bytes = n_haps ? hb->hap_seq_off[n_haps] : 0;
+    const int64_t read_bytes = n_reads ? hb->read_seq_off[n_reads] : 0;
+
+    PlbDeviceBatch* db = new PlbDeviceBatch();
+    memset(db, 0, sizeof *db);
+    db->n_wi = nwi;
+
+    // derived host arrays
+    std::vector<int64_t> ll_off((size_t)nwi + 1);
+    int64_t n_pairs = 0;
+    plb_ll_offsets(hb, ll_off.data(), &n_pairs);
+    std::vector<int32_t> slot_wi((size_t)n_slots);
+    for (int64_t wi = 0; wi < nwi; ++wi)
+        for (int64_t s = hb->wi_slot_off[wi]; s < hb->wi_slot_off[wi + 1]; ++s) slot_wi[(size_t)s] = (int32_t)wi;
+    std::vector<int32_t> hap_win((size_t)n_haps);
+    for (int w = 0; w < W; ++w)
+        for (int h = hb->win_hap_off[w]; h < hb->win_hap_off[w + 1]; ++h) hap_win[(size_t)h] = w;
+
+    TileLists tl;
+    int max_read = 0, max_hap = 0, max_H = 0;
+    plan_tiles(hb, tl, db->aplan, db->dplan, max_read, max_hap, max_H);
+    db->max_haps = max_H;
+
+    // anchor launch shape
+    db->cnt16 = (max_read - kKmer) > 255;
+    const size_t csz = db->cnt16 ? 2 : 1;
+    db->aplan.cnt_stride = ((max_hap + max_read) + 15) & ~15;
+    const size_t cnt_bytes = (size_t)kAnchorThreads * db->aplan.cnt_stride * csz;
+    size_t a_fixed = (size_t)db->aplan.tab_words * 4 + (size_t)db->aplan.next_halfs * 2 +
+                     (size_t)db->aplan.rhash_halfs * 2 + 16 + (size_t)db->aplan.max_slots * sizeof(SlotInfo) +
+                     (size_t)db->aplan.max_group * 16 + 16;
+    db->aplan.cnt_in_smem = (cnt_bytes <= kAnchorCntBudget && a_fixed + cnt_bytes + 1024 <= (size_t)c->smem_optin) ? 1 : 0;
+    db->a_smem = a_fixed + (db->aplan.cnt_in_smem ? cnt_bytes : 0);
+    if (db->a_smem + 1024 > (size_t)c->smem_optin) {
+        delete db;
+        return set_err(PLB_ERR_SHAPE, "anchor tile needs %zu bytes of shared memory", db->a_smem);
+    }
+    int a_occ = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (db->a_smem + 1024)));
+    db->a_grid = std::max(1, std::min(db->aplan.n_tiles, c->n_sm * a_occ));
+    // dp launch shape
+    db->d_smem = (size_t)db->dplan.prof_words * 4 + (size_t)db->dplan.rec_count * sizeof(HapRec) +
+                 (size_t)db->dplan.max_slots * sizeof(DpSlot) + (size_t)db->dplan.max_group * 4 +
+                 (size_t)db->dplan.max_pairs * 12 + 64;
+    if (db->d_smem + 1024 > (size_t)c->smem_optin) {
+        delete db;
+        return set_err(PLB_ERR_SHAPE, "dp tile needs %zu bytes of shared memory", db->d_smem);
+    }
+    int d_occ = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (db->d_smem + 1024)));
+    db->d_grid = std::max(1, std::min(db->dplan.n_tiles, c->n_sm * d_occ));
+
+    // device layout
+    Layout L;
+    const size_t o_win_hap_off = L.take((size_t)(W + 1) * 4), o_win_start = L.take((size_t)W * 4),
+                 o_win_end = L.take((size_t)W * 4), o_hap_start = L.take((size_t)W * 4),
+                 o_hap_seq_off = L.take((size_t)(n_haps + 1) * 8), o_hap_seq = L.take((size_t)hap_bytes + 64),
+                 o_wi_slot_off = L.take((size_t)(nwi + 1) * 8), o_wi_n_good = L.take((size_t)nwi * 4),
+                 o_wi_n_bad = L.take((size_t)nwi * 4), o_slot_read = L.take((size_t)n_slots * 4),
+                 o_read_seq_off = L.take((size_t)(n_reads + 1) * 8), o_read_seq = L.take((size_t)read_bytes + 64),
+                 o_read_qual = L.take((size_t)read_bytes + 64), o_read_pos = L.take((size_t)n_reads * 4),
+                 o_read_end = L.take((size_t)n_reads * 4), o_read_mapq = L.take((size_t)n_reads),
+                 o_read_qcfail = L.take((size_t)n_reads);
+    const bool have_var = hb->max_variants > 0 && hb->win_n_var && hb->hap_var_mask && hb->var_prior;
+    const size_t o_win_n_var = L.take(have_var ? (size_t)W * 4 : 0), o_hap_var_mask = L.take(have_var ? (size_t)n_haps * 8 : 0),
+                 o_var_prior = L.take(have_var ? (size_t)W * hb->max_variants * 8 : 0);
+    const size_t o_slot_wi = L.take((size_t)n_slots * 4), o_hap_win = L.take((size_t)n_haps * 4),
+                 o_ll_off = L.take((size_t)(nwi + 1) * 8);
+    const size_t o_gap = L.take((size_t)hap_bytes + n_haps + 64), o_wgen = L.take((size_t)W + 64),
+                 o_c0 = L.take((size_t)n_pairs * 4), o_c1 = L.take((size_t)n_pairs * 4),
+                 o_score = L.take((size_t)n_pairs * 4);
+    const size_t o_atiles = L.take(tl.a.size() * sizeof(Tile)), o_dtiles = L.take(tl.d.size() * sizeof(Tile));
+    const int qcap = (int)std::min<int64_t>(std::max<int64_t>(4096, n_pairs / 2), 1 << 26);
+    const size_t o_q = L.take((size_t)qcap * sizeof(QueueEntry)), o_qcount = L.take(64);
+    const size_t o_cntg = L.take(db->aplan.cnt_in_smem ? 0 : (size_t)db->a_grid * kAnchorThreads * db->aplan.cnt_stride * csz);
+    const size_t o_ll = L.take((size_t)n_pairs * 8);
+    const int Gp = max_H * (max_H + 1) / 2;
+    db->em_scratch_elems = (size_t)W * nInd * Gp;
+    const size_t o_em = L.take(db->em_scratch_elems * 8);
+
+    int rc = block_get(c, L.off + 256, &db->blk);
+    if (rc) {
+        delete db;
+        return rc;
+    }
+    const Block& B = db->blk;
+    DevBatch& d = db->d;
+    d.n_windows = W;
+    d.n_individuals = nInd;
+    d.n_haps = n_haps;
+    d.n_reads = n_reads;
+    d.n_slots = n_slots;
+    d.n_pairs = n_pairs;
+    d.win_hap_off = at<int32_t>(B, o_win_hap_off);
+    d.win_start = at<int32_t>(B, o_win_start);
+    d.win_end = at<int32_t>(B, o_win_end);
+    d.hap_start = at<int32_t>(B, o_hap_start);
+    d.hap_seq_off = at<int64_t>(B, o_hap_seq_off);
+    d.hap_seq = at<uint8_t>(B, o_hap_seq);
+    d.wi_slot_off = at<int64_t>(B, o_wi_slot_off);
+    d.wi_n_good = at<int32_t>(B, o_wi_n_good);
+    d.wi_n_bad = at<int32_t>(B, o_wi_n_bad);
+    d.slot_read = at<int32_t>(B, o_slot_read);
+    d.read_seq_off = at<int64_t>(B, o_read_seq_off);
+    d.read_seq = at<uint8_t>(B, o_read_seq);
+    d.read_qual = at<uint8_t>(B, o_read_qual);
+    d.read_pos = at<int32_t>(B, o_read_pos);
+    d.read_end = at<int32_t>(B, o_read_end);
+    d.read_mapq = at<uint8_t>(B, o_read_mapq);
+    d.read_qcfail = at<uint8_t>(B, o_read_qcfail);
+    d.max_variants = have_var ? hb->max_variants : 0;
+    d.win_n_var = have_var ? at<int32_t>(B, o_win_n_var) : nullptr;
+    d.hap_var_mask = have_var ? at<uint64_t>(B, o_hap_var_mask) : nullptr;
+    d.var_prior = have_var ? at<double>(B, o_var_prior) : nullptr;
+    d.slot_wi = at<int32_t>(B, o_slot_wi);
+    d.hap_win = at<int32_t>(B, o_hap_win);
+    d.ll_off = at<int64_t>(B, o_ll_off);
+    d.gap_open = at<uint8_t>(B, o_gap);
+    d.win_general = at<uint8_t>(B, o_wgen);
+    d.cand0 = at<int32_t>(B, o_c0);
+    d.cand1 = at<int32_t>(B, o_c1);
+    d.score = at<int32_t>(B, o_score);
+    db->aplan.tiles = at<Tile>(B, o_atiles);
+    db->dplan.tiles = at<Tile>(B, o_dtiles);
+    db->aplan.cnt_global = db->aplan.cnt_in_smem ? nullptr : at<uint8_t>(B, o_cntg);
+    db->q.e = at<QueueEntry>(B, o_q);
+    db->q.count = at<int32_t>(B, o_qcount);
+    db->q.cap = qcap;
+    db->ll_scratch = at<double>(B, o_ll);
+    db->em_scratch = at<double>(B, o_em);
+
+#define H2D(field, type, n)                                                        \
+    if ((rc = h2d<type>(c, (type*)d.field, (const type*)hb->field, (size_t)(n)))) { \
+        block_put(c, db->blk);                                                     \
+        delete db;                                                                 \
+        return rc;                                                                 \
+    }
+    H2D(win_hap_off, int32_t, W + 1)
+    H2D(win_start, int32_t, W)
+    H2D(win_end, int32_t, W)
+    H2D(hap_start, int32_t, W)
+    H2D(hap_seq_off, int64_t, n_haps + 1)
+    H2D(hap_seq, uint8_t, hap_bytes)
+    H2D(wi_slot_off, int64_t, nwi + 1)
+    H2D(wi_n_good, int32_t, nwi)
+    H2D(wi_n_bad, int32_t, nwi)
+    H2D(slot_read, int32_t, n_slots)
+    H2D(read_seq_off, int64_t, n_reads + 1)
+    H2D(read_seq, uint8_t, read_bytes)
+    H2D(read_qual, uint8_t, read_bytes)
+    H2D(read_pos, int32_t, n_reads)
+    H2D(read_end, int32_t, n_reads)
+    H2D(read_mapq, uint8_t, n_reads)
+    H2D(read_qcfail, uint8_t, n_reads)
+    if (have_var) {
+        H2D(win_n_var, int32_t, W)
+        H2D(hap_var_mask, uint64_t, n_haps)
+        H2D(var_prior, double, (size_t)W * hb->max_variants)
+    }
+#undef H2D
+    // derived arrays come from pageable std::vectors: the copy must finish before they die
+    if ((rc = h2d<int32_t>(c, (int32_t*)d.slot_wi, slot_wi.data(), (size_t)n_slots)) ||
+        (rc = h2d<int32_t>(c, (int32_t*)d.hap_win, hap_win.data(), (size_t)n_haps)) ||
+        (rc = h2d<int64_t>(c, (int64_t*)d.ll_off, ll_off.data(), (size_t)nwi + 1)) ||
+        (rc = h2d<Tile>(c, (Tile*)db->aplan.tiles, tl.a.data(), tl.a.size())) ||
+        (rc = h2d<Tile>(c, (Tile*)db->dplan.tiles, tl.d.data(), tl.d.size()))) {
+        block_put(c, db->blk);
+        delete db;
+        return rc;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    *out = db;
+    return PLB_OK;
+}
+
+extern "C" void plb_batch_free(PlbContext* c, PlbDeviceBatch* b) {
+    if (!c || !b) return;
+    cudaStreamSynchronize(c->stream);
+    block_put(c, b->blk);
+    delete b;
+}
+
+// ---- run --------------------------------------------------------------------------------------
+
+template <typename K>
+static int opt_in_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PLB_OK;
+}
+
+static int launch_check(PlbContext* c, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(PLB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    c->launches++;
+    return PLB_OK;
+}
+
+extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOptions* opt, PlbPopulationOut* pop,
+                              PlbLoglikOut* llo) {
+    if (!c || !db) return set_err(PLB_ERR_ARG, "NULL argument");
+    int rc = check_options(opt);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    DevBatch& d = db->d;
+    if (d.n_windows == 0) return PLB_OK;
+    if (pop && pop->max_haps < db->max_haps)
+        return set_err(PLB_ERR_SHAPE, "max_haps %d < largest window (%d haplotypes) (cpopulation.pyx:221)", pop->max_haps,
+                       db->max_haps);
+    cudaStream_t st = c->stream;
+    ScoreParams sp{opt->gap_extend, opt->nuc_prior};
+    CU(cudaMemsetAsync(d.win_general, 0, (size_t)d.n_windows, st));
+    CU(cudaMemsetAsync(db->q.count, 0, 4, st));
+    CU(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), st));
+
+    if (d.n_haps > 0) {
+        k_prep<<<d.n_haps, 128, 0, st>>>(d);
+        if ((rc = launch_check(c, "k_prep"))) return rc;
+    }
+    if (db->aplan.n_tiles > 0) {
+        if (db->cnt16) {
+            if ((rc = opt_in_smem(k_anchor<uint16_t>, db->a_smem))) return rc;
+            k_anchor<uint16_t><<<db->a_grid, kAnchorThreads, db->a_smem, st>>>(d, db->aplan, db->q, sp, c->d_ctr);
+        } else {
+            if ((rc = opt_in_smem(k_anchor<uint8_t>, db->a_smem))) return rc;
+            k_anchor<uint8_t><<<db->a_grid, kAnchorThreads, db->a_smem, st>>>(d, db->aplan, db->q, sp, c->d_ctr);
+        }
+        if ((rc = launch_check(c, "k_anchor"))) return rc;
+        k_general<<<c->n_sm * 4, 128, 0, st>>>(d, db->q, sp);
+        if ((rc = launch_check(c, "k_general"))) return rc;
+    }
+    double* ll = (llo && llo->ll) ? llo->ll : db->ll_scratch;
+    int32_t* sc = llo ? llo->score : nullptr;
+    if (db->dplan.n_tiles > 0) {
+        if ((rc = opt_in_smem(k_dp<kDpThreads>, db->d_smem))) return rc;
+        k_dp<kDpThreads><<<db->d_grid, kDpThreads, db->d_smem, st>>>(d, db->dplan, sp, ll, sc);
+        if ((rc = launch_check(c, "k_dp"))) return rc;
+    }
+    if (pop) {
+        if (!pop->gl) return set_err(PLB_ERR_ARG, "PlbPopulationOut.gl is required");
+        PopOut po{pop->max_haps, pop->gl,   pop->gl_log_max, pop->gof,       pop->hap_like,
+                  pop->freq,     pop->em_post, pop->call,    pop->var_phred, pop->em_iters};
+        const int64_t nwi = (int64_t)d.n_windows * d.n_individuals;
+        k_genotype<<<(unsigned)nwi, 64, 0, st>>>(d, ll, po);
+        if ((rc = launch_check(c, "k_genotype"))) return rc;
+        const int Hm = pop->max_haps;
+        if (!pop->em_post && Hm != db->max_haps)
+            return set_err(PLB_ERR_ARG, "em_post is NULL: max_haps must equal the batch maximum (%d)", db->max_haps);
+        int nthr_em = (int)std::min<size_t>(64, std::max<size_t>(1, (size_t)(40 * 1024) / (8 * (size_t)Hm)));
+        nthr_em = std::min(nthr_em, std::max(1, std::max(d.n_individuals, (int)d.max_variants)));
+        const size_t smem = (size_t)(2 + nthr_em) * Hm * 8;
+        if ((rc = opt_in_smem(k_population, smem))) return rc;
+        k_population<<<d.n_windows, 64, smem, st>>>(d, po, db->em_scratch, opt->max_em_iters, opt->use_em_likelihoods,
+                                                    nthr_em);
+        if ((rc = launch_check(c, "k_population"))) return rc;
+    }
+    CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    return PLB_OK;
+}
+
+extern "C" int plb_last_stats(PlbContext* c, PlbRunStats* out) {
+    if (!c || !out) return set_err(PLB_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    out->n_pairs = (int64_t)c->h_ctr->n_pairs;
+    out->n_pairs_scored = (int64_t)c->h_ctr->n_scored;
+    out->n_dp = (int64_t)c->h_ctr->n_dp;
+    out->cells = (int64_t)c->h_ctr->cells;
+    return PLB_OK;
+}
+
+// ---- host-buffer entry points --------------------------------------------------------------------
+
+static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* opt, PlbPopulationOut* hpop,
+                    PlbLoglikOut* hll) {
+    int rc = check_options(opt);
+    if (rc) return rc;
+    if (!hb) return set_err(PLB_ERR_ARG, "batch is NULL");
+    if (hb->n_windows == 0) return PLB_OK;
+    PlbDeviceBatch* db = nullptr;
+    if ((rc = plb_batch_upload(c, hb, &db))) return rc;
+    const int W = hb->n_windows, nInd = hb->n_individuals;
+    const int64_t n_pairs = db->d.n_pairs;
+    Block ob{nullptr, 0};
+    PlbPopulationOut dpop;
+    PlbLoglikOut dll;
+    memset(&dpop, 0, sizeof dpop);
+    memset(&dll, 0, sizeof dll);
+    Layout L;
+    size_t o_gl = 0, o_glmax = 0, o_gof = 0, o_hl = 0, o_freq = 0, o_em = 0, o_call = 0, o_vp = 0, o_it = 0, o_ll = 0,
+           o_sc = 0;
+    int Hm = 0, Gm = 0, V = hb->max_variants;
+    if (hpop) {
+        Hm = hpop->max_haps;
+        if (Hm < db->max_haps) {
+            plb_batch_free(c, db);
+            return set_err(PLB_ERR_SHAPE, "max_haps %d < largest window (%d haplotypes) (cpopulation.pyx:221)", Hm,
+                           db->max_haps);
+        }
+        Gm = Hm * (Hm + 1) / 2;
+        o_gl = L.take((size_t)W * nInd * Gm * 8);
+        o_glmax = L.take((size_t)W * nInd * 8);
+        o_gof = L.take(hpop->gof ? (size_t)W * Gm * nInd * 8 : 0);
+        o_hl = L.take(hpop->hap_like ? (size_t)W * nInd * Hm * 8 : 0);
+        o_freq = L.take((size_t)W * Hm * 8);
+        o_em = L.take((size_t)W * nInd * Gm * 8);
+        o_call = L.take((size_t)W * nInd * 4);
+        o_vp = L.take((size_t)W * std::max(V, 1) * 8);
+        o_it = L.take((size_t)W * 4);
+    }
+    const bool want_ll = hll && hll->ll, want_sc = hll && hll->score;
+    if (want_ll) o_ll = L.take((size_t)n_pairs * 8);
+    if (want_sc) o_sc = L.take((size_t)n_pairs * 4);
+    if ((rc = block_get(c, L.off + 256, &ob))) {
+        plb_batch_free(c, db);
+        return rc;
+    }
+    if (hpop) {
+        dpop.max_haps = Hm;
+        dpop.gl = at<double>(ob, o_gl);
+        dpop.gl_log_max = at<double>(ob, o_glmax);
+        dpop.gof = hpop->gof ? at<double>(ob, o_gof) : nullptr;
+        dpop.hap_like = hpop->hap_like ? at<double>(ob, o_hl) : nullptr;
+        dpop.freq = at<double>(ob, o_freq);
+        dpop.em_post = at<double>(ob, o_em);
+        dpop.call = at<int32_t>(ob, o_call);
+        dpop.var_phred = (V > 0 && hpop->var_phred) ? at<double>(ob, o_vp) : nullptr;
+        dpop.em_iters = at<int32_t>(ob, o_it);
+    }
+    dll.ll = want_ll ? at<double>(ob, o_ll) : nullptr;
+    dll.score = want_sc ? at<int32_t>(ob, o_sc) : nullptr;
+    rc = plb_run_device(c, db, opt, hpop ? &dpop : nullptr, &dll);
+    cudaStream_t st = c->stream;
+    auto d2h = [&](void* dst, const void* src, size_t bytes) {
+        if (rc == PLB_OK && dst && src && bytes) {
+            cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) rc = set_err(PLB_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+        }
+    };
+    if (hpop) {
+        d2h(hpop->gl, dpop.gl, (size_t)W * nInd * Gm * 8);
+        d2h(hpop->gl_log_max, dpop.gl_log_max, (size_t)W * nInd * 8);
+        d2h(hpop->gof, dpop.gof, (size_t)W * Gm * nInd * 8);
+        d2h(hpop->hap_like, dpop.hap_like, (size_t)W * nInd * Hm * 8);
+        d2h(hpop->freq, dpop.freq, (size_t)W * Hm * 8);
+        d2h(hpop->em_post, dpop.em_post, (size_t)W * nInd * Gm * 8);
+        d2h(hpop->call, dpop.call, (size_t)W * nInd * 4);
+        if (V > 0) d2h(hpop->var_phred, dpop.var_phred, (size_t)W * V * 8);
+        d2h(hpop->em_iters, dpop.em_iters, (size_t)W * 4);
+    }
+    if (want_ll) d2h(hll->ll, dll.ll, (size_t)n_pairs * 8);
+    if (want_sc) d2h(hll->score, dll.score, (size_t)n_pairs * 4);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == PLB_OK && e != cudaSuccess) rc = set_err(PLB_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
+    block_put(c, ob);
+    plb_batch_free(c, db);
+    return rc;
+}
+
+extern "C" int plb_window_loglik_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* opt,
+                                      PlbLoglikOut* out) {
+    if (!c || !out) return set_err(PLB_ERR_ARG, "NULL argument");
+    return run_host(c, hb, opt, nullptr, out);
+}
+
+extern "C" int plb_population_run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* opt,
+                                       PlbPopulationOut* out, PlbLoglikOut* ll) {
+    if (!c || !out) return set_err(PLB_ERR_ARG, "NULL argument");
+    if (!out->gl) return set_err(PLB_ERR_ARG, "PlbPopulationOut.gl is required");
+    return run_host(c, hb, opt, out, ll);
+}
+
+// ---- S1 -----------------------------------------------------------------------------------------
+
+namespace plb {
+// explicit (read, segment) alignments; the packed path for reads >= 9 bp over ACGTN segments
+__global__ void __launch_bounds__(128) k_align_batch(int n, const int64_t* __restrict__ hap_off,
+                                                     const uint8_t* __restrict__ hap, const uint8_t* __restrict__ go,
+                                                     const int64_t* __restrict__ read_off,
+                                                     const uint8_t* __restrict__ rs, const uint8_t* __restrict__ rq,
+                                                     u32* __restrict__ prof_ws, HapRec* __restrict__ rec_ws,
+                                                     const int64_t* __restrict__ prof_off,
+                                                     const int64_t* __restrict__ rec_off, int ext, int nuc,
+                                                     int32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int L = (int)(read_off[i + 1] - read_off[i]);
+    const uint8_t* h = hap + hap_off[i];
+    const uint8_t* g = go + hap_off[i];
+    const uint8_t* r = rs + read_off[i];
+    const uint8_t* q = rq + read_off[i];
+    const int seg = L + 15;
+    bool fast = L >= kMinFastLen;
+    for (int x = 0; x < seg && fast; ++x) fast = fast_code(h[x]) != 5;
+    int v;
+    if (fast) {
+        u32* prof = prof_ws + prof_off[i];
+        HapRec* rec = rec_ws + rec_off[i];
+        const int n_rows = dp_steps(L) + 4;
+        for (int y = 0; y < n_rows; ++y) prof[y] = y < L ? make_profile(fast_code(r[y]), q[y]) : 0u;
+        for (int x = 0; x < seg + kRecPad; ++x) {
+            const int ca = x < seg ? fast_code(h[x]) : 4, cb = x + 4 < seg ? fast_code(h[x + 4]) : 4;
+            const u32 oa = x < seg ? g[x] : 0u, ob = x + 4 < seg ? g[x + 4] : 0u;
+            rec[x].gow = oa | (ob << 16);
+            rec[x].sel = make_sel(ca, cb);
+        }
+        v = band_dp_fast(prof, rec, L, ext, nuc);
+    } else {
+        v = band_dp_general(h, g, r, q, L, ext, nuc);
+    }
+    out[i] = v;
+}
+
+__global__ void k_gap_open_only(int n_haps, const int64_t* __restrict__ off, const uint8_t* __restrict__ seq,
+                                uint8_t* __restrict__ out) {
+    const int h = blockIdx.x;
+    const int len = (int)(off[h + 1] - off[h]);
+    const uint8_t* hap = seq + off[h];
+    uint8_t* go = out + off[h] + h;
+    for (int i = threadIdx.x; i <= len; i += blockDim.x) go[i] = i < len ? gap_open_at(hap, len, i) : 0;
+}
+}  // namespace plb
+
+extern "C" int plb_align_batch_host(PlbContext* c, int32_t n, const int64_t* hap_seg_off, const uint8_t* hap_seg,
+                                    const uint8_t* gap_open, const int64_t* read_off, const uint8_t* read_seq,
+                                    const uint8_t* read_qual, int ext, int nuc, int32_t* scores_out) {
+    if (!c || n < 0 || (n > 0 && (!hap_seg_off || !hap_seg || !gap_open || !read_off || !read_seq || !read_qual || !scores_out)))
+        return set_err(PLB_ERR_ARG, "NULL / bad argument");
+    if (n == 0) return PLB_OK;
+    CU(cudaSetDevice(c->device));
+    std::vector<int64_t> poff((size_t)n + 1), roff((size_t)n + 1);
+    int64_t pw = 0, rw = 0;
+    for (int i = 0; i < n; ++i) {
+        const int64_t L = read_off[i + 1] - read_off[i];
+        if (L < 1 || L > 32767) return set_err(PLB_ERR_SHAPE, "alignment %d: read length %lld out of range", i, (long long)L);
+        if (hap_seg_off[i + 1] - hap_seg_off[i] < L + 15)
+            return set_err(PLB_ERR_SHAPE, "alignment %d: segment shorter than read+15 (align.c:88)", i);
+        poff[i] = pw;
+        roff[i] = rw;
+        pw += dp_steps((int)L) + 8;
+        rw += L + 15 + kRecPad;
+    }
+    poff[n] = pw;
+    roff[n] = rw;
+    const int64_t hb = hap_seg_off[n], rb = read_off[n];
+    Layout L;
+    const size_t o_ho = L.take((size_t)(n + 1) * 8), o_h = L.take((size_t)hb + 64), o_g = L.take((size_t)hb + 64),
+                 o_ro = L.take((size_t)(n + 1) * 8), o_rs = L.take((size_t)rb + 64), o_rq = L.take((size_t)rb + 64),
+                 o_po = L.take((size_t)(n + 1) * 8), o_rco = L.take((size_t)(n + 1) * 8), o_pw = L.take((size_t)pw * 4),
+                 o_rw = L.take((size_t)rw * sizeof(HapRec)), o_out = L.take((size_t)n * 4);
+    Block B;
+    int rc = block_get(c, L.off + 256, &B);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](size_t off, const void* src, size_t bytes) {
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync((uint8_t*)B.p + off, src, bytes, cudaMemcpyHostToDevice, st);
+    };
+    up(o_ho, hap_seg_off, (size_t)(n + 1) * 8);
+    up(o_h, hap_seg, (size_t)hb);
+    up(o_g, gap_open, (size_t)hb);
+    up(o_ro, read_off, (size_t)(n + 1) * 8);
+    up(o_rs, read_seq, (size_t)rb);
+    up(o_rq, read_qual, (size_t)rb);
+    up(o_po, poff.data(), (size_t)(n + 1) * 8);
+    up(o_rco, roff.data(), (size_t)(n + 1) * 8);
+    if (e == cudaSuccess) {
+        k_align_batch<<<(n + 127) / 128, 128, 0, st>>>(n, at<int64_t>(B, o_ho), at<uint8_t>(B, o_h), at<uint8_t>(B, o_g),
+                                                        at<int64_t>(B, o_ro), at<uint8_t>(B, o_rs), at<uint8_t>(B, o_rq),
+                                                        at<u32>(B, o_pw), at<HapRec>(B, o_rw), at<int64_t>(B, o_po),
+                                                        at<int64_t>(B, o_rco), ext, nuc, at<int32_t>(B, o_out));
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(scores_out, (uint8_t*)B.p + o_out, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    block_put(c, B);
+    if (e != cudaSuccess) return set_err(PLB_ERR_CUDA, "plb_align_batch_host: %s", cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return set_err(PLB_ERR_CUDA, "plb_align_batch_host: %s", cudaGetErrorString(e2));
+    return PLB_OK;
+}
+
+extern "C" int plb_fast_align(PlbContext* c, const char* seq1, const char* seq2, const char* qual2, int len1, int len2,
+                              int gapextend, int nucprior, const char* localgapopen, char* aln1, char* aln2,
+                              int* firstpos) {
+    if (!c || !seq1 || !seq2 || !qual2 || !localgapopen) return set_err(PLB_ERR_ARG, "NULL argument");
+    if (aln1 || aln2) return set_err(PLB_ERR_UNSUPPORTED, "traceback (aln1/aln2) is not implemented");
+    if (len1 != len2 + 15) return set_err(PLB_ERR_SHAPE, "len1 must be len2 + 15 (align.c:88)");
+    (void)firstpos;
+    int64_t ho[2] = {0, len1}, ro[2] = {0, len2};
+    int32_t score = 0;
+    int rc = plb_align_batch_host(c, 1, ho, (const uint8_t*)seq1, (const uint8_t*)localgapopen, ro, (const uint8_t*)seq2,
+                                  (const uint8_t*)qual2, gapextend, nucprior, &score);
+    return rc ? rc : score;
+}
+
+extern "C" int plb_gap_open_host(PlbContext* c, int32_t n_haps, const int64_t* off, const uint8_t* seq, uint8_t* out) {
+    if (!c || n_haps < 0 || (n_haps > 0 && (!off || !seq || !out))) return set_err(PLB_ERR_ARG, "NULL / bad argument");
+    if (n_haps == 0) return PLB_OK;
+    CU(cudaSetDevice(c->device));
+    const int64_t nb = off[n_haps];
+    Layout L;
+    const size_t o_off = L.take((size_t)(n_haps + 1) * 8), o_seq = L.take((size_t)nb + 64), o_out = L.take((size_t)nb + n_haps + 64);
+    Block B;
+    int rc = block_get(c, L.off + 256, &B);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    cudaError_t e = cudaMemcpyAsync(at<uint8_t>(B, o_off), off, (size_t)(n_haps + 1) * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && nb) e = cudaMemcpyAsync(at<uint8_t>(B, o_seq), seq, (size_t)nb, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        k_gap_open_only<<<n_haps, 128, 0, st>>>(n_haps, at<int64_t>(B, o_off), at<uint8_t>(B, o_seq), at<uint8_t>(B, o_out));
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, at<uint8_t>(B, o_out), (size_t)nb + n_haps, cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    block_put(c, B);
+    if (e != cudaSuccess) return set_err(PLB_ERR_CUDA, "plb_gap_open_host: %s", cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return set_err(PLB_ERR_CUDA, "plb_gap_open_host: %s", cudaGetErrorString(e2));
+    return PLB_OK;
+}

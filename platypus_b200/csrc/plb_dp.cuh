@@ -1,0 +1,310 @@
+// plb_dp.cuh — banded affine-gap min-plus alignment, one alignment per thread.
+//
+// Replaces the forward pass of fastAlignmentRoutine (reference: src/c/align.c:77-521).
+// The reference sweeps anti-diagonals with 8 SSE2 int16 lanes; here one CUDA thread owns
+// one (read, haplotype segment) alignment and keeps the same 2x8 anti-diagonal lanes in
+// registers as packed s16x2 words, updated with the sm_100a packed-halfword min/add
+// instructions (VIADD.16x2, VIMNMX.S16x2, VIADDMNMX.S16x2) and PRMT.
+//
+// Lane layout.  Step pair t computes two anti-diagonals:
+//   even vector lane i : cell (x = t+i,   y = t-i)   diagonal d = 2i
+//   odd  vector lane i : cell (x = t+1+i, y = t-i)   diagonal d = 2i+1
+// Register k of a vector packs lanes (k, k+4) as (lo16, hi16).  With that packing a
+// one-lane shift of a vector is a register renaming plus ONE PRMT.
+//
+// Substitution cost without compares.  Each read row y has a 32-bit "profile"
+//   prof[y] = cost vs haplotype base A | C<<8 | G<<16 | T<<24   (0 where it matches read[y])
+// and each haplotype position x a PRMT selector that picks byte code(x) for the lo lane and
+// byte code(x+4) for the hi lane (or a zero byte when the haplotype base is 'N', which the
+// reference scores as a free match, align.c:175-178).  One PRMT yields two cells' costs.
+//
+// Everything here is in phred units (the reference works in phred*4 with the traceback
+// label in the low bits; traceback is not computed here and never changes the score).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PLB_HD __host__ __device__ __forceinline__
+#else
+#define PLB_HD static inline
+#ifndef __align__
+#define __align__(n) __attribute__((aligned(n)))
+#endif
+#endif
+
+namespace plb {
+
+typedef uint32_t u32;
+
+constexpr u32 kInf2 = 0x70007000u;  // "+inf" in both lanes; INF + any one-step cost < 0x8000
+constexpr int kInf = 0x7000;
+constexpr int kScoreBig = 1 << 28;
+
+// ---- packed s16x2 primitives (host emulation is used by the CPU unit test of the lane logic)
+#if defined(__CUDA_ARCH__)
+PLB_HD u32 vadd2(u32 a, u32 b) { return __vadd2(a, b); }
+PLB_HD u32 vmin2(u32 a, u32 b) { return __vmins2(a, b); }
+PLB_HD u32 vaddmin2(u32 a, u32 b, u32 c) { return __viaddmin_s16x2(a, b, c); }  // min(a+b, c)
+PLB_HD u32 prmt(u32 a, u32 b, u32 s) { return __byte_perm(a, b, s); }
+#else
+PLB_HD u32 vadd2(u32 a, u32 b) {
+    return ((a + b) & 0xFFFFu) | ((((a >> 16) + (b >> 16)) & 0xFFFFu) << 16);
+}
+PLB_HD u32 vmin2(u32 a, u32 b) {
+    int16_t al = (int16_t)(a & 0xFFFF), bl = (int16_t)(b & 0xFFFF);
+    int16_t ah = (int16_t)(a >> 16), bh = (int16_t)(b >> 16);
+    return (u32)(uint16_t)(al < bl ? al : bl) | ((u32)(uint16_t)(ah < bh ? ah : bh) << 16);
+}
+PLB_HD u32 vaddmin2(u32 a, u32 b, u32 c) { return vmin2(vadd2(a, b), c); }
+PLB_HD u32 prmt(u32 a, u32 b, u32 s) {
+    uint64_t v = ((uint64_t)b << 32) | a;
+    u32 r = 0;
+    for (int i = 0; i < 4; ++i) {
+        u32 n = (s >> (4 * i)) & 0xF;
+        u32 byte = (u32)((v >> (8 * (n & 7))) & 0xFF);
+        if (n & 8) byte = (byte & 0x80) ? 0xFF : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+#endif
+
+// Haplotype record for position x (8 bytes, built when a window is staged):
+//   .x = gap-open pair  open[x] | open[x+4] << 16            (reference: localgapopen, align.c:185-187)
+//   .y = PRMT selector  code(x) | 0x80 | (4+code(x+4)) << 8 | 0x8000, nibble 8 where the base is 'N'
+struct __align__(8) HapRec {
+    u32 gow;
+    u32 sel;
+};
+
+PLB_HD u32 hap_sel_nibble_lo(int code) { return code < 4 ? (u32)code : 8u; }
+PLB_HD u32 hap_sel_nibble_hi(int code) { return code < 4 ? (u32)(4 + code) : 8u; }
+PLB_HD u32 make_sel(int code_lo, int code_hi) {
+    return hap_sel_nibble_lo(code_lo) | 0x80u | (hap_sel_nibble_hi(code_hi) << 8) | 0x8000u;
+}
+// read base + quality -> profile word.  code 0..3 = A,C,G,T; anything else mismatches all.
+PLB_HD u32 make_profile(int code, u32 qual) {
+    u32 p = qual * 0x01010101u;
+    if (code < 4) p &= ~(0xFFu << (8 * code));
+    return p;
+}
+// exact byte -> code for the fast path alphabet; haplotype 'N' is the wildcard (4), every
+// other byte is 5 (never matches anything; windows whose haplotypes contain such bytes take
+// the general path, reads may contain them freely).
+PLB_HD int fast_code(uint8_t ch) {
+    return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : ch == 'N' ? 4 : 5;
+}
+
+// number of step pairs executed for a read of length L (multiple of 8, >= 24)
+PLB_HD int dp_steps(int L) {
+    int n = (L + 8 + 7) & ~7;
+    return n < 24 ? 24 : n;
+}
+constexpr int kMinFastLen = 9;   // shorter reads take the general path
+constexpr int kRecPad = 48;      // zero records appended after each haplotype
+
+struct DpState {
+    u32 ME[4], IE[4], DE[4], MIE[4];
+    u32 MO[4], IO[4], DO[4], MIO[4];
+    u32 P[8];                // profile ring, slot = row & 7
+    u32 Wg[8], Wp[8], Ws[8]; // record ring (gap-open, gap-open+nucprior, selector), slot = index & 7
+    u32 acc[4];              // running min of the last-row cells
+    u32 NM[4];               // 0 in the lane whose row is L-1, 0x7FFF elsewhere
+};
+
+// One group of 8 step pairs starting at t0 (multiple of 8).
+// FIRST: t0 == 0, applies the y = -1 boundary (free start on all 16 diagonals, align.c:244-250).
+// LAST : collects min over the band cells of row L-1 (align.c:261-288, 416-443).
+template <bool FIRST, bool LAST>
+PLB_HD void dp_group(DpState& s, const u32* __restrict__ prof, const HapRec* __restrict__ rec, int t0, int L,
+                     u32 ext2, u32 extp2, u32 nuc2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int t = t0 + j;
+        // new profile row t and record t+4 enter the rings
+        s.P[j & 7] = prof[t];
+        {
+            HapRec r = rec[t + 4];
+            s.Wg[(j + 4) & 7] = r.gow;
+            s.Wp[(j + 4) & 7] = vadd2(r.gow, nuc2);
+            s.Ws[(j + 4) & 7] = r.sel;
+        }
+        if (LAST) {
+            if (t == L - 1) s.NM[0] &= 0xFFFF0000u;
+        }
+        // ---------------- even half: cells (t+i, t-i) ----------------
+        u32 Dt[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const u32 pa = s.P[(j - k) & 7], pb = s.P[(j - k - 4) & 7];
+            const int w0 = (j + k) & 7, w1 = (j + k + 1) & 7;
+            u32 B = vmin2(s.MIE[k], s.DE[k]);                                  // B(x-1,y-1)
+            u32 sub = prmt(pa, pb, s.Ws[w0]);
+            u32 Mn = vadd2(B, sub);
+            u32 In = vaddmin2(s.IO[k], extp2, vadd2(s.MO[k], s.Wp[w0]));       // from (x, y-1), no D->I
+            Dt[k] = vaddmin2(s.DO[k], ext2, vadd2(s.MIO[k], s.Wg[w1]));        // from (x-1, y), I->D allowed
+            s.ME[k] = Mn;
+            s.IE[k] = In;
+            s.MIE[k] = vmin2(Mn, In);
+        }
+        s.DE[3] = Dt[2];
+        s.DE[2] = Dt[1];
+        s.DE[1] = Dt[0];
+        s.DE[0] = prmt(Dt[3], kInf2, 0x1054);  // lane 0 <- +inf, lane 4 <- lane 3
+        if (FIRST && j < 7) {                  // lane j+1 sits on row y = -1: B := 0, M,I := inf
+            const int k = (j + 1) & 3;
+            const u32 keep = (j + 1) < 4 ? 0xFFFF0000u : 0x0000FFFFu;
+            const u32 inf1 = (j + 1) < 4 ? 0x00007000u : 0x70000000u;
+            s.ME[k] = (s.ME[k] & keep) | inf1;
+            s.IE[k] = (s.IE[k] & keep) | inf1;
+            s.MIE[k] = (s.MIE[k] & keep) | inf1;
+            s.DE[k] = (s.DE[k] & keep);
+        }
+        if (LAST) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s.acc[k] = vmin2(s.acc[k], vmin2(s.MIE[k], s.DE[k]) | s.NM[k]);
+        }
+        // ---------------- odd half: cells (t+1+i, t-i) ----------------
+        u32 It[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const u32 pa = s.P[(j - k) & 7], pb = s.P[(j - k - 4) & 7];
+            const int w0 = (j + k) & 7, w1 = (j + k + 1) & 7;
+            u32 B = vmin2(s.MIO[k], s.DO[k]);
+            u32 sub = prmt(pa, pb, s.Ws[w1]);
+            u32 Mn = vadd2(B, sub);
+            u32 Dn = vaddmin2(s.DE[k], ext2, vadd2(s.MIE[k], s.Wg[w1]));
+            It[k] = vaddmin2(s.IE[k], extp2, vadd2(s.ME[k], s.Wp[w0]));
+            s.MO[k] = Mn;
+            s.DO[k] = Dn;
+        }
+        s.IO[0] = It[1];
+        s.IO[1] = It[2];
+        s.IO[2] = It[3];
+        s.IO[3] = prmt(It[0], kInf2, 0x7632);  // lane 3 <- lane 4, lane 7 <- +inf
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s.MIO[k] = vmin2(s.MO[k], s.IO[k]);
+        if (FIRST && j < 7) {                  // row y = -1, even x: M := 0 (align.c:244-250), I := inf
+            const int k = (j + 1) & 3;
+            const u32 keep = (j + 1) < 4 ? 0xFFFF0000u : 0x0000FFFFu;
+            const u32 inf1 = (j + 1) < 4 ? 0x00007000u : 0x70000000u;
+            s.MO[k] = (s.MO[k] & keep);
+            s.IO[k] = (s.IO[k] & keep) | inf1;
+            s.MIO[k] = (s.MIO[k] & keep) | inf1;
+            s.DO[k] = (s.DO[k] & keep);
+        }
+        if (LAST) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s.acc[k] = vmin2(s.acc[k], vmin2(s.MIO[k], s.DO[k]) | s.NM[k]);
+            // hot lane moves up by one for the next step pair
+            u32 n3 = s.NM[3];
+            s.NM[3] = s.NM[2];
+            s.NM[2] = s.NM[1];
+            s.NM[1] = s.NM[0];
+            s.NM[0] = prmt(n3, 0x7FFF7FFFu, 0x1054);
+        }
+    }
+}
+
+// prof : profile words of the read, rows 0..L-1, zero-padded to dp_steps(L) rows
+// rec  : haplotype records, rec[0] is segment position x = 0; must be readable up to
+//        index dp_steps(L)+4 (zero padding past the haplotype end)
+// Requires L >= kMinFastLen.  Returns the alignment score in phred units.
+PLB_HD int band_dp_fast(const u32* __restrict__ prof, const HapRec* __restrict__ rec, int L, int ext, int nuc) {
+    DpState s;
+    const u32 ext2 = (u32)ext * 0x00010001u;
+    const u32 nuc2 = (u32)nuc * 0x00010001u;
+    const u32 extp2 = (u32)(ext + nuc) * 0x00010001u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        s.ME[k] = s.IE[k] = s.DE[k] = s.MIE[k] = kInf2;
+        s.MO[k] = s.IO[k] = s.DO[k] = s.MIO[k] = kInf2;
+        s.acc[k] = 0x7FFF7FFFu;
+        s.NM[k] = 0x7FFF7FFFu;
+    }
+    // "step -1": lane 0 of both vectors sits on row y = -1
+    s.DE[0] = 0x70000000u;   // even lane 0: D := 0 so that B = 0, M = I = inf
+    s.MO[0] = 0x70000000u;   // odd lane 0 (x = 0, even): M := 0
+    s.DO[0] = 0x70000000u;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) s.P[m] = 0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        HapRec r = rec[m];
+        s.Wg[m] = r.gow;
+        s.Wp[m] = vadd2(r.gow, nuc2);
+        s.Ws[m] = r.sel;
+    }
+#pragma unroll
+    for (int m = 4; m < 8; ++m) s.Wg[m] = s.Wp[m] = s.Ws[m] = 0;
+
+    const int n = dp_steps(L);
+    dp_group<true, false>(s, prof, rec, 0, L, ext2, extp2, nuc2);
+    int t0 = 8;
+    for (; t0 < n - 16; t0 += 8) dp_group<false, false>(s, prof, rec, t0, L, ext2, extp2, nuc2);
+    dp_group<false, true>(s, prof, rec, t0, L, ext2, extp2, nuc2);
+    dp_group<false, true>(s, prof, rec, t0 + 8, L, ext2, extp2, nuc2);
+    u32 a = vmin2(vmin2(s.acc[0], s.acc[1]), vmin2(s.acc[2], s.acc[3]));
+    int lo = (int)(a & 0xFFFF), hi = (int)(a >> 16);
+    return lo < hi ? lo : hi;
+}
+
+// General path: arbitrary bytes, any read length >= 1.  Same recurrence cell by cell
+// (SURVEY §3.3), 32-bit scalars.  hap/open point at segment position 0.
+PLB_HD int band_dp_general(const uint8_t* __restrict__ hap, const uint8_t* __restrict__ open,
+                           const uint8_t* __restrict__ read, const uint8_t* __restrict__ qual, int L, int ext,
+                           int nuc) {
+    int Mp[16], Ip[16], Dp[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) Mp[d] = Ip[d] = Dp[d] = kScoreBig;
+    for (int y = 0; y < L; ++y) {
+        const int rb = read[y], q = qual[y];
+        int Mc[16], Ic[16], Dc[16];
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+            const int x = y + d;
+            const int hb = hap[x], go = open[x];
+            const int sub = (hb == 'N' || hb == rb) ? 0 : q;
+            int diag = Mp[d] < Ip[d] ? Mp[d] : Ip[d];
+            diag = diag < Dp[d] ? diag : Dp[d];
+            if (y == 0) diag = 0;
+            int m = diag + sub;
+            int ins;
+            if (y == 0) {
+                ins = (x & 1) ? kScoreBig : go + nuc;
+            } else if (d < 15) {
+                int a = Ip[d + 1] + ext, b = Mp[d + 1] + go;
+                ins = (a < b ? a : b) + nuc;
+            } else {
+                ins = kScoreBig;
+            }
+            int del;
+            if (d >= 1) {
+                int mi = Mc[d - 1] < Ic[d - 1] ? Mc[d - 1] : Ic[d - 1];
+                int a = Dc[d - 1] + ext, b = mi + go;
+                del = a < b ? a : b;
+            } else {
+                del = kScoreBig;
+            }
+            Mc[d] = m < kScoreBig ? m : kScoreBig;
+            Ic[d] = ins < kScoreBig ? ins : kScoreBig;
+            Dc[d] = del < kScoreBig ? del : kScoreBig;
+        }
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+            Mp[d] = Mc[d];
+            Ip[d] = Ic[d];
+            Dp[d] = Dc[d];
+        }
+    }
+    int best = kScoreBig;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+        int b = Mp[d] < Ip[d] ? Mp[d] : Ip[d];
+        b = b < Dp[d] ? b : Dp[d];
+        best = best < b ? best : b;
+    }
+    return best;
+}
+
+}  // namespace plb

@@ -1,0 +1,893 @@
+// plb_kernels.cuh — sm_100a kernels of the read-vs-haplotype likelihood path.
+//
+//   k_anchor   : per tile (window x slot range x haplotype group): gap-open table, 7-mer index of
+//                each haplotype in shared memory, per (read, haplotype) anchor voting, candidate
+//                start offsets                     (reference: src/cython/calign.pyx:94-124, 155-165,
+//                                                   170-272; src/cython/chaplotype.pyx:552-590)
+//   k_general  : band alignments that cannot use the packed path (non-ACGTN haplotype bytes, reads
+//                shorter than 9, third and later tied candidates)      (src/c/align.c:77-521)
+//   k_dp       : per tile: stage read profiles + haplotype records in shared memory, run one packed
+//                band alignment per thread, min per pair, score -> log-likelihood
+//                                                  (src/c/align.c:77-521, chaplotype.pyx:306-377, 594-676)
+//   k_genotype : per (window, individual): genotype log-likelihoods, goodness of fit, rescale
+//                                                  (src/cython/cgenotype.pyx:131-189, cpopulation.pyx:283-309)
+//   k_population: per window: EM over haplotype frequencies, genotype calls, variant posteriors
+//                                                  (src/cython/cpopulation.pyx:384-457, 459-594, 623-720)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "plb_dp.cuh"
+
+namespace plb {
+
+constexpr int kKmer = 7;
+constexpr int kHashSize = 16384;
+constexpr int kScoreNone = 1000000;
+constexpr double kMLTOT = -0.23025850929940459;
+constexpr double kLog10E = 0.43429448190325182;
+constexpr double kLogHalf = -0.69314718055994529;
+constexpr u32 kTabEmpty = 0xFFFFFFFFu;
+
+// ---- device view of a batch (all pointers are device pointers) --------------------------------
+struct DevBatch {
+    int32_t n_windows, n_individuals, n_haps, n_reads;
+    int64_t n_slots, n_pairs;
+    const int32_t* win_hap_off;
+    const int32_t* win_start;
+    const int32_t* win_end;
+    const int32_t* hap_start;
+    const int64_t* hap_seq_off;
+    const uint8_t* hap_seq;
+    const int64_t* wi_slot_off;
+    const int32_t* wi_n_good;
+    const int32_t* wi_n_bad;
+    const int32_t* slot_read;
+    const int64_t* read_seq_off;
+    const uint8_t* read_seq;
+    const uint8_t* read_qual;
+    const int32_t* read_pos;
+    const int32_t* read_end;
+    const uint8_t* read_mapq;
+    const uint8_t* read_qcfail;
+    int32_t max_variants;
+    const int32_t* win_n_var;
+    const uint64_t* hap_var_mask;
+    const double* var_prior;
+    // derived at upload
+    const int32_t* slot_wi;    // [n_slots] index w*nInd+i of each slot
+    const int32_t* hap_win;    // [n_haps] window of each haplotype
+    const int64_t* ll_off;     // [n_windows*nInd+1]
+    // scratch
+    uint8_t* gap_open;         // haplotype h: hapLen+1 entries at hap_seq_off[h] + h
+    uint8_t* win_general;      // [n_windows] 1 = haplotypes contain bytes outside ACGTN
+    int32_t* cand0;            // [n_pairs] first / second packed-path start offset, -1 = none
+    int32_t* cand1;
+    int32_t* score;            // [n_pairs] running min over general-path alignments
+};
+
+struct Tile {
+    int32_t w;        // window
+    int32_t h0, h1;   // haplotype range (global indices)
+    int64_t s0, s1;   // slot range (global indices)
+};
+
+struct QueueEntry {
+    int64_t pair;
+    int32_t hap;
+    int32_t slot;
+    int32_t start;
+    int32_t pad;
+};
+
+struct Queue {
+    QueueEntry* e;
+    int32_t* count;
+    int32_t cap;
+};
+
+struct Counters {  // device-side statistics
+    unsigned long long n_pairs, n_scored, n_dp, cells;
+};
+
+struct ScoreParams {
+    int32_t ext, nuc;
+};
+
+__device__ __forceinline__ u32 base_code(uint8_t ch) {  // calign.pyx:61-90
+    u32 c = ch & 7u;
+    if (c == 7u) c = 2u;
+    return c & 3u;
+}
+
+__device__ __forceinline__ u32 kmer_hash(const uint8_t* p) {
+    u32 h = 0;
+#pragma unroll
+    for (int i = 0; i < kKmer; ++i) h = (h << 2) + base_code(p[i]);
+    return h;
+}
+
+// homopolymer gap-open table evaluated from chaplotype.pyx:64-67 (see oracle for the formula)
+__constant__ uint8_t c_homopol_q[49] = {45, 42, 41, 39, 37, 32, 28, 23, 20, 19, 17, 16, 15, 14, 13, 12, 11,
+                                        11, 10, 9,  9,  8,  8,  7,  7,  7,  6,  6,  6,  5,  5,  5,  4,  4,
+                                        4,  3,  3,  3,  3,  2,  2,  2,  2,  2,  1,  1,  1,  1,  1};
+
+// Gap-open penalty of position i (chaplotype.pyx:552-590).  The reference scans right to left
+// carrying a run length; equivalently run(i) = number of consecutive positions j > i with
+// hap[j] == hap[i], stopping at 'N' (an 'N' never continues a run) and saturating at 48.
+__device__ __forceinline__ uint8_t gap_open_at(const uint8_t* hap, int hap_len, int i) {
+    const uint8_t c = hap[i];
+    int run = 0;
+    if (c != 'N') {
+        // position i extends the run of i+1 iff hap[i] == hap[i+1] (and that base is not 'N')
+        while (run < 48 && i + run + 1 < hap_len && hap[i + run + 1] == c) ++run;
+    }
+    return c_homopol_q[run];
+}
+
+__device__ __forceinline__ u32 tab_slot0(u32 key, int bits) {
+    return bits >= 14 ? key : ((key * 0x9E3779B1u) >> (32 - bits));
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_prep: one block per haplotype.  Gap-open table (chaplotype.pyx:552-590) into global scratch and
+// the per-window "general path" flag (haplotype bytes outside ACGTN need exact byte compares).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_prep(DevBatch b) {
+    const int h = blockIdx.x;
+    const int len = (int)(b.hap_seq_off[h + 1] - b.hap_seq_off[h]);
+    const uint8_t* hap = b.hap_seq + b.hap_seq_off[h];
+    uint8_t* go = b.gap_open + b.hap_seq_off[h] + h;
+    int bad = 0;
+    for (int i = threadIdx.x; i <= len; i += blockDim.x) {
+        if (i < len) {
+            go[i] = gap_open_at(hap, len, i);
+            bad |= (fast_code(hap[i]) == 5);
+        } else {
+            go[i] = 0;
+        }
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) b.win_general[b.hap_win[h]] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_anchor
+// ---------------------------------------------------------------------------------------------
+struct AnchorPlan {
+    const Tile* tiles;
+    int32_t n_tiles;
+    int32_t max_slots;      // slots per tile upper bound
+    int32_t max_group;      // haplotypes per tile upper bound
+    int32_t tab_words;      // smem u32 words for all tables of a group
+    int32_t next_halfs;     // smem u16 entries for all next arrays of a group
+    int32_t rhash_halfs;    // smem u16 entries for read hashes of a tile
+    int32_t cnt_stride;     // count-array entries per thread (max hapLen + readLen, rounded to 16)
+    int32_t cnt_in_smem;    // 1: count arrays live in shared memory, 0: in cnt_global
+    uint8_t* cnt_global;    // [gridDim.x * blockDim.x * cnt_stride * sizeof(CntT)]
+};
+
+struct SlotInfo {
+    int32_t read;     // read pool index
+    int32_t len;      // read length
+    int32_t pos;      // read.pos
+    int32_t hoff;     // offset into the rhash area
+    int32_t flags;    // bit0 = LL forced to 0 (QC fail / overlap < 7)
+};
+
+__device__ __forceinline__ int read_overlap(int ws, int we, int rp, int re) {  // chaplotype.pyx:103-115
+    int s = ws > rp ? ws : rp;
+    int e = we < re ? we : re;
+    return e > s ? e - s : -1;
+}
+
+constexpr int kAnchorThreads = 128;
+
+template <typename CntT>
+__global__ void __launch_bounds__(kAnchorThreads) k_anchor(DevBatch b, AnchorPlan plan, Queue q, ScoreParams sp,
+                                                           Counters* ctr) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    // carve shared memory
+    u32* s_tab = (u32*)smem;
+    uint16_t* s_next = (uint16_t*)(s_tab + plan.tab_words);
+    uint16_t* s_rhash = s_next + plan.next_halfs;
+    SlotInfo* s_slot = (SlotInfo*)(((uintptr_t)(s_rhash + plan.rhash_halfs) + 15) & ~(uintptr_t)15);
+    int32_t* s_hmeta = (int32_t*)(s_slot + plan.max_slots);  // per hap: len, tab off, bits, next off
+    CntT* s_cnt = (CntT*)(((uintptr_t)(s_hmeta + 4 * plan.max_group) + 15) & ~(uintptr_t)15);
+
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    CntT* my_cnt = plan.cnt_in_smem
+                       ? s_cnt + (size_t)tid * plan.cnt_stride
+                       : (CntT*)plan.cnt_global + ((size_t)blockIdx.x * nthr + tid) * plan.cnt_stride;
+
+    unsigned long long st_pairs = 0, st_scored = 0, st_dp = 0, st_cells = 0;
+
+    for (int ti = blockIdx.x; ti < plan.n_tiles; ti += gridDim.x) {
+        const Tile tile = plan.tiles[ti];
+        const int w = tile.w;
+        const int nh = tile.h1 - tile.h0;
+        const int ns = (int)(tile.s1 - tile.s0);
+        __syncthreads();
+        if (tid == 0) {
+            int toff = 0, noff = 0;
+            for (int g = 0; g < nh; ++g) {
+                const int h = tile.h0 + g;
+                const int len = (int)(b.hap_seq_off[h + 1] - b.hap_seq_off[h]);
+                int nk = len - kKmer;
+                if (nk < 1) nk = 1;
+                int bits = 6;
+                while ((1 << bits) < 2 * nk && bits < 14) ++bits;
+                s_hmeta[4 * g + 0] = len;
+                s_hmeta[4 * g + 1] = toff;
+                s_hmeta[4 * g + 2] = bits;
+                s_hmeta[4 * g + 3] = noff;
+                toff += 1 << bits;
+                noff += (len + 2) & ~1;
+            }
+        }
+        // slot metadata + skip rule (chaplotype.pyx:343-361)
+        for (int s = tid; s < ns; s += nthr) {
+            const int64_t gs = tile.s0 + s;
+            const int r = b.slot_read[gs];
+            const int wi = b.slot_wi[gs];
+            const int t = (int)(gs - b.wi_slot_off[wi]);
+            SlotInfo si;
+            si.read = r;
+            si.len = (int)(b.read_seq_off[r + 1] - b.read_seq_off[r]);
+            si.pos = b.read_pos[r];
+            si.flags = 0;
+            if (t < b.wi_n_good[wi] + b.wi_n_bad[wi]) {
+                const int ov = read_overlap(b.win_start[w], b.win_end[w], si.pos, b.read_end[r]);
+                if (b.read_qcfail[r] || ov < kKmer) si.flags = 1;
+            }
+            si.hoff = 0;
+            s_slot[s] = si;
+        }
+        __syncthreads();
+        if (tid == 0) {  // exclusive scan of hash-area offsets (tiles hold at most a few hundred slots)
+            int o = 0;
+            for (int s = 0; s < ns; ++s) {
+                s_slot[s].hoff = o;
+                int nk = s_slot[s].len - kKmer;
+                o += (nk > 0 && !(s_slot[s].flags & 1)) ? nk : 0;
+            }
+        }
+        // clear tables
+        for (int g = 0; g < nh; ++g) {
+            u32* tab = s_tab + s_hmeta[4 * g + 1];
+            const int S = 1 << s_hmeta[4 * g + 2];
+            for (int i = tid; i < S; i += nthr) tab[i] = kTabEmpty;
+        }
+        __syncthreads();
+        // 7-mer index of each haplotype (calign.pyx:94-124: positions 0..len-8).  Open addressing on
+        // the 14-bit hash; equal hashes are chained through s_next.  Vote counts do not depend on
+        // the order inside a chain, so lock-free insertion order is fine.
+        for (int g = 0; g < nh; ++g) {
+            const int h = tile.h0 + g;
+            const int len = s_hmeta[4 * g + 0];
+            const uint8_t* hap = b.hap_seq + b.hap_seq_off[h];
+            u32* tab = s_tab + s_hmeta[4 * g + 1];
+            const int bits = s_hmeta[4 * g + 2];
+            const u32 mask = (1u << bits) - 1;
+            uint16_t* nxt = s_next + s_hmeta[4 * g + 3];
+            for (int i = tid; i < len - kKmer; i += nthr) {
+                const u32 key = kmer_hash(hap + i);
+                u32 slot = tab_slot0(key, bits) & mask;
+                while (true) {
+                    u32 old = atomicCAS(&tab[slot], kTabEmpty, key << 16);
+                    if (old == kTabEmpty || (old >> 16) == key) break;
+                    slot = (slot + 1) & mask;
+                }
+                u32 cur = ((volatile u32*)tab)[slot];
+                while (true) {  // push position i (stored as i+1) on the chain of this key
+                    nxt[i + 1] = (uint16_t)(cur & 0xFFFFu);
+                    u32 old = atomicCAS(&tab[slot], cur, (key << 16) | (u32)(i + 1));
+                    if (old == cur) break;
+                    cur = old;
+                }
+            }
+        }
+        // read 7-mer hashes (calign.pyx:155-165: k-mers 0..len-8)
+        for (int s = 0; s < ns; ++s) {
+            const SlotInfo si = s_slot[s];
+            if (si.flags & 1) continue;
+            const uint8_t* rs = b.read_seq + b.read_seq_off[si.read];
+            for (int i = tid; i < si.len - kKmer; i += nthr) s_rhash[si.hoff + i] = (uint16_t)kmer_hash(rs + i);
+        }
+        __syncthreads();
+        const int general = b.win_general[w];
+
+        // ---- per (slot, haplotype) pair: vote, pick candidates (calign.pyx:206-267) ----
+        const int npairs = ns * nh;
+        for (int p = tid; p < npairs; p += nthr) {
+            const int s = p % ns, g = p / ns;
+            const SlotInfo si = s_slot[s];
+            const int h = tile.h0 + g;
+            const int64_t gs = tile.s0 + s;
+            const int wi = b.slot_wi[gs];
+            const int64_t T = b.wi_slot_off[wi + 1] - b.wi_slot_off[wi];
+            const int64_t pair = b.ll_off[wi] + (int64_t)(h - b.win_hap_off[w]) * T + (gs - b.wi_slot_off[wi]);
+            ++st_pairs;
+            int c0 = -1, c1 = -1, sc = kScoreNone;
+            if (si.flags & 1) {
+                sc = -1;
+            } else if (si.len < kKmer) {
+                sc = 0;  // calign.pyx:182-183
+                ++st_scored;
+                st_cells += 16ull * si.len;
+            } else {
+                ++st_scored;
+                st_cells += 16ull * si.len;
+                const int L = si.len;
+                const int hap_len = s_hmeta[4 * g + 0];
+                const u32* tab = s_tab + s_hmeta[4 * g + 1];
+                const int bits = s_hmeta[4 * g + 2];
+                const u32 mask = (1u << bits) - 1;
+                const uint16_t* nxt = s_next + s_hmeta[4 * g + 3];
+                const uint16_t* rh = s_rhash + si.hoff;
+                const int C = hap_len + L;
+                {  // clear the vote array (memset, calign.pyx:206)
+                    uint4* c4 = (uint4*)my_cnt;
+                    const int n16 = (C * (int)sizeof(CntT) + 15) >> 4;
+                    for (int i = 0; i < n16; ++i) c4[i] = make_uint4(0, 0, 0, 0);
+                }
+                int maxc = 0, ntie = 0, besto = -1;
+                for (int i = 0; i < L - kKmer; ++i) {
+                    const u32 key = rh[i];
+                    u32 slot = tab_slot0(key, bits) & mask;
+                    u32 e = tab[slot];
+                    while (e != kTabEmpty && (e >> 16) != key) {
+                        slot = (slot + 1) & mask;
+                        e = tab[slot];
+                    }
+                    if (e == kTabEmpty) continue;
+                    u32 p1 = e & 0xFFFFu;
+                    while (p1) {
+                        const int o = (int)p1 - i - 1 + L;  // index pos + readLen, calign.pyx:213-215
+                        const int c = (int)my_cnt[o] + 1;
+                        my_cnt[o] = (CntT)c;
+                        if (c > maxc) {
+                            maxc = c;
+                            ntie = 1;
+                            besto = o;
+                        } else if (c == maxc) {
+                            ++ntie;
+                        }
+                        p1 = nxt[p1];
+                    }
+                }
+                // fallback position (calign.pyx:252-256)
+                int idx0 = si.pos - b.hap_start[w];
+                const int lim = hap_len - L - 15;
+                if (lim < idx0) idx0 = lim;
+                // distinct band start offsets: accepted tied-best candidates + the fallback.  The
+                // reference's result is the min over exactly this set (its early exit on score 0 and
+                // its "skip the fallback if it equals the best candidate" rule do not change a min).
+                bool any_accepted = false;
+                const bool slow = general || L < kMinFastLen;
+                auto emit = [&](int start) {
+                    if (start == c0 || start == c1) return;
+                    ++st_dp;
+                    if (!slow && c0 < 0) {
+                        c0 = start;
+                    } else if (!slow && c1 < 0) {
+                        c1 = start;
+                    } else {
+                        // general path: queue it, or run it right here when the queue is full
+                        const int qi = atomicAdd(q.count, 1);
+                        if (qi < q.cap) {
+                            QueueEntry qe;
+                            qe.pair = pair;
+                            qe.hap = h;
+                            qe.slot = (int32_t)gs;
+                            qe.start = start;
+                            qe.pad = 0;
+                            q.e[qi] = qe;
+                        } else {
+                            const uint8_t* hapg = b.hap_seq + b.hap_seq_off[h];
+                            const uint8_t* go = b.gap_open + b.hap_seq_off[h] + h;
+                            const int v = band_dp_general(hapg + start, go + start,
+                                                          b.read_seq + b.read_seq_off[si.read],
+                                                          b.read_qual + b.read_seq_off[si.read], L, sp.ext, sp.nuc);
+                            sc = v < sc ? v : sc;
+                        }
+                    }
+                };
+                if (maxc > 0) {
+                    if (ntie == 1) {
+                        const int idx = besto - L;
+                        if (idx + L + 15 < hap_len) {
+                            any_accepted = true;
+                            emit(idx > 8 ? idx - 8 : 0);
+                        }
+                    } else {
+                        for (int i = 0; i < C; ++i) {
+                            if ((int)my_cnt[i] != maxc) continue;
+                            const int idx = i - L;
+                            if (idx + L + 15 < hap_len) {
+                                any_accepted = true;
+                                emit(idx > 8 ? idx - 8 : 0);
+                            }
+                        }
+                    }
+                }
+                // with no accepted candidate bestMappingPosition stays -1, so a fallback index of
+                // exactly -1 is skipped and the sentinel 1000000 is returned (calign.pyx:258, 272)
+                if (any_accepted || idx0 != -1) emit(idx0 > 8 ? idx0 - 8 : 0);
+            }
+            b.cand0[pair] = c0;
+            b.cand1[pair] = c1;
+            b.score[pair] = sc;
+        }
+    }
+    if (ctr) {  // statistics
+        for (int o = 16; o > 0; o >>= 1) {
+            st_pairs += __shfl_down_sync(0xFFFFFFFFu, st_pairs, o);
+            st_scored += __shfl_down_sync(0xFFFFFFFFu, st_scored, o);
+            st_dp += __shfl_down_sync(0xFFFFFFFFu, st_dp, o);
+            st_cells += __shfl_down_sync(0xFFFFFFFFu, st_cells, o);
+        }
+        if ((tid & 31) == 0) {
+            atomicAdd(&ctr->n_pairs, st_pairs);
+            atomicAdd(&ctr->n_scored, st_scored);
+            atomicAdd(&ctr->n_dp, st_dp);
+            atomicAdd(&ctr->cells, st_cells);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_general: queued alignments on the scalar path
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_general(DevBatch b, Queue q, ScoreParams sp) {
+    int n = *q.count;
+    if (n > q.cap) n = q.cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const QueueEntry qe = q.e[i];
+        const int r = b.slot_read[qe.slot];
+        const int L = (int)(b.read_seq_off[r + 1] - b.read_seq_off[r]);
+        const uint8_t* hap = b.hap_seq + b.hap_seq_off[qe.hap];
+        const uint8_t* go = b.gap_open + b.hap_seq_off[qe.hap] + qe.hap;
+        const int v = band_dp_general(hap + qe.start, go + qe.start, b.read_seq + b.read_seq_off[r],
+                                      b.read_qual + b.read_seq_off[r], L, sp.ext, sp.nuc);
+        atomicMin(&b.score[qe.pair], v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_dp
+// ---------------------------------------------------------------------------------------------
+struct DpPlan {
+    const Tile* tiles;
+    int32_t n_tiles;
+    int32_t max_slots;
+    int32_t max_group;
+    int32_t prof_words;   // smem u32 words for all profile rows of a tile
+    int32_t rec_count;    // smem HapRec entries for a haplotype group
+    int32_t max_pairs;    // max slots*group per tile
+};
+
+struct DpSlot {
+    int32_t read;
+    int32_t len;
+    int32_t poff;    // offset of the profile row (u32 words)
+    int32_t flags;
+    double ll_right; // log(1 - exp(mLTOT*mapq)), chaplotype.pyx:622
+};
+
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParams sp, double* __restrict__ ll_out,
+                                             int32_t* __restrict__ score_out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    u32* s_prof = (u32*)smem;
+    HapRec* s_rec = (HapRec*)(s_prof + plan.prof_words);
+    DpSlot* s_slot = (DpSlot*)(s_rec + plan.rec_count);
+    int32_t* s_roff = (int32_t*)(s_slot + plan.max_slots);       // per hap: record offset
+    int32_t* s_best = s_roff + plan.max_group;                   // per pair: best score
+    u32* s_task = (u32*)(s_best + plan.max_pairs);               // compacted tasks
+    __shared__ int s_ntask;
+
+    const int tid = threadIdx.x;
+    for (int ti = blockIdx.x; ti < plan.n_tiles; ti += gridDim.x) {
+        const Tile tile = plan.tiles[ti];
+        const int w = tile.w;
+        const int nh = tile.h1 - tile.h0;
+        const int ns = (int)(tile.s1 - tile.s0);
+        __syncthreads();
+        if (tid == 0) {
+            s_ntask = 0;
+            int ro = 0;
+            for (int g = 0; g < nh; ++g) {
+                const int h = tile.h0 + g;
+                s_roff[g] = ro;
+                ro += (int)(b.hap_seq_off[h + 1] - b.hap_seq_off[h]) + kRecPad;
+            }
+        }
+        for (int s = tid; s < ns; s += NTHR) {
+            const int64_t gs = tile.s0 + s;
+            const int r = b.slot_read[gs];
+            const int wi = b.slot_wi[gs];
+            const int t = (int)(gs - b.wi_slot_off[wi]);
+            DpSlot ds;
+            ds.read = r;
+            ds.len = (int)(b.read_seq_off[r + 1] - b.read_seq_off[r]);
+            ds.flags = 0;
+            if (t < b.wi_n_good[wi] + b.wi_n_bad[wi]) {
+                const int ov = read_overlap(b.win_start[w], b.win_end[w], b.read_pos[r], b.read_end[r]);
+                if (b.read_qcfail[r] || ov < kKmer) ds.flags = 1;
+            }
+            ds.ll_right = log(1.0 - exp(kMLTOT * (double)b.read_mapq[r]));
+            ds.poff = 0;
+            s_slot[s] = ds;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int o = 0;
+            for (int s = 0; s < ns; ++s) {
+                s_slot[s].poff = o;
+                const int L = s_slot[s].len;
+                if (!(s_slot[s].flags & 1) && L >= kMinFastLen) {
+                    int n = dp_steps(L) + 4;           // rows read by the kernel, +4 keeps rows 16-byte apart
+                    n = (n + 3) & ~3;
+                    if (!((n >> 2) & 1)) n += 4;       // odd multiple of 16 bytes: conflict-free LDS.128
+                    o += n;
+                }
+            }
+        }
+        __syncthreads();
+        const int general = b.win_general[w];
+        // profiles: one warp per read row, lanes along the read (coalesced byte loads)
+        if (!general) {
+            const int warp = tid >> 5, lane = tid & 31, nwarp = NTHR >> 5;
+            for (int s = warp; s < ns; s += nwarp) {
+                const DpSlot ds = s_slot[s];
+                if ((ds.flags & 1) || ds.len < kMinFastLen) continue;
+                const uint8_t* rs = b.read_seq + b.read_seq_off[ds.read];
+                const uint8_t* rq = b.read_qual + b.read_seq_off[ds.read];
+                int n = dp_steps(ds.len) + 4;
+                u32* row = s_prof + ds.poff;
+                for (int y = lane; y < n; y += 32)
+                    row[y] = y < ds.len ? make_profile(fast_code(rs[y]), rq[y]) : 0u;
+            }
+            // haplotype records
+            for (int g = 0; g < nh; ++g) {
+                const int h = tile.h0 + g;
+                const int len = (int)(b.hap_seq_off[h + 1] - b.hap_seq_off[h]);
+                const uint8_t* hap = b.hap_seq + b.hap_seq_off[h];
+                const uint8_t* go = b.gap_open + b.hap_seq_off[h] + h;
+                HapRec* rec = s_rec + s_roff[g];
+                for (int x = tid; x < len + kRecPad; x += NTHR) {
+                    const int ca = x < len ? fast_code(hap[x]) : 4;
+                    const int cb = x + 4 < len ? fast_code(hap[x + 4]) : 4;
+                    const u32 oa = x <= len ? go[x] : 0u;
+                    const u32 ob = x + 4 <= len ? go[x + 4] : 0u;
+                    HapRec r;
+                    r.gow = oa | (ob << 16);
+                    r.sel = make_sel(ca, cb);
+                    rec[x] = r;
+                }
+            }
+        }
+        // best scores start from what the general path produced; compact packed-path tasks
+        const int npairs = ns * nh;
+        for (int p0 = 0; p0 < npairs; p0 += NTHR) {
+            const int p = p0 + tid;
+            int c0 = -1, c1 = -1;
+            if (p < npairs) {
+                const int s = p % ns, g = p / ns;
+                const int64_t gs = tile.s0 + s;
+                const int wi = b.slot_wi[gs];
+                const int64_t T = b.wi_slot_off[wi + 1] - b.wi_slot_off[wi];
+                const int64_t pair =
+                    b.ll_off[wi] + (int64_t)(tile.h0 + g - b.win_hap_off[w]) * T + (gs - b.wi_slot_off[wi]);
+                s_best[p] = b.score[pair];
+                c0 = b.cand0[pair];
+                c1 = b.cand1[pair];
+            }
+            const int cnt = (c0 >= 0) + (c1 >= 0);
+            // block-wide exclusive scan via warp ballots would need two levels; an atomic per
+            // warp keeps it simple (order of tasks inside a tile does not affect the result)
+            const unsigned lane = tid & 31;
+            int incl = cnt;
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if ((int)lane >= o) incl += v;
+            }
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&s_ntask, incl);
+            base = __shfl_sync(0xFFFFFFFFu, base, 31);
+            int pos = base + incl - cnt;
+            if (c0 >= 0) s_task[pos++] = ((u32)p << 15) | (u32)c0;
+            if (c1 >= 0) s_task[pos++] = ((u32)p << 15) | (u32)c1;
+        }
+        __syncthreads();
+        const int ntask = s_ntask;
+        for (int k = tid; k < ntask; k += NTHR) {
+            const u32 tk = s_task[k];
+            const int p = (int)(tk >> 15), start = (int)(tk & 0x7FFFu);
+            const int s = p % ns, g = p / ns;
+            const DpSlot ds = s_slot[s];
+            const int v = band_dp_fast(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc);
+            atomicMin(&s_best[p], v);
+        }
+        __syncthreads();
+        // score -> log-likelihood (chaplotype.pyx:675-676) and output
+        for (int p = tid; p < npairs; p += NTHR) {
+            const int s = p % ns, g = p / ns;
+            const DpSlot ds = s_slot[s];
+            const int64_t gs = tile.s0 + s;
+            const int wi = b.slot_wi[gs];
+            const int64_t T = b.wi_slot_off[wi + 1] - b.wi_slot_off[wi];
+            const int64_t pair =
+                b.ll_off[wi] + (int64_t)(tile.h0 + g - b.win_hap_off[w]) * T + (gs - b.wi_slot_off[wi]);
+            const int sc = s_best[p];
+            double ll;
+            if (ds.flags & 1) {
+                ll = 0.0;
+            } else {
+                const double v = kMLTOT * (double)sc + ds.ll_right;
+                ll = v > -300.0 ? v : -300.0;
+            }
+            if (ll_out) ll_out[pair] = ll;
+            if (score_out) score_out[pair] = sc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_genotype: one block per (window, individual)
+// ---------------------------------------------------------------------------------------------
+struct PopOut {
+    int32_t max_haps;
+    double* gl;
+    double* gl_log_max;
+    double* gof;
+    double* hap_like;
+    double* freq;
+    double* em_post;
+    int32_t* call;
+    double* var_phred;
+    int32_t* em_iters;
+};
+
+__device__ __forceinline__ void genotype_pair(int g, int H, int& h1, int& h2) {
+    int i = 0, rem = g;  // order of cgenotype.pyx:193-218: (0,0),(0,1)..(0,H-1),(1,1)..
+    while (rem >= H - i) {
+        rem -= H - i;
+        ++i;
+    }
+    h1 = i;
+    h2 = i + rem;
+}
+
+__global__ void __launch_bounds__(64) k_genotype(DevBatch b, const double* __restrict__ ll, PopOut out) {
+    const int wi = blockIdx.x;
+    const int nInd = b.n_individuals;
+    const int w = wi / nInd, i = wi % nInd;
+    const int H = b.win_hap_off[w + 1] - b.win_hap_off[w];
+    const int G = H * (H + 1) / 2;
+    const int Hmax = out.max_haps, Gmax = Hmax * (Hmax + 1) / 2;
+    const int T = (int)(b.wi_slot_off[wi + 1] - b.wi_slot_off[wi]);
+    const int ngood = b.wi_n_good[wi];
+    const double* L = ll + b.ll_off[wi];
+    double* gl = out.gl + ((size_t)w * nInd + i) * Gmax;
+    __shared__ double s_max[64];
+    const int tid = threadIdx.x;
+
+    double mymax = -1e7;  // cpopulation.pyx:288
+    for (int g = tid; g < G; g += 64) {
+        int h1, h2;
+        genotype_pair(g, H, h1, h2);
+        double v = 1.0, gof = 0.0;
+        if (ngood != 0) {
+            const double* a1 = L + (size_t)h1 * T;
+            const double* a2 = L + (size_t)h2 * T;
+            double like = 0.0, gsum = 0.0;
+            const bool hom = (h1 == h2);
+            for (int t = 0; t < T; ++t) {  // cgenotype.pyx:151-180
+                const double a = a1[t], c = a2[t];
+                const double la = kLog10E * a, lc = kLog10E * c;
+                gsum += la > lc ? la : lc;
+                if (hom) {
+                    like += a;
+                } else if (fabs(a - c) >= 3) {
+                    like += (kLogHalf + (a > c ? a : c));
+                } else if (fabs(a - c) <= 1e-3) {
+                    like += a;
+                } else {
+                    like += log(0.5 * (exp(a) + exp(c)));
+                }
+            }
+            v = like;
+            gof = (-10 * gsum) / ngood;  // cgenotype.pyx:182-183
+            if (v > mymax) mymax = v;
+        }
+        gl[g] = v;
+        if (out.gof) out.gof[((size_t)w * Gmax + g) * nInd + i] = gof;
+    }
+    for (int g = G + tid; g < Gmax; g += 64) {
+        gl[g] = 0.0;
+        if (out.gof) out.gof[((size_t)w * Gmax + g) * nInd + i] = 0.0;
+    }
+    if (out.hap_like) {
+        for (int h = tid; h < Hmax; h += 64) {
+            double sum = 0.0;
+            if (h < H)
+                for (int t = 0; t < T; ++t) sum += kLog10E * L[(size_t)h * T + t];
+            out.hap_like[((size_t)w * nInd + i) * Hmax + h] = sum;
+        }
+    }
+    s_max[tid] = mymax;
+    __syncthreads();
+    for (int o = 32; o > 0; o >>= 1) {
+        if (tid < o) s_max[tid] = s_max[tid] > s_max[tid + o] ? s_max[tid] : s_max[tid + o];
+        __syncthreads();
+    }
+    const double maxll = s_max[0];
+    if (tid == 0 && out.gl_log_max) out.gl_log_max[wi] = maxll;
+    for (int g = tid; g < G; g += 64) {  // cpopulation.pyx:304-309
+        double v = 1.0;
+        if (ngood != 0) {
+            v = exp(gl[g] - maxll);
+            if (!(v > 1e-300)) v = 1e-300;
+        }
+        gl[g] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_population: one block per window.  EM (cpopulation.pyx:384-457, 678-703), genotype calls
+// (:623-676), variant posteriors (:459-594).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_population(DevBatch b, PopOut out, double* __restrict__ em_scratch,
+                                                   int max_iters, int use_em, int nthr_em) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int w = blockIdx.x;
+    const int nInd = b.n_individuals;
+    const int H = b.win_hap_off[w + 1] - b.win_hap_off[w];
+    const int G = H * (H + 1) / 2;
+    const int Hmax = out.max_haps, Gmax = Hmax * (Hmax + 1) / 2;
+    double* s_freq = (double*)smem;             // [Hmax]
+    double* s_new = s_freq + Hmax;              // [Hmax]
+    double* s_part = s_new + Hmax;              // [nthr_em][Hmax]
+    __shared__ double s_change;
+    __shared__ double s_ch[64];
+    __shared__ int s_nwith[64];
+    const int tid = threadIdx.x;
+    const double* gl = out.gl + (size_t)w * nInd * Gmax;
+    double* emp = (out.em_post ? out.em_post : em_scratch) + (size_t)w * nInd * Gmax;
+    const int32_t* ngood = b.wi_n_good + (size_t)w * nInd;
+
+    const double eps = fmin(1e-3, 1.0 / (nInd * 2 * 2));  // cpopulation.pyx:684
+    for (int k = tid; k < Hmax; k += 64) s_freq[k] = k < H ? 1.0 / H : 0.0;
+    for (int i = 0; i < nInd; ++i)
+        if (ngood[i] == 0)
+            for (int g = tid; g < Gmax; g += 64) emp[(size_t)i * Gmax + g] = 0.0;
+    for (int i = 0; i < nInd; ++i)
+        for (int g = G + tid; g < Gmax; g += 64) emp[(size_t)i * Gmax + g] = 0.0;
+    if (tid == 0) s_change = eps + 1;
+    __syncthreads();
+    int iters = 0;
+    while (s_change > eps && iters < max_iters) {  // uniform: s_change only changes between barriers
+        int nwith = 0;
+        if (tid < nthr_em) {
+            double* part = s_part + (size_t)tid * Hmax;
+            for (int k = 0; k < H; ++k) part[k] = 0.0;
+            for (int i = tid; i < nInd; i += nthr_em) {
+                if (ngood[i] == 0) continue;
+                ++nwith;
+                const double* gli = gl + (size_t)i * Gmax;
+                double* csr = emp + (size_t)i * Gmax;
+                double sum = 0.0;
+                int g = 0;
+                for (int s = 0; s < H; ++s)
+                    for (int r = s; r < H; ++r, ++g) {
+                        const double v = gli[g] * s_freq[s] * s_freq[r] * (1 + (r != s));
+                        csr[g] = v;
+                        sum += v;
+                    }
+                g = 0;
+                for (int s = 0; s < H; ++s)
+                    for (int r = s; r < H; ++r, ++g) {
+                        double v = csr[g];
+                        if (sum > 0.0) {
+                            v /= sum;
+                            csr[g] = v;
+                        }
+                        part[s] += v;
+                        part[r] += v;
+                    }
+            }
+        }
+        s_nwith[tid] = nwith;
+        __syncthreads();
+        int n_with = 0;
+        for (int k = 0; k < 64; ++k) n_with += s_nwith[k];
+        double mych = 0.0;
+        for (int k = tid; k < H; k += 64) {
+            double nf = 0.0;
+            for (int t = 0; t < nthr_em; ++t) nf += s_part[(size_t)t * Hmax + k];
+            if (n_with > 0) nf = nf / (2 * n_with); else nf = s_freq[k];
+            const double ch = fabs(s_freq[k] - nf);
+            if (ch > mych) mych = ch;
+            s_new[k] = nf;
+        }
+        s_ch[tid] = mych;
+        __syncthreads();
+        for (int k = tid; k < H; k += 64) s_freq[k] = s_new[k];
+        if (tid == 0) {
+            double m = 0.0;
+            for (int k = 0; k < 64; ++k) m = s_ch[k] > m ? s_ch[k] : m;
+            s_change = m;
+        }
+        ++iters;
+        __syncthreads();
+    }
+    if (out.freq)
+        for (int k = tid; k < Hmax; k += 64) out.freq[(size_t)w * Hmax + k] = s_freq[k];
+    if (tid == 0 && out.em_iters) out.em_iters[w] = iters;
+    // callGenotypes, cpopulation.pyx:623-676: first strict maximum
+    if (out.call) {
+        for (int i = tid; i < nInd; i += 64) {
+            int bestg = -1;
+            double bestv = 0.0;
+            if (ngood[i] != 0) {
+                const double* src = (use_em == 1 ? emp : gl) + (size_t)i * Gmax;
+                for (int g = 0; g < G; ++g)
+                    if (bestg == -1 || src[g] > bestv) {
+                        bestv = src[g];
+                        bestg = g;
+                    }
+            }
+            out.call[(size_t)w * nInd + i] = bestg;
+        }
+    }
+    // calculatePosterior, cpopulation.pyx:459-594, one thread per variant
+    if (out.var_phred && b.max_variants > 0 && b.win_n_var) {
+        const int nvar = b.win_n_var[w];
+        const uint64_t* masks = b.hap_var_mask + b.win_hap_off[w];
+        __syncthreads();
+        for (int v0 = 0; v0 < b.max_variants; v0 += nthr_em) {
+            const int v = v0 + tid;
+            if (tid < nthr_em && v < b.max_variants) {
+                double ph = 0.0;
+                if (v < nvar) {
+                    double* fp = s_part + (size_t)tid * Hmax;
+                    double sumf = 0.0;
+                    for (int k = 0; k < H; ++k) {
+                        if (!((masks[k] >> v) & 1ull)) {
+                            fp[k] = s_freq[k];
+                            sumf += s_freq[k];
+                        } else {
+                            fp[k] = 0.0;
+                        }
+                    }
+                    if (sumf > 0)
+                        for (int k = 0; k < H; ++k) fp[k] /= sumf;
+                    double slv = 0.0, sln = 0.0;
+                    for (int i = 0; i < nInd; ++i) {
+                        if (ngood[i] == 0) continue;
+                        const double* gli = gl + (size_t)i * Gmax;
+                        double pv = 0.0, pn = 0.0;
+                        int g = 0;
+                        for (int r = 0; r < H; ++r)
+                            for (int s = r; s < H; ++s, ++g) {
+                                const double l = gli[g];
+                                const double factor = (r != s) ? 2.0 : 1.0;
+                                pv += (factor * s_freq[r] * s_freq[s] * l);
+                                pn += (factor * fp[r] * fp[s] * l);
+                            }
+                        slv += pv > 0 ? log(pv) : -708.0;
+                        sln += pn > 0 ? log(pn) : -708.0;
+                    }
+                    double ratio = exp(sln - slv);
+                    if (!(ratio > 1e-300)) ratio = 1e-300;
+                    const double prior = b.var_prior[(size_t)w * b.max_variants + v];
+                    ph = round(-10.0 * (log10(ratio * (1.0 - prior)) - log10(prior + ratio * (1.0 - prior))));
+                }
+                out.var_phred[(size_t)w * b.max_variants + v] = ph;
+            }
+        }
+    }
+}
+
+}  // namespace plb

@@ -1,0 +1,195 @@
+"""
+ctypes binding of libplatypus_b200.so (include/platypus_b200.h) and a thin Engine object.
+
+There is no CPU fallback: if the shared library is missing, or no B200-class GPU is visible,
+construction raises.  PyTorch is used only as plumbing (device memory for the device-resident
+path, streams, torch.distributed); all arithmetic happens in the CUDA kernels.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from .batch import WindowBatch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libplatypus_b200.so")
+_lib = None
+
+
+class PlbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("platypus_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PlbError(_abi.PLB_ERR_CUDA, "%s not built (run python -c 'import __graft_entry__ as g; g.build()'); "
+                           "there is no CPU fallback" % LIB_PATH)
+        _lib = _abi.declare(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def _check(lib, rc):
+    if rc < 0:
+        raise PlbError(rc, lib.plb_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+class Engine:
+    """One engine per GPU.  Mirrors the three seams of the reference:
+    S1 fast_align/align_batch, S2 window_loglik, S3 population_run."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        _check(self.lib, self.lib.plb_context_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.ctx = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.plb_context_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(self.lib.plb_launch_count(self.ctx))
+
+    def last_stats(self):
+        st = _abi.PlbRunStats()
+        _check(self.lib, self.lib.plb_last_stats(self.ctx, C.byref(st)))
+        return st.as_dict()
+
+    # ---- S1 ---------------------------------------------------------------------------------
+    def fast_align(self, seq1: bytes, seq2: bytes, qual2: bytes, gap_open: bytes, gapextend=3, nucprior=2):
+        """fastAlignmentRoutine(seq1, seq2, qual2, len1, len2, gapextend, nucprior, localgapopen, NULL, NULL, NULL)
+        (reference: src/c/align.h:8-9)."""
+        L = len(seq2)
+        if len(seq1) < L + 15 or len(gap_open) < L + 15 or len(qual2) != L:
+            raise PlbError(_abi.PLB_ERR_SHAPE, "need len(seq1) >= len(seq2)+15 and matching qual/gap-open lengths")
+        return _check(self.lib, self.lib.plb_fast_align(self.ctx, seq1, seq2, qual2, L + 15, L, gapextend, nucprior,
+                                                        gap_open, None, None, None))
+
+    def align_batch(self, hap_segs, gap_opens, reads, quals, gapextend=3, nucprior=2):
+        """Batched S1 over explicit (segment, read) pairs given as lists of bytes."""
+        n = len(reads)
+        ho = np.zeros(n + 1, np.int64)
+        ro = np.zeros(n + 1, np.int64)
+        np.cumsum([len(x) for x in hap_segs], out=ho[1:])
+        np.cumsum([len(x) for x in reads], out=ro[1:])
+        for hs, go, rd, q in zip(hap_segs, gap_opens, reads, quals):
+            if len(go) < len(hs) or len(q) != len(rd):
+                raise PlbError(_abi.PLB_ERR_SHAPE, "gap-open shorter than segment or qual/read length mismatch")
+        hseq = np.frombuffer(b"".join(hap_segs), np.uint8)
+        gop = np.frombuffer(b"".join(g[:len(h)] for g, h in zip(gap_opens, hap_segs)), np.uint8)
+        rseq = np.frombuffer(b"".join(reads), np.uint8)
+        rq = np.frombuffer(b"".join(quals), np.uint8)
+        out = np.zeros(max(n, 1), np.int32)
+        _check(self.lib, self.lib.plb_align_batch_host(self.ctx, n, _abi.ptr(ho), hseq.ctypes.data, gop.ctypes.data,
+                                                       _abi.ptr(ro), rseq.ctypes.data, rq.ctypes.data, gapextend,
+                                                       nucprior, _abi.ptr(out)))
+        return out[:n]
+
+    def gap_open(self, haps):
+        """Haplotype.annotateWithGapOpen for a list of haplotype byte strings
+        (reference: src/cython/chaplotype.pyx:552-590); returns a list of bytes of length hapLen+1."""
+        n = len(haps)
+        off = np.zeros(n + 1, np.int64)
+        np.cumsum([len(h) for h in haps], out=off[1:])
+        seq = np.frombuffer(b"".join(haps), np.uint8)
+        out = np.zeros(int(off[-1]) + n + 1, np.uint8)
+        _check(self.lib, self.lib.plb_gap_open_host(self.ctx, n, _abi.ptr(off), seq.ctypes.data if len(seq) else None,
+                                                    _abi.ptr(out)))
+        return [out[int(off[h]) + h:int(off[h + 1]) + h + 1].tobytes() for h in range(n)]
+
+    # ---- S2 ---------------------------------------------------------------------------------
+    def window_loglik(self, batch: WindowBatch, opt=None, want_score=True):
+        """Per-read log-likelihoods of every haplotype of every window
+        (Haplotype.alignReads, reference: src/cython/chaplotype.pyx:306-377).
+        Returns (ll, score) flat arrays in the layout given by batch.ll_offsets()."""
+        opt = opt or _abi.PlbOptions.default()
+        off = batch.ll_offsets()
+        n = int(off[-1])
+        ll = np.zeros(max(n, 1), np.float64)
+        sc = np.zeros(max(n, 1), np.int32) if want_score else None
+        out = _abi.PlbLoglikOut(_abi.ptr(off), _abi.ptr(ll), _abi.ptr(sc))
+        s = batch.as_struct()
+        _check(self.lib, self.lib.plb_window_loglik_host(self.ctx, C.byref(s), C.byref(opt), C.byref(out)))
+        return ll[:n], (sc[:n] if want_score else None)
+
+    # ---- S3 ---------------------------------------------------------------------------------
+    @staticmethod
+    def alloc_population_out(batch: WindowBatch, max_haps=None):
+        W, nI = batch.n_windows, batch.n_individuals
+        Hm = max_haps or batch.max_haps()
+        Gm = Hm * (Hm + 1) // 2
+        V = max(batch.max_variants, 1)
+        return {"max_haps": Hm, "gl": np.zeros((W, nI, Gm)), "gl_log_max": np.zeros((W, nI)),
+                "gof": np.zeros((W, Gm, nI)), "hap_like": np.zeros((W, nI, Hm)), "freq": np.zeros((W, Hm)),
+                "em_post": np.zeros((W, nI, Gm)), "call": np.zeros((W, nI), np.int32),
+                "var_phred": np.zeros((W, V)), "em_iters": np.zeros(W, np.int32)}
+
+    @staticmethod
+    def _pop_struct(arrs, ptr_of=_abi.ptr):
+        o = _abi.PlbPopulationOut()
+        o.max_haps = arrs["max_haps"]
+        for k in ("gl", "gl_log_max", "gof", "hap_like", "freq", "em_post", "call", "var_phred", "em_iters"):
+            setattr(o, k, ptr_of(arrs.get(k)))
+        return o
+
+    def population_run(self, batch: WindowBatch, opt=None, max_haps=None, want_ll=False, out=None):
+        """Population.setup + Population.call for every window (reference:
+        src/cython/cpopulation.pyx:197-309, 678-720).  Host buffers in and out.
+        Returns dict of arrays (+ 'll', 'score' when want_ll)."""
+        opt = opt or _abi.PlbOptions.default()
+        arrs = out or self.alloc_population_out(batch, max_haps)
+        po = self._pop_struct(arrs)
+        lo = None
+        if want_ll:
+            off = batch.ll_offsets()
+            n = int(off[-1])
+            ll = np.zeros(max(n, 1), np.float64)
+            sc = np.zeros(max(n, 1), np.int32)
+            lo = _abi.PlbLoglikOut(_abi.ptr(off), _abi.ptr(ll), _abi.ptr(sc))
+        s = batch.as_struct()
+        _check(self.lib, self.lib.plb_population_run_host(self.ctx, C.byref(s), C.byref(opt), C.byref(po),
+                                                          C.byref(lo) if lo is not None else None))
+        if want_ll:
+            arrs["ll"], arrs["score"] = ll[:n], sc[:n]
+        return arrs
+
+    # ---- device-resident path -------------------------------------------------------------------
+    def upload(self, batch: WindowBatch):
+        h = C.c_void_p()
+        s = batch.as_struct()
+        _check(self.lib, self.lib.plb_batch_upload(self.ctx, C.byref(s), C.byref(h)))
+        return h
+
+    def free(self, handle):
+        self.lib.plb_batch_free(self.ctx, handle)
+
+    def run_device(self, handle, pop_ptrs=None, ll_ptr=None, score_ptr=None, ll_off_ptr=None, opt=None):
+        """Launch the whole path on a device-resident batch; asynchronous on the context stream.
+        pop_ptrs: dict name -> device pointer (int) incl. 'max_haps'."""
+        opt = opt or _abi.PlbOptions.default()
+        po = None
+        if pop_ptrs is not None:
+            po = _abi.PlbPopulationOut()
+            po.max_haps = pop_ptrs["max_haps"]
+            for k in ("gl", "gl_log_max", "gof", "hap_like", "freq", "em_post", "call", "var_phred", "em_iters"):
+                setattr(po, k, pop_ptrs.get(k))
+        lo = _abi.PlbLoglikOut(ll_off_ptr, ll_ptr, score_ptr)
+        _check(self.lib, self.lib.plb_run_device(self.ctx, handle, C.byref(opt), C.byref(po) if po is not None else None,
+                                                 C.byref(lo)))

@@ -1,0 +1,228 @@
+"""
+"synth-v1" synthetic windows: the workload BASELINE.json's configs are quoted on.
+
+Counter-based RNG (numpy Philox) keyed by (seed, chunk of 256 windows), so window w has the
+same bytes no matter how the job is sharded or how many windows are generated around it.
+
+Per window: a reference segment of hapLen+16 iid ACGT (15 % chance of one homopolymer run of
+4-12 in the middle third); haplotype 0 = reference, haplotypes 1..H-1 carry 1-3 variants
+(SNP 70 % / 1-3 bp insertion 15 % / 1-3 bp deletion 15 %) at distinct positions of the central
+50 bp and are re-cut to hapLen, never duplicating another haplotype (the reference dedupes,
+src/cython/variantcaller.pyx:325-390).  Reads are drawn from one of two "true" haplotypes:
+start uniform in [0, hapLen-L-16], qualities 90 % U[25,40] / 10 % U[2,24], substitutions with
+probability 10^(-q/10), 0.2 %/base 1-bp indel errors, mapq 85 % 60 / 10 % U[20,59] / 5 %
+U[0,19], read.pos = hapStart + idx + jitter (0 w.p. 0.9 else U[-5,5]).
+"""
+import numpy as np
+
+from .batch import WindowBatch
+
+SEED = 20261017
+CHUNK = 256
+_ACGT = np.frombuffer(b"ACGT", np.uint8)
+
+
+def _rng(seed, chunk_id):
+    return np.random.Generator(np.random.Philox(key=[seed, chunk_id]))
+
+
+def _make_haps(rng, H, hap_len):
+    """Returns (list of H uint8 arrays of length hap_len, list of variant sets, variant list)."""
+    ref = _ACGT[rng.integers(0, 4, hap_len + 16)]
+    if rng.random() < 0.15:
+        run = int(rng.integers(4, 13))
+        p = int(rng.integers(hap_len // 3, 2 * hap_len // 3 - run))
+        ref[p:p + run] = ref[p]
+    c0 = (hap_len - 50) // 2
+    haps = [ref[:hap_len].copy()]
+    seen = {haps[0].tobytes()}
+    variants = []      # (pos, kind, payload)
+    var_ix = {}
+    hap_vars = [set()]
+    tries = 0
+    while len(haps) < H:
+        tries += 1
+        nv = int(rng.integers(1, 4))
+        pos = sorted(int(x) for x in rng.choice(50, nv, replace=False) + c0)
+        edits = []
+        for p in pos:
+            u = rng.random()
+            if u < 0.70:
+                alt = _ACGT[(int(np.searchsorted(_ACGT, ref[p])) + int(rng.integers(1, 4))) % 4]
+                edits.append((p, "S", bytes([alt])))
+            elif u < 0.85:
+                edits.append((p, "I", _ACGT[rng.integers(0, 4, int(rng.integers(1, 4)))].tobytes()))
+            else:
+                edits.append((p, "D", int(rng.integers(1, 4))))
+        out, cur = [], 0
+        for p, k, pl in edits:
+            if p < cur:
+                continue
+            out.append(ref[cur:p])
+            if k == "S":
+                out.append(np.frombuffer(pl, np.uint8))
+                cur = p + 1
+            elif k == "I":
+                out.append(ref[p:p + 1])
+                out.append(np.frombuffer(pl, np.uint8))
+                cur = p + 1
+            else:
+                cur = p + pl
+        out.append(ref[cur:])
+        seq = np.concatenate(out)
+        if len(seq) < hap_len:
+            continue
+        seq = seq[:hap_len].copy()
+        key = seq.tobytes()
+        if key in seen and tries < 200:
+            continue
+        seen.add(key)
+        vs = set()
+        for e in edits:
+            if e not in var_ix:
+                var_ix[e] = len(variants)
+                variants.append(e)
+            vs.add(var_ix[e])
+        haps.append(seq)
+        hap_vars.append(vs)
+    return haps, hap_vars, variants
+
+
+def make_batch(n_windows, n_haps=8, n_reads=64, read_len=150, hap_len=250, n_individuals=1, seed=SEED,
+               window_offset=0, read_len_range=None, hap_len_range=None, with_variants=True, pos_jitter=0.1):
+    """Build a WindowBatch of synth-v1 windows [window_offset, window_offset+n_windows).
+
+    read_len_range=(lo,hi): per-read length U{lo..hi} (config 3); hap_len_range=(lo,hi): per-window
+    haplotype length U[max(lo, Lmax+16), hi].  n_reads is per individual.
+    """
+    W = n_windows
+    nI = n_individuals
+    win_hap_off = np.arange(W + 1, dtype=np.int32) * n_haps
+    hap_lens = np.zeros(W * n_haps, np.int64)
+    hap_chunks = []
+    R = n_reads * nI
+    read_lens_all, read_seq_chunks, read_qual_chunks = [], [], []
+    read_pos = np.zeros(W * R, np.int32)
+    read_mapq = np.zeros(W * R, np.uint8)
+    hap_start = np.zeros(W, np.int32)
+    win_start = np.zeros(W, np.int32)
+    win_end = np.zeros(W, np.int32)
+    masks = np.zeros(W * n_haps, np.uint64)
+    n_var = np.zeros(W, np.int32)
+    priors = []
+    Lmax = read_len_range[1] if read_len_range else read_len
+
+    first_chunk = window_offset // CHUNK
+    last_chunk = (window_offset + W - 1) // CHUNK if W else first_chunk - 1
+    for ck in range(first_chunk, last_chunk + 1):
+        rng = _rng(seed, ck)
+        for wg in range(ck * CHUNK, (ck + 1) * CHUNK):
+            # every window of the chunk is generated (cheaply skipped ones still advance the RNG)
+            hl = hap_len if not hap_len_range else int(rng.integers(max(hap_len_range[0], Lmax + 16), hap_len_range[1] + 1))
+            haps, hap_vars, variants = _make_haps(rng, n_haps, hl)
+            if read_len_range:
+                L = rng.integers(read_len_range[0], read_len_range[1] + 1, R)
+            else:
+                L = np.full(R, read_len, np.int64)
+            g1, g2 = int(rng.integers(0, n_haps)), int(rng.integers(0, n_haps))
+            src_hap = np.where(rng.random(R) < 0.5, g1, g2)
+            idx = (rng.random(R) * (hl - L - 16 + 1)).astype(np.int64)
+            Lm = int(L.max())
+            q = np.where(rng.random((R, Lm)) < 0.9, rng.integers(25, 41, (R, Lm)), rng.integers(2, 25, (R, Lm))).astype(np.uint8)
+            ev = rng.random((R, Lm))
+            ins = ev < 0.001
+            dele = (ev >= 0.001) & (ev < 0.002)
+            adv = np.ones((R, Lm), np.int64) - ins + dele
+            srcpos = idx[:, None] + np.cumsum(adv, axis=1) - adv
+            srcpos = np.minimum(srcpos, hl - 1)
+            hap2d = np.stack(haps)
+            bases = hap2d[src_hap[:, None], srcpos]
+            rnd_base = _ACGT[rng.integers(0, 4, (R, Lm))]
+            bases = np.where(ins, rnd_base, bases)
+            sub = rng.random((R, Lm)) < np.power(10.0, -q.astype(np.float64) / 10.0)
+            code = np.searchsorted(_ACGT, bases)
+            alt = _ACGT[(code + rng.integers(1, 4, (R, Lm))) % 4]
+            bases = np.where(sub, alt, bases).astype(np.uint8)
+            u = rng.random(R)
+            mq = np.where(u < 0.85, 60, np.where(u < 0.95, rng.integers(20, 60, R), rng.integers(0, 20, R)))
+            jit = np.where(rng.random(R) < (1.0 - pos_jitter), 0, rng.integers(-5, 6, R))
+            if wg < window_offset or wg >= window_offset + W:
+                continue
+            w = wg - window_offset
+            hs = 100000 + wg * 1000
+            hap_start[w] = hs
+            win_start[w] = hs + (hl - 50) // 2
+            win_end[w] = win_start[w] + 50
+            hap_lens[w * n_haps:(w + 1) * n_haps] = hl
+            hap_chunks.append(hap2d.reshape(-1))
+            valid = np.arange(Lm)[None, :] < L[:, None]
+            read_seq_chunks.append(bases[valid])
+            read_qual_chunks.append(q[valid])
+            read_lens_all.append(L)
+            read_pos[w * R:(w + 1) * R] = hs + idx + jit
+            read_mapq[w * R:(w + 1) * R] = mq
+            n_var[w] = min(len(variants), 64)
+            for h in range(n_haps):
+                m = 0
+                for v in hap_vars[h]:
+                    if v < 64:
+                        m |= (1 << v)
+                masks[w * n_haps + h] = m
+            priors.append([1e-3 if v[1] == "S" else 1e-4 for v in variants[:64]])
+
+    read_lens = np.concatenate(read_lens_all) if read_lens_all else np.zeros(0, np.int64)
+    read_seq_off = np.zeros(W * R + 1, np.int64)
+    np.cumsum(read_lens, out=read_seq_off[1:])
+    hap_seq_off = np.zeros(W * n_haps + 1, np.int64)
+    np.cumsum(hap_lens, out=hap_seq_off[1:])
+    b = WindowBatch(
+        n_windows=W, n_individuals=nI, win_hap_off=win_hap_off, win_start=win_start, win_end=win_end,
+        hap_start=hap_start, hap_seq_off=hap_seq_off,
+        hap_seq=np.concatenate(hap_chunks) if hap_chunks else np.zeros(0, np.uint8),
+        wi_slot_off=np.arange(W * nI + 1, dtype=np.int64) * n_reads,
+        wi_n_good=np.full(W * nI, n_reads, np.int32), wi_n_bad=np.zeros(W * nI, np.int32),
+        slot_read=np.arange(W * R, dtype=np.int32),
+        read_seq_off=read_seq_off,
+        read_seq=np.concatenate(read_seq_chunks) if read_seq_chunks else np.zeros(0, np.uint8),
+        read_qual=np.concatenate(read_qual_chunks) if read_qual_chunks else np.zeros(0, np.uint8),
+        read_pos=read_pos, read_end=(read_pos + read_lens).astype(np.int32), read_mapq=read_mapq,
+        read_qcfail=np.zeros(W * R, np.uint8),
+    )
+    if with_variants and W:
+        mv = max(1, int(n_var.max()))
+        pri = np.zeros((W, mv), np.float64)
+        for w, p in enumerate(priors):
+            pri[w, :len(p)] = p
+        b.max_variants = mv
+        b.win_n_var = n_var
+        b.hap_var_mask = masks
+        b.var_prior = pri
+    return b
+
+
+def algorithmic_cells(batch: WindowBatch) -> int:
+    """16 * readLen per (read, haplotype) pair, ignoring LL=0 short-circuits
+    (synth-v1 has none)."""
+    H = np.repeat(batch.haps_per_window().astype(np.int64), batch.n_individuals)
+    tot = 0
+    lens = np.diff(batch.read_seq_off)
+    slot_len = lens[batch.slot_read]
+    cs = np.concatenate([[0], np.cumsum(slot_len)])
+    per_wi = cs[batch.wi_slot_off[1:]] - cs[batch.wi_slot_off[:-1]]
+    tot = int((per_wi * H).sum()) * 16
+    return tot
+
+
+def algorithmic_bytes(batch: WindowBatch) -> int:
+    """Algorithmic HBM bytes of one pass: per read ceil(L/4)+L+8, per haplotype
+    ceil(hapLen/4)+8, outputs 8*H*T (per-read LL) + 8*nInd*G (GL)."""
+    lens = np.diff(batch.read_seq_off)
+    slot_len = lens[batch.slot_read].astype(np.int64)
+    rd = int(((slot_len + 3) // 4 + slot_len + 8).sum())
+    hl = np.diff(batch.hap_seq_off).astype(np.int64)
+    hp = int(((hl + 3) // 4 + 8).sum())
+    H = batch.haps_per_window().astype(np.int64)
+    T = np.diff(batch.wi_slot_off).astype(np.int64)
+    out = int((np.repeat(H, batch.n_individuals) * T).sum()) * 8
+    out += int((H * (H + 1) // 2).sum()) * 8 * batch.n_individuals
+    return rd + hp + out

@@ -1,0 +1,183 @@
+"""Deterministic test-case generators shared by the golden-vector script and the tests."""
+import random
+
+from platypus_b200.batch import Read, Window, WindowBatch
+
+ACGT = b"ACGT"
+
+
+def _rand_seq(rng, n, alphabet=ACGT):
+    return bytes(rng.choice(alphabet) for _ in range(n))
+
+
+def mutate(rng, src: bytes, L: int, sub=0.02, ins=0.008, dele=0.008, n_rate=0.004):
+    """Read of length L copied from src with substitutions / indels / N."""
+    out = bytearray()
+    i = 0
+    while len(out) < L:
+        u = rng.random()
+        if i >= len(src):
+            out.append(rng.choice(ACGT))
+        elif u < sub:
+            out.append(rng.choice(ACGT))
+            i += 1
+        elif u < sub + ins:
+            out.append(rng.choice(ACGT))
+        elif u < sub + ins + dele:
+            i += rng.randint(1, 3)
+        elif u < sub + ins + dele + n_rate:
+            out.append(ord("N"))
+            i += 1
+        else:
+            out.append(src[i])
+            i += 1
+    return bytes(out)
+
+
+def random_alignment_case(rng, i):
+    """(hap_segment >= L+15, gap_open, read, qual) for the L1 kernel."""
+    L = rng.choice([1, 2, 7, 8, 9, 10, 15, 16, 17, 20, 24, 31, 37, 64, 100, 101, 150, 151, 250, 251])
+    n = L + 15 + rng.randint(0, 30)
+    hap = bytearray(_rand_seq(rng, n))
+    kind = i % 8
+    if kind == 1:  # N's in the haplotype (free match, align.c:175-178)
+        for _ in range(rng.randint(1, 6)):
+            hap[rng.randrange(n)] = ord("N")
+    if kind == 2:  # homopolymer
+        p = rng.randrange(max(1, n - 12))
+        for k in range(p, min(n, p + rng.randint(4, 12))):
+            hap[k] = hap[p]
+    if kind == 3:  # IUPAC / lower case bytes: byte-exact compare (align.c:315)
+        for _ in range(rng.randint(1, 4)):
+            hap[rng.randrange(n)] = rng.choice(b"RYKMacgtn")
+    off = rng.randint(0, 15)
+    if kind == 4:
+        read = _rand_seq(rng, L, b"ACGTN")  # unrelated read
+    elif kind == 5:  # leading insertion: read starts with bases absent from the haplotype
+        k = rng.randint(1, min(4, L))
+        read = (_rand_seq(rng, k) + bytes(hap[off:off + L]))[:L]
+    else:
+        read = mutate(rng, bytes(hap[off:]), L)
+    if kind == 3 and L > 4:  # let a read carry the same odd byte so exact equality matters
+        j = rng.randrange(L)
+        read = read[:j] + bytes([hap[min(n - 1, off + j)]]) + read[j + 1:]
+    qual = bytes(0 if rng.random() < 0.08 else rng.randint(1, 41) for _ in range(L))
+    if kind == 6:
+        qual = bytes(rng.randint(30, 60) for _ in range(L))  # high qualities, bigger scores
+    go = bytes(rng.choice([45, 42, 39, 32, 23, 16, 9, 5, 1]) for _ in range(n + 1))
+    return bytes(hap), go, read, qual
+
+
+def random_hap(rng, n):
+    u = rng.random()
+    if u < 0.3:  # tandem repeat -> tied votes
+        unit = _rand_seq(rng, rng.randint(1, 9))
+        h = bytearray((unit * (n // len(unit) + 1))[:n])
+        for _ in range(rng.randint(0, 6)):
+            h[rng.randrange(n)] = rng.choice(ACGT)
+    else:
+        h = bytearray(_rand_seq(rng, n))
+    if rng.random() < 0.15:
+        for _ in range(rng.randint(1, 6)):
+            h[rng.randrange(n)] = ord("N")
+    if rng.random() < 0.05:
+        h[rng.randrange(n)] = rng.choice(b"RYacgt")
+    return bytes(h)
+
+
+def random_mapping_case(rng, i):
+    """(hap, read, qual, read_start, hap_start) for mapAndAlignReadToHaplotype."""
+    L = rng.choice([3, 7, 8, 9, 12, 30, 50, 75, 100, 150, 200])
+    hap_len = L + 16 + rng.randint(0, 400)
+    hap = random_hap(rng, hap_len)
+    idx = rng.randint(0, hap_len - L)
+    if rng.random() < 0.1:
+        read = _rand_seq(rng, L, b"ACGTN")
+    else:
+        read = mutate(rng, hap[idx:], L, sub=0.02, ins=0.005, dele=0.005, n_rate=0.002)
+    qual = bytes(rng.randint(0, 40) for _ in range(L))
+    hap_start = rng.randint(100, 100000)
+    jit = rng.choice([0, 0, 0, rng.randint(-5, 5), rng.randint(-300, 300)])
+    if i % 37 == 0:
+        jit = -idx - 1  # fallback index exactly -1
+    return hap, read, qual, hap_start + idx + jit, hap_start
+
+
+def edge_batch(seed=5, n_windows=12, n_individuals=3):
+    """Small multi-individual batch exercising the edge cases the reference's logic has:
+    N / IUPAC bytes, zeroed qualities, QC-fail, overlap < 7, mapq 0, exact matches, tandem repeats,
+    reads shorter than 7 / 9, ragged lengths, individuals without reads, bad + broken-mate reads,
+    single-haplotype windows, shared reads between windows."""
+    rng = random.Random(seed)
+    windows = []
+    shared = None
+    for w in range(n_windows):
+        hap_len = rng.choice([120, 200, 260, 333])
+        flank = (hap_len - 40) // 2
+        hap_start = 5000 + 700 * w
+        ws, we = hap_start + flank, hap_start + flank + 40
+        ref = bytearray(random_hap(rng, hap_len) if w % 3 == 1 else _rand_seq(rng, hap_len))
+        if w % 4 == 2:
+            ref[rng.randrange(hap_len)] = ord("N")
+        if w == 7:
+            ref[flank + 3] = ord("R")  # IUPAC -> general path for the whole window
+        H = 1 if w == 5 else rng.choice([2, 3, 4, 6])
+        haps = [bytes(ref)]
+        masks = [0]
+        nvar = 0
+        while len(haps) < H:
+            h = bytearray(ref)
+            m = 0
+            for _ in range(rng.randint(1, 2)):
+                p = flank + rng.randrange(40)
+                kind = rng.random()
+                if kind < 0.6:
+                    h[p] = rng.choice([c for c in ACGT if c != h[p]])
+                elif kind < 0.8:
+                    h[p:p] = _rand_seq(rng, rng.randint(1, 3))
+                else:
+                    del h[p:p + rng.randint(1, 3)]
+                m |= 1 << (nvar % 6)
+                nvar += 1
+            h = bytes(h[:hap_len]) if len(h) >= hap_len else bytes(h) + _rand_seq(rng, hap_len - len(h))
+            if h not in haps:
+                haps.append(h)
+                masks.append(m)
+        n_var = min(6, max(1, nvar)) if H > 1 else 0
+        per_ind = []
+        for i in range(n_individuals):
+            if (w + i) % 5 == 4:
+                per_ind.append(([], [], []))  # individual without any reads
+                continue
+            lists = ([], [], [])
+            n_reads = rng.randint(1, 14)
+            for k in range(n_reads):
+                L = rng.choice([5, 7, 8, 9, 20, 36, 50, 75, 76, 100])
+                L = min(L, hap_len - 16)
+                src = haps[rng.randrange(len(haps))]
+                idx = rng.randint(0, hap_len - L - 15)
+                u = rng.random()
+                if u < 0.12:
+                    seq = src[idx:idx + L]  # exact match
+                elif u < 0.2:
+                    seq = _rand_seq(rng, L, b"ACGTN")
+                else:
+                    seq = mutate(rng, src[idx:], L)
+                qual = bytes(0 if rng.random() < 0.1 else rng.randint(2, 41) for _ in range(L))
+                pos = hap_start + idx + rng.choice([0, 0, 0, rng.randint(-5, 5), rng.randint(-60, 60)])
+                mapq = rng.choice([60, 60, 60, 37, 20, 3, 0])
+                r = Read(seq, qual, pos, pos + L, mapq, qcfail=(rng.random() < 0.08))
+                which = 0 if rng.random() < 0.7 else rng.choice([1, 2])
+                lists[which].append(r)
+            if w % 2 == 1 and shared is not None and i == 0:
+                lists[0].append(shared)  # a read object shared with the previous window
+            if lists[0]:
+                shared = lists[0][0]
+            # the no-data rule keys on good reads only (cpopulation.pyx:286-294): make one individual
+            # have bad reads but no good ones
+            if w == 3 and i == 1:
+                lists = ([], lists[0] + lists[1], lists[2])
+            per_ind.append(lists)
+        windows.append(Window(ws, we, hap_start, haps, per_ind, hap_var_mask=masks,
+                              var_prior=[rng.choice([1e-3, 1e-4, 0.5, 3.3e-4]) for _ in range(n_var)]))
+    return WindowBatch.from_windows(windows, n_individuals)

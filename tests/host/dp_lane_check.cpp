@@ -1,0 +1,59 @@
+// CPU check of the packed-lane DP (platypus_b200/csrc/plb_dp.cuh, host emulation of the
+// s16x2 intrinsics) against the oracle's cell-by-cell restatement.  Built and run by
+// tests/test_host_logic.py; no GPU involved.  Prints "mismatches N".
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../platypus_b200/csrc/plb_dp.cuh"
+extern "C" int plo_band_align(const uint8_t*, const uint8_t*, const uint8_t*, int, int, int, const uint8_t*);
+
+static uint64_t rs = 88172645463325252ull;
+static uint32_t rnd() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (uint32_t)(rs >> 11); }
+
+int main(int argc, char** argv) {
+    int n_cases = argc > 1 ? atoi(argv[1]) : 3000;
+    int bad = 0, bad_gen = 0;
+    const char* alpha = "ACGT";
+    for (int c = 0; c < n_cases; ++c) {
+        int L = 9 + rnd() % 260;
+        if (c % 7 == 0) L = 9 + rnd() % 12;
+        int x0 = rnd() % 20;
+        int hapLen = x0 + L + 15 + rnd() % 30;
+        std::vector<uint8_t> hap(hapLen), open(hapLen + 1), read(L), qual(L);
+        for (auto& b : hap) b = alpha[rnd() % 4];
+        if (c % 5 == 0) for (int k = 0; k < 4; ++k) hap[rnd() % hapLen] = 'N';
+        for (auto& o : open) o = (uint8_t)(1 + rnd() % 45);
+        open[hapLen] = 0;
+        int src = x0 + rnd() % 16, i = src;
+        for (int y = 0; y < L; ++y) {
+            uint32_t u = rnd() % 1000;
+            if (c % 11 == 0) { read[y] = "ACGTN"[rnd() % 5]; continue; }           // unrelated read
+            if (u < 20) { read[y] = alpha[rnd() % 4]; ++i; }
+            else if (u < 28) { read[y] = alpha[rnd() % 4]; }
+            else if (u < 36) { i += 1 + rnd() % 3; read[y] = hap[i < hapLen ? i : hapLen - 1]; ++i; }
+            else if (u < 40) { read[y] = 'N'; ++i; }
+            else { read[y] = hap[i < hapLen ? i : hapLen - 1]; ++i; }
+        }
+        for (auto& q : qual) q = (uint8_t)((rnd() % 10 == 0) ? 0 : rnd() % 42);
+        int ext = 3, nuc = 2;
+        int want = plo_band_align(hap.data() + x0, read.data(), qual.data(), L, ext, nuc, open.data() + x0);
+        // device-format staging
+        int n = plb::dp_steps(L);
+        std::vector<plb::u32> prof(n + 8, 0);
+        for (int y = 0; y < L; ++y) prof[y] = plb::make_profile(plb::fast_code(read[y]), qual[y]);
+        std::vector<plb::HapRec> rec(hapLen + plb::kRecPad + 64);
+        for (size_t x = 0; x < rec.size(); ++x) {
+            auto code = [&](size_t p) { return p < (size_t)hapLen ? plb::fast_code(hap[p]) : 4; };
+            auto go = [&](size_t p) { return p <= (size_t)hapLen ? (plb::u32)open[p] : 0u; };
+            rec[x].gow = go(x) | (go(x + 4) << 16);
+            rec[x].sel = plb::make_sel(code(x), code(x + 4));
+        }
+        int got = plb::band_dp_fast(prof.data(), rec.data() + x0, L, ext, nuc);
+        int gen = plb::band_dp_general(hap.data() + x0, open.data() + x0, read.data(), qual.data(), L, ext, nuc);
+        if (got != want) { if (++bad < 6) printf("fast mismatch L=%d x0=%d want=%d got=%d\n", L, x0, want, got); }
+        if (gen != want) { if (++bad_gen < 6) printf("general mismatch L=%d want=%d got=%d\n", L, want, gen); }
+    }
+    printf("mismatches %d general %d of %d\n", bad, bad_gen, n_cases);
+    return (bad || bad_gen) ? 1 : 0;
+}

@@ -1,0 +1,260 @@
+"""GPU parity tests: every check goes through the C ABI (platypus_b200.engine -> libplatypus_b200.so)
+and compares with the CPU oracle / the committed golden vectors.  Integer scores must be
+bit-exact; log-likelihoods, genotype likelihoods, frequencies and posteriors within 1e-4 relative
+(the tolerance BASELINE.json states) - in practice they agree to ~1e-12."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from platypus_b200 import _abi, synth
+from platypus_b200.batch import Read, Window, WindowBatch
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4          # north_star tolerance
+RTOL_TIGHT = 1e-9    # what identical summation order actually gives
+
+
+def _unpack(off, data, i):
+    return data[off[i]:off[i + 1]].tobytes()
+
+
+def test_native_library_is_loaded(engine):
+    assert os.path.basename(engine.lib._name) == "libplatypus_b200.so"
+    assert engine.launch_count == 0
+
+
+def test_s1_golden_align_ref(engine, golden_dir):
+    g = np.load(os.path.join(golden_dir, "align_ref.npz"))
+    n = len(g["score"])
+    haps = [_unpack(g["hap_off"], g["hap"], i) for i in range(n)]
+    gos = [_unpack(g["hap_off"], g["gap_open"], i) for i in range(n)]
+    reads = [_unpack(g["read_off"], g["read"], i) for i in range(n)]
+    quals = [_unpack(g["read_off"], g["qual"], i) for i in range(n)]
+    got = engine.align_batch(haps, gos, reads, quals)
+    assert np.array_equal(got, g["score"])
+    assert engine.launch_count > 0
+
+
+def test_s1_scalar_signature(engine, oracle):
+    rng = random.Random(3)
+    for i in range(6):
+        hap, go, read, qual = cases.random_alignment_case(rng, i)
+        assert engine.fast_align(hap, read, qual, go) == oracle.band_align(hap, read, qual, go)
+
+
+def test_s1_fuzz_vs_oracle(engine, oracle):
+    rng = random.Random(2024)
+    cs = [cases.random_alignment_case(rng, i) for i in range(3000)]
+    got = engine.align_batch([c[0][:len(c[2]) + 15] for c in cs], [c[1] for c in cs], [c[2] for c in cs],
+                             [c[3] for c in cs])
+    want = np.array([oracle.band_align(*[c[0], c[2], c[3], c[1]]) for c in cs], np.int32)
+    assert np.array_equal(got, want)
+
+
+def test_gap_open_vs_oracle(engine, oracle):
+    rng = random.Random(5)
+    haps = [cases.random_hap(rng, rng.randint(1, 700)) for _ in range(60)] + [b"A" * 120, b"ANNNA", b"G"]
+    got = engine.gap_open(haps)
+    for h, g in zip(haps, got):
+        assert g == oracle.gap_open(h)
+
+
+def _mapping_batch(cs):
+    """One window per (hap, read) case so that calign golden cases run through S2."""
+    wins = []
+    for hap, read, qual, rs, hs in cs:
+        r = Read(read, qual, rs, rs + len(read), 60)
+        # window interval = whole haplotype so the overlap rule never fires; broken-mate list skips it anyway
+        wins.append(Window(hs, hs + len(hap), hs, [hap], [([], [], [r])]))
+    return WindowBatch.from_windows(wins, 1)
+
+
+def test_s2_golden_calign_ref(engine, golden_dir):
+    g = np.load(os.path.join(golden_dir, "calign_ref.npz"))
+    n = len(g["score"])
+    cs = []
+    for i in range(n):
+        cs.append((_unpack(g["hap_off"], g["hap"], i), _unpack(g["read_off"], g["read"], i),
+                   _unpack(g["read_off"], g["qual"], i), int(g["read_start"][i]), int(g["hap_start"][i])))
+    b = _mapping_batch(cs)
+    ll, sc = engine.window_loglik(b)
+    assert np.array_equal(sc, g["score"])
+
+
+def test_s2_mapping_fuzz_vs_oracle(engine, oracle):
+    rng = random.Random(77)
+    cs = [cases.random_mapping_case(rng, i) for i in range(1500)]
+    b = _mapping_batch(cs)
+    ll, sc = engine.window_loglik(b)
+    ll0, sc0, st0 = oracle.window_loglik(b)
+    assert np.array_equal(sc, sc0)
+    np.testing.assert_allclose(ll, ll0, rtol=RTOL_TIGHT, atol=0)
+
+
+def _check_population(got, want, rtol=RTOL_TIGHT):
+    for k in ("gl", "gl_log_max", "gof", "hap_like", "freq", "em_post"):
+        np.testing.assert_allclose(got[k], want[k], rtol=rtol, atol=1e-300, err_msg=k)
+    assert np.array_equal(got["call"], want["call"])
+    assert np.array_equal(got["em_iters"], want["em_iters"])
+    np.testing.assert_allclose(got["var_phred"], want["var_phred"], rtol=0, atol=0, err_msg="var_phred")
+
+
+def test_s3_edge_batch_vs_oracle_and_golden(engine, oracle, golden_dir):
+    b = cases.edge_batch(seed=5)
+    got = engine.population_run(b, want_ll=True)
+    want, ll0, sc0, st0 = oracle.population_run(b)
+    assert np.array_equal(got["score"], sc0)
+    np.testing.assert_allclose(got["ll"], ll0, rtol=RTOL_TIGHT, atol=0)
+    _check_population(got, want)
+    g = np.load(os.path.join(golden_dir, "window_restated.npz"))
+    assert np.array_equal(got["score"], g["score"])
+    np.testing.assert_allclose(got["gl"], g["gl"], rtol=RTOL, atol=1e-300)
+    st = engine.last_stats()
+    assert st["n_pairs"] == st0["n_pairs"] and st["n_pairs_scored"] == st0["n_pairs_scored"]
+    assert st["cells"] == st0["cells"]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_s3_more_edge_batches(engine, oracle, seed):
+    b = cases.edge_batch(seed=seed, n_windows=20, n_individuals=4)
+    got = engine.population_run(b, want_ll=True, max_haps=8)
+    want, ll0, sc0, _ = oracle.population_run(b, max_haps=8)
+    assert np.array_equal(got["score"], sc0)
+    _check_population(got, want)
+
+
+def test_s3_synth_config2_shape_sample(engine, oracle):
+    """Config-2 shaped windows (8 haplotypes x 64 reads, 150 bp x 250 bp)."""
+    b = synth.make_batch(96)
+    got = engine.population_run(b, want_ll=True)
+    want, ll0, sc0, st0 = oracle.population_run(b, n_threads=os.cpu_count() or 1)
+    assert np.array_equal(got["score"], sc0)
+    np.testing.assert_allclose(got["ll"], ll0, rtol=RTOL_TIGHT, atol=0)
+    _check_population(got, want)
+
+
+def test_s3_synth_config3_ragged(engine, oracle):
+    """Config-3 shaped windows: read length 100-250, haplotype length 200-500."""
+    b = synth.make_batch(48, read_len_range=(100, 250), hap_len_range=(200, 500))
+    got = engine.population_run(b, want_ll=True)
+    want, ll0, sc0, _ = oracle.population_run(b, n_threads=os.cpu_count() or 1)
+    assert np.array_equal(got["score"], sc0)
+    _check_population(got, want)
+
+
+def test_s3_multi_individual(engine, oracle):
+    b = synth.make_batch(16, n_haps=6, n_reads=10, n_individuals=12, read_len=100, hap_len=220)
+    got = engine.population_run(b, want_ll=True)
+    want, ll0, sc0, _ = oracle.population_run(b)
+    assert np.array_equal(got["score"], sc0)
+    _check_population(got, want, rtol=1e-7)   # newFreq sums over individuals are reduced per thread
+
+
+def test_long_haplotypes_and_reads(engine, oracle):
+    """Realistic flanked haplotypes (~1 kb) and 250-400 bp reads: 16-bit vote counters,
+    global-memory vote arrays, several haplotype groups per window."""
+    rng = random.Random(9)
+    wins = []
+    for w in range(6):
+        hl = rng.choice([900, 1400, 2100])
+        ref = cases._rand_seq(rng, hl)
+        haps = [ref]
+        for _ in range(5):
+            h = bytearray(ref)
+            p = hl // 2 + rng.randint(-20, 20)
+            h[p] = rng.choice([c for c in b"ACGT" if c != h[p]])
+            haps.append(bytes(h))
+        reads = []
+        for k in range(20):
+            L = rng.choice([250, 300, 400])
+            idx = rng.randint(0, hl - L - 16)
+            seq = cases.mutate(rng, haps[rng.randrange(6)][idx:], L)
+            reads.append(Read(seq, bytes(rng.randint(2, 40) for _ in range(L)), 1000 + idx, 1000 + idx + L, 60))
+        wins.append(Window(1000 + hl // 2 - 30, 1000 + hl // 2 + 30, 1000, haps, [(reads, [], [])]))
+    b = WindowBatch.from_windows(wins, 1)
+    got = engine.population_run(b, want_ll=True)
+    want, ll0, sc0, _ = oracle.population_run(b)
+    assert np.array_equal(got["score"], sc0)
+    _check_population(got, want)
+
+
+def test_empty_and_degenerate_batches(engine, oracle):
+    # windows where nobody has reads, and a zero-window batch
+    w = Window(100, 140, 50, [b"ACGT" * 30, b"ACGA" * 30], [([], [], []), ([], [], [])])
+    b = WindowBatch.from_windows([w, w], 2)
+    got = engine.population_run(b)
+    assert (got["gl"][:, :, :3] == 1.0).all() and (got["call"] == -1).all()
+    empty = synth.make_batch(0)
+    ll, sc = engine.window_loglik(empty)
+    assert len(ll) == 0
+
+
+def test_limits_are_errors_not_crashes(engine):
+    from platypus_b200.engine import PlbError
+    b = cases.edge_batch(seed=5)
+    with pytest.raises(PlbError) as e:
+        engine.population_run(b, max_haps=1)
+    assert e.value.code == _abi.PLB_ERR_SHAPE
+    with pytest.raises(PlbError) as e:
+        engine.population_run(b, opt=_abi.PlbOptions.default(use_mapq_cap=1))
+    assert e.value.code == _abi.PLB_ERR_UNSUPPORTED
+
+
+def test_full_size_config2_properties(engine, oracle):
+    """BASELINE config 2 at full size (10k windows x 8 haplotypes x 64 reads) through the C ABI.
+    The oracle cannot score 5.12 M pairs in seconds, so check size-independent properties plus a
+    random sample of windows against the oracle."""
+    W = 10000
+    b = synth.make_batch(W)
+    got = engine.population_run(b, want_ll=True)
+    st = engine.last_stats()
+    assert st["n_pairs"] == W * 8 * 64 and st["cells"] == synth.algorithmic_cells(b)
+    ll, sc = got["ll"], got["score"]
+    assert (sc >= 0).all() and (sc < 15872).all() and (ll <= 0).all() and (ll >= -300).all()
+    # rescaled genotype likelihoods peak at exactly 1, frequencies sum to 1, calls maximise GL
+    np.testing.assert_array_equal(got["gl"].max(axis=2), 1.0)
+    np.testing.assert_allclose(got["freq"].sum(axis=1), 1.0, rtol=1e-12)
+    assert np.array_equal(got["call"][:, 0], got["gl"][:, 0, :].argmax(axis=1))
+    # homozygous genotype log-likelihood = sum of that haplotype's read LLs (linearity check)
+    L = ll.reshape(W, 8, 64)
+    hom = np.array([0, 8, 15, 21, 26, 30, 33, 35])
+    gl_log = np.log(got["gl"][:, 0, :]) + got["gl_log_max"]
+    mask = got["gl"][:, 0, hom] > 1e-290
+    np.testing.assert_allclose(gl_log[:, hom][mask], L.sum(axis=2)[mask], rtol=1e-9)
+    # no cross-window state: reversing the window order reverses the outputs bit for bit
+    idx = np.arange(W)[::-1]
+    sub = [b.slice_windows(int(i), int(i) + 1) for i in idx[:300]]
+    rev = _concat(sub)
+    got_r = engine.population_run(rev, want_ll=True)
+    assert np.array_equal(got_r["score"].reshape(300, -1), sc.reshape(W, -1)[idx[:300]])
+    assert np.array_equal(got_r["gl"], got["gl"][idx[:300]])
+    # random sample of windows against the oracle
+    rng = np.random.default_rng(1)
+    pick = np.sort(rng.choice(W, 40, replace=False))
+    for w in pick:
+        s = b.slice_windows(int(w), int(w) + 1)
+        want, ll0, sc0, _ = oracle.population_run(s)
+        assert np.array_equal(sc.reshape(W, -1)[w], sc0)
+        np.testing.assert_allclose(got["gl"][w], want["gl"][0], rtol=RTOL_TIGHT, atol=1e-300)
+        np.testing.assert_allclose(got["freq"][w], want["freq"][0], rtol=RTOL_TIGHT)
+        np.testing.assert_array_equal(got["var_phred"][w, :want["var_phred"].shape[1]], want["var_phred"][0])
+
+
+def _concat(batches):
+    """Concatenate single-window batches (test helper)."""
+    wins = []
+    for s in batches:
+        haps = [s.hap_seq[s.hap_seq_off[h]:s.hap_seq_off[h + 1]].tobytes() for h in range(s.n_haps)]
+        reads = []
+        for t in range(s.n_slots):
+            r = int(s.slot_read[t])
+            a, e = int(s.read_seq_off[r]), int(s.read_seq_off[r + 1])
+            reads.append(Read(s.read_seq[a:e].tobytes(), s.read_qual[a:e].tobytes(), int(s.read_pos[r]),
+                              int(s.read_end[r]), int(s.read_mapq[r]), bool(s.read_qcfail[r])))
+        wins.append(Window(int(s.win_start[0]), int(s.win_end[0]), int(s.hap_start[0]), haps, [(reads, [], [])],
+                           hap_var_mask=[int(m) for m in s.hap_var_mask],
+                           var_prior=list(s.var_prior[0][:int(s.win_n_var[0])])))
+    return WindowBatch.from_windows(wins, 1)

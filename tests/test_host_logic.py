@@ -1,0 +1,104 @@
+"""CPU tests of the host side: the packed-lane DP (host emulation of the s16x2 intrinsics), batch
+packing / sharding, and that the C-ABI library loads and exports every symbol of
+include/platypus_b200.h (no compute calls: there is no GPU here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from platypus_b200 import _abi, synth
+from platypus_b200.batch import WindowBatch, shard_bounds
+from tests import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_packed_lane_dp_matches_oracle_on_host(oracle, tmp_path):
+    exe = str(tmp_path / "dp_lane_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "host", "dp_lane_check.cpp"),
+                           os.path.join(ROOT, "oracle", "libplatypus_oracle.so"),
+                           "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+    out = subprocess.run([exe, "4000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "mismatches 0 general 0" in out.stdout
+
+
+def _lib():
+    from __graft_entry__ import build
+    build()
+    from platypus_b200.engine import load_library
+    return load_library()
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib()
+    hdr = open(os.path.join(ROOT, "include", "platypus_b200.h")).read()
+    declared = set(re.findall(r"\b(plb_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_abi.EXPORTED_SYMBOLS), declared ^ set(_abi.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.plb_abi_version() == 1
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from platypus_b200.engine import Engine, PlbError
+    with pytest.raises(PlbError) as e:
+        Engine(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_ll_offsets_and_validate():
+    lib = _lib()
+    b = cases.edge_batch(seed=5)
+    s = b.as_struct()
+    off = np.zeros(b.n_windows * b.n_individuals + 1, np.int64)
+    tot = C.c_int64()
+    assert lib.plb_ll_offsets(C.byref(s), off.ctypes.data, C.byref(tot)) == 0
+    assert np.array_equal(off, b.ll_offsets()) and tot.value == off[-1]
+    opt = _abi.PlbOptions.default()
+    assert lib.plb_validate(C.byref(s), C.byref(opt), 0) == 0
+    assert lib.plb_validate(C.byref(s), C.byref(opt), 1) == _abi.PLB_ERR_SHAPE
+    assert b"max_haps" in lib.plb_last_error()
+    opt2 = _abi.PlbOptions.default(calc_flank_score=1)
+    assert lib.plb_validate(C.byref(s), C.byref(opt2), 0) == _abi.PLB_ERR_UNSUPPORTED
+    # haplotype shorter than read + 15: the reference would read out of bounds (calign.pyx:256-259)
+    from platypus_b200.batch import Read, Window
+    w = Window(100, 140, 50, [b"ACGT" * 10], [([Read(b"A" * 30, bytes([30] * 30), 100, 130)], [], [])])
+    s2 = WindowBatch.from_windows([w], 1).as_struct()
+    assert lib.plb_validate(C.byref(s2), C.byref(opt), 0) == _abi.PLB_ERR_SHAPE
+
+
+def test_batch_packing_shares_reads():
+    b = cases.edge_batch(seed=5)
+    assert b.n_slots > b.n_reads, "shared Read objects must be pooled once"
+    assert b.wi_slot_off[-1] == b.n_slots == len(b.slot_read)
+    assert (b.wi_n_good + b.wi_n_bad <= np.diff(b.wi_slot_off)).all()
+
+
+def test_slice_equals_offset_generation():
+    full = synth.make_batch(40, n_haps=4, n_reads=8, read_len=60, hap_len=120)
+    part = synth.make_batch(13, n_haps=4, n_reads=8, read_len=60, hap_len=120, window_offset=20)
+    sl = full.slice_windows(20, 33)
+    for k in ("hap_seq", "read_seq", "read_qual", "read_pos", "read_end", "read_mapq", "win_start", "win_end",
+              "hap_start", "hap_var_mask", "win_n_var"):
+        assert np.array_equal(getattr(part, k), getattr(sl, k)), k
+    assert shard_bounds(10, 4) == [0, 3, 6, 8, 10]
+
+
+def test_synth_shapes_match_config2_accounting():
+    b = synth.make_batch(3)
+    assert b.n_haps == 24 and b.n_reads == 192
+    assert synth.algorithmic_cells(b) == 3 * 8 * 64 * 150 * 16
+    assert synth.algorithmic_bytes(b) == 3 * 17496
+    v = synth.make_batch(5, read_len_range=(100, 250), hap_len_range=(200, 500))
+    lens = np.diff(v.read_seq_off)
+    assert lens.min() >= 100 and lens.max() <= 250
+    hl = np.diff(v.hap_seq_off)
+    assert (hl >= lens.max() + 16).all() and hl.max() <= 500

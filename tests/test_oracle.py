@@ -1,0 +1,157 @@
+"""CPU tests of the oracle: against the committed golden vectors (produced by the reference's own
+align.c / calign.pyx, see tests/golden/make_golden.py), against the compiled reference when
+oracle/_ref is present, and against hand-checkable known answers."""
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+
+from tests import cases
+
+
+def _unpack(off, data, i):
+    return data[off[i]:off[i + 1]].tobytes()
+
+
+def test_golden_align_ref(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "align_ref.npz"))
+    n = len(g["score"])
+    assert n >= 500
+    for i in range(n):
+        hap = _unpack(g["hap_off"], g["hap"], i)
+        go = _unpack(g["hap_off"], g["gap_open"], i)
+        read = _unpack(g["read_off"], g["read"], i)
+        qual = _unpack(g["read_off"], g["qual"], i)
+        assert oracle.band_align(hap, read, qual, go) == int(g["score"][i]), "golden case %d" % i
+
+
+def test_golden_calign_ref(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "calign_ref.npz"))
+    n = len(g["score"])
+    for i in range(n):
+        hap = _unpack(g["hap_off"], g["hap"], i)
+        read = _unpack(g["read_off"], g["read"], i)
+        qual = _unpack(g["read_off"], g["qual"], i)
+        s, _ = oracle.map_and_align(read, qual, int(g["read_start"][i]), int(g["hap_start"][i]), hap)
+        assert s == int(g["score"][i]), "golden case %d" % i
+
+
+def test_golden_window_restated(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "window_restated.npz"))
+    batch = cases.edge_batch(seed=5)
+    arrs, ll, sc, _ = oracle.population_run(batch)
+    assert np.array_equal(sc, g["score"])
+    np.testing.assert_allclose(ll, g["ll"], rtol=1e-12, atol=0)
+    for k in ("gl", "gof", "freq", "em_post", "var_phred", "hap_like"):
+        np.testing.assert_allclose(arrs[k], g[k], rtol=1e-9, atol=1e-300, err_msg=k)
+    assert np.array_equal(arrs["call"], g["call"])
+    assert np.array_equal(arrs["em_iters"], g["em_iters"])
+
+
+def test_vs_ref_alignc_fuzz(oracle):
+    if oracle.ref_align_lib() is None:
+        pytest.skip("oracle/_ref/libalign_ref.so not built (no reference checkout)")
+    rng = random.Random(101)
+    for i in range(1500):
+        hap, go, read, qual = cases.random_alignment_case(rng, i)
+        want = oracle.ref_fast_align(hap, read, qual, go, traceback=bool(i & 1))
+        assert oracle.band_align(hap, read, qual, go) == want, "case %d" % i
+
+
+def test_vs_ref_calign_fuzz(oracle):
+    cw = oracle.ref_calign()
+    if cw is None:
+        pytest.skip("oracle/_ref/calign not built (no reference checkout)")
+    rng = random.Random(102)
+    for i in range(800):
+        hap, read, qual, rs, hs = cases.random_mapping_case(rng, i)
+        go = oracle.gap_open(hap)
+        want = cw.map_and_align(read, qual, rs, hs, hap, go, 3, 2, 1, 0)
+        got, _ = oracle.map_and_align(read, qual, rs, hs, hap, go)
+        assert got == want, "case %d" % i
+
+
+def test_reference_kernel_inside_oracle_agrees(oracle):
+    """The 'reference' CPU baseline (oracle anchoring + align.c DP) equals the pure restatement."""
+    if not oracle.use_reference_kernel(True):
+        pytest.skip("oracle/_ref/libalign_ref.so not built")
+    try:
+        from platypus_b200 import synth
+        b = synth.make_batch(6)
+        ll_ref, sc_ref, _ = oracle.window_loglik(b)
+    finally:
+        oracle.use_reference_kernel(False)
+    ll, sc, _ = oracle.window_loglik(b)
+    assert np.array_equal(sc, sc_ref)
+    assert np.array_equal(ll, ll_ref)
+
+
+def test_known_answers(oracle):
+    """SURVEY §8c spot checks on the reference kernel: exact -> 0, one Q30 mismatch -> 30,
+    2 bp deletion -> 43 (= 40 + 3), 2 bp insertion -> 47 (= 40 + 2 + 3 + 2)."""
+    rng = random.Random(7)
+    hap = cases._rand_seq(rng, 80)
+    # avoid accidental homopolymers influencing the hand computation: constant gap-open 40
+    go = bytes([40] * 81)
+    for off in range(16):
+        read = hap[off:off + 50]
+        assert oracle.band_align(hap, read, bytes([30] * 50), go) == 0
+    read = bytearray(hap[8:58])
+    read[20] = ord("A") if read[20] != ord("A") else ord("C")
+    assert oracle.band_align(hap, bytes(read), bytes([30] * 50), go) == 30
+    assert oracle.band_align(hap, bytes(read), bytes([7] * 50), go) == 7
+    hap2 = b"ACGTTGCAAGGCTTAGCCATGATCGGATACCGTTAGCAATGCGTACGATTGCAGTCAGGCTAACGTTGACCATGCAAGT"
+    base = hap2[8:60]
+    dele = base[:25] + base[27:]           # read lacks 2 haplotype bases
+    assert oracle.band_align(hap2, dele, bytes([30] * len(dele)), bytes([40] * 90)) == 43
+    ins = base[:25] + b"TT" + base[25:48]  # read has 2 extra bases
+    assert oracle.band_align(hap2, ins, bytes([30] * len(ins)), bytes([40] * 90)) == 47
+
+
+def test_homopolymer_table_formula(oracle):
+    """chaplotype.pyx:64-67 evaluated; gap_open() of a run reproduces it."""
+    errs = [2.9e-5, 2.9e-5, 2.9e-5, 2.9e-5, 4.3e-5, 1.1e-4, 2.4e-4, 5.7e-4, 1.0e-3, 1.4e-3] + \
+           [1.4e-3 + 4.3e-4 * (n - 10) for n in range(11, 50)]
+    table = [int(33.5 + 10 * math.log((i + 1) * q) / math.log(0.1)) - 33 for i, q in enumerate(errs)]
+    assert len(table) == 49 and table[0] == 45 and table[-1] == 1
+    go = oracle.gap_open(b"C" + b"A" * 60 + b"G")
+    assert go[-1] == 0 and go[-2] == table[0]
+    # position of the last A has run 0, the one before run 1, ... saturating at 48
+    for k in range(60):
+        assert go[60 - k] == table[min(k, 48)]
+    assert go[0] == table[0]
+    # N never continues a run
+    go = oracle.gap_open(b"ANNNA")
+    assert list(go) == [table[0]] * 5 + [0]
+
+
+def test_hash_aliases(oracle):
+    """calign.pyx:61-76: A->1 C->3 G->2 T->0, N aliases G, case-insensitive."""
+    assert oracle.kmer_hash(b"AAAAAAA") == int("1" * 7, 4)
+    assert oracle.kmer_hash(b"ACGTACG") == int("1320132", 4)
+    assert oracle.kmer_hash(b"NNNNNNN") == oracle.kmer_hash(b"GGGGGGG")
+    assert oracle.kmer_hash(b"acgtacg") == oracle.kmer_hash(b"ACGTACG")
+
+
+def test_score_to_ll(oracle):
+    assert oracle.score_to_ll(0, 0) == -300.0
+    assert oracle.score_to_ll(1000000, 60) == -300.0
+    v = oracle.score_to_ll(30, 60)
+    assert abs(v - (-0.23025850929940459 * 30 + math.log(1 - 1e-6))) < 1e-12
+
+
+def test_genotype_mix_branches(oracle):
+    import ctypes as C
+    L = oracle.lib()
+    a = np.array([-1.0, -10.0, -2.0, -2.0005, 0.0], np.float64)
+    b = np.array([-5.0, -9.0, -2.5, -2.0, 0.0], np.float64)
+    gof = C.c_double()
+    v = L.plo_genotype_loglik(a.ctypes.data, b.ctypes.data, 5, 4, 0, C.byref(gof), None, None)
+    want = (math.log(0.5) + -1.0) + math.log(0.5 * (math.exp(-10) + math.exp(-9))) + \
+        math.log(0.5 * (math.exp(-2) + math.exp(-2.5))) + -2.0005 + 0.0
+    assert abs(v - want) < 1e-12
+    v_h = L.plo_genotype_loglik(a.ctypes.data, a.ctypes.data, 5, 4, 1, C.byref(gof), None, None)
+    assert abs(v_h - a.sum()) < 1e-12
+    assert abs(gof.value - (-10 * 0.43429448190325182 * a.sum() / 4)) < 1e-9
