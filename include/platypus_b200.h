@@ -253,6 +253,13 @@ typedef struct PlbRunStats {
 } PlbRunStats;
 int plb_last_stats(PlbContext* ctx, PlbRunStats* out);
 
+/* Per-kernel device times of the last plb_run_device / *_host call, measured with CUDA events on
+ * the context's stream (enable with plb_set_timing(ctx, 1) before the run; synchronises).
+ * Order: k_prep, k_anchor, k_general, k_dp, k_genotype, k_population; ms must hold 6 floats. */
+#define PLB_N_KERNELS 6
+int plb_set_timing(PlbContext* ctx, int on);
+int plb_kernel_times(PlbContext* ctx, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,10 @@ def declare(lib):
     lib.plb_run_device.restype = C.c_int
     lib.plb_last_stats.argtypes = [_p, P(PlbRunStats)]
     lib.plb_last_stats.restype = C.c_int
+    lib.plb_set_timing.argtypes = [_p, C.c_int]
+    lib.plb_set_timing.restype = C.c_int
+    lib.plb_kernel_times.argtypes = [_p, P(C.c_float)]
+    lib.plb_kernel_times.restype = C.c_int
     return lib
 
 
@@ -108,5 +112,6 @@ EXPORTED_SYMBOLS = [
     "plb_context_create", "plb_context_destroy", "plb_last_error", "plb_abi_version", "plb_launch_count",
     "plb_ll_offsets", "plb_validate", "plb_fast_align", "plb_align_batch_host", "plb_gap_open_host",
     "plb_window_loglik_host", "plb_population_run_host", "plb_batch_upload", "plb_batch_free",
-    "plb_run_device", "plb_last_stats",
+    "plb_run_device", "plb_last_stats", "plb_set_timing", "plb_kernel_times",
 ]
+KERNEL_NAMES = ["k_prep", "k_anchor", "k_general", "k_dp", "k_genotype", "k_population"]

@@ -51,6 +51,9 @@ struct PlbContext {
     Counters* d_ctr;
     Counters* h_ctr;            // pinned
     cudaEvent_t ev;
+    bool timing;
+    cudaEvent_t kev[PLB_N_KERNELS + 1];
+    bool kev_valid[PLB_N_KERNELS + 1];
 };
 
 struct PlbDeviceBatch {
@@ -104,6 +107,11 @@ extern "C" int plb_context_create(int device, void* stream, PlbContext** out) {
     CU(cudaMallocHost(&c->h_ctr, sizeof(Counters)));
     memset(c->h_ctr, 0, sizeof(Counters));
     CU(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
+    c->timing = false;
+    for (int i = 0; i <= PLB_N_KERNELS; ++i) {
+        CU(cudaEventCreate(&c->kev[i]));
+        c->kev_valid[i] = false;
+    }
     *out = c;
     return PLB_OK;
 }
@@ -116,6 +124,7 @@ extern "C" void plb_context_destroy(PlbContext* c) {
     cudaFree(c->d_ctr);
     cudaFreeHost(c->h_ctr);
     cudaEventDestroy(c->ev);
+    for (int i = 0; i <= PLB_N_KERNELS; ++i) cudaEventDestroy(c->kev[i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -636,10 +645,19 @@ extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOption
     CU(cudaMemsetAsync(db->q.count, 0, 4, st));
     CU(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), st));
 
+    auto mark = [&](int i) {
+        if (c->timing) {
+            cudaEventRecord(c->kev[i], st);
+            c->kev_valid[i] = true;
+        }
+    };
+    for (int i = 0; i <= PLB_N_KERNELS; ++i) c->kev_valid[i] = false;
+    mark(0);
     if (d.n_haps > 0) {
         k_prep<<<d.n_haps, 128, 0, st>>>(d);
         if ((rc = launch_check(c, "k_prep"))) return rc;
     }
+    mark(1);
     if (db->aplan.n_tiles > 0) {
         if (db->cnt16) {
             if ((rc = opt_in_smem(k_anchor<uint16_t>, db->a_smem))) return rc;
@@ -649,9 +667,11 @@ extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOption
             k_anchor<uint8_t><<<db->a_grid, kAnchorThreads, db->a_smem, st>>>(d, db->aplan, db->q, sp, c->d_ctr);
         }
         if ((rc = launch_check(c, "k_anchor"))) return rc;
+        mark(2);
         k_general<<<c->n_sm * 4, 128, 0, st>>>(d, db->q, sp);
         if ((rc = launch_check(c, "k_general"))) return rc;
     }
+    mark(3);
     double* ll = (llo && llo->ll) ? llo->ll : db->ll_scratch;
     int32_t* sc = llo ? llo->score : nullptr;
     if (db->dplan.n_tiles > 0) {
@@ -659,6 +679,7 @@ extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOption
         k_dp<kDpThreads><<<db->d_grid, kDpThreads, db->d_smem, st>>>(d, db->dplan, sp, ll, sc);
         if ((rc = launch_check(c, "k_dp"))) return rc;
     }
+    mark(4);
     if (pop) {
         if (!pop->gl) return set_err(PLB_ERR_ARG, "PlbPopulationOut.gl is required");
         PopOut po{pop->max_haps, pop->gl,   pop->gl_log_max, pop->gof,       pop->hap_like,
@@ -666,6 +687,7 @@ extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOption
         const int64_t nwi = (int64_t)d.n_windows * d.n_individuals;
         k_genotype<<<(unsigned)nwi, 64, 0, st>>>(d, ll, po);
         if ((rc = launch_check(c, "k_genotype"))) return rc;
+        mark(5);
         const int Hm = pop->max_haps;
         if (!pop->em_post && Hm != db->max_haps)
             return set_err(PLB_ERR_ARG, "em_post is NULL: max_haps must equal the batch maximum (%d)", db->max_haps);
@@ -677,6 +699,8 @@ extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOption
                                                     nthr_em);
         if ((rc = launch_check(c, "k_population"))) return rc;
     }
+    if (!pop) mark(5);
+    mark(6);
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     return PLB_OK;
 }
@@ -689,6 +713,23 @@ extern "C" int plb_last_stats(PlbContext* c, PlbRunStats* out) {
     out->n_pairs_scored = (int64_t)c->h_ctr->n_scored;
     out->n_dp = (int64_t)c->h_ctr->n_dp;
     out->cells = (int64_t)c->h_ctr->cells;
+    return PLB_OK;
+}
+
+extern "C" int plb_set_timing(PlbContext* c, int on) {
+    if (!c) return set_err(PLB_ERR_ARG, "NULL argument");
+    c->timing = on != 0;
+    return PLB_OK;
+}
+
+extern "C" int plb_kernel_times(PlbContext* c, float* ms) {
+    if (!c || !ms) return set_err(PLB_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < PLB_N_KERNELS; ++i) {
+        ms[i] = 0.f;
+        if (c->kev_valid[i] && c->kev_valid[i + 1]) CU(cudaEventElapsedTime(&ms[i], c->kev[i], c->kev[i + 1]));
+    }
     return PLB_OK;
 }
 

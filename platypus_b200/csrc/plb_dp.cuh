@@ -45,7 +45,13 @@ constexpr int kScoreBig = 1 << 28;
 PLB_HD u32 vadd2(u32 a, u32 b) { return __vadd2(a, b); }
 PLB_HD u32 vmin2(u32 a, u32 b) { return __vmins2(a, b); }
 PLB_HD u32 vaddmin2(u32 a, u32 b, u32 c) { return __viaddmin_s16x2(a, b, c); }  // min(a+b, c)
-PLB_HD u32 prmt(u32 a, u32 b, u32 s) { return __byte_perm(a, b, s); }
+// PTX prmt, default mode: selector nibble bit 3 replicates the sign bit of the selected byte
+// (used to produce zero bytes); __byte_perm() masks that bit off, so go through inline PTX.
+PLB_HD u32 prmt(u32 a, u32 b, u32 s) {
+    u32 d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
+    return d;
+}
 #else
 PLB_HD u32 vadd2(u32 a, u32 b) {
     return ((a + b) & 0xFFFFu) | ((((a >> 16) + (b >> 16)) & 0xFFFFu) << 16);

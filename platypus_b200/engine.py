@@ -72,6 +72,15 @@ class Engine:
         _check(self.lib, self.lib.plb_last_stats(self.ctx, C.byref(st)))
         return st.as_dict()
 
+    def set_timing(self, on=True):
+        _check(self.lib, self.lib.plb_set_timing(self.ctx, 1 if on else 0))
+
+    def kernel_times(self):
+        """Device time (ms) of each kernel of the last run, from CUDA events on the context stream."""
+        ms = (C.c_float * 6)()
+        _check(self.lib, self.lib.plb_kernel_times(self.ctx, ms))
+        return dict(zip(_abi.KERNEL_NAMES, [float(x) for x in ms]))
+
     # ---- S1 ---------------------------------------------------------------------------------
     def fast_align(self, seq1: bytes, seq2: bytes, qual2: bytes, gap_open: bytes, gapextend=3, nucprior=2):
         """fastAlignmentRoutine(seq1, seq2, qual2, len1, len2, gapextend, nucprior, localgapopen, NULL, NULL, NULL)
