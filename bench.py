@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""
+bench.py — headline benchmark of the read-vs-haplotype likelihood path (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric: pair-HMM GCUPS = 10^9 algorithmic band cells per second, 16 * readLen cells per scored
+(read, haplotype) pair.  Workload at every N: BASELINE config 2 per GPU (weak
+scaling) — synth-v1, 10,000 windows x 8 haplotypes x 64 reads, 150 bp reads x 250 bp haplotypes.
+A "step" is one pass of the whole path (anchor voting, band alignment, LL, genotype likelihoods,
+EM, posteriors) over that batch.
+
+  value     device-resident pass: inputs already in HBM, timed with CUDA events on the launch stream
+  e2e       the same pass through the C-ABI host entry point plb_population_run_host with pinned HOST
+            buffers: H2D of all inputs and D2H of all population outputs inside the timed region
+  roofline  k_dp (the dominant kernel): algorithmic bytes per launch / mean launch duration measured
+            with CUDA events inside the timed region, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle with the reference's own align.c for the band alignment
+            (oracle/_ref, kind "reference") on all host cores over a bounded sample of the workload
+
+--impl reference times that CPU path alone (the reference has no GPU implementation).
+Nothing here reads /root/reference at run time.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WINDOWS_PER_GPU = 10000
+N_HAPS, N_READS, READ_LEN, HAP_LEN = 8, 64, 150, 250
+CPU_SAMPLE_WINDOWS = 2000
+METRIC = "pair_hmm_gcups"
+UNIT = "GCUPS"
+
+
+def workload_config(n_gpus, windows):
+    return {
+        "workload": "synth-v1 config2: %d windows x %d haplotypes x %d reads per GPU, %d bp reads x %d bp haplotypes"
+                    % (windows, N_HAPS, N_READS, READ_LEN, HAP_LEN),
+        "windows_per_gpu": windows, "n_gpus": n_gpus, "haplotypes": N_HAPS, "reads": N_READS,
+        "read_len": READ_LEN, "hap_len": HAP_LEN, "individuals": 1,
+        "cells_per_pair": "16*readLen (algorithmic band cells, SURVEY 8d)",
+        "l2": "inputs+outputs of one step (~310 MB per GPU) exceed the 126 MB L2; no explicit flush",
+        "parallelism": "windows sharded over %d GPU(s), one process per GPU%s" %
+                       (n_gpus, ", NCCL all-gather of genotype likelihoods" if n_gpus > 1 else ""),
+    }
+
+
+def make_workload(rank, windows):
+    from platypus_b200 import synth
+    cache = "/tmp/plb_synth_v1_c2_w%d_off%d.npz" % (windows, rank * windows)
+    t0 = time.time()
+    b = synth.make_batch_parallel(windows, window_offset=rank * windows, n_haps=N_HAPS, n_reads=N_READS,
+                                  read_len=READ_LEN, hap_len=HAP_LEN)
+    del cache
+    return b, time.time() - t0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(batch, n_windows, threads, steps=1, warmup=0):
+    """Times the CPU path (oracle anchoring/LL/GL/EM + reference align.c when oracle/_ref exists)
+    over the first n_windows windows.  Returns (gcups, kind, seconds per step, cells)."""
+    from oracle import oracle as O
+    from platypus_b200 import synth
+    sub = batch.slice_windows(0, min(n_windows, batch.n_windows))
+    kind = "reference" if O.use_reference_kernel(True, traceback=True) else "port"
+    cells = synth.algorithmic_cells(sub)
+    for _ in range(warmup):
+        O.population_run(sub, n_threads=threads, want_ll=False)
+    t0 = time.perf_counter()
+    for _ in range(max(1, steps)):
+        O.population_run(sub, n_threads=threads, want_ll=False)
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    O.use_reference_kernel(False)
+    return cells / dt / 1e9, kind, dt, cells, sub.n_windows
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    windows = args.windows
+    batch, _ = make_workload(0, min(windows, CPU_SAMPLE_WINDOWS))
+    cores = os.cpu_count() or 1
+    gcups, kind, dt, cells, nw = cpu_reference_run(batch, CPU_SAMPLE_WINDOWS, cores, steps=args.steps, warmup=args.warmup)
+    sample = "first %d windows of the config-2 workload per step (%d pairs, %.3g cells), %d OpenMP threads, " \
+             "band alignment = %s" % (nw, nw * N_HAPS * N_READS, cells, cores,
+                                      "unmodified reference align.c with traceback (oracle/_ref)" if kind == "reference"
+                                      else "oracle restatement")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gcups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int16 scores / f64 likelihoods", "data": "synthetic (synth-v1, seed 20261017)",
+        "config": workload_config(args.gpus, windows),
+        "cpu_baseline": {"value": gcups, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": gcups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def pin(a):
+    import torch
+    if a is None:
+        return None
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from platypus_b200 import _abi, synth
+    from platypus_b200.engine import Engine
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    windows = args.windows
+    batch, gen_s = make_workload(rank, windows)
+    cells = synth.algorithmic_cells(batch)
+    alg_bytes = synth.algorithmic_bytes(batch)
+    W, nI, Hm = batch.n_windows, batch.n_individuals, batch.max_haps()
+    Gm = Hm * (Hm + 1) // 2
+    V = max(batch.max_variants, 1)
+
+    stream = torch.cuda.Stream(device=dev)
+    eng = Engine(local_rank, stream=stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        handle = eng.upload(batch)
+        out = {
+            "gl": torch.zeros((W, nI, Gm), dtype=torch.float64, device=dev),
+            "gl_log_max": torch.zeros((W, nI), dtype=torch.float64, device=dev),
+            "gof": torch.zeros((W, Gm, nI), dtype=torch.float64, device=dev),
+            "hap_like": torch.zeros((W, nI, Hm), dtype=torch.float64, device=dev),
+            "freq": torch.zeros((W, Hm), dtype=torch.float64, device=dev),
+            "em_post": torch.zeros((W, nI, Gm), dtype=torch.float64, device=dev),
+            "call": torch.zeros((W, nI), dtype=torch.int32, device=dev),
+            "var_phred": torch.zeros((W, V), dtype=torch.float64, device=dev),
+            "em_iters": torch.zeros((W,), dtype=torch.int32, device=dev),
+        }
+        n_pairs = int(batch.ll_offsets()[-1])
+        ll = torch.zeros((n_pairs,), dtype=torch.float64, device=dev)
+        ptrs = {k: v.data_ptr() for k, v in out.items()}
+        ptrs["max_haps"] = Hm
+        gl_all = torch.zeros((world, W, nI, Gm), dtype=torch.float64, device=dev) if world > 1 else None
+
+        def step():
+            eng.run_device(handle, ptrs, ll_ptr=ll.data_ptr())
+            if world > 1:  # the one collective of the path: gather per-window genotype likelihoods
+                dist.all_gather_into_tensor(gl_all, out["gl"])
+
+        for _ in range(max(args.warmup, 3)):
+            step()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = eng.launch_count
+        eng.set_timing(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms_total = e0.elapsed_time(e1)
+        launches = eng.launch_count - launches0 + (args.steps if world > 1 else 0)
+        ktimes, n_timed = eng.kernel_times()
+        eng.set_timing(False)
+        clocks = sampler.stop() if rank == 0 else None
+        stats = eng.last_stats()
+        assert stats["cells"] == cells, (stats, cells)
+
+        # ---- e2e: C-ABI host entry point, pinned host buffers, copies inside the timed region ----
+        pinned = {}
+        hb = type(batch)(**{f: (pin(getattr(batch, f)).numpy() if isinstance(getattr(batch, f), np.ndarray) else getattr(batch, f))
+                            for f in batch.__dataclass_fields__ if f != "_keep"})
+        host_out = {"max_haps": Hm}
+        for k, v in out.items():
+            pinned[k] = torch.zeros(v.shape, dtype=v.dtype).pin_memory()
+            host_out[k] = pinned[k].numpy()
+        h2d = hb.input_nbytes()
+        d2h = sum(int(v.numel() * v.element_size()) for v in pinned.values())
+        for _ in range(2):
+            eng.population_run(hb, out=host_out)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(e2e_steps):
+            eng.population_run(hb, out=host_out)
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        # parity guard: the host path and the device path must agree bit for bit
+        assert np.array_equal(host_out["gl"], out["gl"].cpu().numpy())
+
+    ms_step = ms_total / args.steps
+    t_max = torch.tensor([ms_step, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(cells), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_step, e2e_ms = float(t_max[0]), float(t_max[1])
+    total_cells, total_launches = float(tot[0]), int(tot[1])
+    if rank != 0:
+        eng.free(handle)
+        return
+    value = total_cells / (ms_step * 1e-3) / 1e9
+    e2e_value = total_cells / (e2e_ms * 1e-3) / 1e9
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("k_dp_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    kdp_ms = ktimes["k_dp"]
+    achieved = alg_bytes / (kdp_ms * 1e-3) / 1e9 if kdp_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_dp", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kdp_ms, "launches_averaged": n_timed,
+                "kernel_ms_all": ktimes,
+                "note": "integer-issue bound by construction (0.014 B/cell); see DESIGN.md for the issue-rate roofline"}
+
+    cpu = None
+    if world == 1:
+        cores = os.cpu_count() or 1
+        g, kind, dt, ccells, nw = cpu_reference_run(batch, CPU_SAMPLE_WINDOWS, cores, steps=1, warmup=0)
+        g1, _, dt1, c1, nw1 = cpu_reference_run(batch, max(64, CPU_SAMPLE_WINDOWS // cores), 1, steps=1, warmup=0)
+        cpu = {"value": g, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "first %d windows (%.3g cells) in %.2f s on %d threads; band alignment = %s; "
+                         "single-thread: %.3f GCUPS on %d windows" %
+                         (nw, ccells, dt, cores, "unmodified reference align.c with traceback (oracle/_ref)"
+                          if kind == "reference" else "oracle restatement", g1, nw1),
+               "single_thread_value": g1}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16 scores / f64 likelihoods", "data": "synthetic (synth-v1, seed 20261017)",
+        "config": workload_config(world, windows),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms, "api": "plb_population_run_host (pinned host buffers)"},
+        "gpu_launches": total_launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "stats": stats, "gen_seconds": gen_s,
+    }
+    print(json.dumps(line), flush=True)
+    eng.free(handle)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--windows", type=int, default=WINDOWS_PER_GPU, help="windows per GPU (default: config 2)")
+    args = ap.parse_args()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -253,9 +253,11 @@ typedef struct PlbRunStats {
 } PlbRunStats;
 int plb_last_stats(PlbContext* ctx, PlbRunStats* out);
 
-/* Per-kernel device times of the last plb_run_device / *_host call, measured with CUDA events on
- * the context's stream (enable with plb_set_timing(ctx, 1) before the run; synchronises).
- * Order: k_prep, k_anchor, k_general, k_dp, k_genotype, k_population; ms must hold 6 floats. */
+/* Per-kernel device times, measured with CUDA events recorded on the context's stream around every
+ * kernel of plb_run_device / *_host.  plb_set_timing(ctx, 1) starts (and resets) recording;
+ * plb_kernel_times synchronises and returns the number of runs averaged (up to the last 64) with
+ * the mean milliseconds per run in ms[0..5], order: k_prep, k_anchor, k_general, k_dp, k_genotype,
+ * k_population. */
 #define PLB_N_KERNELS 6
 int plb_set_timing(PlbContext* ctx, int on);
 int plb_kernel_times(PlbContext* ctx, float* ms);

@@ -214,11 +214,7 @@ class WindowBatch:
         rlen = np.diff(self.read_seq_off)[used]
         roff = np.zeros(len(used) + 1, np.int64)
         np.cumsum(rlen, out=roff[1:])
-        if len(used):
-            idx = np.concatenate([np.arange(self.read_seq_off[r], self.read_seq_off[r + 1]) for r in used]) \
-                if len(used) < 4096 else _gather_index(self.read_seq_off, used)
-        else:
-            idx = np.zeros(0, np.int64)
+        idx = _gather_index(self.read_seq_off, used) if len(used) else np.zeros(0, np.int64)
         hb0, hb1 = int(self.hap_seq_off[h0]), int(self.hap_seq_off[h1])
         return WindowBatch(
             n_windows=hi - lo, n_individuals=nI,
@@ -238,6 +234,48 @@ class WindowBatch:
             hap_var_mask=None if self.hap_var_mask is None else self.hap_var_mask[h0:h1].copy(),
             var_prior=None if self.var_prior is None else self.var_prior[lo:hi].copy(),
         )
+
+
+def concat_batches(parts: Sequence["WindowBatch"]) -> "WindowBatch":
+    """Concatenate batches window-wise (read pools are concatenated and re-indexed)."""
+    parts = [p for p in parts if p.n_windows > 0]
+    assert parts, "nothing to concatenate"
+    nI = parts[0].n_individuals
+    assert all(p.n_individuals == nI for p in parts)
+
+    def cat_off(name, dt):
+        out, base = [np.zeros(1, dt)], 0
+        for p in parts:
+            a = getattr(p, name)
+            out.append(a[1:].astype(dt) + base)
+            base += int(a[-1])
+        return np.concatenate(out)
+
+    def cat(name):
+        return np.concatenate([getattr(p, name) for p in parts])
+
+    read_base = np.cumsum([0] + [p.n_reads for p in parts])
+    b = WindowBatch(
+        n_windows=sum(p.n_windows for p in parts), n_individuals=nI,
+        win_hap_off=cat_off("win_hap_off", np.int32), win_start=cat("win_start"), win_end=cat("win_end"),
+        hap_start=cat("hap_start"), hap_seq_off=cat_off("hap_seq_off", np.int64), hap_seq=cat("hap_seq"),
+        wi_slot_off=cat_off("wi_slot_off", np.int64), wi_n_good=cat("wi_n_good"), wi_n_bad=cat("wi_n_bad"),
+        slot_read=np.concatenate([p.slot_read + np.int32(read_base[i]) for i, p in enumerate(parts)]).astype(np.int32),
+        read_seq_off=cat_off("read_seq_off", np.int64), read_seq=cat("read_seq"), read_qual=cat("read_qual"),
+        read_pos=cat("read_pos"), read_end=cat("read_end"), read_mapq=cat("read_mapq"), read_qcfail=cat("read_qcfail"),
+    )
+    if all(p.win_n_var is not None for p in parts):
+        mv = max(p.max_variants for p in parts)
+        b.max_variants = mv
+        b.win_n_var = cat("win_n_var")
+        b.hap_var_mask = cat("hap_var_mask")
+        pri = np.zeros((b.n_windows, mv), np.float64)
+        o = 0
+        for p in parts:
+            pri[o:o + p.n_windows, :p.max_variants] = p.var_prior
+            o += p.n_windows
+        b.var_prior = pri
+    return b
 
 
 def _gather_index(off, used):

@@ -35,6 +35,8 @@ static int set_err(int code, const char* fmt, ...) {
                            __LINE__);                                                              \
     } while (0)
 
+constexpr int kTimingRing = 64;
+
 struct Block {
     void* p;
     size_t cap;
@@ -52,8 +54,8 @@ struct PlbContext {
     Counters* h_ctr;            // pinned
     cudaEvent_t ev;
     bool timing;
-    cudaEvent_t kev[PLB_N_KERNELS + 1];
-    bool kev_valid[PLB_N_KERNELS + 1];
+    int n_timed;                                        // runs recorded since plb_set_timing(1)
+    cudaEvent_t kev[kTimingRing][PLB_N_KERNELS + 1];    // ring of per-run event sets
 };
 
 struct PlbDeviceBatch {
@@ -64,7 +66,6 @@ struct PlbDeviceBatch {
     DpPlan dplan;
     size_t a_smem, d_smem;
     int a_grid, d_grid;
-    bool cnt16;
     Queue q;
     double* ll_scratch;
     double* em_scratch;      // [W][nInd][Gmax_plan]
@@ -108,10 +109,9 @@ extern "C" int plb_context_create(int device, void* stream, PlbContext** out) {
     memset(c->h_ctr, 0, sizeof(Counters));
     CU(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
     c->timing = false;
-    for (int i = 0; i <= PLB_N_KERNELS; ++i) {
-        CU(cudaEventCreate(&c->kev[i]));
-        c->kev_valid[i] = false;
-    }
+    c->n_timed = 0;
+    for (int r = 0; r < kTimingRing; ++r)
+        for (int i = 0; i <= PLB_N_KERNELS; ++i) CU(cudaEventCreate(&c->kev[r][i]));
     *out = c;
     return PLB_OK;
 }
@@ -124,7 +124,8 @@ extern "C" void plb_context_destroy(PlbContext* c) {
     cudaFree(c->d_ctr);
     cudaFreeHost(c->h_ctr);
     cudaEventDestroy(c->ev);
-    for (int i = 0; i <= PLB_N_KERNELS; ++i) cudaEventDestroy(c->kev[i]);
+    for (int r = 0; r < kTimingRing; ++r)
+        for (int i = 0; i <= PLB_N_KERNELS; ++i) cudaEventDestroy(c->kev[r][i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -261,10 +262,11 @@ struct TileLists {
     std::vector<Tile> a, d;
 };
 
-constexpr size_t kAnchorTabBudget = 40 * 1024;   // tables + chains of one haplotype group
-constexpr size_t kAnchorHashBudget = 24 * 1024;  // read hashes of one tile
-constexpr size_t kAnchorCntBudget = 100 * 1024;  // vote arrays in shared memory if they fit
+constexpr size_t kAnchorNextBudget = 24 * 1024;  // position chains of one haplotype group
+constexpr size_t kAnchorHashBudget = 24 * 1024;  // read 7-mer ids of one tile
+constexpr size_t kAnchorCntBudget = 48 * 1024;   // per-warp vote arrays of the exact (tie) path
 constexpr int kAnchorMaxSlots = 256;
+constexpr int kAnchorMaxPairs = 4096;
 constexpr size_t kDpRecBudget = 40 * 1024;
 constexpr size_t kDpProfBudget = 56 * 1024;
 constexpr int kDpMaxSlots = 128;
@@ -311,45 +313,52 @@ static int plan_tiles(const PlbWindowBatch* hb, TileLists& tl, AnchorPlan& ap, D
         std::vector<std::pair<int, int>> groups;
         {
             int g0 = h0;
-            size_t bytes = 0;
-            int tw = 0, nh_ = 0;
+            size_t next_bytes = 0;
             for (int h = h0; h < h1; ++h) {
                 const int len = (int)(hb->hap_seq_off[h + 1] - hb->hap_seq_off[h]);
                 max_hap = std::max(max_hap, len);
-                const size_t need = ((size_t)4 << tab_bits(len)) + 2 * (size_t)((len + 2) & ~1);
-                if (h > g0 && (bytes + need > kAnchorTabBudget || h - g0 >= 64)) {
+                const size_t need = 2 * (size_t)((len + 2) & ~1);
+                if (h > g0 && (next_bytes + need > kAnchorNextBudget || h - g0 >= 64)) {
                     groups.push_back({g0, h});
                     g0 = h;
-                    bytes = 0;
+                    next_bytes = 0;
                 }
-                bytes += need;
+                next_bytes += need;
             }
             groups.push_back({g0, h1});
             for (auto& g : groups) {
-                tw = 0;
-                nh_ = 0;
+                int nh_ = 0, sum_nk = 0;
                 for (int h = g.first; h < g.second; ++h) {
                     const int len = (int)(hb->hap_seq_off[h + 1] - hb->hap_seq_off[h]);
-                    tw += 1 << tab_bits(len);
                     nh_ += (len + 2) & ~1;
+                    sum_nk += std::max(0, len - kKmer);
                 }
-                ap.tab_words = std::max(ap.tab_words, tw);
+                int bits = 6;
+                while ((1 << bits) < 2 * sum_nk && bits < 14) ++bits;
+                ap.tab_bits = std::max(ap.tab_bits, bits);
                 ap.next_halfs = std::max(ap.next_halfs, nh_);
                 ap.max_group = std::max(ap.max_group, g.second - g.first);
+                ap.heads_halfs = std::max(ap.heads_halfs, std::min(kHashSize, sum_nk) + 1);
             }
         }
         {
+            int maxg = 1;
+            for (auto& g : groups) maxg = std::max(maxg, g.second - g.first);
             int64_t c0 = s0;
             size_t halfs = 0;
             auto flush = [&](int64_t c1) {
                 if (c1 <= c0) return;
-                for (auto& g : groups) tl.a.push_back(Tile{w, g.first, g.second, c0, c1});
+                for (auto& g : groups) {
+                    tl.a.push_back(Tile{w, g.first, g.second, c0, c1});
+                    ap.max_pairs = std::max<int>(ap.max_pairs, (int)(c1 - c0) * (g.second - g.first));
+                }
                 ap.max_slots = std::max<int>(ap.max_slots, (int)(c1 - c0));
-                ap.rhash_halfs = std::max<int>(ap.rhash_halfs, (int)halfs);
+                ap.rid_halfs = std::max<int>(ap.rid_halfs, (int)halfs);
             };
             for (int64_t s = s0; s < s1; ++s) {
-                const int nk = std::max(0, slot_len[(size_t)(s - s0)] - kKmer);
-                if (s > c0 && (2 * (halfs + nk) > kAnchorHashBudget || s - c0 >= kAnchorMaxSlots)) {
+                const int nk = (std::max(0, slot_len[(size_t)(s - s0)] - kKmer) + 7) & ~7;
+                if (s > c0 && (2 * (halfs + nk) > kAnchorHashBudget || s - c0 >= kAnchorMaxSlots ||
+                               (s - c0 + 1) * maxg > kAnchorMaxPairs)) {
                     flush(s);
                     c0 = s;
                     halfs = 0;
@@ -457,18 +466,25 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
     db->max_haps = max_H;
 
     // anchor launch shape
-    db->cnt16 = (max_read - kKmer) > 255;
-    const size_t csz = db->cnt16 ? 2 : 1;
-    db->aplan.cnt_stride = ((max_hap + max_read) + 15) & ~15;
-    const size_t cnt_bytes = (size_t)kAnchorThreads * db->aplan.cnt_stride * csz;
-    size_t a_fixed = (size_t)db->aplan.tab_words * 4 + (size_t)db->aplan.next_halfs * 2 +
-                     (size_t)db->aplan.rhash_halfs * 2 + 16 + (size_t)db->aplan.max_slots * sizeof(SlotInfo) +
-                     (size_t)db->aplan.max_group * 16 + 16;
-    db->aplan.cnt_in_smem = (cnt_bytes <= kAnchorCntBudget && a_fixed + cnt_bytes + 1024 <= (size_t)c->smem_optin) ? 1 : 0;
-    db->a_smem = a_fixed + (db->aplan.cnt_in_smem ? cnt_bytes : 0);
+    {
+        AnchorPlan& ap = db->aplan;
+        ap.max_pairs = (ap.max_pairs + 3) & ~3;
+        ap.rid_halfs = (ap.rid_halfs + 7) & ~7;
+        ap.next_halfs = (ap.next_halfs + 7) & ~7;
+        ap.heads_halfs = std::max(ap.heads_halfs, 4096);
+        ap.heads_halfs = (ap.heads_halfs + 7) & ~7;
+        ap.tab_bits = std::max(ap.tab_bits, 6);
+        ap.cnt_words = (((max_hap + max_read + 2) >> 1) + 3) & ~3;
+        const int nwarps = kAnchorThreads / 32;
+        ap.n_cnt = (int)std::max<size_t>(1, std::min<size_t>(nwarps, kAnchorCntBudget / ((size_t)ap.cnt_words * 4)));
+        db->a_smem = ((size_t)4 << ap.tab_bits) + (size_t)ap.n_cnt * ap.cnt_words * 4 + (size_t)ap.max_pairs * 4 +
+                     (size_t)ap.rid_halfs * 2 + (size_t)ap.next_halfs * 2 + (size_t)ap.heads_halfs * 2 + 16 +
+                     (size_t)ap.max_slots * sizeof(SlotInfo) + (size_t)ap.max_group * 8 + 16;
+    }
     if (db->a_smem + 1024 > (size_t)c->smem_optin) {
+        size_t need = db->a_smem;
         delete db;
-        return set_err(PLB_ERR_SHAPE, "anchor tile needs %zu bytes of shared memory", db->a_smem);
+        return set_err(PLB_ERR_SHAPE, "anchor tile needs %zu bytes of shared memory", need);
     }
     int a_occ = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (db->a_smem + 1024)));
     db->a_grid = std::max(1, std::min(db->aplan.n_tiles, c->n_sm * a_occ));
@@ -477,8 +493,9 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
                  (size_t)db->dplan.max_slots * sizeof(DpSlot) + (size_t)db->dplan.max_group * 4 +
                  (size_t)db->dplan.max_pairs * 12 + 64;
     if (db->d_smem + 1024 > (size_t)c->smem_optin) {
+        size_t need = db->d_smem;
         delete db;
-        return set_err(PLB_ERR_SHAPE, "dp tile needs %zu bytes of shared memory", db->d_smem);
+        return set_err(PLB_ERR_SHAPE, "dp tile needs %zu bytes of shared memory", need);
     }
     int d_occ = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (db->d_smem + 1024)));
     db->d_grid = std::max(1, std::min(db->dplan.n_tiles, c->n_sm * d_occ));
@@ -505,7 +522,6 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
     const size_t o_atiles = L.take(tl.a.size() * sizeof(Tile)), o_dtiles = L.take(tl.d.size() * sizeof(Tile));
     const int qcap = (int)std::min<int64_t>(std::max<int64_t>(4096, n_pairs / 2), 1 << 26);
     const size_t o_q = L.take((size_t)qcap * sizeof(QueueEntry)), o_qcount = L.take(64);
-    const size_t o_cntg = L.take(db->aplan.cnt_in_smem ? 0 : (size_t)db->a_grid * kAnchorThreads * db->aplan.cnt_stride * csz);
     const size_t o_ll = L.take((size_t)n_pairs * 8);
     const int Gp = max_H * (max_H + 1) / 2;
     db->em_scratch_elems = (size_t)W * nInd * Gp;
@@ -555,7 +571,6 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
     d.score = at<int32_t>(B, o_score);
     db->aplan.tiles = at<Tile>(B, o_atiles);
     db->dplan.tiles = at<Tile>(B, o_dtiles);
-    db->aplan.cnt_global = db->aplan.cnt_in_smem ? nullptr : at<uint8_t>(B, o_cntg);
     db->q.e = at<QueueEntry>(B, o_q);
     db->q.count = at<int32_t>(B, o_qcount);
     db->q.cap = qcap;
@@ -645,13 +660,10 @@ extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOption
     CU(cudaMemsetAsync(db->q.count, 0, 4, st));
     CU(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), st));
 
+    const int tslot = c->n_timed % kTimingRing;
     auto mark = [&](int i) {
-        if (c->timing) {
-            cudaEventRecord(c->kev[i], st);
-            c->kev_valid[i] = true;
-        }
+        if (c->timing) cudaEventRecord(c->kev[tslot][i], st);
     };
-    for (int i = 0; i <= PLB_N_KERNELS; ++i) c->kev_valid[i] = false;
     mark(0);
     if (d.n_haps > 0) {
         k_prep<<<d.n_haps, 128, 0, st>>>(d);
@@ -659,13 +671,8 @@ extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOption
     }
     mark(1);
     if (db->aplan.n_tiles > 0) {
-        if (db->cnt16) {
-            if ((rc = opt_in_smem(k_anchor<uint16_t>, db->a_smem))) return rc;
-            k_anchor<uint16_t><<<db->a_grid, kAnchorThreads, db->a_smem, st>>>(d, db->aplan, db->q, sp, c->d_ctr);
-        } else {
-            if ((rc = opt_in_smem(k_anchor<uint8_t>, db->a_smem))) return rc;
-            k_anchor<uint8_t><<<db->a_grid, kAnchorThreads, db->a_smem, st>>>(d, db->aplan, db->q, sp, c->d_ctr);
-        }
+        if ((rc = opt_in_smem(k_anchor, db->a_smem))) return rc;
+        k_anchor<<<db->a_grid, kAnchorThreads, db->a_smem, st>>>(d, db->aplan, db->q, sp, c->d_ctr);
         if ((rc = launch_check(c, "k_anchor"))) return rc;
         mark(2);
         k_general<<<c->n_sm * 4, 128, 0, st>>>(d, db->q, sp);
@@ -701,6 +708,7 @@ extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOption
     }
     if (!pop) mark(5);
     mark(6);
+    if (c->timing) c->n_timed++;
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     return PLB_OK;
 }
@@ -719,6 +727,7 @@ extern "C" int plb_last_stats(PlbContext* c, PlbRunStats* out) {
 extern "C" int plb_set_timing(PlbContext* c, int on) {
     if (!c) return set_err(PLB_ERR_ARG, "NULL argument");
     c->timing = on != 0;
+    c->n_timed = 0;
     return PLB_OK;
 }
 
@@ -726,11 +735,17 @@ extern "C" int plb_kernel_times(PlbContext* c, float* ms) {
     if (!c || !ms) return set_err(PLB_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    const int n = c->n_timed < kTimingRing ? c->n_timed : kTimingRing;
     for (int i = 0; i < PLB_N_KERNELS; ++i) {
-        ms[i] = 0.f;
-        if (c->kev_valid[i] && c->kev_valid[i + 1]) CU(cudaEventElapsedTime(&ms[i], c->kev[i], c->kev[i + 1]));
+        double sum = 0.0;
+        for (int r = 0; r < n; ++r) {
+            float t = 0.f;
+            CU(cudaEventElapsedTime(&t, c->kev[r][i], c->kev[r][i + 1]));
+            sum += t;
+        }
+        ms[i] = n ? (float)(sum / n) : 0.f;
     }
-    return PLB_OK;
+    return n;
 }
 
 // ---- host-buffer entry points --------------------------------------------------------------------

@@ -151,26 +151,41 @@ __global__ void __launch_bounds__(128) k_prep(DevBatch b) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_anchor
+// k_anchor — anchor voting (calign.pyx:206-267) for every (read, haplotype) pair of a tile.
+//
+// The reference keeps, per haplotype, a 16384-entry hash table plus chains, and per pair a vote
+// array of hapLen+readLen counters that it clears, fills and scans.  Here:
+//   * one open-addressed table per TILE maps the 14-bit 7-mer hash to a dense id over the union of
+//     the group's haplotype 7-mers; each read 7-mer is translated to its id ONCE (s_rid) and
+//     reused for every haplotype;
+//   * per haplotype, head[id] / next[pos] chains give the positions carrying that 7-mer (the
+//     reference's hash_table / next_array, calign.pyx:94-124);
+//   * votes are not stored: a Boyer-Moore pass finds the only offset that can hold a strict
+//     majority of the votes and a second pass counts it exactly.  A strict majority is the unique
+//     maximum, i.e. exactly the single candidate the reference would align (ties impossible).
+//   * pairs without a strict majority (split votes, repeats, unrelated reads) go to a per-tile
+//     list and are re-voted by a whole warp with a real counter array, reproducing the tied-maximum
+//     scan of calign.pyx:222-247.
 // ---------------------------------------------------------------------------------------------
 struct AnchorPlan {
     const Tile* tiles;
     int32_t n_tiles;
     int32_t max_slots;      // slots per tile upper bound
     int32_t max_group;      // haplotypes per tile upper bound
-    int32_t tab_words;      // smem u32 words for all tables of a group
-    int32_t next_halfs;     // smem u16 entries for all next arrays of a group
-    int32_t rhash_halfs;    // smem u16 entries for read hashes of a tile
-    int32_t cnt_stride;     // count-array entries per thread (max hapLen + readLen, rounded to 16)
-    int32_t cnt_in_smem;    // 1: count arrays live in shared memory, 0: in cnt_global
-    uint8_t* cnt_global;    // [gridDim.x * blockDim.x * cnt_stride * sizeof(CntT)]
+    int32_t max_pairs;      // slots*haplotypes per tile upper bound
+    int32_t tab_bits;       // log2(slots) of the union 7-mer table
+    int32_t next_halfs;     // u16 entries for all next arrays of a group
+    int32_t rid_halfs;      // u16 entries for the read 7-mer ids of a tile
+    int32_t heads_halfs;    // u16 entries of the head area (>= largest union size + 1)
+    int32_t cnt_words;      // u32 words of one warp's counter array (2 counters per word)
+    int32_t n_cnt;          // counter arrays available in shared memory (>= 1)
 };
 
 struct SlotInfo {
     int32_t read;     // read pool index
     int32_t len;      // read length
     int32_t pos;      // read.pos
-    int32_t hoff;     // offset into the rhash area
+    int32_t hoff;     // offset into the read-id area
     int32_t flags;    // bit0 = LL forced to 0 (QC fail / overlap < 7)
 };
 
@@ -180,25 +195,73 @@ __device__ __forceinline__ int read_overlap(int ws, int we, int rp, int re) {  /
     return e > s ? e - s : -1;
 }
 
-constexpr int kAnchorThreads = 128;
+constexpr int kAnchorThreads = 256;
 
-template <typename CntT>
-__global__ void __launch_bounds__(kAnchorThreads) k_anchor(DevBatch b, AnchorPlan plan, Queue q, ScoreParams sp,
+__device__ __noinline__ int general_dp_now(const DevBatch& b, int h, int read, int start, int L, ScoreParams sp) {
+    const uint8_t* hapg = b.hap_seq + b.hap_seq_off[h];
+    const uint8_t* go = b.gap_open + b.hap_seq_off[h] + h;
+    return band_dp_general(hapg + start, go + start, b.read_seq + b.read_seq_off[read],
+                           b.read_qual + b.read_seq_off[read], L, sp.ext, sp.nuc);
+}
+
+// Collects the distinct band start offsets of one pair: the first two go to the packed path
+// (cand0/cand1), the rest - and everything on the general path - to the queue.
+struct Emitter {
+    int c0, c1, sc;
+    unsigned n_dp;
+    __device__ __forceinline__ void emit(const DevBatch& b, const Queue& q, ScoreParams sp, bool slow, int64_t pair,
+                                         int h, int64_t gs, int read, int L, int start) {
+        if (start == c0 || start == c1) return;
+        ++n_dp;
+        if (!slow && c0 < 0) {
+            c0 = start;
+        } else if (!slow && c1 < 0) {
+            c1 = start;
+        } else {
+            const int qi = atomicAdd(q.count, 1);
+            if (qi < q.cap) {
+                QueueEntry qe;
+                qe.pair = pair;
+                qe.hap = h;
+                qe.slot = (int32_t)gs;
+                qe.start = start;
+                qe.pad = 0;
+                q.e[qi] = qe;
+            } else {  // queue full: run it right here
+                const int v = general_dp_now(b, h, read, start, L, sp);
+                sc = v < sc ? v : sc;
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ u32 tab_lookup(const u32* tab, int bits, u32 key) {
+    const u32 mask = (1u << bits) - 1;
+    u32 slot = tab_slot0(key, bits) & mask;
+    while (true) {
+        const u32 e = tab[slot];
+        if (e == kTabEmpty) return 0;
+        if ((e >> 16) == key) return e & 0xFFFFu;
+        slot = (slot + 1) & mask;
+    }
+}
+
+__global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, AnchorPlan plan, Queue q, ScoreParams sp,
                                                            Counters* ctr) {
     extern __shared__ __align__(16) uint8_t smem[];
-    // carve shared memory
     u32* s_tab = (u32*)smem;
-    uint16_t* s_next = (uint16_t*)(s_tab + plan.tab_words);
-    uint16_t* s_rhash = s_next + plan.next_halfs;
-    SlotInfo* s_slot = (SlotInfo*)(((uintptr_t)(s_rhash + plan.rhash_halfs) + 15) & ~(uintptr_t)15);
-    int32_t* s_hmeta = (int32_t*)(s_slot + plan.max_slots);  // per hap: len, tab off, bits, next off
-    CntT* s_cnt = (CntT*)(((uintptr_t)(s_hmeta + 4 * plan.max_group) + 15) & ~(uintptr_t)15);
+    u32* s_cnt = s_tab + (1 << plan.tab_bits);
+    u32* s_fblist = s_cnt + (size_t)plan.n_cnt * plan.cnt_words;
+    uint16_t* s_rid = (uint16_t*)(s_fblist + plan.max_pairs);
+    uint16_t* s_next = s_rid + plan.rid_halfs;
+    uint16_t* s_heads = s_next + plan.next_halfs;
+    SlotInfo* s_slot = (SlotInfo*)(((uintptr_t)(s_heads + plan.heads_halfs) + 15) & ~(uintptr_t)15);
+    int32_t* s_hmeta = (int32_t*)(s_slot + plan.max_slots);  // per hap: len, next offset
+    __shared__ int s_nid, s_nfb, s_scan[kAnchorThreads / 32];
 
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    CntT* my_cnt = plan.cnt_in_smem
-                       ? s_cnt + (size_t)tid * plan.cnt_stride
-                       : (CntT*)plan.cnt_global + ((size_t)blockIdx.x * nthr + tid) * plan.cnt_stride;
-
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    const int bits = plan.tab_bits;
+    const int S = 1 << bits;
     unsigned long long st_pairs = 0, st_scored = 0, st_dp = 0, st_cells = 0;
 
     for (int ti = blockIdx.x; ti < plan.n_tiles; ti += gridDim.x) {
@@ -208,22 +271,17 @@ __global__ void __launch_bounds__(kAnchorThreads) k_anchor(DevBatch b, AnchorPla
         const int ns = (int)(tile.s1 - tile.s0);
         __syncthreads();
         if (tid == 0) {
-            int toff = 0, noff = 0;
+            int noff = 0;
             for (int g = 0; g < nh; ++g) {
                 const int h = tile.h0 + g;
                 const int len = (int)(b.hap_seq_off[h + 1] - b.hap_seq_off[h]);
-                int nk = len - kKmer;
-                if (nk < 1) nk = 1;
-                int bits = 6;
-                while ((1 << bits) < 2 * nk && bits < 14) ++bits;
-                s_hmeta[4 * g + 0] = len;
-                s_hmeta[4 * g + 1] = toff;
-                s_hmeta[4 * g + 2] = bits;
-                s_hmeta[4 * g + 3] = noff;
-                toff += 1 << bits;
+                s_hmeta[2 * g + 0] = len;
+                s_hmeta[2 * g + 1] = noff;
                 noff += (len + 2) & ~1;
             }
+            s_nfb = 0;
         }
+        for (int i = tid; i < S; i += nthr) s_tab[i] = kTabEmpty;
         // slot metadata + skip rule (chaplotype.pyx:343-361)
         for (int s = tid; s < ns; s += nthr) {
             const int64_t gs = tile.s0 + s;
@@ -243,180 +301,286 @@ __global__ void __launch_bounds__(kAnchorThreads) k_anchor(DevBatch b, AnchorPla
             s_slot[s] = si;
         }
         __syncthreads();
-        if (tid == 0) {  // exclusive scan of hash-area offsets (tiles hold at most a few hundred slots)
+        if (tid == 0) {  // offsets of the per-read id rows (rows padded to 8 entries = 16 bytes)
             int o = 0;
             for (int s = 0; s < ns; ++s) {
                 s_slot[s].hoff = o;
-                int nk = s_slot[s].len - kKmer;
-                o += (nk > 0 && !(s_slot[s].flags & 1)) ? nk : 0;
+                const int nk = s_slot[s].len - kKmer;
+                if (nk > 0 && !(s_slot[s].flags & 1)) o += (nk + 7) & ~7;
             }
         }
-        // clear tables
+        // ---- union table: insert the 14-bit hash of every indexed haplotype position
+        //      (calign.pyx:109: positions 0 .. len-8) ----
         for (int g = 0; g < nh; ++g) {
-            u32* tab = s_tab + s_hmeta[4 * g + 1];
-            const int S = 1 << s_hmeta[4 * g + 2];
-            for (int i = tid; i < S; i += nthr) tab[i] = kTabEmpty;
-        }
-        __syncthreads();
-        // 7-mer index of each haplotype (calign.pyx:94-124: positions 0..len-8).  Open addressing on
-        // the 14-bit hash; equal hashes are chained through s_next.  Vote counts do not depend on
-        // the order inside a chain, so lock-free insertion order is fine.
-        for (int g = 0; g < nh; ++g) {
-            const int h = tile.h0 + g;
-            const int len = s_hmeta[4 * g + 0];
-            const uint8_t* hap = b.hap_seq + b.hap_seq_off[h];
-            u32* tab = s_tab + s_hmeta[4 * g + 1];
-            const int bits = s_hmeta[4 * g + 2];
-            const u32 mask = (1u << bits) - 1;
-            uint16_t* nxt = s_next + s_hmeta[4 * g + 3];
+            const int len = s_hmeta[2 * g];
+            const uint8_t* hap = b.hap_seq + b.hap_seq_off[tile.h0 + g];
             for (int i = tid; i < len - kKmer; i += nthr) {
                 const u32 key = kmer_hash(hap + i);
+                const u32 mask = (1u << bits) - 1;
                 u32 slot = tab_slot0(key, bits) & mask;
                 while (true) {
-                    u32 old = atomicCAS(&tab[slot], kTabEmpty, key << 16);
+                    const u32 old = atomicCAS(&s_tab[slot], kTabEmpty, key << 16);
                     if (old == kTabEmpty || (old >> 16) == key) break;
                     slot = (slot + 1) & mask;
                 }
-                u32 cur = ((volatile u32*)tab)[slot];
-                while (true) {  // push position i (stored as i+1) on the chain of this key
-                    nxt[i + 1] = (uint16_t)(cur & 0xFFFFu);
-                    u32 old = atomicCAS(&tab[slot], cur, (key << 16) | (u32)(i + 1));
-                    if (old == cur) break;
-                    cur = old;
+            }
+        }
+        __syncthreads();
+        // ---- dense ids 1..U for the occupied slots (block-wide exclusive scan) ----
+        {
+            const int per = (S + nthr - 1) / nthr;
+            const int lo = tid * per, hi = min(S, lo + per);
+            int cnt = 0;
+            for (int i = lo; i < hi; ++i) cnt += (s_tab[i] != kTabEmpty);
+            int incl = cnt;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) s_scan[warp] = incl;
+            __syncthreads();
+            int base = 0;
+            for (int k = 0; k < warp; ++k) base += s_scan[k];
+            if (tid == nthr - 1) s_nid = base + incl;
+            int id = base + incl - cnt;
+            for (int i = lo; i < hi; ++i)
+                if (s_tab[i] != kTabEmpty) s_tab[i] = (s_tab[i] & 0xFFFF0000u) | (u32)(++id);
+        }
+        __syncthreads();
+        const int U = s_nid;  // number of distinct 7-mers in this haplotype group
+        // ---- read 7-mer ids (calign.pyx:155-165: k-mers 0..len-8); rolling hash per thread ----
+        {
+            // work item = (slot, block of 32 consecutive k-mers)
+            for (int s = warp; s < ns; s += nwarp) {
+                const SlotInfo si = s_slot[s];
+                const int nk = si.len - kKmer;
+                if ((si.flags & 1) || nk <= 0) continue;
+                const uint8_t* rs = b.read_seq + b.read_seq_off[si.read];
+                const int nkp = (nk + 7) & ~7;
+                // each lane hashes a run of consecutive k-mers
+                const int run = (nkp + 31) / 32;
+                const int i0 = lane * run;
+                if (i0 < nkp) {
+                    u32 h = 0;
+                    if (i0 < nk) h = kmer_hash(rs + i0);
+                    for (int i = i0; i < min(nkp, i0 + run); ++i) {
+                        uint16_t id = 0;
+                        if (i < nk) {
+                            if (i > i0) h = ((h << 2) & (kHashSize - 1)) + base_code(rs[i + kKmer - 1]);
+                            id = (uint16_t)tab_lookup(s_tab, bits, h);
+                        }
+                        s_rid[si.hoff + i] = id;
+                    }
                 }
             }
         }
-        // read 7-mer hashes (calign.pyx:155-165: k-mers 0..len-8)
-        for (int s = 0; s < ns; ++s) {
-            const SlotInfo si = s_slot[s];
-            if (si.flags & 1) continue;
-            const uint8_t* rs = b.read_seq + b.read_seq_off[si.read];
-            for (int i = tid; i < si.len - kKmer; i += nthr) s_rhash[si.hoff + i] = (uint16_t)kmer_hash(rs + i);
-        }
-        __syncthreads();
         const int general = b.win_general[w];
-
-        // ---- per (slot, haplotype) pair: vote, pick candidates (calign.pyx:206-267) ----
-        const int npairs = ns * nh;
-        for (int p = tid; p < npairs; p += nthr) {
-            const int s = p % ns, g = p / ns;
-            const SlotInfo si = s_slot[s];
-            const int h = tile.h0 + g;
-            const int64_t gs = tile.s0 + s;
-            const int wi = b.slot_wi[gs];
-            const int64_t T = b.wi_slot_off[wi + 1] - b.wi_slot_off[wi];
-            const int64_t pair = b.ll_off[wi] + (int64_t)(h - b.win_hap_off[w]) * T + (gs - b.wi_slot_off[wi]);
-            ++st_pairs;
-            int c0 = -1, c1 = -1, sc = kScoreNone;
-            if (si.flags & 1) {
-                sc = -1;
-            } else if (si.len < kKmer) {
-                sc = 0;  // calign.pyx:182-183
-                ++st_scored;
-                st_cells += 16ull * si.len;
-            } else {
-                ++st_scored;
-                st_cells += 16ull * si.len;
-                const int L = si.len;
-                const int hap_len = s_hmeta[4 * g + 0];
-                const u32* tab = s_tab + s_hmeta[4 * g + 1];
-                const int bits = s_hmeta[4 * g + 2];
-                const u32 mask = (1u << bits) - 1;
-                const uint16_t* nxt = s_next + s_hmeta[4 * g + 3];
-                const uint16_t* rh = s_rhash + si.hoff;
-                const int C = hap_len + L;
-                {  // clear the vote array (memset, calign.pyx:206)
-                    uint4* c4 = (uint4*)my_cnt;
-                    const int n16 = (C * (int)sizeof(CntT) + 15) >> 4;
-                    for (int i = 0; i < n16; ++i) c4[i] = make_uint4(0, 0, 0, 0);
-                }
-                int maxc = 0, ntie = 0, besto = -1;
-                for (int i = 0; i < L - kKmer; ++i) {
-                    const u32 key = rh[i];
-                    u32 slot = tab_slot0(key, bits) & mask;
-                    u32 e = tab[slot];
-                    while (e != kTabEmpty && (e >> 16) != key) {
-                        slot = (slot + 1) & mask;
-                        e = tab[slot];
-                    }
-                    if (e == kTabEmpty) continue;
-                    u32 p1 = e & 0xFFFFu;
-                    while (p1) {
-                        const int o = (int)p1 - i - 1 + L;  // index pos + readLen, calign.pyx:213-215
-                        const int c = (int)my_cnt[o] + 1;
-                        my_cnt[o] = (CntT)c;
-                        if (c > maxc) {
-                            maxc = c;
-                            ntie = 1;
-                            besto = o;
-                        } else if (c == maxc) {
-                            ++ntie;
-                        }
-                        p1 = nxt[p1];
+        const int hstride = U + 1;
+        const int sub_max = max(1, min(nh, plan.heads_halfs / hstride));
+        for (int g0 = 0; g0 < nh; g0 += sub_max) {
+            const int g1 = min(nh, g0 + sub_max);
+            __syncthreads();
+            // ---- chains of this haplotype sub-group (calign.pyx:94-124) ----
+            for (int i = tid; i < (g1 - g0) * hstride; i += nthr) s_heads[i] = 0;
+            __syncthreads();
+            for (int g = g0; g < g1; ++g) {
+                const int len = s_hmeta[2 * g];
+                const uint8_t* hap = b.hap_seq + b.hap_seq_off[tile.h0 + g];
+                uint16_t* nxt = s_next + s_hmeta[2 * g + 1];
+                unsigned short* head = (unsigned short*)(s_heads + (g - g0) * hstride);
+                for (int i = tid; i < len - kKmer; i += nthr) {
+                    const u32 id = tab_lookup(s_tab, bits, kmer_hash(hap + i));
+                    unsigned short cur = head[id];
+                    while (true) {  // push position i (stored as i+1); order inside a chain is irrelevant
+                        nxt[i + 1] = cur;
+                        const unsigned short old = atomicCAS(&head[id], cur, (unsigned short)(i + 1));
+                        if (old == cur) break;
+                        cur = old;
                     }
                 }
-                // fallback position (calign.pyx:252-256)
-                int idx0 = si.pos - b.hap_start[w];
-                const int lim = hap_len - L - 15;
-                if (lim < idx0) idx0 = lim;
-                // distinct band start offsets: accepted tied-best candidates + the fallback.  The
-                // reference's result is the min over exactly this set (its early exit on score 0 and
-                // its "skip the fallback if it equals the best candidate" rule do not change a min).
-                bool any_accepted = false;
-                const bool slow = general || L < kMinFastLen;
-                auto emit = [&](int start) {
-                    if (start == c0 || start == c1) return;
-                    ++st_dp;
-                    if (!slow && c0 < 0) {
-                        c0 = start;
-                    } else if (!slow && c1 < 0) {
-                        c1 = start;
-                    } else {
-                        // general path: queue it, or run it right here when the queue is full
-                        const int qi = atomicAdd(q.count, 1);
-                        if (qi < q.cap) {
-                            QueueEntry qe;
-                            qe.pair = pair;
-                            qe.hap = h;
-                            qe.slot = (int32_t)gs;
-                            qe.start = start;
-                            qe.pad = 0;
-                            q.e[qi] = qe;
-                        } else {
-                            const uint8_t* hapg = b.hap_seq + b.hap_seq_off[h];
-                            const uint8_t* go = b.gap_open + b.hap_seq_off[h] + h;
-                            const int v = band_dp_general(hapg + start, go + start,
-                                                          b.read_seq + b.read_seq_off[si.read],
-                                                          b.read_qual + b.read_seq_off[si.read], L, sp.ext, sp.nuc);
-                            sc = v < sc ? v : sc;
-                        }
-                    }
-                };
-                if (maxc > 0) {
-                    if (ntie == 1) {
-                        const int idx = besto - L;
-                        if (idx + L + 15 < hap_len) {
-                            any_accepted = true;
-                            emit(idx > 8 ? idx - 8 : 0);
-                        }
-                    } else {
-                        for (int i = 0; i < C; ++i) {
-                            if ((int)my_cnt[i] != maxc) continue;
-                            const int idx = i - L;
-                            if (idx + L + 15 < hap_len) {
-                                any_accepted = true;
-                                emit(idx > 8 ? idx - 8 : 0);
+            }
+            __syncthreads();
+            // ---- per (slot, haplotype) pair: majority vote ----
+            const int npairs = ns * (g1 - g0);
+            for (int p = tid; p < npairs; p += nthr) {
+                const int s = p % ns, g = g0 + p / ns;
+                const SlotInfo si = s_slot[s];
+                const int h = tile.h0 + g;
+                const int64_t gs = tile.s0 + s;
+                const int wi = b.slot_wi[gs];
+                const int64_t T = b.wi_slot_off[wi + 1] - b.wi_slot_off[wi];
+                const int64_t pair = b.ll_off[wi] + (int64_t)(h - b.win_hap_off[w]) * T + (gs - b.wi_slot_off[wi]);
+                ++st_pairs;
+                Emitter em;
+                em.c0 = em.c1 = -1;
+                em.sc = kScoreNone;
+                em.n_dp = 0;
+                bool done = true;
+                if (si.flags & 1) {
+                    em.sc = -1;
+                } else if (si.len < kKmer) {
+                    em.sc = 0;  // calign.pyx:182-183
+                    ++st_scored;
+                    st_cells += 16ull * si.len;
+                } else {
+                    ++st_scored;
+                    st_cells += 16ull * si.len;
+                    const int L = si.len, nk = L - kKmer;
+                    const int hap_len = s_hmeta[2 * g];
+                    const uint16_t* nxt = s_next + s_hmeta[2 * g + 1];
+                    const uint16_t* head = s_heads + (g - g0) * hstride;
+                    const uint4* rid4 = (const uint4*)(s_rid + si.hoff);
+                    // pass 1: Boyer-Moore majority candidate over the vote stream (vote = offset p-i)
+                    int cand = 0, wgt = 0, V = 0;
+                    for (int i8 = 0; i8 < nk; i8 += 8) {
+                        const uint4 v = rid4[i8 >> 3];
+                        const u32 ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const u32 id = (ws[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                            if (id) {
+                                u32 p1 = head[id];
+                                while (p1) {
+                                    const int o = (int)p1 - (i8 + k);
+                                    ++V;
+                                    if (wgt == 0) {
+                                        cand = o;
+                                        wgt = 1;
+                                    } else {
+                                        wgt += (o == cand) ? 1 : -1;
+                                    }
+                                    p1 = nxt[p1];
+                                }
                             }
                         }
                     }
+                    // pass 2: exact count of the candidate
+                    int cc = 0;
+                    if (V > 0) {
+                        for (int i8 = 0; i8 < nk; i8 += 8) {
+                            const uint4 v = rid4[i8 >> 3];
+                            const u32 ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const u32 id = (ws[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                                if (id) {
+                                    u32 p1 = head[id];
+                                    while (p1) {
+                                        cc += ((int)p1 - (i8 + k) == cand);
+                                        p1 = nxt[p1];
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (V > 0 && 2 * cc <= V) {
+                        done = false;  // no strict majority: exact tie scan by a warp, below
+                        s_fblist[atomicAdd(&s_nfb, 1)] = (u32)p;
+                    } else {
+                        // fallback position (calign.pyx:252-256)
+                        int idx0 = si.pos - b.hap_start[w];
+                        const int lim = hap_len - L - 15;
+                        if (lim < idx0) idx0 = lim;
+                        const bool slow = general || L < kMinFastLen;
+                        bool any_accepted = false;
+                        if (V > 0) {
+                            const int idx = cand - 1;  // p1 stores position+1
+                            if (idx + L + 15 < hap_len) {  // calign.pyx:228
+                                any_accepted = true;
+                                em.emit(b, q, sp, slow, pair, h, gs, si.read, L, idx > 8 ? idx - 8 : 0);
+                            }
+                        }
+                        // with no accepted candidate bestMappingPosition stays -1, so a fallback index of
+                        // exactly -1 is skipped and the sentinel 1000000 is returned (calign.pyx:258, 272)
+                        if (any_accepted || idx0 != -1)
+                            em.emit(b, q, sp, slow, pair, h, gs, si.read, L, idx0 > 8 ? idx0 - 8 : 0);
+                    }
                 }
-                // with no accepted candidate bestMappingPosition stays -1, so a fallback index of
-                // exactly -1 is skipped and the sentinel 1000000 is returned (calign.pyx:258, 272)
-                if (any_accepted || idx0 != -1) emit(idx0 > 8 ? idx0 - 8 : 0);
+                if (done) {
+                    st_dp += em.n_dp;
+                    b.cand0[pair] = em.c0;
+                    b.cand1[pair] = em.c1;
+                    b.score[pair] = em.sc;
+                }
             }
-            b.cand0[pair] = c0;
-            b.cand1[pair] = c1;
-            b.score[pair] = sc;
+            __syncthreads();
+            // ---- pairs without a strict majority: exact vote array per warp (calign.pyx:206-247) ----
+            const int nfb = s_nfb;
+            const int n_fbw = min(nwarp, plan.n_cnt);  // warps that own a counter array
+            for (int f = warp; f < nfb && warp < n_fbw; f += n_fbw) {
+                const int p = (int)s_fblist[f];
+                const int s = p % ns, g = g0 + p / ns;
+                const SlotInfo si = s_slot[s];
+                const int h = tile.h0 + g;
+                const int64_t gs = tile.s0 + s;
+                const int wi = b.slot_wi[gs];
+                const int64_t T = b.wi_slot_off[wi + 1] - b.wi_slot_off[wi];
+                const int64_t pair = b.ll_off[wi] + (int64_t)(h - b.win_hap_off[w]) * T + (gs - b.wi_slot_off[wi]);
+                const int L = si.len, nk = L - kKmer;
+                const int hap_len = s_hmeta[2 * g];
+                const uint16_t* nxt = s_next + s_hmeta[2 * g + 1];
+                const uint16_t* head = s_heads + (g - g0) * hstride;
+                const uint16_t* rid = s_rid + si.hoff;
+                u32* cw = s_cnt + (size_t)warp * plan.cnt_words;
+                const int C = hap_len + L;
+                const int words = (C + 1) >> 1;
+                for (int k = lane; k < words; k += 32) cw[k] = 0;
+                __syncwarp();
+                for (int i = lane; i < nk; i += 32) {
+                    const u32 id = rid[i];
+                    if (!id) continue;
+                    u32 p1 = head[id];
+                    while (p1) {
+                        const int o = (int)p1 - i - 1 + L;  // index pos + readLen, calign.pyx:213-215
+                        atomicAdd(&cw[o >> 1], 1u << (16 * (o & 1)));
+                        p1 = nxt[p1];
+                    }
+                }
+                __syncwarp();
+                u32 m = 0;
+                for (int k = lane; k < words; k += 32) {
+                    const u32 v = cw[k];
+                    m = max(m, max(v & 0xFFFFu, v >> 16));
+                }
+                for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+                Emitter em;
+                em.c0 = em.c1 = -1;
+                em.sc = kScoreNone;
+                em.n_dp = 0;
+                const bool slow = general || L < kMinFastLen;
+                bool any_accepted = false;
+                for (int base = 0; base < C; base += 32) {  // ascending offsets, calign.pyx:223
+                    const int o = base + lane;
+                    u32 c = 0;
+                    if (o < C) c = (cw[o >> 1] >> (16 * (o & 1))) & 0xFFFFu;
+                    const int idx = o - L;
+                    const bool hit = (o < C) && m > 0 && c == m && (idx + L + 15 < hap_len);
+                    unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+                    if (lane == 0) {
+                        while (bal) {
+                            const int k = __ffs(bal) - 1;
+                            bal &= bal - 1;
+                            const int ix = base + k - L;
+                            any_accepted = true;
+                            em.emit(b, q, sp, slow, pair, h, gs, si.read, L, ix > 8 ? ix - 8 : 0);
+                        }
+                    }
+                }
+                if (lane == 0) {
+                    int idx0 = si.pos - b.hap_start[w];
+                    const int lim = hap_len - L - 15;
+                    if (lim < idx0) idx0 = lim;
+                    if (any_accepted || idx0 != -1)
+                        em.emit(b, q, sp, slow, pair, h, gs, si.read, L, idx0 > 8 ? idx0 - 8 : 0);
+                    st_dp += em.n_dp;
+                    b.cand0[pair] = em.c0;
+                    b.cand1[pair] = em.c1;
+                    b.score[pair] = em.sc;
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+            if (tid == 0) s_nfb = 0;
         }
     }
     if (ctr) {  // statistics
@@ -426,7 +590,7 @@ __global__ void __launch_bounds__(kAnchorThreads) k_anchor(DevBatch b, AnchorPla
             st_dp += __shfl_down_sync(0xFFFFFFFFu, st_dp, o);
             st_cells += __shfl_down_sync(0xFFFFFFFFu, st_cells, o);
         }
-        if ((tid & 31) == 0) {
+        if (lane == 0) {
             atomicAdd(&ctr->n_pairs, st_pairs);
             atomicAdd(&ctr->n_scored, st_scored);
             atomicAdd(&ctr->n_dp, st_dp);

@@ -76,10 +76,11 @@ class Engine:
         _check(self.lib, self.lib.plb_set_timing(self.ctx, 1 if on else 0))
 
     def kernel_times(self):
-        """Device time (ms) of each kernel of the last run, from CUDA events on the context stream."""
+        """Mean device time (ms) of each kernel over the runs since set_timing(True), from CUDA events
+        on the context stream.  Returns (dict, number of runs averaged)."""
         ms = (C.c_float * 6)()
-        _check(self.lib, self.lib.plb_kernel_times(self.ctx, ms))
-        return dict(zip(_abi.KERNEL_NAMES, [float(x) for x in ms]))
+        n = _check(self.lib, self.lib.plb_kernel_times(self.ctx, ms))
+        return dict(zip(_abi.KERNEL_NAMES, [float(x) for x in ms])), n
 
     # ---- S1 ---------------------------------------------------------------------------------
     def fast_align(self, seq1: bytes, seq2: bytes, qual2: bytes, gap_open: bytes, gapextend=3, nucprior=2):

@@ -226,3 +226,26 @@ def algorithmic_bytes(batch: WindowBatch) -> int:
     out = int((np.repeat(H, batch.n_individuals) * T).sum()) * 8
     out += int((H * (H + 1) // 2).sum()) * 8 * batch.n_individuals
     return rd + hp + out
+
+
+def _make_range(args):
+    lo, hi, kw = args
+    return make_batch(hi - lo, window_offset=lo, **kw)
+
+
+def make_batch_parallel(n_windows, window_offset=0, n_procs=None, **kw):
+    """make_batch() over a process pool (chunk-aligned ranges, so the bytes are identical)."""
+    import multiprocessing as mp
+    import os
+    from .batch import concat_batches
+    n_procs = n_procs or min(os.cpu_count() or 1, 32)
+    if n_procs <= 1 or n_windows <= 2 * CHUNK:
+        return make_batch(n_windows, window_offset=window_offset, **kw)
+    lo, hi = window_offset, window_offset + n_windows
+    cuts = sorted(set([lo, hi] + list(range((lo // CHUNK + 1) * CHUNK, hi, CHUNK))))
+    step = max(1, (len(cuts) - 1 + n_procs * 2 - 1) // (n_procs * 2))
+    cuts = cuts[::step] + ([hi] if cuts[::step][-1] != hi else [])
+    jobs = [(a, b, kw) for a, b in zip(cuts[:-1], cuts[1:])]
+    with mp.get_context("fork").Pool(n_procs) as pool:
+        parts = pool.map(_make_range, jobs)
+    return concat_batches(parts)
