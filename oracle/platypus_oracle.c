@@ -402,6 +402,7 @@ int plo_window_loglik(const PlbWindowBatch* b, const PlbOptions* opt, PlbLoglikO
         stats->n_pairs_scored = tot_scored;
         stats->n_dp = tot_dp;
         stats->cells = tot_cells;
+        stats->n_anchor_heavy = stats->n_anchor_verify = stats->n_anchor_exact = 0;
     }
     return err;
 }

@@ -50,7 +50,8 @@ class PlbPopulationOut(C.Structure):
 
 
 class PlbRunStats(C.Structure):
-    _fields_ = [("n_pairs", C.c_int64), ("n_pairs_scored", C.c_int64), ("n_dp", C.c_int64), ("cells", C.c_int64)]
+    _fields_ = [("n_pairs", C.c_int64), ("n_pairs_scored", C.c_int64), ("n_dp", C.c_int64), ("cells", C.c_int64),
+                ("n_anchor_heavy", C.c_int64), ("n_anchor_verify", C.c_int64), ("n_anchor_exact", C.c_int64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

@@ -405,7 +405,7 @@ static int plan_tiles(const PlbWindowBatch* hb, TileLists& tl, AnchorPlan& ap, D
             };
             for (int64_t s = s0; s < s1; ++s) {
                 const int L = slot_len[(size_t)(s - s0)];
-                const int wds = L >= kMinFastLen ? prof_row_words(L) : 0;
+                const int wds = (L >= kMinFastLen && L <= kMaxFastLen) ? prof_row_words(L) : 0;
                 if (s > c0 && (4 * (words + wds) > kDpProfBudget || s - c0 >= kDpMaxSlots ||
                                (s - c0 + 1) * maxg > kDpMaxPairs)) {
                     flush(s);
@@ -477,8 +477,8 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
         ap.cnt_words = (((max_hap + max_read + 2) >> 1) + 3) & ~3;
         const int nwarps = kAnchorThreads / 32;
         ap.n_cnt = (int)std::max<size_t>(1, std::min<size_t>(nwarps, kAnchorCntBudget / ((size_t)ap.cnt_words * 4)));
-        db->a_smem = ((size_t)4 << ap.tab_bits) + (size_t)ap.n_cnt * ap.cnt_words * 4 + (size_t)ap.max_pairs * 4 +
-                     (size_t)ap.rid_halfs * 2 + (size_t)ap.next_halfs * 2 + (size_t)ap.heads_halfs * 2 + 16 +
+        db->a_smem = ((size_t)4 << ap.tab_bits) + (size_t)ap.n_cnt * ap.cnt_words * 4 + (size_t)ap.max_pairs * 16 +
+                     (size_t)ap.rid_halfs * 2 + (size_t)ap.next_halfs * 4 + (size_t)ap.heads_halfs * 4 + 16 +
                      (size_t)ap.max_slots * sizeof(SlotInfo) + (size_t)ap.max_group * 8 + 16;
     }
     if (db->a_smem + 1024 > (size_t)c->smem_optin) {
@@ -516,7 +516,7 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
                  o_var_prior = L.take(have_var ? (size_t)W * hb->max_variants * 8 : 0);
     const size_t o_slot_wi = L.take((size_t)n_slots * 4), o_hap_win = L.take((size_t)n_haps * 4),
                  o_ll_off = L.take((size_t)(nwi + 1) * 8);
-    const size_t o_gap = L.take((size_t)hap_bytes + n_haps + 64), o_wgen = L.take((size_t)W + 64),
+    const size_t o_gap = L.take((size_t)hap_bytes + n_haps + 64), o_wgen = L.take((size_t)W * 4 + 64),
                  o_c0 = L.take((size_t)n_pairs * 4), o_c1 = L.take((size_t)n_pairs * 4),
                  o_score = L.take((size_t)n_pairs * 4);
     const size_t o_atiles = L.take(tl.a.size() * sizeof(Tile)), o_dtiles = L.take(tl.d.size() * sizeof(Tile));
@@ -565,7 +565,7 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
     d.hap_win = at<int32_t>(B, o_hap_win);
     d.ll_off = at<int64_t>(B, o_ll_off);
     d.gap_open = at<uint8_t>(B, o_gap);
-    d.win_general = at<uint8_t>(B, o_wgen);
+    d.win_flags = at<uint32_t>(B, o_wgen);
     d.cand0 = at<int32_t>(B, o_c0);
     d.cand1 = at<int32_t>(B, o_c1);
     d.score = at<int32_t>(B, o_score);
@@ -656,7 +656,7 @@ extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOption
                        db->max_haps);
     cudaStream_t st = c->stream;
     ScoreParams sp{opt->gap_extend, opt->nuc_prior};
-    CU(cudaMemsetAsync(d.win_general, 0, (size_t)d.n_windows, st));
+    CU(cudaMemsetAsync(d.win_flags, 0, (size_t)d.n_windows * 4, st));
     CU(cudaMemsetAsync(db->q.count, 0, 4, st));
     CU(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), st));
 
@@ -721,6 +721,9 @@ extern "C" int plb_last_stats(PlbContext* c, PlbRunStats* out) {
     out->n_pairs_scored = (int64_t)c->h_ctr->n_scored;
     out->n_dp = (int64_t)c->h_ctr->n_dp;
     out->cells = (int64_t)c->h_ctr->cells;
+    out->n_anchor_heavy = (int64_t)c->h_ctr->n_heavy;
+    out->n_anchor_verify = (int64_t)c->h_ctr->n_verify;
+    out->n_anchor_exact = (int64_t)c->h_ctr->n_exact;
     return PLB_OK;
 }
 
@@ -869,21 +872,33 @@ __global__ void __launch_bounds__(128) k_align_batch(int n, const int64_t* __res
     const uint8_t* r = rs + read_off[i];
     const uint8_t* q = rq + read_off[i];
     const int seg = L + 15;
-    bool fast = L >= kMinFastLen;
+    bool fast = L >= kMinFastLen && L <= kMaxFastLen;
     for (int x = 0; x < seg && fast; ++x) fast = fast_code(h[x]) != 5;
+    bool six = fast;
+    for (int x = 0; x < seg && six; ++x) six = fast_code(h[x]) != 4;
     int v;
     if (fast) {
         u32* prof = prof_ws + prof_off[i];
         HapRec* rec = rec_ws + rec_off[i];
         const int n_rows = dp_steps(L) + 4;
-        for (int y = 0; y < n_rows; ++y) prof[y] = y < L ? make_profile(fast_code(r[y]), q[y]) : 0u;
+        const int K = 2 * ext + nuc;
+        for (int y = 0; y < n_rows; ++y) {
+            u32 pv = 0u;
+            if (y < L) pv = six ? make_profile6(fast_code(r[y]), q[y], K) : make_profile(fast_code(r[y]), q[y]);
+            prof[y] = pv;
+        }
         for (int x = 0; x < seg + kRecPad; ++x) {
             const int ca = x < seg ? fast_code(h[x]) : 4, cb = x + 4 < seg ? fast_code(h[x + 4]) : 4;
             const u32 oa = x < seg ? g[x] : 0u, ob = x + 4 < seg ? g[x + 4] : 0u;
-            rec[x].gow = oa | (ob << 16);
-            rec[x].sel = make_sel(ca, cb);
+            if (six) {
+                rec[x].gow = pack_s16x2((int)oa - ext, (int)ob - ext);
+                rec[x].sel = make_sel6(ca < 4 ? ca : 0, cb < 4 ? cb : 0);
+            } else {
+                rec[x].gow = oa | (ob << 16);
+                rec[x].sel = make_sel(ca, cb);
+            }
         }
-        v = band_dp_fast(prof, rec, L, ext, nuc);
+        v = six ? band_dp_fast6(prof, rec, L, ext, nuc) : band_dp_fast(prof, rec, L, ext, nuc);
     } else {
         v = band_dp_general(h, g, r, q, L, ext, nuc);
     }

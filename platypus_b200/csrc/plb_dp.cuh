@@ -255,6 +255,193 @@ PLB_HD int band_dp_fast(const u32* __restrict__ prof, const HapRec* __restrict__
     return lo < hi ? lo : hi;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 6-op variant (haplotype groups without 'N').
+//
+// Every state is stored relative to the frame  f(x,y) = (ext+nuc)*y + ext*x :  S~ = S - f.
+// An insertion step (y+1) adds ext+nuc and a deletion step (x+1) adds ext, so in this frame
+// both gap-extension additions vanish and both gap-open terms become the same per-position
+// constant open[x] - ext:
+//     M~ = B~' + (sub - K)                 K = 2*ext + nuc (the diagonal step crosses both axes)
+//     I~ = min(I~', M~' + (open[x]-ext))   one VIADDMNMX
+//     D~ = min(D~', MI~' + (open[x]-ext))  one VIADDMNMX
+//     MI~ = min(M~, I~),  B~ = min(MI~, D~)
+// i.e. 6 packed ops per 2 cells instead of 8.  The profile bytes hold sub-K as SIGNED bytes and
+// the PRMT selector sign-extends them (nibble 8|c), which leaves no spare byte for the 'N'
+// wildcard - groups with an 'N' use the 8-op variant above.
+// Absolute score = relative + f; the last-row extraction adds ext*d per diagonal and the common
+// (2*ext+nuc)*(L-1) at the end.
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+PLB_HD u32 vmax2(u32 a, u32 b) { return __vmaxs2(a, b); }
+#else
+PLB_HD u32 vmax2(u32 a, u32 b) {
+    int16_t al = (int16_t)(a & 0xFFFF), bl = (int16_t)(b & 0xFFFF);
+    int16_t ah = (int16_t)(a >> 16), bh = (int16_t)(b >> 16);
+    return (u32)(uint16_t)(al > bl ? al : bl) | ((u32)(uint16_t)(ah > bh ? ah : bh) << 16);
+}
+#endif
+
+constexpr int kMaxFastLen = 2000;  // relative values reach -(2*ext+nuc)*L: stay far inside int16
+
+PLB_HD u32 make_sel6(int code_lo, int code_hi) {  // codes 0..3 only
+    const u32 lo = (u32)code_lo, hi = (u32)(4 + code_hi);
+    return lo | ((8u | lo) << 4) | (hi << 8) | ((8u | hi) << 12);
+}
+// profile word of signed bytes: mismatch q-K, match -K.  code > 3 (N or any other byte) mismatches all.
+PLB_HD u32 make_profile6(int code, int qual, int K) {
+    const u32 mis = (u32)(uint8_t)(int8_t)(qual - K), mat = (u32)(uint8_t)(int8_t)(-K);
+    u32 p = mis * 0x01010101u;
+    if (code < 4) p = (p & ~(0xFFu << (8 * code))) | (mat << (8 * code));
+    return p;
+}
+PLB_HD u32 pack_s16x2(int lo, int hi) { return ((u32)lo & 0xFFFFu) | ((u32)hi << 16); }
+
+struct DpState6 {
+    u32 ME[4], IE[4], DE[4], MIE[4];
+    u32 MO[4], IO[4], DO[4], MIO[4];
+    u32 P[8];
+    u32 Wg[8], Ws[8];
+    u32 acc[4];
+    u32 NM[4];   // 0x8000 in the lane whose row is L-1, 0x7FFF elsewhere
+};
+
+template <bool FIRST, bool LAST>
+PLB_HD void dp_group6(DpState6& s, const u32* __restrict__ prof, const HapRec* __restrict__ rec, int t0, int L,
+                      int ext, int extp) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int t = t0 + j;
+        s.P[j & 7] = prof[t];
+        {
+            HapRec r = rec[t + 4];
+            s.Wg[(j + 4) & 7] = r.gow;
+            s.Ws[(j + 4) & 7] = r.sel;
+        }
+        if (LAST) {
+            if (t == L - 1) s.NM[0] = (s.NM[0] & 0xFFFF0000u) | 0x8000u;
+        }
+        // ---------------- even half: cells (t+i, t-i) ----------------
+        u32 Dt[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const u32 pa = s.P[(j - k) & 7], pb = s.P[(j - k - 4) & 7];
+            const int w0 = (j + k) & 7, w1 = (j + k + 1) & 7;
+            u32 B = vmin2(s.MIE[k], s.DE[k]);
+            u32 Mn = vadd2(B, prmt(pa, pb, s.Ws[w0]));
+            u32 In = vaddmin2(s.MO[k], s.Wg[w0], s.IO[k]);
+            Dt[k] = vaddmin2(s.MIO[k], s.Wg[w1], s.DO[k]);
+            s.ME[k] = Mn;
+            s.IE[k] = In;
+            s.MIE[k] = vmin2(Mn, In);
+        }
+        s.DE[3] = Dt[2];
+        s.DE[2] = Dt[1];
+        s.DE[1] = Dt[0];
+        s.DE[0] = prmt(Dt[3], kInf2, 0x1054);
+        if (FIRST && j < 7) {  // lane j+1 on row y = -1, x = 2j+1: B := 0 (absolute), M, I := inf
+            const int k = (j + 1) & 3;
+            const bool lo = (j + 1) < 4;
+            const u32 keep = lo ? 0xFFFF0000u : 0x0000FFFFu;
+            const u32 inf1 = lo ? 0x00007000u : 0x70000000u;
+            const u32 zero = ((u32)(extp - ext * (2 * j + 1)) & 0xFFFFu) << (lo ? 0 : 16);  // 0 - f(x,-1)
+            s.ME[k] = (s.ME[k] & keep) | inf1;
+            s.IE[k] = (s.IE[k] & keep) | inf1;
+            s.MIE[k] = (s.MIE[k] & keep) | inf1;
+            s.DE[k] = (s.DE[k] & keep) | zero;
+        }
+        if (LAST) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const u32 dc = pack_s16x2(ext * 2 * k, ext * 2 * (k + 4));   // + ext*d, d = 2*lane
+                s.acc[k] = vmin2(s.acc[k], vmax2(vadd2(vmin2(s.MIE[k], s.DE[k]), dc), s.NM[k]));
+            }
+        }
+        // ---------------- odd half: cells (t+1+i, t-i) ----------------
+        u32 It[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const u32 pa = s.P[(j - k) & 7], pb = s.P[(j - k - 4) & 7];
+            const int w0 = (j + k) & 7, w1 = (j + k + 1) & 7;
+            u32 B = vmin2(s.MIO[k], s.DO[k]);
+            u32 Mn = vadd2(B, prmt(pa, pb, s.Ws[w1]));
+            u32 Dn = vaddmin2(s.MIE[k], s.Wg[w1], s.DE[k]);
+            It[k] = vaddmin2(s.ME[k], s.Wg[w0], s.IE[k]);
+            s.MO[k] = Mn;
+            s.DO[k] = Dn;
+        }
+        s.IO[0] = It[1];
+        s.IO[1] = It[2];
+        s.IO[2] = It[3];
+        s.IO[3] = prmt(It[0], kInf2, 0x7632);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s.MIO[k] = vmin2(s.MO[k], s.IO[k]);
+        if (FIRST && j < 7) {  // row y = -1, x = 2j+2 (even): M := 0 (absolute), I := inf
+            const int k = (j + 1) & 3;
+            const bool lo = (j + 1) < 4;
+            const u32 keep = lo ? 0xFFFF0000u : 0x0000FFFFu;
+            const u32 inf1 = lo ? 0x00007000u : 0x70000000u;
+            const u32 zero = ((u32)(extp - ext * (2 * j + 2)) & 0xFFFFu) << (lo ? 0 : 16);
+            s.MO[k] = (s.MO[k] & keep) | zero;
+            s.IO[k] = (s.IO[k] & keep) | inf1;
+            s.MIO[k] = (s.MIO[k] & keep) | inf1;
+            s.DO[k] = (s.DO[k] & keep) | zero;
+        }
+        if (LAST) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const u32 dc = pack_s16x2(ext * (2 * k + 1), ext * (2 * (k + 4) + 1));  // d = 2*lane + 1
+                s.acc[k] = vmin2(s.acc[k], vmax2(vadd2(vmin2(s.MIO[k], s.DO[k]), dc), s.NM[k]));
+            }
+            u32 n3 = s.NM[3];
+            s.NM[3] = s.NM[2];
+            s.NM[2] = s.NM[1];
+            s.NM[1] = s.NM[0];
+            s.NM[0] = prmt(n3, 0x7FFF7FFFu, 0x1054);
+        }
+    }
+}
+
+// prof : make_profile6 words (K = 2*ext+nuc), rows 0..L-1, zero-padded to dp_steps(L) rows
+// rec  : records with .gow = pack(open[x]-ext, open[x+4]-ext), .sel = make_sel6(code(x), code(x+4))
+// Requires kMinFastLen <= L <= kMaxFastLen and no 'N' in the segment.
+PLB_HD int band_dp_fast6(const u32* __restrict__ prof, const HapRec* __restrict__ rec, int L, int ext, int nuc) {
+    DpState6 s;
+    const int extp = ext + nuc;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        s.ME[k] = s.IE[k] = s.DE[k] = s.MIE[k] = kInf2;
+        s.MO[k] = s.IO[k] = s.DO[k] = s.MIO[k] = kInf2;
+        s.acc[k] = 0x7FFF7FFFu;
+        s.NM[k] = 0x7FFF7FFFu;
+    }
+    // "step -1": lane 0 of both vectors sits on row y = -1 (even lane: x = -1, odd lane: x = 0)
+    s.DE[0] = 0x70000000u | ((u32)(extp + ext) & 0xFFFFu);   // absolute 0 at (x=-1,y=-1)
+    s.MO[0] = 0x70000000u | ((u32)extp & 0xFFFFu);           // absolute 0 at (x=0,y=-1)
+    s.DO[0] = s.MO[0];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) s.P[m] = 0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        HapRec r = rec[m];
+        s.Wg[m] = r.gow;
+        s.Ws[m] = r.sel;
+    }
+#pragma unroll
+    for (int m = 4; m < 8; ++m) s.Wg[m] = s.Ws[m] = 0;
+
+    const int n = dp_steps(L);
+    dp_group6<true, false>(s, prof, rec, 0, L, ext, extp);
+    int t0 = 8;
+    for (; t0 < n - 16; t0 += 8) dp_group6<false, false>(s, prof, rec, t0, L, ext, extp);
+    dp_group6<false, true>(s, prof, rec, t0, L, ext, extp);
+    dp_group6<false, true>(s, prof, rec, t0 + 8, L, ext, extp);
+    u32 a = vmin2(vmin2(s.acc[0], s.acc[1]), vmin2(s.acc[2], s.acc[3]));
+    int lo = (int)(int16_t)(a & 0xFFFF), hi = (int)(int16_t)(a >> 16);
+    // relative -> absolute: + (ext+nuc)*(L-1) + ext*x with x = (L-1) + d; ext*d was added per lane
+    return (lo < hi ? lo : hi) + (extp + ext) * (L - 1);
+}
+
 // General path: arbitrary bytes, any read length >= 1.  Same recurrence cell by cell
 // (SURVEY §3.3), 32-bit scalars.  hap/open point at segment position 0.
 PLB_HD int band_dp_general(const uint8_t* __restrict__ hap, const uint8_t* __restrict__ open,

@@ -60,7 +60,7 @@ struct DevBatch {
     const int64_t* ll_off;     // [n_windows*nInd+1]
     // scratch
     uint8_t* gap_open;         // haplotype h: hapLen+1 entries at hap_seq_off[h] + h
-    uint8_t* win_general;      // [n_windows] 1 = haplotypes contain bytes outside ACGTN
+    uint32_t* win_flags;       // [n_windows] bit0 = haplotype bytes outside ACGTN, bit1 = contains 'N'
     int32_t* cand0;            // [n_pairs] first / second packed-path start offset, -1 = none
     int32_t* cand1;
     int32_t* score;            // [n_pairs] running min over general-path alignments
@@ -88,6 +88,7 @@ struct Queue {
 
 struct Counters {  // device-side statistics
     unsigned long long n_pairs, n_scored, n_dp, cells;
+    unsigned long long n_heavy, n_verify, n_exact;  // n_exact: anchor pairs that needed the exact vote array
 };
 
 struct ScoreParams {
@@ -138,16 +139,22 @@ __global__ void __launch_bounds__(128) k_prep(DevBatch b) {
     const int len = (int)(b.hap_seq_off[h + 1] - b.hap_seq_off[h]);
     const uint8_t* hap = b.hap_seq + b.hap_seq_off[h];
     uint8_t* go = b.gap_open + b.hap_seq_off[h] + h;
-    int bad = 0;
+    int bad = 0, has_n = 0;
     for (int i = threadIdx.x; i <= len; i += blockDim.x) {
         if (i < len) {
             go[i] = gap_open_at(hap, len, i);
-            bad |= (fast_code(hap[i]) == 5);
+            const int c = fast_code(hap[i]);
+            bad |= (c == 5);
+            has_n |= (c == 4);
         } else {
             go[i] = 0;
         }
     }
-    if (__syncthreads_or(bad) && threadIdx.x == 0) b.win_general[b.hap_win[h]] = 1;
+    bad = __syncthreads_or(bad);
+    has_n = __syncthreads_or(has_n);
+    // bit 0: bytes outside ACGTN (general path); bit 1: contains 'N' (8-op packed variant)
+    if ((bad || has_n) && threadIdx.x == 0)
+        atomicOr((unsigned int*)(b.win_flags + b.hap_win[h]), (bad ? 1u : 0u) | (has_n ? 2u : 0u));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -187,6 +194,7 @@ struct SlotInfo {
     int32_t pos;      // read.pos
     int32_t hoff;     // offset into the read-id area
     int32_t flags;    // bit0 = LL forced to 0 (QC fail / overlap < 7)
+    int32_t vub;      // upper bound of the votes this read can cast on any haplotype of the sub-group
 };
 
 __device__ __forceinline__ int read_overlap(int ws, int we, int rp, int re) {  // chaplotype.pyx:103-115
@@ -246,15 +254,119 @@ __device__ __forceinline__ u32 tab_lookup(const u32* tab, int bits, u32 key) {
     }
 }
 
+// Light pass.  A read 7-mer i votes for offset idx iff the haplotype carries the same 7-mer at
+// position i+idx, so the number of votes for ONE offset is an element-wise comparison of the read's
+// id row with the haplotype's id row shifted by idx - no chains, no gathers.
+__device__ __forceinline__ int count_offset(const uint4* rid4, const uint16_t* hid0, int nk_read, int nk_hap, int idx) {
+    const uint16_t* hid = hid0 + idx;
+    const int lo = idx < 0 ? -idx : 0;
+    const int hi = min(nk_read, nk_hap - idx);
+    int c = 0;
+    int i8 = lo & ~7;
+    if (i8 < lo && i8 < hi) {  // ragged first block
+        const uint4 v = rid4[i8 >> 3];
+        const u32 ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = i8 + k;
+            const u32 id = (ws[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+            if (i >= lo && i < hi) c += (id == (u32)hid[i]);
+        }
+        i8 += 8;
+    }
+    for (; i8 + 8 <= hi; i8 += 8) {  // full blocks
+        const uint4 v = rid4[i8 >> 3];
+        const u32 ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const u32 id = (ws[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+            c += (id == (u32)hid[i8 + k]);
+        }
+    }
+    if (i8 < hi) {  // ragged last block
+        const uint4 v = rid4[i8 >> 3];
+        const u32 ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = i8 + k;
+            const u32 id = (ws[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+            if (i < hi) c += (id == (u32)hid[i]);
+        }
+    }
+    return c;
+}
+
+// Decides a pair without a vote array when it can.  Guesses: the offsets implied by the first, the
+// last and the middle read 7-mer that occur exactly once in the haplotype.  Each guess is counted
+// exactly with count_offset; everything not yet counted is bounded by R = V_ub - (counted votes),
+// where V_ub bounds ALL votes the read can cast.  As soon as the best counted offset beats R, no
+// uncounted offset can reach it, so the maximum of the reference's vote array (calign.pyx:206-220)
+// is attained exactly at the counted offsets with that count - unique or tied.
+// res[0..2] = tied-maximum offsets + 1 (kNoCand where unused); returns 1 when decided, else 0.
+constexpr int kNoCand = 0x40000000;
+constexpr int kPairSkip = 0x40000001;       // nothing to decide (LL forced to 0 / read shorter than 7)
+constexpr int kPairUndecided = 0x40000002;  // goes to the exact vote array
+
+struct LightArgs {
+    u32 head_off, rid_off, hid_off, res_off;
+    int nk_read, nk_hap, vub;
+};
+
+__device__ __forceinline__ int unique_hit_offset(const uint16_t* head, const uint16_t* rid, int i0, int i1, int step) {
+    for (int i = i0; i != i1; i += step) {
+        const u32 hd = head[rid[i]];
+        if (hd && !(hd & 0x8000u)) return (int)hd - 1 - i;
+    }
+    return kNoCand;
+}
+
+__device__ __noinline__ int light_decide(LightArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint16_t* head = (const uint16_t*)(smem + a.head_off);
+    const uint16_t* rid = (const uint16_t*)(smem + a.rid_off);
+    const uint16_t* hid0 = (const uint16_t*)(smem + a.hid_off);
+    const uint4* rid4 = (const uint4*)rid;
+    u32* res = (u32*)(smem + a.res_off);
+    const int nk = a.nk_read;
+    if (a.vub == 0) {  // no read 7-mer occurs in this haplotype group: maxcount == 0, no candidates
+        res[0] = res[1] = res[2] = (u32)kNoCand;
+        return 1;
+    }
+    const int lim = min(nk, 24);
+    int g[3], c[3] = {0, 0, 0};
+    g[0] = unique_hit_offset(head, rid, 0, lim, 1);
+    g[1] = unique_hit_offset(head, rid, nk - 1, nk - 1 - lim, -1);
+    const int mid = nk >> 1;
+    g[2] = unique_hit_offset(head, rid, mid, min(nk, mid + lim), 1);
+    if (g[1] == g[0]) g[1] = kNoCand;
+    if (g[2] == g[0] || g[2] == g[1]) g[2] = kNoCand;
+    int R = a.vub, top = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        if (g[j] == kNoCand) continue;
+        c[j] = count_offset(rid4, hid0, nk, a.nk_hap, g[j]);
+        R -= c[j];
+        top = max(top, c[j]);
+        if (top > R) break;
+    }
+    if (!(top > R) || top == 0) return 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) res[j] = (u32)((g[j] != kNoCand && c[j] == top) ? g[j] + 1 : kNoCand);
+    return 1;
+}
+
 __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, AnchorPlan plan, Queue q, ScoreParams sp,
                                                            Counters* ctr) {
     extern __shared__ __align__(16) uint8_t smem[];
     u32* s_tab = (u32*)smem;
     u32* s_cnt = s_tab + (1 << plan.tab_bits);
     u32* s_fblist = s_cnt + (size_t)plan.n_cnt * plan.cnt_words;
-    uint16_t* s_rid = (uint16_t*)(s_fblist + plan.max_pairs);
+    u32* s_vlist = s_fblist + plan.max_pairs;                 // per pair: up to three tied-maximum offsets
+    uint16_t* s_rid = (uint16_t*)(s_vlist + 3 * (size_t)plan.max_pairs);
     uint16_t* s_next = s_rid + plan.rid_halfs;
-    uint16_t* s_heads = s_next + plan.next_halfs;
+    uint16_t* s_hid = s_next + plan.next_halfs;               // per haplotype position: id of its 7-mer
+    uint16_t* s_mult = s_hid + plan.next_halfs;               // per id: upper bound of its multiplicity in a haplotype
+    uint16_t* s_heads = s_mult + plan.heads_halfs;
     SlotInfo* s_slot = (SlotInfo*)(((uintptr_t)(s_heads + plan.heads_halfs) + 15) & ~(uintptr_t)15);
     int32_t* s_hmeta = (int32_t*)(s_slot + plan.max_slots);  // per hap: len, next offset
     __shared__ int s_nid, s_nfb, s_scan[kAnchorThreads / 32];
@@ -298,6 +410,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
                 if (b.read_qcfail[r] || ov < kKmer) si.flags = 1;
             }
             si.hoff = 0;
+            si.vub = 0;
             s_slot[s] = si;
         }
         __syncthreads();
@@ -374,7 +487,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
                 }
             }
         }
-        const int general = b.win_general[w];
+        const int general = b.win_flags[w] & 1;
         const int hstride = U + 1;
         const int sub_max = max(1, min(nh, plan.heads_halfs / hstride));
         for (int g0 = 0; g0 < nh; g0 += sub_max) {
@@ -382,130 +495,140 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
             __syncthreads();
             // ---- chains of this haplotype sub-group (calign.pyx:94-124) ----
             for (int i = tid; i < (g1 - g0) * hstride; i += nthr) s_heads[i] = 0;
+            for (int i = tid; i < hstride; i += nthr) s_mult[i] = i ? 1 : 0;
             __syncthreads();
             for (int g = g0; g < g1; ++g) {
                 const int len = s_hmeta[2 * g];
                 const uint8_t* hap = b.hap_seq + b.hap_seq_off[tile.h0 + g];
                 uint16_t* nxt = s_next + s_hmeta[2 * g + 1];
                 unsigned short* head = (unsigned short*)(s_heads + (g - g0) * hstride);
+                uint16_t* hid = s_hid + s_hmeta[2 * g + 1];
                 for (int i = tid; i < len - kKmer; i += nthr) {
                     const u32 id = tab_lookup(s_tab, bits, kmer_hash(hap + i));
+                    hid[i] = (uint16_t)id;
                     unsigned short cur = head[id];
-                    while (true) {  // push position i (stored as i+1); order inside a chain is irrelevant
-                        nxt[i + 1] = cur;
-                        const unsigned short old = atomicCAS(&head[id], cur, (unsigned short)(i + 1));
+                    while (true) {  // push position i (stored as i+1); order inside a chain is irrelevant.
+                        // bit 15 of the head marks chains with more than one element.
+                        nxt[i + 1] = cur & 0x7FFFu;
+                        const unsigned short nv = (unsigned short)((i + 1) | (cur ? 0x8000u : 0u));
+                        const unsigned short old = atomicCAS(&head[id], cur, nv);
                         if (old == cur) break;
                         cur = old;
                     }
                 }
             }
             __syncthreads();
-            // ---- per (slot, haplotype) pair: majority vote ----
-            const int npairs = ns * (g1 - g0);
-            for (int p = tid; p < npairs; p += nthr) {
-                const int s = p % ns, g = g0 + p / ns;
+            // multiplicity bound per id (1 unless some haplotype repeats the 7-mer), then per read the
+            // bound V_ub >= number of votes it can cast on any haplotype of this sub-group
+            for (int i = tid; i < (g1 - g0) * hstride; i += nthr) {
+                const u32 hd = s_heads[i];
+                if (hd & 0x8000u) {
+                    const int g = g0 + i / hstride, id = i % hstride;
+                    const uint16_t* nxt = s_next + s_hmeta[2 * g + 1];
+                    unsigned short len = 0;
+                    for (u32 p1 = hd & 0x7FFFu; p1; p1 = nxt[p1]) ++len;
+                    unsigned short cur = s_mult[id];
+                    while (cur < len) {
+                        const unsigned short old = atomicCAS((unsigned short*)&s_mult[id], cur, len);
+                        if (old == cur) break;
+                        cur = old;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int s = warp; s < ns; s += nwarp) {
                 const SlotInfo si = s_slot[s];
-                const int h = tile.h0 + g;
-                const int64_t gs = tile.s0 + s;
+                const int nk = si.len - kKmer;
+                if ((si.flags & 1) || nk <= 0) continue;
+                int sum = 0;
+                for (int i = lane; i < nk; i += 32) sum += s_mult[s_rid[si.hoff + i]];
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+                if (lane == 0) s_slot[s].vub = sum;
+            }
+            __syncthreads();
+            // ---- per (slot, haplotype) pair: light decision, else exact vote array ----
+            const int npairs = ns * (g1 - g0);
+            auto pair_id = [&](int p, int& s, int& g, int64_t& gs, int64_t& pair) {
+                s = p % ns;
+                g = g0 + p / ns;
+                gs = tile.s0 + s;
                 const int wi = b.slot_wi[gs];
                 const int64_t T = b.wi_slot_off[wi + 1] - b.wi_slot_off[wi];
-                const int64_t pair = b.ll_off[wi] + (int64_t)(h - b.win_hap_off[w]) * T + (gs - b.wi_slot_off[wi]);
+                pair = b.ll_off[wi] + (int64_t)(tile.h0 + g - b.win_hap_off[w]) * T + (gs - b.wi_slot_off[wi]);
+            };
+            for (int p = tid; p < npairs; p += nthr) {
+                int s, g;
+                int64_t gs, pair;
+                pair_id(p, s, g, gs, pair);
+                const SlotInfo si = s_slot[s];
                 ++st_pairs;
+                if ((si.flags & 1) || si.len < kKmer) {  // LL forced to 0, or calign.pyx:182-183 (score 0)
+                    b.cand0[pair] = -1;
+                    b.cand1[pair] = -1;
+                    b.score[pair] = (si.flags & 1) ? -1 : 0;
+                    if (!(si.flags & 1)) {
+                        ++st_scored;
+                        st_cells += 16ull * si.len;
+                    }
+                    s_vlist[3 * p] = (u32)kPairSkip;
+                    continue;
+                }
+                ++st_scored;
+                st_cells += 16ull * si.len;
+                LightArgs la;
+                la.head_off = (u32)((uint8_t*)(s_heads + (g - g0) * hstride) - smem);
+                la.rid_off = (u32)((uint8_t*)(s_rid + si.hoff) - smem);
+                la.hid_off = (u32)((uint8_t*)(s_hid + s_hmeta[2 * g + 1]) - smem);
+                la.res_off = (u32)((uint8_t*)(s_vlist + 3 * p) - smem);
+                la.nk_read = si.len - kKmer;
+                la.nk_hap = s_hmeta[2 * g] - kKmer;
+                la.vub = si.vub;
+                if (!light_decide(la)) {
+                    s_vlist[3 * p] = (u32)kPairUndecided;
+                    s_fblist[atomicAdd(&s_nfb, 1)] = (u32)p;
+                }
+            }
+            __syncthreads();
+            // ---- emit the band starts of the decided pairs ----
+            for (int p = tid; p < npairs; p += nthr) {
+                const int c0 = (int)s_vlist[3 * p];
+                if (c0 == kPairSkip || c0 == kPairUndecided) continue;
+                int s, g;
+                int64_t gs, pair;
+                pair_id(p, s, g, gs, pair);
+                const SlotInfo si = s_slot[s];
+                const int L = si.len, hap_len = s_hmeta[2 * g], h = tile.h0 + g;
                 Emitter em;
                 em.c0 = em.c1 = -1;
                 em.sc = kScoreNone;
                 em.n_dp = 0;
-                bool done = true;
-                if (si.flags & 1) {
-                    em.sc = -1;
-                } else if (si.len < kKmer) {
-                    em.sc = 0;  // calign.pyx:182-183
-                    ++st_scored;
-                    st_cells += 16ull * si.len;
-                } else {
-                    ++st_scored;
-                    st_cells += 16ull * si.len;
-                    const int L = si.len, nk = L - kKmer;
-                    const int hap_len = s_hmeta[2 * g];
-                    const uint16_t* nxt = s_next + s_hmeta[2 * g + 1];
-                    const uint16_t* head = s_heads + (g - g0) * hstride;
-                    const uint4* rid4 = (const uint4*)(s_rid + si.hoff);
-                    // pass 1: Boyer-Moore majority candidate over the vote stream (vote = offset p-i)
-                    int cand = 0, wgt = 0, V = 0;
-                    for (int i8 = 0; i8 < nk; i8 += 8) {
-                        const uint4 v = rid4[i8 >> 3];
-                        const u32 ws[4] = {v.x, v.y, v.z, v.w};
+                int idx0 = si.pos - b.hap_start[w];  // fallback position (calign.pyx:252-256)
+                const int lim = hap_len - L - 15;
+                if (lim < idx0) idx0 = lim;
+                const bool slow = general || L < kMinFastLen || L > kMaxFastLen;
+                bool any_accepted = false;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const u32 id = (ws[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-                            if (id) {
-                                u32 p1 = head[id];
-                                while (p1) {
-                                    const int o = (int)p1 - (i8 + k);
-                                    ++V;
-                                    if (wgt == 0) {
-                                        cand = o;
-                                        wgt = 1;
-                                    } else {
-                                        wgt += (o == cand) ? 1 : -1;
-                                    }
-                                    p1 = nxt[p1];
-                                }
-                            }
-                        }
-                    }
-                    // pass 2: exact count of the candidate
-                    int cc = 0;
-                    if (V > 0) {
-                        for (int i8 = 0; i8 < nk; i8 += 8) {
-                            const uint4 v = rid4[i8 >> 3];
-                            const u32 ws[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const u32 id = (ws[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-                                if (id) {
-                                    u32 p1 = head[id];
-                                    while (p1) {
-                                        cc += ((int)p1 - (i8 + k) == cand);
-                                        p1 = nxt[p1];
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    if (V > 0 && 2 * cc <= V) {
-                        done = false;  // no strict majority: exact tie scan by a warp, below
-                        s_fblist[atomicAdd(&s_nfb, 1)] = (u32)p;
-                    } else {
-                        // fallback position (calign.pyx:252-256)
-                        int idx0 = si.pos - b.hap_start[w];
-                        const int lim = hap_len - L - 15;
-                        if (lim < idx0) idx0 = lim;
-                        const bool slow = general || L < kMinFastLen;
-                        bool any_accepted = false;
-                        if (V > 0) {
-                            const int idx = cand - 1;  // p1 stores position+1
-                            if (idx + L + 15 < hap_len) {  // calign.pyx:228
-                                any_accepted = true;
-                                em.emit(b, q, sp, slow, pair, h, gs, si.read, L, idx > 8 ? idx - 8 : 0);
-                            }
-                        }
-                        // with no accepted candidate bestMappingPosition stays -1, so a fallback index of
-                        // exactly -1 is skipped and the sentinel 1000000 is returned (calign.pyx:258, 272)
-                        if (any_accepted || idx0 != -1)
-                            em.emit(b, q, sp, slow, pair, h, gs, si.read, L, idx0 > 8 ? idx0 - 8 : 0);
+                for (int j = 0; j < 3; ++j) {
+                    const int cj = (int)s_vlist[3 * p + j];
+                    if (cj == kNoCand) continue;
+                    const int idx = cj - 1;
+                    if (idx + L + 15 < hap_len) {  // calign.pyx:228
+                        any_accepted = true;
+                        em.emit(b, q, sp, slow, pair, h, gs, si.read, L, idx > 8 ? idx - 8 : 0);
                     }
                 }
-                if (done) {
-                    st_dp += em.n_dp;
-                    b.cand0[pair] = em.c0;
-                    b.cand1[pair] = em.c1;
-                    b.score[pair] = em.sc;
-                }
+                // with no accepted candidate bestMappingPosition stays -1, so a fallback index of
+                // exactly -1 is skipped and the sentinel 1000000 is returned (calign.pyx:258, 272)
+                if (any_accepted || idx0 != -1) em.emit(b, q, sp, slow, pair, h, gs, si.read, L, idx0 > 8 ? idx0 - 8 : 0);
+                st_dp += em.n_dp;
+                b.cand0[pair] = em.c0;
+                b.cand1[pair] = em.c1;
+                b.score[pair] = em.sc;
             }
             __syncthreads();
-            // ---- pairs without a strict majority: exact vote array per warp (calign.pyx:206-247) ----
+            // ---- undecided pairs: exact vote array per warp (calign.pyx:206-247) ----
             const int nfb = s_nfb;
+            if (tid == 0 && ctr) atomicAdd(&ctr->n_exact, (unsigned long long)nfb);
             const int n_fbw = min(nwarp, plan.n_cnt);  // warps that own a counter array
             for (int f = warp; f < nfb && warp < n_fbw; f += n_fbw) {
                 const int p = (int)s_fblist[f];
@@ -529,7 +652,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
                 for (int i = lane; i < nk; i += 32) {
                     const u32 id = rid[i];
                     if (!id) continue;
-                    u32 p1 = head[id];
+                    u32 p1 = head[id] & 0x7FFFu;
                     while (p1) {
                         const int o = (int)p1 - i - 1 + L;  // index pos + readLen, calign.pyx:213-215
                         atomicAdd(&cw[o >> 1], 1u << (16 * (o & 1)));
@@ -547,7 +670,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
                 em.c0 = em.c1 = -1;
                 em.sc = kScoreNone;
                 em.n_dp = 0;
-                const bool slow = general || L < kMinFastLen;
+                const bool slow = general || L < kMinFastLen || L > kMaxFastLen;
                 bool any_accepted = false;
                 for (int base = 0; base < C; base += 32) {  // ascending offsets, calign.pyx:223
                     const int o = base + lane;
@@ -689,7 +812,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
             for (int s = 0; s < ns; ++s) {
                 s_slot[s].poff = o;
                 const int L = s_slot[s].len;
-                if (!(s_slot[s].flags & 1) && L >= kMinFastLen) {
+                if (!(s_slot[s].flags & 1) && L >= kMinFastLen && L <= kMaxFastLen) {
                     int n = dp_steps(L) + 4;           // rows read by the kernel, +4 keeps rows 16-byte apart
                     n = (n + 3) & ~3;
                     if (!((n >> 2) & 1)) n += 4;       // odd multiple of 16 bytes: conflict-free LDS.128
@@ -698,19 +821,28 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
             }
         }
         __syncthreads();
-        const int general = b.win_general[w];
+        const u32 wflags = b.win_flags[w];
+        const int general = wflags & 1;
+        const bool six = !(wflags & 2);   // no 'N' in the window's haplotypes: 6-op variant
+        const int K = 2 * sp.ext + sp.nuc;
         // profiles: one warp per read row, lanes along the read (coalesced byte loads)
         if (!general) {
             const int warp = tid >> 5, lane = tid & 31, nwarp = NTHR >> 5;
             for (int s = warp; s < ns; s += nwarp) {
                 const DpSlot ds = s_slot[s];
-                if ((ds.flags & 1) || ds.len < kMinFastLen) continue;
+                if ((ds.flags & 1) || ds.len < kMinFastLen || ds.len > kMaxFastLen) continue;
                 const uint8_t* rs = b.read_seq + b.read_seq_off[ds.read];
                 const uint8_t* rq = b.read_qual + b.read_seq_off[ds.read];
                 int n = dp_steps(ds.len) + 4;
                 u32* row = s_prof + ds.poff;
-                for (int y = lane; y < n; y += 32)
-                    row[y] = y < ds.len ? make_profile(fast_code(rs[y]), rq[y]) : 0u;
+                for (int y = lane; y < n; y += 32) {
+                    u32 v = 0u;
+                    if (y < ds.len) {
+                        const int code = fast_code(rs[y]);
+                        v = six ? make_profile6(code, rq[y], K) : make_profile(code, rq[y]);
+                    }
+                    row[y] = v;
+                }
             }
             // haplotype records
             for (int g = 0; g < nh; ++g) {
@@ -725,8 +857,13 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                     const u32 oa = x <= len ? go[x] : 0u;
                     const u32 ob = x + 4 <= len ? go[x + 4] : 0u;
                     HapRec r;
-                    r.gow = oa | (ob << 16);
-                    r.sel = make_sel(ca, cb);
+                    if (six) {
+                        r.gow = pack_s16x2((int)oa - sp.ext, (int)ob - sp.ext);
+                        r.sel = make_sel6(ca < 4 ? ca : 0, cb < 4 ? cb : 0);
+                    } else {
+                        r.gow = oa | (ob << 16);
+                        r.sel = make_sel(ca, cb);
+                    }
                     rec[x] = r;
                 }
             }
@@ -770,7 +907,8 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
             const int p = (int)(tk >> 15), start = (int)(tk & 0x7FFFu);
             const int s = p % ns, g = p / ns;
             const DpSlot ds = s_slot[s];
-            const int v = band_dp_fast(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc);
+            const int v = six ? band_dp_fast6(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc)
+                              : band_dp_fast(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc);
             atomicMin(&s_best[p], v);
         }
         __syncthreads();

@@ -13,7 +13,7 @@ static uint32_t rnd() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (u
 
 int main(int argc, char** argv) {
     int n_cases = argc > 1 ? atoi(argv[1]) : 3000;
-    int bad = 0, bad_gen = 0;
+    int bad = 0, bad_gen = 0, n6 = 0;
     const char* alpha = "ACGT";
     for (int c = 0; c < n_cases; ++c) {
         int L = 9 + rnd() % 260;
@@ -52,8 +52,26 @@ int main(int argc, char** argv) {
         int got = plb::band_dp_fast(prof.data(), rec.data() + x0, L, ext, nuc);
         int gen = plb::band_dp_general(hap.data() + x0, open.data() + x0, read.data(), qual.data(), L, ext, nuc);
         if (got != want) { if (++bad < 6) printf("fast mismatch L=%d x0=%d want=%d got=%d\n", L, x0, want, got); }
+        // 6-op variant: only defined for segments without 'N'
+        bool has_n = false;
+        for (int x = x0; x < x0 + L + 15 && x < hapLen; ++x) has_n |= hap[x] == 'N';
+        if (!has_n) {
+            const int K = 2 * ext + nuc;
+            std::vector<plb::u32> prof6(n + 8, 0);
+            for (int y = 0; y < L; ++y) prof6[y] = plb::make_profile6(plb::fast_code(read[y]), qual[y], K);
+            std::vector<plb::HapRec> rec6(rec.size());
+            for (size_t x = 0; x < rec6.size(); ++x) {
+                auto code = [&](size_t p) { int c = p < (size_t)hapLen ? plb::fast_code(hap[p]) : 0; return c < 4 ? c : 0; };
+                auto go = [&](size_t p) { return (p <= (size_t)hapLen ? (int)open[p] : 0) - ext; };
+                rec6[x].gow = plb::pack_s16x2(go(x), go(x + 4));
+                rec6[x].sel = plb::make_sel6(code(x), code(x + 4));
+            }
+            int got6 = plb::band_dp_fast6(prof6.data(), rec6.data() + x0, L, ext, nuc);
+            if (got6 != want) { if (++bad < 6) printf("fast6 mismatch L=%d x0=%d want=%d got=%d\n", L, x0, want, got6); }
+            ++n6;
+        }
         if (gen != want) { if (++bad_gen < 6) printf("general mismatch L=%d want=%d got=%d\n", L, want, gen); }
     }
-    printf("mismatches %d general %d of %d\n", bad, bad_gen, n_cases);
+    printf("mismatches %d general %d of %d (%d through the 6-op variant)\n", bad, bad_gen, n_cases, n6);
     return (bad || bad_gen) ? 1 : 0;
 }

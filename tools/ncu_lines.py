@@ -17,5 +17,6 @@ for r in rows:
         lines.append((ie, sm, cur_file, r[0], r[1].strip()[:110], d.get("L1 Wavefronts Shared Excessive", "0")))
 tot_i = sum(l[0] for l in lines); tot_s = sum(l[1] for l in lines)
 print("total instr %d samples %d" % (tot_i, tot_s))
-for l in sorted(lines, key=lambda x: -x[0])[:top]:
+key = (lambda x: -x[1]) if (len(sys.argv) > 3 and sys.argv[3] == "samp") else (lambda x: -x[0])
+for l in sorted(lines, key=key)[:top]:
     print("%5.1f%% inst %5.1f%% samp  %s:%s  %s   [smem excess wf %s]" % (100.0*l[0]/max(tot_i,1), 100.0*l[1]/max(tot_s,1), l[2], l[3], l[4], l[5]))
