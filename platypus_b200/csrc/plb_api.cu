@@ -327,12 +327,14 @@ static int plan_tiles(const PlbWindowBatch* hb, TileLists& tl, AnchorPlan& ap, D
             }
             groups.push_back({g0, h1});
             for (auto& g : groups) {
-                int nh_ = 0, sum_nk = 0;
+                int nh_ = 0, sum_nk = 0, hpk = 0;
                 for (int h = g.first; h < g.second; ++h) {
                     const int len = (int)(hb->hap_seq_off[h + 1] - hb->hap_seq_off[h]);
                     nh_ += (len + 2) & ~1;
                     sum_nk += std::max(0, len - kKmer);
+                    hpk += ((len + 15) >> 4) + 2 * kPackPadWords;
                 }
+                ap.hpk_words = std::max(ap.hpk_words, hpk);
                 int bits = 6;
                 while ((1 << bits) < 2 * sum_nk && bits < 14) ++bits;
                 ap.tab_bits = std::max(ap.tab_bits, bits);
@@ -345,7 +347,7 @@ static int plan_tiles(const PlbWindowBatch* hb, TileLists& tl, AnchorPlan& ap, D
             int maxg = 1;
             for (auto& g : groups) maxg = std::max(maxg, g.second - g.first);
             int64_t c0 = s0;
-            size_t halfs = 0;
+            size_t halfs = 0, pkw = 0;
             auto flush = [&](int64_t c1) {
                 if (c1 <= c0) return;
                 for (auto& g : groups) {
@@ -354,16 +356,20 @@ static int plan_tiles(const PlbWindowBatch* hb, TileLists& tl, AnchorPlan& ap, D
                 }
                 ap.max_slots = std::max<int>(ap.max_slots, (int)(c1 - c0));
                 ap.rid_halfs = std::max<int>(ap.rid_halfs, (int)halfs);
+                ap.rpk_words = std::max<int>(ap.rpk_words, (int)pkw);
             };
             for (int64_t s = s0; s < s1; ++s) {
-                const int nk = (std::max(0, slot_len[(size_t)(s - s0)] - kKmer) + 7) & ~7;
+                const int len = slot_len[(size_t)(s - s0)];
+                const int nk = (std::max(0, len - kKmer) + 7) & ~7;
                 if (s > c0 && (2 * (halfs + nk) > kAnchorHashBudget || s - c0 >= kAnchorMaxSlots ||
                                (s - c0 + 1) * maxg > kAnchorMaxPairs)) {
                     flush(s);
                     c0 = s;
                     halfs = 0;
+                    pkw = 0;
                 }
                 halfs += nk;
+                pkw += ((len + 15) >> 4) + kPackPadWords;
             }
             flush(s1);
         }
@@ -470,6 +476,8 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
         AnchorPlan& ap = db->aplan;
         ap.max_pairs = (ap.max_pairs + 3) & ~3;
         ap.rid_halfs = (ap.rid_halfs + 7) & ~7;
+        ap.rpk_words = (ap.rpk_words + 3) & ~3;
+        ap.hpk_words = (ap.hpk_words + 3) & ~3;
         ap.next_halfs = (ap.next_halfs + 7) & ~7;
         ap.heads_halfs = std::max(ap.heads_halfs, 4096);
         ap.heads_halfs = (ap.heads_halfs + 7) & ~7;
@@ -478,8 +486,9 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
         const int nwarps = kAnchorThreads / 32;
         ap.n_cnt = (int)std::max<size_t>(1, std::min<size_t>(nwarps, kAnchorCntBudget / ((size_t)ap.cnt_words * 4)));
         db->a_smem = ((size_t)4 << ap.tab_bits) + (size_t)ap.n_cnt * ap.cnt_words * 4 + (size_t)ap.max_pairs * 16 +
-                     (size_t)ap.rid_halfs * 2 + (size_t)ap.next_halfs * 4 + (size_t)ap.heads_halfs * 4 + 16 +
-                     (size_t)ap.max_slots * sizeof(SlotInfo) + (size_t)ap.max_group * 8 + 16;
+                     (size_t)(ap.rpk_words + ap.hpk_words) * 4 + (size_t)ap.rid_halfs * 2 + (size_t)ap.next_halfs * 2 +
+                     (size_t)ap.heads_halfs * 4 + 16 + (size_t)ap.max_slots * sizeof(SlotInfo) +
+                     (size_t)ap.max_group * 12 + 16;
     }
     if (db->a_smem + 1024 > (size_t)c->smem_optin) {
         size_t need = db->a_smem;

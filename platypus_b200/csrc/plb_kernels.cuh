@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include "plb_dp.cuh"
+#include "plb_kmer.cuh"
 
 namespace plb {
 
@@ -184,6 +185,8 @@ struct AnchorPlan {
     int32_t next_halfs;     // u16 entries for all next arrays of a group
     int32_t rid_halfs;      // u16 entries for the read 7-mer ids of a tile
     int32_t heads_halfs;    // u16 entries of the head area (>= largest union size + 1)
+    int32_t rpk_words;      // u32 words for the 2-bit packed reads of a tile
+    int32_t hpk_words;      // u32 words for the 2-bit packed haplotypes of a group
     int32_t cnt_words;      // u32 words of one warp's counter array (2 counters per word)
     int32_t n_cnt;          // counter arrays available in shared memory (>= 1)
 };
@@ -195,6 +198,7 @@ struct SlotInfo {
     int32_t hoff;     // offset into the read-id area
     int32_t flags;    // bit0 = LL forced to 0 (QC fail / overlap < 7)
     int32_t vub;      // upper bound of the votes this read can cast on any haplotype of the sub-group
+    int32_t poff;     // offset (u32 words) of the 2-bit packed read
 };
 
 __device__ __forceinline__ int read_overlap(int ws, int we, int rp, int re) {  // chaplotype.pyx:103-115
@@ -254,48 +258,6 @@ __device__ __forceinline__ u32 tab_lookup(const u32* tab, int bits, u32 key) {
     }
 }
 
-// Light pass.  A read 7-mer i votes for offset idx iff the haplotype carries the same 7-mer at
-// position i+idx, so the number of votes for ONE offset is an element-wise comparison of the read's
-// id row with the haplotype's id row shifted by idx - no chains, no gathers.
-__device__ __forceinline__ int count_offset(const uint4* rid4, const uint16_t* hid0, int nk_read, int nk_hap, int idx) {
-    const uint16_t* hid = hid0 + idx;
-    const int lo = idx < 0 ? -idx : 0;
-    const int hi = min(nk_read, nk_hap - idx);
-    int c = 0;
-    int i8 = lo & ~7;
-    if (i8 < lo && i8 < hi) {  // ragged first block
-        const uint4 v = rid4[i8 >> 3];
-        const u32 ws[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int i = i8 + k;
-            const u32 id = (ws[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-            if (i >= lo && i < hi) c += (id == (u32)hid[i]);
-        }
-        i8 += 8;
-    }
-    for (; i8 + 8 <= hi; i8 += 8) {  // full blocks
-        const uint4 v = rid4[i8 >> 3];
-        const u32 ws[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const u32 id = (ws[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-            c += (id == (u32)hid[i8 + k]);
-        }
-    }
-    if (i8 < hi) {  // ragged last block
-        const uint4 v = rid4[i8 >> 3];
-        const u32 ws[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int i = i8 + k;
-            const u32 id = (ws[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-            if (i < hi) c += (id == (u32)hid[i]);
-        }
-    }
-    return c;
-}
-
 // Decides a pair without a vote array when it can.  Guesses: the offsets implied by the first, the
 // last and the middle read 7-mer that occur exactly once in the haplotype.  Each guess is counted
 // exactly with count_offset; everything not yet counted is bounded by R = V_ub - (counted votes),
@@ -308,7 +270,7 @@ constexpr int kPairSkip = 0x40000001;       // nothing to decide (LL forced to 0
 constexpr int kPairUndecided = 0x40000002;  // goes to the exact vote array
 
 struct LightArgs {
-    u32 head_off, rid_off, hid_off, res_off;
+    u32 head_off, rid_off, rpk_off, hpk_off, res_off;
     int nk_read, nk_hap, vub;
 };
 
@@ -324,8 +286,8 @@ __device__ __noinline__ int light_decide(LightArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint16_t* head = (const uint16_t*)(smem + a.head_off);
     const uint16_t* rid = (const uint16_t*)(smem + a.rid_off);
-    const uint16_t* hid0 = (const uint16_t*)(smem + a.hid_off);
-    const uint4* rid4 = (const uint4*)rid;
+    const u32* rpk = (const u32*)(smem + a.rpk_off);
+    const u32* hpk = (const u32*)(smem + a.hpk_off);
     u32* res = (u32*)(smem + a.res_off);
     const int nk = a.nk_read;
     if (a.vub == 0) {  // no read 7-mer occurs in this haplotype group: maxcount == 0, no candidates
@@ -344,7 +306,7 @@ __device__ __noinline__ int light_decide(LightArgs a) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         if (g[j] == kNoCand) continue;
-        c[j] = count_offset(rid4, hid0, nk, a.nk_hap, g[j]);
+        c[j] = count_offset_bits(rpk, hpk, nk, a.nk_hap, g[j]);
         R -= c[j];
         top = max(top, c[j]);
         if (top > R) break;
@@ -362,13 +324,14 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
     u32* s_cnt = s_tab + (1 << plan.tab_bits);
     u32* s_fblist = s_cnt + (size_t)plan.n_cnt * plan.cnt_words;
     u32* s_vlist = s_fblist + plan.max_pairs;                 // per pair: up to three tied-maximum offsets
-    uint16_t* s_rid = (uint16_t*)(s_vlist + 3 * (size_t)plan.max_pairs);
+    u32* s_rpk = s_vlist + 3 * (size_t)plan.max_pairs;        // 2-bit packed reads
+    u32* s_hpk = s_rpk + plan.rpk_words;                      // 2-bit packed haplotypes (padded both sides)
+    uint16_t* s_rid = (uint16_t*)(s_hpk + plan.hpk_words);
     uint16_t* s_next = s_rid + plan.rid_halfs;
-    uint16_t* s_hid = s_next + plan.next_halfs;               // per haplotype position: id of its 7-mer
-    uint16_t* s_mult = s_hid + plan.next_halfs;               // per id: upper bound of its multiplicity in a haplotype
+    uint16_t* s_mult = s_next + plan.next_halfs;              // per id: upper bound of its multiplicity in a haplotype
     uint16_t* s_heads = s_mult + plan.heads_halfs;
     SlotInfo* s_slot = (SlotInfo*)(((uintptr_t)(s_heads + plan.heads_halfs) + 15) & ~(uintptr_t)15);
-    int32_t* s_hmeta = (int32_t*)(s_slot + plan.max_slots);  // per hap: len, next offset
+    int32_t* s_hmeta = (int32_t*)(s_slot + plan.max_slots);  // per hap: len, next offset, packed offset
     __shared__ int s_nid, s_nfb, s_scan[kAnchorThreads / 32];
 
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
@@ -383,13 +346,15 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
         const int ns = (int)(tile.s1 - tile.s0);
         __syncthreads();
         if (tid == 0) {
-            int noff = 0;
+            int noff = 0, poff = 0;
             for (int g = 0; g < nh; ++g) {
                 const int h = tile.h0 + g;
                 const int len = (int)(b.hap_seq_off[h + 1] - b.hap_seq_off[h]);
-                s_hmeta[2 * g + 0] = len;
-                s_hmeta[2 * g + 1] = noff;
+                s_hmeta[3 * g + 0] = len;
+                s_hmeta[3 * g + 1] = noff;
+                s_hmeta[3 * g + 2] = poff + kPackPadWords;   // word index of base 0
                 noff += (len + 2) & ~1;
+                poff += ((len + 15) >> 4) + 2 * kPackPadWords;
             }
             s_nfb = 0;
         }
@@ -411,21 +376,26 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
             }
             si.hoff = 0;
             si.vub = 0;
+            si.poff = 0;
             s_slot[s] = si;
         }
         __syncthreads();
         if (tid == 0) {  // offsets of the per-read id rows (rows padded to 8 entries = 16 bytes)
-            int o = 0;
+            int o = 0, po = 0;
             for (int s = 0; s < ns; ++s) {
                 s_slot[s].hoff = o;
+                s_slot[s].poff = po;
                 const int nk = s_slot[s].len - kKmer;
-                if (nk > 0 && !(s_slot[s].flags & 1)) o += (nk + 7) & ~7;
+                if (nk > 0 && !(s_slot[s].flags & 1)) {
+                    o += (nk + 7) & ~7;
+                    po += ((s_slot[s].len + 15) >> 4) + kPackPadWords;
+                }
             }
         }
         // ---- union table: insert the 14-bit hash of every indexed haplotype position
         //      (calign.pyx:109: positions 0 .. len-8) ----
         for (int g = 0; g < nh; ++g) {
-            const int len = s_hmeta[2 * g];
+            const int len = s_hmeta[3 * g];
             const uint8_t* hap = b.hap_seq + b.hap_seq_off[tile.h0 + g];
             for (int i = tid; i < len - kKmer; i += nthr) {
                 const u32 key = kmer_hash(hap + i);
@@ -487,6 +457,42 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
                 }
             }
         }
+        // ---- 2-bit packed reads and haplotypes for the per-offset vote counts (plb_kmer.cuh) ----
+        for (int s = warp; s < ns; s += nwarp) {
+            const SlotInfo si = s_slot[s];
+            if ((si.flags & 1) || si.len <= kKmer) continue;
+            const uint8_t* rs = b.read_seq + b.read_seq_off[si.read];
+            const int nw = ((si.len + 15) >> 4) + kPackPadWords;
+            for (int wd = lane; wd < nw; wd += 32) {
+                u32 v = 0;
+                const int i0 = 16 * wd;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {  // 16 independent predicated byte loads
+                    const int i = i0 + k;
+                    const uint8_t ch = i < si.len ? rs[i] : (uint8_t)0;
+                    v |= (i < si.len ? kmer_base_code(ch) : 0u) << (2 * k);
+                }
+                s_rpk[si.poff + wd] = v;
+            }
+        }
+        for (int g = 0; g < nh; ++g) {
+            const int len = s_hmeta[3 * g];
+            const uint8_t* hap = b.hap_seq + b.hap_seq_off[tile.h0 + g];
+            u32* dst = s_hpk + s_hmeta[3 * g + 2] - kPackPadWords;
+            const int nw = ((len + 15) >> 4) + 2 * kPackPadWords;
+            for (int wd = tid; wd < nw; wd += nthr) {
+                u32 v = 0;
+                const int i0 = 16 * (wd - kPackPadWords);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int i = i0 + k;
+                    const bool in = i >= 0 && i < len;
+                    const uint8_t ch = in ? hap[i] : (uint8_t)0;
+                    v |= (in ? kmer_base_code(ch) : 0u) << (2 * k);
+                }
+                dst[wd] = v;
+            }
+        }
         const int general = b.win_flags[w] & 1;
         const int hstride = U + 1;
         const int sub_max = max(1, min(nh, plan.heads_halfs / hstride));
@@ -498,14 +504,12 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
             for (int i = tid; i < hstride; i += nthr) s_mult[i] = i ? 1 : 0;
             __syncthreads();
             for (int g = g0; g < g1; ++g) {
-                const int len = s_hmeta[2 * g];
+                const int len = s_hmeta[3 * g];
                 const uint8_t* hap = b.hap_seq + b.hap_seq_off[tile.h0 + g];
-                uint16_t* nxt = s_next + s_hmeta[2 * g + 1];
+                uint16_t* nxt = s_next + s_hmeta[3 * g + 1];
                 unsigned short* head = (unsigned short*)(s_heads + (g - g0) * hstride);
-                uint16_t* hid = s_hid + s_hmeta[2 * g + 1];
                 for (int i = tid; i < len - kKmer; i += nthr) {
                     const u32 id = tab_lookup(s_tab, bits, kmer_hash(hap + i));
-                    hid[i] = (uint16_t)id;
                     unsigned short cur = head[id];
                     while (true) {  // push position i (stored as i+1); order inside a chain is irrelevant.
                         // bit 15 of the head marks chains with more than one element.
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
                 const u32 hd = s_heads[i];
                 if (hd & 0x8000u) {
                     const int g = g0 + i / hstride, id = i % hstride;
-                    const uint16_t* nxt = s_next + s_hmeta[2 * g + 1];
+                    const uint16_t* nxt = s_next + s_hmeta[3 * g + 1];
                     unsigned short len = 0;
                     for (u32 p1 = hd & 0x7FFFu; p1; p1 = nxt[p1]) ++len;
                     unsigned short cur = s_mult[id];
@@ -578,10 +582,11 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
                 LightArgs la;
                 la.head_off = (u32)((uint8_t*)(s_heads + (g - g0) * hstride) - smem);
                 la.rid_off = (u32)((uint8_t*)(s_rid + si.hoff) - smem);
-                la.hid_off = (u32)((uint8_t*)(s_hid + s_hmeta[2 * g + 1]) - smem);
+                la.rpk_off = (u32)((uint8_t*)(s_rpk + si.poff) - smem);
+                la.hpk_off = (u32)((uint8_t*)(s_hpk + s_hmeta[3 * g + 2]) - smem);
                 la.res_off = (u32)((uint8_t*)(s_vlist + 3 * p) - smem);
                 la.nk_read = si.len - kKmer;
-                la.nk_hap = s_hmeta[2 * g] - kKmer;
+                la.nk_hap = s_hmeta[3 * g] - kKmer;
                 la.vub = si.vub;
                 if (!light_decide(la)) {
                     s_vlist[3 * p] = (u32)kPairUndecided;
@@ -597,7 +602,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
                 int64_t gs, pair;
                 pair_id(p, s, g, gs, pair);
                 const SlotInfo si = s_slot[s];
-                const int L = si.len, hap_len = s_hmeta[2 * g], h = tile.h0 + g;
+                const int L = si.len, hap_len = s_hmeta[3 * g], h = tile.h0 + g;
                 Emitter em;
                 em.c0 = em.c1 = -1;
                 em.sc = kScoreNone;
@@ -640,8 +645,8 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
                 const int64_t T = b.wi_slot_off[wi + 1] - b.wi_slot_off[wi];
                 const int64_t pair = b.ll_off[wi] + (int64_t)(h - b.win_hap_off[w]) * T + (gs - b.wi_slot_off[wi]);
                 const int L = si.len, nk = L - kKmer;
-                const int hap_len = s_hmeta[2 * g];
-                const uint16_t* nxt = s_next + s_hmeta[2 * g + 1];
+                const int hap_len = s_hmeta[3 * g];
+                const uint16_t* nxt = s_next + s_hmeta[3 * g + 1];
                 const uint16_t* head = s_heads + (g - g0) * hstride;
                 const uint16_t* rid = s_rid + si.hoff;
                 u32* cw = s_cnt + (size_t)warp * plan.cnt_words;
