@@ -5,7 +5,11 @@
 // points: without a usable CUDA device every call fails with PLB_ERR_CUDA.
 #include <cuda_runtime.h>
 
+#include <omp.h>
+
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -36,6 +40,8 @@ static int set_err(int code, const char* fmt, ...) {
     } while (0)
 
 constexpr int kTimingRing = 64;
+constexpr int kMaxChunks = 5;           // pipelined host path: chunks of windows per call
+constexpr int kMinChunkWindows = 1024;
 
 struct Block {
     void* p;
@@ -45,6 +51,12 @@ struct Block {
 struct PlbContext {
     int device;
     cudaStream_t stream;
+    cudaStream_t copy_stream;   // H2D of the pipelined host path
+    cudaStream_t stream2;       // second compute stream: odd chunks of the pipelined host path
+    cudaEvent_t ev_s2;
+    std::vector<std::pair<uint8_t*, size_t>> pin_blocks;   // pinned staging for planner outputs
+    size_t pin_off = 0;
+    cudaEvent_t ev_chunk[kMaxChunks + 1];
     bool own_stream;
     int64_t launches;
     int n_sm;
@@ -58,21 +70,35 @@ struct PlbContext {
     cudaEvent_t kev[kTimingRing][PLB_N_KERNELS + 1];    // ring of per-run event sets
 };
 
+struct TileLists {
+    std::vector<Tile> a, d;
+};
+
+// Launch plan of one chunk of windows [w0, w1): tile lists (host + device) and kernel shapes.
+struct ChunkPlan {
+    int w0 = 0, w1 = 0;
+    int h0 = 0, h1 = 0;   // haplotype range of the chunk
+    AnchorPlan ap{};
+    DpPlan dp{};
+    size_t a_smem = 0, d_smem = 0;
+    int a_occ = 1, d_occ = 1;
+    Block tiles_blk{nullptr, 0};
+    TileLists tl;
+};
+
 struct PlbDeviceBatch {
-    DevBatch d;
-    Block blk;
-    // plans
-    AnchorPlan aplan;
-    DpPlan dplan;
-    size_t a_smem, d_smem;
-    int a_grid, d_grid;
-    Queue q;
-    double* ll_scratch;
-    double* em_scratch;      // [W][nInd][Gmax_plan]
-    int32_t max_haps;        // largest H in the batch
-    size_t em_scratch_elems;
-    // host copies kept for output sizing
-    int64_t n_wi;
+    DevBatch d{};
+    Block blk{nullptr, 0};
+    Queue q{}, q2{};                   // general-path queues (one per compute stream)
+    double* ll_scratch = nullptr;
+    double* em_scratch = nullptr;      // [W][nInd][Gmax_plan]
+    int32_t max_haps = 0;              // largest H in the batch
+    size_t em_scratch_elems = 0;
+    bool have_var = false;
+    int64_t n_wi = 0;
+    std::vector<ChunkPlan> chunks;     // plb_batch_upload plans one chunk covering every window
+    int64_t* h_ll_off = nullptr;       // pinned
+    int64_t hap_done[2] = {0, 0}, read_done[2] = {0, 0};  // byte intervals already on the device
 };
 
 extern "C" const char* plb_last_error(void) { return g_err; }
@@ -108,6 +134,10 @@ extern "C" int plb_context_create(int device, void* stream, PlbContext** out) {
     CU(cudaMallocHost(&c->h_ctr, sizeof(Counters)));
     memset(c->h_ctr, 0, sizeof(Counters));
     CU(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_s2, cudaEventDisableTiming));
+    for (int i = 0; i <= kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
     c->timing = false;
     c->n_timed = 0;
     for (int r = 0; r < kTimingRing; ++r)
@@ -124,6 +154,13 @@ extern "C" void plb_context_destroy(PlbContext* c) {
     cudaFree(c->d_ctr);
     cudaFreeHost(c->h_ctr);
     cudaEventDestroy(c->ev);
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+    cudaStreamSynchronize(c->stream2);
+    cudaStreamDestroy(c->stream2);
+    cudaEventDestroy(c->ev_s2);
+    for (auto& pb : c->pin_blocks) cudaFreeHost(pb.first);
+    for (int i = 0; i <= kMaxChunks; ++i) cudaEventDestroy(c->ev_chunk[i]);
     for (int r = 0; r < kTimingRing; ++r)
         for (int i = 0; i <= PLB_N_KERNELS; ++i) cudaEventDestroy(c->kev[r][i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -155,6 +192,29 @@ static int block_get(PlbContext* c, size_t bytes, Block* out) {
 
 static void block_put(PlbContext* c, Block b) {
     if (b.p) c->cache.push_back(b);
+}
+
+// Pinned host staging memory (valid until the next pin_reset; every API call synchronises its
+// streams before returning, so one arena per context is enough).
+static void pin_reset(PlbContext* c) { c->pin_off = 0; }
+
+static void* pin_alloc(PlbContext* c, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (!c->pin_blocks.empty()) {
+        auto& last = c->pin_blocks.back();
+        if (c->pin_off + bytes <= last.second) {
+            void* p = last.first + c->pin_off;
+            c->pin_off += bytes;
+            return p;
+        }
+    }
+    // grow: a new block twice the size; older blocks stay alive (copies from them may be in flight)
+    size_t cap = std::max<size_t>(bytes * 2, c->pin_blocks.empty() ? (size_t)(4 << 20) : c->pin_blocks.back().second * 2);
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    c->pin_blocks.push_back({(uint8_t*)p, cap});
+    c->pin_off = bytes;
+    return p;
 }
 
 // ---- host helpers -----------------------------------------------------------------------------
@@ -258,10 +318,6 @@ T* at(const Block& b, size_t off) {
     return (T*)((uint8_t*)b.p + off);
 }
 
-struct TileLists {
-    std::vector<Tile> a, d;
-};
-
 constexpr size_t kAnchorNextBudget = 24 * 1024;  // position chains of one haplotype group
 constexpr size_t kAnchorHashBudget = 24 * 1024;  // read 7-mer ids of one tile
 constexpr size_t kAnchorCntBudget = 48 * 1024;   // per-warp vote arrays of the exact (tie) path
@@ -290,8 +346,8 @@ int tab_bits(int len) {
 
 }  // namespace
 
-static int plan_tiles(const PlbWindowBatch* hb, TileLists& tl, AnchorPlan& ap, DpPlan& dp, int& max_read, int& max_hap,
-                      int& max_H) {
+static int plan_tiles(const PlbWindowBatch* hb, int w_begin, int w_end, TileLists& tl, AnchorPlan& ap, DpPlan& dp,
+                      int& max_read, int& max_hap, int& max_H) {
     memset(&ap, 0, sizeof ap);
     memset(&dp, 0, sizeof dp);
     max_read = 0;
@@ -299,7 +355,10 @@ static int plan_tiles(const PlbWindowBatch* hb, TileLists& tl, AnchorPlan& ap, D
     max_H = 0;
     const int nInd = hb->n_individuals;
     std::vector<int> slot_len;
-    for (int w = 0; w < hb->n_windows; ++w) {
+    std::vector<std::pair<int, int>> groups, dgroups;
+    for (int w = w_begin; w < w_end; ++w) {
+        groups.clear();
+        dgroups.clear();
         const int h0 = hb->win_hap_off[w], h1 = hb->win_hap_off[w + 1];
         max_H = std::max(max_H, h1 - h0);
         const int64_t s0 = hb->wi_slot_off[(int64_t)w * nInd], s1 = hb->wi_slot_off[(int64_t)(w + 1) * nInd];
@@ -310,7 +369,6 @@ static int plan_tiles(const PlbWindowBatch* hb, TileLists& tl, AnchorPlan& ap, D
             max_read = std::max(max_read, slot_len[(size_t)(s - s0)]);
         }
         // ---- anchor tiles
-        std::vector<std::pair<int, int>> groups;
         {
             int g0 = h0;
             size_t next_bytes = 0;
@@ -374,7 +432,6 @@ static int plan_tiles(const PlbWindowBatch* hb, TileLists& tl, AnchorPlan& ap, D
             flush(s1);
         }
         // ---- dp tiles
-        std::vector<std::pair<int, int>> dgroups;
         {
             int g0 = h0;
             size_t recs = 0;
@@ -433,14 +490,36 @@ static int plan_tiles(const PlbWindowBatch* hb, TileLists& tl, AnchorPlan& ap, D
     return PLB_OK;
 }
 
-template <typename T>
-static int h2d(PlbContext* c, T* dst, const T* src, size_t n) {
-    if (n == 0 || !src) return PLB_OK;
-    CU(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
-    return PLB_OK;
+// Bytes of the big sequence arrays (hap_seq / read_seq / read_qual) that windows [w0, w1) need.
+struct ByteRanges {
+    int64_t hap0, hap1;    // byte range of hap_seq
+    int64_t read0, read1;  // byte range of read_seq / read_qual (hull over the reads the slots refer to)
+};
+
+static ByteRanges byte_ranges(const PlbWindowBatch* hb, int w0, int w1) {
+    ByteRanges r{0, 0, 0, 0};
+    if (w1 <= w0) return r;
+    const int nInd = hb->n_individuals;
+    r.hap0 = hb->hap_seq_off[hb->win_hap_off[w0]];
+    r.hap1 = hb->hap_seq_off[hb->win_hap_off[w1]];
+    const int64_t s0 = hb->wi_slot_off[(int64_t)w0 * nInd], s1 = hb->wi_slot_off[(int64_t)w1 * nInd];
+    int rmin = INT32_MAX, rmax = -1;
+    const int32_t* sr = hb->slot_read;
+#pragma omp parallel for reduction(min : rmin) reduction(max : rmax) schedule(static) if (s1 - s0 > 32768)
+    for (int64_t s = s0; s < s1; ++s) {
+        const int rd = sr[s];
+        rmin = std::min(rmin, rd);
+        rmax = std::max(rmax, rd);
+    }
+    if (rmax >= 0) {
+        r.read0 = hb->read_seq_off[rmin];
+        r.read1 = hb->read_seq_off[rmax + 1];
+    }
+    return r;
 }
 
-extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch** out) {
+// Plans tiles, allocates one device block and lays every array out in it.  No copies.
+static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch** out) {
     if (!c || !hb || !out) return set_err(PLB_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(c->device));
     const int W = hb->n_windows, nInd = hb->n_individuals;
@@ -452,62 +531,19 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
     const int64_t read_bytes = n_reads ? hb->read_seq_off[n_reads] : 0;
 
     PlbDeviceBatch* db = new PlbDeviceBatch();
-    memset(db, 0, sizeof *db);
     db->n_wi = nwi;
-
-    // derived host arrays
-    std::vector<int64_t> ll_off((size_t)nwi + 1);
+    pin_reset(c);
+    db->h_ll_off = (int64_t*)pin_alloc(c, ((size_t)nwi + 1) * 8);
+    if (!db->h_ll_off) {
+        delete db;
+        return set_err(PLB_ERR_NOMEM, "pinned host allocation failed");
+    }
     int64_t n_pairs = 0;
-    plb_ll_offsets(hb, ll_off.data(), &n_pairs);
-    std::vector<int32_t> slot_wi((size_t)n_slots);
-    for (int64_t wi = 0; wi < nwi; ++wi)
-        for (int64_t s = hb->wi_slot_off[wi]; s < hb->wi_slot_off[wi + 1]; ++s) slot_wi[(size_t)s] = (int32_t)wi;
-    std::vector<int32_t> hap_win((size_t)n_haps);
-    for (int w = 0; w < W; ++w)
-        for (int h = hb->win_hap_off[w]; h < hb->win_hap_off[w + 1]; ++h) hap_win[(size_t)h] = w;
+    plb_ll_offsets(hb, db->h_ll_off, &n_pairs);
 
-    TileLists tl;
-    int max_read = 0, max_hap = 0, max_H = 0;
-    plan_tiles(hb, tl, db->aplan, db->dplan, max_read, max_hap, max_H);
+    int max_H = 0;
+    for (int w = 0; w < W; ++w) max_H = std::max(max_H, hb->win_hap_off[w + 1] - hb->win_hap_off[w]);
     db->max_haps = max_H;
-
-    // anchor launch shape
-    {
-        AnchorPlan& ap = db->aplan;
-        ap.max_pairs = (ap.max_pairs + 3) & ~3;
-        ap.rid_halfs = (ap.rid_halfs + 7) & ~7;
-        ap.rpk_words = (ap.rpk_words + 3) & ~3;
-        ap.hpk_words = (ap.hpk_words + 3) & ~3;
-        ap.next_halfs = (ap.next_halfs + 7) & ~7;
-        ap.heads_halfs = std::max(ap.heads_halfs, 4096);
-        ap.heads_halfs = (ap.heads_halfs + 7) & ~7;
-        ap.tab_bits = std::max(ap.tab_bits, 6);
-        ap.cnt_words = (((max_hap + max_read + 2) >> 1) + 3) & ~3;
-        const int nwarps = kAnchorThreads / 32;
-        ap.n_cnt = (int)std::max<size_t>(1, std::min<size_t>(nwarps, kAnchorCntBudget / ((size_t)ap.cnt_words * 4)));
-        db->a_smem = ((size_t)4 << ap.tab_bits) + (size_t)ap.n_cnt * ap.cnt_words * 4 + (size_t)ap.max_pairs * 16 +
-                     (size_t)(ap.rpk_words + ap.hpk_words) * 4 + (size_t)ap.rid_halfs * 2 + (size_t)ap.next_halfs * 2 +
-                     (size_t)ap.heads_halfs * 4 + 16 + (size_t)ap.max_slots * sizeof(SlotInfo) +
-                     (size_t)ap.max_group * 12 + 16;
-    }
-    if (db->a_smem + 1024 > (size_t)c->smem_optin) {
-        size_t need = db->a_smem;
-        delete db;
-        return set_err(PLB_ERR_SHAPE, "anchor tile needs %zu bytes of shared memory", need);
-    }
-    int a_occ = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (db->a_smem + 1024)));
-    db->a_grid = std::max(1, std::min(db->aplan.n_tiles, c->n_sm * a_occ));
-    // dp launch shape
-    db->d_smem = (size_t)db->dplan.prof_words * 4 + (size_t)db->dplan.rec_count * sizeof(HapRec) +
-                 (size_t)db->dplan.max_slots * sizeof(DpSlot) + (size_t)db->dplan.max_group * 4 +
-                 (size_t)db->dplan.max_pairs * 12 + 64;
-    if (db->d_smem + 1024 > (size_t)c->smem_optin) {
-        size_t need = db->d_smem;
-        delete db;
-        return set_err(PLB_ERR_SHAPE, "dp tile needs %zu bytes of shared memory", need);
-    }
-    int d_occ = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (db->d_smem + 1024)));
-    db->d_grid = std::max(1, std::min(db->dplan.n_tiles, c->n_sm * d_occ));
 
     // device layout
     Layout L;
@@ -521,6 +557,7 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
                  o_read_end = L.take((size_t)n_reads * 4), o_read_mapq = L.take((size_t)n_reads),
                  o_read_qcfail = L.take((size_t)n_reads);
     const bool have_var = hb->max_variants > 0 && hb->win_n_var && hb->hap_var_mask && hb->var_prior;
+    db->have_var = have_var;
     const size_t o_win_n_var = L.take(have_var ? (size_t)W * 4 : 0), o_hap_var_mask = L.take(have_var ? (size_t)n_haps * 8 : 0),
                  o_var_prior = L.take(have_var ? (size_t)W * hb->max_variants * 8 : 0);
     const size_t o_slot_wi = L.take((size_t)n_slots * 4), o_hap_win = L.take((size_t)n_haps * 4),
@@ -528,9 +565,9 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
     const size_t o_gap = L.take((size_t)hap_bytes + n_haps + 64), o_wgen = L.take((size_t)W * 4 + 64),
                  o_c0 = L.take((size_t)n_pairs * 4), o_c1 = L.take((size_t)n_pairs * 4),
                  o_score = L.take((size_t)n_pairs * 4);
-    const size_t o_atiles = L.take(tl.a.size() * sizeof(Tile)), o_dtiles = L.take(tl.d.size() * sizeof(Tile));
     const int qcap = (int)std::min<int64_t>(std::max<int64_t>(4096, n_pairs / 2), 1 << 26);
     const size_t o_q = L.take((size_t)qcap * sizeof(QueueEntry)), o_qcount = L.take(64);
+    const size_t o_q2 = L.take((size_t)qcap * sizeof(QueueEntry)), o_qcount2 = L.take(64);
     const size_t o_ll = L.take((size_t)n_pairs * 8);
     const int Gp = max_H * (max_H + 1) / 2;
     db->em_scratch_elems = (size_t)W * nInd * Gp;
@@ -578,54 +615,223 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
     d.cand0 = at<int32_t>(B, o_c0);
     d.cand1 = at<int32_t>(B, o_c1);
     d.score = at<int32_t>(B, o_score);
-    db->aplan.tiles = at<Tile>(B, o_atiles);
-    db->dplan.tiles = at<Tile>(B, o_dtiles);
     db->q.e = at<QueueEntry>(B, o_q);
     db->q.count = at<int32_t>(B, o_qcount);
     db->q.cap = qcap;
+    db->q2.e = at<QueueEntry>(B, o_q2);
+    db->q2.count = at<int32_t>(B, o_qcount2);
+    db->q2.cap = qcap;
     db->ll_scratch = at<double>(B, o_ll);
     db->em_scratch = at<double>(B, o_em);
+    *out = db;
+    return PLB_OK;
+}
 
-#define H2D(field, type, n)                                                        \
-    if ((rc = h2d<type>(c, (type*)d.field, (const type*)hb->field, (size_t)(n)))) { \
-        block_put(c, db->blk);                                                     \
-        delete db;                                                                 \
-        return rc;                                                                 \
+#define CUQ(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return set_err(PLB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                           __LINE__);                                                                      \
+    } while (0)
+
+// Plans the tiles of windows [w0, w1), sizes the kernels' shared memory and puts the tile lists on
+// the device (async on st).
+static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* hb, int w0, int w1, cudaStream_t st) {
+    db->chunks.emplace_back();
+    ChunkPlan& ch = db->chunks.back();
+    ch.w0 = w0;
+    ch.w1 = w1;
+    ch.h0 = hb->win_hap_off[w0];
+    ch.h1 = hb->win_hap_off[w1];
+    int max_read = 0, max_hap = 0, max_H = 0;
+    {
+        // plan sub-ranges of the chunk on several host threads, then concatenate in window order
+        const int nw = w1 - w0;
+        const int parts = std::max(1, std::min(omp_get_max_threads(), std::min(16, nw / 256)));
+        std::vector<TileLists> tls(parts);
+        std::vector<AnchorPlan> aps(parts);
+        std::vector<DpPlan> dps(parts);
+        std::vector<int> mr(parts, 0), mh(parts, 0), mH(parts, 0);
+#pragma omp parallel for schedule(static, 1) num_threads(parts) if (parts > 1)
+        for (int p = 0; p < parts; ++p) {
+            const int a = w0 + (int)((int64_t)nw * p / parts), b = w0 + (int)((int64_t)nw * (p + 1) / parts);
+            plan_tiles(hb, a, b, tls[p], aps[p], dps[p], mr[p], mh[p], mH[p]);
+        }
+        memset(&ch.ap, 0, sizeof ch.ap);
+        memset(&ch.dp, 0, sizeof ch.dp);
+        size_t na_ = 0, nd_ = 0;
+        for (int p = 0; p < parts; ++p) {
+            na_ += tls[p].a.size();
+            nd_ += tls[p].d.size();
+        }
+        ch.tl.a.reserve(na_);
+        ch.tl.d.reserve(nd_);
+        for (int p = 0; p < parts; ++p) {
+            ch.tl.a.insert(ch.tl.a.end(), tls[p].a.begin(), tls[p].a.end());
+            ch.tl.d.insert(ch.tl.d.end(), tls[p].d.begin(), tls[p].d.end());
+            AnchorPlan& A = ch.ap;
+            const AnchorPlan& q = aps[p];
+            A.max_slots = std::max(A.max_slots, q.max_slots);
+            A.max_group = std::max(A.max_group, q.max_group);
+            A.max_pairs = std::max(A.max_pairs, q.max_pairs);
+            A.tab_bits = std::max(A.tab_bits, q.tab_bits);
+            A.next_halfs = std::max(A.next_halfs, q.next_halfs);
+            A.rid_halfs = std::max(A.rid_halfs, q.rid_halfs);
+            A.heads_halfs = std::max(A.heads_halfs, q.heads_halfs);
+            A.rpk_words = std::max(A.rpk_words, q.rpk_words);
+            A.hpk_words = std::max(A.hpk_words, q.hpk_words);
+            DpPlan& D = ch.dp;
+            const DpPlan& r = dps[p];
+            D.max_slots = std::max(D.max_slots, r.max_slots);
+            D.max_group = std::max(D.max_group, r.max_group);
+            D.prof_words = std::max(D.prof_words, r.prof_words);
+            D.rec_count = std::max(D.rec_count, r.rec_count);
+            D.max_pairs = std::max(D.max_pairs, r.max_pairs);
+            max_read = std::max(max_read, mr[p]);
+            max_hap = std::max(max_hap, mh[p]);
+            max_H = std::max(max_H, mH[p]);
+        }
+        ch.ap.n_tiles = (int)ch.tl.a.size();
+        ch.dp.n_tiles = (int)ch.tl.d.size();
     }
-    H2D(win_hap_off, int32_t, W + 1)
-    H2D(win_start, int32_t, W)
-    H2D(win_end, int32_t, W)
-    H2D(hap_start, int32_t, W)
-    H2D(hap_seq_off, int64_t, n_haps + 1)
-    H2D(hap_seq, uint8_t, hap_bytes)
-    H2D(wi_slot_off, int64_t, nwi + 1)
-    H2D(wi_n_good, int32_t, nwi)
-    H2D(wi_n_bad, int32_t, nwi)
-    H2D(slot_read, int32_t, n_slots)
-    H2D(read_seq_off, int64_t, n_reads + 1)
-    H2D(read_seq, uint8_t, read_bytes)
-    H2D(read_qual, uint8_t, read_bytes)
-    H2D(read_pos, int32_t, n_reads)
-    H2D(read_end, int32_t, n_reads)
-    H2D(read_mapq, uint8_t, n_reads)
-    H2D(read_qcfail, uint8_t, n_reads)
-    if (have_var) {
-        H2D(win_n_var, int32_t, W)
-        H2D(hap_var_mask, uint64_t, n_haps)
-        H2D(var_prior, double, (size_t)W * hb->max_variants)
+    {
+        AnchorPlan& ap = ch.ap;
+        ap.max_pairs = (ap.max_pairs + 3) & ~3;
+        ap.rid_halfs = (ap.rid_halfs + 7) & ~7;
+        ap.rpk_words = (ap.rpk_words + 3) & ~3;
+        ap.hpk_words = (ap.hpk_words + 3) & ~3;
+        ap.next_halfs = (ap.next_halfs + 7) & ~7;
+        ap.heads_halfs = std::max(ap.heads_halfs, 4096);
+        ap.heads_halfs = (ap.heads_halfs + 7) & ~7;
+        ap.tab_bits = std::max(ap.tab_bits, 6);
+        ap.cnt_words = (((max_hap + max_read + 2) >> 1) + 3) & ~3;
+        const int nwarps = kAnchorThreads / 32;
+        ap.n_cnt = (int)std::max<size_t>(1, std::min<size_t>(nwarps, kAnchorCntBudget / ((size_t)ap.cnt_words * 4)));
+        ch.a_smem = ((size_t)4 << ap.tab_bits) + (size_t)ap.n_cnt * ap.cnt_words * 4 + (size_t)ap.max_pairs * 16 +
+                    (size_t)(ap.rpk_words + ap.hpk_words) * 4 + (size_t)ap.rid_halfs * 2 + (size_t)ap.next_halfs * 2 +
+                    (size_t)ap.heads_halfs * 4 + 16 + (size_t)ap.max_slots * sizeof(SlotInfo) +
+                    (size_t)ap.max_group * 12 + 16;
     }
-#undef H2D
-    // derived arrays come from pageable std::vectors: the copy must finish before they die
-    if ((rc = h2d<int32_t>(c, (int32_t*)d.slot_wi, slot_wi.data(), (size_t)n_slots)) ||
-        (rc = h2d<int32_t>(c, (int32_t*)d.hap_win, hap_win.data(), (size_t)n_haps)) ||
-        (rc = h2d<int64_t>(c, (int64_t*)d.ll_off, ll_off.data(), (size_t)nwi + 1)) ||
-        (rc = h2d<Tile>(c, (Tile*)db->aplan.tiles, tl.a.data(), tl.a.size())) ||
-        (rc = h2d<Tile>(c, (Tile*)db->dplan.tiles, tl.d.data(), tl.d.size()))) {
-        block_put(c, db->blk);
-        delete db;
+    if (ch.a_smem + 1024 > (size_t)c->smem_optin)
+        return set_err(PLB_ERR_SHAPE, "anchor tile needs %zu bytes of shared memory", ch.a_smem);
+    ch.a_occ = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (ch.a_smem + 1024)));
+    ch.d_smem = (size_t)ch.dp.prof_words * 4 + (size_t)ch.dp.rec_count * sizeof(HapRec) +
+                (size_t)ch.dp.max_slots * sizeof(DpSlot) + (size_t)ch.dp.max_group * 4 + (size_t)ch.dp.max_pairs * 12 + 64;
+    if (ch.d_smem + 1024 > (size_t)c->smem_optin)
+        return set_err(PLB_ERR_SHAPE, "dp tile needs %zu bytes of shared memory", ch.d_smem);
+    ch.d_occ = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (ch.d_smem + 1024)));
+    const size_t na = ch.tl.a.size() * sizeof(Tile), nd = ch.tl.d.size() * sizeof(Tile);
+    int rc = block_get(c, na + nd + 512, &ch.tiles_blk);
+    if (rc) return rc;
+    ch.ap.tiles = (const Tile*)ch.tiles_blk.p;
+    ch.dp.tiles = (const Tile*)((uint8_t*)ch.tiles_blk.p + ((na + 255) & ~(size_t)255));
+    // stage through pinned memory: a copy from a pageable std::vector would block the host until
+    // everything queued earlier on the stream (the sequence bytes) has been transferred
+    uint8_t* stage = (uint8_t*)pin_alloc(c, na + nd + 16);
+    if (!stage) return set_err(PLB_ERR_NOMEM, "pinned host allocation failed");
+    if (na) memcpy(stage, ch.tl.a.data(), na);
+    if (nd) memcpy(stage + na, ch.tl.d.data(), nd);
+    if (na) CUQ(cudaMemcpyAsync((void*)ch.ap.tiles, stage, na, cudaMemcpyHostToDevice, st));
+    if (nd) CUQ(cudaMemcpyAsync((void*)ch.dp.tiles, stage + na, nd, cudaMemcpyHostToDevice, st));
+    return PLB_OK;
+}
+
+namespace plb {
+// slot -> (window, individual) index and haplotype -> window maps, derived on the device
+__global__ void k_derive(DevBatch b) {
+    const int64_t nwi = (int64_t)b.n_windows * b.n_individuals;
+    for (int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wi < nwi; wi += (int64_t)gridDim.x * blockDim.x) {
+        int32_t* sw = (int32_t*)b.slot_wi;
+        for (int64_t s = b.wi_slot_off[wi]; s < b.wi_slot_off[wi + 1]; ++s) sw[s] = (int32_t)wi;
+    }
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < b.n_windows; w += gridDim.x * blockDim.x) {
+        int32_t* hw = (int32_t*)b.hap_win;
+        for (int h = b.win_hap_off[w]; h < b.win_hap_off[w + 1]; ++h) hw[h] = w;
+    }
+}
+}  // namespace plb
+
+// Copies everything except the three big byte arrays, then derives slot_wi / hap_win on the device.
+static int copy_meta(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* hb, cudaStream_t st) {
+    const DevBatch& d = db->d;
+    const int W = d.n_windows, nInd = d.n_individuals;
+    const int64_t nwi = (int64_t)W * nInd;
+    auto cp = [&](const void* dst, const void* src, size_t bytes) -> cudaError_t {
+        if (!bytes || !src) return cudaSuccess;
+        return cudaMemcpyAsync((void*)dst, src, bytes, cudaMemcpyHostToDevice, st);
+    };
+    CUQ(cp(d.win_hap_off, hb->win_hap_off, (size_t)(W + 1) * 4));
+    CUQ(cp(d.win_start, hb->win_start, (size_t)W * 4));
+    CUQ(cp(d.win_end, hb->win_end, (size_t)W * 4));
+    CUQ(cp(d.hap_start, hb->hap_start, (size_t)W * 4));
+    CUQ(cp(d.hap_seq_off, hb->hap_seq_off, (size_t)(d.n_haps + 1) * 8));
+    CUQ(cp(d.wi_slot_off, hb->wi_slot_off, (size_t)(nwi + 1) * 8));
+    CUQ(cp(d.wi_n_good, hb->wi_n_good, (size_t)nwi * 4));
+    CUQ(cp(d.wi_n_bad, hb->wi_n_bad, (size_t)nwi * 4));
+    CUQ(cp(d.slot_read, hb->slot_read, (size_t)d.n_slots * 4));
+    CUQ(cp(d.read_seq_off, hb->read_seq_off, (size_t)(d.n_reads + 1) * 8));
+    CUQ(cp(d.read_pos, hb->read_pos, (size_t)d.n_reads * 4));
+    CUQ(cp(d.read_end, hb->read_end, (size_t)d.n_reads * 4));
+    CUQ(cp(d.read_mapq, hb->read_mapq, (size_t)d.n_reads));
+    CUQ(cp(d.read_qcfail, hb->read_qcfail, (size_t)d.n_reads));
+    if (db->have_var) {
+        CUQ(cp(d.win_n_var, hb->win_n_var, (size_t)W * 4));
+        CUQ(cp(d.hap_var_mask, hb->hap_var_mask, (size_t)d.n_haps * 8));
+        CUQ(cp(d.var_prior, hb->var_prior, (size_t)W * hb->max_variants * 8));
+    }
+    CUQ(cp(d.ll_off, db->h_ll_off, (size_t)(nwi + 1) * 8));
+    if (W > 0) {
+        k_derive<<<std::max(1, std::min(4 * c->n_sm, (int)((nwi + 127) / 128))), 128, 0, st>>>(d);
+        CUQ(cudaGetLastError());
+        c->launches++;
+    }
+    return PLB_OK;
+}
+
+// Copies the parts of [lo, hi) of a byte array that are not on the device yet; `done` is the
+// interval already uploaded (kept as one interval: a gap between intervals is simply filled).
+static int copy_bytes(uint8_t* dst, const uint8_t* src, int64_t lo, int64_t hi, int64_t done[2], cudaStream_t st) {
+    if (hi <= lo) return PLB_OK;
+    if (done[1] <= done[0]) {
+        CUQ(cudaMemcpyAsync(dst + lo, src + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
+        done[0] = lo;
+        done[1] = hi;
+        return PLB_OK;
+    }
+    if (lo < done[0]) {
+        CUQ(cudaMemcpyAsync(dst + lo, src + lo, (size_t)(done[0] - lo), cudaMemcpyHostToDevice, st));
+        done[0] = lo;
+    }
+    if (hi > done[1]) {
+        CUQ(cudaMemcpyAsync(dst + done[1], src + done[1], (size_t)(hi - done[1]), cudaMemcpyHostToDevice, st));
+        done[1] = hi;
+    }
+    return PLB_OK;
+}
+
+static int copy_seq_for_windows(PlbDeviceBatch* db, const PlbWindowBatch* hb, int w0, int w1, cudaStream_t st) {
+    const ByteRanges r = byte_ranges(hb, w0, w1);
+    int rc;
+    if ((rc = copy_bytes((uint8_t*)db->d.hap_seq, hb->hap_seq, r.hap0, r.hap1, db->hap_done, st))) return rc;
+    int64_t qdone[2] = {db->read_done[0], db->read_done[1]};
+    if ((rc = copy_bytes((uint8_t*)db->d.read_seq, hb->read_seq, r.read0, r.read1, db->read_done, st))) return rc;
+    if ((rc = copy_bytes((uint8_t*)db->d.read_qual, hb->read_qual, r.read0, r.read1, qdone, st))) return rc;
+    return PLB_OK;
+}
+
+extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch** out) {
+    PlbDeviceBatch* db = nullptr;
+    int rc = prepare_batch(c, hb, &db);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    if ((rc = copy_meta(c, db, hb, st)) || (rc = copy_seq_for_windows(db, hb, 0, hb->n_windows, st)) ||
+        (rc = plan_chunk(c, db, hb, 0, hb->n_windows, st))) {
+        cudaStreamSynchronize(st);
+        plb_batch_free(c, db);
         return rc;
     }
-    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(st));
     *out = db;
     return PLB_OK;
 }
@@ -633,6 +839,9 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
 extern "C" void plb_batch_free(PlbContext* c, PlbDeviceBatch* b) {
     if (!c || !b) return;
     cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream2);
+    cudaStreamSynchronize(c->copy_stream);
+    for (auto& ch : b->chunks) block_put(c, ch.tiles_blk);
     block_put(c, b->blk);
     delete b;
 }
@@ -652,72 +861,97 @@ static int launch_check(PlbContext* c, const char* what) {
     return PLB_OK;
 }
 
+// Launches the whole kernel sequence for one planned chunk of windows on stream st.  `timed` records
+// the per-kernel events of plb_kernel_times (whole-batch launches only).
+static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch, const PlbOptions* opt,
+                          PlbPopulationOut* pop, PlbLoglikOut* llo, cudaStream_t st, bool timed, const Queue& q) {
+    int rc;
+    DevBatch& d = db->d;
+    const int w0 = ch.w0, w1 = ch.w1;
+    if (w1 <= w0) return PLB_OK;
+    ScoreParams sp{opt->gap_extend, opt->nuc_prior};
+    const int nInd = d.n_individuals;
+    const int h0 = ch.h0, h1 = ch.h1;
+    CU(cudaMemsetAsync(d.win_flags + w0, 0, (size_t)(w1 - w0) * 4, st));
+    CU(cudaMemsetAsync(q.count, 0, 4, st));
+    const int tslot = c->n_timed % kTimingRing;
+    auto mark = [&](int i) {
+        if (timed && c->timing) cudaEventRecord(c->kev[tslot][i], st);
+    };
+    mark(0);
+    if (h1 > h0) {
+        k_prep<<<h1 - h0, 128, 0, st>>>(d, h0);
+        if ((rc = launch_check(c, "k_prep"))) return rc;
+    }
+    mark(1);
+    if (ch.ap.n_tiles > 0) {
+        const AnchorPlan& ap = ch.ap;
+        if ((rc = opt_in_smem(k_anchor, ch.a_smem))) return rc;
+        const int grid = std::max(1, std::min(ap.n_tiles, c->n_sm * ch.a_occ));
+        k_anchor<<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr);
+        if ((rc = launch_check(c, "k_anchor"))) return rc;
+        mark(2);
+        k_general<<<c->n_sm * 4, 128, 0, st>>>(d, q, sp);
+        if ((rc = launch_check(c, "k_general"))) return rc;
+    } else {
+        mark(2);
+    }
+    mark(3);
+    double* ll = (llo && llo->ll) ? llo->ll : db->ll_scratch;
+    int32_t* sc = llo ? llo->score : nullptr;
+    if (ch.dp.n_tiles > 0) {
+        const DpPlan& dp = ch.dp;
+        if ((rc = opt_in_smem(k_dp<kDpThreads>, ch.d_smem))) return rc;
+        const int grid = std::max(1, std::min(dp.n_tiles, c->n_sm * ch.d_occ));
+        k_dp<kDpThreads><<<grid, kDpThreads, ch.d_smem, st>>>(d, dp, sp, ll, sc);
+        if ((rc = launch_check(c, "k_dp"))) return rc;
+    }
+    mark(4);
+    if (pop) {
+        PopOut po{pop->max_haps, pop->gl,   pop->gl_log_max, pop->gof,       pop->hap_like,
+                  pop->freq,     pop->em_post, pop->call,    pop->var_phred, pop->em_iters};
+        k_genotype<<<(unsigned)((int64_t)(w1 - w0) * nInd), 64, 0, st>>>(d, ll, po, w0 * nInd);
+        if ((rc = launch_check(c, "k_genotype"))) return rc;
+        mark(5);
+        const int Hm = pop->max_haps;
+        int nthr_em = (int)std::min<size_t>(64, std::max<size_t>(1, (size_t)(40 * 1024) / (8 * (size_t)Hm)));
+        nthr_em = std::min(nthr_em, std::max(1, std::max(d.n_individuals, (int)d.max_variants)));
+        const size_t smem = (size_t)(2 + nthr_em) * Hm * 8;
+        if ((rc = opt_in_smem(k_population, smem))) return rc;
+        k_population<<<w1 - w0, 64, smem, st>>>(d, po, db->em_scratch, opt->max_em_iters, opt->use_em_likelihoods,
+                                                nthr_em, w0);
+        if ((rc = launch_check(c, "k_population"))) return rc;
+    } else {
+        mark(5);
+    }
+    mark(6);
+    if (timed && c->timing) c->n_timed++;
+    return PLB_OK;
+}
+
+static int check_pop(const PlbDeviceBatch* db, const PlbPopulationOut* pop) {
+    if (!pop) return PLB_OK;
+    if (pop->max_haps < db->max_haps)
+        return set_err(PLB_ERR_SHAPE, "max_haps %d < largest window (%d haplotypes) (cpopulation.pyx:221)", pop->max_haps,
+                       db->max_haps);
+    if (!pop->gl) return set_err(PLB_ERR_ARG, "PlbPopulationOut.gl is required");
+    if (!pop->em_post && pop->max_haps != db->max_haps)
+        return set_err(PLB_ERR_ARG, "em_post is NULL: max_haps must equal the batch maximum (%d)", db->max_haps);
+    return PLB_OK;
+}
+
 extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOptions* opt, PlbPopulationOut* pop,
                               PlbLoglikOut* llo) {
     if (!c || !db) return set_err(PLB_ERR_ARG, "NULL argument");
     int rc = check_options(opt);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
-    DevBatch& d = db->d;
-    if (d.n_windows == 0) return PLB_OK;
-    if (pop && pop->max_haps < db->max_haps)
-        return set_err(PLB_ERR_SHAPE, "max_haps %d < largest window (%d haplotypes) (cpopulation.pyx:221)", pop->max_haps,
-                       db->max_haps);
+    if (db->d.n_windows == 0) return PLB_OK;
+    if ((rc = check_pop(db, pop))) return rc;
     cudaStream_t st = c->stream;
-    ScoreParams sp{opt->gap_extend, opt->nuc_prior};
-    CU(cudaMemsetAsync(d.win_flags, 0, (size_t)d.n_windows * 4, st));
-    CU(cudaMemsetAsync(db->q.count, 0, 4, st));
     CU(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), st));
-
-    const int tslot = c->n_timed % kTimingRing;
-    auto mark = [&](int i) {
-        if (c->timing) cudaEventRecord(c->kev[tslot][i], st);
-    };
-    mark(0);
-    if (d.n_haps > 0) {
-        k_prep<<<d.n_haps, 128, 0, st>>>(d);
-        if ((rc = launch_check(c, "k_prep"))) return rc;
-    }
-    mark(1);
-    if (db->aplan.n_tiles > 0) {
-        if ((rc = opt_in_smem(k_anchor, db->a_smem))) return rc;
-        k_anchor<<<db->a_grid, kAnchorThreads, db->a_smem, st>>>(d, db->aplan, db->q, sp, c->d_ctr);
-        if ((rc = launch_check(c, "k_anchor"))) return rc;
-        mark(2);
-        k_general<<<c->n_sm * 4, 128, 0, st>>>(d, db->q, sp);
-        if ((rc = launch_check(c, "k_general"))) return rc;
-    }
-    mark(3);
-    double* ll = (llo && llo->ll) ? llo->ll : db->ll_scratch;
-    int32_t* sc = llo ? llo->score : nullptr;
-    if (db->dplan.n_tiles > 0) {
-        if ((rc = opt_in_smem(k_dp<kDpThreads>, db->d_smem))) return rc;
-        k_dp<kDpThreads><<<db->d_grid, kDpThreads, db->d_smem, st>>>(d, db->dplan, sp, ll, sc);
-        if ((rc = launch_check(c, "k_dp"))) return rc;
-    }
-    mark(4);
-    if (pop) {
-        if (!pop->gl) return set_err(PLB_ERR_ARG, "PlbPopulationOut.gl is required");
-        PopOut po{pop->max_haps, pop->gl,   pop->gl_log_max, pop->gof,       pop->hap_like,
-                  pop->freq,     pop->em_post, pop->call,    pop->var_phred, pop->em_iters};
-        const int64_t nwi = (int64_t)d.n_windows * d.n_individuals;
-        k_genotype<<<(unsigned)nwi, 64, 0, st>>>(d, ll, po);
-        if ((rc = launch_check(c, "k_genotype"))) return rc;
-        mark(5);
-        const int Hm = pop->max_haps;
-        if (!pop->em_post && Hm != db->max_haps)
-            return set_err(PLB_ERR_ARG, "em_post is NULL: max_haps must equal the batch maximum (%d)", db->max_haps);
-        int nthr_em = (int)std::min<size_t>(64, std::max<size_t>(1, (size_t)(40 * 1024) / (8 * (size_t)Hm)));
-        nthr_em = std::min(nthr_em, std::max(1, std::max(d.n_individuals, (int)d.max_variants)));
-        const size_t smem = (size_t)(2 + nthr_em) * Hm * 8;
-        if ((rc = opt_in_smem(k_population, smem))) return rc;
-        k_population<<<d.n_windows, 64, smem, st>>>(d, po, db->em_scratch, opt->max_em_iters, opt->use_em_likelihoods,
-                                                    nthr_em);
-        if ((rc = launch_check(c, "k_population"))) return rc;
-    }
-    if (!pop) mark(5);
-    mark(6);
-    if (c->timing) c->n_timed++;
+    for (const ChunkPlan& ch : db->chunks)
+        if ((rc = launch_windows(c, db, ch, opt, pop, llo, st, db->chunks.size() == 1, db->q))) return rc;
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     return PLB_OK;
 }
@@ -761,6 +995,15 @@ extern "C" int plb_kernel_times(PlbContext* c, float* ms) {
 }
 
 // ---- host-buffer entry points --------------------------------------------------------------------
+//
+// Pipelined: the batch is cut into chunks of windows; chunk k+1's sequence bytes travel over PCIe on
+// the copy stream while chunk k's kernels run on the compute stream, and every chunk's outputs go
+// back as soon as its kernels are done.  With pinned host buffers the call costs about
+// max(transfer, compute) instead of their sum.
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* opt, PlbPopulationOut* hpop,
                     PlbLoglikOut* hll) {
@@ -768,8 +1011,11 @@ static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* o
     if (rc) return rc;
     if (!hb) return set_err(PLB_ERR_ARG, "batch is NULL");
     if (hb->n_windows == 0) return PLB_OK;
+    static const bool trace = getenv("PLB_TRACE") != nullptr;
+    const double t_start = now_ms();
     PlbDeviceBatch* db = nullptr;
-    if ((rc = plb_batch_upload(c, hb, &db))) return rc;
+    if ((rc = prepare_batch(c, hb, &db))) return rc;
+    const double t_prep = now_ms();
     const int W = hb->n_windows, nInd = hb->n_individuals;
     const int64_t n_pairs = db->d.n_pairs;
     Block ob{nullptr, 0};
@@ -815,34 +1061,80 @@ static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* o
         dpop.freq = at<double>(ob, o_freq);
         dpop.em_post = at<double>(ob, o_em);
         dpop.call = at<int32_t>(ob, o_call);
-        dpop.var_phred = (V > 0 && hpop->var_phred) ? at<double>(ob, o_vp) : nullptr;
+        dpop.var_phred = (V > 0 && db->have_var && hpop->var_phred) ? at<double>(ob, o_vp) : nullptr;
         dpop.em_iters = at<int32_t>(ob, o_it);
     }
     dll.ll = want_ll ? at<double>(ob, o_ll) : nullptr;
     dll.score = want_sc ? at<int32_t>(ob, o_sc) : nullptr;
-    rc = plb_run_device(c, db, opt, hpop ? &dpop : nullptr, &dll);
-    cudaStream_t st = c->stream;
-    auto d2h = [&](void* dst, const void* src, size_t bytes) {
-        if (rc == PLB_OK && dst && src && bytes) {
-            cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
-            if (e != cudaSuccess) rc = set_err(PLB_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
-        }
+
+    cudaStream_t cs = c->copy_stream, st = c->stream;
+    cudaStream_t kst = st;   // compute stream of the current chunk (chunks alternate between two streams
+                             // so that one chunk's kernel tails overlap the next chunk's kernels)
+    cudaError_t e = cudaSuccess;
+    auto d2h = [&](void* dst, const void* src, size_t off, size_t bytes) {
+        if (rc == PLB_OK && e == cudaSuccess && dst && src && bytes)
+            e = cudaMemcpyAsync((uint8_t*)dst + off, (const uint8_t*)src + off, bytes, cudaMemcpyDeviceToHost, kst);
     };
-    if (hpop) {
-        d2h(hpop->gl, dpop.gl, (size_t)W * nInd * Gm * 8);
-        d2h(hpop->gl_log_max, dpop.gl_log_max, (size_t)W * nInd * 8);
-        d2h(hpop->gof, dpop.gof, (size_t)W * Gm * nInd * 8);
-        d2h(hpop->hap_like, dpop.hap_like, (size_t)W * nInd * Hm * 8);
-        d2h(hpop->freq, dpop.freq, (size_t)W * Hm * 8);
-        d2h(hpop->em_post, dpop.em_post, (size_t)W * nInd * Gm * 8);
-        d2h(hpop->call, dpop.call, (size_t)W * nInd * 4);
-        if (V > 0) d2h(hpop->var_phred, dpop.var_phred, (size_t)W * V * 8);
-        d2h(hpop->em_iters, dpop.em_iters, (size_t)W * 4);
+    // chunking: enough chunks to overlap, few enough to keep launches cheap
+    int n_chunks = std::max(1, std::min(kMaxChunks, W / kMinChunkWindows));
+    db->chunks.reserve(n_chunks);
+    rc = copy_meta(c, db, hb, cs);
+    if (rc == PLB_OK) e = cudaEventRecord(c->ev_chunk[0], cs);
+    if (rc == PLB_OK && e == cudaSuccess) e = cudaStreamWaitEvent(st, c->ev_chunk[0], 0);
+    if (rc == PLB_OK && e == cudaSuccess) e = cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), st);
+    if (rc == PLB_OK && e == cudaSuccess) e = cudaEventRecord(c->ev_s2, st);
+    if (rc == PLB_OK && e == cudaSuccess) e = cudaStreamWaitEvent(c->stream2, c->ev_s2, 0);
+    for (int k = 0; k < n_chunks && rc == PLB_OK && e == cudaSuccess; ++k) {
+        // a small first chunk gets the GPU busy early; the rest are equal
+        auto cut = [&](int i) -> int {
+            if (i <= 0) return 0;
+            if (i >= n_chunks) return W;
+            if (n_chunks < 3) return (int)((int64_t)W * i / n_chunks);
+            const int64_t first = W / (2 * n_chunks);
+            return (int)(first + (int64_t)(W - first) * (i - 1) / (n_chunks - 1));
+        };
+        const int w0 = cut(k), w1 = cut(k + 1);
+        // bytes first (DMA runs while the host plans the chunk's tiles), then the tile lists
+        if ((rc = copy_seq_for_windows(db, hb, w0, w1, cs))) break;
+        if ((rc = plan_chunk(c, db, hb, w0, w1, cs))) break;
+        kst = (k & 1) ? c->stream2 : st;
+        e = cudaEventRecord(c->ev_chunk[1 + k], cs);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(kst, c->ev_chunk[1 + k], 0);
+        if (e != cudaSuccess) break;
+        if ((rc = launch_windows(c, db, db->chunks.back(), opt, hpop ? &dpop : nullptr, &dll, kst, false,
+                                 (k & 1) ? db->q2 : db->q)))
+            break;
+        if (hpop) {
+            const size_t wq = (size_t)w0, wn = (size_t)(w1 - w0);
+            d2h(hpop->gl, dpop.gl, wq * nInd * Gm * 8, wn * nInd * Gm * 8);
+            d2h(hpop->gl_log_max, dpop.gl_log_max, wq * nInd * 8, wn * nInd * 8);
+            d2h(hpop->gof, dpop.gof, wq * Gm * nInd * 8, wn * Gm * nInd * 8);
+            d2h(hpop->hap_like, dpop.hap_like, wq * nInd * Hm * 8, wn * nInd * Hm * 8);
+            d2h(hpop->freq, dpop.freq, wq * Hm * 8, wn * Hm * 8);
+            d2h(hpop->em_post, dpop.em_post, wq * nInd * Gm * 8, wn * nInd * Gm * 8);
+            d2h(hpop->call, dpop.call, wq * nInd * 4, wn * nInd * 4);
+            if (V > 0) d2h(hpop->var_phred, dpop.var_phred, wq * V * 8, wn * V * 8);
+            d2h(hpop->em_iters, dpop.em_iters, wq * 4, wn * 4);
+        }
+        const int64_t p0 = db->h_ll_off[(size_t)w0 * nInd], p1 = db->h_ll_off[(size_t)w1 * nInd];
+        if (want_ll) d2h(hll->ll, dll.ll, (size_t)p0 * 8, (size_t)(p1 - p0) * 8);
+        if (want_sc) d2h(hll->score, dll.score, (size_t)p0 * 4, (size_t)(p1 - p0) * 4);
     }
-    if (want_ll) d2h(hll->ll, dll.ll, (size_t)n_pairs * 8);
-    if (want_sc) d2h(hll->score, dll.score, (size_t)n_pairs * 4);
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (rc == PLB_OK && e != cudaSuccess) rc = set_err(PLB_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
+    // join the second compute stream into the first, then fetch the counters
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_s2, c->stream2);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, c->ev_s2, 0);
+    if (rc == PLB_OK && e == cudaSuccess)
+        e = cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st);
+    const double t_issue = now_ms();
+    cudaError_t e2 = cudaStreamSynchronize(cs);
+    const double t_copy = now_ms();
+    cudaError_t e3 = cudaStreamSynchronize(st);
+    if (trace)
+        fprintf(stderr, "[plb] run_host: prepare %.2f ms, issue %.2f ms, copy-stream drain +%.2f ms, compute drain +%.2f ms (%d chunks)\n",
+                t_prep - t_start, t_issue - t_prep, t_copy - t_issue, now_ms() - t_copy, n_chunks);
+    if (rc == PLB_OK && e != cudaSuccess) rc = set_err(PLB_ERR_CUDA, "pipelined run failed: %s", cudaGetErrorString(e));
+    if (rc == PLB_OK && e2 != cudaSuccess) rc = set_err(PLB_ERR_CUDA, "copy stream: %s", cudaGetErrorString(e2));
+    if (rc == PLB_OK && e3 != cudaSuccess) rc = set_err(PLB_ERR_CUDA, "compute stream: %s", cudaGetErrorString(e3));
     block_put(c, ob);
     plb_batch_free(c, db);
     return rc;

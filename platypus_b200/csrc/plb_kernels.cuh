@@ -135,8 +135,8 @@ __device__ __forceinline__ u32 tab_slot0(u32 key, int bits) {
 // k_prep: one block per haplotype.  Gap-open table (chaplotype.pyx:552-590) into global scratch and
 // the per-window "general path" flag (haplotype bytes outside ACGTN need exact byte compares).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_prep(DevBatch b) {
-    const int h = blockIdx.x;
+__global__ void __launch_bounds__(128) k_prep(DevBatch b, int h_base) {
+    const int h = h_base + blockIdx.x;
     const int len = (int)(b.hap_seq_off[h + 1] - b.hap_seq_off[h]);
     const uint8_t* hap = b.hap_seq + b.hap_seq_off[h];
     uint8_t* go = b.gap_open + b.hap_seq_off[h] + h;
@@ -966,8 +966,8 @@ __device__ __forceinline__ void genotype_pair(int g, int H, int& h1, int& h2) {
     h2 = i + rem;
 }
 
-__global__ void __launch_bounds__(64) k_genotype(DevBatch b, const double* __restrict__ ll, PopOut out) {
-    const int wi = blockIdx.x;
+__global__ void __launch_bounds__(64) k_genotype(DevBatch b, const double* __restrict__ ll, PopOut out, int wi_base) {
+    const int wi = wi_base + blockIdx.x;
     const int nInd = b.n_individuals;
     const int w = wi / nInd, i = wi % nInd;
     const int H = b.win_hap_off[w + 1] - b.win_hap_off[w];
@@ -1046,9 +1046,9 @@ __global__ void __launch_bounds__(64) k_genotype(DevBatch b, const double* __res
 // (:623-676), variant posteriors (:459-594).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k_population(DevBatch b, PopOut out, double* __restrict__ em_scratch,
-                                                   int max_iters, int use_em, int nthr_em) {
+                                                   int max_iters, int use_em, int nthr_em, int w_base) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int w = blockIdx.x;
+    const int w = w_base + blockIdx.x;
     const int nInd = b.n_individuals;
     const int H = b.win_hap_off[w + 1] - b.win_hap_off[w];
     const int G = H * (H + 1) / 2;
