@@ -702,6 +702,7 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
         ap.rpk_words = (ap.rpk_words + 3) & ~3;
         ap.hpk_words = (ap.hpk_words + 3) & ~3;
         ap.next_halfs = (ap.next_halfs + 7) & ~7;
+        ap.mult_halfs = (ap.heads_halfs + 7) & ~7;
         ap.heads_halfs = std::max(ap.heads_halfs, 4096);
         ap.heads_halfs = (ap.heads_halfs + 7) & ~7;
         ap.tab_bits = std::max(ap.tab_bits, 6);
@@ -710,7 +711,7 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
         ap.n_cnt = (int)std::max<size_t>(1, std::min<size_t>(nwarps, kAnchorCntBudget / ((size_t)ap.cnt_words * 4)));
         ch.a_smem = ((size_t)4 << ap.tab_bits) + (size_t)ap.n_cnt * ap.cnt_words * 4 + (size_t)ap.max_pairs * 16 +
                     (size_t)(ap.rpk_words + ap.hpk_words) * 4 + (size_t)ap.rid_halfs * 2 + (size_t)ap.next_halfs * 2 +
-                    (size_t)ap.heads_halfs * 4 + 16 + (size_t)ap.max_slots * sizeof(SlotInfo) +
+                    (size_t)(ap.heads_halfs + ap.mult_halfs) * 2 + 16 + (size_t)ap.max_slots * sizeof(SlotInfo) +
                     (size_t)ap.max_group * 12 + 16;
     }
     if (ch.a_smem + 1024 > (size_t)c->smem_optin)

@@ -185,6 +185,7 @@ struct AnchorPlan {
     int32_t next_halfs;     // u16 entries for all next arrays of a group
     int32_t rid_halfs;      // u16 entries for the read 7-mer ids of a tile
     int32_t heads_halfs;    // u16 entries of the head area (>= largest union size + 1)
+    int32_t mult_halfs;     // u16 entries of the per-id multiplicity bounds (>= largest union size + 1)
     int32_t rpk_words;      // u32 words for the 2-bit packed reads of a tile
     int32_t hpk_words;      // u32 words for the 2-bit packed haplotypes of a group
     int32_t cnt_words;      // u32 words of one warp's counter array (2 counters per word)
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
     uint16_t* s_rid = (uint16_t*)(s_hpk + plan.hpk_words);
     uint16_t* s_next = s_rid + plan.rid_halfs;
     uint16_t* s_mult = s_next + plan.next_halfs;              // per id: upper bound of its multiplicity in a haplotype
-    uint16_t* s_heads = s_mult + plan.heads_halfs;
+    uint16_t* s_heads = s_mult + plan.mult_halfs;
     SlotInfo* s_slot = (SlotInfo*)(((uintptr_t)(s_heads + plan.heads_halfs) + 15) & ~(uintptr_t)15);
     int32_t* s_hmeta = (int32_t*)(s_slot + plan.max_slots);  // per hap: len, next offset, packed offset
     __shared__ int s_nid, s_nfb, s_scan[kAnchorThreads / 32];
@@ -380,84 +381,38 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
             s_slot[s] = si;
         }
         __syncthreads();
-        if (tid == 0) {  // offsets of the per-read id rows (rows padded to 8 entries = 16 bytes)
-            int o = 0, po = 0;
-            for (int s = 0; s < ns; ++s) {
-                s_slot[s].hoff = o;
-                s_slot[s].poff = po;
-                const int nk = s_slot[s].len - kKmer;
-                if (nk > 0 && !(s_slot[s].flags & 1)) {
-                    o += (nk + 7) & ~7;
-                    po += ((s_slot[s].len + 15) >> 4) + kPackPadWords;
-                }
-            }
-        }
-        // ---- union table: insert the 14-bit hash of every indexed haplotype position
-        //      (calign.pyx:109: positions 0 .. len-8) ----
-        for (int g = 0; g < nh; ++g) {
-            const int len = s_hmeta[3 * g];
-            const uint8_t* hap = b.hap_seq + b.hap_seq_off[tile.h0 + g];
-            for (int i = tid; i < len - kKmer; i += nthr) {
-                const u32 key = kmer_hash(hap + i);
-                const u32 mask = (1u << bits) - 1;
-                u32 slot = tab_slot0(key, bits) & mask;
-                while (true) {
-                    const u32 old = atomicCAS(&s_tab[slot], kTabEmpty, key << 16);
-                    if (old == kTabEmpty || (old >> 16) == key) break;
-                    slot = (slot + 1) & mask;
-                }
-            }
-        }
-        __syncthreads();
-        // ---- dense ids 1..U for the occupied slots (block-wide exclusive scan) ----
-        {
-            const int per = (S + nthr - 1) / nthr;
-            const int lo = tid * per, hi = min(S, lo + per);
-            int cnt = 0;
-            for (int i = lo; i < hi; ++i) cnt += (s_tab[i] != kTabEmpty);
-            int incl = cnt;
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (lane == 31) s_scan[warp] = incl;
-            __syncthreads();
-            int base = 0;
-            for (int k = 0; k < warp; ++k) base += s_scan[k];
-            if (tid == nthr - 1) s_nid = base + incl;
-            int id = base + incl - cnt;
-            for (int i = lo; i < hi; ++i)
-                if (s_tab[i] != kTabEmpty) s_tab[i] = (s_tab[i] & 0xFFFF0000u) | (u32)(++id);
-        }
-        __syncthreads();
-        const int U = s_nid;  // number of distinct 7-mers in this haplotype group
-        // ---- read 7-mer ids (calign.pyx:155-165: k-mers 0..len-8); rolling hash per thread ----
-        {
-            // work item = (slot, block of 32 consecutive k-mers)
-            for (int s = warp; s < ns; s += nwarp) {
-                const SlotInfo si = s_slot[s];
-                const int nk = si.len - kKmer;
-                if ((si.flags & 1) || nk <= 0) continue;
-                const uint8_t* rs = b.read_seq + b.read_seq_off[si.read];
-                const int nkp = (nk + 7) & ~7;
-                // each lane hashes a run of consecutive k-mers
-                const int run = (nkp + 31) / 32;
-                const int i0 = lane * run;
-                if (i0 < nkp) {
-                    u32 h = 0;
-                    if (i0 < nk) h = kmer_hash(rs + i0);
-                    for (int i = i0; i < min(nkp, i0 + run); ++i) {
-                        uint16_t id = 0;
-                        if (i < nk) {
-                            if (i > i0) h = ((h << 2) & (kHashSize - 1)) + base_code(rs[i + kKmer - 1]);
-                            id = (uint16_t)tab_lookup(s_tab, bits, h);
-                        }
-                        s_rid[si.hoff + i] = id;
+        if (tid < 32) {  // offsets of the per-read id rows (padded to 8 entries) and packed rows: warp scan
+            int co = 0, cp = 0;
+            for (int s0 = 0; s0 < ns; s0 += 32) {
+                const int s = s0 + tid;
+                int no = 0, np = 0;
+                if (s < ns) {
+                    const int nk = s_slot[s].len - kKmer;
+                    if (nk > 0 && !(s_slot[s].flags & 1)) {
+                        no = (nk + 7) & ~7;
+                        np = ((s_slot[s].len + 15) >> 4) + kPackPadWords;
                     }
                 }
+                int io = no, ip = np;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int vo = __shfl_up_sync(0xFFFFFFFFu, io, o), vp = __shfl_up_sync(0xFFFFFFFFu, ip, o);
+                    if (tid >= o) {
+                        io += vo;
+                        ip += vp;
+                    }
+                }
+                if (s < ns) {
+                    s_slot[s].hoff = co + io - no;
+                    s_slot[s].poff = cp + ip - np;
+                }
+                co += __shfl_sync(0xFFFFFFFFu, io, 31);
+                cp += __shfl_sync(0xFFFFFFFFu, ip, 31);
             }
         }
-        // ---- 2-bit packed reads and haplotypes for the per-offset vote counts (plb_kmer.cuh) ----
+        __syncthreads();
+        // ---- the only pass over the raw bases: pack reads and haplotypes 2 bits per base (the
+        //      reference's hash digit, calign.pyx:69-74).  7-mer keys, read ids and vote counts all
+        //      derive from these words. ----
         for (int s = warp; s < ns; s += nwarp) {
             const SlotInfo si = s_slot[s];
             if ((si.flags & 1) || si.len <= kKmer) continue;
@@ -493,6 +448,59 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
                 dst[wd] = v;
             }
         }
+        __syncthreads();
+        // 7-mer key of position p of a packed sequence: its 14 bits, first base in the low bits (a
+        // digit-reversed copy of the reference's hash - any bijection of the hash gives the same votes)
+        auto key_at = [](const u32* pk, int p) -> u32 { return fsr(pk[p >> 4], pk[(p >> 4) + 1], 2 * (p & 15)) & 0x3FFFu; };
+        // ---- union table: insert the key of every indexed haplotype position
+        //      (calign.pyx:109: positions 0 .. len-8) ----
+        for (int g = 0; g < nh; ++g) {
+            const int nkh = s_hmeta[3 * g] - kKmer;
+            const u32* hpk = s_hpk + s_hmeta[3 * g + 2];
+            for (int i = tid; i < nkh; i += nthr) {
+                const u32 key = key_at(hpk, i);
+                const u32 mask = (1u << bits) - 1;
+                u32 slot = tab_slot0(key, bits) & mask;
+                while (true) {
+                    const u32 old = atomicCAS(&s_tab[slot], kTabEmpty, key << 16);
+                    if (old == kTabEmpty || (old >> 16) == key) break;
+                    slot = (slot + 1) & mask;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- dense ids 1..U for the occupied slots (block-wide exclusive scan) ----
+        {
+            const int per = (S + nthr - 1) / nthr;
+            const int lo = tid * per, hi = min(S, lo + per);
+            int cnt = 0;
+            for (int i = lo; i < hi; ++i) cnt += (s_tab[i] != kTabEmpty);
+            int incl = cnt;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) s_scan[warp] = incl;
+            __syncthreads();
+            int base = 0;
+            for (int k = 0; k < warp; ++k) base += s_scan[k];
+            if (tid == nthr - 1) s_nid = base + incl;
+            int id = base + incl - cnt;
+            for (int i = lo; i < hi; ++i)
+                if (s_tab[i] != kTabEmpty) s_tab[i] = (s_tab[i] & 0xFFFF0000u) | (u32)(++id);
+        }
+        __syncthreads();
+        const int U = s_nid;  // number of distinct 7-mers in this haplotype group
+        // ---- read 7-mer ids (calign.pyx:155-165: k-mers 0..len-8) ----
+        for (int s = warp; s < ns; s += nwarp) {
+            const SlotInfo si = s_slot[s];
+            const int nk = si.len - kKmer;
+            if ((si.flags & 1) || nk <= 0) continue;
+            const u32* rpk = s_rpk + si.poff;
+            const int nkp = (nk + 7) & ~7;
+            for (int i = lane; i < nkp; i += 32)
+                s_rid[si.hoff + i] = i < nk ? (uint16_t)tab_lookup(s_tab, bits, key_at(rpk, i)) : (uint16_t)0;
+        }
         const int general = b.win_flags[w] & 1;
         const int hstride = U + 1;
         const int sub_max = max(1, min(nh, plan.heads_halfs / hstride));
@@ -505,11 +513,11 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
             __syncthreads();
             for (int g = g0; g < g1; ++g) {
                 const int len = s_hmeta[3 * g];
-                const uint8_t* hap = b.hap_seq + b.hap_seq_off[tile.h0 + g];
+                const u32* hpk = s_hpk + s_hmeta[3 * g + 2];
                 uint16_t* nxt = s_next + s_hmeta[3 * g + 1];
                 unsigned short* head = (unsigned short*)(s_heads + (g - g0) * hstride);
                 for (int i = tid; i < len - kKmer; i += nthr) {
-                    const u32 id = tab_lookup(s_tab, bits, kmer_hash(hap + i));
+                    const u32 id = tab_lookup(s_tab, bits, key_at(hpk, i));
                     unsigned short cur = head[id];
                     while (true) {  // push position i (stored as i+1); order inside a chain is irrelevant.
                         // bit 15 of the head marks chains with more than one element.
@@ -812,17 +820,26 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
             s_slot[s] = ds;
         }
         __syncthreads();
-        if (tid == 0) {
-            int o = 0;
-            for (int s = 0; s < ns; ++s) {
-                s_slot[s].poff = o;
-                const int L = s_slot[s].len;
-                if (!(s_slot[s].flags & 1) && L >= kMinFastLen && L <= kMaxFastLen) {
-                    int n = dp_steps(L) + 4;           // rows read by the kernel, +4 keeps rows 16-byte apart
-                    n = (n + 3) & ~3;
-                    if (!((n >> 2) & 1)) n += 4;       // odd multiple of 16 bytes: conflict-free LDS.128
-                    o += n;
+        if (tid < 32) {  // exclusive scan of the profile-row sizes by one warp
+            int carry = 0;
+            for (int s0 = 0; s0 < ns; s0 += 32) {
+                const int s = s0 + tid;
+                int n = 0;
+                if (s < ns) {
+                    const int L = s_slot[s].len;
+                    if (!(s_slot[s].flags & 1) && L >= kMinFastLen && L <= kMaxFastLen) {
+                        n = dp_steps(L) + 4;           // rows read by the kernel, +4 keeps rows 16-byte apart
+                        n = (n + 3) & ~3;
+                        if (!((n >> 2) & 1)) n += 4;   // odd multiple of 16 bytes: conflict-free LDS.128
+                    }
                 }
+                int incl = n;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (tid >= o) incl += v;
+                }
+                if (s < ns) s_slot[s].poff = carry + incl - n;
+                carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
             }
         }
         __syncthreads();
@@ -840,13 +857,26 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                 const uint8_t* rq = b.read_qual + b.read_seq_off[ds.read];
                 int n = dp_steps(ds.len) + 4;
                 u32* row = s_prof + ds.poff;
-                for (int y = lane; y < n; y += 32) {
-                    u32 v = 0u;
-                    if (y < ds.len) {
-                        const int code = fast_code(rs[y]);
-                        v = six ? make_profile6(code, rq[y], K) : make_profile(code, rq[y]);
+                for (int y0 = 0; y0 < n; y0 += 192) {   // 6 rows per lane, all loads issued before use
+                    uint8_t cb[6], qb[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const int y = y0 + lane + 32 * k;
+                        cb[k] = y < ds.len ? rs[y] : (uint8_t)0;
+                        qb[k] = y < ds.len ? rq[y] : (uint8_t)0;
                     }
-                    row[y] = v;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const int y = y0 + lane + 32 * k;
+                        if (y < n) {
+                            u32 v = 0u;
+                            if (y < ds.len) {
+                                const int code = fast_code(cb[k]);
+                                v = six ? make_profile6(code, qb[k], K) : make_profile(code, qb[k]);
+                            }
+                            row[y] = v;
+                        }
+                    }
                 }
             }
             // haplotype records
@@ -857,10 +887,10 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                 const uint8_t* go = b.gap_open + b.hap_seq_off[h] + h;
                 HapRec* rec = s_rec + s_roff[g];
                 for (int x = tid; x < len + kRecPad; x += NTHR) {
-                    const int ca = x < len ? fast_code(hap[x]) : 4;
-                    const int cb = x + 4 < len ? fast_code(hap[x + 4]) : 4;
+                    const uint8_t ha = x < len ? hap[x] : (uint8_t)'N', hb = x + 4 < len ? hap[x + 4] : (uint8_t)'N';
                     const u32 oa = x <= len ? go[x] : 0u;
                     const u32 ob = x + 4 <= len ? go[x + 4] : 0u;
+                    const int ca = fast_code(ha), cb = fast_code(hb);
                     HapRec r;
                     if (six) {
                         r.gow = pack_s16x2((int)oa - sp.ext, (int)ob - sp.ext);
