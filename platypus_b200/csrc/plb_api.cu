@@ -413,7 +413,6 @@ static int plan_tiles(const PlbWindowBatch* hb, int w_begin, int w_end, TileList
                     ap.max_pairs = std::max<int>(ap.max_pairs, (int)(c1 - c0) * (g.second - g.first));
                 }
                 ap.max_slots = std::max<int>(ap.max_slots, (int)(c1 - c0));
-                ap.rid_halfs = std::max<int>(ap.rid_halfs, (int)halfs);
                 ap.rpk_words = std::max<int>(ap.rpk_words, (int)pkw);
             };
             for (int64_t s = s0; s < s1; ++s) {
@@ -677,7 +676,6 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
             A.max_pairs = std::max(A.max_pairs, q.max_pairs);
             A.tab_bits = std::max(A.tab_bits, q.tab_bits);
             A.next_halfs = std::max(A.next_halfs, q.next_halfs);
-            A.rid_halfs = std::max(A.rid_halfs, q.rid_halfs);
             A.heads_halfs = std::max(A.heads_halfs, q.heads_halfs);
             A.rpk_words = std::max(A.rpk_words, q.rpk_words);
             A.hpk_words = std::max(A.hpk_words, q.hpk_words);
@@ -698,7 +696,6 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
     {
         AnchorPlan& ap = ch.ap;
         ap.max_pairs = (ap.max_pairs + 3) & ~3;
-        ap.rid_halfs = (ap.rid_halfs + 7) & ~7;
         ap.rpk_words = (ap.rpk_words + 3) & ~3;
         ap.hpk_words = (ap.hpk_words + 3) & ~3;
         ap.next_halfs = (ap.next_halfs + 7) & ~7;
@@ -710,7 +707,7 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
         const int nwarps = kAnchorThreads / 32;
         ap.n_cnt = (int)std::max<size_t>(1, std::min<size_t>(nwarps, kAnchorCntBudget / ((size_t)ap.cnt_words * 4)));
         ch.a_smem = ((size_t)4 << ap.tab_bits) + (size_t)ap.n_cnt * ap.cnt_words * 4 + (size_t)ap.max_pairs * 16 +
-                    (size_t)(ap.rpk_words + ap.hpk_words) * 4 + (size_t)ap.rid_halfs * 2 + (size_t)ap.next_halfs * 2 +
+                    (size_t)(ap.rpk_words + ap.hpk_words) * 4 + (size_t)ap.next_halfs * 2 +
                     (size_t)(ap.heads_halfs + ap.mult_halfs) * 2 + 16 + (size_t)ap.max_slots * sizeof(SlotInfo) +
                     (size_t)ap.max_group * 12 + 16;
     }

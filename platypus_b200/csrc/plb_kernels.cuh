@@ -164,8 +164,7 @@ __global__ void __launch_bounds__(128) k_prep(DevBatch b, int h_base) {
 // The reference keeps, per haplotype, a 16384-entry hash table plus chains, and per pair a vote
 // array of hapLen+readLen counters that it clears, fills and scans.  Here:
 //   * one open-addressed table per TILE maps the 14-bit 7-mer hash to a dense id over the union of
-//     the group's haplotype 7-mers; each read 7-mer is translated to its id ONCE (s_rid) and
-//     reused for every haplotype;
+//     the group's haplotype 7-mers;
 //   * per haplotype, head[id] / next[pos] chains give the positions carrying that 7-mer (the
 //     reference's hash_table / next_array, calign.pyx:94-124);
 //   * votes are not stored: a Boyer-Moore pass finds the only offset that can hold a strict
@@ -183,7 +182,6 @@ struct AnchorPlan {
     int32_t max_pairs;      // slots*haplotypes per tile upper bound
     int32_t tab_bits;       // log2(slots) of the union 7-mer table
     int32_t next_halfs;     // u16 entries for all next arrays of a group
-    int32_t rid_halfs;      // u16 entries for the read 7-mer ids of a tile
     int32_t heads_halfs;    // u16 entries of the head area (>= largest union size + 1)
     int32_t mult_halfs;     // u16 entries of the per-id multiplicity bounds (>= largest union size + 1)
     int32_t rpk_words;      // u32 words for the 2-bit packed reads of a tile
@@ -196,7 +194,6 @@ struct SlotInfo {
     int32_t read;     // read pool index
     int32_t len;      // read length
     int32_t pos;      // read.pos
-    int32_t hoff;     // offset into the read-id area
     int32_t flags;    // bit0 = LL forced to 0 (QC fail / overlap < 7)
     int32_t vub;      // upper bound of the votes this read can cast on any haplotype of the sub-group
     int32_t poff;     // offset (u32 words) of the 2-bit packed read
@@ -248,6 +245,12 @@ struct Emitter {
     }
 };
 
+// 7-mer key of position p of a packed sequence: its 14 bits, first base in the low bits (a
+// digit-reversed copy of the reference's hash - any bijection of the hash gives the same votes)
+__device__ __forceinline__ u32 key_at(const u32* pk, int p) {
+    return fsr(pk[p >> 4], pk[(p >> 4) + 1], 2 * (p & 15)) & 0x3FFFu;
+}
+
 __device__ __forceinline__ u32 tab_lookup(const u32* tab, int bits, u32 key) {
     const u32 mask = (1u << bits) - 1;
     u32 slot = tab_slot0(key, bits) & mask;
@@ -271,13 +274,16 @@ constexpr int kPairSkip = 0x40000001;       // nothing to decide (LL forced to 0
 constexpr int kPairUndecided = 0x40000002;  // goes to the exact vote array
 
 struct LightArgs {
-    u32 head_off, rid_off, rpk_off, hpk_off, res_off;
-    int nk_read, nk_hap, vub;
+    u32 head_off, rpk_off, hpk_off, res_off;
+    int nk_read, nk_hap, vub, bits;
 };
 
-__device__ __forceinline__ int unique_hit_offset(const uint16_t* head, const uint16_t* rid, int i0, int i1, int step) {
+// offset implied by the first read 7-mer in [i0, i1) (walking by step) that occurs exactly once in
+// the haplotype; read 7-mer -> id through the tile's table (smem offset 0), id -> position through head
+__device__ __forceinline__ int unique_hit_offset(const u32* tab, int bits, const uint16_t* head, const u32* rpk, int i0,
+                                                 int i1, int step) {
     for (int i = i0; i != i1; i += step) {
-        const u32 hd = head[rid[i]];
+        const u32 hd = head[tab_lookup(tab, bits, key_at(rpk, i))];
         if (hd && !(hd & 0x8000u)) return (int)hd - 1 - i;
     }
     return kNoCand;
@@ -286,7 +292,7 @@ __device__ __forceinline__ int unique_hit_offset(const uint16_t* head, const uin
 __device__ __noinline__ int light_decide(LightArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint16_t* head = (const uint16_t*)(smem + a.head_off);
-    const uint16_t* rid = (const uint16_t*)(smem + a.rid_off);
+    const u32* tab = (const u32*)smem;
     const u32* rpk = (const u32*)(smem + a.rpk_off);
     const u32* hpk = (const u32*)(smem + a.hpk_off);
     u32* res = (u32*)(smem + a.res_off);
@@ -297,10 +303,10 @@ __device__ __noinline__ int light_decide(LightArgs a) {
     }
     const int lim = min(nk, 24);
     int g[3], c[3] = {0, 0, 0};
-    g[0] = unique_hit_offset(head, rid, 0, lim, 1);
-    g[1] = unique_hit_offset(head, rid, nk - 1, nk - 1 - lim, -1);
+    g[0] = unique_hit_offset(tab, a.bits, head, rpk, 0, lim, 1);
+    g[1] = unique_hit_offset(tab, a.bits, head, rpk, nk - 1, nk - 1 - lim, -1);
     const int mid = nk >> 1;
-    g[2] = unique_hit_offset(head, rid, mid, min(nk, mid + lim), 1);
+    g[2] = unique_hit_offset(tab, a.bits, head, rpk, mid, min(nk, mid + lim), 1);
     if (g[1] == g[0]) g[1] = kNoCand;
     if (g[2] == g[0] || g[2] == g[1]) g[2] = kNoCand;
     int R = a.vub, top = 0;
@@ -318,7 +324,7 @@ __device__ __noinline__ int light_decide(LightArgs a) {
     return 1;
 }
 
-__global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, AnchorPlan plan, Queue q, ScoreParams sp,
+__global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, AnchorPlan plan, Queue q, ScoreParams sp,
                                                            Counters* ctr) {
     extern __shared__ __align__(16) uint8_t smem[];
     u32* s_tab = (u32*)smem;
@@ -327,8 +333,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
     u32* s_vlist = s_fblist + plan.max_pairs;                 // per pair: up to three tied-maximum offsets
     u32* s_rpk = s_vlist + 3 * (size_t)plan.max_pairs;        // 2-bit packed reads
     u32* s_hpk = s_rpk + plan.rpk_words;                      // 2-bit packed haplotypes (padded both sides)
-    uint16_t* s_rid = (uint16_t*)(s_hpk + plan.hpk_words);
-    uint16_t* s_next = s_rid + plan.rid_halfs;
+    uint16_t* s_next = (uint16_t*)(s_hpk + plan.hpk_words);
     uint16_t* s_mult = s_next + plan.next_halfs;              // per id: upper bound of its multiplicity in a haplotype
     uint16_t* s_heads = s_mult + plan.mult_halfs;
     SlotInfo* s_slot = (SlotInfo*)(((uintptr_t)(s_heads + plan.heads_halfs) + 15) & ~(uintptr_t)15);
@@ -375,37 +380,24 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
                 const int ov = read_overlap(b.win_start[w], b.win_end[w], si.pos, b.read_end[r]);
                 if (b.read_qcfail[r] || ov < kKmer) si.flags = 1;
             }
-            si.hoff = 0;
             si.vub = 0;
             si.poff = 0;
             s_slot[s] = si;
         }
         __syncthreads();
-        if (tid < 32) {  // offsets of the per-read id rows (padded to 8 entries) and packed rows: warp scan
-            int co = 0, cp = 0;
+        if (tid < 32) {  // offsets of the packed read rows: warp scan
+            int cp = 0;
             for (int s0 = 0; s0 < ns; s0 += 32) {
                 const int s = s0 + tid;
-                int no = 0, np = 0;
-                if (s < ns) {
-                    const int nk = s_slot[s].len - kKmer;
-                    if (nk > 0 && !(s_slot[s].flags & 1)) {
-                        no = (nk + 7) & ~7;
-                        np = ((s_slot[s].len + 15) >> 4) + kPackPadWords;
-                    }
-                }
-                int io = no, ip = np;
+                int np = 0;
+                if (s < ns && s_slot[s].len > kKmer && !(s_slot[s].flags & 1))
+                    np = ((s_slot[s].len + 15) >> 4) + kPackPadWords;
+                int ip = np;
                 for (int o = 1; o < 32; o <<= 1) {
-                    const int vo = __shfl_up_sync(0xFFFFFFFFu, io, o), vp = __shfl_up_sync(0xFFFFFFFFu, ip, o);
-                    if (tid >= o) {
-                        io += vo;
-                        ip += vp;
-                    }
+                    const int vp = __shfl_up_sync(0xFFFFFFFFu, ip, o);
+                    if (tid >= o) ip += vp;
                 }
-                if (s < ns) {
-                    s_slot[s].hoff = co + io - no;
-                    s_slot[s].poff = cp + ip - np;
-                }
-                co += __shfl_sync(0xFFFFFFFFu, io, 31);
+                if (s < ns) s_slot[s].poff = cp + ip - np;
                 cp += __shfl_sync(0xFFFFFFFFu, ip, 31);
             }
         }
@@ -449,9 +441,6 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
             }
         }
         __syncthreads();
-        // 7-mer key of position p of a packed sequence: its 14 bits, first base in the low bits (a
-        // digit-reversed copy of the reference's hash - any bijection of the hash gives the same votes)
-        auto key_at = [](const u32* pk, int p) -> u32 { return fsr(pk[p >> 4], pk[(p >> 4) + 1], 2 * (p & 15)) & 0x3FFFu; };
         // ---- union table: insert the key of every indexed haplotype position
         //      (calign.pyx:109: positions 0 .. len-8) ----
         for (int g = 0; g < nh; ++g) {
@@ -491,16 +480,6 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
         }
         __syncthreads();
         const int U = s_nid;  // number of distinct 7-mers in this haplotype group
-        // ---- read 7-mer ids (calign.pyx:155-165: k-mers 0..len-8) ----
-        for (int s = warp; s < ns; s += nwarp) {
-            const SlotInfo si = s_slot[s];
-            const int nk = si.len - kKmer;
-            if ((si.flags & 1) || nk <= 0) continue;
-            const u32* rpk = s_rpk + si.poff;
-            const int nkp = (nk + 7) & ~7;
-            for (int i = lane; i < nkp; i += 32)
-                s_rid[si.hoff + i] = i < nk ? (uint16_t)tab_lookup(s_tab, bits, key_at(rpk, i)) : (uint16_t)0;
-        }
         const int general = b.win_flags[w] & 1;
         const int hstride = U + 1;
         const int sub_max = max(1, min(nh, plan.heads_halfs / hstride));
@@ -553,7 +532,8 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
                 const int nk = si.len - kKmer;
                 if ((si.flags & 1) || nk <= 0) continue;
                 int sum = 0;
-                for (int i = lane; i < nk; i += 32) sum += s_mult[s_rid[si.hoff + i]];
+                const u32* rpk = s_rpk + si.poff;   // read 7-mers 0..len-8 (calign.pyx:155-165)
+                for (int i = lane; i < nk; i += 32) sum += s_mult[tab_lookup(s_tab, bits, key_at(rpk, i))];
                 for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
                 if (lane == 0) s_slot[s].vub = sum;
             }
@@ -589,13 +569,13 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
                 st_cells += 16ull * si.len;
                 LightArgs la;
                 la.head_off = (u32)((uint8_t*)(s_heads + (g - g0) * hstride) - smem);
-                la.rid_off = (u32)((uint8_t*)(s_rid + si.hoff) - smem);
                 la.rpk_off = (u32)((uint8_t*)(s_rpk + si.poff) - smem);
                 la.hpk_off = (u32)((uint8_t*)(s_hpk + s_hmeta[3 * g + 2]) - smem);
                 la.res_off = (u32)((uint8_t*)(s_vlist + 3 * p) - smem);
                 la.nk_read = si.len - kKmer;
                 la.nk_hap = s_hmeta[3 * g] - kKmer;
                 la.vub = si.vub;
+                la.bits = bits;
                 if (!light_decide(la)) {
                     s_vlist[3 * p] = (u32)kPairUndecided;
                     s_fblist[atomicAdd(&s_nfb, 1)] = (u32)p;
@@ -656,14 +636,14 @@ __global__ void __launch_bounds__(kAnchorThreads, 3) k_anchor(DevBatch b, Anchor
                 const int hap_len = s_hmeta[3 * g];
                 const uint16_t* nxt = s_next + s_hmeta[3 * g + 1];
                 const uint16_t* head = s_heads + (g - g0) * hstride;
-                const uint16_t* rid = s_rid + si.hoff;
+                const u32* rpk = s_rpk + si.poff;
                 u32* cw = s_cnt + (size_t)warp * plan.cnt_words;
                 const int C = hap_len + L;
                 const int words = (C + 1) >> 1;
                 for (int k = lane; k < words; k += 32) cw[k] = 0;
                 __syncwarp();
                 for (int i = lane; i < nk; i += 32) {
-                    const u32 id = rid[i];
+                    const u32 id = tab_lookup(s_tab, bits, key_at(rpk, i));
                     if (!id) continue;
                     u32 p1 = head[id] & 0x7FFFu;
                     while (p1) {
