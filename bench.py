@@ -43,6 +43,10 @@ UNIT = "GCUPS"
 
 
 def workload_config(n_gpus, windows):
+    if RAGGED:
+        return {"workload": "synth-v1 config3 shapes: %d windows x %d haplotypes x %d reads per GPU, reads 100-250 bp, "
+                            "haplotypes 200-500 bp (profiling configuration, not the headline)" % (windows, N_HAPS, N_READS),
+                "windows_per_gpu": windows, "n_gpus": n_gpus}
     return {
         "workload": "synth-v1 config2: %d windows x %d haplotypes x %d reads per GPU, %d bp reads x %d bp haplotypes"
                     % (windows, N_HAPS, N_READS, READ_LEN, HAP_LEN),
@@ -55,13 +59,14 @@ def workload_config(n_gpus, windows):
     }
 
 
+RAGGED = False   # --config 3: read length U{100..250}, haplotype length U[max(200, Lmax+16), 500]
+
+
 def make_workload(rank, windows):
     from platypus_b200 import synth
-    cache = "/tmp/plb_synth_v1_c2_w%d_off%d.npz" % (windows, rank * windows)
     t0 = time.time()
-    b = synth.make_batch_parallel(windows, window_offset=rank * windows, n_haps=N_HAPS, n_reads=N_READS,
-                                  read_len=READ_LEN, hap_len=HAP_LEN)
-    del cache
+    kw = dict(read_len_range=(100, 250), hap_len_range=(200, 500)) if RAGGED else dict(read_len=READ_LEN, hap_len=HAP_LEN)
+    b = synth.make_batch_parallel(windows, window_offset=rank * windows, n_haps=N_HAPS, n_reads=N_READS, **kw)
     return b, time.time() - t0
 
 
@@ -329,7 +334,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--windows", type=int, default=WINDOWS_PER_GPU, help="windows per GPU (default: config 2)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
+                    help="2 = BASELINE config 2 (headline); 3 = ragged read/haplotype lengths (profiling only)")
     args = ap.parse_args()
+    global RAGGED
+    RAGGED = args.config == 3
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

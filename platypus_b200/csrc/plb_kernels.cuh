@@ -762,7 +762,8 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
     HapRec* s_rec = (HapRec*)(s_prof + plan.prof_words);
     DpSlot* s_slot = (DpSlot*)(s_rec + plan.rec_count);
     int32_t* s_roff = (int32_t*)(s_slot + plan.max_slots);       // per hap: record offset
-    int32_t* s_best = s_roff + plan.max_group;                   // per pair: best score
+    int32_t* s_order = s_roff + plan.max_group;                  // slots by decreasing read length
+    int32_t* s_best = s_order + plan.max_slots;                  // per pair: best score
     u32* s_task = (u32*)(s_best + plan.max_pairs);               // compacted tasks
     __shared__ int s_ntask;
 
@@ -800,6 +801,17 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
             s_slot[s] = ds;
         }
         __syncthreads();
+        // Tasks are enumerated slot-major in order of decreasing read length, so that the 32 alignments
+        // of a warp have (almost) the same number of steps and the longest ones start first.
+        for (int s = tid; s < ns; s += NTHR) {
+            const int L = s_slot[s].len;
+            int rank = 0;
+            for (int j = 0; j < ns; ++j) {
+                const int Lj = s_slot[j].len;
+                rank += (Lj > L) || (Lj == L && j < s);
+            }
+            s_order[rank] = s;
+        }
         if (tid < 32) {  // exclusive scan of the profile-row sizes by one warp
             int carry = 0;
             for (int s0 = 0; s0 < ns; s0 += 32) {
@@ -889,7 +901,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
             const int p = p0 + tid;
             int c0 = -1, c1 = -1;
             if (p < npairs) {
-                const int s = p % ns, g = p / ns;
+                const int s = s_order[p / nh], g = p % nh;
                 const int64_t gs = tile.s0 + s;
                 const int wi = b.slot_wi[gs];
                 const int64_t T = b.wi_slot_off[wi + 1] - b.wi_slot_off[wi];
@@ -920,7 +932,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
         for (int k = tid; k < ntask; k += NTHR) {
             const u32 tk = s_task[k];
             const int p = (int)(tk >> 15), start = (int)(tk & 0x7FFFu);
-            const int s = p % ns, g = p / ns;
+            const int s = s_order[p / nh], g = p % nh;
             const DpSlot ds = s_slot[s];
             const int v = six ? band_dp_fast6(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc)
                               : band_dp_fast(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc);
@@ -929,7 +941,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
         __syncthreads();
         // score -> log-likelihood (chaplotype.pyx:675-676) and output
         for (int p = tid; p < npairs; p += NTHR) {
-            const int s = p % ns, g = p / ns;
+            const int s = s_order[p / nh], g = p % nh;
             const DpSlot ds = s_slot[s];
             const int64_t gs = tile.s0 + s;
             const int wi = b.slot_wi[gs];

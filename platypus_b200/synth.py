@@ -200,17 +200,34 @@ def make_batch(n_windows, n_haps=8, n_reads=64, read_len=150, hap_len=250, n_ind
     return b
 
 
+def scored_slots(batch: WindowBatch) -> np.ndarray:
+    """Boolean per slot: True where the reference scores the read, False where Haplotype.alignReads
+    short-circuits it to LL = 0 (QC fail or < 7 bp overlap with the window, good and bad reads only;
+    reference: src/cython/chaplotype.pyx:343-361)."""
+    nI = batch.n_individuals
+    n_slots = batch.n_slots
+    wi_of_slot = np.repeat(np.arange(batch.n_windows * nI), np.diff(batch.wi_slot_off))
+    t = np.arange(n_slots) - batch.wi_slot_off[wi_of_slot]
+    checked = t < (batch.wi_n_good + batch.wi_n_bad)[wi_of_slot]
+    w = wi_of_slot // nI
+    r = batch.slot_read
+    s = np.maximum(batch.win_start[w], batch.read_pos[r])
+    e = np.minimum(batch.win_end[w], batch.read_end[r])
+    overlap = np.where(e > s, e - s, -1)
+    skip = checked & ((batch.read_qcfail[r] != 0) | (overlap < 7))
+    return ~skip
+
+
 def algorithmic_cells(batch: WindowBatch) -> int:
-    """16 * readLen per (read, haplotype) pair, ignoring LL=0 short-circuits
-    (synth-v1 has none)."""
-    H = np.repeat(batch.haps_per_window().astype(np.int64), batch.n_individuals)
-    tot = 0
+    """16 * readLen per scored (read, haplotype) pair; pairs short-circuited by the
+    QC-fail / overlap rule count 0."""
+    nI = batch.n_individuals
+    H = np.repeat(batch.haps_per_window().astype(np.int64), nI)
     lens = np.diff(batch.read_seq_off)
-    slot_len = lens[batch.slot_read]
+    slot_len = np.where(scored_slots(batch), lens[batch.slot_read], 0).astype(np.int64)
     cs = np.concatenate([[0], np.cumsum(slot_len)])
     per_wi = cs[batch.wi_slot_off[1:]] - cs[batch.wi_slot_off[:-1]]
-    tot = int((per_wi * H).sum()) * 16
-    return tot
+    return int((per_wi * H).sum()) * 16
 
 
 def algorithmic_bytes(batch: WindowBatch) -> int:
