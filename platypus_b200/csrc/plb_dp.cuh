@@ -98,13 +98,11 @@ PLB_HD u32 make_profile(int code, u32 qual) {
 // other byte is 5 (never matches anything; windows whose haplotypes contain such bytes take
 // the general path, reads may contain them freely).
 PLB_HD int fast_code(uint8_t ch) {
-    // branch-free: (ch>>1)&7 maps A,C,T,G,N to 0,1,2,3,7; the byte tables confirm the exact letter
-    const u32 idx = (ch >> 1) & 7u;
-    const unsigned long long expect = 0x4EFFFFFF47544341ull;   // 'A','C','T','G',ff,ff,ff,'N'
-    const unsigned long long codes = 0x0405050502030100ull;    //  0 , 1 , 3 , 2 , 5, 5, 5, 4
-    const u32 e = (u32)(expect >> (8 * idx)) & 0xFFu;
-    const u32 c = (u32)(codes >> (8 * idx)) & 0xFFu;
-    return e == ch ? (int)c : 5;
+    // branch-free: (ch>>1)&3 maps A,C,T,G to 0,1,2,3; the byte table confirms the exact letter
+    const u32 idx = (ch >> 1) & 3u;
+    const u32 e = (0x47544341u >> (8 * idx)) & 0xFFu;   // 'A','C','T','G'
+    const u32 c = (0x02030100u >> (8 * idx)) & 0xFFu;   //  0 , 1 , 3 , 2
+    return e == ch ? (int)c : (ch == 'N' ? 4 : 5);
 }
 
 // number of step pairs executed for a read of length L (multiple of 8, >= 24)

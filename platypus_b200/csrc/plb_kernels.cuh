@@ -197,6 +197,8 @@ struct SlotInfo {
     int32_t flags;    // bit0 = LL forced to 0 (QC fail / overlap < 7)
     int32_t vub;      // upper bound of the votes this read can cast on any haplotype of the sub-group
     int32_t poff;     // offset (u32 words) of the 2-bit packed read
+    int32_t T;        // reads of this (window, individual): stride between haplotype rows of the LL block
+    int64_t pair0;    // LL index of (first haplotype of the window, this slot)
 };
 
 __device__ __forceinline__ int read_overlap(int ws, int we, int rp, int re) {  // chaplotype.pyx:103-115
@@ -382,6 +384,8 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             }
             si.vub = 0;
             si.poff = 0;
+            si.T = (int)(b.wi_slot_off[wi + 1] - b.wi_slot_off[wi]);
+            si.pair0 = b.ll_off[wi] + t;
             s_slot[s] = si;
         }
         __syncthreads();
@@ -540,13 +544,12 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             __syncthreads();
             // ---- per (slot, haplotype) pair: light decision, else exact vote array ----
             const int npairs = ns * (g1 - g0);
+            const int hloc0 = tile.h0 - b.win_hap_off[w];   // index of the tile's first haplotype in its window
             auto pair_id = [&](int p, int& s, int& g, int64_t& gs, int64_t& pair) {
                 s = p % ns;
                 g = g0 + p / ns;
                 gs = tile.s0 + s;
-                const int wi = b.slot_wi[gs];
-                const int64_t T = b.wi_slot_off[wi + 1] - b.wi_slot_off[wi];
-                pair = b.ll_off[wi] + (int64_t)(tile.h0 + g - b.win_hap_off[w]) * T + (gs - b.wi_slot_off[wi]);
+                pair = s_slot[s].pair0 + (int64_t)(hloc0 + g) * s_slot[s].T;
             };
             for (int p = tid; p < npairs; p += nthr) {
                 int s, g;
@@ -629,9 +632,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 const SlotInfo si = s_slot[s];
                 const int h = tile.h0 + g;
                 const int64_t gs = tile.s0 + s;
-                const int wi = b.slot_wi[gs];
-                const int64_t T = b.wi_slot_off[wi + 1] - b.wi_slot_off[wi];
-                const int64_t pair = b.ll_off[wi] + (int64_t)(h - b.win_hap_off[w]) * T + (gs - b.wi_slot_off[wi]);
+                const int64_t pair = si.pair0 + (int64_t)(h - b.win_hap_off[w]) * si.T;
                 const int L = si.len, nk = L - kKmer;
                 const int hap_len = s_hmeta[3 * g];
                 const uint16_t* nxt = s_next + s_hmeta[3 * g + 1];

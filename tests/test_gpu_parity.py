@@ -153,6 +153,23 @@ def test_s3_multi_individual(engine, oracle):
     _check_population(got, want, rtol=1e-7)   # newFreq sums over individuals are reduced per thread
 
 
+def test_s3_many_individuals(engine, oracle):
+    """Multi-sample shape (config 5 in miniature): 300 individuals x 4 reads per window, so that a
+    window spans several tiles and the EM / posterior kernels run their multi-individual path."""
+    b = synth.make_batch(5, n_haps=5, n_reads=4, n_individuals=300, read_len=80, hap_len=200)
+    got = engine.population_run(b, want_ll=True)
+    want, ll0, sc0, _ = oracle.population_run(b, n_threads=os.cpu_count() or 1)
+    assert np.array_equal(got["score"], sc0)
+    np.testing.assert_allclose(got["ll"], ll0, rtol=RTOL_TIGHT, atol=0)
+    for k in ("gl", "gof", "hap_like"):
+        np.testing.assert_allclose(got[k], want[k], rtol=RTOL_TIGHT, atol=1e-300, err_msg=k)
+    # sums over 300 individuals are reduced per thread: compare at the contract's tolerance
+    np.testing.assert_allclose(got["freq"], want["freq"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(got["em_post"], want["em_post"], rtol=RTOL, atol=1e-12)
+    assert np.array_equal(got["call"], want["call"])
+    assert np.abs(got["var_phred"] - want["var_phred"]).max() <= 1.0   # rounded phred of a 300-term log sum
+
+
 def test_long_haplotypes_and_reads(engine, oracle):
     """Realistic flanked haplotypes (~1 kb) and 250-400 bp reads: 16-bit vote counters,
     global-memory vote arrays, several haplotype groups per window."""
