@@ -737,6 +737,44 @@ __global__ void __launch_bounds__(128) k_general(DevBatch b, Queue q, ScoreParam
 // ---------------------------------------------------------------------------------------------
 // k_dp
 // ---------------------------------------------------------------------------------------------
+// ---- TMA (bulk async copy) + mbarrier wrappers: cp.async.bulk global -> shared, completion counted
+//      in bytes on an mbarrier.  SASS: UBLKCP / SYNCS. ----
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, u32 bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, u32 parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(
+            smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, u32 bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(smem_dst)),
+                 "l"(__cvta_generic_to_global(gmem_src)), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// words of one profile row in shared memory (same rule as the host planner)
+__device__ __forceinline__ int prof_row_words_dev(int L) {
+    int n = dp_steps(L) + 4;           // rows read by the kernel, +4 keeps rows 16-byte apart
+    n = (n + 3) & ~3;
+    if (!((n >> 2) & 1)) n += 4;       // odd multiple of 16 bytes: conflict-free LDS.128
+    return n;
+}
+constexpr int kTmaMaxLen = 192;   // rows up to this length are staged by TMA (raw bytes fit the row tail)
+__device__ __forceinline__ int tma_raw_bytes(int L) { return (L + 30 + 15) & ~15; }   // per array, 16-byte multiple
+
 struct DpPlan {
     const Tile* tiles;
     int32_t n_tiles;
@@ -767,8 +805,12 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
     int32_t* s_best = s_order + plan.max_slots;                  // per pair: best score
     u32* s_task = (u32*)(s_best + plan.max_pairs);               // compacted tasks
     __shared__ int s_ntask;
+    __shared__ __align__(8) uint64_t s_bar;   // counts the bytes of the tile's TMA copies
 
     const int tid = threadIdx.x;
+    if (tid == 0) mbar_init(&s_bar, NTHR);
+    u32 bar_phase = 0;
+    __syncthreads();
     for (int ti = blockIdx.x; ti < plan.n_tiles; ti += gridDim.x) {
         const Tile tile = plan.tiles[ti];
         const int w = tile.w;
@@ -820,11 +862,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                 int n = 0;
                 if (s < ns) {
                     const int L = s_slot[s].len;
-                    if (!(s_slot[s].flags & 1) && L >= kMinFastLen && L <= kMaxFastLen) {
-                        n = dp_steps(L) + 4;           // rows read by the kernel, +4 keeps rows 16-byte apart
-                        n = (n + 3) & ~3;
-                        if (!((n >> 2) & 1)) n += 4;   // odd multiple of 16 bytes: conflict-free LDS.128
-                    }
+                    if (!(s_slot[s].flags & 1) && L >= kMinFastLen && L <= kMaxFastLen) n = prof_row_words_dev(L);
                 }
                 int incl = n;
                 for (int o = 1; o < 32; o <<= 1) {
@@ -840,39 +878,29 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
         const int general = wflags & 1;
         const bool six = !(wflags & 2);   // no 'N' in the window's haplotypes: 6-op variant
         const int K = 2 * sp.ext + sp.nuc;
-        // profiles: one warp per read row, lanes along the read (coalesced byte loads)
-        if (!general) {
-            const int warp = tid >> 5, lane = tid & 31, nwarp = NTHR >> 5;
-            for (int s = warp; s < ns; s += nwarp) {
-                const DpSlot ds = s_slot[s];
-                if ((ds.flags & 1) || ds.len < kMinFastLen || ds.len > kMaxFastLen) continue;
-                const uint8_t* rs = b.read_seq + b.read_seq_off[ds.read];
-                const uint8_t* rq = b.read_qual + b.read_seq_off[ds.read];
-                int n = dp_steps(ds.len) + 4;
-                u32* row = s_prof + ds.poff;
-                for (int y0 = 0; y0 < n; y0 += 192) {   // 6 rows per lane, all loads issued before use
-                    uint8_t cb[6], qb[6];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        const int y = y0 + lane + 32 * k;
-                        cb[k] = y < ds.len ? rs[y] : (uint8_t)0;
-                        qb[k] = y < ds.len ? rq[y] : (uint8_t)0;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        const int y = y0 + lane + 32 * k;
-                        if (y < n) {
-                            u32 v = 0u;
-                            if (y < ds.len) {
-                                const int code = fast_code(cb[k]);
-                                v = six ? make_profile6(code, qb[k], K) : make_profile(code, qb[k]);
-                            }
-                            row[y] = v;
-                        }
-                    }
+        // ---- TMA: one bulk copy per read for bases and one for qualities, straight into the tail of
+        //      the read's profile row; every thread arrives on the mbarrier, copies add their bytes ----
+        {
+            bool issued = false;
+            if (!general && tid < ns) {
+                const DpSlot ds = s_slot[tid];
+                if (!(ds.flags & 1) && ds.len >= kMinFastLen && ds.len <= kTmaMaxLen) {
+                    const int64_t o = b.read_seq_off[ds.read];
+                    const int64_t a0 = o & ~(int64_t)15;
+                    const u32 nb = (u32)(((o + ds.len + 15) & ~(int64_t)15) - a0);   // <= tma_raw_bytes(len)
+                    uint8_t* row_end = (uint8_t*)(s_prof + ds.poff + prof_row_words_dev(ds.len));
+                    const int NB = tma_raw_bytes(ds.len);
+                    fence_proxy_async();   // the row was read through the generic proxy by the previous tile
+                    mbar_arrive_expect_tx(&s_bar, 2 * nb);
+                    tma_load_1d(row_end - 2 * NB, b.read_seq + a0, nb, &s_bar);
+                    tma_load_1d(row_end - NB, b.read_qual + a0, nb, &s_bar);
+                    issued = true;
                 }
             }
-            // haplotype records
+            if (!issued) mbar_arrive(&s_bar);
+        }
+        // haplotype records (while the read bytes are in flight)
+        if (!general) {
             for (int g = 0; g < nh; ++g) {
                 const int h = tile.h0 + g;
                 const int len = (int)(b.hap_seq_off[h + 1] - b.hap_seq_off[h]);
@@ -893,6 +921,70 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                         r.sel = make_sel(ca, cb);
                     }
                     rec[x] = r;
+                }
+            }
+        }
+        mbar_wait(&s_bar, bar_phase);
+        bar_phase ^= 1;
+        // profiles: one warp per read row, lanes along the read
+        if (!general) {
+            const int warp = tid >> 5, lane = tid & 31, nwarp = NTHR >> 5;
+            for (int s = warp; s < ns; s += nwarp) {
+                const DpSlot ds = s_slot[s];
+                if ((ds.flags & 1) || ds.len < kMinFastLen || ds.len > kMaxFastLen) continue;
+                const int64_t o = b.read_seq_off[ds.read];
+                int n = dp_steps(ds.len) + 4;
+                u32* row = s_prof + ds.poff;
+                if (ds.len <= kTmaMaxLen) {
+                    // raw bytes sit in the row's own tail: pull all of them into registers, then overwrite
+                    const uint8_t* row_end = (const uint8_t*)(row + prof_row_words_dev(ds.len));
+                    const int NB = tma_raw_bytes(ds.len);
+                    const uint8_t* rs = row_end - 2 * NB + (int)(o & 15);
+                    const uint8_t* rq = row_end - NB + (int)(o & 15);
+                    uint8_t cb[6], qb[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const int y = lane + 32 * k;
+                        cb[k] = y < ds.len ? rs[y] : (uint8_t)0;
+                        qb[k] = y < ds.len ? rq[y] : (uint8_t)0;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const int y = lane + 32 * k;
+                        if (y < n) {
+                            u32 v = 0u;
+                            if (y < ds.len) {
+                                const int code = fast_code(cb[k]);
+                                v = six ? make_profile6(code, qb[k], K) : make_profile(code, qb[k]);
+                            }
+                            row[y] = v;
+                        }
+                    }
+                    continue;
+                }
+                const uint8_t* rs = b.read_seq + o;
+                const uint8_t* rq = b.read_qual + o;
+                for (int y0 = 0; y0 < n; y0 += 192) {   // long reads: plain loads, 6 rows per lane
+                    uint8_t cb[6], qb[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const int y = y0 + lane + 32 * k;
+                        cb[k] = y < ds.len ? rs[y] : (uint8_t)0;
+                        qb[k] = y < ds.len ? rq[y] : (uint8_t)0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const int y = y0 + lane + 32 * k;
+                        if (y < n) {
+                            u32 v = 0u;
+                            if (y < ds.len) {
+                                const int code = fast_code(cb[k]);
+                                v = six ? make_profile6(code, qb[k], K) : make_profile(code, qb[k]);
+                            }
+                            row[y] = v;
+                        }
+                    }
                 }
             }
         }
