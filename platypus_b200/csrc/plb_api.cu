@@ -706,10 +706,8 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
         ap.cnt_words = (((max_hap + max_read + 2) >> 1) + 3) & ~3;
         const int nwarps = kAnchorThreads / 32;
         ap.n_cnt = (int)std::max<size_t>(1, std::min<size_t>(nwarps, kAnchorCntBudget / ((size_t)ap.cnt_words * 4)));
-        ch.a_smem = ((size_t)4 << ap.tab_bits) + (size_t)ap.n_cnt * ap.cnt_words * 4 + (size_t)ap.max_pairs * 16 +
-                    (size_t)(ap.rpk_words + ap.hpk_words) * 4 + (size_t)ap.next_halfs * 2 +
-                    (size_t)(ap.heads_halfs + ap.mult_halfs) * 2 + 16 + (size_t)ap.max_slots * sizeof(SlotInfo) +
-                    (size_t)ap.max_group * 12 + 16;
+        anchor_layout(ap, sizeof(SlotInfo));
+        ch.a_smem = ap.smem_bytes;
     }
     if (ch.a_smem + 1024 > (size_t)c->smem_optin)
         return set_err(PLB_ERR_SHAPE, "anchor tile needs %zu bytes of shared memory", ch.a_smem);

@@ -188,7 +188,26 @@ struct AnchorPlan {
     int32_t hpk_words;      // u32 words for the 2-bit packed haplotypes of a group
     int32_t cnt_words;      // u32 words of one warp's counter array (2 counters per word)
     int32_t n_cnt;          // counter arrays available in shared memory (>= 1)
+    // byte offsets of the shared-memory areas (laid out by the host planner, 16-byte aligned)
+    uint32_t o_cnt, o_fb, o_vl, o_rpk, o_hpk, o_next, o_mult, o_heads, o_slot, o_hmeta, smem_bytes;
 };
+
+// host + device: lays out the shared memory of k_anchor from the plan's element counts
+inline void anchor_layout(AnchorPlan& ap, size_t slot_bytes) {
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    size_t o = (size_t)4 << ap.tab_bits;
+    ap.o_cnt = (uint32_t)o;    o = al(o + (size_t)ap.n_cnt * ap.cnt_words * 4);
+    ap.o_fb = (uint32_t)o;     o = al(o + (size_t)ap.max_pairs * 4);
+    ap.o_vl = (uint32_t)o;     o = al(o + (size_t)ap.max_pairs * 12);
+    ap.o_rpk = (uint32_t)o;    o = al(o + (size_t)ap.rpk_words * 4);
+    ap.o_hpk = (uint32_t)o;    o = al(o + (size_t)ap.hpk_words * 4);
+    ap.o_next = (uint32_t)o;   o = al(o + (size_t)ap.next_halfs * 2);
+    ap.o_mult = (uint32_t)o;   o = al(o + (size_t)ap.mult_halfs * 2);
+    ap.o_heads = (uint32_t)o;  o = al(o + (size_t)ap.heads_halfs * 2);
+    ap.o_slot = (uint32_t)o;   o = al(o + (size_t)ap.max_slots * slot_bytes);
+    ap.o_hmeta = (uint32_t)o;  o = al(o + (size_t)ap.max_group * 12);
+    ap.smem_bytes = (uint32_t)o;
+}
 
 struct SlotInfo {
     int32_t read;     // read pool index
@@ -329,17 +348,19 @@ __device__ __noinline__ int light_decide(LightArgs a) {
 __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, AnchorPlan plan, Queue q, ScoreParams sp,
                                                            Counters* ctr) {
     extern __shared__ __align__(16) uint8_t smem[];
+    // areas at host-planned byte offsets (integer offsets keep every access a plain 32-bit shared
+    // address; generic-pointer arithmetic costs an S2R/LEA sequence per use)
     u32* s_tab = (u32*)smem;
-    u32* s_cnt = s_tab + (1 << plan.tab_bits);
-    u32* s_fblist = s_cnt + (size_t)plan.n_cnt * plan.cnt_words;
-    u32* s_vlist = s_fblist + plan.max_pairs;                 // per pair: up to three tied-maximum offsets
-    u32* s_rpk = s_vlist + 3 * (size_t)plan.max_pairs;        // 2-bit packed reads
-    u32* s_hpk = s_rpk + plan.rpk_words;                      // 2-bit packed haplotypes (padded both sides)
-    uint16_t* s_next = (uint16_t*)(s_hpk + plan.hpk_words);
-    uint16_t* s_mult = s_next + plan.next_halfs;              // per id: upper bound of its multiplicity in a haplotype
-    uint16_t* s_heads = s_mult + plan.mult_halfs;
-    SlotInfo* s_slot = (SlotInfo*)(((uintptr_t)(s_heads + plan.heads_halfs) + 15) & ~(uintptr_t)15);
-    int32_t* s_hmeta = (int32_t*)(s_slot + plan.max_slots);  // per hap: len, next offset, packed offset
+    u32* s_cnt = (u32*)(smem + plan.o_cnt);
+    u32* s_fblist = (u32*)(smem + plan.o_fb);
+    u32* s_vlist = (u32*)(smem + plan.o_vl);                  // per pair: up to three tied-maximum offsets
+    u32* s_rpk = (u32*)(smem + plan.o_rpk);                   // 2-bit packed reads
+    u32* s_hpk = (u32*)(smem + plan.o_hpk);                   // 2-bit packed haplotypes (padded both sides)
+    uint16_t* s_next = (uint16_t*)(smem + plan.o_next);
+    uint16_t* s_mult = (uint16_t*)(smem + plan.o_mult);       // per id: upper bound of its multiplicity in a haplotype
+    uint16_t* s_heads = (uint16_t*)(smem + plan.o_heads);
+    SlotInfo* s_slot = (SlotInfo*)(smem + plan.o_slot);
+    int32_t* s_hmeta = (int32_t*)(smem + plan.o_hmeta);      // per hap: len, next offset, packed offset
     __shared__ int s_nid, s_nfb, s_scan[kAnchorThreads / 32];
 
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
@@ -571,10 +592,10 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 ++st_scored;
                 st_cells += 16ull * si.len;
                 LightArgs la;
-                la.head_off = (u32)((uint8_t*)(s_heads + (g - g0) * hstride) - smem);
-                la.rpk_off = (u32)((uint8_t*)(s_rpk + si.poff) - smem);
-                la.hpk_off = (u32)((uint8_t*)(s_hpk + s_hmeta[3 * g + 2]) - smem);
-                la.res_off = (u32)((uint8_t*)(s_vlist + 3 * p) - smem);
+                la.head_off = plan.o_heads + 2u * (u32)((g - g0) * hstride);
+                la.rpk_off = plan.o_rpk + 4u * (u32)si.poff;
+                la.hpk_off = plan.o_hpk + 4u * (u32)s_hmeta[3 * g + 2];
+                la.res_off = plan.o_vl + 12u * (u32)p;
                 la.nk_read = si.len - kKmer;
                 la.nk_hap = s_hmeta[3 * g] - kKmer;
                 la.vub = si.vub;
