@@ -127,6 +127,22 @@ __device__ __forceinline__ uint8_t gap_open_at(const uint8_t* hap, int hap_len, 
     return c_homopol_q[run];
 }
 
+// compare-and-swap of one u16 element of a shared-memory array, through its containing 32-bit word
+// (native ATOMS.CAS; the library's 16-bit atomicCAS goes through a generic-address call)
+__device__ __forceinline__ unsigned short cas_u16(uint16_t* arr, int idx, unsigned short expect, unsigned short val) {
+    u32* word = (u32*)(arr + (idx & ~1));
+    const int sh = 16 * (idx & 1);
+    u32 cur = *(volatile u32*)word;
+    while (true) {
+        const unsigned short have = (unsigned short)(cur >> sh);
+        if (have != expect) return have;
+        const u32 want = (cur & ~(0xFFFFu << sh)) | ((u32)val << sh);
+        const u32 old = atomicCAS(word, cur, want);
+        if (old == cur) return expect;
+        cur = old;
+    }
+}
+
 __device__ __forceinline__ u32 tab_slot0(u32 key, int bits) {
     return bits >= 14 ? key : ((key * 0x9E3779B1u) >> (32 - bits));
 }
@@ -506,7 +522,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
         __syncthreads();
         const int U = s_nid;  // number of distinct 7-mers in this haplotype group
         const int general = b.win_flags[w] & 1;
-        const int hstride = U + 1;
+        const int hstride = (U + 2) & ~1;   // even: rows stay 4-byte aligned for the 32-bit CAS on u16 pairs
         const int sub_max = max(1, min(nh, plan.heads_halfs / hstride));
         for (int g0 = 0; g0 < nh; g0 += sub_max) {
             const int g1 = min(nh, g0 + sub_max);
@@ -519,7 +535,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 const int len = s_hmeta[3 * g];
                 const u32* hpk = s_hpk + s_hmeta[3 * g + 2];
                 uint16_t* nxt = s_next + s_hmeta[3 * g + 1];
-                unsigned short* head = (unsigned short*)(s_heads + (g - g0) * hstride);
+                uint16_t* head = s_heads + (g - g0) * hstride;
                 for (int i = tid; i < len - kKmer; i += nthr) {
                     const u32 id = tab_lookup(s_tab, bits, key_at(hpk, i));
                     unsigned short cur = head[id];
@@ -527,7 +543,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                         // bit 15 of the head marks chains with more than one element.
                         nxt[i + 1] = cur & 0x7FFFu;
                         const unsigned short nv = (unsigned short)((i + 1) | (cur ? 0x8000u : 0u));
-                        const unsigned short old = atomicCAS(&head[id], cur, nv);
+                        const unsigned short old = cas_u16(head, (int)id, cur, nv);
                         if (old == cur) break;
                         cur = old;
                     }
@@ -545,7 +561,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                     for (u32 p1 = hd & 0x7FFFu; p1; p1 = nxt[p1]) ++len;
                     unsigned short cur = s_mult[id];
                     while (cur < len) {
-                        const unsigned short old = atomicCAS((unsigned short*)&s_mult[id], cur, len);
+                        const unsigned short old = cas_u16(s_mult, id, cur, len);
                         if (old == cur) break;
                         cur = old;
                     }
