@@ -15,8 +15,13 @@ from htslibWrapper cimport cAlignedRead
 
 
 def map_and_align(bytes read, bytes quals, int read_start, int hap_start, bytes hap, bytes gap_open,
-                  int gap_extend=3, int nucprior=2, int hap_flank=1, int do_flank=0, int max_read_len=0):
-    """mapAndAlignReadToHaplotype (calign.pyx:170-272) for one (read, haplotype) pair."""
+                  int gap_extend=3, int nucprior=2, int hap_flank=1, int do_flank=0, int max_read_len=0,
+                  bytes hash_read=None):
+    """mapAndAlignReadToHaplotype (calign.pyx:170-272) for one (read, haplotype) pair.
+
+    hash_read: when given, read.hash is built from THIS sequence instead of `read` - that is
+    what alignReadToHaplotype does in HLA mode, where read/quals/readLen are clipped but
+    read.hash stays that of the whole read (chaplotype.pyx:637-638, 647-655)."""
     cdef int read_len = len(read)
     cdef int hap_len = len(hap)
     cdef short* hh = NULL
@@ -36,9 +41,18 @@ def map_and_align(bytes read, bytes quals, int read_start, int hap_start, bytes 
     n_counts = 2 * (hap_len + max_read_len)
     counts = <int*>malloc(n_counts * sizeof(int))
     calign.hash_sequence_multihit(c_hap, hap_len, &hh, &hn)
-    r.seq = c_read
+    cdef char* c_hash_read = c_read
+    cdef int hash_len = read_len
+    if hash_read is not None:
+        c_hash_read = hash_read
+        hash_len = len(hash_read)
+        if hash_len < read_len:
+            raise ValueError("hash_read shorter than read")
+    if hash_len > max_read_len:
+        max_read_len = hash_len
+    r.seq = c_hash_read
     r.qual = c_quals
-    r.rlen = read_len
+    r.rlen = hash_len
     r.hash = NULL
     calign.hashReadForMapping(&r)
     score = calign.mapAndAlignReadToHaplotype(c_read, c_quals, read_start, hap_start, read_len, hap_len,

@@ -39,6 +39,21 @@ def lib():
         L.plo_map_and_align.restype = C.c_int
         L.plo_score_to_ll.argtypes = [C.c_int, C.c_int]
         L.plo_score_to_ll.restype = C.c_double
+        L.plo_score_to_ll_hla.argtypes = [C.c_int, C.c_int]
+        L.plo_score_to_ll_hla.restype = C.c_double
+        L.plo_band_align_tb.argtypes = [u8, u8, u8, C.c_int, C.c_int, C.c_int, u8, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_int)]
+        L.plo_band_align_tb.restype = C.c_int
+        L.plo_flank_score.argtypes = [C.c_int, C.c_int, u8, u8, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
+        L.plo_flank_score.restype = C.c_int
+        L.plo_band_align_flank.argtypes = [u8, u8, u8, C.c_int, C.c_int, C.c_int, u8, C.c_int, C.c_int, C.c_int,
+                                           C.POINTER(C.c_int)]
+        L.plo_band_align_flank.restype = C.c_int
+        L.plo_map_and_align_ex.argtypes = [u8, u8, C.c_int, C.c_int, C.c_int, C.c_int, u8, u8, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, u8, C.c_int, C.POINTER(C.c_int)]
+        L.plo_map_and_align_ex.restype = C.c_int
+        L.plo_set_flank_fn.argtypes = [C.c_void_p]
+        L.plo_set_flank_fn.restype = None
         L.plo_overlap.argtypes = [C.c_int] * 4
         L.plo_overlap.restype = C.c_int
         L.plo_window_loglik.argtypes = [C.POINTER(_abi.PlbWindowBatch), C.POINTER(_abi.PlbOptions),
@@ -74,6 +89,9 @@ def ref_align_lib():
         R.fastAlignmentRoutine.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         R.fastAlignmentRoutine.restype = C.c_int
+        R.calculateFlankScore.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int,
+                                          C.c_char_p, C.c_char_p]
+        R.calculateFlankScore.restype = C.c_int
         _ref = R
     return _ref
 
@@ -91,17 +109,62 @@ def ref_fast_align(hap_seg: bytes, read: bytes, qual: bytes, gap_open: bytes, ex
     return R.fastAlignmentRoutine(hap_seg, read, qual, L + 15, L, ext, nuc, gap_open, None, None, C.byref(fp))
 
 
+def ref_fast_align_tb(hap_seg: bytes, read: bytes, qual: bytes, gap_open: bytes, ext=3, nuc=2):
+    """fastAlignmentRoutine of the reference with traceback: (score, aln1, aln2, firstpos)."""
+    R = ref_align_lib()
+    L = len(read)
+    assert len(hap_seg) >= L + 15 and len(gap_open) >= L + 15
+    fp = C.c_int(0)
+    a1 = C.create_string_buffer(2 * L + 16)
+    a2 = C.create_string_buffer(2 * L + 16)
+    s = R.fastAlignmentRoutine(hap_seg, read, qual, L + 15, L, ext, nuc, gap_open, a1, a2, C.byref(fp))
+    return s, a1.value, a2.value, fp.value
+
+
+def ref_flank_score(hap_len, hap_flank, qual: bytes, gap_open: bytes, firstpos, aln1: bytes, aln2: bytes, ext=3, nuc=2):
+    """calculateFlankScore of the reference (src/c/align.c:593)."""
+    return ref_align_lib().calculateFlankScore(hap_len, hap_flank, qual, gap_open, ext, nuc, firstpos, aln1, aln2)
+
+
+def band_align_tb(hap_seg: bytes, read: bytes, qual: bytes, gap_open: bytes, ext=3, nuc=2):
+    """Restated traceback: (score, aln1, aln2, firstpos)."""
+    L = len(read)
+    assert len(hap_seg) >= L + 15 and len(gap_open) >= L + 15
+    fp = C.c_int(0)
+    a1 = C.create_string_buffer(2 * L + 16)
+    a2 = C.create_string_buffer(2 * L + 16)
+    s = lib().plo_band_align_tb(hap_seg, read, qual, L, ext, nuc, gap_open, a1, a2, C.byref(fp))
+    return s, a1.value, a2.value, fp.value
+
+
+def flank_score(hap_len, hap_flank, qual: bytes, gap_open: bytes, firstpos, aln1: bytes, aln2: bytes, ext=3, nuc=2):
+    return lib().plo_flank_score(hap_len, hap_flank, qual, gap_open, ext, nuc, firstpos, aln1, aln2)
+
+
+def band_align_flank(hap: bytes, read: bytes, qual: bytes, gap_open: bytes, start, hap_flank, ext=3, nuc=2):
+    """One forward pass: (score, flank score of the traceback alignment).  hap / gap_open are the
+    WHOLE haplotype and its table; the band segment starts at `start`."""
+    L = len(read)
+    assert len(hap) >= start + L + 15
+    f = C.c_int(0)
+    s = lib().plo_band_align_flank(hap[start:], read, qual, L, ext, nuc, gap_open[start:], start, len(hap),
+                                   hap_flank, C.byref(f))
+    return s, f.value
+
+
 def use_reference_kernel(on=True, traceback=True):
     """Route every band alignment of the oracle through the reference's align.c
     (kind 'reference' CPU baseline).  Returns False when oracle/_ref is absent."""
     L = lib()
     if not on:
         L.plo_set_align_fn(None, 0)
+        L.plo_set_flank_fn(None)
         return True
     R = ref_align_lib()
     if R is None:
         return False
     L.plo_set_align_fn(C.cast(R.fastAlignmentRoutine, C.c_void_p), 1 if traceback else 0)
+    L.plo_set_flank_fn(C.cast(R.calculateFlankScore, C.c_void_p))
     return True
 
 
@@ -148,8 +211,22 @@ def map_and_align(read: bytes, qual: bytes, read_start: int, hap_start: int, hap
     return s, n.value
 
 
+def map_and_align_ex(read: bytes, qual: bytes, read_start: int, hap_start: int, hap: bytes, go: bytes = None,
+                     hap_flank=1, do_flank=0, hash_read: bytes = None, ext=3, nuc=2):
+    if go is None:
+        go = gap_open(hap)
+    n = C.c_int(0)
+    s = lib().plo_map_and_align_ex(read, qual, read_start, hap_start, len(read), len(hap), hap, go, ext, nuc,
+                                   hap_flank, do_flank, hash_read, len(hash_read) if hash_read else 0, C.byref(n))
+    return s, n.value
+
+
 def score_to_ll(score, mapq):
     return lib().plo_score_to_ll(score, mapq)
+
+
+def score_to_ll_hla(score, mapq):
+    return lib().plo_score_to_ll_hla(score, mapq)
 
 
 def window_loglik(batch, opt=None, n_threads=1, want_score=True):

@@ -84,6 +84,210 @@ int plo_band_align(const uint8_t* hap, const uint8_t* read, const uint8_t* qual,
     return best;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * L1 with traceback, src/c/align.c:344-365, 493-515 (back-pointers) and :523-577 (walk).
+ *
+ * With traceback on, every int16 value of the reference carries the label of its own state in
+ * its two low bits (M=0, I=1, D=3; scores are x4 so sums keep the label of the operand) and
+ * every `min` compares value AND label: equal scores resolve to the smaller label (M < I < D).
+ * The label that survives a cell's min is that state's back-pointer.  Restated here with
+ * key = 4*score + label.  The end cell is the first diagonal (ascending) holding the
+ * smallest key of the last read row (:261-288, 416-443 compare labelled values).
+ * Out-of-band / ramp-up values are "infinite" and never lie on the chosen path, so their
+ * garbage pointers are not reproduced.
+ * -----------------------------------------------------------------------------------------*/
+#define LBL_M 0
+#define LBL_I 1
+#define LBL_D 3
+#define KBIG ((int64_t)1 << 40)
+
+typedef struct { int64_t m, i, d; } Keys3;      /* 4*score + own label */
+
+static inline int64_t kmin(int64_t a, int64_t b) { return a < b ? a : b; }
+static inline int64_t relabel(int64_t k, int lbl) { return k >= KBIG ? KBIG + lbl : ((k >> 2) << 2) + lbl; }
+
+/* Computes the banded matrix keeping the three back-pointers of every cell in ptr[y*16+d]
+ * (bits 0-1 M, 2-3 I, 6-7 D, as align.c:346-348 packs them).  Returns the end diagonal, the
+ * state to start the walk in and the score. */
+static int band_forward_tb(const uint8_t* hap, const uint8_t* read, const uint8_t* qual, int L, int ext, int nuc,
+                           const uint8_t* open, uint8_t* ptr, int* end_diag, int* end_state) {
+    Keys3 prev[BAND], cur[BAND];
+    for (int y = 0; y < L; ++y) {
+        for (int d = 0; d < BAND; ++d) {
+            int x = y + d;
+            int sub = (hap[x] == 'N' || hap[x] == read[y]) ? 0 : (int)qual[y];
+            int64_t diag = (y == 0) ? (int64_t)LBL_M : kmin(prev[d].m, kmin(prev[d].i, prev[d].d));
+            int pm = (int)(diag & 3);
+            int64_t m = diag >= KBIG ? KBIG : diag + 4 * sub;
+            int64_t ins;
+            if (y == 0) ins = (x % 2 == 0) ? (int64_t)LBL_M + 4 * ((int)open[x] + nuc) : KBIG;
+            else if (d + 1 < BAND) {
+                int64_t a = prev[d + 1].i >= KBIG ? KBIG : prev[d + 1].i + 4 * ext;
+                int64_t bq = prev[d + 1].m >= KBIG ? KBIG : prev[d + 1].m + 4 * (int)open[x];
+                ins = kmin(a, bq);
+                if (ins < KBIG) ins += 4 * nuc;
+            } else ins = KBIG;
+            int pi = (int)(ins & 3);
+            int64_t del;
+            if (d >= 1) {
+                int64_t a = cur[d - 1].d >= KBIG ? KBIG : cur[d - 1].d + 4 * ext;
+                int64_t mi = kmin(cur[d - 1].m, cur[d - 1].i);
+                int64_t bq = mi >= KBIG ? KBIG : mi + 4 * (int)open[x];
+                del = kmin(a, bq);
+            } else del = KBIG;
+            int pd = (int)(del & 3);
+            ptr[y * BAND + d] = (uint8_t)(pm | (pi << 2) | (pd << 6));
+            cur[d].m = relabel(m, LBL_M);
+            cur[d].i = relabel(ins, LBL_I);
+            cur[d].d = relabel(del, LBL_D);
+        }
+        memcpy(prev, cur, sizeof prev);
+    }
+    int64_t best = KBIG + 8;
+    int bd = 0;
+    for (int d = 0; d < BAND; ++d) {
+        int64_t k = kmin(prev[d].m, kmin(prev[d].i, prev[d].d));
+        if (k < best) { best = k; bd = d; }
+    }
+    *end_diag = bd;
+    *end_state = (int)(best & 3);
+    return (int)(best >> 2);
+}
+
+int plo_band_align_tb(const uint8_t* hap, const uint8_t* read, const uint8_t* qual, int L, int ext, int nuc,
+                      const uint8_t* open, char* aln1, char* aln2, int* firstpos) {
+    uint8_t* ptr = (uint8_t*)malloc((size_t)L * BAND + 1);
+    int ed = 0, state = 0;
+    int score = band_forward_tb(hap, read, qual, L, ext, nuc, open, ptr, &ed, &state);
+    /* walk, align.c:523-577: (cx, cy) is the cell whose symbol pair is emitted next */
+    int cx = L - 1 + ed, cy = L - 1, n = 0;
+    while (cy >= 0) {
+        int d = cx - cy;
+        uint8_t p = (d >= 0 && d < BAND) ? ptr[cy * BAND + d] : 0;
+        int newstate = (p >> (2 * state)) & 3;
+        if (state == LBL_M) { aln1[n] = (char)hap[cx]; aln2[n] = (char)read[cy]; --cx; --cy; }
+        else if (state == LBL_I) { aln1[n] = '-'; aln2[n] = (char)read[cy]; --cy; }
+        else { aln1[n] = (char)hap[cx]; aln2[n] = '-'; --cx; }
+        state = newstate;
+        ++n;
+    }
+    aln1[n] = 0;
+    aln2[n] = 0;
+    if (firstpos) *firstpos = cx + 1;
+    for (int i = 0, j = n - 1; i < j; ++i, --j) { /* :561-571 */
+        char t = aln1[i]; aln1[i] = aln1[j]; aln1[j] = t;
+        t = aln2[i]; aln2[i] = aln2[j]; aln2[j] = t;
+    }
+    free(ptr);
+    return score;
+}
+
+/* src/c/align.c:593-644 calculateFlankScore: cost of the alignment columns whose haplotype
+ * coordinate lies in a flank (x < hapFlank or x >= hapLen - hapFlank). */
+int plo_flank_score(int hap_len, int hap_flank, const uint8_t* qual, const uint8_t* gap_open, int ext, int nuc,
+                    int firstpos, const char* aln1, const char* aln2) {
+    char prev = 'M';
+    int x = firstpos, y = 0, score = 0;
+    for (int i = 0; aln1[i]; ++i) {
+        char st = 'M';
+        if (aln1[i] == '-') st = 'I';
+        if (aln2[i] == '-') st = 'D';
+        int in_flank = (x < hap_flank || x >= hap_len - hap_flank);
+        if (st == 'M') {
+            if (aln1[i] != aln2[i] && in_flank) score += (aln1[i] == 'N') ? 0 : (int)qual[y]; /* n_score/4 = 0 */
+            ++x; ++y;
+        } else if (st == 'I') {
+            if (in_flank) score += (prev == 'I') ? ext + nuc : (int)gap_open[x - 1] + nuc;
+            ++y;
+        } else {
+            if (in_flank) score += (prev == 'D') ? ext : (int)gap_open[x];
+            ++x;
+        }
+        prev = st;
+    }
+    return score;
+}
+
+/* The same two steps fused into one forward pass (what the CUDA path computes): every state
+ * carries, next to its key, the in-flank cost of the path its back-pointers describe.  `start`
+ * is the offset of the segment in the haplotype, so column x of the band is haplotype
+ * position start + x.  An insertion at cell (x, y) is charged at haplotype position x + 1
+ * (align.c:621-631: x has already moved past the preceding match).
+ * Returns the score; *flank receives calculateFlankScore of the traceback alignment. */
+int plo_band_align_flank(const uint8_t* hap, const uint8_t* read, const uint8_t* qual, int L, int ext, int nuc,
+                         const uint8_t* open, int start, int hap_len, int hap_flank, int* flank) {
+    Keys3 prev[BAND], cur[BAND];
+    int fpm[BAND], fpi[BAND], fpd[BAND], fcm[BAND], fci[BAND], fcd[BAND];
+    for (int y = 0; y < L; ++y) {
+        for (int d = 0; d < BAND; ++d) {
+            int x = y + d;
+            int hx = start + x;
+            int in_x = (hx < hap_flank || hx >= hap_len - hap_flank);
+            int in_x1 = (hx + 1 < hap_flank || hx + 1 >= hap_len - hap_flank);
+            int sub = (hap[x] == 'N' || hap[x] == read[y]) ? 0 : (int)qual[y];
+            /* M */
+            int64_t diag;
+            int fdiag;
+            if (y == 0) { diag = LBL_M; fdiag = 0; }
+            else {
+                diag = prev[d].m; fdiag = fpm[d];
+                if (prev[d].i < diag) { diag = prev[d].i; fdiag = fpi[d]; }
+                if (prev[d].d < diag) { diag = prev[d].d; fdiag = fpd[d]; }
+            }
+            int64_t m = diag >= KBIG ? KBIG : diag + 4 * sub;
+            fcm[d] = fdiag + (in_x ? sub : 0);
+            /* I */
+            int64_t ins;
+            int fins = 0;
+            if (y == 0) {
+                if (x % 2 == 0) { ins = (int64_t)LBL_M + 4 * ((int)open[x] + nuc); fins = in_x1 ? (int)open[x] + nuc : 0; }
+                else ins = KBIG;
+            } else if (d + 1 < BAND) {
+                int64_t a = prev[d + 1].i >= KBIG ? KBIG : prev[d + 1].i + 4 * ext;
+                int64_t bq = prev[d + 1].m >= KBIG ? KBIG : prev[d + 1].m + 4 * (int)open[x];
+                if (bq <= a) { ins = bq; fins = fpm[d + 1] + (in_x1 ? (int)open[x] + nuc : 0); }   /* label M(0) < I(1) */
+                else { ins = a; fins = fpi[d + 1] + (in_x1 ? ext + nuc : 0); }
+                if (ins < KBIG) ins += 4 * nuc;
+            } else ins = KBIG;
+            fci[d] = fins;
+            /* D */
+            int64_t del;
+            int fdel = 0;
+            if (d >= 1) {
+                int64_t a = cur[d - 1].d >= KBIG ? KBIG : cur[d - 1].d + 4 * ext;
+                int64_t mi = cur[d - 1].m;
+                int fmi = fcm[d - 1];
+                if (cur[d - 1].i < mi) { mi = cur[d - 1].i; fmi = fci[d - 1]; }
+                int64_t bq = mi >= KBIG ? KBIG : mi + 4 * (int)open[x];
+                if (bq <= a) { del = bq; fdel = fmi + (in_x ? (int)open[x] : 0); }
+                else { del = a; fdel = fcd[d - 1] + (in_x ? ext : 0); }
+            } else del = KBIG;
+            fcd[d] = fdel;
+            cur[d].m = relabel(m, LBL_M);
+            cur[d].i = relabel(ins, LBL_I);
+            cur[d].d = relabel(del, LBL_D);
+        }
+        memcpy(prev, cur, sizeof prev);
+        memcpy(fpm, fcm, sizeof fpm);
+        memcpy(fpi, fci, sizeof fpi);
+        memcpy(fpd, fcd, sizeof fpd);
+    }
+    int64_t best = KBIG + 8;
+    int bf = 0;
+    for (int d = 0; d < BAND; ++d) {
+        int64_t k = prev[d].m;
+        int f = fpm[d];
+        if (prev[d].i < k) { k = prev[d].i; f = fpi[d]; }
+        if (prev[d].d < k) { k = prev[d].d; f = fpd[d]; }
+        if (k < best) { best = k; bf = f; }
+    }
+    if (flank) *flank = bf;
+    return (int)(best >> 2);
+}
+
+static plo_flank_fn g_flank_fn = 0;
+void plo_set_flank_fn(plo_flank_fn fn) { g_flank_fn = fn; }
+
 static int do_align(const uint8_t* hap_seg, const uint8_t* read, const uint8_t* qual, int read_len,
                     int ext, int nuc, const uint8_t* open, char* aln1, char* aln2) {
     if (g_align_fn) {
@@ -93,6 +297,27 @@ static int do_align(const uint8_t* hap_seg, const uint8_t* read, const uint8_t* 
                           g_align_traceback ? aln1 : 0, g_align_traceback ? aln2 : 0, &firstpos);
     }
     return plo_band_align(hap_seg, read, qual, read_len, ext, nuc, open);
+}
+
+/* One band alignment as calign.pyx:232-237 / 258-263 run it with doCalculateFlankScore = 1:
+ * traceback, then the flank cost is taken off a positive score. */
+static int do_align_flank(const uint8_t* hap, const uint8_t* gap_open, int hap_len, int hap_flank, int start,
+                          const uint8_t* read, const uint8_t* qual, int read_len, int ext, int nuc,
+                          char* aln1, char* aln2) {
+    int firstpos = 0, s;
+    if (g_align_fn)
+        s = g_align_fn((const char*)hap + start, (const char*)read, (const char*)qual, read_len + 15, read_len, ext,
+                       nuc, (const char*)gap_open + start, aln1, aln2, &firstpos);
+    else
+        s = plo_band_align_tb(hap + start, read, qual, read_len, ext, nuc, gap_open + start, aln1, aln2, &firstpos);
+    if (s > 0) {
+        if (g_flank_fn)
+            s -= g_flank_fn(hap_len, hap_flank, (const char*)qual, (const char*)gap_open, ext, nuc, firstpos + start,
+                            aln1, aln2);
+        else
+            s -= plo_flank_score(hap_len, hap_flank, qual, gap_open, ext, nuc, firstpos + start, aln1, aln2);
+    }
+    return s;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -181,7 +406,7 @@ static void read_hashes(const uint8_t* read, int read_len, int16_t* out) {
 static int map_and_align(const uint8_t* read, const uint8_t* qual, const int16_t* rhash, int read_start,
                          int hap_start, int read_len, int hap_len, const uint8_t* hap,
                          const HapIndex* ix, const uint8_t* gap_open, int ext, int nuc, int* counts,
-                         char* aln1, char* aln2, int* n_dp) {
+                         char* aln1, char* aln2, int* n_dp, int hap_flank, int do_flank) {
     if (n_dp) *n_dp = 0;
     if (read_len < KMER) return 0; /* :182-183 */
     int maxcount = 0;
@@ -204,7 +429,10 @@ static int map_and_align(const uint8_t* read, const uint8_t* qual, const int16_t
             int idx = i - read_len;
             if (idx >= -read_len && idx + read_len + 15 < hap_len) {
                 int start = imax(0, idx - 8);
-                int s = do_align(hap + start, read, qual, read_len, ext, nuc, gap_open + start, aln1, aln2);
+                /* :236-238: the flank cost comes off when doCalculateFlankScore and hapFlank > 0 */
+                int s = (do_flank && hap_flank > 0)
+                            ? do_align_flank(hap, gap_open, hap_len, hap_flank, start, read, qual, read_len, ext, nuc, aln1, aln2)
+                            : do_align(hap + start, read, qual, read_len, ext, nuc, gap_open + start, aln1, aln2);
                 if (n_dp) ++*n_dp;
                 if (s < best) {
                     best = s;
@@ -218,32 +446,41 @@ static int map_and_align(const uint8_t* read, const uint8_t* qual, const int16_t
     int idx0 = imin(read_start - hap_start, hap_len - read_len - 15);
     if (idx0 != best_pos) {
         int start = imax(0, idx0 - 8);
-        int s = do_align(hap + start, read, qual, read_len, ext, nuc, gap_open + start, aln1, aln2);
+        /* :262-264 tests hapLen > 0 here (not hapFlank); with hapFlank <= 0 the reference has no
+         * traceback buffers and would dereference NULL, so callers must pass hap_flank > 0 */
+        int s = do_flank ? do_align_flank(hap, gap_open, hap_len, hap_flank, start, read, qual, read_len, ext, nuc, aln1, aln2)
+                         : do_align(hap + start, read, qual, read_len, ext, nuc, gap_open + start, aln1, aln2);
         if (n_dp) ++*n_dp;
         if (s < best) best = s;
     }
     return best;
 }
 
-int plo_map_and_align(const uint8_t* read, const uint8_t* qual, int read_start, int hap_start,
-                      int read_len, int hap_len, const uint8_t* hap, const uint8_t* gap_open,
-                      int ext, int nuc, int* n_dp) {
+/* hash_read (may be NULL = read): the sequence whose 7-mer hashes vote.  In HLA mode the
+ * reference clips read/quals/readLen but keeps read.hash of the UNCLIPPED read
+ * (chaplotype.pyx:637-638, 647-655), so 7-mer i of the unclipped read votes as if it were
+ * 7-mer i of the clipped one. */
+int plo_map_and_align_ex(const uint8_t* read, const uint8_t* qual, int read_start, int hap_start,
+                         int read_len, int hap_len, const uint8_t* hap, const uint8_t* gap_open,
+                         int ext, int nuc, int hap_flank, int do_flank, const uint8_t* hash_read,
+                         int hash_read_len, int* n_dp) {
     if (read_len < KMER) {
         if (n_dp) *n_dp = 0;
         return 0;
     }
+    if (!hash_read) { hash_read = read; hash_read_len = read_len; }
     HapIndex ix;
     ix.head = (int16_t*)malloc(HASH_SIZE * sizeof(int16_t));
     ix.next = 0;
     ix.cap_next = 0;
     hap_index_build(&ix, hap, hap_len);
-    int16_t* rh = (int16_t*)malloc((size_t)(read_len + 1) * sizeof(int16_t));
-    read_hashes(read, read_len, rh);
+    int16_t* rh = (int16_t*)malloc((size_t)(hash_read_len + 1) * sizeof(int16_t));
+    read_hashes(hash_read, hash_read_len, rh);
     int* counts = (int*)malloc((size_t)(hap_len + read_len + 1) * sizeof(int));
     char* aln1 = (char*)malloc((size_t)(2 * read_len + 16));
     char* aln2 = (char*)malloc((size_t)(2 * read_len + 16));
     int s = map_and_align(read, qual, rh, read_start, hap_start, read_len, hap_len, hap, &ix, gap_open, ext,
-                          nuc, counts, aln1, aln2, n_dp);
+                          nuc, counts, aln1, aln2, n_dp, hap_flank, do_flank);
     free(aln1);
     free(aln2);
     free(counts);
@@ -253,12 +490,34 @@ int plo_map_and_align(const uint8_t* read, const uint8_t* qual, int read_start, 
     return s;
 }
 
+int plo_map_and_align(const uint8_t* read, const uint8_t* qual, int read_start, int hap_start,
+                      int read_len, int hap_len, const uint8_t* hap, const uint8_t* gap_open,
+                      int ext, int nuc, int* n_dp) {
+    return plo_map_and_align_ex(read, qual, read_start, hap_start, read_len, hap_len, hap, gap_open, ext, nuc,
+                                1, 0, 0, 0, n_dp);
+}
+
 /* src/cython/chaplotype.pyx:621-622, 634, 675-676 (useMapQualCap = 0):
  * LL = max(-300, mLTOT*score + log(1 - exp(mLTOT*mapq))). */
 double plo_score_to_ll(int score, int mapq) {
     double right = log(1.0 - exp(M_LTOT * (double)mapq));
     double v = M_LTOT * (double)score + right;
     return v > PLB_LL_CAP ? v : PLB_LL_CAP; /* NaN cannot occur: score, mapq finite */
+}
+
+/* src/cython/chaplotype.pyx:621-634, 664-676 with useMapQualCap = 1 (--HLATyping): the cap is
+ * the log-probability of a wrong mapping, and scores above 100 are flattened smoothly:
+ * mLTOT * (99 + (score - 99)^0.5 / 0.5). */
+double plo_score_to_ll_hla(int score, int mapq) {
+    double cap = M_LTOT * (double)mapq;
+    double right = log(1.0 - exp(M_LTOT * (double)mapq));
+    const double threshold = 100.0, shape = 0.5;
+    double v;
+    if ((double)score > threshold)
+        v = M_LTOT * (threshold - 1.0 + pow((double)score - threshold + 1.0, shape) / shape);
+    else
+        v = M_LTOT * (double)score + right;
+    return v > cap ? v : cap; /* Python max(cap, v): v only when strictly greater (-inf loses) */
 }
 
 /* src/cython/chaplotype.pyx:103-115 */
@@ -273,7 +532,8 @@ int plo_overlap(int hap_start, int hap_end, int read_pos, int read_end) {
  * -----------------------------------------------------------------------------------------*/
 static int check_opts(const PlbOptions* opt) {
     if (!opt) return PLB_ERR_ARG;
-    if (opt->use_mapq_cap || opt->calc_flank_score) return PLB_ERR_UNSUPPORTED;
+    if (opt->use_mapq_cap != 0 && opt->use_mapq_cap != 1) return PLB_ERR_ARG;
+    if (opt->calc_flank_score != 0 && opt->calc_flank_score != 1) return PLB_ERR_ARG;
     return PLB_OK;
 }
 
@@ -382,13 +642,31 @@ int plo_window_loglik(const PlbWindowBatch* b, const PlbOptions* opt, PlbLoglikO
                         const uint8_t* rs = b->read_seq + b->read_seq_off[r];
                         const uint8_t* rq = b->read_qual + b->read_seq_off[r];
                         int ndp = 0;
-                        int sc = map_and_align(rs, rq, rh + rh_off[s0 + t - ws0], b->read_pos[r], b->hap_start[w], rlen,
+                        int read_start = b->read_pos[r];
+                        /* hapFlank = hap.endBufferSize = startPos - hapStart (chaplotype.pyx:604, 609) */
+                        int hap_flank = b->win_start[w] - b->hap_start[w];
+                        if (opt->use_mapq_cap) { /* chaplotype.pyx:647-655: clip the read to the haplotype */
+                            int off1 = b->hap_start[w] - read_start;
+                            int off2 = read_start + rlen - b->win_start[w] - hap_len; /* sic: startPos, not hapStart */
+                            if (off1 < 0) off1 = 0;
+                            if (off2 < 0) off2 = 0;
+                            read_start += off1;
+                            rlen -= off1 + off2;
+                            rs += off1;
+                            rq += off1;
+                        }
+                        if (rlen >= KMER && hap_len < rlen + 15) { err = PLB_ERR_SHAPE; continue; }
+                        if (opt->calc_flank_score && hap_flank <= 0) { err = PLB_ERR_ARG; continue; }
+                        /* the 7-mer hashes stay those of the unclipped read (read.hash, :637-638) */
+                        int sc = map_and_align(rs, rq, rh + rh_off[s0 + t - ws0], read_start, b->hap_start[w], rlen,
                                                hap_len, hap, &ix, go, opt->gap_extend, opt->nuc_prior, counts, aln1,
-                                               aln2, &ndp);
+                                               aln2, &ndp, hap_flank, opt->calc_flank_score);
                         ++tot_scored;
                         tot_dp += ndp;
-                        tot_cells += 16 * (int64_t)rlen;
-                        if (out->ll) out->ll[base + t] = plo_score_to_ll(sc, b->read_mapq[r]);
+                        tot_cells += 16 * (int64_t)(rlen > 0 ? rlen : 0);
+                        if (out->ll)
+                            out->ll[base + t] = opt->use_mapq_cap ? plo_score_to_ll_hla(sc, b->read_mapq[r])
+                                                                  : plo_score_to_ll(sc, b->read_mapq[r]);
                         if (out->score) out->score[base + t] = sc;
                     }
                 }

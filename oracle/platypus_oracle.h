@@ -39,6 +39,27 @@ void plo_set_align_fn(plo_align_fn fn, int traceback);
 int plo_band_align(const uint8_t* hap_seg, const uint8_t* read, const uint8_t* qual, int read_len,
                    int gap_extend, int nuc_prior, const uint8_t* gap_open);
 
+/* L1 with traceback (src/c/align.c:344-365, 493-577): aln1/aln2 receive the NUL-terminated
+ * alignment rows (2*read_len+16 bytes each), *firstpos the segment column of the first row. */
+int plo_band_align_tb(const uint8_t* hap_seg, const uint8_t* read, const uint8_t* qual, int read_len,
+                      int gap_extend, int nuc_prior, const uint8_t* gap_open, char* aln1, char* aln2,
+                      int* firstpos);
+
+/* src/c/align.c:593-644 calculateFlankScore. */
+int plo_flank_score(int hap_len, int hap_flank, const uint8_t* qual, const uint8_t* gap_open, int gap_extend,
+                    int nuc_prior, int firstpos, const char* aln1, const char* aln2);
+typedef int (*plo_flank_fn)(int hapLen, int hapFlank, const char* quals, const char* localgapopen, int gapextend,
+                            int nucprior, int firstpos, const char* aln1, const char* aln2);
+/* Use the reference's own calculateFlankScore (oracle/_ref/libalign_ref.so); NULL restores ours. */
+void plo_set_flank_fn(plo_flank_fn fn);
+
+/* Traceback + flank score in ONE forward pass (the formulation the CUDA path uses): returns the
+ * score, *flank = calculateFlankScore of the alignment the traceback would have produced.
+ * `start` = offset of hap_seg inside the haplotype (gap_open is the segment's table). */
+int plo_band_align_flank(const uint8_t* hap_seg, const uint8_t* read, const uint8_t* qual, int read_len,
+                         int gap_extend, int nuc_prior, const uint8_t* gap_open, int start, int hap_len,
+                         int hap_flank, int* flank);
+
 /* src/cython/chaplotype.pyx:64-67, 552-590: out[hap_len+1]. */
 void plo_gap_open(const uint8_t* hap, int hap_len, uint8_t* out);
 
@@ -51,8 +72,18 @@ int plo_map_and_align(const uint8_t* read, const uint8_t* qual, int read_start, 
                       int read_len, int hap_len, const uint8_t* hap, const uint8_t* gap_open,
                       int gap_extend, int nuc_prior, int* n_dp);
 
+/* L2 with the two run-time modes: hap_flank / do_flank = hapFlank / doCalculateFlankScore of
+ * calign.pyx:170; hash_read = sequence whose 7-mers vote (NULL = read; HLA mode passes the
+ * unclipped read, chaplotype.pyx:637-655). */
+int plo_map_and_align_ex(const uint8_t* read, const uint8_t* qual, int read_start, int hap_start,
+                         int read_len, int hap_len, const uint8_t* hap, const uint8_t* gap_open,
+                         int gap_extend, int nuc_prior, int hap_flank, int do_flank,
+                         const uint8_t* hash_read, int hash_read_len, int* n_dp);
+
 /* src/cython/chaplotype.pyx:621-676, default mode (useMapQualCap = 0). */
 double plo_score_to_ll(int score, int mapq);
+/* same, useMapQualCap = 1 (--HLATyping=1): cap = mLTOT*mapq, smooth flattening above score 100. */
+double plo_score_to_ll_hla(int score, int mapq);
 
 /* src/cython/chaplotype.pyx:103-115 */
 int plo_overlap(int hap_start, int hap_end, int read_pos, int read_end);

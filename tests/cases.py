@@ -103,7 +103,7 @@ def random_mapping_case(rng, i):
     return hap, read, qual, hap_start + idx + jit, hap_start
 
 
-def edge_batch(seed=5, n_windows=12, n_individuals=3):
+def edge_batch(seed=5, n_windows=12, n_individuals=3, overhang=False):
     """Small multi-individual batch exercising the edge cases the reference's logic has:
     N / IUPAC bytes, zeroed qualities, QC-fail, overlap < 7, mapq 0, exact matches, tandem repeats,
     reads shorter than 7 / 9, ragged lengths, individuals without reads, bad + broken-mate reads,
@@ -165,6 +165,17 @@ def edge_batch(seed=5, n_windows=12, n_individuals=3):
                     seq = mutate(rng, src[idx:], L)
                 qual = bytes(0 if rng.random() < 0.1 else rng.randint(2, 41) for _ in range(L))
                 pos = hap_start + idx + rng.choice([0, 0, 0, rng.randint(-5, 5), rng.randint(-60, 60)])
+                if overhang and rng.random() < 0.35:
+                    # reads hanging over either end of the haplotype: HLA mode clips them
+                    # (chaplotype.pyx:647-655; the right-hand clip is measured from startPos + hapLen)
+                    if rng.random() < 0.5:
+                        k = rng.randint(1, min(25, L - 1))
+                        seq = _rand_seq(rng, k) + mutate(rng, src, L - k)
+                        pos = hap_start - k
+                    else:
+                        k = rng.randint(1, min(25, L - 1))
+                        pos = hap_start + flank + hap_len - L + k
+                        seq = mutate(rng, src[max(0, hap_len - L):], L)
                 mapq = rng.choice([60, 60, 60, 37, 20, 3, 0])
                 r = Read(seq, qual, pos, pos + L, mapq, qcfail=(rng.random() < 0.08))
                 which = 0 if rng.random() < 0.7 else rng.choice([1, 2])

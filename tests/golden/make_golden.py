@@ -7,6 +7,13 @@ Generates the golden fixtures in this directory.  Run in the BUILD container, wh
   calign_ref.npz  inputs + scores from the reference's src/cython/calign.pyx
                   mapAndAlignReadToHaplotype (oracle/_ref/calign*.so), gap-open tables from the
                   oracle's restatement of chaplotype.pyx:552-590
+  align_tb_ref.npz   inputs + traceback rows / firstpos of fastAlignmentRoutine and
+                  calculateFlankScore values (src/c/align.c:523-644) from the same library
+  calign_modes_ref.npz  mapAndAlignReadToHaplotype with doCalculateFlankScore = 1 and with
+                  HLA-style clipped reads whose hashes stay those of the unclipped read
+                  (chaplotype.pyx:637-655), from the reference's calign.pyx
+  window_modes_restated.npz  the edge batch under --calculateFlankScore=1 / --HLATyping=1 from the
+                  oracle (restated above the integer score)
   window_restated.npz  a small multi-individual batch with per-read LL, GL, EM frequencies and
                   posteriors from the oracle (restatement of chaplotype/cgenotype/cpopulation:
                   "parity unpinned" above the integer score, see oracle/platypus_oracle.h)
@@ -80,6 +87,78 @@ def make_calign(n=500, seed=12):
     print("calign_ref.npz:", n, "cases;", sum(1 for s in scores if s == 1000000), "sentinel")
 
 
+def make_align_tb(n=400, seed=21):
+    assert O.ref_align_lib() is not None
+    rng = random.Random(seed)
+    haps, gos, reads, quals = [], [], [], []
+    scores, a1s, a2s, fps, flanks, hflank = [], [], [], [], [], []
+    for i in range(n):
+        hap, go, read, qual = cases.random_alignment_case(rng, i)
+        s, a1, a2, fp = O.ref_fast_align_tb(hap, read, qual, go)
+        fl = rng.randint(1, max(1, len(hap) // 2))
+        f = O.ref_flank_score(len(hap), fl, qual, go, fp, a1, a2)
+        haps.append(hap); gos.append(go[:len(hap)]); reads.append(read); quals.append(qual)
+        scores.append(s); a1s.append(a1); a2s.append(a2); fps.append(fp); flanks.append(f); hflank.append(fl)
+    ho, hs = pack(haps)
+    _, gs = pack(gos)
+    ro, rs = pack(reads)
+    _, qs = pack(quals)
+    ao, a1 = pack(a1s)
+    _, a2 = pack(a2s)
+    np.savez_compressed(os.path.join(HERE, "align_tb_ref.npz"), hap_off=ho, hap=hs, gap_open=gs, read_off=ro, read=rs,
+                        qual=qs, score=np.array(scores, np.int32), aln_off=ao, aln1=a1, aln2=a2,
+                        firstpos=np.array(fps, np.int32), hap_flank=np.array(hflank, np.int32),
+                        flank_score=np.array(flanks, np.int32))
+    print("align_tb_ref.npz:", n, "cases,", sum(1 for f in flanks if f), "with a nonzero flank score")
+
+
+def make_calign_modes(n=400, seed=22):
+    cw = O.ref_calign()
+    assert cw is not None
+    rng = random.Random(seed)
+    haps, reads, quals, hreads = [], [], [], []
+    rstart, hstart, hflank, doflank, scores = [], [], [], [], []
+    for i in range(n):
+        hap, read, qual, read_start, hap_start = cases.random_mapping_case(rng, i)
+        go = O.gap_open(hap)
+        fl = rng.randint(1, max(1, len(hap) // 2))
+        do = 0 if i % 4 == 3 else 1
+        hread = read
+        if i % 2 == 1 and len(read) > 30:   # HLA-style clip; votes still come from the whole read
+            off1 = rng.choice([0, 1, 3, 10]); off2 = rng.choice([0, 2, 7])
+            read, qual, read_start = read[off1:len(read) - off2], qual[off1:len(qual) - off2], read_start + off1
+        s = cw.map_and_align(read, qual, read_start, hap_start, hap, go, 3, 2, fl, do, 0, hread)
+        haps.append(hap); reads.append(read); quals.append(qual); hreads.append(hread)
+        rstart.append(read_start); hstart.append(hap_start); hflank.append(fl); doflank.append(do); scores.append(s)
+    ho, hs = pack(haps)
+    ro, rs = pack(reads)
+    _, qs = pack(quals)
+    uo, us = pack(hreads)
+    np.savez_compressed(os.path.join(HERE, "calign_modes_ref.npz"), hap_off=ho, hap=hs, read_off=ro, read=rs, qual=qs,
+                        hash_read_off=uo, hash_read=us, read_start=np.array(rstart, np.int32),
+                        hap_start=np.array(hstart, np.int32), hap_flank=np.array(hflank, np.int32),
+                        do_flank=np.array(doflank, np.int32), score=np.array(scores, np.int32))
+    print("calign_modes_ref.npz:", n, "cases")
+
+
+def make_window_modes():
+    from platypus_b200 import _abi
+    out = {}
+    for name, kw in (("flank", dict(calc_flank_score=1)), ("hla", dict(use_mapq_cap=1)),
+                     ("both", dict(calc_flank_score=1, use_mapq_cap=1))):
+        batch = cases.edge_batch(seed=5, overhang=True)
+        opt = _abi.PlbOptions.default()
+        for k, v in kw.items():
+            setattr(opt, k, v)
+        arrs, ll, sc, st = O.population_run(batch, opt)
+        out[name + "_ll"] = ll
+        out[name + "_score"] = sc
+        for k in ("gl", "freq", "var_phred", "call"):
+            out[name + "_" + k] = arrs[k]
+    np.savez_compressed(os.path.join(HERE, "window_modes_restated.npz"), **out)
+    print("window_modes_restated.npz written")
+
+
 def make_window():
     batch = cases.edge_batch(seed=5)
     arrs, ll, sc, st = O.population_run(batch)
@@ -91,4 +170,7 @@ def make_window():
 if __name__ == "__main__":
     make_align()
     make_calign()
+    make_align_tb()
+    make_calign_modes()
     make_window()
+    make_window_modes()

@@ -155,3 +155,115 @@ def test_genotype_mix_branches(oracle):
     v_h = L.plo_genotype_loglik(a.ctypes.data, a.ctypes.data, 5, 4, 1, C.byref(gof), None, None)
     assert abs(v_h - a.sum()) < 1e-12
     assert abs(gof.value - (-10 * 0.43429448190325182 * a.sum() / 4)) < 1e-9
+
+
+# ---- scope row a2 / N2: traceback, calculateFlankScore, HLA map-qual cap ------------------------
+
+def test_golden_align_tb_ref(oracle, golden_dir):
+    """Traceback rows, firstpos and calculateFlankScore against the reference's align.c outputs."""
+    g = np.load(os.path.join(golden_dir, "align_tb_ref.npz"))
+    n = len(g["score"])
+    assert n >= 300
+    for i in range(n):
+        hap = _unpack(g["hap_off"], g["hap"], i)
+        go = _unpack(g["hap_off"], g["gap_open"], i)
+        read = _unpack(g["read_off"], g["read"], i)
+        qual = _unpack(g["read_off"], g["qual"], i)
+        a1 = _unpack(g["aln_off"], g["aln1"], i)
+        a2 = _unpack(g["aln_off"], g["aln2"], i)
+        s, m1, m2, fp = oracle.band_align_tb(hap, read, qual, go)
+        assert (s, m1, m2, fp) == (int(g["score"][i]), a1, a2, int(g["firstpos"][i])), "golden case %d" % i
+        fl = int(g["hap_flank"][i])
+        assert oracle.flank_score(len(hap), fl, qual, go, fp, m1, m2) == int(g["flank_score"][i]), "case %d" % i
+        # the one-pass formulation the CUDA path uses
+        assert oracle.band_align_flank(hap, read, qual, go, 0, fl) == (s, int(g["flank_score"][i])), "case %d" % i
+
+
+def test_golden_calign_modes_ref(oracle, golden_dir):
+    """mapAndAlignReadToHaplotype with doCalculateFlankScore=1 and with clipped reads voting through
+    the unclipped read's hashes (HLA mode) against the reference's calign.pyx outputs."""
+    g = np.load(os.path.join(golden_dir, "calign_modes_ref.npz"))
+    n = len(g["score"])
+    for i in range(n):
+        hap = _unpack(g["hap_off"], g["hap"], i)
+        read = _unpack(g["read_off"], g["read"], i)
+        qual = _unpack(g["read_off"], g["qual"], i)
+        hread = _unpack(g["hash_read_off"], g["hash_read"], i)
+        s, _ = oracle.map_and_align_ex(read, qual, int(g["read_start"][i]), int(g["hap_start"][i]), hap, None,
+                                       int(g["hap_flank"][i]), int(g["do_flank"][i]), hread)
+        assert s == int(g["score"][i]), "golden case %d" % i
+
+
+def test_vs_ref_traceback_and_flank_fuzz(oracle):
+    if oracle.ref_align_lib() is None:
+        pytest.skip("oracle/_ref/libalign_ref.so not built (no reference checkout)")
+    rng = random.Random(201)
+    for i in range(1500):
+        hap, go, read, qual = cases.random_alignment_case(rng, i)
+        want = oracle.ref_fast_align_tb(hap, read, qual, go)
+        got = oracle.band_align_tb(hap, read, qual, go)
+        assert got == want, "case %d" % i
+        fl = rng.randint(1, max(1, len(hap) // 2))
+        f = oracle.ref_flank_score(len(hap), fl, qual, go, want[3], want[1], want[2])
+        assert oracle.flank_score(len(hap), fl, qual, go, got[3], got[1], got[2]) == f
+        assert oracle.band_align_flank(hap, read, qual, go, 0, fl) == (want[0], f)
+
+
+def test_vs_ref_calign_modes_fuzz(oracle):
+    cw = oracle.ref_calign()
+    if cw is None:
+        pytest.skip("oracle/_ref/calign not built (no reference checkout)")
+    rng = random.Random(202)
+    for i in range(700):
+        hap, read, qual, rs, hs = cases.random_mapping_case(rng, i)
+        go = oracle.gap_open(hap)
+        fl = rng.randint(1, max(1, len(hap) // 2))
+        hread = read
+        if i % 2 and len(read) > 30:
+            o1, o2 = rng.choice([0, 1, 3, 10]), rng.choice([0, 2, 7])
+            read, qual, rs = read[o1:len(read) - o2], qual[o1:len(qual) - o2], rs + o1
+        do = int(i % 3 != 0)
+        want = cw.map_and_align(read, qual, rs, hs, hap, go, 3, 2, fl, do, 0, hread)
+        got, _ = oracle.map_and_align_ex(read, qual, rs, hs, hap, go, fl, do, hread)
+        assert got == want, "case %d" % i
+
+
+def test_score_to_ll_hla(oracle):
+    m = -0.23025850929940459
+    # below the threshold: standard transform, capped by the log-probability of a wrong mapping
+    assert abs(oracle.score_to_ll_hla(10, 60) - (m * 10 + math.log(1 - 1e-6))) < 1e-12
+    assert oracle.score_to_ll_hla(100, 20) == m * 20
+    assert oracle.score_to_ll_hla(0, 0) == 0.0                 # log(1 - 1) = -inf loses against the cap 0
+    # above: mLTOT * (99 + 2*sqrt(score - 99)), chaplotype.pyx:668-672
+    assert abs(oracle.score_to_ll_hla(199, 60) - max(m * 60, m * (99 + 2 * math.sqrt(100)))) < 1e-12
+    assert abs(oracle.score_to_ll_hla(101, 250) - m * (99 + 2 * math.sqrt(2))) < 1e-12
+    assert oracle.score_to_ll_hla(101, 93) == m * 93          # the cap wins
+
+
+def test_golden_window_modes_restated(oracle, golden_dir):
+    from platypus_b200 import _abi
+    g = np.load(os.path.join(golden_dir, "window_modes_restated.npz"))
+    for name, kw in (("flank", dict(calc_flank_score=1)), ("hla", dict(use_mapq_cap=1)),
+                     ("both", dict(calc_flank_score=1, use_mapq_cap=1))):
+        batch = cases.edge_batch(seed=5, overhang=True)
+        arrs, ll, sc, _ = oracle.population_run(batch, _abi.PlbOptions.default(**kw))
+        assert np.array_equal(sc, g[name + "_score"]), name
+        np.testing.assert_allclose(ll, g[name + "_ll"], rtol=1e-12, atol=0, err_msg=name)
+        np.testing.assert_allclose(arrs["gl"], g[name + "_gl"], rtol=1e-9, atol=1e-300, err_msg=name)
+        assert np.array_equal(arrs["call"], g[name + "_call"]), name
+
+
+def test_reference_kernel_inside_oracle_agrees_flank_mode(oracle):
+    """Window path in flank mode: reference align.c + calculateFlankScore vs the restatement."""
+    if not oracle.use_reference_kernel(True):
+        pytest.skip("oracle/_ref/libalign_ref.so not built")
+    from platypus_b200 import _abi
+    opt = _abi.PlbOptions.default(calc_flank_score=1)
+    try:
+        b = cases.edge_batch(seed=8, overhang=True)
+        ll_ref, sc_ref, _ = oracle.window_loglik(b, opt)
+    finally:
+        oracle.use_reference_kernel(False)
+    ll, sc, _ = oracle.window_loglik(b, opt)
+    assert np.array_equal(sc, sc_ref)
+    assert np.array_equal(ll, ll_ref)
