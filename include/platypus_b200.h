@@ -21,14 +21,14 @@
 extern "C" {
 #endif
 
-#define PLB_ABI_VERSION 1
+#define PLB_ABI_VERSION 2
 
 /* status codes */
 #define PLB_OK              0
 #define PLB_ERR_ARG        -1   /* NULL pointer / inconsistent offsets                         */
 #define PLB_ERR_SHAPE      -2   /* limit exceeded (haplotype > 16384 bp, H > max_haps, ...)     */
 #define PLB_ERR_CUDA       -3   /* CUDA runtime error, no device, or kernel image missing       */
-#define PLB_ERR_UNSUPPORTED -4  /* option not implemented yet (flank score, HLA map-qual cap)   */
+#define PLB_ERR_UNSUPPORTED -4  /* option not implemented (none at present; kept for ABI stability) */
 #define PLB_ERR_NOMEM      -5
 
 /* limits inherited from the reference */
@@ -48,8 +48,12 @@ extern "C" {
 typedef struct PlbOptions {
     int32_t gap_extend;         /* 3 */
     int32_t nuc_prior;          /* 2 */
-    int32_t use_mapq_cap;       /* options.HLATyping; must be 0 (PLB_ERR_UNSUPPORTED otherwise) */
-    int32_t calc_flank_score;   /* options.calculateFlankScore; must be 0                       */
+    int32_t use_mapq_cap;       /* options.HLATyping = useMapQualCap of alignReads (cpopulation.pyx:296):
+                                   reads clipped to the haplotype, cap = mLTOT*mapq, smooth cap above
+                                   score 100 (chaplotype.pyx:631-672); 0 or 1                          */
+    int32_t calc_flank_score;   /* options.calculateFlankScore: every band alignment with a positive
+                                   score loses its in-flank cost (calign.pyx:236-238, 262-264,
+                                   align.c:593-644); flank = win_start - hap_start must be > 0; 0 or 1 */
     int32_t max_em_iters;       /* 100 */
     int32_t use_em_likelihoods; /* options.useEMLikelihoods, cpopulation.pyx:654-657            */
 } PlbOptions;
@@ -177,11 +181,13 @@ int plb_validate(const PlbWindowBatch* host_batch, const PlbOptions* opt, int32_
 /* -- S1: kernel seam ------------------------------------------------------------- */
 
 /*
- * Replaces fastAlignmentRoutine (src/c/align.h:8-9, src/c/align.c:77-586) for the
- * score (aln1/aln2/firstpos are accepted for signature compatibility and must be
- * NULL: traceback is scope row N2).  Same argument meaning: seq1 = haplotype segment
- * of len1 = len2+15 bases, seq2/qual2 = read, localgapopen >= len1 entries.  Host
- * buffers; launches a 1-element batch.  Returns the score (>= 0) or a negative status.
+ * Replaces fastAlignmentRoutine (src/c/align.h:8-9, src/c/align.c:77-586).  Same argument
+ * meaning: seq1 = haplotype segment of len1 = len2+15 bases, seq2/qual2 = read,
+ * localgapopen >= len1 entries.  As in the reference, traceback is requested by passing
+ * aln1/aln2 (both, 2*len2+16 bytes each, align.c:96): they receive the NUL-terminated
+ * alignment rows and *firstpos the segment column of the first row (align.c:523-577,
+ * same tie-breaking: M before I before D).  Host buffers; launches a 1-element batch.
+ * Returns the score (>= 0) or a negative status.
  */
 int plb_fast_align(PlbContext* ctx, const char* seq1, const char* seq2, const char* qual2,
                    int len1, int len2, int gapextend, int nucprior,
@@ -196,6 +202,31 @@ int plb_align_batch_host(PlbContext* ctx, int32_t n,
                          const int64_t* hap_seg_off, const uint8_t* hap_seg, const uint8_t* gap_open,
                          const int64_t* read_off, const uint8_t* read_seq, const uint8_t* read_qual,
                          int gapextend, int nucprior, int32_t* scores_out);
+
+/*
+ * Batched fastAlignmentRoutine WITH traceback.  Alignment i writes its rows at
+ * aln1_out/aln2_out + 2*read_off[i] + 16*i (2*len+16 bytes, NUL-terminated) and
+ * firstpos_out[i].
+ */
+int plb_align_traceback_host(PlbContext* ctx, int32_t n,
+                             const int64_t* hap_seg_off, const uint8_t* hap_seg, const uint8_t* gap_open,
+                             const int64_t* read_off, const uint8_t* read_seq, const uint8_t* read_qual,
+                             int gapextend, int nucprior, int32_t* scores_out,
+                             char* aln1_out, char* aln2_out, int32_t* firstpos_out);
+
+/*
+ * Batched fastAlignmentRoutine + calculateFlankScore (src/c/align.h:11-12, align.c:593-644)
+ * as mapAndAlignReadToHaplotype chains them (calign.pyx:232-238): alignment i runs on the
+ * band segment that starts at seg_start[i] of WHOLE haplotype i (hap_off/hap_seq/gap_open
+ * index whole haplotypes), flank_out[i] = calculateFlankScore(hapLen_i, hap_flank[i], quals,
+ * localgapopen, gapextend, nucprior, firstpos + seg_start[i], aln1, aln2) of the alignment the
+ * traceback produces.  Computed in one forward pass (no back-pointer storage).
+ */
+int plb_align_flank_batch_host(PlbContext* ctx, int32_t n,
+                               const int64_t* hap_off, const uint8_t* hap_seq, const uint8_t* gap_open,
+                               const int32_t* seg_start, const int32_t* hap_flank,
+                               const int64_t* read_off, const uint8_t* read_seq, const uint8_t* read_qual,
+                               int gapextend, int nucprior, int32_t* scores_out, int32_t* flank_out);
 
 /*
  * Replaces Haplotype.annotateWithGapOpen (src/cython/chaplotype.pyx:552-590) for a

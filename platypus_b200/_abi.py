@@ -87,6 +87,10 @@ def declare(lib):
     lib.plb_fast_align.restype = C.c_int
     lib.plb_align_batch_host.argtypes = [_p, C.c_int32, _p, _p, _p, _p, _p, _p, C.c_int, C.c_int, _p]
     lib.plb_align_batch_host.restype = C.c_int
+    lib.plb_align_traceback_host.argtypes = [_p, C.c_int32, _p, _p, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p, _p, _p]
+    lib.plb_align_traceback_host.restype = C.c_int
+    lib.plb_align_flank_batch_host.argtypes = [_p, C.c_int32, _p, _p, _p, _p, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p]
+    lib.plb_align_flank_batch_host.restype = C.c_int
     lib.plb_gap_open_host.argtypes = [_p, C.c_int32, _p, _p, _p]
     lib.plb_gap_open_host.restype = C.c_int
     lib.plb_window_loglik_host.argtypes = [_p, P(PlbWindowBatch), P(PlbOptions), P(PlbLoglikOut)]
@@ -111,7 +115,8 @@ def declare(lib):
 # every symbol the header declares; tests check the built library exports all of them
 EXPORTED_SYMBOLS = [
     "plb_context_create", "plb_context_destroy", "plb_last_error", "plb_abi_version", "plb_launch_count",
-    "plb_ll_offsets", "plb_validate", "plb_fast_align", "plb_align_batch_host", "plb_gap_open_host",
+    "plb_ll_offsets", "plb_validate", "plb_fast_align", "plb_align_batch_host", "plb_align_traceback_host",
+    "plb_align_flank_batch_host", "plb_gap_open_host",
     "plb_window_loglik_host", "plb_population_run_host", "plb_batch_upload", "plb_batch_free",
     "plb_run_device", "plb_last_stats", "plb_set_timing", "plb_kernel_times",
 ]

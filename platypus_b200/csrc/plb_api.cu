@@ -90,6 +90,8 @@ struct PlbDeviceBatch {
     DevBatch d{};
     Block blk{nullptr, 0};
     Queue q{}, q2{};                   // general-path queues (one per compute stream)
+    Block mode_blk{nullptr, 0};        // larger queues for the run-time modes (every alignment is queued),
+    Queue mq{}, mq2{};                 // allocated on the first run with calc_flank_score / use_mapq_cap
     double* ll_scratch = nullptr;
     double* em_scratch = nullptr;      // [W][nInd][Gmax_plan]
     int32_t max_haps = 0;              // largest H in the batch
@@ -235,8 +237,9 @@ extern "C" int plb_ll_offsets(const PlbWindowBatch* b, int64_t* ll_off, int64_t*
 
 static int check_options(const PlbOptions* o) {
     if (!o) return set_err(PLB_ERR_ARG, "options is NULL");
-    if (o->use_mapq_cap) return set_err(PLB_ERR_UNSUPPORTED, "use_mapq_cap (HLATyping) is not implemented");
-    if (o->calc_flank_score) return set_err(PLB_ERR_UNSUPPORTED, "calc_flank_score is not implemented");
+    if (o->use_mapq_cap != 0 && o->use_mapq_cap != 1) return set_err(PLB_ERR_ARG, "use_mapq_cap must be 0 or 1");
+    if (o->calc_flank_score != 0 && o->calc_flank_score != 1)
+        return set_err(PLB_ERR_ARG, "calc_flank_score must be 0 or 1");
     if (o->gap_extend < 0 || o->gap_extend > 64 || o->nuc_prior < 0 || o->nuc_prior > 64)
         return set_err(PLB_ERR_ARG, "gap_extend / nuc_prior out of range");
     return PLB_OK;
@@ -268,6 +271,9 @@ extern "C" int plb_validate(const PlbWindowBatch* b, const PlbOptions* opt, int3
         if (max_haps > 0 && H > max_haps)
             return set_err(PLB_ERR_SHAPE, "window %d has %d haplotypes > max_haps %d (cpopulation.pyx:221)", w, H,
                            max_haps);
+        if (opt && opt->calc_flank_score && b->win_start[w] - b->hap_start[w] <= 0)
+            return set_err(PLB_ERR_ARG, "window %d: calc_flank_score needs a positive flank (win_start - hap_start)", w);
+        const bool hla = opt && opt->use_mapq_cap;
         int min_len = 1 << 30;
         for (int h = b->win_hap_off[w]; h < b->win_hap_off[w + 1]; ++h) {
             const int64_t len = b->hap_seq_off[h + 1] - b->hap_seq_off[h];
@@ -288,9 +294,20 @@ extern "C" int plb_validate(const PlbWindowBatch* b, const PlbOptions* opt, int3
                 const int64_t L = b->read_seq_off[r + 1] - b->read_seq_off[r];
                 if (L < 0 || L > 32767) return set_err(PLB_ERR_SHAPE, "read %d length %lld out of range", r, (long long)L);
                 // the reference would read past the haplotype (calign.pyx:256-259); refuse instead
-                if (L >= PLB_KMER && L + 15 > min_len)
+                if (!hla && L >= PLB_KMER && L + 15 > min_len)
                     return set_err(PLB_ERR_SHAPE, "window %d: read %d (%lld bp) + 15 exceeds haplotype length %d", w, r,
                                    (long long)L, min_len);
+                if (hla) {  // same rule on the read as clipped to each haplotype (chaplotype.pyx:647-655)
+                    for (int h = b->win_hap_off[w]; h < b->win_hap_off[w + 1]; ++h) {
+                        const int hl = (int)(b->hap_seq_off[h + 1] - b->hap_seq_off[h]);
+                        const int o1 = std::max(0, b->hap_start[w] - b->read_pos[r]);
+                        const int o2 = std::max(0, b->read_pos[r] + (int)L - b->win_start[w] - hl);
+                        const int Lc = (int)L - o1 - o2;
+                        if (Lc >= PLB_KMER && Lc + 15 > hl)
+                            return set_err(PLB_ERR_SHAPE, "window %d: clipped read %d (%d bp) + 15 exceeds haplotype length %d",
+                                           w, r, Lc, hl);
+                    }
+                }
             }
         }
     }
@@ -839,6 +856,7 @@ extern "C" void plb_batch_free(PlbContext* c, PlbDeviceBatch* b) {
     cudaStreamSynchronize(c->stream2);
     cudaStreamSynchronize(c->copy_stream);
     for (auto& ch : b->chunks) block_put(c, ch.tiles_blk);
+    if (b->mode_blk.p) block_put(c, b->mode_blk);
     block_put(c, b->blk);
     delete b;
 }
@@ -858,6 +876,27 @@ static int launch_check(PlbContext* c, const char* what) {
     return PLB_OK;
 }
 
+// In the run-time modes (flank score, HLA clipping) every band alignment goes through the queue, so
+// the default capacity (half the pairs) would overflow into the slow in-kernel fallback: get two
+// queues of ~2 entries per pair instead.  Overflow beyond that still falls back, never drops work.
+static int mode_queues(PlbContext* c, PlbDeviceBatch* db, bool two) {
+    if (db->mode_blk.p) return PLB_OK;
+    const int64_t want = std::min<int64_t>(2 * db->d.n_pairs + 4096, (int64_t)1 << 26);
+    const size_t qbytes = (((size_t)want * sizeof(QueueEntry)) + 255) & ~(size_t)255;
+    int rc = block_get(c, (two ? 2 : 1) * (qbytes + 256) + 256, &db->mode_blk);
+    if (rc) return rc;
+    uint8_t* p = (uint8_t*)db->mode_blk.p;
+    db->mq.e = (QueueEntry*)p;
+    db->mq.count = (int32_t*)(p + qbytes);
+    db->mq.cap = (int32_t)want;
+    db->mq2 = db->mq;
+    if (two) {
+        db->mq2.e = (QueueEntry*)(p + qbytes + 256);
+        db->mq2.count = (int32_t*)(p + 2 * qbytes + 256);
+    }
+    return PLB_OK;
+}
+
 // Launches the whole kernel sequence for one planned chunk of windows on stream st.  `timed` records
 // the per-kernel events of plb_kernel_times (whole-batch launches only).
 static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch, const PlbOptions* opt,
@@ -866,7 +905,7 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
     DevBatch& d = db->d;
     const int w0 = ch.w0, w1 = ch.w1;
     if (w1 <= w0) return PLB_OK;
-    ScoreParams sp{opt->gap_extend, opt->nuc_prior};
+    ScoreParams sp{opt->gap_extend, opt->nuc_prior, opt->calc_flank_score, opt->use_mapq_cap};
     const int nInd = d.n_individuals;
     const int h0 = ch.h0, h1 = ch.h1;
     CU(cudaMemsetAsync(d.win_flags + w0, 0, (size_t)(w1 - w0) * 4, st));
@@ -883,12 +922,20 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
     mark(1);
     if (ch.ap.n_tiles > 0) {
         const AnchorPlan& ap = ch.ap;
-        if ((rc = opt_in_smem(k_anchor, ch.a_smem))) return rc;
+        const bool modes = sp.flank || sp.hla;
+        if ((rc = opt_in_smem(k_anchor<false>, ch.a_smem)) || (modes && (rc = opt_in_smem(k_anchor<true>, ch.a_smem))))
+            return rc;
         const int grid = std::max(1, std::min(ap.n_tiles, c->n_sm * ch.a_occ));
-        k_anchor<<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr);
+        if (modes)
+            k_anchor<true><<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr);
+        else
+            k_anchor<false><<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr);
         if ((rc = launch_check(c, "k_anchor"))) return rc;
         mark(2);
-        k_general<<<c->n_sm * 4, 128, 0, st>>>(d, q, sp);
+        if (modes)
+            k_general<true><<<c->n_sm * 4, 128, 0, st>>>(d, q, sp);
+        else
+            k_general<false><<<c->n_sm * 4, 128, 0, st>>>(d, q, sp);
         if ((rc = launch_check(c, "k_general"))) return rc;
     } else {
         mark(2);
@@ -947,8 +994,10 @@ extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOption
     if ((rc = check_pop(db, pop))) return rc;
     cudaStream_t st = c->stream;
     CU(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), st));
+    const bool modes = opt->calc_flank_score || opt->use_mapq_cap;
+    if (modes && (rc = mode_queues(c, db, false))) return rc;
     for (const ChunkPlan& ch : db->chunks)
-        if ((rc = launch_windows(c, db, ch, opt, pop, llo, st, db->chunks.size() == 1, db->q))) return rc;
+        if ((rc = launch_windows(c, db, ch, opt, pop, llo, st, db->chunks.size() == 1, modes ? db->mq : db->q))) return rc;
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     return PLB_OK;
 }
@@ -1075,7 +1124,9 @@ static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* o
     // chunking: enough chunks to overlap, few enough to keep launches cheap
     int n_chunks = std::max(1, std::min(kMaxChunks, W / kMinChunkWindows));
     db->chunks.reserve(n_chunks);
-    rc = copy_meta(c, db, hb, cs);
+    const bool modes = opt->calc_flank_score || opt->use_mapq_cap;
+    rc = modes ? mode_queues(c, db, n_chunks > 1) : PLB_OK;
+    if (rc == PLB_OK) rc = copy_meta(c, db, hb, cs);
     if (rc == PLB_OK) e = cudaEventRecord(c->ev_chunk[0], cs);
     if (rc == PLB_OK && e == cudaSuccess) e = cudaStreamWaitEvent(st, c->ev_chunk[0], 0);
     if (rc == PLB_OK && e == cudaSuccess) e = cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), st);
@@ -1099,7 +1150,7 @@ static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* o
         if (e == cudaSuccess) e = cudaStreamWaitEvent(kst, c->ev_chunk[1 + k], 0);
         if (e != cudaSuccess) break;
         if ((rc = launch_windows(c, db, db->chunks.back(), opt, hpop ? &dpop : nullptr, &dll, kst, false,
-                                 (k & 1) ? db->q2 : db->q)))
+                                 modes ? ((k & 1) ? db->mq2 : db->mq) : ((k & 1) ? db->q2 : db->q))))
             break;
         if (hpop) {
             const size_t wq = (size_t)w0, wn = (size_t)(w1 - w0);
@@ -1272,17 +1323,174 @@ extern "C" int plb_align_batch_host(PlbContext* c, int32_t n, const int64_t* hap
     return PLB_OK;
 }
 
+namespace plb {
+// scope row a2: explicit alignments with traceback rows (align.c:523-577) ...
+__global__ void __launch_bounds__(64) k_align_traceback(int n, const int64_t* __restrict__ hap_off,
+                                                        const uint8_t* __restrict__ hap, const uint8_t* __restrict__ go,
+                                                        const int64_t* __restrict__ read_off,
+                                                        const uint8_t* __restrict__ rs, const uint8_t* __restrict__ rq,
+                                                        uint8_t* __restrict__ ptr_ws, char* __restrict__ aln1,
+                                                        char* __restrict__ aln2, int ext, int nuc,
+                                                        int32_t* __restrict__ score, int32_t* __restrict__ firstpos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t ro = read_off[i];
+    const int L = (int)(read_off[i + 1] - ro);
+    // per alignment: 16 back-pointer bytes per read row; alignment rows of 2L+16 bytes
+    int fp = 0;
+    score[i] = band_dp_traceback(hap + hap_off[i], go + hap_off[i], rs + ro, rq + ro, L, ext, nuc, ptr_ws + 16 * ro,
+                                 aln1 + 2 * ro + 16 * (int64_t)i, aln2 + 2 * ro + 16 * (int64_t)i, &fp);
+    firstpos[i] = fp;
+}
+
+// ... and with the flank score of calculateFlankScore (align.c:593-644) from one forward pass
+__global__ void __launch_bounds__(64) k_align_flank(int n, const int64_t* __restrict__ hap_off,
+                                                    const uint8_t* __restrict__ hap, const uint8_t* __restrict__ go,
+                                                    const int32_t* __restrict__ seg_start,
+                                                    const int32_t* __restrict__ hap_flank,
+                                                    const int64_t* __restrict__ read_off, const uint8_t* __restrict__ rs,
+                                                    const uint8_t* __restrict__ rq, int ext, int nuc,
+                                                    int32_t* __restrict__ score, int32_t* __restrict__ flank) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t ro = read_off[i], ho = hap_off[i];
+    const int L = (int)(read_off[i + 1] - ro), hap_len = (int)(hap_off[i + 1] - ho), st = seg_start[i];
+    int fl = 0;
+    score[i] = band_dp_flank(hap + ho + st, go + ho + st, rs + ro, rq + ro, L, ext, nuc, st, hap_len, hap_flank[i], &fl);
+    flank[i] = fl;
+}
+}  // namespace plb
+
+extern "C" int plb_align_traceback_host(PlbContext* c, int32_t n, const int64_t* hap_seg_off, const uint8_t* hap_seg,
+                                        const uint8_t* gap_open, const int64_t* read_off, const uint8_t* read_seq,
+                                        const uint8_t* read_qual, int ext, int nuc, int32_t* scores_out, char* aln1_out,
+                                        char* aln2_out, int32_t* firstpos_out) {
+    if (!c || n < 0 || (n > 0 && (!hap_seg_off || !hap_seg || !gap_open || !read_off || !read_seq || !read_qual ||
+                                  !scores_out || !aln1_out || !aln2_out || !firstpos_out)))
+        return set_err(PLB_ERR_ARG, "NULL / bad argument");
+    if (n == 0) return PLB_OK;
+    CU(cudaSetDevice(c->device));
+    for (int i = 0; i < n; ++i) {
+        const int64_t L = read_off[i + 1] - read_off[i];
+        if (L < 1 || L > 32767) return set_err(PLB_ERR_SHAPE, "alignment %d: read length %lld out of range", i, (long long)L);
+        if (hap_seg_off[i + 1] - hap_seg_off[i] < L + 15)
+            return set_err(PLB_ERR_SHAPE, "alignment %d: segment shorter than read+15 (align.c:88)", i);
+    }
+    const int64_t hb = hap_seg_off[n], rb = read_off[n];
+    const size_t aln_bytes = (size_t)(2 * rb + 16 * (int64_t)n);
+    Layout L;
+    const size_t o_ho = L.take((size_t)(n + 1) * 8), o_h = L.take((size_t)hb + 64), o_g = L.take((size_t)hb + 64),
+                 o_ro = L.take((size_t)(n + 1) * 8), o_rs = L.take((size_t)rb + 64), o_rq = L.take((size_t)rb + 64),
+                 o_ptr = L.take((size_t)rb * 16 + 64), o_a1 = L.take(aln_bytes), o_a2 = L.take(aln_bytes),
+                 o_sc = L.take((size_t)n * 4), o_fp = L.take((size_t)n * 4);
+    Block B;
+    int rc = block_get(c, L.off + 256, &B);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](size_t off, const void* src, size_t bytes) {
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync((uint8_t*)B.p + off, src, bytes, cudaMemcpyHostToDevice, st);
+    };
+    up(o_ho, hap_seg_off, (size_t)(n + 1) * 8);
+    up(o_h, hap_seg, (size_t)hb);
+    up(o_g, gap_open, (size_t)hb);
+    up(o_ro, read_off, (size_t)(n + 1) * 8);
+    up(o_rs, read_seq, (size_t)rb);
+    up(o_rq, read_qual, (size_t)rb);
+    if (e == cudaSuccess) {
+        k_align_traceback<<<(n + 63) / 64, 64, 0, st>>>(n, at<int64_t>(B, o_ho), at<uint8_t>(B, o_h), at<uint8_t>(B, o_g),
+                                                        at<int64_t>(B, o_ro), at<uint8_t>(B, o_rs), at<uint8_t>(B, o_rq),
+                                                        at<uint8_t>(B, o_ptr), at<char>(B, o_a1), at<char>(B, o_a2), ext, nuc,
+                                                        at<int32_t>(B, o_sc), at<int32_t>(B, o_fp));
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    auto down = [&](void* dst, size_t off, size_t bytes) {
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(dst, (uint8_t*)B.p + off, bytes, cudaMemcpyDeviceToHost, st);
+    };
+    down(scores_out, o_sc, (size_t)n * 4);
+    down(firstpos_out, o_fp, (size_t)n * 4);
+    down(aln1_out, o_a1, aln_bytes);
+    down(aln2_out, o_a2, aln_bytes);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    block_put(c, B);
+    if (e != cudaSuccess) return set_err(PLB_ERR_CUDA, "plb_align_traceback_host: %s", cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return set_err(PLB_ERR_CUDA, "plb_align_traceback_host: %s", cudaGetErrorString(e2));
+    return PLB_OK;
+}
+
+extern "C" int plb_align_flank_batch_host(PlbContext* c, int32_t n, const int64_t* hap_off, const uint8_t* hap_seq,
+                                          const uint8_t* gap_open, const int32_t* seg_start, const int32_t* hap_flank,
+                                          const int64_t* read_off, const uint8_t* read_seq, const uint8_t* read_qual,
+                                          int ext, int nuc, int32_t* scores_out, int32_t* flank_out) {
+    if (!c || n < 0 || (n > 0 && (!hap_off || !hap_seq || !gap_open || !seg_start || !hap_flank || !read_off ||
+                                  !read_seq || !read_qual || !scores_out || !flank_out)))
+        return set_err(PLB_ERR_ARG, "NULL / bad argument");
+    if (n == 0) return PLB_OK;
+    CU(cudaSetDevice(c->device));
+    for (int i = 0; i < n; ++i) {
+        const int64_t L = read_off[i + 1] - read_off[i];
+        if (L < 1 || L > 32767) return set_err(PLB_ERR_SHAPE, "alignment %d: read length %lld out of range", i, (long long)L);
+        if (seg_start[i] < 0 || hap_off[i + 1] - hap_off[i] < seg_start[i] + L + 15)
+            return set_err(PLB_ERR_SHAPE, "alignment %d: haplotype shorter than start+read+15 (align.c:88)", i);
+    }
+    const int64_t hb = hap_off[n], rb = read_off[n];
+    Layout L;
+    const size_t o_ho = L.take((size_t)(n + 1) * 8), o_h = L.take((size_t)hb + 64), o_g = L.take((size_t)hb + 64),
+                 o_ss = L.take((size_t)n * 4), o_hf = L.take((size_t)n * 4), o_ro = L.take((size_t)(n + 1) * 8),
+                 o_rs = L.take((size_t)rb + 64), o_rq = L.take((size_t)rb + 64), o_sc = L.take((size_t)n * 4),
+                 o_fl = L.take((size_t)n * 4);
+    Block B;
+    int rc = block_get(c, L.off + 256, &B);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](size_t off, const void* src, size_t bytes) {
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync((uint8_t*)B.p + off, src, bytes, cudaMemcpyHostToDevice, st);
+    };
+    up(o_ho, hap_off, (size_t)(n + 1) * 8);
+    up(o_h, hap_seq, (size_t)hb);
+    up(o_g, gap_open, (size_t)hb);
+    up(o_ss, seg_start, (size_t)n * 4);
+    up(o_hf, hap_flank, (size_t)n * 4);
+    up(o_ro, read_off, (size_t)(n + 1) * 8);
+    up(o_rs, read_seq, (size_t)rb);
+    up(o_rq, read_qual, (size_t)rb);
+    if (e == cudaSuccess) {
+        k_align_flank<<<(n + 63) / 64, 64, 0, st>>>(n, at<int64_t>(B, o_ho), at<uint8_t>(B, o_h), at<uint8_t>(B, o_g),
+                                                    at<int32_t>(B, o_ss), at<int32_t>(B, o_hf), at<int64_t>(B, o_ro),
+                                                    at<uint8_t>(B, o_rs), at<uint8_t>(B, o_rq), ext, nuc,
+                                                    at<int32_t>(B, o_sc), at<int32_t>(B, o_fl));
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(scores_out, (uint8_t*)B.p + o_sc, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(flank_out, (uint8_t*)B.p + o_fl, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    block_put(c, B);
+    if (e != cudaSuccess) return set_err(PLB_ERR_CUDA, "plb_align_flank_batch_host: %s", cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return set_err(PLB_ERR_CUDA, "plb_align_flank_batch_host: %s", cudaGetErrorString(e2));
+    return PLB_OK;
+}
+
 extern "C" int plb_fast_align(PlbContext* c, const char* seq1, const char* seq2, const char* qual2, int len1, int len2,
                               int gapextend, int nucprior, const char* localgapopen, char* aln1, char* aln2,
                               int* firstpos) {
     if (!c || !seq1 || !seq2 || !qual2 || !localgapopen) return set_err(PLB_ERR_ARG, "NULL argument");
-    if (aln1 || aln2) return set_err(PLB_ERR_UNSUPPORTED, "traceback (aln1/aln2) is not implemented");
+    if ((aln1 == nullptr) != (aln2 == nullptr)) return set_err(PLB_ERR_ARG, "aln1 and aln2 must both be given or both be NULL");
     if (len1 != len2 + 15) return set_err(PLB_ERR_SHAPE, "len1 must be len2 + 15 (align.c:88)");
-    (void)firstpos;
     int64_t ho[2] = {0, len1}, ro[2] = {0, len2};
     int32_t score = 0;
-    int rc = plb_align_batch_host(c, 1, ho, (const uint8_t*)seq1, (const uint8_t*)localgapopen, ro, (const uint8_t*)seq2,
+    int rc;
+    if (aln1) {  // traceback requested exactly as the reference decides it (align.c:96)
+        int32_t fp = 0;
+        rc = plb_align_traceback_host(c, 1, ho, (const uint8_t*)seq1, (const uint8_t*)localgapopen, ro, (const uint8_t*)seq2,
+                                      (const uint8_t*)qual2, gapextend, nucprior, &score, aln1, aln2, &fp);
+        if (rc == PLB_OK && firstpos) *firstpos = fp;
+    } else {
+        rc = plb_align_batch_host(c, 1, ho, (const uint8_t*)seq1, (const uint8_t*)localgapopen, ro, (const uint8_t*)seq2,
                                   (const uint8_t*)qual2, gapextend, nucprior, &score);
+    }
     return rc ? rc : score;
 }
 

@@ -504,4 +504,195 @@ PLB_HD int band_dp_general(const uint8_t* __restrict__ hap, const uint8_t* __res
     return best;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Scope row a2 / N2: traceback and calculateFlankScore (src/c/align.c:344-365, 493-644).
+//
+// With traceback on, every value of the reference carries the label of its own state in its two
+// low bits (M=0, I=1, D=3; scores are x4) and every `min` compares value and label, so equal
+// scores resolve to the smaller label; the label surviving a cell's min is that state's
+// back-pointer.  key = 4*score + label reproduces that order exactly.
+//
+// band_dp_flank computes the flank score WITHOUT storing back-pointers or walking them: each
+// state carries, next to its key, the in-flank cost of the path its back-pointers describe
+// (a min over keys selects exactly the predecessor the traceback would follow, and
+// calculateFlankScore charges each alignment column the same cost the recurrence charged,
+// counted only where the column's haplotype coordinate lies in a flank).  One 32-bit word per
+// state: key in bits 14.., flank cost in bits 0..13 (flank <= score < 15872).  Candidates of one
+// min never share a key (their labels differ), so the packed min is the min by key.
+//   column coordinate: M and D at cell (x, y) -> x;  I -> x + 1 (align.c:621-631)
+// Returns the score; *flank_out = calculateFlankScore of the traceback alignment.
+// ---------------------------------------------------------------------------------------------
+constexpr u32 kFlInf = 0xFC000000u;
+constexpr u32 kFlLblMask = 3u << 14;
+
+PLB_HD u32 fl_min(u32 a, u32 b) { return a < b ? a : b; }
+PLB_HD u32 fl_fix(u32 v, u32 lbl) { v = v < kFlInf ? v : kFlInf; return (v & ~kFlLblMask) | (lbl << 14); }
+
+PLB_HD int band_dp_flank(const uint8_t* __restrict__ hap, const uint8_t* __restrict__ open,
+                         const uint8_t* __restrict__ read, const uint8_t* __restrict__ qual, int L, int ext, int nuc,
+                         int start, int hap_len, int hap_flank, int* flank_out) {
+    u32 M[16], I[16], D[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) M[d] = I[d] = D[d] = kFlInf;
+    const int hi_lo = hap_len - hap_flank;   // columns >= hi_lo or < hap_flank are flank columns
+    // fm bit d = column (start + y + d) lies in a flank, for d = 0..16
+    u32 fm = 0;
+    for (int d = 0; d <= 16; ++d) {
+        const int hx = start + d;
+        fm |= (u32)((hx < hap_flank) | (hx >= hi_lo)) << d;
+    }
+    for (int y = 0; y < L; ++y) {
+        const u32 rb = read[y], q = qual[y];
+        u32 mp = kFlInf, ip = kFlInf, dp = kFlInf;   // states of cell (x-1, y), i.e. diagonal d-1 of this row
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+            const int x = y + d;
+            const u32 hb = hap[x], go = open[x];
+            const u32 wx = 65536u + ((fm >> d) & 1u);        // cost weight: 4<<14 for the key + 1 if in flank
+            const u32 wx1 = 65536u + ((fm >> (d + 1)) & 1u);
+            const u32 sub = (hb == 'N' || hb == rb) ? 0u : q;
+            u32 diag = fl_min(M[d], fl_min(I[d], D[d]));
+            if (y == 0) diag = 0u;
+            const u32 m = diag + sub * wx;
+            u32 ins;
+            if (y == 0) {
+                ins = (x & 1) ? kFlInf : (go + (u32)nuc) * wx1;
+            } else if (d < 15) {
+                ins = fl_min(I[d + 1] + (u32)ext * wx1, M[d + 1] + go * wx1) + (u32)nuc * wx1;
+            } else {
+                ins = kFlInf;
+            }
+            u32 del;
+            if (d >= 1) {
+                del = fl_min(dp + (u32)ext * wx, fl_min(mp, ip) + go * wx);
+            } else {
+                del = kFlInf;
+            }
+            mp = fl_fix(m, 0u);
+            ip = fl_fix(ins, 1u);
+            dp = fl_fix(del, 3u);
+            M[d] = mp;
+            I[d] = ip;
+            D[d] = dp;
+        }
+        const int hx = start + y + 17;
+        fm = (fm >> 1) | ((u32)((hx < hap_flank) | (hx >= hi_lo)) << 16);
+    }
+    u32 best = 0xFFFFFFFFu;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {   // first diagonal with the smallest labelled value, align.c:261-288, 416-443
+        const u32 k = fl_min(M[d], fl_min(I[d], D[d]));
+        if ((k >> 14) < (best >> 14)) best = k;
+    }
+    if (flank_out) *flank_out = (int)(best & 0x3FFFu);
+    return (int)(best >> 16);
+}
+
+// Score of one band alignment as mapAndAlignReadToHaplotype uses it with doCalculateFlankScore = 1
+// (calign.pyx:232-238, 258-264): a positive score loses its flank part.
+PLB_HD int band_dp_flank_adjusted(const uint8_t* __restrict__ hap, const uint8_t* __restrict__ open,
+                                  const uint8_t* __restrict__ read, const uint8_t* __restrict__ qual, int L, int ext,
+                                  int nuc, int start, int hap_len, int hap_flank) {
+    int fl = 0;
+    const int s = band_dp_flank(hap + start, open + start, read, qual, L, ext, nuc, start, hap_len, hap_flank, &fl);
+    return s > 0 ? s - fl : s;
+}
+
+// Full traceback (plb_fast_align with aln1/aln2): forward pass storing one byte of back-pointers
+// per cell (bits 0-1 M, 2-3 I, 6-7 D, the packing of align.c:346-348) in ptr[L*16], then the walk
+// of align.c:523-577.  aln1/aln2 must hold 2L+16 bytes.  Returns the score.
+PLB_HD int band_dp_traceback(const uint8_t* __restrict__ hap, const uint8_t* __restrict__ open,
+                             const uint8_t* __restrict__ read, const uint8_t* __restrict__ qual, int L, int ext,
+                             int nuc, uint8_t* __restrict__ ptr, char* __restrict__ aln1, char* __restrict__ aln2,
+                             int* firstpos) {
+    int M[16], I[16], D[16];   // keys 4*score + label
+    const int big = kScoreBig;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) M[d] = I[d] = D[d] = big;
+    for (int y = 0; y < L; ++y) {
+        const int rb = read[y], q = qual[y];
+        int mp = big, ip = big, dp = big;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+            const int x = y + d;
+            const int hb = hap[x], go = open[x];
+            const int sub = (hb == 'N' || hb == rb) ? 0 : q;
+            int diag = M[d] < I[d] ? M[d] : I[d];
+            diag = diag < D[d] ? diag : D[d];
+            if (y == 0) diag = 0;
+            int m = diag + 4 * sub;
+            int ins;
+            if (y == 0) {
+                ins = (x & 1) ? big : 4 * (go + nuc);
+            } else if (d < 15) {
+                const int a = I[d + 1] + 4 * ext, b = M[d + 1] + 4 * go;
+                ins = (a < b ? a : b) + 4 * nuc;
+            } else {
+                ins = big;
+            }
+            int del;
+            if (d >= 1) {
+                const int mi = mp < ip ? mp : ip;
+                const int a = dp + 4 * ext, b = mi + 4 * go;
+                del = a < b ? a : b;
+            } else {
+                del = big;
+            }
+            ptr[y * 16 + d] = (uint8_t)((m & 3) | ((ins & 3) << 2) | ((del & 3) << 6));
+            mp = m < big ? (m & ~3) : big;
+            ip = ins < big ? ((ins & ~3) | 1) : big + 1;
+            dp = del < big ? ((del & ~3) | 3) : big + 3;
+            M[d] = mp;
+            I[d] = ip;
+            D[d] = dp;
+        }
+    }
+    int best = big + 8, bd = 0;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+        int k = M[d] < I[d] ? M[d] : I[d];
+        k = k < D[d] ? k : D[d];
+        if (k < best) {
+            best = k;
+            bd = d;
+        }
+    }
+    int state = best & 3;
+    int cx = L - 1 + bd, cy = L - 1, n = 0;
+    while (cy >= 0) {
+        const int d = cx - cy;
+        const int p = (d >= 0 && d < 16) ? ptr[cy * 16 + d] : 0;
+        const int ns = (p >> (2 * state)) & 3;
+        if (state == 0) {
+            aln1[n] = (char)hap[cx];
+            aln2[n] = (char)read[cy];
+            --cx;
+            --cy;
+        } else if (state == 1) {
+            aln1[n] = '-';
+            aln2[n] = (char)read[cy];
+            --cy;
+        } else {
+            aln1[n] = (char)hap[cx];
+            aln2[n] = '-';
+            --cx;
+        }
+        state = ns;
+        ++n;
+    }
+    aln1[n] = 0;
+    aln2[n] = 0;
+    if (firstpos) *firstpos = cx + 1;
+    for (int i = 0, j = n - 1; i < j; ++i, --j) {
+        char t = aln1[i];
+        aln1[i] = aln1[j];
+        aln1[j] = t;
+        t = aln2[i];
+        aln2[i] = aln2[j];
+        aln2[j] = t;
+    }
+    return best >> 2;
+}
+
 }  // namespace plb

@@ -78,7 +78,7 @@ struct QueueEntry {
     int32_t hap;
     int32_t slot;
     int32_t start;
-    int32_t pad;
+    uint32_t clip;    // HLA mode: bases clipped off the read front | clipped read length << 16 (0 = unclipped)
 };
 
 struct Queue {
@@ -94,7 +94,31 @@ struct Counters {  // device-side statistics
 
 struct ScoreParams {
     int32_t ext, nuc;
+    int32_t flank;    // options.calculateFlankScore: every band alignment loses its in-flank cost (calign.pyx:236-238)
+    int32_t hla;      // options.HLATyping (useMapQualCap): reads clipped to the haplotype, map-qual cap (chaplotype.pyx:631-672)
 };
+
+// HLA mode clips a read to the haplotype before scoring (chaplotype.pyx:647-655).  The right-hand
+// clip is measured from startPos + hapLen (window start, not haplotype start) exactly as the
+// reference does; the 7-mer hashes stay those of the unclipped read (read.hash, :637-638).
+struct PairClip {
+    int off1;   // bases dropped at the front (readSeq += offset1, readStart += offset1)
+    int L;      // clipped read length (may be <= 0)
+};
+__device__ __forceinline__ PairClip pair_clip(const ScoreParams& sp, int read_pos, int read_len, int hap_start,
+                                              int win_start, int hap_len) {
+    PairClip c;
+    c.off1 = 0;
+    c.L = read_len;
+    if (sp.hla) {
+        int o1 = hap_start - read_pos, o2 = read_pos + read_len - win_start - hap_len;
+        o1 = o1 < 0 ? 0 : o1;
+        o2 = o2 < 0 ? 0 : o2;
+        c.off1 = o1;
+        c.L = read_len - o1 - o2;
+    }
+    return c;
+}
 
 __device__ __forceinline__ u32 base_code(uint8_t ch) {  // calign.pyx:61-90
     u32 c = ch & 7u;
@@ -244,20 +268,33 @@ __device__ __forceinline__ int read_overlap(int ws, int we, int rp, int re) {  /
 
 constexpr int kAnchorThreads = 256;
 
-__device__ __noinline__ int general_dp_now(const DevBatch& b, int h, int read, int start, int L, ScoreParams sp) {
+// One band alignment on the scalar path: any bytes, any length, both run-time modes.  `roff` = bases
+// clipped off the read front (HLA mode), L = (clipped) read length.
+template <bool kModes>
+__device__ __noinline__ int general_dp_now(const DevBatch& b, int h, int read, int start, int roff, int L,
+                                           ScoreParams sp) {
     const uint8_t* hapg = b.hap_seq + b.hap_seq_off[h];
     const uint8_t* go = b.gap_open + b.hap_seq_off[h] + h;
-    return band_dp_general(hapg + start, go + start, b.read_seq + b.read_seq_off[read],
-                           b.read_qual + b.read_seq_off[read], L, sp.ext, sp.nuc);
+    const uint8_t* rs = b.read_seq + b.read_seq_off[read] + roff;
+    const uint8_t* rq = b.read_qual + b.read_seq_off[read] + roff;
+    if (kModes && sp.flank) {
+        const int w = b.hap_win[h];
+        const int hap_len = (int)(b.hap_seq_off[h + 1] - b.hap_seq_off[h]);
+        // hapFlank = hap.endBufferSize = startPos - hapStart (chaplotype.pyx:604, 609)
+        return band_dp_flank_adjusted(hapg, go, rs, rq, L, sp.ext, sp.nuc, start, hap_len,
+                                      b.win_start[w] - b.hap_start[w]);
+    }
+    return band_dp_general(hapg + start, go + start, rs, rq, L, sp.ext, sp.nuc);
 }
 
 // Collects the distinct band start offsets of one pair: the first two go to the packed path
 // (cand0/cand1), the rest - and everything on the general path - to the queue.
+template <bool kModes>
 struct Emitter {
     int c0, c1, sc;
     unsigned n_dp;
     __device__ __forceinline__ void emit(const DevBatch& b, const Queue& q, ScoreParams sp, bool slow, int64_t pair,
-                                         int h, int64_t gs, int read, int L, int start) {
+                                         int h, int64_t gs, int read, int roff, int L, int start) {
         if (start == c0 || start == c1) return;
         ++n_dp;
         if (!slow && c0 < 0) {
@@ -272,10 +309,10 @@ struct Emitter {
                 qe.hap = h;
                 qe.slot = (int32_t)gs;
                 qe.start = start;
-                qe.pad = 0;
+                qe.clip = (kModes && sp.hla) ? ((u32)roff | ((u32)L << 16)) : 0u;
                 q.e[qi] = qe;
             } else {  // queue full: run it right here
-                const int v = general_dp_now(b, h, read, start, L, sp);
+                const int v = general_dp_now<kModes>(b, h, read, start, roff, L, sp);
                 sc = v < sc ? v : sc;
             }
         }
@@ -361,8 +398,12 @@ __device__ __noinline__ int light_decide(LightArgs a) {
     return 1;
 }
 
-__global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, AnchorPlan plan, Queue q, ScoreParams sp,
+// kModes = false is the default instance (no flank score, no HLA clipping): the mode logic compiles away.
+template <bool kModes>
+__global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, AnchorPlan plan, Queue q, ScoreParams sp_in,
                                                            Counters* ctr) {
+    ScoreParams sp = sp_in;
+    if (!kModes) sp.flank = sp.hla = 0;
     extern __shared__ __align__(16) uint8_t smem[];
     // areas at host-planned byte offsets (integer offsets keep every access a plain 32-bit shared
     // address; generic-pointer arithmetic costs an S2R/LEA sequence per use)
@@ -582,6 +623,8 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             // ---- per (slot, haplotype) pair: light decision, else exact vote array ----
             const int npairs = ns * (g1 - g0);
             const int hloc0 = tile.h0 - b.win_hap_off[w];   // index of the tile's first haplotype in its window
+            const int hap_start_w = b.hap_start[w], win_start_w = b.win_start[w];
+            const bool mode_slow = sp.flank || sp.hla;      // both run-time modes take the scalar path
             auto pair_id = [&](int p, int& s, int& g, int64_t& gs, int64_t& pair) {
                 s = p % ns;
                 g = g0 + p / ns;
@@ -593,26 +636,27 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 int64_t gs, pair;
                 pair_id(p, s, g, gs, pair);
                 const SlotInfo si = s_slot[s];
+                const PairClip pc = pair_clip(sp, si.pos, si.len, hap_start_w, win_start_w, s_hmeta[3 * g]);
                 ++st_pairs;
-                if ((si.flags & 1) || si.len < kKmer) {  // LL forced to 0, or calign.pyx:182-183 (score 0)
+                if ((si.flags & 1) || pc.L < kKmer) {  // LL forced to 0, or calign.pyx:182-183 (score 0)
                     b.cand0[pair] = -1;
                     b.cand1[pair] = -1;
                     b.score[pair] = (si.flags & 1) ? -1 : 0;
                     if (!(si.flags & 1)) {
                         ++st_scored;
-                        st_cells += 16ull * si.len;
+                        st_cells += 16ull * (unsigned)(pc.L > 0 ? pc.L : 0);
                     }
                     s_vlist[3 * p] = (u32)kPairSkip;
                     continue;
                 }
                 ++st_scored;
-                st_cells += 16ull * si.len;
+                st_cells += 16ull * (unsigned)pc.L;
                 LightArgs la;
                 la.head_off = plan.o_heads + 2u * (u32)((g - g0) * hstride);
                 la.rpk_off = plan.o_rpk + 4u * (u32)si.poff;
                 la.hpk_off = plan.o_hpk + 4u * (u32)s_hmeta[3 * g + 2];
                 la.res_off = plan.o_vl + 12u * (u32)p;
-                la.nk_read = si.len - kKmer;
+                la.nk_read = pc.L - kKmer;   // HLA mode: 7-mers 0..L'-8 of the UNCLIPPED read vote
                 la.nk_hap = s_hmeta[3 * g] - kKmer;
                 la.vub = si.vub;
                 la.bits = bits;
@@ -630,15 +674,17 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 int64_t gs, pair;
                 pair_id(p, s, g, gs, pair);
                 const SlotInfo si = s_slot[s];
-                const int L = si.len, hap_len = s_hmeta[3 * g], h = tile.h0 + g;
-                Emitter em;
+                const int hap_len = s_hmeta[3 * g], h = tile.h0 + g;
+                const PairClip pc = pair_clip(sp, si.pos, si.len, hap_start_w, win_start_w, hap_len);
+                const int L = pc.L, roff = pc.off1;
+                Emitter<kModes> em;
                 em.c0 = em.c1 = -1;
                 em.sc = kScoreNone;
                 em.n_dp = 0;
-                int idx0 = si.pos - b.hap_start[w];  // fallback position (calign.pyx:252-256)
+                int idx0 = si.pos + roff - hap_start_w;  // fallback position (calign.pyx:252-256)
                 const int lim = hap_len - L - 15;
                 if (lim < idx0) idx0 = lim;
-                const bool slow = general || L < kMinFastLen || L > kMaxFastLen;
+                const bool slow = general || mode_slow || L < kMinFastLen || L > kMaxFastLen;
                 bool any_accepted = false;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
@@ -647,12 +693,13 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                     const int idx = cj - 1;
                     if (idx + L + 15 < hap_len) {  // calign.pyx:228
                         any_accepted = true;
-                        em.emit(b, q, sp, slow, pair, h, gs, si.read, L, idx > 8 ? idx - 8 : 0);
+                        em.emit(b, q, sp, slow, pair, h, gs, si.read, roff, L, idx > 8 ? idx - 8 : 0);
                     }
                 }
                 // with no accepted candidate bestMappingPosition stays -1, so a fallback index of
                 // exactly -1 is skipped and the sentinel 1000000 is returned (calign.pyx:258, 272)
-                if (any_accepted || idx0 != -1) em.emit(b, q, sp, slow, pair, h, gs, si.read, L, idx0 > 8 ? idx0 - 8 : 0);
+                if (any_accepted || idx0 != -1)
+                    em.emit(b, q, sp, slow, pair, h, gs, si.read, roff, L, idx0 > 8 ? idx0 - 8 : 0);
                 st_dp += em.n_dp;
                 b.cand0[pair] = em.c0;
                 b.cand1[pair] = em.c1;
@@ -670,8 +717,9 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 const int h = tile.h0 + g;
                 const int64_t gs = tile.s0 + s;
                 const int64_t pair = si.pair0 + (int64_t)(h - b.win_hap_off[w]) * si.T;
-                const int L = si.len, nk = L - kKmer;
                 const int hap_len = s_hmeta[3 * g];
+                const PairClip pc = pair_clip(sp, si.pos, si.len, hap_start_w, win_start_w, hap_len);
+                const int L = pc.L, roff = pc.off1, nk = L - kKmer;
                 const uint16_t* nxt = s_next + s_hmeta[3 * g + 1];
                 const uint16_t* head = s_heads + (g - g0) * hstride;
                 const u32* rpk = s_rpk + si.poff;
@@ -697,11 +745,11 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                     m = max(m, max(v & 0xFFFFu, v >> 16));
                 }
                 for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-                Emitter em;
+                Emitter<kModes> em;
                 em.c0 = em.c1 = -1;
                 em.sc = kScoreNone;
                 em.n_dp = 0;
-                const bool slow = general || L < kMinFastLen || L > kMaxFastLen;
+                const bool slow = general || mode_slow || L < kMinFastLen || L > kMaxFastLen;
                 bool any_accepted = false;
                 for (int base = 0; base < C; base += 32) {  // ascending offsets, calign.pyx:223
                     const int o = base + lane;
@@ -716,16 +764,16 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                             bal &= bal - 1;
                             const int ix = base + k - L;
                             any_accepted = true;
-                            em.emit(b, q, sp, slow, pair, h, gs, si.read, L, ix > 8 ? ix - 8 : 0);
+                            em.emit(b, q, sp, slow, pair, h, gs, si.read, roff, L, ix > 8 ? ix - 8 : 0);
                         }
                     }
                 }
                 if (lane == 0) {
-                    int idx0 = si.pos - b.hap_start[w];
+                    int idx0 = si.pos + roff - hap_start_w;
                     const int lim = hap_len - L - 15;
                     if (lim < idx0) idx0 = lim;
                     if (any_accepted || idx0 != -1)
-                        em.emit(b, q, sp, slow, pair, h, gs, si.read, L, idx0 > 8 ? idx0 - 8 : 0);
+                        em.emit(b, q, sp, slow, pair, h, gs, si.read, roff, L, idx0 > 8 ? idx0 - 8 : 0);
                     st_dp += em.n_dp;
                     b.cand0[pair] = em.c0;
                     b.cand1[pair] = em.c1;
@@ -756,17 +804,27 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
 // ---------------------------------------------------------------------------------------------
 // k_general: queued alignments on the scalar path
 // ---------------------------------------------------------------------------------------------
+template <bool kModes>
 __global__ void __launch_bounds__(128) k_general(DevBatch b, Queue q, ScoreParams sp) {
     int n = *q.count;
     if (n > q.cap) n = q.cap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const QueueEntry qe = q.e[i];
         const int r = b.slot_read[qe.slot];
-        const int L = (int)(b.read_seq_off[r + 1] - b.read_seq_off[r]);
-        const uint8_t* hap = b.hap_seq + b.hap_seq_off[qe.hap];
-        const uint8_t* go = b.gap_open + b.hap_seq_off[qe.hap] + qe.hap;
-        const int v = band_dp_general(hap + qe.start, go + qe.start, b.read_seq + b.read_seq_off[r],
-                                      b.read_qual + b.read_seq_off[r], L, sp.ext, sp.nuc);
+        int L = (int)(b.read_seq_off[r + 1] - b.read_seq_off[r]), roff = 0;
+        if (kModes && sp.hla) {
+            roff = (int)(qe.clip & 0xFFFFu);
+            L = (int)(qe.clip >> 16);
+        }
+        int v;
+        if (kModes) {
+            v = general_dp_now<true>(b, qe.hap, r, qe.start, roff, L, sp);
+        } else {
+            const uint8_t* hap = b.hap_seq + b.hap_seq_off[qe.hap];
+            const uint8_t* go = b.gap_open + b.hap_seq_off[qe.hap] + qe.hap;
+            v = band_dp_general(hap + qe.start, go + qe.start, b.read_seq + b.read_seq_off[r],
+                                b.read_qual + b.read_seq_off[r], L, sp.ext, sp.nuc);
+        }
         atomicMin(&b.score[qe.pair], v);
     }
 }
@@ -876,6 +934,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                 const int ov = read_overlap(b.win_start[w], b.win_end[w], b.read_pos[r], b.read_end[r]);
                 if (b.read_qcfail[r] || ov < kKmer) ds.flags = 1;
             }
+            ds.flags |= (int)b.read_mapq[r] << 8;
             ds.ll_right = log(1.0 - exp(kMLTOT * (double)b.read_mapq[r]));
             ds.poff = 0;
             s_slot[s] = ds;
@@ -912,7 +971,9 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
         }
         __syncthreads();
         const u32 wflags = b.win_flags[w];
-        const int general = wflags & 1;
+        // the run-time modes (flank score, HLA clipping) run every alignment on the scalar path
+        // (k_general); this kernel then only turns their scores into log-likelihoods
+        const int general = (wflags & 1) | sp.flank | sp.hla;
         const bool six = !(wflags & 2);   // no 'N' in the window's haplotypes: 6-op variant
         const int K = 2 * sp.ext + sp.nuc;
         // ---- TMA: one bulk copy per read for bases and one for qualities, straight into the tail of
@@ -1082,6 +1143,13 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
             double ll;
             if (ds.flags & 1) {
                 ll = 0.0;
+            } else if (sp.hla) {
+                // chaplotype.pyx:631-634, 664-676: the cap is the log-probability of a wrong mapping and
+                // scores above 100 are flattened: mLTOT * (99 + (score - 99)^0.5 / 0.5)
+                const double cap = kMLTOT * (double)((ds.flags >> 8) & 0xFF);
+                const double v = sc > 100 ? kMLTOT * (99.0 + sqrt((double)sc - 99.0) / 0.5)
+                                          : kMLTOT * (double)sc + ds.ll_right;
+                ll = v > cap ? v : cap;
             } else {
                 const double v = kMLTOT * (double)sc + ds.ll_right;
                 ll = v > -300.0 ? v : -300.0;

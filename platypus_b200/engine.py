@@ -92,6 +92,69 @@ class Engine:
         return _check(self.lib, self.lib.plb_fast_align(self.ctx, seq1, seq2, qual2, L + 15, L, gapextend, nucprior,
                                                         gap_open, None, None, None))
 
+    def fast_align_traceback(self, seq1: bytes, seq2: bytes, qual2: bytes, gap_open: bytes, gapextend=3, nucprior=2):
+        """fastAlignmentRoutine with aln1/aln2/firstpos (reference: src/c/align.c:523-577).
+        Returns (score, aln1, aln2, firstpos)."""
+        L = len(seq2)
+        if len(seq1) < L + 15 or len(gap_open) < L + 15 or len(qual2) != L:
+            raise PlbError(_abi.PLB_ERR_SHAPE, "need len(seq1) >= len(seq2)+15 and matching qual/gap-open lengths")
+        a1 = C.create_string_buffer(2 * L + 16)
+        a2 = C.create_string_buffer(2 * L + 16)
+        fp = C.c_int(0)
+        s = _check(self.lib, self.lib.plb_fast_align(self.ctx, seq1, seq2, qual2, L + 15, L, gapextend, nucprior,
+                                                     gap_open, C.addressof(a1), C.addressof(a2), C.addressof(fp)))
+        return s, a1.value, a2.value, fp.value
+
+    def align_traceback_batch(self, hap_segs, gap_opens, reads, quals, gapextend=3, nucprior=2):
+        """Batched traceback: list of (score, aln1, aln2, firstpos)."""
+        n = len(reads)
+        ho = np.zeros(n + 1, np.int64)
+        ro = np.zeros(n + 1, np.int64)
+        np.cumsum([len(x) for x in hap_segs], out=ho[1:])
+        np.cumsum([len(x) for x in reads], out=ro[1:])
+        hseq = np.frombuffer(b"".join(hap_segs), np.uint8)
+        gop = np.frombuffer(b"".join(g[:len(h)] for g, h in zip(gap_opens, hap_segs)), np.uint8)
+        rseq = np.frombuffer(b"".join(reads), np.uint8)
+        rq = np.frombuffer(b"".join(quals), np.uint8)
+        sc = np.zeros(max(n, 1), np.int32)
+        fp = np.zeros(max(n, 1), np.int32)
+        nb = 2 * int(ro[-1]) + 16 * n
+        a1 = np.zeros(max(nb, 1), np.uint8)
+        a2 = np.zeros(max(nb, 1), np.uint8)
+        _check(self.lib, self.lib.plb_align_traceback_host(self.ctx, n, _abi.ptr(ho), hseq.ctypes.data, gop.ctypes.data,
+                                                           _abi.ptr(ro), rseq.ctypes.data, rq.ctypes.data, gapextend,
+                                                           nucprior, _abi.ptr(sc), _abi.ptr(a1), _abi.ptr(a2),
+                                                           _abi.ptr(fp)))
+        out = []
+        for i in range(n):
+            o = 2 * int(ro[i]) + 16 * i
+            r1 = a1[o:o + 2 * len(reads[i]) + 16].tobytes()
+            r2 = a2[o:o + 2 * len(reads[i]) + 16].tobytes()
+            out.append((int(sc[i]), r1[:r1.index(b"\0")], r2[:r2.index(b"\0")], int(fp[i])))
+        return out
+
+    def align_flank_batch(self, haps, gap_opens, seg_starts, hap_flanks, reads, quals, gapextend=3, nucprior=2):
+        """fastAlignmentRoutine + calculateFlankScore (reference: src/c/align.c:593-644) for explicit
+        (whole haplotype, band start, flank, read) tuples.  Returns (scores, flank scores)."""
+        n = len(reads)
+        ho = np.zeros(n + 1, np.int64)
+        ro = np.zeros(n + 1, np.int64)
+        np.cumsum([len(x) for x in haps], out=ho[1:])
+        np.cumsum([len(x) for x in reads], out=ro[1:])
+        hseq = np.frombuffer(b"".join(haps), np.uint8)
+        gop = np.frombuffer(b"".join(g[:len(h)] for g, h in zip(gap_opens, haps)), np.uint8)
+        rseq = np.frombuffer(b"".join(reads), np.uint8)
+        rq = np.frombuffer(b"".join(quals), np.uint8)
+        ss = np.asarray(seg_starts, np.int32)
+        hf = np.asarray(hap_flanks, np.int32)
+        sc = np.zeros(max(n, 1), np.int32)
+        fl = np.zeros(max(n, 1), np.int32)
+        _check(self.lib, self.lib.plb_align_flank_batch_host(self.ctx, n, _abi.ptr(ho), hseq.ctypes.data, gop.ctypes.data,
+                                                             _abi.ptr(ss), _abi.ptr(hf), _abi.ptr(ro), rseq.ctypes.data,
+                                                             rq.ctypes.data, gapextend, nucprior, _abi.ptr(sc),
+                                                             _abi.ptr(fl)))
+        return sc[:n], fl[:n]
+
     def align_batch(self, hap_segs, gap_opens, reads, quals, gapextend=3, nucprior=2):
         """Batched S1 over explicit (segment, read) pairs given as lists of bytes."""
         n = len(reads)

@@ -7,13 +7,17 @@
 #include <vector>
 #include "../../platypus_b200/csrc/plb_dp.cuh"
 extern "C" int plo_band_align(const uint8_t*, const uint8_t*, const uint8_t*, int, int, int, const uint8_t*);
+extern "C" int plo_band_align_tb(const uint8_t*, const uint8_t*, const uint8_t*, int, int, int, const uint8_t*, char*, char*,
+                                 int*);
+extern "C" int plo_band_align_flank(const uint8_t*, const uint8_t*, const uint8_t*, int, int, int, const uint8_t*, int, int,
+                                    int, int*);
 
 static uint64_t rs = 88172645463325252ull;
 static uint32_t rnd() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (uint32_t)(rs >> 11); }
 
 int main(int argc, char** argv) {
     int n_cases = argc > 1 ? atoi(argv[1]) : 3000;
-    int bad = 0, bad_gen = 0, n6 = 0;
+    int bad = 0, bad_gen = 0, n6 = 0, bad_fl = 0, bad_tb = 0;
     const char* alpha = "ACGT";
     for (int c = 0; c < n_cases; ++c) {
         int L = 9 + rnd() % 260;
@@ -70,8 +74,30 @@ int main(int argc, char** argv) {
             if (got6 != want) { if (++bad < 6) printf("fast6 mismatch L=%d x0=%d want=%d got=%d\n", L, x0, want, got6); }
             ++n6;
         }
+        {   // scope row a2: one-pass flank score and the full traceback against the oracle
+            const int flank = 1 + rnd() % (hapLen / 2 + 1);
+            int fw = 0, fg = 0;
+            const int sw = plo_band_align_flank(hap.data() + x0, read.data(), qual.data(), L, ext, nuc, open.data() + x0, x0,
+                                                hapLen, flank, &fw);
+            const int sg = plb::band_dp_flank(hap.data() + x0, open.data() + x0, read.data(), qual.data(), L, ext, nuc, x0,
+                                              hapLen, flank, &fg);
+            if (sw != want || sg != sw || fg != fw) {
+                if (++bad_fl < 6) printf("flank mismatch L=%d x0=%d flank=%d want=(%d,%d) got=(%d,%d)\n", L, x0, flank, sw, fw, sg, fg);
+            }
+            std::vector<char> a1(2 * L + 16), a2(2 * L + 16), b1(2 * L + 16), b2(2 * L + 16);
+            std::vector<uint8_t> ptr((size_t)L * 16);
+            int fp_w = -1, fp_g = -1;
+            const int tw = plo_band_align_tb(hap.data() + x0, read.data(), qual.data(), L, ext, nuc, open.data() + x0, a1.data(),
+                                             a2.data(), &fp_w);
+            const int tg = plb::band_dp_traceback(hap.data() + x0, open.data() + x0, read.data(), qual.data(), L, ext, nuc,
+                                                  ptr.data(), b1.data(), b2.data(), &fp_g);
+            if (tw != tg || fp_w != fp_g || strcmp(a1.data(), b1.data()) || strcmp(a2.data(), b2.data())) {
+                if (++bad_tb < 6) printf("traceback mismatch L=%d x0=%d\n", L, x0);
+            }
+        }
         if (gen != want) { if (++bad_gen < 6) printf("general mismatch L=%d want=%d got=%d\n", L, want, gen); }
     }
     printf("mismatches %d general %d of %d (%d through the 6-op variant)\n", bad, bad_gen, n_cases, n6);
-    return (bad || bad_gen) ? 1 : 0;
+    printf("flank mismatches %d traceback mismatches %d\n", bad_fl, bad_tb);
+    return (bad || bad_gen || bad_fl || bad_tb) ? 1 : 0;
 }

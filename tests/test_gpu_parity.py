@@ -216,8 +216,8 @@ def test_limits_are_errors_not_crashes(engine):
         engine.population_run(b, max_haps=1)
     assert e.value.code == _abi.PLB_ERR_SHAPE
     with pytest.raises(PlbError) as e:
-        engine.population_run(b, opt=_abi.PlbOptions.default(use_mapq_cap=1))
-    assert e.value.code == _abi.PLB_ERR_UNSUPPORTED
+        engine.population_run(b, opt=_abi.PlbOptions.default(use_mapq_cap=2))
+    assert e.value.code == _abi.PLB_ERR_ARG
 
 
 def test_full_size_config2_properties(engine, oracle):
@@ -275,3 +275,128 @@ def _concat(batches):
                            hap_var_mask=[int(m) for m in s.hap_var_mask],
                            var_prior=list(s.var_prior[0][:int(s.win_n_var[0])])))
     return WindowBatch.from_windows(wins, 1)
+
+
+# ---- scope row a2 / N2: traceback, calculateFlankScore, HLA map-qual cap ------------------------
+
+def _tb_cases(g, n):
+    haps = [_unpack(g["hap_off"], g["hap"], i) for i in range(n)]
+    gos = [_unpack(g["hap_off"], g["gap_open"], i) for i in range(n)]
+    reads = [_unpack(g["read_off"], g["read"], i) for i in range(n)]
+    quals = [_unpack(g["read_off"], g["qual"], i) for i in range(n)]
+    return haps, gos, reads, quals
+
+
+def test_s1_traceback_golden_ref(engine, golden_dir):
+    """plb_fast_align / plb_align_traceback_host reproduce the reference's alignment rows, firstpos and
+    score (src/c/align.c:523-577 run here at fixture time)."""
+    g = np.load(os.path.join(golden_dir, "align_tb_ref.npz"))
+    n = len(g["score"])
+    haps, gos, reads, quals = _tb_cases(g, n)
+    got = engine.align_traceback_batch([h[:len(r) + 15] for h, r in zip(haps, reads)], gos, reads, quals)
+    for i in range(n):
+        want = (int(g["score"][i]), _unpack(g["aln_off"], g["aln1"], i), _unpack(g["aln_off"], g["aln2"], i),
+                int(g["firstpos"][i]))
+        assert got[i] == want, "golden case %d" % i
+    # the scalar signature, traceback requested through aln1/aln2 like the reference (align.c:96)
+    for i in range(0, n, 57):
+        assert engine.fast_align_traceback(haps[i], reads[i], quals[i], gos[i]) == got[i]
+
+
+def test_s1_flank_score_golden_ref(engine, golden_dir):
+    """One-pass flank score == calculateFlankScore of the reference's traceback (align.c:593-644)."""
+    g = np.load(os.path.join(golden_dir, "align_tb_ref.npz"))
+    n = len(g["score"])
+    haps, gos, reads, quals = _tb_cases(g, n)
+    sc, fl = engine.align_flank_batch(haps, gos, [0] * n, list(g["hap_flank"]), reads, quals)
+    assert np.array_equal(sc, g["score"])
+    assert np.array_equal(fl, g["flank_score"])
+
+
+def test_s1_traceback_and_flank_fuzz_vs_oracle(engine, oracle):
+    rng = random.Random(77)
+    cs = [cases.random_alignment_case(rng, i) for i in range(1500)]
+    got = engine.align_traceback_batch([c[0][:len(c[2]) + 15] for c in cs], [c[1] for c in cs], [c[2] for c in cs],
+                                       [c[3] for c in cs])
+    starts, flanks, want_f = [], [], []
+    for i, c in enumerate(cs):
+        assert got[i] == oracle.band_align_tb(c[0], c[2], c[3], c[1]), "case %d" % i
+        st = rng.randint(0, len(c[0]) - len(c[2]) - 15)
+        fk = rng.randint(1, max(1, len(c[0]) // 2))
+        starts.append(st)
+        flanks.append(fk)
+        want_f.append(oracle.band_align_flank(c[0], c[2], c[3], c[1], st, fk))
+    sc, fl = engine.align_flank_batch([c[0] for c in cs], [c[1] for c in cs], starts, flanks, [c[2] for c in cs],
+                                      [c[3] for c in cs])
+    assert [(int(a), int(b)) for a, b in zip(sc, fl)] == want_f
+
+
+def _modes_mapping_batch(g, i0, i1, do_flank):
+    """One window per golden case of calign_modes_ref.npz with the wanted flank setting; HLA-clipped
+    cases cannot be expressed as windows (their clip is given, not derived) and are skipped."""
+    wins, idx = [], []
+    for i in range(i0, i1):
+        if int(g["do_flank"][i]) != do_flank:
+            continue
+        read = _unpack(g["read_off"], g["read"], i)
+        if read != _unpack(g["hash_read_off"], g["hash_read"], i) or len(read) < 7:
+            continue
+        hap = _unpack(g["hap_off"], g["hap"], i)
+        hs, fl = int(g["hap_start"][i]), int(g["hap_flank"][i])
+        rd = Read(read, _unpack(g["read_off"], g["qual"], i), int(g["read_start"][i]), int(g["read_start"][i]) + len(read), 60)
+        # broken-mate list: scored without the overlap test (chaplotype.pyx:363-370)
+        wins.append(Window(hs + fl, hs + fl + 1, hs, [hap], [([], [], [rd])]))
+        idx.append(i)
+    return WindowBatch.from_windows(wins, 1), idx
+
+
+def test_s2_flank_mode_golden_calign_ref(engine, golden_dir):
+    """Window path with calc_flank_score = 1 against the reference's mapAndAlignReadToHaplotype
+    (doCalculateFlankScore = 1) outputs."""
+    g = np.load(os.path.join(golden_dir, "calign_modes_ref.npz"))
+    n = len(g["score"])
+    b, idx = _modes_mapping_batch(g, 0, n, 1)
+    assert len(idx) > 100
+    ll, sc = engine.window_loglik(b, opt=_abi.PlbOptions.default(calc_flank_score=1))
+    assert np.array_equal(sc, g["score"][idx])
+
+
+@pytest.mark.parametrize("mode", [dict(calc_flank_score=1), dict(use_mapq_cap=1),
+                                  dict(calc_flank_score=1, use_mapq_cap=1)])
+def test_s3_modes_edge_batch_vs_oracle_and_golden(engine, oracle, golden_dir, mode):
+    name = {(1, 0): "flank", (0, 1): "hla", (1, 1): "both"}[(mode.get("calc_flank_score", 0), mode.get("use_mapq_cap", 0))]
+    opt = _abi.PlbOptions.default(**mode)
+    b = cases.edge_batch(seed=5, overhang=True)
+    got = engine.population_run(b, opt=opt, want_ll=True)
+    want, ll0, sc0, st0 = oracle.population_run(b, opt)
+    assert np.array_equal(got["score"], sc0)
+    np.testing.assert_allclose(got["ll"], ll0, rtol=RTOL_TIGHT, atol=0)
+    _check_population(got, want)
+    g = np.load(os.path.join(golden_dir, "window_modes_restated.npz"))
+    assert np.array_equal(got["score"], g[name + "_score"])
+    np.testing.assert_allclose(got["gl"], g[name + "_gl"], rtol=RTOL, atol=1e-300)
+    st = engine.last_stats()
+    assert st["cells"] == st0["cells"] and st["n_pairs_scored"] == st0["n_pairs_scored"]
+    for seed in (2, 3):
+        b = cases.edge_batch(seed=seed, n_windows=20, n_individuals=4, overhang=True)
+        got = engine.population_run(b, opt=opt, want_ll=True, max_haps=8)
+        want, ll0, sc0, _ = oracle.population_run(b, opt, max_haps=8)
+        assert np.array_equal(got["score"], sc0), seed
+        _check_population(got, want)
+
+
+def test_s3_modes_synth_sample(engine, oracle):
+    """Config-2 shaped windows under both run-time modes (every alignment on the scalar path,
+    queues sized for it), device-resident and host paths."""
+    b = synth.make_batch(64)
+    for mode in (dict(calc_flank_score=1), dict(use_mapq_cap=1)):
+        opt = _abi.PlbOptions.default(**mode)
+        got = engine.population_run(b, opt=opt, want_ll=True)
+        want, ll0, sc0, _ = oracle.population_run(b, opt, n_threads=os.cpu_count() or 1)
+        assert np.array_equal(got["score"], sc0), mode
+        np.testing.assert_allclose(got["ll"], ll0, rtol=RTOL_TIGHT, atol=0)
+        _check_population(got, want)
+    # the default mode still takes the packed path afterwards (mode state does not leak)
+    got = engine.population_run(b, want_ll=True)
+    want, ll0, sc0, _ = oracle.population_run(b, n_threads=os.cpu_count() or 1)
+    assert np.array_equal(got["score"], sc0)

@@ -25,6 +25,7 @@ def test_packed_lane_dp_matches_oracle_on_host(oracle, tmp_path):
     out = subprocess.run([exe, "4000"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert "mismatches 0 general 0" in out.stdout
+    assert "flank mismatches 0 traceback mismatches 0" in out.stdout
 
 
 def _lib():
@@ -41,7 +42,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_abi.EXPORTED_SYMBOLS), declared ^ set(_abi.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.plb_abi_version() == 1
+    assert lib.plb_abi_version() == 2
 
 
 def test_no_gpu_fails_loudly():
@@ -66,8 +67,11 @@ def test_ll_offsets_and_validate():
     assert lib.plb_validate(C.byref(s), C.byref(opt), 0) == 0
     assert lib.plb_validate(C.byref(s), C.byref(opt), 1) == _abi.PLB_ERR_SHAPE
     assert b"max_haps" in lib.plb_last_error()
-    opt2 = _abi.PlbOptions.default(calc_flank_score=1)
-    assert lib.plb_validate(C.byref(s), C.byref(opt2), 0) == _abi.PLB_ERR_UNSUPPORTED
+    # both run-time modes are accepted (scope row a2 / N2); anything but 0/1 is an argument error
+    for kw in (dict(calc_flank_score=1), dict(use_mapq_cap=1)):
+        assert lib.plb_validate(C.byref(s), C.byref(_abi.PlbOptions.default(**kw)), 0) == 0
+    opt2 = _abi.PlbOptions.default(calc_flank_score=2)
+    assert lib.plb_validate(C.byref(s), C.byref(opt2), 0) == _abi.PLB_ERR_ARG
     # haplotype shorter than read + 15: the reference would read out of bounds (calign.pyx:256-259)
     from platypus_b200.batch import Read, Window
     w = Window(100, 140, 50, [b"ACGT" * 10], [([Read(b"A" * 30, bytes([30] * 30), 100, 130)], [], [])])
