@@ -258,8 +258,11 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         t0 = time.perf_counter()
         e2e_steps = max(3, min(args.steps, 10))
+        e2e_each = []
         for _ in range(e2e_steps):
+            t1 = time.perf_counter()
             eng.population_run(hb, out=host_out)
+            e2e_each.append(round((time.perf_counter() - t1) * 1e3, 3))
         e2e_s = (time.perf_counter() - t0) / e2e_steps
         # parity guard: the host path and the device path must agree bit for bit
         assert np.array_equal(host_out["gl"], out["gl"].cpu().numpy())
@@ -317,7 +320,8 @@ def run_ours(args, rank, world, local_rank):
         "config": workload_config(world, windows),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_ms, "api": "plb_population_run_host (pinned host buffers)"},
+                "ms_per_step": e2e_ms, "ms_each_step": e2e_each,
+                "api": "plb_population_run_host (pinned host buffers)"},
         "gpu_launches": total_launches,
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -281,8 +281,8 @@ typedef struct PlbRunStats {
     int64_t n_pairs_scored;
     int64_t n_dp;
     int64_t cells;
-    int64_t n_anchor_heavy;   /* pairs not decided by the light anchor pass                    */
-    int64_t n_anchor_verify;  /* ... of which needed a second count of the majority candidate  */
+    int64_t n_anchor_heavy;   /* diagnostic: anchor tiles with >= 64 pairs on the exact vote path */
+    int64_t n_anchor_verify;  /* diagnostic: longest anchor tile: microseconds << 32 | window    */
     int64_t n_anchor_exact;   /* pairs without a strict majority (exact tied-maximum scan)     */
 } PlbRunStats;
 int plb_last_stats(PlbContext* ctx, PlbRunStats* out);

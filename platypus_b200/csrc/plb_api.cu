@@ -40,7 +40,7 @@ static int set_err(int code, const char* fmt, ...) {
     } while (0)
 
 constexpr int kTimingRing = 64;
-constexpr int kMaxChunks = 5;           // pipelined host path: chunks of windows per call
+constexpr int kMaxChunks = 6;           // pipelined host path: chunks of windows per call
 constexpr int kMinChunkWindows = 1024;
 
 struct Block {
@@ -52,8 +52,9 @@ struct PlbContext {
     int device;
     cudaStream_t stream;
     cudaStream_t copy_stream;   // H2D of the pipelined host path
-    cudaStream_t stream2;       // second compute stream: odd chunks of the pipelined host path
-    cudaEvent_t ev_s2;
+    cudaStream_t stream2;       // further compute streams: chunk k of the pipelined host path runs on
+    cudaStream_t stream3;       // stream k mod 3, so one chunk's latency-bound tails overlap the next chunks
+    cudaEvent_t ev_s2, ev_s3;
     std::vector<std::pair<uint8_t*, size_t>> pin_blocks;   // pinned staging for planner outputs
     size_t pin_off = 0;
     cudaEvent_t ev_chunk[kMaxChunks + 1];
@@ -89,9 +90,9 @@ struct ChunkPlan {
 struct PlbDeviceBatch {
     DevBatch d{};
     Block blk{nullptr, 0};
-    Queue q{}, q2{};                   // general-path queues (one per compute stream)
+    Queue q{}, q2{}, q3{};             // general-path queues (one per compute stream)
     Block mode_blk{nullptr, 0};        // larger queues for the run-time modes (every alignment is queued),
-    Queue mq{}, mq2{};                 // allocated on the first run with calc_flank_score / use_mapq_cap
+    Queue mq{}, mq2{}, mq3{};          // allocated on the first run with calc_flank_score / use_mapq_cap
     double* ll_scratch = nullptr;
     double* em_scratch = nullptr;      // [W][nInd][Gmax_plan]
     int32_t max_haps = 0;              // largest H in the batch
@@ -101,6 +102,7 @@ struct PlbDeviceBatch {
     std::vector<ChunkPlan> chunks;     // plb_batch_upload plans one chunk covering every window
     int64_t* h_ll_off = nullptr;       // pinned
     int64_t hap_done[2] = {0, 0}, read_done[2] = {0, 0};  // byte intervals already on the device
+    int64_t readmeta_done[2] = {0, 0};                    // read-index interval whose per-read arrays are on the device
 };
 
 extern "C" const char* plb_last_error(void) { return g_err; }
@@ -138,7 +140,9 @@ extern "C" int plb_context_create(int device, void* stream, PlbContext** out) {
     CU(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_s2, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_s3, cudaEventDisableTiming));
     for (int i = 0; i <= kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
     c->timing = false;
     c->n_timed = 0;
@@ -160,7 +164,10 @@ extern "C" void plb_context_destroy(PlbContext* c) {
     cudaStreamDestroy(c->copy_stream);
     cudaStreamSynchronize(c->stream2);
     cudaStreamDestroy(c->stream2);
+    cudaStreamSynchronize(c->stream3);
+    cudaStreamDestroy(c->stream3);
     cudaEventDestroy(c->ev_s2);
+    cudaEventDestroy(c->ev_s3);
     for (auto& pb : c->pin_blocks) cudaFreeHost(pb.first);
     for (int i = 0; i <= kMaxChunks; ++i) cudaEventDestroy(c->ev_chunk[i]);
     for (int r = 0; r < kTimingRing; ++r)
@@ -510,10 +517,11 @@ static int plan_tiles(const PlbWindowBatch* hb, int w_begin, int w_end, TileList
 struct ByteRanges {
     int64_t hap0, hap1;    // byte range of hap_seq
     int64_t read0, read1;  // byte range of read_seq / read_qual (hull over the reads the slots refer to)
+    int rmin, rmax;        // that hull as read indices (rmax < rmin: no reads)
 };
 
 static ByteRanges byte_ranges(const PlbWindowBatch* hb, int w0, int w1) {
-    ByteRanges r{0, 0, 0, 0};
+    ByteRanges r{0, 0, 0, 0, 0, -1};
     if (w1 <= w0) return r;
     const int nInd = hb->n_individuals;
     r.hap0 = hb->hap_seq_off[hb->win_hap_off[w0]];
@@ -530,6 +538,8 @@ static ByteRanges byte_ranges(const PlbWindowBatch* hb, int w0, int w1) {
     if (rmax >= 0) {
         r.read0 = hb->read_seq_off[rmin];
         r.read1 = hb->read_seq_off[rmax + 1];
+        r.rmin = rmin;
+        r.rmax = rmax;
     }
     return r;
 }
@@ -584,6 +594,7 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
     const int qcap = (int)std::min<int64_t>(std::max<int64_t>(4096, n_pairs / 2), 1 << 26);
     const size_t o_q = L.take((size_t)qcap * sizeof(QueueEntry)), o_qcount = L.take(64);
     const size_t o_q2 = L.take((size_t)qcap * sizeof(QueueEntry)), o_qcount2 = L.take(64);
+    const size_t o_q3 = L.take((size_t)qcap * sizeof(QueueEntry)), o_qcount3 = L.take(64);
     const size_t o_ll = L.take((size_t)n_pairs * 8);
     const int Gp = max_H * (max_H + 1) / 2;
     db->em_scratch_elems = (size_t)W * nInd * Gp;
@@ -637,6 +648,9 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
     db->q2.e = at<QueueEntry>(B, o_q2);
     db->q2.count = at<int32_t>(B, o_qcount2);
     db->q2.cap = qcap;
+    db->q3.e = at<QueueEntry>(B, o_q3);
+    db->q3.count = at<int32_t>(B, o_qcount3);
+    db->q3.cap = qcap;
     db->ll_scratch = at<double>(B, o_ll);
     db->em_scratch = at<double>(B, o_em);
     *out = db;
@@ -653,7 +667,10 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
 
 // Plans the tiles of windows [w0, w1), sizes the kernels' shared memory and puts the tile lists on
 // the device (async on st).
-static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* hb, int w0, int w1, cudaStream_t st) {
+// zero_copy: the kernels read the tile lists straight from pinned host memory (unified addressing) instead
+// of a device copy - a small H2D copy would queue behind the pipelined path's big sequence transfers.
+static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* hb, int w0, int w1, cudaStream_t st,
+                      bool zero_copy = false) {
     db->chunks.emplace_back();
     ChunkPlan& ch = db->chunks.back();
     ch.w0 = w0;
@@ -728,77 +745,150 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
     }
     if (ch.a_smem + 1024 > (size_t)c->smem_optin)
         return set_err(PLB_ERR_SHAPE, "anchor tile needs %zu bytes of shared memory", ch.a_smem);
-    ch.a_occ = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (ch.a_smem + 1024)));
+    // k_anchor is compiled for 4 resident CTAs per SM (__launch_bounds__(256, 4): 64 registers per thread)
+    ch.a_occ = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / (ch.a_smem + 1024)));
     ch.d_smem = (size_t)ch.dp.prof_words * 4 + (size_t)ch.dp.rec_count * sizeof(HapRec) +
                 (size_t)ch.dp.max_slots * (sizeof(DpSlot) + 4) + (size_t)ch.dp.max_group * 4 + (size_t)ch.dp.max_pairs * 12 +
                 64;
     if (ch.d_smem + 1024 > (size_t)c->smem_optin)
         return set_err(PLB_ERR_SHAPE, "dp tile needs %zu bytes of shared memory", ch.d_smem);
     ch.d_occ = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (ch.d_smem + 1024)));
+    // Tail splitting: the tiles left over after the last full wave of the persistent DP grid would keep a
+    // few CTAs busy for a whole tile time while the others idle.  Cut each of them into k pieces by slot
+    // range (k <= 3: a piece still fills the CTA's threads about once) when that shortens the last wave.
+    {
+        const int G = c->n_sm * ch.d_occ;
+        const int T = (int)ch.tl.d.size();
+        const int r = T % G;
+        if (r > 0 && T > 0) {
+            int best_k = 1;
+            double best = 1.0;
+            for (int k = 2; k <= 3; ++k) {
+                const double t = (double)((r * k + G - 1) / G) / k;
+                if (t < best - 1e-9) {
+                    best = t;
+                    best_k = k;
+                }
+            }
+            if (best_k > 1) {
+                std::vector<Tile> tail(ch.tl.d.end() - r, ch.tl.d.end());
+                ch.tl.d.resize((size_t)(T - r));
+                for (const Tile& t : tail) {
+                    const int64_t n = t.s1 - t.s0;
+                    const int k = (int)std::min<int64_t>(best_k, std::max<int64_t>(1, n));
+                    for (int j = 0; j < k; ++j) {
+                        Tile p = t;
+                        p.s0 = t.s0 + n * j / k;
+                        p.s1 = t.s0 + n * (j + 1) / k;
+                        if (p.s1 > p.s0) ch.tl.d.push_back(p);
+                    }
+                }
+                ch.dp.n_tiles = (int)ch.tl.d.size();
+            }
+        }
+    }
     const size_t na = ch.tl.a.size() * sizeof(Tile), nd = ch.tl.d.size() * sizeof(Tile);
-    int rc = block_get(c, na + nd + 512, &ch.tiles_blk);
-    if (rc) return rc;
-    ch.ap.tiles = (const Tile*)ch.tiles_blk.p;
-    ch.dp.tiles = (const Tile*)((uint8_t*)ch.tiles_blk.p + ((na + 255) & ~(size_t)255));
+    const size_t na_al = (na + 255) & ~(size_t)255;
     // stage through pinned memory: a copy from a pageable std::vector would block the host until
     // everything queued earlier on the stream (the sequence bytes) has been transferred
-    uint8_t* stage = (uint8_t*)pin_alloc(c, na + nd + 16);
+    uint8_t* stage = (uint8_t*)pin_alloc(c, na_al + nd + 16);
     if (!stage) return set_err(PLB_ERR_NOMEM, "pinned host allocation failed");
     if (na) memcpy(stage, ch.tl.a.data(), na);
-    if (nd) memcpy(stage + na, ch.tl.d.data(), nd);
+    if (nd) memcpy(stage + na_al, ch.tl.d.data(), nd);
+    if (zero_copy) {
+        ch.ap.tiles = (const Tile*)stage;
+        ch.dp.tiles = (const Tile*)(stage + na_al);
+        return PLB_OK;
+    }
+    int rc = block_get(c, na_al + nd + 512, &ch.tiles_blk);
+    if (rc) return rc;
+    ch.ap.tiles = (const Tile*)ch.tiles_blk.p;
+    ch.dp.tiles = (const Tile*)((uint8_t*)ch.tiles_blk.p + na_al);
     if (na) CUQ(cudaMemcpyAsync((void*)ch.ap.tiles, stage, na, cudaMemcpyHostToDevice, st));
-    if (nd) CUQ(cudaMemcpyAsync((void*)ch.dp.tiles, stage + na, nd, cudaMemcpyHostToDevice, st));
+    if (nd) CUQ(cudaMemcpyAsync((void*)ch.dp.tiles, stage + na_al, nd, cudaMemcpyHostToDevice, st));
     return PLB_OK;
 }
 
 namespace plb {
 // slot -> (window, individual) index and haplotype -> window maps, derived on the device
-__global__ void k_derive(DevBatch b) {
-    const int64_t nwi = (int64_t)b.n_windows * b.n_individuals;
-    for (int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wi < nwi; wi += (int64_t)gridDim.x * blockDim.x) {
+__global__ void k_derive(DevBatch b, int w0, int w1) {
+    const int64_t wi0 = (int64_t)w0 * b.n_individuals, wi1 = (int64_t)w1 * b.n_individuals;
+    for (int64_t wi = wi0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wi < wi1; wi += (int64_t)gridDim.x * blockDim.x) {
         int32_t* sw = (int32_t*)b.slot_wi;
         for (int64_t s = b.wi_slot_off[wi]; s < b.wi_slot_off[wi + 1]; ++s) sw[s] = (int32_t)wi;
     }
-    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < b.n_windows; w += gridDim.x * blockDim.x) {
+    for (int w = w0 + blockIdx.x * blockDim.x + threadIdx.x; w < w1; w += gridDim.x * blockDim.x) {
         int32_t* hw = (int32_t*)b.hap_win;
         for (int h = b.win_hap_off[w]; h < b.win_hap_off[w + 1]; ++h) hw[h] = w;
     }
 }
 }  // namespace plb
 
-// Copies everything except the three big byte arrays, then derives slot_wi / hap_win on the device.
-static int copy_meta(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* hb, cudaStream_t st) {
+// Copies the metadata (everything except the three big byte arrays) that windows [w0, w1) need
+// (slot_wi / hap_win are derived by k_derive at the head of the chunk's kernel sequence - never on the
+// copy stream, where a kernel would have to wait for SM space behind the persistent kernels and stall
+// the DMA queue).  Called once per chunk by the pipelined host path, so the first kernels wait for the
+// first chunk's share only.  Per-read arrays follow the same
+// "interval already uploaded" rule as the sequence bytes (reads are shared between windows).
+static int copy_meta(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* hb, int w0, int w1, int rmin, int rmax,
+                     cudaStream_t st) {
     const DevBatch& d = db->d;
-    const int W = d.n_windows, nInd = d.n_individuals;
-    const int64_t nwi = (int64_t)W * nInd;
-    auto cp = [&](const void* dst, const void* src, size_t bytes) -> cudaError_t {
-        if (!bytes || !src) return cudaSuccess;
-        return cudaMemcpyAsync((void*)dst, src, bytes, cudaMemcpyHostToDevice, st);
+    const int nInd = d.n_individuals;
+    if (w1 <= w0) return PLB_OK;
+    auto cp = [&](const void* dst, const void* src, size_t first, size_t count, size_t esz) -> cudaError_t {
+        if (!count || !src) return cudaSuccess;
+        return cudaMemcpyAsync((uint8_t*)dst + first * esz, (const uint8_t*)src + first * esz, count * esz,
+                               cudaMemcpyHostToDevice, st);
     };
-    CUQ(cp(d.win_hap_off, hb->win_hap_off, (size_t)(W + 1) * 4));
-    CUQ(cp(d.win_start, hb->win_start, (size_t)W * 4));
-    CUQ(cp(d.win_end, hb->win_end, (size_t)W * 4));
-    CUQ(cp(d.hap_start, hb->hap_start, (size_t)W * 4));
-    CUQ(cp(d.hap_seq_off, hb->hap_seq_off, (size_t)(d.n_haps + 1) * 8));
-    CUQ(cp(d.wi_slot_off, hb->wi_slot_off, (size_t)(nwi + 1) * 8));
-    CUQ(cp(d.wi_n_good, hb->wi_n_good, (size_t)nwi * 4));
-    CUQ(cp(d.wi_n_bad, hb->wi_n_bad, (size_t)nwi * 4));
-    CUQ(cp(d.slot_read, hb->slot_read, (size_t)d.n_slots * 4));
-    CUQ(cp(d.read_seq_off, hb->read_seq_off, (size_t)(d.n_reads + 1) * 8));
-    CUQ(cp(d.read_pos, hb->read_pos, (size_t)d.n_reads * 4));
-    CUQ(cp(d.read_end, hb->read_end, (size_t)d.n_reads * 4));
-    CUQ(cp(d.read_mapq, hb->read_mapq, (size_t)d.n_reads));
-    CUQ(cp(d.read_qcfail, hb->read_qcfail, (size_t)d.n_reads));
+    const size_t nw = (size_t)(w1 - w0);
+    const size_t wi0 = (size_t)w0 * nInd, nwi = nw * nInd;
+    const size_t h0 = (size_t)hb->win_hap_off[w0], nh = (size_t)hb->win_hap_off[w1] - h0;
+    const size_t s0 = (size_t)hb->wi_slot_off[wi0], ns = (size_t)hb->wi_slot_off[wi0 + nwi] - s0;
+    CUQ(cp(d.win_hap_off, hb->win_hap_off, w0, nw + 1, 4));
+    CUQ(cp(d.win_start, hb->win_start, w0, nw, 4));
+    CUQ(cp(d.win_end, hb->win_end, w0, nw, 4));
+    CUQ(cp(d.hap_start, hb->hap_start, w0, nw, 4));
+    CUQ(cp(d.hap_seq_off, hb->hap_seq_off, h0, nh + 1, 8));
+    CUQ(cp(d.wi_slot_off, hb->wi_slot_off, wi0, nwi + 1, 8));
+    CUQ(cp(d.wi_n_good, hb->wi_n_good, wi0, nwi, 4));
+    CUQ(cp(d.wi_n_bad, hb->wi_n_bad, wi0, nwi, 4));
+    CUQ(cp(d.slot_read, hb->slot_read, s0, ns, 4));
     if (db->have_var) {
-        CUQ(cp(d.win_n_var, hb->win_n_var, (size_t)W * 4));
-        CUQ(cp(d.hap_var_mask, hb->hap_var_mask, (size_t)d.n_haps * 8));
-        CUQ(cp(d.var_prior, hb->var_prior, (size_t)W * hb->max_variants * 8));
+        CUQ(cp(d.win_n_var, hb->win_n_var, w0, nw, 4));
+        CUQ(cp(d.hap_var_mask, hb->hap_var_mask, h0, nh, 8));
+        CUQ(cp(d.var_prior, hb->var_prior, (size_t)w0 * hb->max_variants, nw * hb->max_variants, 8));
     }
-    CUQ(cp(d.ll_off, db->h_ll_off, (size_t)(nwi + 1) * 8));
-    if (W > 0) {
-        k_derive<<<std::max(1, std::min(4 * c->n_sm, (int)((nwi + 127) / 128))), 128, 0, st>>>(d);
-        CUQ(cudaGetLastError());
-        c->launches++;
+    CUQ(cp(d.ll_off, db->h_ll_off, wi0, nwi + 1, 8));
+    // per-read arrays: the parts of [rmin, rmax] not uploaded yet
+    if (rmax >= rmin) {
+        auto reads = [&](size_t first, size_t count) -> int {
+            if (!count) return PLB_OK;
+            CUQ(cp(d.read_pos, hb->read_pos, first, count, 4));
+            CUQ(cp(d.read_end, hb->read_end, first, count, 4));
+            CUQ(cp(d.read_mapq, hb->read_mapq, first, count, 1));
+            CUQ(cp(d.read_qcfail, hb->read_qcfail, first, count, 1));
+            return PLB_OK;
+        };
+        int64_t* done = db->readmeta_done;
+        const int64_t lo = rmin, hi = (int64_t)rmax + 1;
+        int rc;
+        if (done[1] <= done[0]) {
+            if ((rc = reads((size_t)lo, (size_t)(hi - lo)))) return rc;
+            CUQ(cp(d.read_seq_off, hb->read_seq_off, (size_t)lo, (size_t)(hi - lo) + 1, 8));
+            done[0] = lo;
+            done[1] = hi;
+        } else {
+            if (lo < done[0]) {
+                if ((rc = reads((size_t)lo, (size_t)(done[0] - lo)))) return rc;
+                CUQ(cp(d.read_seq_off, hb->read_seq_off, (size_t)lo, (size_t)(done[0] - lo), 8));
+                done[0] = lo;
+            }
+            if (hi > done[1]) {
+                if ((rc = reads((size_t)done[1], (size_t)(hi - done[1])))) return rc;
+                CUQ(cp(d.read_seq_off, hb->read_seq_off, (size_t)done[1] + 1, (size_t)(hi - done[1]), 8));
+                done[1] = hi;
+            }
+        }
     }
     return PLB_OK;
 }
@@ -824,9 +914,12 @@ static int copy_bytes(uint8_t* dst, const uint8_t* src, int64_t lo, int64_t hi, 
     return PLB_OK;
 }
 
-static int copy_seq_for_windows(PlbDeviceBatch* db, const PlbWindowBatch* hb, int w0, int w1, cudaStream_t st) {
+// Metadata first (small), then the sequence bytes of windows [w0, w1).
+static int copy_seq_for_windows(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* hb, int w0, int w1,
+                                cudaStream_t st) {
     const ByteRanges r = byte_ranges(hb, w0, w1);
     int rc;
+    if ((rc = copy_meta(c, db, hb, w0, w1, r.rmin, r.rmax, st))) return rc;
     if ((rc = copy_bytes((uint8_t*)db->d.hap_seq, hb->hap_seq, r.hap0, r.hap1, db->hap_done, st))) return rc;
     int64_t qdone[2] = {db->read_done[0], db->read_done[1]};
     if ((rc = copy_bytes((uint8_t*)db->d.read_seq, hb->read_seq, r.read0, r.read1, db->read_done, st))) return rc;
@@ -834,13 +927,23 @@ static int copy_seq_for_windows(PlbDeviceBatch* db, const PlbWindowBatch* hb, in
     return PLB_OK;
 }
 
+static int launch_check(PlbContext* c, const char* what);
+
+static int derive_all(PlbContext* c, PlbDeviceBatch* db, cudaStream_t st) {
+    const DevBatch& d = db->d;
+    if (d.n_windows <= 0) return PLB_OK;
+    const int64_t nwi = (int64_t)d.n_windows * d.n_individuals;
+    k_derive<<<std::max(1, std::min(4 * c->n_sm, (int)((nwi + 127) / 128))), 128, 0, st>>>(d, 0, d.n_windows);
+    return launch_check(c, "k_derive");
+}
+
 extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch** out) {
     PlbDeviceBatch* db = nullptr;
     int rc = prepare_batch(c, hb, &db);
     if (rc) return rc;
     cudaStream_t st = c->stream;
-    if ((rc = copy_meta(c, db, hb, st)) || (rc = copy_seq_for_windows(db, hb, 0, hb->n_windows, st)) ||
-        (rc = plan_chunk(c, db, hb, 0, hb->n_windows, st))) {
+    if ((rc = copy_seq_for_windows(c, db, hb, 0, hb->n_windows, st)) ||
+        (rc = plan_chunk(c, db, hb, 0, hb->n_windows, st)) || (rc = derive_all(c, db, st))) {
         cudaStreamSynchronize(st);
         plb_batch_free(c, db);
         return rc;
@@ -854,6 +957,7 @@ extern "C" void plb_batch_free(PlbContext* c, PlbDeviceBatch* b) {
     if (!c || !b) return;
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream2);
+    cudaStreamSynchronize(c->stream3);
     cudaStreamSynchronize(c->copy_stream);
     for (auto& ch : b->chunks) block_put(c, ch.tiles_blk);
     if (b->mode_blk.p) block_put(c, b->mode_blk);
@@ -879,20 +983,20 @@ static int launch_check(PlbContext* c, const char* what) {
 // In the run-time modes (flank score, HLA clipping) every band alignment goes through the queue, so
 // the default capacity (half the pairs) would overflow into the slow in-kernel fallback: get two
 // queues of ~2 entries per pair instead.  Overflow beyond that still falls back, never drops work.
-static int mode_queues(PlbContext* c, PlbDeviceBatch* db, bool two) {
+static int mode_queues(PlbContext* c, PlbDeviceBatch* db, bool multi) {
     if (db->mode_blk.p) return PLB_OK;
-    const int64_t want = std::min<int64_t>(2 * db->d.n_pairs + 4096, (int64_t)1 << 26);
+    const int n = multi ? 3 : 1;
+    const int64_t want = std::min<int64_t>((multi ? 1 : 2) * db->d.n_pairs + 4096, (int64_t)1 << 26);
     const size_t qbytes = (((size_t)want * sizeof(QueueEntry)) + 255) & ~(size_t)255;
-    int rc = block_get(c, (two ? 2 : 1) * (qbytes + 256) + 256, &db->mode_blk);
+    int rc = block_get(c, n * (qbytes + 256) + 256, &db->mode_blk);
     if (rc) return rc;
     uint8_t* p = (uint8_t*)db->mode_blk.p;
-    db->mq.e = (QueueEntry*)p;
-    db->mq.count = (int32_t*)(p + qbytes);
-    db->mq.cap = (int32_t)want;
-    db->mq2 = db->mq;
-    if (two) {
-        db->mq2.e = (QueueEntry*)(p + qbytes + 256);
-        db->mq2.count = (int32_t*)(p + 2 * qbytes + 256);
+    Queue* qs[3] = {&db->mq, &db->mq2, &db->mq3};
+    for (int i = 0; i < 3; ++i) {
+        const int j = i < n ? i : 0;
+        qs[i]->e = (QueueEntry*)(p + (size_t)j * (qbytes + 256));
+        qs[i]->count = (int32_t*)(p + (size_t)j * (qbytes + 256) + qbytes);
+        qs[i]->cap = (int32_t)want;
     }
     return PLB_OK;
 }
@@ -900,16 +1004,22 @@ static int mode_queues(PlbContext* c, PlbDeviceBatch* db, bool two) {
 // Launches the whole kernel sequence for one planned chunk of windows on stream st.  `timed` records
 // the per-kernel events of plb_kernel_times (whole-batch launches only).
 static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch, const PlbOptions* opt,
-                          PlbPopulationOut* pop, PlbLoglikOut* llo, cudaStream_t st, bool timed, const Queue& q) {
+                          PlbPopulationOut* pop, PlbLoglikOut* llo, cudaStream_t st, bool timed, const Queue& q,
+                          bool derive = false) {
     int rc;
     DevBatch& d = db->d;
     const int w0 = ch.w0, w1 = ch.w1;
     if (w1 <= w0) return PLB_OK;
+    if (derive) {  // slot -> (window, individual) and haplotype -> window maps of this chunk
+        const int64_t nwi = (int64_t)(w1 - w0) * d.n_individuals;
+        k_derive<<<std::max(1, std::min(4 * c->n_sm, (int)((nwi + 127) / 128))), 128, 0, st>>>(d, w0, w1);
+        if ((rc = launch_check(c, "k_derive"))) return rc;
+    }
     ScoreParams sp{opt->gap_extend, opt->nuc_prior, opt->calc_flank_score, opt->use_mapq_cap};
     const int nInd = d.n_individuals;
     const int h0 = ch.h0, h1 = ch.h1;
     CU(cudaMemsetAsync(d.win_flags + w0, 0, (size_t)(w1 - w0) * 4, st));
-    CU(cudaMemsetAsync(q.count, 0, 4, st));
+    CU(cudaMemsetAsync(q.count, 0, 12, st));   // queue fill + the tile counters of k_anchor and k_dp
     const int tslot = c->n_timed % kTimingRing;
     auto mark = [&](int i) {
         if (timed && c->timing) cudaEventRecord(c->kev[tslot][i], st);
@@ -947,7 +1057,7 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
         const DpPlan& dp = ch.dp;
         if ((rc = opt_in_smem(k_dp<kDpThreads>, ch.d_smem))) return rc;
         const int grid = std::max(1, std::min(dp.n_tiles, c->n_sm * ch.d_occ));
-        k_dp<kDpThreads><<<grid, kDpThreads, ch.d_smem, st>>>(d, dp, sp, ll, sc);
+        k_dp<kDpThreads><<<grid, kDpThreads, ch.d_smem, st>>>(d, dp, sp, ll, sc, q.count + 2);
         if ((rc = launch_check(c, "k_dp"))) return rc;
     }
     mark(4);
@@ -958,13 +1068,22 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
         if ((rc = launch_check(c, "k_genotype"))) return rc;
         mark(5);
         const int Hm = pop->max_haps;
-        int nthr_em = (int)std::min<size_t>(64, std::max<size_t>(1, (size_t)(40 * 1024) / (8 * (size_t)Hm)));
-        nthr_em = std::min(nthr_em, std::max(1, std::max(d.n_individuals, (int)d.max_variants)));
-        const size_t smem = (size_t)(2 + nthr_em) * Hm * 8;
-        if ((rc = opt_in_smem(k_population, smem))) return rc;
-        k_population<<<w1 - w0, 64, smem, st>>>(d, po, db->em_scratch, opt->max_em_iters, opt->use_em_likelihoods,
-                                                nthr_em, w0);
-        if ((rc = launch_check(c, "k_population"))) return rc;
+        const size_t few_smem = (size_t)kPopFewWarps * ((size_t)Hm * (Hm + 1) / 2 + 2 * (size_t)Hm) * 8;
+        if (d.n_individuals <= 8 && few_smem <= (size_t)c->smem_optin - 1024) {
+            // few individuals: a warp per window, lanes across genotypes (a thread per individual would idle)
+            if ((rc = opt_in_smem(k_population_few, few_smem))) return rc;
+            k_population_few<<<(w1 - w0 + kPopFewWarps - 1) / kPopFewWarps, 32 * kPopFewWarps, few_smem, st>>>(
+                d, po, db->em_scratch, opt->max_em_iters, opt->use_em_likelihoods, w0, w1);
+            if ((rc = launch_check(c, "k_population_few"))) return rc;
+        } else {
+            int nthr_em = (int)std::min<size_t>(64, std::max<size_t>(1, (size_t)(40 * 1024) / (8 * (size_t)Hm)));
+            nthr_em = std::min(nthr_em, std::max(1, std::max(d.n_individuals, (int)d.max_variants)));
+            const size_t smem = (size_t)(2 + nthr_em) * Hm * 8;
+            if ((rc = opt_in_smem(k_population, smem))) return rc;
+            k_population<<<w1 - w0, 64, smem, st>>>(d, po, db->em_scratch, opt->max_em_iters, opt->use_em_likelihoods,
+                                                    nthr_em, w0);
+            if ((rc = launch_check(c, "k_population"))) return rc;
+        }
     } else {
         mark(5);
     }
@@ -1126,32 +1245,71 @@ static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* o
     db->chunks.reserve(n_chunks);
     const bool modes = opt->calc_flank_score || opt->use_mapq_cap;
     rc = modes ? mode_queues(c, db, n_chunks > 1) : PLB_OK;
-    if (rc == PLB_OK) rc = copy_meta(c, db, hb, cs);
+    // PLB_TRACE: device timeline of the pipeline (events with timing, created per call)
+    std::vector<cudaEvent_t> tev;
+    std::vector<const char*> ttag;
+    auto tmark_t = [&](cudaStream_t s_, const char* tag) {
+        if (!trace) return;
+        cudaEvent_t ev_;
+        cudaEventCreate(&ev_);
+        cudaEventRecord(ev_, s_);
+        tev.push_back(ev_);
+        ttag.push_back(tag);
+    };
+    auto tmark = [&](cudaStream_t s_) { tmark_t(s_, s_ == cs ? "h2d:" : "k:"); };
+    tmark(cs);
     if (rc == PLB_OK) e = cudaEventRecord(c->ev_chunk[0], cs);
     if (rc == PLB_OK && e == cudaSuccess) e = cudaStreamWaitEvent(st, c->ev_chunk[0], 0);
     if (rc == PLB_OK && e == cudaSuccess) e = cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), st);
     if (rc == PLB_OK && e == cudaSuccess) e = cudaEventRecord(c->ev_s2, st);
     if (rc == PLB_OK && e == cudaSuccess) e = cudaStreamWaitEvent(c->stream2, c->ev_s2, 0);
+    if (rc == PLB_OK && e == cudaSuccess) e = cudaStreamWaitEvent(c->stream3, c->ev_s2, 0);
+    cudaStream_t kstreams[3] = {st, c->stream2, c->stream3};
+    const Queue* kqueues[3] = {modes ? &db->mq : &db->q, modes ? &db->mq2 : &db->q2, modes ? &db->mq3 : &db->q3};
+    // Chunk sizes grow geometrically (x1.3): the first kernels start after a small upload, and because
+    // the kernels need ~1.3x the time of the PCIe transfer of the same windows, chunk k+1 has just
+    // arrived when chunk k finishes.  Sizes are rounded to whole waves of the DP grid (one DP tile
+    // per window in the common case) so that no chunk ends in a nearly empty wave.
+    auto cut = [&](int i) -> int {
+        if (i <= 0) return 0;
+        if (i >= n_chunks) return W;
+        const double r = 1.3;
+        double tot = 0.0, part = 0.0, term = 1.0;
+        for (int j = 0; j < n_chunks; ++j, term *= r) {
+            tot += term;
+            if (j < i) part += term;
+        }
+        int64_t v = (int64_t)((double)W * part / tot);
+        const int64_t wave = (int64_t)c->n_sm * 3;
+        if (W / n_chunks >= 2 * wave) v = std::max<int64_t>(wave, (v + wave / 2) / wave * wave);
+        return (int)std::min<int64_t>(v, W);
+    };
+    // The DMA must never wait for the host: the copies of chunk k+1 are queued BEFORE chunk k is planned,
+    // and once the first chunk is launched all remaining copies are queued at once.
+    int copies_queued = 0;
+    auto queue_copies = [&](int upto) {
+        for (; copies_queued < upto && copies_queued < n_chunks && rc == PLB_OK && e == cudaSuccess; ++copies_queued) {
+            const int a = cut(copies_queued), b2 = cut(copies_queued + 1);
+            if (b2 > a) rc = copy_seq_for_windows(c, db, hb, a, b2, cs);
+            if (rc == PLB_OK) e = cudaEventRecord(c->ev_chunk[1 + copies_queued], cs);
+            tmark(cs);
+        }
+    };
     for (int k = 0; k < n_chunks && rc == PLB_OK && e == cudaSuccess; ++k) {
-        // a small first chunk gets the GPU busy early; the rest are equal
-        auto cut = [&](int i) -> int {
-            if (i <= 0) return 0;
-            if (i >= n_chunks) return W;
-            if (n_chunks < 3) return (int)((int64_t)W * i / n_chunks);
-            const int64_t first = W / (2 * n_chunks);
-            return (int)(first + (int64_t)(W - first) * (i - 1) / (n_chunks - 1));
-        };
+        queue_copies(k == 0 ? 2 : n_chunks);
+        if (rc != PLB_OK || e != cudaSuccess) break;
         const int w0 = cut(k), w1 = cut(k + 1);
-        // bytes first (DMA runs while the host plans the chunk's tiles), then the tile lists
-        if ((rc = copy_seq_for_windows(db, hb, w0, w1, cs))) break;
-        if ((rc = plan_chunk(c, db, hb, w0, w1, cs))) break;
-        kst = (k & 1) ? c->stream2 : st;
-        e = cudaEventRecord(c->ev_chunk[1 + k], cs);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(kst, c->ev_chunk[1 + k], 0);
+        if (w1 <= w0) continue;
+        kst = kstreams[k % 3];
+        // tile lists are read from pinned host memory (a small H2D copy would wait behind the sequence bytes)
+        if ((rc = plan_chunk(c, db, hb, w0, w1, kst, true))) break;
+        e = cudaStreamWaitEvent(kst, c->ev_chunk[1 + k], 0);
         if (e != cudaSuccess) break;
+        tmark(kst);
         if ((rc = launch_windows(c, db, db->chunks.back(), opt, hpop ? &dpop : nullptr, &dll, kst, false,
-                                 modes ? ((k & 1) ? db->mq2 : db->mq) : ((k & 1) ? db->q2 : db->q))))
+                                 *kqueues[k % 3], true)))
             break;
+        tmark(kst);
         if (hpop) {
             const size_t wq = (size_t)w0, wn = (size_t)(w1 - w0);
             d2h(hpop->gl, dpop.gl, wq * nInd * Gm * 8, wn * nInd * Gm * 8);
@@ -1167,16 +1325,30 @@ static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* o
         const int64_t p0 = db->h_ll_off[(size_t)w0 * nInd], p1 = db->h_ll_off[(size_t)w1 * nInd];
         if (want_ll) d2h(hll->ll, dll.ll, (size_t)p0 * 8, (size_t)(p1 - p0) * 8);
         if (want_sc) d2h(hll->score, dll.score, (size_t)p0 * 4, (size_t)(p1 - p0) * 4);
+        tmark(kst);
     }
     // join the second compute stream into the first, then fetch the counters
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_s2, c->stream2);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(st, c->ev_s2, 0);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_s3, c->stream3);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, c->ev_s3, 0);
     if (rc == PLB_OK && e == cudaSuccess)
         e = cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st);
     const double t_issue = now_ms();
     cudaError_t e2 = cudaStreamSynchronize(cs);
     const double t_copy = now_ms();
     cudaError_t e3 = cudaStreamSynchronize(st);
+    if (trace && !tev.empty()) {
+        // events in issue order; copy-stream marks are tagged by position: print all as ms after the first
+        fprintf(stderr, "[plb] timeline (ms):");
+        for (size_t i = 1; i < tev.size(); ++i) {
+            float t = 0;
+            cudaEventElapsedTime(&t, tev[0], tev[i]);
+            fprintf(stderr, " %s%.2f", ttag[i], t);
+        }
+        fprintf(stderr, "\n");
+        for (cudaEvent_t ev_ : tev) cudaEventDestroy(ev_);
+    }
     if (trace)
         fprintf(stderr, "[plb] run_host: prepare %.2f ms, issue %.2f ms, copy-stream drain +%.2f ms, compute drain +%.2f ms (%d chunks)\n",
                 t_prep - t_start, t_issue - t_prep, t_copy - t_issue, now_ms() - t_copy, n_chunks);

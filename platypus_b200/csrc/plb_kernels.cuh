@@ -29,6 +29,8 @@ constexpr double kMLTOT = -0.23025850929940459;
 constexpr double kLog10E = 0.43429448190325182;
 constexpr double kLogHalf = -0.69314718055994529;
 constexpr u32 kTabEmpty = 0xFFFFFFFFu;
+constexpr int kRankWords = kHashSize / 32;            // one presence bit per possible 7-mer key
+constexpr size_t kRankTabBytes = kRankWords * 8;      // uint2 {bits, number of set bits in earlier words}
 
 // ---- device view of a batch (all pointers are device pointers) --------------------------------
 struct DevBatch {
@@ -235,7 +237,7 @@ struct AnchorPlan {
 // host + device: lays out the shared memory of k_anchor from the plan's element counts
 inline void anchor_layout(AnchorPlan& ap, size_t slot_bytes) {
     auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    size_t o = (size_t)4 << ap.tab_bits;
+    size_t o = kRankTabBytes;   // 7-mer key -> dense id: 512 x {presence bits, rank prefix}
     ap.o_cnt = (uint32_t)o;    o = al(o + (size_t)ap.n_cnt * ap.cnt_words * 4);
     ap.o_fb = (uint32_t)o;     o = al(o + (size_t)ap.max_pairs * 4);
     ap.o_vl = (uint32_t)o;     o = al(o + (size_t)ap.max_pairs * 12);
@@ -255,6 +257,7 @@ struct SlotInfo {
     int32_t pos;      // read.pos
     int32_t flags;    // bit0 = LL forced to 0 (QC fail / overlap < 7)
     int32_t vub;      // upper bound of the votes this read can cast on any haplotype of the sub-group
+    int32_t lph;      // light | heavy << 16: read 7-mers whose id occurs once / more than once in a haplotype
     int32_t poff;     // offset (u32 words) of the 2-bit packed read
     int32_t T;        // reads of this (window, individual): stride between haplotype rows of the LL block
     int64_t pair0;    // LL index of (first haplotype of the window, this slot)
@@ -319,21 +322,47 @@ struct Emitter {
     }
 };
 
+// 2-bit codes (calign.pyx:69-74) of the 16 bases seq[i0 .. i0+15], base i0+k at bits 2k; positions
+// outside [0, len) give 0.  i0 is a multiple of 16.  Reads five aligned 32-bit words (the arrays are
+// padded by 64 bytes) and converts four bases at a time:
+//   c = byte & 7;  code = (c & 3) ^ (c == 7)      (A->1, C->3, G->2, T->0, N->2: 7 -> 2)
+//   four 2-bit codes of a word gathered into one byte by a multiply (no two partial products overlap)
+__device__ __forceinline__ u32 pack16_codes(const uint8_t* __restrict__ seq, int i0, int len) {
+    if (i0 < 0 || i0 >= len) return 0u;
+    const uintptr_t a = (uintptr_t)(seq + i0);
+    const u32* wp = (const u32*)(a & ~(uintptr_t)3);
+    const int sh = 8 * (int)(a & 3);
+    u32 w[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w[k] = __ldg(wp + k);
+    u32 v = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const u32 x = __funnelshift_r(w[k], w[k + 1], sh) & 0x07070707u;
+        const u32 is7 = ((x + 0x01010101u) >> 3) & 0x01010101u;
+        const u32 code = (x & 0x03030303u) ^ is7;
+        v |= ((code * 0x01041040u) >> 24) << (8 * k);
+    }
+    const int n = len - i0;
+    if (n < 16) v &= (1u << (2 * n)) - 1u;
+    return v;
+}
+
 // 7-mer key of position p of a packed sequence: its 14 bits, first base in the low bits (a
 // digit-reversed copy of the reference's hash - any bijection of the hash gives the same votes)
 __device__ __forceinline__ u32 key_at(const u32* pk, int p) {
     return fsr(pk[p >> 4], pk[(p >> 4) + 1], 2 * (p & 15)) & 0x3FFFu;
 }
 
+// key -> dense id (1..U) over the union of the group's haplotype 7-mers, 0 when absent.  The table is a
+// 16384-bit presence map with a rank directory: id = (set bits before the key) + 1.  One LDS.64, a
+// popcount and no probing; built with atomicOr + one 512-entry scan (no CAS loops).
 __device__ __forceinline__ u32 tab_lookup(const u32* tab, int bits, u32 key) {
-    const u32 mask = (1u << bits) - 1;
-    u32 slot = tab_slot0(key, bits) & mask;
-    while (true) {
-        const u32 e = tab[slot];
-        if (e == kTabEmpty) return 0;
-        if ((e >> 16) == key) return e & 0xFFFFu;
-        slot = (slot + 1) & mask;
-    }
+    (void)bits;
+    const uint2 e = ((const uint2*)tab)[key >> 5];
+    const u32 bit = key & 31u;
+    const u32 below = e.x & ((1u << bit) - 1u);
+    return ((e.x >> bit) & 1u) ? e.y + (u32)__popc(below) + 1u : 0u;
 }
 
 // Decides a pair without a vote array when it can.  Guesses: the offsets implied by the first, the
@@ -350,6 +379,7 @@ constexpr int kPairUndecided = 0x40000002;  // goes to the exact vote array
 struct LightArgs {
     u32 head_off, rpk_off, hpk_off, res_off;
     int nk_read, nk_hap, vub, bits;
+    int lp, hh;   // read 7-mers that vote exactly once (light) / possibly several times (heavy)
 };
 
 // offset implied by the first read 7-mer in [i0, i1) (walking by step) that occurs exactly once in
@@ -375,26 +405,58 @@ __device__ __noinline__ int light_decide(LightArgs a) {
         res[0] = res[1] = res[2] = (u32)kNoCand;
         return 1;
     }
+    // Guesses are generated lazily: read 7-mers near the start, the end, the middle, then the quarters and
+    // eighths (reads that differ from the haplotype by several indels split their votes over several
+    // offsets; each extra exact count is ~100x cheaper than the warp-wide vote array).
     const int lim = min(nk, 24);
-    int g[3], c[3] = {0, 0, 0};
-    g[0] = unique_hit_offset(tab, a.bits, head, rpk, 0, lim, 1);
-    g[1] = unique_hit_offset(tab, a.bits, head, rpk, nk - 1, nk - 1 - lim, -1);
-    const int mid = nk >> 1;
-    g[2] = unique_hit_offset(tab, a.bits, head, rpk, mid, min(nk, mid + lim), 1);
-    if (g[1] == g[0]) g[1] = kNoCand;
-    if (g[2] == g[0] || g[2] == g[1]) g[2] = kNoCand;
-    int R = a.vub, top = 0;
+    constexpr int NG = 7;
+    int g[NG], c[NG];
+    // Two bounds on the votes of any offset not counted yet:
+    //   R  = (all votes the read can cast) - (votes counted so far)
+    //   R2 = heavy + (light - light votes counted so far): every read 7-mer gives an offset at most ONE vote,
+    //        light 7-mers vote exactly once in total, and a counted offset with c votes holds at least
+    //        c - heavy light ones.  R2 is what decides reads over long homopolymers, whose repeated 7-mer
+    //        sprays hundreds of votes over neighbouring offsets.
+    int R = a.vub, top = 0, R2 = a.hh + a.lp;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        if (g[j] == kNoCand) continue;
-        c[j] = count_offset_bits(rpk, hpk, nk, a.nk_hap, g[j]);
+    for (int j = 0; j < NG; ++j) {
+        int i0, i1, step = 1;
+        if (j == 1) {
+            i0 = nk - 1;
+            i1 = nk - 1 - lim;
+            step = -1;
+        } else {
+            // j = 0: start; 2: middle; 3, 4: quarters; 5, 6: eighths next to the ends
+            const int num = j == 0 ? 0 : j == 2 ? 4 : j == 3 ? 2 : j == 4 ? 6 : j == 5 ? 1 : 7;
+            i0 = (nk * num) >> 3;
+            i1 = min(nk, i0 + lim);
+        }
+        g[j] = kNoCand;
+        c[j] = 0;
+        if (top > min(R, R2)) continue;        // already decided
+        const int gj = unique_hit_offset(tab, a.bits, head, rpk, i0, i1, step);
+        bool dup = gj == kNoCand;
+#pragma unroll
+        for (int k = 0; k < NG; ++k)
+            if (k < j && g[k] == gj) dup = true;
+        if (dup) continue;
+        g[j] = gj;
+        c[j] = count_offset_bits(rpk, hpk, nk, a.nk_hap, gj);
         R -= c[j];
+        R2 -= max(0, c[j] - a.hh);
         top = max(top, c[j]);
-        if (top > R) break;
     }
-    if (!(top > R) || top == 0) return 0;
+    if (!(top > min(R, R2)) || top == 0) return 0;
+    int nt = 0;
+    res[0] = res[1] = res[2] = (u32)kNoCand;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) res[j] = (u32)((g[j] != kNoCand && c[j] == top) ? g[j] + 1 : kNoCand);
+    for (int j = 0; j < NG; ++j)
+        if (g[j] != kNoCand && c[j] == top) {
+            if (nt < 3) res[nt] = (u32)(g[j] + 1);
+            ++nt;
+        }
+    if (nt > 3) return 0;   // more tied maxima than the result holds: exact path
+    // (the order of the tied offsets is irrelevant: the score is a min over the set, calign.pyx:239-247)
     return 1;
 }
 
@@ -421,13 +483,29 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
     __shared__ int s_nid, s_nfb, s_scan[kAnchorThreads / 32];
 
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-    const int bits = plan.tab_bits;
-    const int S = 1 << bits;
-    unsigned long long st_pairs = 0, st_scored = 0, st_dp = 0, st_cells = 0;
+    const int bits = 0;   // (the rank table needs no size parameter)
+    unsigned long long st_pairs = 0, st_scored = 0, st_dp = 0, st_cells = 0, t_tile0 = 0;
+    int w_prev = 0;
+    __shared__ int s_tile;
 
-    for (int ti = blockIdx.x; ti < plan.n_tiles; ti += gridDim.x) {
+    // Tiles are handed out through a counter (q.count[1]), not by block index: when this kernel shares the
+    // GPU with another chunk's kernels not all of its CTAs are resident at once, and a static split would
+    // leave the late CTAs' share for the end.
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(q.count + 1, 1);
+        __syncthreads();
+        const int ti = s_tile;
+        if (tid == 0 && ctr) {   // longest tile so far, in microseconds (diagnostic: PlbRunStats.n_anchor_verify)
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t_tile0) atomicMax(&ctr->n_verify, (((now - t_tile0) / 1000ull) << 32) | (unsigned)w_prev);
+            t_tile0 = now;
+        }
+        if (ti >= plan.n_tiles) break;
         const Tile tile = plan.tiles[ti];
         const int w = tile.w;
+        w_prev = w;
         const int nh = tile.h1 - tile.h0;
         const int ns = (int)(tile.s1 - tile.s0);
         __syncthreads();
@@ -444,7 +522,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             }
             s_nfb = 0;
         }
-        for (int i = tid; i < S; i += nthr) s_tab[i] = kTabEmpty;
+        for (int i = tid; i < kRankWords; i += nthr) ((uint2*)s_tab)[i] = make_uint2(0u, 0u);
         // slot metadata + skip rule (chaplotype.pyx:343-361)
         for (int s = tid; s < ns; s += nthr) {
             const int64_t gs = tile.s0 + s;
@@ -461,6 +539,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 if (b.read_qcfail[r] || ov < kKmer) si.flags = 1;
             }
             si.vub = 0;
+            si.lph = 0;
             si.poff = 0;
             si.T = (int)(b.wi_slot_off[wi + 1] - b.wi_slot_off[wi]);
             si.pair0 = b.ll_off[wi] + t;
@@ -492,60 +571,33 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             if ((si.flags & 1) || si.len <= kKmer) continue;
             const uint8_t* rs = b.read_seq + b.read_seq_off[si.read];
             const int nw = ((si.len + 15) >> 4) + kPackPadWords;
-            for (int wd = lane; wd < nw; wd += 32) {
-                u32 v = 0;
-                const int i0 = 16 * wd;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {  // 16 independent predicated byte loads
-                    const int i = i0 + k;
-                    const uint8_t ch = i < si.len ? rs[i] : (uint8_t)0;
-                    v |= (i < si.len ? kmer_base_code(ch) : 0u) << (2 * k);
-                }
-                s_rpk[si.poff + wd] = v;
-            }
+            for (int wd = lane; wd < nw; wd += 32) s_rpk[si.poff + wd] = pack16_codes(rs, 16 * wd, si.len);
         }
         for (int g = 0; g < nh; ++g) {
             const int len = s_hmeta[3 * g];
             const uint8_t* hap = b.hap_seq + b.hap_seq_off[tile.h0 + g];
             u32* dst = s_hpk + s_hmeta[3 * g + 2] - kPackPadWords;
             const int nw = ((len + 15) >> 4) + 2 * kPackPadWords;
-            for (int wd = tid; wd < nw; wd += nthr) {
-                u32 v = 0;
-                const int i0 = 16 * (wd - kPackPadWords);
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int i = i0 + k;
-                    const bool in = i >= 0 && i < len;
-                    const uint8_t ch = in ? hap[i] : (uint8_t)0;
-                    v |= (in ? kmer_base_code(ch) : 0u) << (2 * k);
-                }
-                dst[wd] = v;
-            }
+            for (int wd = tid; wd < nw; wd += nthr) dst[wd] = pack16_codes(hap, 16 * (wd - kPackPadWords), len);
         }
         __syncthreads();
-        // ---- union table: insert the key of every indexed haplotype position
+        // ---- union table: mark the key of every indexed haplotype position
         //      (calign.pyx:109: positions 0 .. len-8) ----
         for (int g = 0; g < nh; ++g) {
             const int nkh = s_hmeta[3 * g] - kKmer;
             const u32* hpk = s_hpk + s_hmeta[3 * g + 2];
             for (int i = tid; i < nkh; i += nthr) {
                 const u32 key = key_at(hpk, i);
-                const u32 mask = (1u << bits) - 1;
-                u32 slot = tab_slot0(key, bits) & mask;
-                while (true) {
-                    const u32 old = atomicCAS(&s_tab[slot], kTabEmpty, key << 16);
-                    if (old == kTabEmpty || (old >> 16) == key) break;
-                    slot = (slot + 1) & mask;
-                }
+                atomicOr(&s_tab[2 * (key >> 5)], 1u << (key & 31u));
             }
         }
         __syncthreads();
-        // ---- dense ids 1..U for the occupied slots (block-wide exclusive scan) ----
+        // ---- rank directory: exclusive prefix of the popcounts (block-wide scan over 512 words) ----
         {
-            const int per = (S + nthr - 1) / nthr;
-            const int lo = tid * per, hi = min(S, lo + per);
+            const int per = (kRankWords + nthr - 1) / nthr;
+            const int lo = tid * per, hi = min(kRankWords, lo + per);
             int cnt = 0;
-            for (int i = lo; i < hi; ++i) cnt += (s_tab[i] != kTabEmpty);
+            for (int i = lo; i < hi; ++i) cnt += __popc(s_tab[2 * i]);
             int incl = cnt;
             for (int o = 1; o < 32; o <<= 1) {
                 const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -556,9 +608,11 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             int base = 0;
             for (int k = 0; k < warp; ++k) base += s_scan[k];
             if (tid == nthr - 1) s_nid = base + incl;
-            int id = base + incl - cnt;
-            for (int i = lo; i < hi; ++i)
-                if (s_tab[i] != kTabEmpty) s_tab[i] = (s_tab[i] & 0xFFFF0000u) | (u32)(++id);
+            int run = base + incl - cnt;
+            for (int i = lo; i < hi; ++i) {
+                s_tab[2 * i + 1] = (u32)run;
+                run += __popc(s_tab[2 * i]);
+            }
         }
         __syncthreads();
         const int U = s_nid;  // number of distinct 7-mers in this haplotype group
@@ -613,11 +667,21 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 const SlotInfo si = s_slot[s];
                 const int nk = si.len - kKmer;
                 if ((si.flags & 1) || nk <= 0) continue;
-                int sum = 0;
+                int sum = 0, lh = 0;   // lh: light count | heavy count << 16
                 const u32* rpk = s_rpk + si.poff;   // read 7-mers 0..len-8 (calign.pyx:155-165)
-                for (int i = lane; i < nk; i += 32) sum += s_mult[tab_lookup(s_tab, bits, key_at(rpk, i))];
-                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-                if (lane == 0) s_slot[s].vub = sum;
+                for (int i = lane; i < nk; i += 32) {
+                    const int m = s_mult[tab_lookup(s_tab, bits, key_at(rpk, i))];
+                    sum += m;
+                    lh += (m == 1) + ((m > 1) << 16);
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+                    lh += __shfl_xor_sync(0xFFFFFFFFu, lh, o);
+                }
+                if (lane == 0) {
+                    s_slot[s].vub = sum;
+                    s_slot[s].lph = lh;
+                }
             }
             __syncthreads();
             // ---- per (slot, haplotype) pair: light decision, else exact vote array ----
@@ -659,6 +723,8 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 la.nk_read = pc.L - kKmer;   // HLA mode: 7-mers 0..L'-8 of the UNCLIPPED read vote
                 la.nk_hap = s_hmeta[3 * g] - kKmer;
                 la.vub = si.vub;
+                la.lp = si.lph & 0xFFFF;
+                la.hh = si.lph >> 16;
                 la.bits = bits;
                 if (!light_decide(la)) {
                     s_vlist[3 * p] = (u32)kPairUndecided;
@@ -708,7 +774,10 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             __syncthreads();
             // ---- undecided pairs: exact vote array per warp (calign.pyx:206-247) ----
             const int nfb = s_nfb;
-            if (tid == 0 && ctr) atomicAdd(&ctr->n_exact, (unsigned long long)nfb);
+            if (tid == 0 && ctr) {
+                atomicAdd(&ctr->n_exact, (unsigned long long)nfb);
+                if (nfb >= 64) atomicAdd(&ctr->n_heavy, 1ull);   // tiles with many exact-path pairs
+            }
             const int n_fbw = min(nwarp, plan.n_cnt);  // warps that own a counter array
             for (int f = warp; f < nfb && warp < n_fbw; f += n_fbw) {
                 const int p = (int)s_fblist[f];
@@ -890,7 +959,7 @@ struct DpSlot {
 
 template <int NTHR>
 __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParams sp, double* __restrict__ ll_out,
-                                             int32_t* __restrict__ score_out) {
+                                             int32_t* __restrict__ score_out, int* __restrict__ tile_counter) {
     extern __shared__ __align__(16) uint8_t smem[];
     u32* s_prof = (u32*)smem;
     HapRec* s_rec = (HapRec*)(s_prof + plan.prof_words);
@@ -906,12 +975,17 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
     if (tid == 0) mbar_init(&s_bar, NTHR);
     u32 bar_phase = 0;
     __syncthreads();
-    for (int ti = blockIdx.x; ti < plan.n_tiles; ti += gridDim.x) {
+    __shared__ int s_tile;
+    while (true) {   // dynamic tile hand-out, see k_anchor
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(tile_counter, 1);
+        __syncthreads();
+        const int ti = s_tile;
+        if (ti >= plan.n_tiles) break;
         const Tile tile = plan.tiles[ti];
         const int w = tile.w;
         const int nh = tile.h1 - tile.h0;
         const int ns = (int)(tile.s1 - tile.s0);
-        __syncthreads();
         if (tid == 0) {
             s_ntask = 0;
             int ro = 0;
@@ -1051,12 +1125,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                     for (int k = 0; k < 6; ++k) {
                         const int y = lane + 32 * k;
                         if (y < n) {
-                            u32 v = 0u;
-                            if (y < ds.len) {
-                                const int code = fast_code(cb[k]);
-                                v = six ? make_profile6(code, qb[k], K) : make_profile(code, qb[k]);
-                            }
-                            row[y] = v;
+                            row[y] = y < ds.len ? profile_from_byte(cb[k], qb[k], K, six) : 0u;
                         }
                     }
                     continue;
@@ -1075,12 +1144,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                     for (int k = 0; k < 6; ++k) {
                         const int y = y0 + lane + 32 * k;
                         if (y < n) {
-                            u32 v = 0u;
-                            if (y < ds.len) {
-                                const int code = fast_code(cb[k]);
-                                v = six ? make_profile6(code, qb[k], K) : make_profile(code, qb[k]);
-                            }
-                            row[y] = v;
+                            row[y] = y < ds.len ? profile_from_byte(cb[k], qb[k], K, six) : 0u;
                         }
                     }
                 }
@@ -1186,6 +1250,23 @@ __device__ __forceinline__ void genotype_pair(int g, int H, int& h1, int& h2) {
     h2 = i + rem;
 }
 
+// The per-read mixture has four branches (cgenotype.pyx:164-180); only the last one needs exp/log and
+// it is rare, but with one thread per genotype a warp pays for it whenever ANY of its lanes takes it.
+// So the (genotype, read) pairs that need it are first listed (count -> prefix -> fill), evaluated
+// densely by all threads, and the ordered per-genotype sums then pick the finished terms up in read
+// order - every sum adds the same values in the same order as the reference.
+constexpr int kMidCap = 512;    // listed terms per round of 64 genotypes; overflow is computed in place
+
+__device__ __forceinline__ double mix_mid(double a, double c) { return log(0.5 * (exp(a) + exp(c))); }
+// 0 = homozygous or |a-c| <= 1e-3 (term a), 1 = |a-c| >= 3 (log(1/2) + max), 2 = full mixture
+__device__ __forceinline__ int mix_class(bool hom, double a, double c) {
+    if (hom) return 0;
+    const double d = fabs(a - c);
+    if (d >= 3) return 1;
+    if (d <= 1e-3) return 0;
+    return 2;
+}
+
 __global__ void __launch_bounds__(64) k_genotype(DevBatch b, const double* __restrict__ ll, PopOut out, int wi_base) {
     const int wi = wi_base + blockIdx.x;
     const int nInd = b.n_individuals;
@@ -1198,38 +1279,75 @@ __global__ void __launch_bounds__(64) k_genotype(DevBatch b, const double* __res
     const double* L = ll + b.ll_off[wi];
     double* gl = out.gl + ((size_t)w * nInd + i) * Gmax;
     __shared__ double s_max[64];
+    __shared__ double s_mid[kMidCap];
+    __shared__ uint32_t s_ent[kMidCap];    // genotype (local to the round) << 16 | read... as two u16 when T < 65536
+    __shared__ int s_off[65];
     const int tid = threadIdx.x;
 
     double mymax = -1e7;  // cpopulation.pyx:288
-    for (int g = tid; g < G; g += 64) {
-        int h1, h2;
-        genotype_pair(g, H, h1, h2);
-        double v = 1.0, gof = 0.0;
-        if (ngood != 0) {
-            const double* a1 = L + (size_t)h1 * T;
-            const double* a2 = L + (size_t)h2 * T;
-            double like = 0.0, gsum = 0.0;
-            const bool hom = (h1 == h2);
-            for (int t = 0; t < T; ++t) {  // cgenotype.pyx:151-180
-                const double a = a1[t], c = a2[t];
-                const double la = kLog10E * a, lc = kLog10E * c;
-                gsum += la > lc ? la : lc;
-                if (hom) {
-                    like += a;
-                } else if (fabs(a - c) >= 3) {
-                    like += (kLogHalf + (a > c ? a : c));
-                } else if (fabs(a - c) <= 1e-3) {
-                    like += a;
-                } else {
-                    like += log(0.5 * (exp(a) + exp(c)));
-                }
-            }
-            v = like;
-            gof = (-10 * gsum) / ngood;  // cgenotype.pyx:182-183
-            if (v > mymax) mymax = v;
+    for (int g0 = 0; g0 < G; g0 += 64) {   // rounds of 64 genotypes (uniform trip count)
+        const int g = g0 + tid;
+        int h1 = 0, h2 = 0;
+        const bool act = g < G && ngood != 0;
+        if (g < G) genotype_pair(g, H, h1, h2);
+        const double* a1 = L + (size_t)h1 * T;
+        const double* a2 = L + (size_t)h2 * T;
+        const bool hom = (h1 == h2);
+        // pass 1: how many full-mixture terms does this genotype have
+        int n_mid = 0;
+        if (act && !hom)
+            for (int t = 0; t < T; ++t) n_mid += (mix_class(false, a1[t], a2[t]) == 2);
+        __syncthreads();   // previous round's readers of s_off / s_mid are done
+        s_off[tid + 1] = n_mid;
+        if (tid == 0) s_off[0] = 0;
+        __syncthreads();
+        if (tid == 0)
+            for (int k = 1; k <= 64; ++k) s_off[k] += s_off[k - 1];
+        __syncthreads();
+        const int off = s_off[tid], total = min(s_off[64], kMidCap);
+        // pass 2: list them (read order inside a genotype)
+        if (n_mid > 0) {
+            int k = off;
+            for (int t = 0; t < T && k < kMidCap; ++t)
+                if (mix_class(false, a1[t], a2[t]) == 2) s_ent[k++] = ((uint32_t)tid << 24) | (uint32_t)t;
         }
-        gl[g] = v;
-        if (out.gof) out.gof[((size_t)w * Gmax + g) * nInd + i] = gof;
+        __syncthreads();
+        // pass 3: all threads evaluate the listed terms
+        for (int e = tid; e < total; e += 64) {
+            const uint32_t en = s_ent[e];
+            int e1, e2;
+            genotype_pair(g0 + (int)(en >> 24), H, e1, e2);
+            const int t = (int)(en & 0xFFFFFFu);
+            s_mid[e] = mix_mid(L[(size_t)e1 * T + t], L[(size_t)e2 * T + t]);
+        }
+        __syncthreads();
+        // pass 4: the ordered sums (cgenotype.pyx:151-180)
+        if (g < G) {
+            double v = 1.0, gof = 0.0;
+            if (ngood != 0) {
+                double like = 0.0, gsum = 0.0;
+                int k = off;
+                for (int t = 0; t < T; ++t) {
+                    const double a = a1[t], c = a2[t];
+                    const double la = kLog10E * a, lc = kLog10E * c;
+                    gsum += la > lc ? la : lc;
+                    const int cls = mix_class(hom, a, c);
+                    if (cls == 0) {
+                        like += a;
+                    } else if (cls == 1) {
+                        like += (kLogHalf + (a > c ? a : c));
+                    } else {
+                        like += (k < kMidCap) ? s_mid[k] : mix_mid(a, c);
+                        ++k;
+                    }
+                }
+                v = like;
+                gof = (-10 * gsum) / ngood;  // cgenotype.pyx:182-183
+                if (v > mymax) mymax = v;
+            }
+            gl[g] = v;
+            if (out.gof) out.gof[((size_t)w * Gmax + g) * nInd + i] = gof;
+        }
     }
     for (int g = G + tid; g < Gmax; g += 64) {
         gl[g] = 0.0;
@@ -1413,6 +1531,167 @@ __global__ void __launch_bounds__(64) k_population(DevBatch b, PopOut out, doubl
                 }
                 out.var_phred[(size_t)w * b.max_variants + v] = ph;
             }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// k_population_few: same model as k_population for batches with FEW individuals, where a thread per
+// individual leaves the GPU idle.  One WARP per window; inside an individual the lanes work across
+// genotypes / haplotypes, and every floating-point sum still runs in the reference's order:
+//   * csr[g] = GL * f_s * f_r * (1 + [r != s])        lanes over g (independent products)
+//   * sum over g                                        lane 0, ascending g        (cpopulation.pyx:420-427)
+//   * csr[g] /= sum                                     lanes over g
+//   * newFreq[k] += csr[g] for g containing k           lane k, ascending g, twice when homozygous
+//                                                       (cpopulation.pyx:431-440: part[s] += v; part[r] += v)
+// Individuals are visited in order, so newFreq accumulates exactly as in the reference.
+// Shared memory per warp: Gmax doubles (csr) + 2*Hmax doubles.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPopFewWarps = 4;
+
+__global__ void __launch_bounds__(32 * kPopFewWarps) k_population_few(DevBatch b, PopOut out, double* __restrict__ em_scratch,
+                                                                  int max_iters, int use_em, int w_base, int w_end) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = w_base + blockIdx.x * kPopFewWarps + warp;
+    if (w >= w_end) return;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int nInd = b.n_individuals;
+    const int H = b.win_hap_off[w + 1] - b.win_hap_off[w];
+    const int G = H * (H + 1) / 2;
+    const int Hmax = out.max_haps, Gmax = Hmax * (Hmax + 1) / 2;
+    double* s_csr = (double*)smem + (size_t)warp * (Gmax + 2 * Hmax);
+    double* s_freq = s_csr + Gmax;
+    double* s_new = s_freq + Hmax;
+    const double* gl = out.gl + (size_t)w * nInd * Gmax;
+    double* emp = (out.em_post ? out.em_post : em_scratch) + (size_t)w * nInd * Gmax;
+    const int32_t* ngood = b.wi_n_good + (size_t)w * nInd;
+
+    const double eps = fmin(1e-3, 1.0 / (nInd * 2 * 2));  // cpopulation.pyx:684
+    for (int k = lane; k < Hmax; k += 32) s_freq[k] = k < H ? 1.0 / H : 0.0;
+    for (int i = 0; i < nInd; ++i) {
+        if (ngood[i] == 0)
+            for (int g = lane; g < Gmax; g += 32) emp[(size_t)i * Gmax + g] = 0.0;
+        for (int g = G + lane; g < Gmax; g += 32) emp[(size_t)i * Gmax + g] = 0.0;
+    }
+    __syncwarp();
+    double change = eps + 1;
+    int iters = 0;
+    while (change > eps && iters < max_iters) {
+        for (int k = lane; k < H; k += 32) s_new[k] = 0.0;
+        int n_with = 0;
+        for (int i = 0; i < nInd; ++i) {
+            if (ngood[i] == 0) continue;
+            ++n_with;
+            const double* gli = gl + (size_t)i * Gmax;
+            double* csr = emp + (size_t)i * Gmax;
+            __syncwarp();
+            for (int g = lane; g < G; g += 32) {
+                int sI, rI;
+                genotype_pair(g, H, sI, rI);
+                s_csr[g] = gli[g] * s_freq[sI] * s_freq[rI] * (1 + (rI != sI));
+            }
+            __syncwarp();
+            double sum = 0.0;
+            if (lane == 0)
+                for (int g = 0; g < G; ++g) sum += s_csr[g];
+            sum = __shfl_sync(FULL, sum, 0);
+            for (int g = lane; g < G; g += 32) {
+                double v = s_csr[g];
+                if (sum > 0.0) v /= sum;
+                s_csr[g] = v;
+                csr[g] = v;
+            }
+            __syncwarp();
+            for (int k = lane; k < H; k += 32) {   // haplotype k: its genotypes in ascending g
+                double acc = s_new[k];
+                int g = 0;
+                for (int sI = 0; sI < H; ++sI)
+                    for (int rI = sI; rI < H; ++rI, ++g) {
+                        if (sI == k) acc += s_csr[g];
+                        if (rI == k) acc += s_csr[g];
+                    }
+                s_new[k] = acc;
+            }
+        }
+        __syncwarp();
+        double mych = 0.0;
+        for (int k = lane; k < H; k += 32) {
+            double nf = s_new[k];
+            if (n_with > 0) nf = nf / (2 * n_with); else nf = s_freq[k];
+            const double ch = fabs(s_freq[k] - nf);
+            if (ch > mych) mych = ch;
+            s_new[k] = nf;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(FULL, mych, o);
+            mych = other > mych ? other : mych;
+        }
+        __syncwarp();
+        for (int k = lane; k < H; k += 32) s_freq[k] = s_new[k];
+        __syncwarp();
+        change = mych;
+        ++iters;
+    }
+    if (out.freq)
+        for (int k = lane; k < Hmax; k += 32) out.freq[(size_t)w * Hmax + k] = s_freq[k];
+    if (lane == 0 && out.em_iters) out.em_iters[w] = iters;
+    // callGenotypes, cpopulation.pyx:623-676: first strict maximum
+    if (out.call) {
+        for (int i = lane; i < nInd; i += 32) {
+            int bestg = -1;
+            double bestv = 0.0;
+            if (ngood[i] != 0) {
+                const double* src = (use_em == 1 ? emp : gl) + (size_t)i * Gmax;
+                for (int g = 0; g < G; ++g)
+                    if (bestg == -1 || src[g] > bestv) {
+                        bestv = src[g];
+                        bestg = g;
+                    }
+            }
+            out.call[(size_t)w * nInd + i] = bestg;
+        }
+    }
+    // calculatePosterior, cpopulation.pyx:459-594: one lane per variant, genotypes in order
+    if (out.var_phred && b.max_variants > 0 && b.win_n_var) {
+        const int nvar = b.win_n_var[w];
+        const uint64_t* masks = b.hap_var_mask + b.win_hap_off[w];
+        __syncwarp();
+        for (int v = lane; v < b.max_variants; v += 32) {
+            double ph = 0.0;
+            if (v < nvar) {
+                double sumf = 0.0;
+                for (int k = 0; k < H; ++k)
+                    if (!((masks[k] >> v) & 1ull)) sumf += s_freq[k];
+                auto fp = [&](int k) -> double {   // frequencies with the variant's haplotypes removed, renormalised
+                    if ((masks[k] >> v) & 1ull) return 0.0;
+                    return sumf > 0 ? s_freq[k] / sumf : s_freq[k];
+                };
+                double slv = 0.0, sln = 0.0;
+                for (int i = 0; i < nInd; ++i) {
+                    if (ngood[i] == 0) continue;
+                    const double* gli = gl + (size_t)i * Gmax;
+                    double pv = 0.0, pn = 0.0;
+                    int g = 0;
+                    for (int r = 0; r < H; ++r) {
+                        const double fr = fp(r);
+                        for (int sI = r; sI < H; ++sI, ++g) {
+                            const double l = gli[g];
+                            const double factor = (r != sI) ? 2.0 : 1.0;
+                            pv += (factor * s_freq[r] * s_freq[sI] * l);
+                            pn += (factor * fr * fp(sI) * l);
+                        }
+                    }
+                    slv += pv > 0 ? log(pv) : -708.0;
+                    sln += pn > 0 ? log(pn) : -708.0;
+                }
+                double ratio = exp(sln - slv);
+                if (!(ratio > 1e-300)) ratio = 1e-300;
+                const double prior = b.var_prior[(size_t)w * b.max_variants + v];
+                ph = round(-10.0 * (log10(ratio * (1.0 - prior)) - log10(prior + ratio * (1.0 - prior))));
+            }
+            out.var_phred[(size_t)w * b.max_variants + v] = ph;
         }
     }
 }
