@@ -514,6 +514,12 @@ static int plan_tiles(const PlbWindowBatch* hb, int w_begin, int w_end, TileList
 }
 
 // Bytes of the big sequence arrays (hap_seq / read_seq / read_qual) that windows [w0, w1) need.
+// One OpenMP team size for every host-side parallel region of the library.
+static int host_threads() {
+    static const int n = std::max(1, std::min(omp_get_max_threads(), 8));
+    return n;
+}
+
 struct ByteRanges {
     int64_t hap0, hap1;    // byte range of hap_seq
     int64_t read0, read1;  // byte range of read_seq / read_qual (hull over the reads the slots refer to)
@@ -529,7 +535,8 @@ static ByteRanges byte_ranges(const PlbWindowBatch* hb, int w0, int w1) {
     const int64_t s0 = hb->wi_slot_off[(int64_t)w0 * nInd], s1 = hb->wi_slot_off[(int64_t)w1 * nInd];
     int rmin = INT32_MAX, rmax = -1;
     const int32_t* sr = hb->slot_read;
-#pragma omp parallel for reduction(min : rmin) reduction(max : rmax) schedule(static) if (s1 - s0 > 32768)
+#pragma omp parallel for reduction(min : rmin) reduction(max : rmax) schedule(static) num_threads(host_threads()) \
+    if (s1 - s0 > 32768)
     for (int64_t s = s0; s < s1; ++s) {
         const int rd = sr[s];
         rmin = std::min(rmin, rd);
@@ -681,12 +688,13 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
     {
         // plan sub-ranges of the chunk on several host threads, then concatenate in window order
         const int nw = w1 - w0;
-        const int parts = std::max(1, std::min(omp_get_max_threads(), std::min(16, nw / 256)));
+        const int parts = std::max(1, std::min(2 * host_threads(), nw / 128));
         std::vector<TileLists> tls(parts);
         std::vector<AnchorPlan> aps(parts);
         std::vector<DpPlan> dps(parts);
         std::vector<int> mr(parts, 0), mh(parts, 0), mH(parts, 0);
-#pragma omp parallel for schedule(static, 1) num_threads(parts) if (parts > 1)
+        // always the same team size: libgomp rebuilds its thread team whenever num_threads changes
+#pragma omp parallel for schedule(static, 1) num_threads(host_threads()) if (parts > 1)
         for (int p = 0; p < parts; ++p) {
             const int a = w0 + (int)((int64_t)nw * p / parts), b = w0 + (int)((int64_t)nw * (p + 1) / parts);
             plan_tiles(hb, a, b, tls[p], aps[p], dps[p], mr[p], mh[p], mH[p]);

@@ -870,31 +870,126 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
     }
 }
 
+// One band alignment by 16 lanes: lane d owns diagonal d and the lanes sweep anti-diagonals in lock step,
+// exchanging neighbours' states by warp shuffles (the reference's SSE2 scheme, src/c/align.c:199-515, with
+// one lane per diagonal instead of two interleaved 8-lane vectors).  Cell (x, y) has x - y = d and is
+// computed at step s = x + y, so a lane is active on every other step:
+//   M(x,y) <- own diagonal, two steps ago        I(x,y) <- lane d+1, previous step        D(x,y) <- lane d-1
+// Latency per alignment is ~2L steps instead of the 16L cells of the one-thread scalar form, which is what
+// the queue needs: few alignments, nothing to hide their latency behind.  Same recurrence as
+// band_dp_general (byte-exact compares, any read length >= 1).  All 32 lanes of the warp must call it;
+// `sub` selects the half-warp's alignment (lanes 0-15 / 16-31), inactive halves pass L = 0.
+__device__ __forceinline__ int band_dp_wave16(const uint8_t* __restrict__ hap, const uint8_t* __restrict__ open,
+                                              const uint8_t* __restrict__ read, const uint8_t* __restrict__ qual, int L,
+                                              int Lmax, int ext, int nuc) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int d = threadIdx.x & 15;
+    int M = kScoreBig, I = kScoreBig, D = kScoreBig;   // this diagonal's most recent cell
+    const int n_steps = 2 * (Lmax - 1) + 16;           // uniform over the warp
+    // bytes of the lane's next cell, loaded two steps ahead (its cells are (d,0), (d+1,1), ...)
+    int hb = 0, go = 0, rb = 0, q = 0;
+    if (L > 0) {
+        hb = hap[d];
+        go = open[d];
+        rb = read[0];
+        q = qual[0];
+    }
+    for (int s = 0; s < n_steps; ++s) {
+        // neighbours' states as of the previous step (lane d+1: cell (x, y-1); lane d-1: cell (x-1, y))
+        const int upI = __shfl_down_sync(FULL, I, 1, 16), upM = __shfl_down_sync(FULL, M, 1, 16);
+        const int lfD = __shfl_up_sync(FULL, D, 1, 16);
+        const int mi = M < I ? M : I;
+        const int lfMI = __shfl_up_sync(FULL, mi, 1, 16);
+        const int y2 = s - d;
+        if (y2 < 0 || (y2 & 1)) continue;
+        const int y = y2 >> 1, x = y + d;
+        if (y >= L) continue;
+        const int chb = hb, cgo = go, crb = rb, cq = q;
+        if (y + 1 < L) {   // prefetch the next cell of this diagonal
+            hb = hap[x + 1];
+            go = open[x + 1];
+            rb = read[y + 1];
+            q = qual[y + 1];
+        }
+        const int sub = (chb == 'N' || chb == crb) ? 0 : cq;
+        int diag = mi < D ? mi : D;                     // B(x-1, y-1): own state from two steps ago
+        if (y == 0) diag = 0;
+        const int m = diag + sub;
+        int ins;
+        if (y == 0) {
+            ins = (x & 1) ? kScoreBig : cgo + nuc;
+        } else if (d < 15) {
+            const int a = upI + ext, c = upM + cgo;
+            ins = (a < c ? a : c) + nuc;
+        } else {
+            ins = kScoreBig;
+        }
+        int del;
+        if (d >= 1) {
+            const int a = lfD + ext, c = lfMI + cgo;
+            del = a < c ? a : c;
+        } else {
+            del = kScoreBig;
+        }
+        M = m < kScoreBig ? m : kScoreBig;
+        I = ins < kScoreBig ? ins : kScoreBig;
+        D = del < kScoreBig ? del : kScoreBig;
+    }
+    int best = M < I ? M : I;
+    best = best < D ? best : D;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        const int v = __shfl_xor_sync(FULL, best, o, 16);
+        best = v < best ? v : best;
+    }
+    return best;
+}
+
 // ---------------------------------------------------------------------------------------------
-// k_general: queued alignments on the scalar path
+// k_general: queued alignments.  Default mode: 16 lanes per alignment (band_dp_wave16); run-time modes
+// (flank score / HLA clipping, where EVERY alignment is queued): one thread per alignment.
 // ---------------------------------------------------------------------------------------------
 template <bool kModes>
 __global__ void __launch_bounds__(128) k_general(DevBatch b, Queue q, ScoreParams sp) {
     int n = *q.count;
     if (n > q.cap) n = q.cap;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const QueueEntry qe = q.e[i];
-        const int r = b.slot_read[qe.slot];
-        int L = (int)(b.read_seq_off[r + 1] - b.read_seq_off[r]), roff = 0;
-        if (kModes && sp.hla) {
-            roff = (int)(qe.clip & 0xFFFFu);
-            L = (int)(qe.clip >> 16);
+    if (kModes) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const QueueEntry qe = q.e[i];
+            const int r = b.slot_read[qe.slot];
+            int L = (int)(b.read_seq_off[r + 1] - b.read_seq_off[r]), roff = 0;
+            if (sp.hla) {
+                roff = (int)(qe.clip & 0xFFFFu);
+                L = (int)(qe.clip >> 16);
+            }
+            const int v = general_dp_now<true>(b, qe.hap, r, qe.start, roff, L, sp);
+            atomicMin(&b.score[qe.pair], v);
         }
-        int v;
-        if (kModes) {
-            v = general_dp_now<true>(b, qe.hap, r, qe.start, roff, L, sp);
-        } else {
-            const uint8_t* hap = b.hap_seq + b.hap_seq_off[qe.hap];
-            const uint8_t* go = b.gap_open + b.hap_seq_off[qe.hap] + qe.hap;
-            v = band_dp_general(hap + qe.start, go + qe.start, b.read_seq + b.read_seq_off[r],
-                                b.read_qual + b.read_seq_off[r], L, sp.ext, sp.nuc);
+        return;
+    }
+    const int hw = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;     // global half-warp index
+    const int n_hw = (gridDim.x * blockDim.x) >> 4;
+    const int n_round = (n + n_hw - 1) / n_hw;
+    for (int k = 0; k < n_round; ++k) {                               // uniform trip count per warp
+        const int i = k * n_hw + hw;
+        int L = 0;
+        const uint8_t *hap = nullptr, *go = nullptr, *rs = nullptr, *rq = nullptr;
+        int64_t pair = 0;
+        if (i < n) {
+            const QueueEntry qe = q.e[i];
+            const int r = b.slot_read[qe.slot];
+            L = (int)(b.read_seq_off[r + 1] - b.read_seq_off[r]);
+            hap = b.hap_seq + b.hap_seq_off[qe.hap] + qe.start;
+            go = b.gap_open + b.hap_seq_off[qe.hap] + qe.hap + qe.start;
+            rs = b.read_seq + b.read_seq_off[r];
+            rq = b.read_qual + b.read_seq_off[r];
+            pair = qe.pair;
         }
-        atomicMin(&b.score[qe.pair], v);
+        const int Lo = __shfl_xor_sync(0xFFFFFFFFu, L, 16);
+        const int Lmax = L > Lo ? L : Lo;
+        if (Lmax == 0) continue;                                      // both halves idle (warp-uniform)
+        const int v = band_dp_wave16(hap, go, rs, rq, L, Lmax, sp.ext, sp.nuc);
+        if (i < n && L > 0 && (threadIdx.x & 15) == 0) atomicMin(&b.score[pair], v);
     }
 }
 

@@ -400,3 +400,19 @@ def test_s3_modes_synth_sample(engine, oracle):
     got = engine.population_run(b, want_ll=True)
     want, ll0, sc0, _ = oracle.population_run(b, n_threads=os.cpu_count() or 1)
     assert np.array_equal(got["score"], sc0)
+
+
+def test_general_path_wavefront_vs_oracle(engine, oracle):
+    """Windows whose haplotypes carry a byte outside ACGTN take the general path: every alignment is queued
+    and runs as a 16-lane anti-diagonal wavefront (band_dp_wave16).  Config-2 shapes plus ragged lengths."""
+    for b in (synth.make_batch(48), synth.make_batch(40, read_len_range=(100, 250), hap_len_range=(200, 500))):
+        hs = b.hap_seq.copy()
+        for w in range(b.n_windows):      # an IUPAC byte in the first haplotype of every window
+            h = int(b.win_hap_off[w])
+            hs[int(b.hap_seq_off[h]) + 5] = ord("R")
+        b.hap_seq = hs
+        got = engine.population_run(b, want_ll=True)
+        want, ll0, sc0, _ = oracle.population_run(b, n_threads=os.cpu_count() or 1)
+        assert np.array_equal(got["score"], sc0)
+        np.testing.assert_allclose(got["ll"], ll0, rtol=RTOL_TIGHT, atol=0)
+        _check_population(got, want)
