@@ -259,6 +259,52 @@ int plb_population_run_host(PlbContext* ctx, const PlbWindowBatch* host_batch,
                             const PlbOptions* opt, PlbPopulationOut* host_out,
                             PlbLoglikOut* host_ll);
 
+/* -- N4: per-site genotype calls (the step after the window model) --------------------- */
+
+/*
+ * Sites of a batch of windows, as outputCallToVCF walks them (src/cython/vcfutils.pyx:391-417):
+ * one site = one reported position with the variants reported there (variantsThisPos).  Variants are
+ * named by their window-local index (the bit of hap_var_mask); hap_is_ref is
+ * haplotypeIsRefAtThisPos (vcfutils.pyx:403-417: 0 where a variant of the haplotype spans the
+ * position), one byte per haplotype of the site's window.
+ */
+typedef struct PlbSiteBatch {
+    int32_t n_sites;
+    const int32_t* site_win;      /* [n_sites] window of the site                                   */
+    const int32_t* site_var_off;  /* [n_sites+1] offsets into site_var                               */
+    const int32_t* site_var;      /* window-local variant indices, variantsThisPos order             */
+    const int64_t* site_hap_off;  /* [n_sites+1] offsets into hap_is_ref (H_w entries per site)       */
+    const uint8_t* hap_is_ref;
+    int32_t min_posterior;        /* options.minPosterior (runner.py: 5)                              */
+} PlbSiteBatch;
+
+/*
+ * Per (site, individual): what computeGenotypeCallAndLikelihoods (src/cython/vcfutils.pyx:163-334)
+ * returns and what outputCallToVCF derives from it (vcfutils.pyx:504-548).  Allele pairs are ordered
+ * as the reference loops them: (0,0),(1,0),(1,1),(2,0),(2,1),(2,2)...; stride max_pairs.
+ * Any pointer may be NULL.  Individuals without reads get GT -1/-1 and zeros (vcfutils.pyx:497-499).
+ * The final text formatting (round(log10 GL, 2), int(GOF), the minReads rule on per-variant read
+ * counts) is the VCF writer's and is not done here.
+ */
+typedef struct PlbSiteOut {
+    int32_t  max_pairs;
+    int32_t* phased;      /* [n_sites][nInd][2]  phasedIndex1, phasedIndex2                          */
+    double*  lik;         /* [n_sites][nInd][max_pairs] marginal genotype likelihoods                 */
+    double*  post;        /* [n_sites][nInd][3]  genotype, non-ref and ref posterior                  */
+    int32_t* phred;       /* [n_sites][nInd][3]  GQ = phredPosterior, phredNonRef, phredRef           */
+    double*  gof;         /* [n_sites][nInd]     bestGoodnessOfFitValue                               */
+    int32_t* gt;          /* [n_sites][nInd][2]  GT after the minPosterior rules, -1 = "."            */
+    double*  gl_log10;    /* [n_sites][nInd][3]  log10(max(L/maxL, 1e-300)); -1 at multi-allelic sites */
+} PlbSiteOut;
+
+/*
+ * Replaces the per-sample loop of outputCallToVCF around computeGenotypeCallAndLikelihoods for every
+ * site of a batch.  Host buffers.  `batch` supplies win_hap_off, hap_var_mask (varInHap) and wi_n_good;
+ * `pop` the gl / gof / freq arrays a previous plb_population_run_host produced for the same batch.
+ */
+int plb_site_genotypes_host(PlbContext* ctx, const PlbWindowBatch* batch, const PlbPopulationOut* pop,
+                            const PlbSiteBatch* sites, PlbSiteOut* out);
+
 /* -- device-resident variants (inputs already in HBM; used by the multi-GPU driver) -- */
 
 /* Copies a HOST batch into device memory owned by the context and returns an opaque

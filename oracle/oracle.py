@@ -71,6 +71,9 @@ def lib():
         L.plo_posterior.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_double]
         L.plo_posterior.restype = C.c_double
+        L.plo_site_genotypes.argtypes = [C.POINTER(_abi.PlbWindowBatch), C.POINTER(_abi.PlbPopulationOut),
+                                         C.POINTER(_abi.PlbSiteBatch), C.POINTER(_abi.PlbSiteOut)]
+        L.plo_site_genotypes.restype = C.c_int
         L.plo_set_align_fn.argtypes = [C.c_void_p, C.c_int]
         L.plo_set_align_fn.restype = None
         _lib = L
@@ -283,3 +286,16 @@ def population_run(batch, opt=None, n_threads=1, max_haps=None, want_ll=True):
     if rc:
         raise RuntimeError("oracle plo_population_run failed: %d" % rc)
     return arrs, ll[:n], sc[:n], st.as_dict()
+
+
+def site_genotypes(batch, pop_arrs, sites):
+    """N4 restatement: dict of per-(site, individual) arrays (layout of PlbSiteOut)."""
+    from platypus_b200.batch import alloc_site_out, site_out_struct
+    arrs = alloc_site_out(batch, sites)
+    so = site_out_struct(arrs)
+    po = population_struct(pop_arrs)
+    s, ss = batch.as_struct(), sites.as_struct()
+    rc = lib().plo_site_genotypes(C.byref(s), C.byref(po), C.byref(ss), C.byref(so))
+    if rc:
+        raise RuntimeError("oracle plo_site_genotypes failed: %d" % rc)
+    return arrs

@@ -918,3 +918,114 @@ int plo_population_run(const PlbWindowBatch* b, const PlbOptions* opt, PlbPopula
     free(ll_own);
     return err;
 }
+
+
+/* ------------------------------------------------------------------------------------------
+ * N4 — computeGenotypeCallAndLikelihoods, src/cython/vcfutils.pyx:163-334, and what
+ * outputCallToVCF derives per sample (vcfutils.pyx:491-548).  "Parity unpinned": restated from the
+ * cited lines (the module needs the whole Python-2 object graph).
+ * Python semantics kept: max(a, b) returns a unless b > a (so a NaN second argument loses),
+ * round() is half away from zero, C division (cdivision=True, src/setup.py:56) may give inf/NaN.
+ * -----------------------------------------------------------------------------------------*/
+static double py_max(double a, double b) { return b > a ? b : a; }
+static double py_min(double a, double b) { return b < a ? b : a; }
+
+int plo_site_genotypes(const PlbWindowBatch* b, const PlbPopulationOut* pop, const PlbSiteBatch* st,
+                       PlbSiteOut* out) {
+    if (!b || !pop || !st || !out || !pop->gl || !pop->gof || !pop->freq || !b->hap_var_mask) return PLB_ERR_ARG;
+    const int nInd = b->n_individuals;
+    const int Hm = pop->max_haps, Gm = Hm * (Hm + 1) / 2;
+    const int P = out->max_pairs;
+    for (int s = 0; s < st->n_sites; ++s) {
+        const int w = st->site_win[s];
+        const int h0 = b->win_hap_off[w], H = b->win_hap_off[w + 1] - h0;
+        const int nV = st->site_var_off[s + 1] - st->site_var_off[s];
+        const int32_t* vars = st->site_var + st->site_var_off[s];
+        const uint8_t* is_ref = st->hap_is_ref + st->site_hap_off[s];
+        if ((nV + 1) * (nV + 2) / 2 > P) return PLB_ERR_SHAPE;
+        const double* freq = pop->freq + (size_t)w * Hm;
+        for (int i = 0; i < nInd; ++i) {
+            const size_t o = (size_t)s * nInd + i;
+            const double* gl = pop->gl + ((size_t)w * nInd + i) * Gm;
+            if (out->lik) for (int k = 0; k < P; ++k) out->lik[o * P + k] = 0.0;
+            if (b->wi_n_good[(size_t)w * nInd + i] == 0) { /* vcfutils.pyx:497-499 */
+                if (out->phased) out->phased[o * 2] = out->phased[o * 2 + 1] = -1;
+                if (out->post) out->post[o * 3] = out->post[o * 3 + 1] = out->post[o * 3 + 2] = 0.0;
+                if (out->phred) out->phred[o * 3] = out->phred[o * 3 + 1] = out->phred[o * 3 + 2] = 0;
+                if (out->gof) out->gof[o] = 0.0;
+                if (out->gt) out->gt[o * 2] = out->gt[o * 2 + 1] = -1;
+                if (out->gl_log10) out->gl_log10[o * 3] = out->gl_log10[o * 3 + 1] = out->gl_log10[o * 3 + 2] = 0.0;
+                continue;
+            }
+            double sum_lik = 0.0, best_gof = 1e6, best_lik = -1.0, nonref = 0.0, ref = 0.0, phased_max = -1e6;
+            double liks[3] = {0.0, 0.0, 0.0}, max_lik = 0.0;
+            int ph1 = -1, ph2 = -1, pair = 0, have_max = 0;
+            for (int i1 = 0; i1 <= nV; ++i1)
+                for (int i2 = 0; i2 <= i1; ++i2, ++pair) {
+                    double marg = 0.0;
+                    int g = 0;
+                    for (int a = 0; a < H; ++a)          /* haplotypeIndexes: (a, c), a <= c, cgenotype.pyx:193-218 */
+                        for (int c = a; c < H; ++c, ++g) {
+                            const int ref1 = is_ref[a], ref2 = is_ref[c];
+                            const double factor = (a != c) ? 2.0 : 1.0;
+                            int v1h1 = 0, v1h2 = 0, v2h1 = 0, v2h2 = 0, match = 0;
+                            if (i1 == 0 && i2 == 0) {
+                                match = ref1 && ref2;
+                            } else if (i2 == 0) {
+                                v1h1 = (int)((b->hap_var_mask[h0 + a] >> vars[i1 - 1]) & 1);
+                                v1h2 = (int)((b->hap_var_mask[h0 + c] >> vars[i1 - 1]) & 1);
+                                match = (ref2 && v1h1) || (ref1 && v1h2);
+                            } else {
+                                v1h1 = (int)((b->hap_var_mask[h0 + a] >> vars[i1 - 1]) & 1);
+                                v1h2 = (int)((b->hap_var_mask[h0 + c] >> vars[i1 - 1]) & 1);
+                                v2h1 = (int)((b->hap_var_mask[h0 + a] >> vars[i2 - 1]) & 1);
+                                v2h2 = (int)((b->hap_var_mask[h0 + c] >> vars[i2 - 1]) & 1);
+                                match = (v1h1 && v2h2) || (v2h1 && v1h2);
+                            }
+                            if (!match) continue;
+                            const double cur = nInd > 25 ? (factor * freq[a] * freq[c] * gl[g]) : (factor * gl[g]);
+                            marg += cur;
+                            if (cur > phased_max) { /* :276-316 */
+                                phased_max = cur;
+                                if (i1 == 0 && i2 == 0) { ph1 = i1; ph2 = i2; }
+                                else if (i2 == 0 && i1 != 0) {
+                                    if (v1h1) { ph1 = i1; ph2 = i2; }
+                                    else if (v1h2) { ph1 = i2; ph2 = i1; }
+                                } else if (i2 == i1 && i1 > 0) { ph1 = i1; ph2 = i2; }
+                                else if (i2 > 0 && i1 > 0 && i2 != i1) {
+                                    if (v1h1 && v2h2) { ph1 = i1; ph2 = i2; }
+                                    else if (v1h2 && v2h1) { ph1 = i2; ph2 = i1; }
+                                }
+                            }
+                            const double gf = pop->gof[((size_t)w * Gm + g) * nInd + i];
+                            if (gf < best_gof) best_gof = gf;
+                        }
+                    if (marg > best_lik) best_lik = marg;
+                    if ((i1 == 1 && i2 == 0) || (i1 == 1 && i2 == 1)) nonref += marg;
+                    else if (i1 == 0 && i2 == 0) ref += marg;
+                    sum_lik += marg;
+                    if (out->lik) out->lik[o * P + pair] = marg;
+                    if (pair < 3) liks[pair] = marg;
+                    if (!have_max || marg > max_lik) { max_lik = marg; have_max = 1; }  /* Python max(list) */
+                }
+            const double gpost = best_lik / sum_lik, npost = nonref / sum_lik, rpost = ref / sum_lik;
+            const int q_g = (int)py_min(99, round(-10.0 * log10(py_max(1e-10, 1.0 - gpost))));
+            const int q_n = (int)py_min(99, round(-10.0 * log10(py_max(1e-10, 1.0 - npost))));
+            const int q_r = (int)py_min(99, round(-10.0 * log10(py_max(1e-10, 1.0 - rpost))));
+            int gt1 = ph1, gt2 = ph2;
+            double gl3[3] = {-1.0, -1.0, -1.0};
+            if (nV == 1) { /* :518-532 */
+                if (q_n < st->min_posterior && q_r < st->min_posterior) gt1 = gt2 = -1;
+                else if (q_n < st->min_posterior) gt1 = gt2 = 0;
+                for (int k = 0; k < 3; ++k) gl3[k] = log10(py_max(liks[k] / max_lik, 1e-300));
+            }
+            if (out->phased) { out->phased[o * 2] = ph1; out->phased[o * 2 + 1] = ph2; }
+            if (out->post) { out->post[o * 3] = gpost; out->post[o * 3 + 1] = npost; out->post[o * 3 + 2] = rpost; }
+            if (out->phred) { out->phred[o * 3] = q_g; out->phred[o * 3 + 1] = q_n; out->phred[o * 3 + 2] = q_r; }
+            if (out->gof) out->gof[o] = best_gof;
+            if (out->gt) { out->gt[o * 2] = gt1; out->gt[o * 2 + 1] = gt2; }
+            if (out->gl_log10) for (int k = 0; k < 3; ++k) out->gl_log10[o * 3 + k] = gl3[k];
+        }
+    }
+    return PLB_OK;
+}

@@ -99,6 +99,11 @@ int plo_window_loglik(const PlbWindowBatch* b, const PlbOptions* opt, PlbLoglikO
 int plo_population_run(const PlbWindowBatch* b, const PlbOptions* opt, PlbPopulationOut* out,
                        PlbLoglikOut* ll, int n_threads, PlbRunStats* stats);
 
+/* N4: computeGenotypeCallAndLikelihoods + the per-sample derivations of outputCallToVCF
+ * (src/cython/vcfutils.pyx:163-334, 491-548) for every (site, individual). */
+int plo_site_genotypes(const PlbWindowBatch* b, const PlbPopulationOut* pop, const PlbSiteBatch* sites,
+                       PlbSiteOut* out);
+
 /* Pieces of S3 exposed for unit tests. */
 double plo_genotype_loglik(const double* ll1, const double* ll2, int n_total, int n_good,
                            int homozygous, double* gof, double* hap1_like, double* hap2_like);

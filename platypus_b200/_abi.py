@@ -49,6 +49,16 @@ class PlbPopulationOut(C.Structure):
                 ("freq", _p), ("em_post", _p), ("call", _p), ("var_phred", _p), ("em_iters", _p)]
 
 
+class PlbSiteBatch(C.Structure):
+    _fields_ = [("n_sites", C.c_int32), ("site_win", _p), ("site_var_off", _p), ("site_var", _p),
+                ("site_hap_off", _p), ("hap_is_ref", _p), ("min_posterior", C.c_int32)]
+
+
+class PlbSiteOut(C.Structure):
+    _fields_ = [("max_pairs", C.c_int32), ("phased", _p), ("lik", _p), ("post", _p), ("phred", _p), ("gof", _p),
+                ("gt", _p), ("gl_log10", _p)]
+
+
 class PlbRunStats(C.Structure):
     _fields_ = [("n_pairs", C.c_int64), ("n_pairs_scored", C.c_int64), ("n_dp", C.c_int64), ("cells", C.c_int64),
                 ("n_anchor_heavy", C.c_int64), ("n_anchor_verify", C.c_int64), ("n_anchor_exact", C.c_int64)]
@@ -97,6 +107,8 @@ def declare(lib):
     lib.plb_window_loglik_host.restype = C.c_int
     lib.plb_population_run_host.argtypes = [_p, P(PlbWindowBatch), P(PlbOptions), P(PlbPopulationOut), P(PlbLoglikOut)]
     lib.plb_population_run_host.restype = C.c_int
+    lib.plb_site_genotypes_host.argtypes = [_p, P(PlbWindowBatch), P(PlbPopulationOut), P(PlbSiteBatch), P(PlbSiteOut)]
+    lib.plb_site_genotypes_host.restype = C.c_int
     lib.plb_batch_upload.argtypes = [_p, P(PlbWindowBatch), P(_p)]
     lib.plb_batch_upload.restype = C.c_int
     lib.plb_batch_free.argtypes = [_p, _p]
@@ -117,7 +129,7 @@ EXPORTED_SYMBOLS = [
     "plb_context_create", "plb_context_destroy", "plb_last_error", "plb_abi_version", "plb_launch_count",
     "plb_ll_offsets", "plb_validate", "plb_fast_align", "plb_align_batch_host", "plb_align_traceback_host",
     "plb_align_flank_batch_host", "plb_gap_open_host",
-    "plb_window_loglik_host", "plb_population_run_host", "plb_batch_upload", "plb_batch_free",
+    "plb_window_loglik_host", "plb_population_run_host", "plb_site_genotypes_host", "plb_batch_upload", "plb_batch_free",
     "plb_run_device", "plb_last_stats", "plb_set_timing", "plb_kernel_times",
 ]
 KERNEL_NAMES = ["k_prep", "k_anchor", "k_general", "k_dp", "k_genotype", "k_population"]

@@ -294,3 +294,66 @@ def shard_bounds(n_windows: int, world_size: int):
     for r in range(world_size):
         bounds.append(bounds[-1] + base + (1 if r < rem else 0))
     return bounds
+
+
+# ---- sites (scope row N4: the per-sample loop of outputCallToVCF) --------------------------------
+@dataclass
+class SiteBatch:
+    """Reported positions of a WindowBatch and what computeGenotypeCallAndLikelihoods needs per site
+    (reference: src/cython/vcfutils.pyx:391-417): the window, the window-local indices of the variants
+    reported at the site (variantsThisPos order) and haplotypeIsRefAtThisPos per haplotype."""
+    site_win: np.ndarray        # int32 [S]
+    site_var_off: np.ndarray    # int32 [S+1]
+    site_var: np.ndarray        # int32
+    site_hap_off: np.ndarray    # int64 [S+1]
+    hap_is_ref: np.ndarray      # uint8
+    min_posterior: int = 5
+
+    @property
+    def n_sites(self):
+        return len(self.site_win)
+
+    def max_pairs(self):
+        nv = int(np.max(np.diff(self.site_var_off))) if self.n_sites else 1
+        return (nv + 1) * (nv + 2) // 2
+
+    def as_struct(self):
+        from . import _abi
+        s = _abi.PlbSiteBatch()
+        s.n_sites = self.n_sites
+        for name in ("site_win", "site_var_off", "site_var", "site_hap_off", "hap_is_ref"):
+            setattr(s, name, _abi.ptr(getattr(self, name)))
+        s.min_posterior = int(self.min_posterior)
+        return s
+
+    @staticmethod
+    def from_lists(batch, sites, min_posterior=5):
+        """sites: list of (window, [variant indices], [is_ref per haplotype of the window])."""
+        sw, svo, sv, sho, ref = [], [0], [], [0], []
+        for w, vs, isref in sites:
+            H = int(batch.win_hap_off[w + 1] - batch.win_hap_off[w])
+            assert len(isref) == H
+            sw.append(w)
+            sv.extend(vs)
+            svo.append(len(sv))
+            ref.extend(isref)
+            sho.append(len(ref))
+        return SiteBatch(np.asarray(sw, np.int32), np.asarray(svo, np.int32),
+                         np.asarray(sv, np.int32).reshape(-1), np.asarray(sho, np.int64),
+                         np.asarray(ref, np.uint8).reshape(-1), min_posterior)
+
+
+def alloc_site_out(batch, sites):
+    S, nI, Pm = sites.n_sites, batch.n_individuals, sites.max_pairs()
+    return {"max_pairs": Pm, "phased": np.zeros((S, nI, 2), np.int32), "lik": np.zeros((S, nI, Pm)),
+            "post": np.zeros((S, nI, 3)), "phred": np.zeros((S, nI, 3), np.int32), "gof": np.zeros((S, nI)),
+            "gt": np.zeros((S, nI, 2), np.int32), "gl_log10": np.zeros((S, nI, 3))}
+
+
+def site_out_struct(arrs):
+    from . import _abi
+    o = _abi.PlbSiteOut()
+    o.max_pairs = arrs["max_pairs"]
+    for k in ("phased", "lik", "post", "phred", "gof", "gt", "gl_log10"):
+        setattr(o, k, _abi.ptr(arrs[k]))
+    return o

@@ -1381,6 +1381,102 @@ extern "C" int plb_population_run_host(PlbContext* c, const PlbWindowBatch* hb, 
     return run_host(c, hb, opt, out, ll);
 }
 
+// ---- N4: per-site genotype calls ------------------------------------------------------------------
+
+extern "C" int plb_site_genotypes_host(PlbContext* c, const PlbWindowBatch* hb, const PlbPopulationOut* pop,
+                                       const PlbSiteBatch* st, PlbSiteOut* out) {
+    if (!c || !hb || !pop || !st || !out) return set_err(PLB_ERR_ARG, "NULL argument");
+    if (!pop->gl || !pop->gof || !pop->freq) return set_err(PLB_ERR_ARG, "PlbPopulationOut needs gl, gof and freq");
+    if (!hb->win_hap_off || !hb->hap_var_mask || !hb->wi_n_good)
+        return set_err(PLB_ERR_ARG, "batch needs win_hap_off, hap_var_mask and wi_n_good");
+    const int S = st->n_sites, W = hb->n_windows, nInd = hb->n_individuals;
+    if (S < 0 || nInd < 1) return set_err(PLB_ERR_ARG, "bad n_sites / n_individuals");
+    if (S == 0) return PLB_OK;
+    if (!st->site_win || !st->site_var_off || !st->site_hap_off || !st->hap_is_ref)
+        return set_err(PLB_ERR_ARG, "NULL array in site batch");
+    const int Hm = pop->max_haps, Gm = Hm * (Hm + 1) / 2, P = out->max_pairs;
+    for (int s = 0; s < S; ++s) {
+        const int w = st->site_win[s];
+        if (w < 0 || w >= W) return set_err(PLB_ERR_ARG, "site %d: window %d out of range", s, w);
+        const int H = hb->win_hap_off[w + 1] - hb->win_hap_off[w];
+        if (H > Hm) return set_err(PLB_ERR_SHAPE, "site %d: window has %d haplotypes > max_haps %d", s, H, Hm);
+        if (st->site_hap_off[s + 1] - st->site_hap_off[s] != H)
+            return set_err(PLB_ERR_ARG, "site %d: hap_is_ref must hold one entry per haplotype of its window", s);
+        const int nV = st->site_var_off[s + 1] - st->site_var_off[s];
+        if (nV < 0 || (nV + 1) * (nV + 2) / 2 > P)
+            return set_err(PLB_ERR_SHAPE, "site %d: %d variants need %d allele pairs > max_pairs %d", s, nV,
+                           (nV + 1) * (nV + 2) / 2, P);
+        for (int k = 0; k < nV; ++k) {
+            const int v = st->site_var[st->site_var_off[s] + k];
+            if (v < 0 || v >= 64) return set_err(PLB_ERR_ARG, "site %d: variant index %d out of range", s, v);
+        }
+    }
+    CU(cudaSetDevice(c->device));
+    const int n_haps = hb->win_hap_off[W];
+    const int64_t n_sv = st->site_var_off[S], n_sh = st->site_hap_off[S];
+    const size_t SI = (size_t)S * nInd;
+    Layout L;
+    const size_t o_sw = L.take((size_t)S * 4), o_svo = L.take((size_t)(S + 1) * 4), o_sv = L.take((size_t)n_sv * 4 + 4),
+                 o_sho = L.take((size_t)(S + 1) * 8), o_ref = L.take((size_t)n_sh + 4), o_who = L.take((size_t)(W + 1) * 4),
+                 o_mask = L.take((size_t)n_haps * 8), o_ng = L.take((size_t)W * nInd * 4),
+                 o_gl = L.take((size_t)W * nInd * Gm * 8), o_gof = L.take((size_t)W * Gm * nInd * 8),
+                 o_fr = L.take((size_t)W * Hm * 8);
+    const size_t o_ph = L.take(out->phased ? SI * 8 : 0), o_lik = L.take(out->lik ? SI * P * 8 : 0),
+                 o_post = L.take(out->post ? SI * 24 : 0), o_phr = L.take(out->phred ? SI * 12 : 0),
+                 o_og = L.take(out->gof ? SI * 8 : 0), o_gt = L.take(out->gt ? SI * 8 : 0),
+                 o_l10 = L.take(out->gl_log10 ? SI * 24 : 0);
+    Block B;
+    int rc = block_get(c, L.off + 256, &B);
+    if (rc) return rc;
+    cudaStream_t stq = c->stream;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](size_t off, const void* src, size_t bytes) {
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync((uint8_t*)B.p + off, src, bytes, cudaMemcpyHostToDevice, stq);
+    };
+    up(o_sw, st->site_win, (size_t)S * 4);
+    up(o_svo, st->site_var_off, (size_t)(S + 1) * 4);
+    up(o_sv, st->site_var, (size_t)n_sv * 4);
+    up(o_sho, st->site_hap_off, (size_t)(S + 1) * 8);
+    up(o_ref, st->hap_is_ref, (size_t)n_sh);
+    up(o_who, hb->win_hap_off, (size_t)(W + 1) * 4);
+    up(o_mask, hb->hap_var_mask, (size_t)n_haps * 8);
+    up(o_ng, hb->wi_n_good, (size_t)W * nInd * 4);
+    up(o_gl, pop->gl, (size_t)W * nInd * Gm * 8);
+    up(o_gof, pop->gof, (size_t)W * Gm * nInd * 8);
+    up(o_fr, pop->freq, (size_t)W * Hm * 8);
+    if (e == cudaSuccess) {
+        SiteIn in{S, nInd, Hm, st->min_posterior, at<int32_t>(B, o_sw), at<int32_t>(B, o_svo), at<int32_t>(B, o_sv),
+                  at<int64_t>(B, o_sho), at<uint8_t>(B, o_ref), at<int32_t>(B, o_who), at<uint64_t>(B, o_mask),
+                  at<int32_t>(B, o_ng), at<double>(B, o_gl), at<double>(B, o_gof), at<double>(B, o_fr)};
+        SiteOutDev od{P,
+                      out->phased ? at<int32_t>(B, o_ph) : nullptr,
+                      out->lik ? at<double>(B, o_lik) : nullptr,
+                      out->post ? at<double>(B, o_post) : nullptr,
+                      out->phred ? at<int32_t>(B, o_phr) : nullptr,
+                      out->gof ? at<double>(B, o_og) : nullptr,
+                      out->gt ? at<int32_t>(B, o_gt) : nullptr,
+                      out->gl_log10 ? at<double>(B, o_l10) : nullptr};
+        k_site_genotypes<<<(unsigned)((SI + 127) / 128), 128, 0, stq>>>(in, od);
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    auto down = [&](void* dst, size_t off, size_t bytes) {
+        if (e == cudaSuccess && dst && bytes) e = cudaMemcpyAsync(dst, (uint8_t*)B.p + off, bytes, cudaMemcpyDeviceToHost, stq);
+    };
+    down(out->phased, o_ph, SI * 8);
+    down(out->lik, o_lik, SI * P * 8);
+    down(out->post, o_post, SI * 24);
+    down(out->phred, o_phr, SI * 12);
+    down(out->gof, o_og, SI * 8);
+    down(out->gt, o_gt, SI * 8);
+    down(out->gl_log10, o_l10, SI * 24);
+    cudaError_t e2 = cudaStreamSynchronize(stq);
+    block_put(c, B);
+    if (e != cudaSuccess) return set_err(PLB_ERR_CUDA, "plb_site_genotypes_host: %s", cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return set_err(PLB_ERR_CUDA, "plb_site_genotypes_host: %s", cudaGetErrorString(e2));
+    return PLB_OK;
+}
+
 // ---- S1 -----------------------------------------------------------------------------------------
 
 namespace plb {

@@ -1791,4 +1791,168 @@ __global__ void __launch_bounds__(32 * kPopFewWarps) k_population_few(DevBatch b
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k_site_genotypes (scope row N4): computeGenotypeCallAndLikelihoods (src/cython/vcfutils.pyx:163-334)
+// and the per-sample derivations of outputCallToVCF (vcfutils.pyx:491-548), one thread per
+// (site, individual); allele pairs and genotypes are visited in the reference's order, so every sum
+// adds the same values in the same order.
+// ---------------------------------------------------------------------------------------------
+struct SiteIn {
+    int32_t n_sites, n_individuals, max_haps, min_posterior;
+    const int32_t* site_win;
+    const int32_t* site_var_off;
+    const int32_t* site_var;
+    const int64_t* site_hap_off;
+    const uint8_t* hap_is_ref;
+    const int32_t* win_hap_off;
+    const uint64_t* hap_var_mask;
+    const int32_t* wi_n_good;
+    const double* gl;
+    const double* gof;
+    const double* freq;
+};
+struct SiteOutDev {
+    int32_t max_pairs;
+    int32_t* phased;
+    double* lik;
+    double* post;
+    int32_t* phred;
+    double* gof;
+    int32_t* gt;
+    double* gl_log10;
+};
+
+__device__ __forceinline__ double py_max(double a, double b) { return b > a ? b : a; }   // Python max(a, b)
+__device__ __forceinline__ double py_min(double a, double b) { return b < a ? b : a; }
+
+__global__ void __launch_bounds__(128) k_site_genotypes(SiteIn in, SiteOutDev out) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nInd = in.n_individuals;
+    if (o >= (int64_t)in.n_sites * nInd) return;
+    const int s = (int)(o / nInd), i = (int)(o % nInd);
+    const int w = in.site_win[s];
+    const int h0 = in.win_hap_off[w], H = in.win_hap_off[w + 1] - h0;
+    const int Hm = in.max_haps, Gm = Hm * (Hm + 1) / 2;
+    const int P = out.max_pairs;
+    const int nV = in.site_var_off[s + 1] - in.site_var_off[s];
+    const int32_t* vars = in.site_var + in.site_var_off[s];
+    const uint8_t* is_ref = in.hap_is_ref + in.site_hap_off[s];
+    const uint64_t* masks = in.hap_var_mask + h0;
+    const double* freq = in.freq + (size_t)w * Hm;
+    const double* gl = in.gl + ((size_t)w * nInd + i) * Gm;
+    if (out.lik)
+        for (int k = 0; k < P; ++k) out.lik[o * P + k] = 0.0;
+    if (in.wi_n_good[(size_t)w * nInd + i] == 0) {   // vcfutils.pyx:497-499
+        if (out.phased) out.phased[o * 2] = out.phased[o * 2 + 1] = -1;
+        if (out.post) out.post[o * 3] = out.post[o * 3 + 1] = out.post[o * 3 + 2] = 0.0;
+        if (out.phred) out.phred[o * 3] = out.phred[o * 3 + 1] = out.phred[o * 3 + 2] = 0;
+        if (out.gof) out.gof[o] = 0.0;
+        if (out.gt) out.gt[o * 2] = out.gt[o * 2 + 1] = -1;
+        if (out.gl_log10) out.gl_log10[o * 3] = out.gl_log10[o * 3 + 1] = out.gl_log10[o * 3 + 2] = 0.0;
+        return;
+    }
+    double sum_lik = 0.0, best_gof = 1e6, best_lik = -1.0, nonref = 0.0, ref = 0.0, phased_max = -1e6;
+    double liks[3] = {0.0, 0.0, 0.0}, max_lik = 0.0;
+    int ph1 = -1, ph2 = -1, pair = 0;
+    bool have_max = false;
+    for (int i1 = 0; i1 <= nV; ++i1)
+        for (int i2 = 0; i2 <= i1; ++i2, ++pair) {
+            double marg = 0.0;
+            int g = 0;
+            for (int a = 0; a < H; ++a)
+                for (int c = a; c < H; ++c, ++g) {
+                    const bool ref1 = is_ref[a] != 0, ref2 = is_ref[c] != 0;
+                    const double factor = (a != c) ? 2.0 : 1.0;
+                    bool v1h1 = false, v1h2 = false, v2h1 = false, v2h2 = false, match;
+                    if (i1 == 0 && i2 == 0) {
+                        match = ref1 && ref2;
+                    } else if (i2 == 0) {
+                        v1h1 = (masks[a] >> vars[i1 - 1]) & 1ull;
+                        v1h2 = (masks[c] >> vars[i1 - 1]) & 1ull;
+                        match = (ref2 && v1h1) || (ref1 && v1h2);
+                    } else {
+                        v1h1 = (masks[a] >> vars[i1 - 1]) & 1ull;
+                        v1h2 = (masks[c] >> vars[i1 - 1]) & 1ull;
+                        v2h1 = (masks[a] >> vars[i2 - 1]) & 1ull;
+                        v2h2 = (masks[c] >> vars[i2 - 1]) & 1ull;
+                        match = (v1h1 && v2h2) || (v2h1 && v1h2);
+                    }
+                    if (!match) continue;
+                    const double cur = nInd > 25 ? (factor * freq[a] * freq[c] * gl[g]) : (factor * gl[g]);
+                    marg += cur;
+                    if (cur > phased_max) {   // phase by the maximum-likelihood genotype, :276-316
+                        phased_max = cur;
+                        if (i1 == 0 && i2 == 0) {
+                            ph1 = i1;
+                            ph2 = i2;
+                        } else if (i2 == 0 && i1 != 0) {
+                            if (v1h1) {
+                                ph1 = i1;
+                                ph2 = i2;
+                            } else if (v1h2) {
+                                ph1 = i2;
+                                ph2 = i1;
+                            }
+                        } else if (i2 == i1 && i1 > 0) {
+                            ph1 = i1;
+                            ph2 = i2;
+                        } else if (i2 > 0 && i1 > 0 && i2 != i1) {
+                            if (v1h1 && v2h2) {
+                                ph1 = i1;
+                                ph2 = i2;
+                            } else if (v1h2 && v2h1) {
+                                ph1 = i2;
+                                ph2 = i1;
+                            }
+                        }
+                    }
+                    const double gf = in.gof[((size_t)w * Gm + g) * nInd + i];
+                    if (gf < best_gof) best_gof = gf;
+                }
+            if (marg > best_lik) best_lik = marg;
+            if ((i1 == 1 && i2 == 0) || (i1 == 1 && i2 == 1)) nonref += marg;
+            else if (i1 == 0 && i2 == 0) ref += marg;
+            sum_lik += marg;
+            if (out.lik && pair < P) out.lik[o * P + pair] = marg;
+            if (pair < 3) liks[pair] = marg;
+            if (!have_max || marg > max_lik) {
+                max_lik = marg;
+                have_max = true;
+            }
+        }
+    const double gpost = best_lik / sum_lik, npost = nonref / sum_lik, rpost = ref / sum_lik;
+    const int q_g = (int)py_min(99, round(-10.0 * log10(py_max(1e-10, 1.0 - gpost))));
+    const int q_n = (int)py_min(99, round(-10.0 * log10(py_max(1e-10, 1.0 - npost))));
+    const int q_r = (int)py_min(99, round(-10.0 * log10(py_max(1e-10, 1.0 - rpost))));
+    int gt1 = ph1, gt2 = ph2;
+    double gl3[3] = {-1.0, -1.0, -1.0};
+    if (nV == 1) {   // vcfutils.pyx:518-532
+        if (q_n < in.min_posterior && q_r < in.min_posterior) gt1 = gt2 = -1;
+        else if (q_n < in.min_posterior) gt1 = gt2 = 0;
+        for (int k = 0; k < 3; ++k) gl3[k] = log10(py_max(liks[k] / max_lik, 1e-300));
+    }
+    if (out.phased) {
+        out.phased[o * 2] = ph1;
+        out.phased[o * 2 + 1] = ph2;
+    }
+    if (out.post) {
+        out.post[o * 3] = gpost;
+        out.post[o * 3 + 1] = npost;
+        out.post[o * 3 + 2] = rpost;
+    }
+    if (out.phred) {
+        out.phred[o * 3] = q_g;
+        out.phred[o * 3 + 1] = q_n;
+        out.phred[o * 3 + 2] = q_r;
+    }
+    if (out.gof) out.gof[o] = best_gof;
+    if (out.gt) {
+        out.gt[o * 2] = gt1;
+        out.gt[o * 2 + 1] = gt2;
+    }
+    if (out.gl_log10)
+        for (int k = 0; k < 3; ++k) out.gl_log10[o * 3 + k] = gl3[k];
+}
+
 }  // namespace plb

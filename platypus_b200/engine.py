@@ -243,6 +243,19 @@ class Engine:
             arrs["ll"], arrs["score"] = ll[:n], sc[:n]
         return arrs
 
+    # ---- N4 ---------------------------------------------------------------------------------
+    def site_genotypes(self, batch: WindowBatch, pop: dict, sites):
+        """computeGenotypeCallAndLikelihoods + the per-sample derivations of outputCallToVCF for every
+        (site, individual) (reference: src/cython/vcfutils.pyx:163-334, 491-548).  `pop` is the dict
+        population_run returned for `batch`; `sites` a batch.SiteBatch.  Returns a dict of arrays."""
+        from .batch import alloc_site_out, site_out_struct
+        arrs = alloc_site_out(batch, sites)
+        so = site_out_struct(arrs)
+        po = self._pop_struct(pop)
+        s, ss = batch.as_struct(), sites.as_struct()
+        _check(self.lib, self.lib.plb_site_genotypes_host(self.ctx, C.byref(s), C.byref(po), C.byref(ss), C.byref(so)))
+        return arrs
+
     # ---- device-resident path -------------------------------------------------------------------
     def upload(self, batch: WindowBatch):
         h = C.c_void_p()

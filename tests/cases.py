@@ -192,3 +192,35 @@ def edge_batch(seed=5, n_windows=12, n_individuals=3, overhang=False):
         windows.append(Window(ws, we, hap_start, haps, per_ind, hap_var_mask=masks,
                               var_prior=[rng.choice([1e-3, 1e-4, 0.5, 3.3e-4]) for _ in range(n_var)]))
     return WindowBatch.from_windows(windows, n_individuals)
+
+
+def sites_for_batch(batch, seed=3):
+    """Reported sites for a WindowBatch (scope row N4): one bi-allelic site per window variant, plus a
+    multi-allelic site where a window has two or more variants.  haplotypeIsRefAtThisPos is 0 for the
+    haplotypes that carry a variant of the site and, now and then, for one carrying another variant that
+    spans the position (vcfutils.pyx:403-417)."""
+    from platypus_b200.batch import SiteBatch
+    rng = random.Random(seed)
+    sites = []
+    for w in range(batch.n_windows):
+        nv = int(batch.win_n_var[w]) if batch.win_n_var is not None else 0
+        h0, h1 = int(batch.win_hap_off[w]), int(batch.win_hap_off[w + 1])
+        masks = [int(batch.hap_var_mask[h]) for h in range(h0, h1)]
+
+        def is_ref(vs):
+            out = []
+            for m in masks:
+                r = 0 if any((m >> v) & 1 for v in vs) else 1
+                if r and m and rng.random() < 0.15:
+                    r = 0   # another variant of this haplotype spans the position
+                out.append(r)
+            return out
+        for v in range(nv):
+            sites.append((w, [v], is_ref([v])))
+        if nv >= 2:
+            vs = rng.sample(range(nv), 2)
+            sites.append((w, vs, is_ref(vs)))
+        if nv >= 3 and rng.random() < 0.5:
+            vs = rng.sample(range(nv), 3)
+            sites.append((w, vs, is_ref(vs)))
+    return SiteBatch.from_lists(batch, sites, min_posterior=5)

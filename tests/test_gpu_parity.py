@@ -416,3 +416,33 @@ def test_general_path_wavefront_vs_oracle(engine, oracle):
         assert np.array_equal(got["score"], sc0)
         np.testing.assert_allclose(got["ll"], ll0, rtol=RTOL_TIGHT, atol=0)
         _check_population(got, want)
+
+
+# ---- scope row N4: per-site genotype calls -------------------------------------------------------
+
+@pytest.mark.parametrize("n_ind", [1, 3, 30])
+def test_n4_site_genotypes_vs_oracle(engine, oracle, n_ind):
+    """plb_site_genotypes_host against the restatement of computeGenotypeCallAndLikelihoods; 30 individuals
+    switch on the EM-frequency weighting (nIndividuals > 25, vcfutils.pyx:264-267)."""
+    b = cases.edge_batch(seed=11, n_windows=16, n_individuals=n_ind)
+    pop = engine.population_run(b)
+    sites = cases.sites_for_batch(b, seed=n_ind)
+    got = engine.site_genotypes(b, pop, sites)
+    want = oracle.site_genotypes(b, pop, sites)
+    for k in ("phased", "phred", "gt"):
+        assert np.array_equal(got[k], want[k]), k
+    for k in ("lik", "post", "gof", "gl_log10"):
+        np.testing.assert_allclose(got[k], want[k], rtol=RTOL_TIGHT, atol=0, equal_nan=True, err_msg=k)
+
+
+def test_n4_site_genotypes_synth(engine, oracle):
+    b = synth.make_batch(200)
+    pop = engine.population_run(b)
+    sites = cases.sites_for_batch(b, seed=9)
+    got = engine.site_genotypes(b, pop, sites)
+    want = oracle.site_genotypes(b, pop, sites)
+    for k in ("phased", "phred", "gt"):
+        assert np.array_equal(got[k], want[k]), k
+    np.testing.assert_allclose(got["lik"], want["lik"], rtol=RTOL_TIGHT, atol=0)
+    called = (got["gt"][:, 0, 0] > 0) | (got["gt"][:, 0, 1] > 0)
+    assert called.any() and not called.all()

@@ -267,3 +267,53 @@ def test_reference_kernel_inside_oracle_agrees_flank_mode(oracle):
     ll, sc, _ = oracle.window_loglik(b, opt)
     assert np.array_equal(sc, sc_ref)
     assert np.array_equal(ll, ll_ref)
+
+
+# ---- scope row N4: per-site genotype calls -------------------------------------------------------
+
+def test_site_genotypes_known_answer(oracle):
+    """computeGenotypeCallAndLikelihoods on a case small enough to do by hand (vcfutils.pyx:163-334):
+    two haplotypes (reference, one variant), GL = [0.1, 1.0, 0.2] for genotypes (0,0), (0,1), (1,1)."""
+    from platypus_b200.batch import Read, Window, WindowBatch, SiteBatch
+    rd = Read(b"A" * 30, bytes([30] * 30), 100, 130)
+    w = Window(100, 140, 50, [b"ACGT" * 30, b"ACGA" * 30], [([rd], [], [])], hap_var_mask=[0, 1], var_prior=[1e-3])
+    b = WindowBatch.from_windows([w], 1)
+    pop = oracle.alloc_population_out(b)
+    pop["gl"][0, 0, :3] = [0.1, 1.0, 0.2]
+    pop["gof"][0, :3, 0] = [7.0, 3.0, 5.0]
+    pop["freq"][0, :2] = [0.5, 0.5]
+    sites = SiteBatch.from_lists(b, [(0, [0], [1, 0])])
+    r = oracle.site_genotypes(b, pop, sites)
+    np.testing.assert_allclose(r["lik"][0, 0], [0.1, 2.0, 0.2], rtol=1e-15)
+    np.testing.assert_allclose(r["post"][0, 0], [2.0 / 2.3, 2.2 / 2.3, 0.1 / 2.3], rtol=1e-14)
+    assert r["phred"][0, 0].tolist() == [9, 14, 0]
+    assert r["phased"][0, 0].tolist() == [0, 1]          # the variant sits on the second haplotype: "0/1"
+    assert r["gt"][0, 0].tolist() == [0, 1]
+    assert r["gof"][0, 0] == 3.0
+    np.testing.assert_allclose(r["gl_log10"][0, 0], [math.log10(0.05), 0.0, math.log10(0.1)], rtol=1e-14)
+    # a weak call falls back to 0/0, a hopeless one to ./. (vcfutils.pyx:518-526)
+    pop["gl"][0, 0, :3] = [1.0, 0.2, 0.0]     # ref posterior 1/1.4: phred 5; non-ref 0.4/1.4: phred 1
+    r = oracle.site_genotypes(b, pop, sites)
+    assert r["phred"][0, 0].tolist() == [5, 1, 5] and r["gt"][0, 0].tolist() == [0, 0]
+    pop["gl"][0, 0, :3] = [1.0, 0.5, 0.0]
+    r = oracle.site_genotypes(b, pop, sites)
+    assert r["phred"][0, 0, 1] < 5 and r["phred"][0, 0, 2] < 5 and r["gt"][0, 0].tolist() == [-1, -1]
+
+
+def test_site_genotypes_edge_batch_properties(oracle):
+    b = cases.edge_batch(seed=5)
+    pop, _, _, _ = oracle.population_run(b)
+    sites = cases.sites_for_batch(b)
+    assert sites.n_sites > 20
+    r = oracle.site_genotypes(b, pop, sites)
+    nI = b.n_individuals
+    for s in range(sites.n_sites):
+        w = int(sites.site_win[s])
+        for i in range(nI):
+            if b.wi_n_good[w * nI + i] == 0:
+                assert r["gt"][s, i].tolist() == [-1, -1] and r["phred"][s, i].tolist() == [0, 0, 0]
+                continue
+            tot = r["lik"][s, i].sum()
+            if tot > 0:
+                assert abs(r["post"][s, i, 0] - r["lik"][s, i].max() / tot) < 1e-12
+                assert 0 <= r["phred"][s, i, 0] <= 99
