@@ -1034,7 +1034,7 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
     };
     mark(0);
     if (h1 > h0) {
-        k_prep<<<h1 - h0, 128, 0, st>>>(d, h0);
+        k_prep<<<h1 - h0, 128, 0, st>>>(d, h0, sp.ext);
         if ((rc = launch_check(c, "k_prep"))) return rc;
     }
     mark(1);
@@ -1501,6 +1501,8 @@ __global__ void __launch_bounds__(128) k_align_batch(int n, const int64_t* __res
     for (int x = 0; x < seg && fast; ++x) fast = fast_code(h[x]) != 5;
     bool six = fast;
     for (int x = 0; x < seg && six; ++x) six = fast_code(h[x]) != 4;
+    bool five = six;   // every gap-open >= ext: one three-input min per cell pair
+    for (int x = 0; x < seg && five; ++x) five = (int)g[x] >= ext;
     int v;
     if (fast) {
         u32* prof = prof_ws + prof_off[i];
@@ -1523,7 +1525,8 @@ __global__ void __launch_bounds__(128) k_align_batch(int n, const int64_t* __res
                 rec[x].sel = make_sel(ca, cb);
             }
         }
-        v = six ? band_dp_fast6(prof, rec, L, ext, nuc) : band_dp_fast(prof, rec, L, ext, nuc);
+        v = five ? band_dp_fast5(prof, rec, L, ext, nuc)
+                 : six ? band_dp_fast6(prof, rec, L, ext, nuc) : band_dp_fast(prof, rec, L, ext, nuc);
     } else {
         v = band_dp_general(h, g, r, q, L, ext, nuc);
     }

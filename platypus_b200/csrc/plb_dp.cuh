@@ -459,6 +459,166 @@ PLB_HD int band_dp_fast6(const u32* __restrict__ prof, const HapRec* __restrict_
     return (lo < hi ? lo : hi) + (extp + ext) * (L - 1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// 5-op variant: ONE three-input min per cell pair instead of two two-input ones.
+//
+// The reference opens a deletion from min(M, I) of the cell to the left (align.c:320-329), so the 6-op form
+// keeps MI = min(M, I) next to B = min(MI, D).  Where every gap-open penalty of the window is >= the
+// gap-extension penalty, opening from B gives the same value:
+//     min(D + ext, min(M, I, D) + open) = min(D + ext, MI + open, D + open) = min(D + ext, MI + open)
+// because D + open >= D + ext.  Then only B is needed - for the diagonal step and for the deletion - and it
+// is one VIMNMX3 of the three fresh states.  Per cell pair: PRMT, VIADD, VIADDMNMX, VIADDMNMX, VIMNMX3
+// = 4 ALU-pipe ops + 1 add (the 6-op form has 5 + 1).  The homopolymer table (chaplotype.pyx:64-67) drops
+// below ext = 3 only inside runs of 40 or more identical bases; k_prep flags such windows and they keep
+// the 6-op form.  Same profile / record format as band_dp_fast6.
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+PLB_HD u32 vmin3(u32 a, u32 b, u32 c) { return __vimin3_s16x2(a, b, c); }
+#else
+PLB_HD u32 vmin3(u32 a, u32 b, u32 c) { return vmin2(vmin2(a, b), c); }
+#endif
+
+struct DpState5 {
+    u32 ME[4], IE[4], DE[4], BE[4];
+    u32 MO[4], IO[4], DO[4], BO[4];
+    u32 P[8];
+    u32 Wg[8], Ws[8];
+    u32 acc[4];
+    u32 NM[4];   // 0x8000 in the lane whose row is L-1, 0x7FFF elsewhere
+};
+
+template <bool FIRST, bool LAST>
+PLB_HD void dp_group5(DpState5& s, const u32* __restrict__ prof, const HapRec* __restrict__ rec, int t0, int L,
+                      int ext, int extp) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int t = t0 + j;
+        s.P[j & 7] = prof[t];
+        {
+            HapRec r = rec[t + 4];
+            s.Wg[(j + 4) & 7] = r.gow;
+            s.Ws[(j + 4) & 7] = r.sel;
+        }
+        if (LAST) {
+            if (t == L - 1) s.NM[0] = (s.NM[0] & 0xFFFF0000u) | 0x8000u;
+        }
+        // ---------------- even half: cells (t+i, t-i) ----------------
+        u32 Dt[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const u32 pa = s.P[(j - k) & 7], pb = s.P[(j - k - 4) & 7];
+            const int w0 = (j + k) & 7, w1 = (j + k + 1) & 7;
+            const u32 Mn = vadd2(s.BE[k], prmt(pa, pb, s.Ws[w0]));
+            const u32 In = vaddmin2(s.MO[k], s.Wg[w0], s.IO[k]);
+            Dt[k] = vaddmin2(s.BO[k], s.Wg[w1], s.DO[k]);
+            s.ME[k] = Mn;
+            s.IE[k] = In;
+        }
+        s.DE[3] = Dt[2];
+        s.DE[2] = Dt[1];
+        s.DE[1] = Dt[0];
+        s.DE[0] = prmt(Dt[3], kInf2, 0x1054);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s.BE[k] = vmin3(s.ME[k], s.IE[k], s.DE[k]);
+        if (FIRST && j < 7) {  // lane j+1 on row y = -1, x = 2j+1: B := 0 (absolute), M, I := inf
+            const int k = (j + 1) & 3;
+            const bool lo = (j + 1) < 4;
+            const u32 keep = lo ? 0xFFFF0000u : 0x0000FFFFu;
+            const u32 inf1 = lo ? 0x00007000u : 0x70000000u;
+            const u32 zero = ((u32)(extp - ext * (2 * j + 1)) & 0xFFFFu) << (lo ? 0 : 16);  // 0 - f(x,-1)
+            s.ME[k] = (s.ME[k] & keep) | inf1;
+            s.IE[k] = (s.IE[k] & keep) | inf1;
+            s.DE[k] = (s.DE[k] & keep) | inf1;
+            s.BE[k] = (s.BE[k] & keep) | zero;
+        }
+        if (LAST) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const u32 dc = pack_s16x2(ext * 2 * k, ext * 2 * (k + 4));   // + ext*d, d = 2*lane
+                s.acc[k] = vmin2(s.acc[k], vmax2(vadd2(s.BE[k], dc), s.NM[k]));
+            }
+        }
+        // ---------------- odd half: cells (t+1+i, t-i) ----------------
+        u32 It[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const u32 pa = s.P[(j - k) & 7], pb = s.P[(j - k - 4) & 7];
+            const int w0 = (j + k) & 7, w1 = (j + k + 1) & 7;
+            const u32 Mn = vadd2(s.BO[k], prmt(pa, pb, s.Ws[w1]));
+            const u32 Dn = vaddmin2(s.BE[k], s.Wg[w1], s.DE[k]);
+            It[k] = vaddmin2(s.ME[k], s.Wg[w0], s.IE[k]);
+            s.MO[k] = Mn;
+            s.DO[k] = Dn;
+        }
+        s.IO[0] = It[1];
+        s.IO[1] = It[2];
+        s.IO[2] = It[3];
+        s.IO[3] = prmt(It[0], kInf2, 0x7632);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s.BO[k] = vmin3(s.MO[k], s.IO[k], s.DO[k]);
+        if (FIRST && j < 7) {  // row y = -1, x = 2j+2 (even): M := 0 and B := 0 (absolute), I, D := inf
+            const int k = (j + 1) & 3;
+            const bool lo = (j + 1) < 4;
+            const u32 keep = lo ? 0xFFFF0000u : 0x0000FFFFu;
+            const u32 inf1 = lo ? 0x00007000u : 0x70000000u;
+            const u32 zero = ((u32)(extp - ext * (2 * j + 2)) & 0xFFFFu) << (lo ? 0 : 16);
+            s.MO[k] = (s.MO[k] & keep) | zero;
+            s.IO[k] = (s.IO[k] & keep) | inf1;
+            s.DO[k] = (s.DO[k] & keep) | inf1;
+            s.BO[k] = (s.BO[k] & keep) | zero;
+        }
+        if (LAST) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const u32 dc = pack_s16x2(ext * (2 * k + 1), ext * (2 * (k + 4) + 1));  // d = 2*lane + 1
+                s.acc[k] = vmin2(s.acc[k], vmax2(vadd2(s.BO[k], dc), s.NM[k]));
+            }
+            u32 n3 = s.NM[3];
+            s.NM[3] = s.NM[2];
+            s.NM[2] = s.NM[1];
+            s.NM[1] = s.NM[0];
+            s.NM[0] = prmt(n3, 0x7FFF7FFFu, 0x1054);
+        }
+    }
+}
+
+// Requires kMinFastLen <= L <= kMaxFastLen, no 'N' in the segment and open[x] >= ext for every x of it.
+PLB_HD int band_dp_fast5(const u32* __restrict__ prof, const HapRec* __restrict__ rec, int L, int ext, int nuc) {
+    DpState5 s;
+    const int extp = ext + nuc;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        s.ME[k] = s.IE[k] = s.DE[k] = s.BE[k] = kInf2;
+        s.MO[k] = s.IO[k] = s.DO[k] = s.BO[k] = kInf2;
+        s.acc[k] = 0x7FFF7FFFu;
+        s.NM[k] = 0x7FFF7FFFu;
+    }
+    // "step -1": lane 0 of both vectors sits on row y = -1 (even lane: x = -1, odd lane: x = 0)
+    s.BE[0] = 0x70000000u | ((u32)(extp + ext) & 0xFFFFu);   // absolute 0 at (x=-1,y=-1)
+    s.MO[0] = 0x70000000u | ((u32)extp & 0xFFFFu);           // absolute 0 at (x=0,y=-1)
+    s.BO[0] = s.MO[0];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) s.P[m] = 0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        HapRec r = rec[m];
+        s.Wg[m] = r.gow;
+        s.Ws[m] = r.sel;
+    }
+#pragma unroll
+    for (int m = 4; m < 8; ++m) s.Wg[m] = s.Ws[m] = 0;
+
+    const int n = dp_steps(L);
+    dp_group5<true, false>(s, prof, rec, 0, L, ext, extp);
+    int t0 = 8;
+    for (; t0 < n - 16; t0 += 8) dp_group5<false, false>(s, prof, rec, t0, L, ext, extp);
+    dp_group5<false, true>(s, prof, rec, t0, L, ext, extp);
+    dp_group5<false, true>(s, prof, rec, t0 + 8, L, ext, extp);
+    u32 a = vmin2(vmin2(s.acc[0], s.acc[1]), vmin2(s.acc[2], s.acc[3]));
+    int lo = (int)(int16_t)(a & 0xFFFF), hi = (int)(int16_t)(a >> 16);
+    return (lo < hi ? lo : hi) + (extp + ext) * (L - 1);
+}
+
 // General path: arbitrary bytes, any read length >= 1.  Same recurrence cell by cell
 // (SURVEY §3.3), 32-bit scalars.  hap/open point at segment position 0.
 PLB_HD int band_dp_general(const uint8_t* __restrict__ hap, const uint8_t* __restrict__ open,

@@ -177,15 +177,17 @@ __device__ __forceinline__ u32 tab_slot0(u32 key, int bits) {
 // k_prep: one block per haplotype.  Gap-open table (chaplotype.pyx:552-590) into global scratch and
 // the per-window "general path" flag (haplotype bytes outside ACGTN need exact byte compares).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_prep(DevBatch b, int h_base) {
+__global__ void __launch_bounds__(128) k_prep(DevBatch b, int h_base, int ext) {
     const int h = h_base + blockIdx.x;
     const int len = (int)(b.hap_seq_off[h + 1] - b.hap_seq_off[h]);
     const uint8_t* hap = b.hap_seq + b.hap_seq_off[h];
     uint8_t* go = b.gap_open + b.hap_seq_off[h] + h;
-    int bad = 0, has_n = 0;
+    int bad = 0, has_n = 0, small_open = 0;
     for (int i = threadIdx.x; i <= len; i += blockDim.x) {
         if (i < len) {
-            go[i] = gap_open_at(hap, len, i);
+            const uint8_t g = gap_open_at(hap, len, i);
+            go[i] = g;
+            small_open |= ((int)g < ext);
             const int c = fast_code(hap[i]);
             bad |= (c == 5);
             has_n |= (c == 4);
@@ -195,9 +197,12 @@ __global__ void __launch_bounds__(128) k_prep(DevBatch b, int h_base) {
     }
     bad = __syncthreads_or(bad);
     has_n = __syncthreads_or(has_n);
-    // bit 0: bytes outside ACGTN (general path); bit 1: contains 'N' (8-op packed variant)
-    if ((bad || has_n) && threadIdx.x == 0)
-        atomicOr((unsigned int*)(b.win_flags + b.hap_win[h]), (bad ? 1u : 0u) | (has_n ? 2u : 0u));
+    small_open = __syncthreads_or(small_open);
+    // bit 0: bytes outside ACGTN (general path); bit 1: contains 'N' (8-op packed variant);
+    // bit 2: some gap-open penalty below the gap-extension penalty (6-op instead of 5-op variant)
+    if ((bad || has_n || small_open) && threadIdx.x == 0)
+        atomicOr((unsigned int*)(b.win_flags + b.hap_win[h]),
+                 (bad ? 1u : 0u) | (has_n ? 2u : 0u) | (small_open ? 4u : 0u));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1144,6 +1149,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
         // (k_general); this kernel then only turns their scores into log-likelihoods
         const int general = (wflags & 1) | sp.flank | sp.hla;
         const bool six = !(wflags & 2);   // no 'N' in the window's haplotypes: 6-op variant
+        const bool five = six && !(wflags & 4);   // ... and every gap-open >= ext: 5-op variant (one VIMNMX3)
         const int K = 2 * sp.ext + sp.nuc;
         // ---- TMA: one bulk copy per read for bases and one for qualities, straight into the tail of
         //      the read's profile row; every thread arrives on the mbarrier, copies add their bytes ----
@@ -1284,8 +1290,9 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
             const int p = (int)(tk >> 15), start = (int)(tk & 0x7FFFu);
             const int s = s_order[p / nh], g = p % nh;
             const DpSlot ds = s_slot[s];
-            const int v = six ? band_dp_fast6(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc)
-                              : band_dp_fast(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc);
+            const int v = five  ? band_dp_fast5(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc)
+                          : six ? band_dp_fast6(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc)
+                                : band_dp_fast(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc);
             atomicMin(&s_best[p], v);
         }
         __syncthreads();
