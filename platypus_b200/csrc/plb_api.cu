@@ -757,7 +757,7 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
     ch.a_occ = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / (ch.a_smem + 1024)));
     ch.d_smem = (size_t)ch.dp.prof_words * 4 + (size_t)ch.dp.rec_count * sizeof(HapRec) +
                 (size_t)ch.dp.max_slots * (sizeof(DpSlot) + 4) + (size_t)ch.dp.max_group * 4 + (size_t)ch.dp.max_pairs * 12 +
-                64;
+                (size_t)kProfTabWords * 4 + 256 + 64;
     if (ch.d_smem + 1024 > (size_t)c->smem_optin)
         return set_err(PLB_ERR_SHAPE, "dp tile needs %zu bytes of shared memory", ch.d_smem);
     ch.d_occ = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (ch.d_smem + 1024)));

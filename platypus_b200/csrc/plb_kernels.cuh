@@ -1036,6 +1036,7 @@ __device__ __forceinline__ int prof_row_words_dev(int L) {
     if (!((n >> 2) & 1)) n += 4;       // odd multiple of 16 bytes: conflict-free LDS.128
     return n;
 }
+constexpr int kProfTabWords = 5 * 128;   // k_dp's profile table: 5 base codes x 128 qualities
 constexpr int kTmaMaxLen = 192;   // rows up to this length are staged by TMA (raw bytes fit the row tail)
 __device__ __forceinline__ int tma_raw_bytes(int L) { return (L + 30 + 15) & ~15; }   // per array, 16-byte multiple
 
@@ -1068,12 +1069,19 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
     int32_t* s_order = s_roff + plan.max_group;                  // slots by decreasing read length
     int32_t* s_best = s_order + plan.max_slots;                  // per pair: best score
     u32* s_task = (u32*)(s_best + plan.max_pairs);               // compacted tasks
+    u32* s_ptab = s_task + 2 * plan.max_pairs;                   // profile word by (base code, quality): [5][128]
+    uint8_t* s_code = (uint8_t*)(s_ptab + kProfTabWords);        // byte -> base code 0..3 (exact A/C/G/T) or 4
     __shared__ int s_ntask;
     __shared__ __align__(8) uint64_t s_bar;   // counts the bytes of the tile's TMA copies
 
     const int tid = threadIdx.x;
     if (tid == 0) mbar_init(&s_bar, NTHR);
     u32 bar_phase = 0;
+    for (int c = tid; c < 256; c += NTHR) {
+        const int fc = fast_code((uint8_t)c);
+        s_code[c] = (uint8_t)(fc < 4 ? fc : 4);
+    }
+    int ptab_mode = -1;   // which variant (6-op / 8-op costs) the profile table currently holds
     __syncthreads();
     __shared__ int s_tile;
     while (true) {   // dynamic tile hand-out, see k_anchor
@@ -1151,6 +1159,15 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
         const bool six = !(wflags & 2);   // no 'N' in the window's haplotypes: 6-op variant
         const bool five = six && !(wflags & 4);   // ... and every gap-open >= ext: 5-op variant (one VIMNMX3)
         const int K = 2 * sp.ext + sp.nuc;
+        // Profile words come from a table indexed by (base code, quality): two LDS instead of a dozen ALU ops
+        // per read base (the ALU pipe is this kernel's bottleneck, the LSU pipe is nearly idle).
+        if (!general && ptab_mode != (int)six) {   // warp-uniform: wflags is per tile
+            for (int e = tid; e < kProfTabWords; e += NTHR) {
+                const int c = e >> 7, q = e & 127;
+                s_ptab[e] = six ? make_profile6(c < 4 ? c : 5, q, K) : make_profile(c < 4 ? c : 5, (u32)q);
+            }
+            ptab_mode = (int)six;   // visible to the profile pass after the barriers below
+        }
         // ---- TMA: one bulk copy per read for bases and one for qualities, straight into the tail of
         //      the read's profile row; every thread arrives on the mbarrier, copies add their bytes ----
         {
@@ -1226,7 +1243,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                     for (int k = 0; k < 6; ++k) {
                         const int y = lane + 32 * k;
                         if (y < n) {
-                            row[y] = y < ds.len ? profile_from_byte(cb[k], qb[k], K, six) : 0u;
+                            row[y] = y < ds.len ? s_ptab[((u32)s_code[cb[k]] << 7) | (qb[k] & 127u)] : 0u;
                         }
                     }
                     continue;
@@ -1245,7 +1262,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                     for (int k = 0; k < 6; ++k) {
                         const int y = y0 + lane + 32 * k;
                         if (y < n) {
-                            row[y] = y < ds.len ? profile_from_byte(cb[k], qb[k], K, six) : 0u;
+                            row[y] = y < ds.len ? s_ptab[((u32)s_code[cb[k]] << 7) | (qb[k] & 127u)] : 0u;
                         }
                     }
                 }
