@@ -224,3 +224,25 @@ def sites_for_batch(batch, seed=3):
             vs = rng.sample(range(nv), 3)
             sites.append((w, vs, is_ref(vs)))
     return SiteBatch.from_lists(batch, sites, min_posterior=5)
+
+
+def hla_fixture_batch(golden_dir):
+    """BASELINE config 1: the windows of tests/golden/hla_window_ref.npz (real reads of the reference's
+    test BAM, HLA-A allele haplotypes; made by tests/golden/make_hla_fixture.py).  Returns (batch, fixture)."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(golden_dir, "hla_window_ref.npz"))
+    windows = []
+    h = r = 0
+    for ws, we, hs, nh, ng, nb in g["windows"]:
+        haps = [g["hap"][g["hap_off"][h + k]:g["hap_off"][h + k + 1]].tobytes() for k in range(nh)]
+        rds = []
+        for k in range(ng + nb):
+            i = r + k
+            rds.append(Read(g["read"][g["read_off"][i]:g["read_off"][i + 1]].tobytes(),
+                            g["qual"][g["read_off"][i]:g["read_off"][i + 1]].tobytes(), int(g["read_pos"][i]),
+                            int(g["read_end"][i]), int(g["read_mapq"][i]), bool(g["read_qcfail"][i])))
+        windows.append(Window(int(ws), int(we), int(hs), haps, [(rds[:ng], rds[ng:], [])]))
+        h += nh
+        r += ng + nb
+    return WindowBatch.from_windows(windows, 1), g

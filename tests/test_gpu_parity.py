@@ -446,3 +446,18 @@ def test_n4_site_genotypes_synth(engine, oracle):
     np.testing.assert_allclose(got["lik"], want["lik"], rtol=RTOL_TIGHT, atol=0)
     called = (got["gt"][:, 0, 0] > 0) | (got["gt"][:, 0, 1] > 0)
     assert called.any() and not called.all()
+
+
+def test_config1_hla_bam_windows_golden_ref(engine, oracle, golden_dir):
+    """BASELINE config 1 on the GPU: real reads of the reference's test BAM against HLA-A allele haplotypes,
+    integer scores equal to the reference's calign.pyx in all three modes, LL / GL equal to the oracle."""
+    from tests.test_oracle import _check_hla_fixture
+    b, g = cases.hla_fixture_batch(golden_dir)
+    _check_hla_fixture(lambda kw: engine.window_loglik(b, opt=_abi.PlbOptions.default(**kw))[1], g)
+    for kw in ({}, dict(use_mapq_cap=1), dict(calc_flank_score=1)):
+        opt = _abi.PlbOptions.default(**kw)
+        got = engine.population_run(b, opt=opt, want_ll=True)
+        want, ll0, sc0, _ = oracle.population_run(b, opt)
+        assert np.array_equal(got["score"], sc0)
+        np.testing.assert_allclose(got["ll"], ll0, rtol=RTOL_TIGHT, atol=0)
+        _check_population(got, want)

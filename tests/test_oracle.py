@@ -317,3 +317,71 @@ def test_site_genotypes_edge_batch_properties(oracle):
             if tot > 0:
                 assert abs(r["post"][s, i, 0] - r["lik"][s, i].max() / tot) < 1e-12
                 assert 0 <= r["phred"][s, i, 0] <= 99
+
+
+# ---- BASELINE config 1: the reference's own test BAM -----------------------------------------------
+
+def _check_hla_fixture(score_of_mode, g):
+    """score_of_mode(mode kwargs) -> flat score array in PlbLoglikOut layout; golden scores hold every pair,
+    ours -1 where the QC-fail / overlap rule skips the read (chaplotype.pyx:343-361)."""
+    n_scored = 0
+    for name, kw in (("default", {}), ("hla", dict(use_mapq_cap=1)), ("flank", dict(calc_flank_score=1))):
+        sc = score_of_mode(kw)
+        want = g["score_" + name]
+        assert len(sc) == len(want)
+        live = sc != -1
+        assert np.array_equal(sc[live], want[live]), name
+        n_scored += int(live.sum())
+    assert n_scored > 1500
+
+
+def test_config1_hla_bam_windows_vs_reference_calign(oracle, golden_dir):
+    """Real reads of test/S55_test_realigned.bam against HLA-A allele haplotypes: the oracle's window path
+    (all three modes) equals mapAndAlignReadToHaplotype of the reference's calign.pyx pair by pair."""
+    from platypus_b200 import _abi
+    b, g = cases.hla_fixture_batch(golden_dir)
+    assert b.n_windows == 4 and b.n_reads > 150
+    _check_hla_fixture(lambda kw: oracle.window_loglik(b, _abi.PlbOptions.default(**kw))[1], g)
+
+
+def test_read_staging_rules():
+    """checkAndTrimRead / setWindowPointers mirrors (cwindow.pyx:332-481, 208-236) on hand-made reads."""
+    from platypus_b200 import reads as R
+    def mk(pos, flag=0, mapq=60, qual=None, cigar=None, isize=0, mpos=0, n=40):
+        q = bytearray(qual if qual is not None else [30] * n)
+        return R.AlignedRead(b"A" * n, q, cigar or [(0, n)], 0, pos, pos + n, mapq, flag, 0, mpos, isize)
+    opt, cnt = R.ReadFilterOptions(), {}
+    assert not R.check_and_trim_read(mk(10, mapq=5), None, opt, cnt) and cnt == {"low_map_qual": 1}
+    r = mk(10, qual=[30] * 15 + [3] * 25)
+    assert not R.check_and_trim_read(r, None, opt, cnt) and (r.flag & R.F_QCFAIL)          # < 20 good bases
+    r = mk(10, flag=R.F_PAIRED | R.F_MATE_UNMAPPED)
+    assert not R.check_and_trim_read(r, None, opt, cnt) and not (r.flag & R.F_QCFAIL)      # broken pair: no QC flag
+    a, b2 = mk(10), mk(10)
+    assert R.check_and_trim_read(a, None, opt, cnt) and not R.check_and_trim_read(b2, a, opt, cnt)   # duplicate
+    r = mk(10, qual=[30] * 36 + [4, 30, 2, 1])       # forward read: tail trimmed until a base with q >= 5
+    assert R.check_and_trim_read(r, None, opt, cnt) and list(r.qual[36:]) == [4, 30, 0, 0]
+    r = mk(10, flag=R.F_REVERSE, qual=[1, 2, 30] + [30] * 37)
+    assert R.check_and_trim_read(r, None, opt, cnt) and list(r.qual[:3]) == [0, 0, 30]
+    r = mk(10, cigar=[(4, 5), (0, 30), (4, 5)])      # soft clips -> quality 0
+    assert R.check_and_trim_read(r, None, opt, cnt) and list(r.qual[:5]) == [0] * 5 and list(r.qual[35:]) == [0] * 5
+    r = mk(10, flag=R.F_PAIRED | R.F_PROPER | R.F_MATE_REVERSE, isize=60, mpos=30)   # overlapping mates
+    assert R.check_and_trim_read(r, None, opt, cnt) and list(r.qual[-21:]) == [0] * 21 and r.qual[-22] == 30
+    rs = [mk(p) for p in (0, 30, 60, 90, 120)]
+    got = R.window_slice(rs, 65, 95)                 # first read with pos >= 65 - 40, dropping reads ending <= 65
+    assert [x.pos for x in got] == [30, 60, 90]
+
+
+def test_read_staging_on_reference_bam():
+    ref = os.environ.get("PLATYPUS_REFERENCE", "/root/reference")
+    bam = os.path.join(ref, "test", "S55_test_realigned.bam")
+    if not os.path.exists(bam):
+        pytest.skip("reference checkout not present")
+    from platypus_b200 import reads as R
+    refs, recs = R.decode_bam(bam)
+    assert refs[recs[0].chrom_id] == "6" and len(recs) == 2115              # SURVEY §4: 2115 reads on contig 6
+    assert max(r.rlen for r in recs) == 251
+    assert all(0 <= q <= 93 for r in recs[:200] for q in r.qual)
+    buf = R.ReadBuffer()
+    for r in recs:
+        buf.add(r)
+    assert len(buf.reads) + len(buf.bad_reads) == 2115 and len(buf.reads) > 1500
