@@ -1084,12 +1084,16 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
                 d, po, db->em_scratch, opt->max_em_iters, opt->use_em_likelihoods, w0, w1);
             if ((rc = launch_check(c, "k_population_few"))) return rc;
         } else {
-            int nthr_em = (int)std::min<size_t>(64, std::max<size_t>(1, (size_t)(40 * 1024) / (8 * (size_t)Hm)));
-            nthr_em = std::min(nthr_em, std::max(1, std::max(d.n_individuals, (int)d.max_variants)));
-            const size_t smem = (size_t)(2 + nthr_em) * Hm * 8;
+            // thread per individual: as many threads as shared memory allows partial-frequency rows for
+            size_t nt = std::min<size_t>(kPopMaxThreads, ((size_t)(96 * 1024) / (8 * (size_t)Hm)) - 3);
+            nt = std::min<size_t>(nt, (size_t)((d.n_individuals + 31) / 32) * 32);
+            nt = std::max<size_t>(32, nt / 32 * 32);
+            const size_t smem = (size_t)(3 + nt) * Hm * 8;
+            if (smem + 8192 > (size_t)c->smem_optin)
+                return set_err(PLB_ERR_SHAPE, "population model needs %zu bytes of shared memory for %d haplotypes", smem, Hm);
             if ((rc = opt_in_smem(k_population, smem))) return rc;
-            k_population<<<w1 - w0, 64, smem, st>>>(d, po, db->em_scratch, opt->max_em_iters, opt->use_em_likelihoods,
-                                                    nthr_em, w0);
+            k_population<<<w1 - w0, (unsigned)nt, smem, st>>>(d, po, db->em_scratch, opt->max_em_iters,
+                                                              opt->use_em_likelihoods, (int)nt, w0);
             if ((rc = launch_check(c, "k_population"))) return rc;
         }
     } else {

@@ -1499,99 +1499,138 @@ __global__ void __launch_bounds__(64) k_genotype(DevBatch b, const double* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_population: one block per window.  EM (cpopulation.pyx:384-457, 678-703), genotype calls
-// (:623-676), variant posteriors (:459-594).
+// k_population: one block per window, a THREAD PER INDIVIDUAL (many-sample batches; k_population_few
+// handles batches with a handful of individuals).  EM (cpopulation.pyx:384-457, 678-703), genotype calls
+// (:623-676), variant posteriors (:459-594).  blockDim.x = NT threads (a multiple of 32, up to 512);
+// thread t owns individuals t, t+NT, ...  Per individual every sum runs in the reference's order; sums
+// ACROSS individuals (new haplotype frequencies, the posterior's sums of logs) are reduced in a fixed
+// two-level order (32 per warp, then the warps), which differs from the reference's sequential order by
+// rounding only (<= 1e-13 relative).
+// Shared memory: (3 + NT) * Hmax doubles (freq, new, fp, per-thread partial frequencies).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_population(DevBatch b, PopOut out, double* __restrict__ em_scratch,
-                                                   int max_iters, int use_em, int nthr_em, int w_base) {
+constexpr int kPopMaxThreads = 512;
+
+// sum of one double per thread, deterministic: lanes of a warp in order, then the warps in order
+__device__ __forceinline__ double block_sum_ordered(double v, double* s_red /* [NT] */, double* s_w /* [NT/32] */) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    s_red[tid] = v;
+    __syncthreads();
+    if ((tid & 31) == 0) {
+        double a = 0.0;
+        for (int k = 0; k < 32; ++k) a += s_red[tid + k];
+        s_w[tid >> 5] = a;
+    }
+    __syncthreads();
+    double tot = 0.0;
+    for (int k = 0; k < (NT >> 5); ++k) tot += s_w[k];
+    __syncthreads();
+    return tot;
+}
+
+__global__ void __launch_bounds__(kPopMaxThreads) k_population(DevBatch b, PopOut out, double* __restrict__ em_scratch,
+                                                               int max_iters, int use_em, int nthr_em, int w_base) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int w = w_base + blockIdx.x;
     const int nInd = b.n_individuals;
+    const int NT = blockDim.x;
     const int H = b.win_hap_off[w + 1] - b.win_hap_off[w];
     const int G = H * (H + 1) / 2;
     const int Hmax = out.max_haps, Gmax = Hmax * (Hmax + 1) / 2;
     double* s_freq = (double*)smem;             // [Hmax]
     double* s_new = s_freq + Hmax;              // [Hmax]
-    double* s_part = s_new + Hmax;              // [nthr_em][Hmax]
+    double* s_fp = s_new + Hmax;                // [Hmax] frequencies without one variant's haplotypes
+    double* s_part = s_fp + Hmax;               // [NT][Hmax]
+    __shared__ double s_red[kPopMaxThreads];
+    __shared__ double s_w[kPopMaxThreads / 32];
     __shared__ double s_change;
-    __shared__ double s_ch[64];
-    __shared__ int s_nwith[64];
     const int tid = threadIdx.x;
+    (void)nthr_em;
     const double* gl = out.gl + (size_t)w * nInd * Gmax;
     double* emp = (out.em_post ? out.em_post : em_scratch) + (size_t)w * nInd * Gmax;
     const int32_t* ngood = b.wi_n_good + (size_t)w * nInd;
 
     const double eps = fmin(1e-3, 1.0 / (nInd * 2 * 2));  // cpopulation.pyx:684
-    for (int k = tid; k < Hmax; k += 64) s_freq[k] = k < H ? 1.0 / H : 0.0;
-    for (int i = 0; i < nInd; ++i)
-        if (ngood[i] == 0)
-            for (int g = tid; g < Gmax; g += 64) emp[(size_t)i * Gmax + g] = 0.0;
-    for (int i = 0; i < nInd; ++i)
-        for (int g = G + tid; g < Gmax; g += 64) emp[(size_t)i * Gmax + g] = 0.0;
+    for (int k = tid; k < Hmax; k += NT) s_freq[k] = k < H ? 1.0 / H : 0.0;
+    int my_with = 0;
+    for (int i = tid; i < nInd; i += NT) {
+        if (ngood[i] == 0) {
+            for (int g = 0; g < Gmax; ++g) emp[(size_t)i * Gmax + g] = 0.0;
+        } else {
+            ++my_with;
+            for (int g = G; g < Gmax; ++g) emp[(size_t)i * Gmax + g] = 0.0;
+        }
+    }
+    const int n_with = (int)(block_sum_ordered((double)my_with, s_red, s_w) + 0.5);   // individuals with reads
     if (tid == 0) s_change = eps + 1;
     __syncthreads();
     int iters = 0;
     while (s_change > eps && iters < max_iters) {  // uniform: s_change only changes between barriers
-        int nwith = 0;
-        if (tid < nthr_em) {
-            double* part = s_part + (size_t)tid * Hmax;
-            for (int k = 0; k < H; ++k) part[k] = 0.0;
-            for (int i = tid; i < nInd; i += nthr_em) {
-                if (ngood[i] == 0) continue;
-                ++nwith;
-                const double* gli = gl + (size_t)i * Gmax;
-                double* csr = emp + (size_t)i * Gmax;
-                double sum = 0.0;
-                int g = 0;
-                for (int s = 0; s < H; ++s)
-                    for (int r = s; r < H; ++r, ++g) {
-                        const double v = gli[g] * s_freq[s] * s_freq[r] * (1 + (r != s));
+        double* part = s_part + (size_t)tid * Hmax;
+        for (int k = 0; k < H; ++k) part[k] = 0.0;
+        for (int i = tid; i < nInd; i += NT) {
+            if (ngood[i] == 0) continue;
+            const double* gli = gl + (size_t)i * Gmax;
+            double* csr = emp + (size_t)i * Gmax;
+            double sum = 0.0;
+            int g = 0;
+            for (int s = 0; s < H; ++s)
+                for (int r = s; r < H; ++r, ++g) {
+                    const double v = gli[g] * s_freq[s] * s_freq[r] * (1 + (r != s));
+                    csr[g] = v;
+                    sum += v;
+                }
+            g = 0;
+            for (int s = 0; s < H; ++s)
+                for (int r = s; r < H; ++r, ++g) {
+                    double v = csr[g];
+                    if (sum > 0.0) {
+                        v /= sum;
                         csr[g] = v;
-                        sum += v;
                     }
-                g = 0;
-                for (int s = 0; s < H; ++s)
-                    for (int r = s; r < H; ++r, ++g) {
-                        double v = csr[g];
-                        if (sum > 0.0) {
-                            v /= sum;
-                            csr[g] = v;
-                        }
-                        part[s] += v;
-                        part[r] += v;
-                    }
-            }
+                    part[s] += v;
+                    part[r] += v;
+                }
         }
-        s_nwith[tid] = nwith;
         __syncthreads();
-        int n_with = 0;
-        for (int k = 0; k < 64; ++k) n_with += s_nwith[k];
+        // new frequency of haplotype k: partial sums of the threads, 32 per warp then the warps, in order
+        for (int k0 = 0; k0 < H; k0 += NT / 32) {     // warp j reduces haplotype k0 + j over its 32-thread groups
+            const int k = k0 + (tid >> 5);
+            double a = 0.0;
+            if (k < H) {
+                for (int t = (tid & 31); t < NT; t += 32) {   // lane l sums threads l, l+32, ... (order fixed)
+                    a += s_part[(size_t)t * Hmax + k];
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xFFFFFFFFu, a, o);
+            if (k < H && (tid & 31) == 0) s_new[k] = a;
+        }
+        __syncthreads();
         double mych = 0.0;
-        for (int k = tid; k < H; k += 64) {
-            double nf = 0.0;
-            for (int t = 0; t < nthr_em; ++t) nf += s_part[(size_t)t * Hmax + k];
+        for (int k = tid; k < H; k += NT) {
+            double nf = s_new[k];
             if (n_with > 0) nf = nf / (2 * n_with); else nf = s_freq[k];
             const double ch = fabs(s_freq[k] - nf);
             if (ch > mych) mych = ch;
             s_new[k] = nf;
         }
-        s_ch[tid] = mych;
+        s_red[tid] = mych;
         __syncthreads();
-        for (int k = tid; k < H; k += 64) s_freq[k] = s_new[k];
+        for (int k = tid; k < H; k += NT) s_freq[k] = s_new[k];
         if (tid == 0) {
             double m = 0.0;
-            for (int k = 0; k < 64; ++k) m = s_ch[k] > m ? s_ch[k] : m;
+            const int lim = H < NT ? H : NT;
+            for (int k = 0; k < lim; ++k) m = s_red[k] > m ? s_red[k] : m;
             s_change = m;
         }
         ++iters;
         __syncthreads();
     }
     if (out.freq)
-        for (int k = tid; k < Hmax; k += 64) out.freq[(size_t)w * Hmax + k] = s_freq[k];
+        for (int k = tid; k < Hmax; k += NT) out.freq[(size_t)w * Hmax + k] = s_freq[k];
     if (tid == 0 && out.em_iters) out.em_iters[w] = iters;
     // callGenotypes, cpopulation.pyx:623-676: first strict maximum
     if (out.call) {
-        for (int i = tid; i < nInd; i += 64) {
+        for (int i = tid; i < nInd; i += NT) {
             int bestg = -1;
             double bestv = 0.0;
             if (ngood[i] != 0) {
@@ -1605,55 +1644,55 @@ __global__ void __launch_bounds__(64) k_population(DevBatch b, PopOut out, doubl
             out.call[(size_t)w * nInd + i] = bestg;
         }
     }
-    // calculatePosterior, cpopulation.pyx:459-594, one thread per variant
+    // calculatePosterior, cpopulation.pyx:459-594: variants one after the other, individuals across threads
     if (out.var_phred && b.max_variants > 0 && b.win_n_var) {
         const int nvar = b.win_n_var[w];
         const uint64_t* masks = b.hap_var_mask + b.win_hap_off[w];
-        __syncthreads();
-        for (int v0 = 0; v0 < b.max_variants; v0 += nthr_em) {
-            const int v = v0 + tid;
-            if (tid < nthr_em && v < b.max_variants) {
-                double ph = 0.0;
-                if (v < nvar) {
-                    double* fp = s_part + (size_t)tid * Hmax;
+        for (int v = 0; v < b.max_variants; ++v) {
+            double ph = 0.0;
+            if (v < nvar) {   // uniform over the block
+                __syncthreads();
+                if (tid == 0) {
                     double sumf = 0.0;
                     for (int k = 0; k < H; ++k) {
                         if (!((masks[k] >> v) & 1ull)) {
-                            fp[k] = s_freq[k];
+                            s_fp[k] = s_freq[k];
                             sumf += s_freq[k];
                         } else {
-                            fp[k] = 0.0;
+                            s_fp[k] = 0.0;
                         }
                     }
                     if (sumf > 0)
-                        for (int k = 0; k < H; ++k) fp[k] /= sumf;
-                    double slv = 0.0, sln = 0.0;
-                    for (int i = 0; i < nInd; ++i) {
-                        if (ngood[i] == 0) continue;
-                        const double* gli = gl + (size_t)i * Gmax;
-                        double pv = 0.0, pn = 0.0;
-                        int g = 0;
-                        for (int r = 0; r < H; ++r)
-                            for (int s = r; s < H; ++s, ++g) {
-                                const double l = gli[g];
-                                const double factor = (r != s) ? 2.0 : 1.0;
-                                pv += (factor * s_freq[r] * s_freq[s] * l);
-                                pn += (factor * fp[r] * fp[s] * l);
-                            }
-                        slv += pv > 0 ? log(pv) : -708.0;
-                        sln += pn > 0 ? log(pn) : -708.0;
-                    }
-                    double ratio = exp(sln - slv);
-                    if (!(ratio > 1e-300)) ratio = 1e-300;
-                    const double prior = b.var_prior[(size_t)w * b.max_variants + v];
-                    ph = round(-10.0 * (log10(ratio * (1.0 - prior)) - log10(prior + ratio * (1.0 - prior))));
+                        for (int k = 0; k < H; ++k) s_fp[k] /= sumf;
                 }
-                out.var_phred[(size_t)w * b.max_variants + v] = ph;
+                __syncthreads();
+                double slv = 0.0, sln = 0.0;
+                for (int i = tid; i < nInd; i += NT) {
+                    if (ngood[i] == 0) continue;
+                    const double* gli = gl + (size_t)i * Gmax;
+                    double pv = 0.0, pn = 0.0;
+                    int g = 0;
+                    for (int r = 0; r < H; ++r)
+                        for (int s = r; s < H; ++s, ++g) {
+                            const double l = gli[g];
+                            const double factor = (r != s) ? 2.0 : 1.0;
+                            pv += (factor * s_freq[r] * s_freq[s] * l);
+                            pn += (factor * s_fp[r] * s_fp[s] * l);
+                        }
+                    slv += pv > 0 ? log(pv) : -708.0;
+                    sln += pn > 0 ? log(pn) : -708.0;
+                }
+                slv = block_sum_ordered(slv, s_red, s_w);
+                sln = block_sum_ordered(sln, s_red, s_w);
+                double ratio = exp(sln - slv);
+                if (!(ratio > 1e-300)) ratio = 1e-300;
+                const double prior = b.var_prior[(size_t)w * b.max_variants + v];
+                ph = round(-10.0 * (log10(ratio * (1.0 - prior)) - log10(prior + ratio * (1.0 - prior))));
             }
+            if (tid == 0) out.var_phred[(size_t)w * b.max_variants + v] = ph;
         }
     }
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // k_population_few: same model as k_population for batches with FEW individuals, where a thread per
