@@ -37,7 +37,7 @@ import numpy as np  # noqa: E402
 
 WINDOWS_PER_GPU = 10000
 N_HAPS, N_READS, READ_LEN, HAP_LEN = 8, 64, 150, 250
-CPU_SAMPLE_WINDOWS = 2000
+CPU_SAMPLE_WINDOWS = 10000   # the whole config-2 workload: ~0.8 s on 16 threads (~13 s of CPU work) per step
 METRIC = "pair_hmm_gcups"
 UNIT = "GCUPS"
 
@@ -305,7 +305,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1:
         cores = os.cpu_count() or 1
         g, kind, dt, ccells, nw = cpu_reference_run(batch, CPU_SAMPLE_WINDOWS, cores, steps=1, warmup=0)
-        g1, _, dt1, c1, nw1 = cpu_reference_run(batch, max(64, CPU_SAMPLE_WINDOWS // cores), 1, steps=1, warmup=0)
+        g1, _, dt1, c1, nw1 = cpu_reference_run(batch, 250, 1, steps=1, warmup=0)
         cpu = {"value": g, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": "first %d windows (%.3g cells) in %.2f s on %d threads; band alignment = %s; "
                          "single-thread: %.3f GCUPS on %d windows" %
