@@ -8,6 +8,9 @@ itself.  TEST INFRASTRUCTURE ONLY.
   oracle/_ref/calign*.so         the reference's src/cython/calign.pyx compiled in a scratch
   oracle/_ref/calign_ref_wrap*.so   directory with three non-algorithmic accommodations
                                   + our forwarding wrapper (L2 ground truth)
+  oracle/_ref/chaplotype*.so ... the reference's chaplotype.pyx / cgenotype.pyx and the modules they import,
+  oracle/_ref/l3_ref_wrap*.so    cythonized for Python 3 (build_l3_ref) + our forwarding wrapper (L3 ground
+                                 truth for per-read log-likelihoods and genotype likelihoods)
 
 Reference sources are never copied into the repo: scratch copies live in a temp dir that is
 deleted afterwards, only binaries land in oracle/_ref/ (git-ignored, travels to the GPU box).
@@ -123,6 +126,97 @@ def build_calign_ref(force=False):
     return mod, wrap
 
 
+L3_MODULES = ["htslibWrapper", "fastafile", "cerrormodel", "variant", "chaplotype", "cgenotype", "l3_ref_wrap"]
+
+
+def l3_ref_paths():
+    return [os.path.join(REF_OUT, m + _ext_suffix()) for m in L3_MODULES]
+
+
+def build_l3_ref(force=False):
+    """L3: the reference's chaplotype.pyx / cgenotype.pyx (+ the modules they import: variant, fastafile,
+    cerrormodel with tandem.c, calign with align.c), cythonized in a scratch dir for Python 3.
+
+    Accommodations, none touching the arithmetic of the path:
+      (i)-(iii) as for calign.pyx (hash_size literal; no runtime `import htslibWrapper`; htslibWrapper.pxd
+            replaced by an excerpt of itself - here the cAlignedRead struct (187-201), the flag accessors
+            (233-296) and the three function declarations (301-303))
+      (iv)  a shim htslibWrapper module defining those three functions as no-ops (destroyRead / compressRead /
+            uncompressRead: read-buffer housekeeping, never called on the likelihood path; the real module
+            needs htslib, which is not in this image)
+      (v)   `StandardError = Exception` added after the __future__ import of each module (Python 2 builtin)
+      (vi)  chaplotype.pyx:68  bytes(''.join([chr(x) ...])) -> bytes(bytearray([x ...]))   (same bytes; Python 3
+            cannot join characters into bytes) and chaplotype.pyx:447  bytes(''.join(bits)) -> bytes(b''.join(bits))
+    Reference sequence is served from memory by a FastaFile subclass in oracle/l3_ref_wrap.pyx instead of a
+    FASTA file (fastafile.pyx parses its index with Python 2 str methods); it returns the same bytes.
+    """
+    outs = l3_ref_paths()
+    if not have_reference():
+        return outs if all(os.path.exists(o) for o in outs) else None
+    try:
+        import Cython  # noqa: F401
+    except ImportError:
+        return None
+    cy = os.path.join(REF, "src", "cython")
+    srcs = [os.path.join(cy, f) for f in ("chaplotype.pyx", "cgenotype.pyx", "variant.pyx", "fastafile.pyx",
+                                           "cerrormodel.pyx", "calign.pyx")] + [os.path.join(HERE, "l3_ref_wrap.pyx")]
+    if not force and all(_newer(o, srcs) for o in outs):
+        return outs
+    os.makedirs(REF_OUT, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="plb_l3_")
+    try:
+        for m in ("chaplotype", "cgenotype", "variant", "fastafile", "calign", "cerrormodel"):
+            shutil.copy(os.path.join(cy, m + ".pyx"), tmp)
+            shutil.copy(os.path.join(cy, m + ".pxd"), tmp)
+        for f in ("align.c", "align.h", "tandem.c", "tandem.h"):
+            shutil.copy(os.path.join(REF, "src", "c", f), tmp)
+        shutil.copy(os.path.join(HERE, "l3_ref_wrap.pyx"), tmp)
+        lines = open(os.path.join(cy, "htslibWrapper.pxd")).read().split("\n")
+        excerpt = lines[186:201] + [""] + lines[232:296] + [""] + lines[300:303]
+        assert excerpt[0].startswith("ctypedef struct cAlignedRead") and "destroyRead" in excerpt[-3]
+        open(os.path.join(tmp, "htslibWrapper.pxd"), "w").write("\n".join(excerpt) + "\n")
+        open(os.path.join(tmp, "htslibWrapper.pyx"), "w").write(
+            "# shim (accommodation iv): the struct and flag accessors come from the excerpted .pxd\n"
+            "cdef void destroyRead(cAlignedRead* theRead):\n    pass\n"
+            "cdef void compressRead(cAlignedRead* read, char* refSeq, int refStart, int refEnd, int qualBinSize, int fullComp):\n    pass\n"
+            "cdef void uncompressRead(cAlignedRead* read, char* refSeq, int refStart, int refEnd, int qualBinSize):\n    pass\n")
+
+        def patch(name, pairs, future=True):
+            p = os.path.join(tmp, name)
+            s = open(p).read()
+            for old, new in pairs:
+                assert old in s, (name, old)
+                s = s.replace(old, new)
+            if future is not None:
+                fut = "from __future__ import division\n"
+                if fut in s:
+                    s = s.replace(fut, fut + "StandardError = Exception\n", 1)
+                else:
+                    s = "StandardError = Exception\n" + s
+            open(p, "w").write(s)
+        patch("calign.pyx", [("cdef int hash_size = 4**hash_nucs", "cdef int hash_size = 16384"),
+                             ("\nimport htslibWrapper\n", "\n#import htslibWrapper\n")], future=None)
+        patch("variant.pyx", [("\nimport htslibWrapper\n", "\n#import htslibWrapper\n")])
+        patch("fastafile.pyx", [])
+        patch("cerrormodel.pyx", [])
+        patch("cgenotype.pyx", [])
+        patch("chaplotype.pyx", [
+            ("cdef bytes homopolq = bytes(''.join([chr(int(33.5 + 10*log( (idx+1)*q )/log(0.1) )) for idx,q in enumerate(per_base_indel_errors)]))",
+             "cdef bytes homopolq = bytes(bytearray([int(33.5 + 10*log( (idx+1)*q )/log(0.1) ) for idx,q in enumerate(per_base_indel_errors)]))"),
+            ("self.haplotypeSequence = bytes(''.join(bitsOfMutatedSeq))", "self.haplotypeSequence = bytes(b''.join(bitsOfMutatedSeq))")])
+        inc = sysconfig.get_paths()["include"]
+        cflags = REF_CFLAGS + ["-shared", "-w", "-I" + tmp, "-I" + inc]
+        for m in ("htslibWrapper", "fastafile", "calign", "cerrormodel", "variant", "chaplotype", "cgenotype"):
+            _run([sys.executable, "-m", "cython", "-2", "-I", tmp, m + ".pyx", "-o", m + ".c"], cwd=tmp)
+        _run([sys.executable, "-m", "cython", "-3", "-I", tmp, "l3_ref_wrap.pyx", "-o", "l3_ref_wrap.c"], cwd=tmp)
+        extra = {"cerrormodel": ["tandem.c"], "chaplotype": ["align.c"], "calign": ["align.c"]}
+        for m in ("htslibWrapper", "fastafile", "calign", "cerrormodel", "variant", "chaplotype", "cgenotype", "l3_ref_wrap"):
+            _run(["gcc"] + cflags + [m + ".c"] + extra.get(m, []) + ["-o", os.path.join(REF_OUT, m + _ext_suffix())], cwd=tmp)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return outs
+
+
 def build_all(force=False, verbose=False):
     out = {"oracle": build_oracle(force), "align_ref": build_align_ref(force)}
     try:
@@ -130,6 +224,11 @@ def build_all(force=False, verbose=False):
     except Exception as e:  # the L2 reference build is a bonus; L1 + restatement still stand
         out["calign_ref"] = None
         out["calign_ref_error"] = str(e)
+    try:
+        out["l3_ref"] = build_l3_ref(force)
+    except Exception as e:  # bonus as well: without it L3 parity rests on the committed golden vectors
+        out["l3_ref"] = None
+        out["l3_ref_error"] = str(e)
     if verbose:
         for k, v in out.items():
             print(k, "->", v)

@@ -188,6 +188,23 @@ def ref_calign():
         return None
 
 
+def ref_l3():
+    """The reference's chaplotype.pyx / cgenotype.pyx behind oracle/l3_ref_wrap.pyx, or None."""
+    try:
+        paths = _build.build_l3_ref()
+    except Exception:
+        paths = None
+    if not paths:
+        return None
+    d = os.path.dirname(paths[0])
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    try:
+        return importlib.import_module("l3_ref_wrap")
+    except ImportError:
+        return None
+
+
 # ---- restatement entry points -----------------------------------------------------------------
 def band_align(hap_seg: bytes, read: bytes, qual: bytes, gap_open: bytes, ext=3, nuc=2):
     assert len(hap_seg) >= len(read) + 15 and len(gap_open) >= len(read) + 15

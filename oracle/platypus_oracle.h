@@ -7,12 +7,18 @@
  *
  * Parity pinning: the reference ships no golden vectors for this path.
  * The restatement is pinned by executing the reference itself in the build container:
- *   L1  plo_band_align        vs unmodified src/c/align.c          (oracle/_ref/libalign_ref.so)
- *   L2  plo_map_and_align     vs src/cython/calign.pyx             (oracle/_ref/calign_ref*.so)
- * and the resulting inputs/outputs are committed as tests/golden/*.npz.
- * L3 (chaplotype/cgenotype/cpopulation arithmetic) cannot be built here (Python 2,
- * htslib, FASTA object graph): those functions are restated line-by-line from the
- * cited lines and are "parity unpinned" above the integer score.
+ *   L1  plo_band_align, plo_band_align_tb, plo_flank_score   vs unmodified src/c/align.c
+ *                                                             (oracle/_ref/libalign_ref.so)
+ *   L2  plo_map_and_align(_ex)                                vs src/cython/calign.pyx
+ *                                                             (oracle/_ref/calign_ref_wrap*.so)
+ *   L3  per-read log-likelihoods (Haplotype.alignReads, default / HLA / flank mode), genotype
+ *       log-likelihoods, GOF and hapLike (DiploidGenotype.calculateDataLikelihood)
+ *                                                             vs src/cython/chaplotype.pyx, cgenotype.pyx
+ *                                                             (oracle/_ref/l3_ref_wrap*.so)
+ * and the resulting inputs/outputs are committed as tests/golden/ *.npz.
+ * Still restated without a reference run ("parity unpinned"): the max-rescale, EM, genotype calls and
+ * variant posteriors of cpopulation.pyx and the per-site calls of vcfutils.pyx (those modules import the
+ * reference's whole Python-2 I/O stack and could not be built here).
  */
 #ifndef PLATYPUS_ORACLE_H
 #define PLATYPUS_ORACLE_H

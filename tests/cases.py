@@ -246,3 +246,120 @@ def hla_fixture_batch(golden_dir):
         h += nh
         r += ng + nb
     return WindowBatch.from_windows(windows, 1), g
+
+
+def l3_window_case(seed):
+    """One window for the reference's Haplotype / DiploidGenotype classes (oracle/l3_ref_wrap.pyx): a random
+    genome, a 40-60 bp window, 2-5 haplotypes made of SNP / insertion / deletion variants (as
+    (refPos, removed, added) tuples, sorted, non-overlapping) and good / bad / broken-mate reads drawn from the
+    haplotypes with errors, low qualities, mapq 0, QC-fail flags, reads that barely overlap the window and
+    reads hanging over the haplotype ends."""
+    rng = random.Random(seed)
+    genome = _rand_seq(rng, 2400)
+    if seed % 3 == 0:   # a homopolymer inside the window (context-dependent gap-open penalties)
+        genome = genome[:1210] + bytes([rng.choice(ACGT)]) * rng.randint(6, 14) + genome[1224:]
+        genome = genome[:2400]
+    ws = 1200
+    we = ws + rng.randint(40, 60)
+    max_read_len = rng.choice([100, 150])
+    n_haps = rng.randint(2, 5)
+    hap_variants = [[]]
+    while len(hap_variants) < n_haps:
+        vs, pos = [], ws + rng.randint(2, 8)
+        for _ in range(rng.randint(1, 3)):
+            if pos >= we - 4:
+                break
+            kind = rng.random()
+            if kind < 0.6:
+                alt = rng.choice([c for c in ACGT if c != genome[pos]])
+                vs.append((pos, genome[pos:pos + 1], bytes([alt])))
+            elif kind < 0.8:
+                vs.append((pos, b"", _rand_seq(rng, rng.randint(1, 3))))
+            else:
+                k = rng.randint(1, 3)
+                vs.append((pos, genome[pos:pos + k], b""))
+            pos += rng.randint(5, 15)
+        if vs and vs not in hap_variants:
+            hap_variants.append(vs)
+    flank = min(2 * max_read_len, 500)
+
+    def apply(vs):   # plain substitution, only to draw reads from (the reference builds its own sequences)
+        out, cur = bytearray(), ws - flank
+        for p, rem, add in vs:
+            if rem and add:
+                out += genome[cur:p] + add
+                cur = p + len(rem)
+            elif add:
+                out += genome[cur:p + 1] + add
+                cur = p + 1
+            else:
+                out += genome[cur:p]
+                cur = p + len(rem)
+        out += genome[cur:we + flank]
+        return bytes(out)
+    seqs = [apply(vs) for vs in hap_variants]
+
+    def reads(n):
+        out = []
+        for _ in range(n):
+            L = rng.choice([30, 60, 75, max_read_len])
+            src = rng.choice(seqs)
+            u = rng.random()
+            if u < 0.75:
+                idx = rng.randint(max(0, flank - L + 8), min(len(src) - L - 16, flank + (we - ws) - 8))
+            elif u < 0.9:
+                idx = rng.randint(0, len(src) - L - 16)            # may not overlap the window at all
+            else:
+                idx = rng.randint(0, 4)                           # starts at the haplotype's left end
+            seq = mutate(rng, src[idx:], L, n_rate=0.003)
+            qual = bytes(0 if rng.random() < 0.05 else rng.randint(2, 41) for _ in range(L))
+            pos = ws - flank + idx + rng.choice([0, 0, 0, rng.randint(-4, 4), rng.randint(-40, 10)])
+            flag = 512 if rng.random() < 0.06 else 0
+            out.append((seq, qual, pos, pos + L, rng.choice([60, 60, 60, 40, 23, 5, 0]), flag))
+        return out
+    return dict(genome=genome, win_start=ws, win_end=we, hap_variants=hap_variants, good=reads(rng.randint(4, 14)),
+                bad=reads(rng.randint(0, 4)), broken=reads(rng.randint(0, 3)), max_read_len=max_read_len)
+
+
+def l3_case_batch(case, hap_seqs, hap_start):
+    """WindowBatch of an l3_window_case, haplotype sequences as the reference built them."""
+    def mk(t):
+        return Read(t[0], t[1], t[2], t[3], t[4], bool(t[5] & 512))
+    w = Window(case["win_start"], case["win_end"], hap_start, list(hap_seqs),
+               [([mk(t) for t in case["good"]], [mk(t) for t in case["bad"]], [mk(t) for t in case["broken"]])])
+    return WindowBatch.from_windows([w], 1)
+
+
+L3_MODES = [(0, 0), (1, 0), (0, 1), (1, 1)]   # (use_mapq_cap, calc_flank_score)
+
+
+def l3_golden_cases(golden_dir):
+    """Yields (batch, {(hla, flank): (ll [H][T], geno [G][4] = logL, gof, hap1Like, hap2Like)}) for the windows
+    of tests/golden/l3_ref.npz (outputs of the reference's own chaplotype.pyx / cgenotype.pyx)."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(golden_dir, "l3_ref.npz"))
+    for seed in range(int(g["n_cases"])):
+        c = l3_window_case(seed)
+        off, hs = g["c%d_hap_off" % seed], g["c%d_hap" % seed]
+        haps = [hs[off[k]:off[k + 1]].tobytes() for k in range(len(off) - 1)]
+        b = l3_case_batch(c, haps, int(g["c%d_hap_start" % seed]))
+        yield b, {m: (g["c%d_m%d%d_ll" % (seed, m[0], m[1])], g["c%d_m%d%d_geno" % (seed, m[0], m[1])]) for m in L3_MODES}
+
+
+def check_l3(ll, pop, want_ll, want_geno, rtol=1e-9):
+    """Per-read log-likelihoods, genotype log-likelihoods (ours are stored rescaled: log(gl) + gl_log_max), GOF and
+    hapLike of ONE single-individual window against the reference's values."""
+    import numpy as np
+    H, T = want_ll.shape
+    np.testing.assert_allclose(np.asarray(ll).reshape(H, T), want_ll, rtol=1e-12, atol=0)
+    G = H * (H + 1) // 2
+    logl = np.log(pop["gl"][0, 0, :G]) + pop["gl_log_max"][0, 0]
+    np.testing.assert_allclose(logl, want_geno[:, 0], rtol=rtol, atol=1e-9)
+    np.testing.assert_allclose(pop["gof"][0, :G, 0], want_geno[:, 1], rtol=1e-12, atol=0)
+    g = 0
+    for i in range(H):
+        for j in range(i, H):
+            np.testing.assert_allclose(pop["hap_like"][0, 0, i], want_geno[g, 2], rtol=1e-12, atol=0)
+            np.testing.assert_allclose(pop["hap_like"][0, 0, j], want_geno[g, 3], rtol=1e-12, atol=0)
+            g += 1

@@ -12,6 +12,10 @@ Generates the golden fixtures in this directory.  Run in the BUILD container, wh
   calign_modes_ref.npz  mapAndAlignReadToHaplotype with doCalculateFlankScore = 1 and with
                   HLA-style clipped reads whose hashes stay those of the unclipped read
                   (chaplotype.pyx:637-655), from the reference's calign.pyx
+  l3_ref.npz      per-read log-likelihoods (Haplotype.alignReads) and genotype log-likelihoods / GOF / hapLike
+                  (DiploidGenotype.calculateDataLikelihood) from the reference's own chaplotype.pyx / cgenotype.pyx
+                  (oracle/_ref/l3_ref_wrap*.so) for the windows of tests/cases.l3_window_case, in default, HLA and
+                  flank mode; haplotype sequences as the reference's Haplotype constructor built them
   window_modes_restated.npz  the edge batch under --calculateFlankScore=1 / --HLATyping=1 from the
                   oracle (restated above the integer score)
   window_restated.npz  a small multi-individual batch with per-read LL, GL, EM frequencies and
@@ -159,6 +163,30 @@ def make_window_modes():
     print("window_modes_restated.npz written")
 
 
+def make_l3(n=60):
+    W = O.ref_l3()
+    assert W is not None, "reference chaplotype.pyx / cgenotype.pyx not built (need /root/reference + Cython)"
+    out = {}
+    modes = [(0, 0), (1, 0), (0, 1), (1, 1)]
+    n_ll = 0
+    for seed in range(n):
+        c = cases.l3_window_case(seed)
+        for hla, flank in modes:
+            r = W.window_likelihoods(c["genome"], c["win_start"], c["win_end"], c["hap_variants"], c["good"], c["bad"],
+                                     c["broken"], c["max_read_len"], hla, flank)
+            key = "c%d_m%d%d_" % (seed, hla, flank)
+            if (hla, flank) == (0, 0):
+                ho, hs = pack(r["hap_seq"])
+                out["c%d_hap_off" % seed] = ho
+                out["c%d_hap" % seed] = hs
+                out["c%d_hap_start" % seed] = np.int32(r["hap_start"])
+            out[key + "ll"] = np.array(r["ll"], np.float64)
+            out[key + "geno"] = np.array([g[2:] for g in r["genotypes"]], np.float64)   # logL, gof, hap1Like, hap2Like
+            n_ll += out[key + "ll"].size
+    np.savez_compressed(os.path.join(HERE, "l3_ref.npz"), n_cases=np.int32(n), **out)
+    print("l3_ref.npz:", n, "windows x", len(modes), "modes,", n_ll, "log-likelihoods")
+
+
 def make_window():
     batch = cases.edge_batch(seed=5)
     arrs, ll, sc, st = O.population_run(batch)
@@ -172,5 +200,6 @@ if __name__ == "__main__":
     make_calign()
     make_align_tb()
     make_calign_modes()
+    make_l3()
     make_window()
     make_window_modes()

@@ -461,3 +461,15 @@ def test_config1_hla_bam_windows_golden_ref(engine, oracle, golden_dir):
         assert np.array_equal(got["score"], sc0)
         np.testing.assert_allclose(got["ll"], ll0, rtol=RTOL_TIGHT, atol=0)
         _check_population(got, want)
+
+
+def test_l3_golden_ref(engine, golden_dir):
+    """GPU per-read log-likelihoods, genotype likelihoods, GOF and hapLike against outputs of the reference's own
+    chaplotype.pyx / cgenotype.pyx (tests/golden/l3_ref.npz), all four mode combinations."""
+    n = 0
+    for b, want in cases.l3_golden_cases(golden_dir):
+        for (hla, flank), (w_ll, w_geno) in want.items():
+            got = engine.population_run(b, opt=_abi.PlbOptions.default(use_mapq_cap=hla, calc_flank_score=flank), want_ll=True)
+            cases.check_l3(got["ll"], got, w_ll, w_geno)
+            n += w_ll.size
+    assert n > 9000

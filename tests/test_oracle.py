@@ -385,3 +385,34 @@ def test_read_staging_on_reference_bam():
     for r in recs:
         buf.add(r)
     assert len(buf.reads) + len(buf.bad_reads) == 2115 and len(buf.reads) > 1500
+
+
+# ---- L3 pinned: the reference's own Haplotype / DiploidGenotype classes -------------------------------
+
+def test_golden_l3_ref(oracle, golden_dir):
+    """Per-read log-likelihoods (Haplotype.alignReads), genotype log-likelihoods, GOF and hapLike
+    (DiploidGenotype.calculateDataLikelihood) against outputs of the reference's own chaplotype.pyx /
+    cgenotype.pyx, in default, HLA, flank and HLA+flank mode."""
+    from platypus_b200 import _abi
+    n = 0
+    for b, want in cases.l3_golden_cases(golden_dir):
+        for (hla, flank), (w_ll, w_geno) in want.items():
+            arrs, ll, sc, _ = oracle.population_run(b, _abi.PlbOptions.default(use_mapq_cap=hla, calc_flank_score=flank))
+            cases.check_l3(ll, arrs, w_ll, w_geno)
+            n += w_ll.size
+    assert n > 9000
+
+
+def test_vs_ref_l3_fuzz(oracle):
+    W = oracle.ref_l3()
+    if W is None:
+        pytest.skip("oracle/_ref/l3_ref_wrap not built (no reference checkout)")
+    from platypus_b200 import _abi
+    for seed in range(1000, 1120):
+        c = cases.l3_window_case(seed)
+        hla, flank = cases.L3_MODES[seed % 4]
+        r = W.window_likelihoods(c["genome"], c["win_start"], c["win_end"], c["hap_variants"], c["good"], c["bad"],
+                                 c["broken"], c["max_read_len"], hla, flank)
+        b = cases.l3_case_batch(c, r["hap_seq"], r["hap_start"])
+        arrs, ll, sc, _ = oracle.population_run(b, _abi.PlbOptions.default(use_mapq_cap=hla, calc_flank_score=flank))
+        cases.check_l3(ll, arrs, np.array(r["ll"]), np.array([g[2:] for g in r["genotypes"]]))
