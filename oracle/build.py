@@ -114,7 +114,8 @@ def build_calign_ref(force=False):
         lines = open(os.path.join(cy, "htslibWrapper.pxd")).read().split("\n")
         excerpt = lines[186:201] + [""] + lines[232:296]
         assert excerpt[0].startswith("ctypedef struct cAlignedRead")
-        open(os.path.join(tmp, "htslibWrapper.pxd"), "w").write("\n".join(excerpt) + "\n")
+        classes = "\ncdef class Samfile:\n    pass\n\ncdef class ReadIterator:\n    pass\n"
+        open(os.path.join(tmp, "htslibWrapper.pxd"), "w").write("\n".join(excerpt) + "\n" + classes)
         inc = sysconfig.get_paths()["include"]
         _run([sys.executable, "-m", "cython", "-2", "-I", tmp, "calign.pyx", "-o", "calign.c"], cwd=tmp)
         _run([sys.executable, "-m", "cython", "-3", "-I", tmp, "calign_ref_wrap.pyx", "-o", "calign_ref_wrap.c"], cwd=tmp)
@@ -126,7 +127,8 @@ def build_calign_ref(force=False):
     return mod, wrap
 
 
-L3_MODULES = ["htslibWrapper", "fastafile", "cerrormodel", "variant", "chaplotype", "cgenotype", "l3_ref_wrap"]
+L3_MODULES = ["htslibWrapper", "fastafile", "cerrormodel", "variant", "chaplotype", "cgenotype", "vcfutils", "cwindow",
+              "cpopulation", "l3_ref_wrap"]
 
 
 def l3_ref_paths():
@@ -134,8 +136,9 @@ def l3_ref_paths():
 
 
 def build_l3_ref(force=False):
-    """L3: the reference's chaplotype.pyx / cgenotype.pyx (+ the modules they import: variant, fastafile,
-    cerrormodel with tandem.c, calign with align.c), cythonized in a scratch dir for Python 3.
+    """L3: the reference's chaplotype.pyx / cgenotype.pyx / cpopulation.pyx (+ the modules they import: variant,
+    fastafile, cwindow, cerrormodel with tandem.c, calign with align.c), cythonized in a scratch dir for Python 3
+    with Cython's legacy_implicit_noexcept (the exception semantics of the Cython 0.2x the reference targets).
 
     Accommodations, none touching the arithmetic of the path:
       (i)-(iii) as for calign.pyx (hash_size literal; no runtime `import htslibWrapper`; htslibWrapper.pxd
@@ -143,7 +146,10 @@ def build_l3_ref(force=False):
             (233-296) and the three function declarations (301-303))
       (iv)  a shim htslibWrapper module defining those three functions as no-ops (destroyRead / compressRead /
             uncompressRead: read-buffer housekeeping, never called on the likelihood path; the real module
-            needs htslib, which is not in this image)
+            needs htslib, which is not in this image) and two empty classes Samfile / ReadIterator that
+            cwindow.pxd names but cwindow.pyx never touches; a shim vcfutils module with empty vcfINFO /
+            vcfFILTER (VCF INFO/FILTER formatting, only reached by Population.call(maxIters, computeVCFFields=1);
+            the real vcfutils imports the Python-2 vcf.py and the BAM I/O stack)
       (v)   `StandardError = Exception` added after the __future__ import of each module (Python 2 builtin)
       (vi)  chaplotype.pyx:68  bytes(''.join([chr(x) ...])) -> bytes(bytearray([x ...]))   (same bytes; Python 3
             cannot join characters into bytes) and chaplotype.pyx:447  bytes(''.join(bits)) -> bytes(b''.join(bits))
@@ -158,14 +164,14 @@ def build_l3_ref(force=False):
     except ImportError:
         return None
     cy = os.path.join(REF, "src", "cython")
-    srcs = [os.path.join(cy, f) for f in ("chaplotype.pyx", "cgenotype.pyx", "variant.pyx", "fastafile.pyx",
-                                           "cerrormodel.pyx", "calign.pyx")] + [os.path.join(HERE, "l3_ref_wrap.pyx")]
+    srcs = [os.path.join(cy, f) for f in ("chaplotype.pyx", "cgenotype.pyx", "cpopulation.pyx", "cwindow.pyx", "variant.pyx",
+                                           "fastafile.pyx", "cerrormodel.pyx", "calign.pyx")] + [os.path.join(HERE, "l3_ref_wrap.pyx")]
     if not force and all(_newer(o, srcs) for o in outs):
         return outs
     os.makedirs(REF_OUT, exist_ok=True)
     tmp = tempfile.mkdtemp(prefix="plb_l3_")
     try:
-        for m in ("chaplotype", "cgenotype", "variant", "fastafile", "calign", "cerrormodel"):
+        for m in ("chaplotype", "cgenotype", "variant", "fastafile", "calign", "cerrormodel", "cwindow", "cpopulation"):
             shutil.copy(os.path.join(cy, m + ".pyx"), tmp)
             shutil.copy(os.path.join(cy, m + ".pxd"), tmp)
         for f in ("align.c", "align.h", "tandem.c", "tandem.h"):
@@ -174,12 +180,24 @@ def build_l3_ref(force=False):
         lines = open(os.path.join(cy, "htslibWrapper.pxd")).read().split("\n")
         excerpt = lines[186:201] + [""] + lines[232:296] + [""] + lines[300:303]
         assert excerpt[0].startswith("ctypedef struct cAlignedRead") and "destroyRead" in excerpt[-3]
-        open(os.path.join(tmp, "htslibWrapper.pxd"), "w").write("\n".join(excerpt) + "\n")
+        classes = "\ncdef class Samfile:\n    pass\n\ncdef class ReadIterator:\n    pass\n"
+        open(os.path.join(tmp, "htslibWrapper.pxd"), "w").write("\n".join(excerpt) + "\n" + classes)
         open(os.path.join(tmp, "htslibWrapper.pyx"), "w").write(
             "# shim (accommodation iv): the struct and flag accessors come from the excerpted .pxd\n"
             "cdef void destroyRead(cAlignedRead* theRead):\n    pass\n"
             "cdef void compressRead(cAlignedRead* read, char* refSeq, int refStart, int refEnd, int qualBinSize, int fullComp):\n    pass\n"
-            "cdef void uncompressRead(cAlignedRead* read, char* refSeq, int refStart, int refEnd, int qualBinSize):\n    pass\n")
+            "cdef void uncompressRead(cAlignedRead* read, char* refSeq, int refStart, int refEnd, int qualBinSize):\n    pass\n"
+            + classes)
+        open(os.path.join(tmp, "vcfutils.pxd"), "w").write(
+            "from fastafile cimport FastaFile\n"
+            "cdef dict vcfINFO(double* haplotypeFrequencies, dict variantPosteriors, list genotypeCalls, list genotypes, "
+            "list haplotypes, list readBuffers, int nHaplotypes, options, FastaFile refFile)\n"
+            "cdef dict vcfFILTER(list genotypeCalls, list haplotypes, dict vcfInfo, dict varsByPos, options)\n")
+        open(os.path.join(tmp, "vcfutils.pyx"), "w").write(
+            "# shim (accommodation iv): never called with computeVCFFields = 0\n"
+            "cdef dict vcfINFO(double* haplotypeFrequencies, dict variantPosteriors, list genotypeCalls, list genotypes, "
+            "list haplotypes, list readBuffers, int nHaplotypes, options, FastaFile refFile):\n    return {}\n"
+            "cdef dict vcfFILTER(list genotypeCalls, list haplotypes, dict vcfInfo, dict varsByPos, options):\n    return {}\n")
 
         def patch(name, pairs, future=True):
             p = os.path.join(tmp, name)
@@ -200,17 +218,22 @@ def build_l3_ref(force=False):
         patch("fastafile.pyx", [])
         patch("cerrormodel.pyx", [])
         patch("cgenotype.pyx", [])
+        patch("cwindow.pyx", [])
+        patch("cpopulation.pyx", [])
         patch("chaplotype.pyx", [
             ("cdef bytes homopolq = bytes(''.join([chr(int(33.5 + 10*log( (idx+1)*q )/log(0.1) )) for idx,q in enumerate(per_base_indel_errors)]))",
              "cdef bytes homopolq = bytes(bytearray([int(33.5 + 10*log( (idx+1)*q )/log(0.1) ) for idx,q in enumerate(per_base_indel_errors)]))"),
             ("self.haplotypeSequence = bytes(''.join(bitsOfMutatedSeq))", "self.haplotypeSequence = bytes(b''.join(bitsOfMutatedSeq))")])
         inc = sysconfig.get_paths()["include"]
         cflags = REF_CFLAGS + ["-shared", "-w", "-I" + tmp, "-I" + inc]
-        for m in ("htslibWrapper", "fastafile", "calign", "cerrormodel", "variant", "chaplotype", "cgenotype"):
-            _run([sys.executable, "-m", "cython", "-2", "-I", tmp, m + ".pyx", "-o", m + ".c"], cwd=tmp)
+        ref_mods = ("htslibWrapper", "fastafile", "calign", "cerrormodel", "variant", "chaplotype", "cgenotype", "vcfutils",
+                    "cwindow", "cpopulation")
+        for m in ref_mods:
+            _run([sys.executable, "-m", "cython", "-2", "-X", "legacy_implicit_noexcept=True", "-I", tmp, m + ".pyx", "-o", m + ".c"],
+                 cwd=tmp)
         _run([sys.executable, "-m", "cython", "-3", "-I", tmp, "l3_ref_wrap.pyx", "-o", "l3_ref_wrap.c"], cwd=tmp)
         extra = {"cerrormodel": ["tandem.c"], "chaplotype": ["align.c"], "calign": ["align.c"]}
-        for m in ("htslibWrapper", "fastafile", "calign", "cerrormodel", "variant", "chaplotype", "cgenotype", "l3_ref_wrap"):
+        for m in ref_mods + ("l3_ref_wrap",):
             _run(["gcc"] + cflags + [m + ".c"] + extra.get(m, []) + ["-o", os.path.join(REF_OUT, m + _ext_suffix())], cwd=tmp)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

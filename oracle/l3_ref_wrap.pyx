@@ -14,6 +14,7 @@ oracle/_ref/.
 """
 from libc.stdlib cimport malloc, calloc, free
 from libc.string cimport memcpy
+from cpython.exc cimport PyErr_Clear
 
 cimport fastafile
 cimport variant
@@ -25,6 +26,11 @@ from variant cimport Variant
 from chaplotype cimport Haplotype
 from cgenotype cimport DiploidGenotype
 from htslibWrapper cimport cAlignedRead
+cimport cwindow
+cimport cpopulation
+from cwindow cimport bamReadBuffer
+from cpopulation cimport Population
+from cgenotype cimport generateAllGenotypesFromHaplotypeList
 
 
 cdef class MemFasta(FastaFile):
@@ -53,9 +59,31 @@ cdef class MemFasta(FastaFile):
 
 
 class _Options(object):
-    def __init__(self, flank):
+    """The attributes of the reference's `options` object that Haplotype, bamReadBuffer and Population read
+    (defaults of src/python/runner.py:519-597)."""
+    def __init__(self, flank, hla=0, n_ind=1, max_haps=64, use_em=0):
         self.verbosity = 0
         self.calculateFlankScore = flank
+        self.HLATyping = hla
+        self.nInd = n_ind
+        self.maxHaplotypes = max_haps
+        self.maxGenotypes = max_haps * (max_haps + 1) // 2
+        self.useEMLikelihoods = use_em
+        self.minPosterior = -1            # keep every variant's posterior (the threshold is applied by the caller)
+        self.rlen = 150
+        self.maxReads = 5000000
+        self.minBaseQual = 20
+        self.minFlank = 10
+        self.trimReadFlank = 0
+        self.minMapQual = 20
+        self.minGoodQualBases = 20
+        self.trimOverlapping = 1
+        self.trimAdapter = 1
+        self.trimSoftClipped = 1
+        self.filterDuplicates = 1
+        self.filterReadsWithUnmappedMates = 1
+        self.filterReadsWithDistantMates = 1
+        self.filterReadPairsWithSmallInserts = 1
 
 
 cdef cAlignedRead** _make_reads(list reads, list keep) except NULL:
@@ -142,4 +170,97 @@ def window_likelihoods(bytes genome, int win_start, int win_end, list hap_varian
         _free_reads(g, ng)
         _free_reads(b, nb)
         _free_reads(k, nk)
+    return out
+
+
+def population(bytes genome, int win_start, int win_end, list hap_variants, list per_ind_reads, int max_read_len=150,
+               int hla=0, int flank=0, int use_em=0, int max_iters=100):
+    """One window through the reference's Population class (src/cython/cpopulation.pyx): setup() then
+    call(max_iters, 0).  per_ind_reads: per individual (good, bad, broken) read lists as in
+    window_likelihoods.  Reads go straight into the buffers' arrays (no filtering: the lists ARE the window's
+    reads) and the window pointers span them.
+    Returns dict: hap_seq, hap_start, freq [H], gl [nInd][G] (rescaled), em [nInd][G], gl_log_max [nInd],
+    gof [G][nInd], call [nInd] (genotype index, -1 = no reads), variants [(refPos, removed, added,
+    phred posterior under the flat prior 0.5, Variant.calculatePrior or None, phred posterior under it or
+    None, [haplotype indices holding it])]."""
+    cdef bytes name = b"chr"
+    cdef MemFasta fa = MemFasta(name, genome)
+    cdef int n_ind = len(per_ind_reads)
+    cdef int H = len(hap_variants)
+    opts = _Options(flank, hla, n_ind, max(H, 2), use_em)
+    cdef list keep = [], haps = [], buffers = [], all_arrays = []
+    cdef Haplotype hap
+    cdef bamReadBuffer buf
+    cdef Population pop
+    cdef cAlignedRead** arr
+    cdef Variant v
+    cdef int i, g, h, k, n, G = H * (H + 1) // 2
+    cdef dict uniq = {}
+    out = {"hap_seq": [], "hap_start": None}
+    try:
+        for vs in hap_variants:
+            variants = []
+            for (p, rem, add) in vs:      # one Variant object per distinct variant, shared between haplotypes
+                key = (p, rem, add)
+                if key not in uniq:
+                    uniq[key] = Variant(name, p, rem, add, 1, 1)
+                variants.append(uniq[key])
+            hap = Haplotype(name, win_start, win_end, tuple(variants), fa, max_read_len, opts)
+            haps.append(hap)
+            out["hap_seq"].append(<bytes>hap.cHaplotypeSequence[:hap.hapLen])
+            out["hap_start"] = hap.startPos - hap.endBufferSize
+        for (good, bad, broken) in per_ind_reads:
+            buf = bamReadBuffer(name, win_start, win_end, opts)
+            buf.sample = b"s"
+            for lst, ra in ((good, buf.reads), (bad, buf.badReads), (broken, buf.brokenMates)):
+                n = len(lst)
+                arr = _make_reads(lst, keep)
+                all_arrays.append((<size_t>arr, n))
+                for k in range(n):
+                    (<cwindow.ReadArray>ra).append(arr[k])
+                (<cwindow.ReadArray>ra).windowStart = (<cwindow.ReadArray>ra).array
+                (<cwindow.ReadArray>ra).windowEnd = (<cwindow.ReadArray>ra).array + n
+            buffers.append(buf)
+        genotypes = generateAllGenotypesFromHaplotypeList(haps)
+        pop = Population(opts)
+        pop.setup(list(uniq.values()), haps, genotypes, n_ind, 0, buffers)
+        try:
+            pop.call(max_iters, 0)
+        except Exception:
+            pass
+        # call() ends with computeVariantPosteriors, which asks every variant for its prior; for indels that is
+        # the indel prior model of variant.pyx, which indexes Python-2 strings as char* and fails under Python 3
+        # AFTER the EM and the genotype calls are complete.  The prior model is outside this path (priors enter as
+        # numbers), so a pending error from it is dropped and the posteriors are taken below with explicit priors.
+        PyErr_Clear()
+        out["freq"] = [pop.frequencies[h] for h in range(H)]
+        out["gl"] = [[pop.genotypeLikelihoods[i][g] for g in range(G)] for i in range(n_ind)]
+        out["em"] = [[pop.EMLikelihoods[i][g] for g in range(G)] for i in range(n_ind)]
+        out["gl_log_max"] = [pop.maxLogLikelihoods[i] for i in range(n_ind)]
+        out["gof"] = [[pop.goodnessOfFitValues[g][i] for i in range(n_ind)] for g in range(G)]
+        out["n_reads"] = [pop.nReads[i] for i in range(n_ind)]
+        calls = []
+        for gt in pop.genotypeCalls:
+            calls.append(-1 if gt is None else [x is gt for x in genotypes].index(True))
+        out["call"] = calls
+        vars_out = []
+        for key, v in uniq.items():
+            # calculatePosterior with the flat prior 0.5 for every variant and, for substitutions, with the
+            # reference's own prior (Variant.calculatePrior; the indel prior model of variant.pyx is prior
+            # modelling outside this path and indexes Python-2 strings as char*, so it is not exercised)
+            post_flat = pop.calculatePosterior(v, 1)
+            prior = None
+            post = None
+            if len(key[1]) == len(key[2]):
+                prior = v.calculatePrior(fa)
+                post = pop.calculatePosterior(v, 0)
+            holders = [h for h in range(H) if v in (<Haplotype>haps[h]).variants]
+            vars_out.append((key[0], key[1], key[2], post_flat, prior, post, holders))
+        out["variants"] = vars_out
+    finally:
+        pop = None
+        buffers = []
+        haps = []
+        for (a, n) in all_arrays:
+            _free_reads(<cAlignedRead**><size_t>a, n)
     return out

@@ -12,13 +12,13 @@
  *   L2  plo_map_and_align(_ex)                                vs src/cython/calign.pyx
  *                                                             (oracle/_ref/calign_ref_wrap*.so)
  *   L3  per-read log-likelihoods (Haplotype.alignReads, default / HLA / flank mode), genotype
- *       log-likelihoods, GOF and hapLike (DiploidGenotype.calculateDataLikelihood)
- *                                                             vs src/cython/chaplotype.pyx, cgenotype.pyx
- *                                                             (oracle/_ref/l3_ref_wrap*.so)
+ *       log-likelihoods, GOF and hapLike (DiploidGenotype.calculateDataLikelihood), and the window model
+ *       (Population.setup + call: max-rescale, EM frequencies and posteriors, genotype calls,
+ *       calculatePosterior)                                   vs src/cython/chaplotype.pyx, cgenotype.pyx,
+ *                                                             cpopulation.pyx (oracle/_ref/l3_ref_wrap*.so)
  * and the resulting inputs/outputs are committed as tests/golden/ *.npz.
- * Still restated without a reference run ("parity unpinned"): the max-rescale, EM, genotype calls and
- * variant posteriors of cpopulation.pyx and the per-site calls of vcfutils.pyx (those modules import the
- * reference's whole Python-2 I/O stack and could not be built here).
+ * Still restated without a reference run ("parity unpinned"): the per-site calls of vcfutils.pyx (row N4;
+ * that module imports the reference's Python-2 VCF and BAM I/O stack and could not be built here).
  */
 #ifndef PLATYPUS_ORACLE_H
 #define PLATYPUS_ORACLE_H

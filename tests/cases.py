@@ -248,7 +248,10 @@ def hla_fixture_batch(golden_dir):
     return WindowBatch.from_windows(windows, 1), g
 
 
-def l3_window_case(seed):
+L3_MODES = [(0, 0), (1, 0), (0, 1), (1, 1)]   # (use_mapq_cap, calc_flank_score)
+
+
+def l3_window_case(seed, n_ind=1):
     """One window for the reference's Haplotype / DiploidGenotype classes (oracle/l3_ref_wrap.pyx): a random
     genome, a 40-60 bp window, 2-5 haplotypes made of SNP / insertion / deletion variants (as
     (refPos, removed, added) tuples, sorted, non-overlapping) and good / bad / broken-mate reads drawn from the
@@ -317,20 +320,51 @@ def l3_window_case(seed):
             flag = 512 if rng.random() < 0.06 else 0
             out.append((seq, qual, pos, pos + L, rng.choice([60, 60, 60, 40, 23, 5, 0]), flag))
         return out
-    return dict(genome=genome, win_start=ws, win_end=we, hap_variants=hap_variants, good=reads(rng.randint(4, 14)),
-                bad=reads(rng.randint(0, 4)), broken=reads(rng.randint(0, 3)), max_read_len=max_read_len)
+    first = (reads(rng.randint(4, 14)), reads(rng.randint(0, 4)), reads(rng.randint(0, 3)))
+    per_ind = [first]
+    for i in range(1, n_ind):   # further individuals (drawn after the first one: the n_ind = 1 stream is unchanged)
+        if i % 4 == 2:
+            per_ind.append(([], reads(rng.randint(0, 2)), []))          # no good reads: "no data" for the model
+        else:
+            per_ind.append((reads(rng.randint(1, 10)), reads(rng.randint(0, 2)), reads(rng.randint(0, 1))))
+    return dict(genome=genome, win_start=ws, win_end=we, hap_variants=hap_variants, good=first[0], bad=first[1],
+                broken=first[2], per_ind=per_ind, max_read_len=max_read_len)
 
 
-def l3_case_batch(case, hap_seqs, hap_start):
-    """WindowBatch of an l3_window_case, haplotype sequences as the reference built them."""
+def l3_case_batch(case, hap_seqs, hap_start, masks=None, priors=None):
+    """WindowBatch of an l3_window_case (all its individuals), haplotype sequences as the reference built them."""
     def mk(t):
         return Read(t[0], t[1], t[2], t[3], t[4], bool(t[5] & 512))
+    per = case["per_ind"]
     w = Window(case["win_start"], case["win_end"], hap_start, list(hap_seqs),
-               [([mk(t) for t in case["good"]], [mk(t) for t in case["bad"]], [mk(t) for t in case["broken"]])])
-    return WindowBatch.from_windows([w], 1)
+               [([mk(t) for t in g], [mk(t) for t in b], [mk(t) for t in k]) for (g, b, k) in per],
+               hap_var_mask=masks, var_prior=priors)
+    return WindowBatch.from_windows([w], len(per))
 
 
-L3_MODES = [(0, 0), (1, 0), (0, 1), (1, 1)]   # (use_mapq_cap, calc_flank_score)
+def l3_population_setup(seed):
+    """(case, n_ind, (hla, flank), use_em, flat_prior) of the population fixtures."""
+    rng = random.Random(seed * 7919 + 13)
+    n_ind = rng.choice([1, 2, 3, 5, 8])
+    return l3_window_case(seed, n_ind), n_ind, L3_MODES[seed % 4], seed % 2, seed % 3 == 0
+
+
+def l3_population_batch(case, ref_out, flat_prior):
+    """Batch + expected phred posteriors from an oracle/l3_ref_wrap.population() result (or its golden copy):
+    variant v of the window = entry v of ref_out["variants"]."""
+    H = len(ref_out["hap_seq"])
+    masks = [0] * H
+    priors, phred = [], []
+    for vi, v in enumerate(ref_out["variants"]):
+        for h in v[6]:
+            masks[h] |= 1 << vi
+        use_flat = flat_prior or v[4] is None
+        priors.append(0.5 if use_flat else v[4])
+        phred.append(v[3] if use_flat else v[5])
+    return l3_case_batch(case, ref_out["hap_seq"], ref_out["hap_start"], masks, priors), phred
+
+
+
 
 
 def l3_golden_cases(golden_dir):
@@ -363,3 +397,36 @@ def check_l3(ll, pop, want_ll, want_geno, rtol=1e-9):
             np.testing.assert_allclose(pop["hap_like"][0, 0, i], want_geno[g, 2], rtol=1e-12, atol=0)
             np.testing.assert_allclose(pop["hap_like"][0, 0, j], want_geno[g, 3], rtol=1e-12, atol=0)
             g += 1
+
+
+def l3_pop_golden_cases(golden_dir):
+    """Yields (batch, expected dict, use_em, (hla, flank)) for the windows of tests/golden/l3_pop_ref.npz (outputs of
+    the reference's own Population class)."""
+    import os
+    import pickle
+    import numpy as np
+    g = np.load(os.path.join(golden_dir, "l3_pop_ref.npz"))
+    for seed in range(int(g["n_cases"])):
+        c, n_ind, mode, use_em, flat = l3_population_setup(seed)
+        key = "p%d_" % seed
+        off, hs = g[key + "hap_off"], g[key + "hap"]
+        ref = {"hap_seq": [hs[off[k]:off[k + 1]].tobytes() for k in range(len(off) - 1)],
+               "hap_start": int(g[key + "hap_start"]), "variants": pickle.loads(g[key + "variants"].tobytes())}
+        b, phred = l3_population_batch(c, ref, flat)
+        want = {k: g[key + k] for k in ("freq", "gl", "em", "gl_log_max", "gof", "call")}
+        want["var_phred"] = phred
+        yield b, want, use_em, mode
+
+
+def check_l3_pop(got, want, rtol=1e-12):
+    import numpy as np
+    nI, G = want["gl"].shape
+    H = len(want["freq"])
+    np.testing.assert_allclose(got["gl"][0, :, :G], want["gl"], rtol=rtol, atol=0, err_msg="gl")
+    np.testing.assert_allclose(got["gof"][0, :G, :], want["gof"], rtol=rtol, atol=0, err_msg="gof")
+    np.testing.assert_allclose(got["freq"][0, :H], want["freq"], rtol=1e-9, atol=0, err_msg="freq")
+    np.testing.assert_allclose(got["em_post"][0, :, :G], want["em"], rtol=1e-9, atol=1e-300, err_msg="em")
+    has = want["call"] >= 0
+    np.testing.assert_allclose(got["gl_log_max"][0][has], want["gl_log_max"][has], rtol=rtol, atol=0, err_msg="gl_log_max")
+    assert list(got["call"][0]) == list(want["call"])
+    assert list(got["var_phred"][0, :len(want["var_phred"])]) == list(want["var_phred"])

@@ -16,6 +16,9 @@ Generates the golden fixtures in this directory.  Run in the BUILD container, wh
                   (DiploidGenotype.calculateDataLikelihood) from the reference's own chaplotype.pyx / cgenotype.pyx
                   (oracle/_ref/l3_ref_wrap*.so) for the windows of tests/cases.l3_window_case, in default, HLA and
                   flank mode; haplotype sequences as the reference's Haplotype constructor built them
+  l3_pop_ref.npz  the reference's own Population class (cpopulation.pyx setup() + call()): rescaled genotype
+                  likelihoods, maxLogLikelihoods, GOF, EM haplotype frequencies, EM genotype posteriors, genotype
+                  calls and calculatePosterior values for multi-individual windows (tests/cases.l3_population_setup)
   window_modes_restated.npz  the edge batch under --calculateFlankScore=1 / --HLATyping=1 from the
                   oracle (restated above the integer score)
   window_restated.npz  a small multi-individual batch with per-read LL, GL, EM frequencies and
@@ -187,6 +190,27 @@ def make_l3(n=60):
     print("l3_ref.npz:", n, "windows x", len(modes), "modes,", n_ll, "log-likelihoods")
 
 
+def make_l3_pop(n=48):
+    import pickle
+    W = O.ref_l3()
+    assert W is not None
+    out = {}
+    for seed in range(n):
+        c, n_ind, (hla, flank), use_em, flat = cases.l3_population_setup(seed)
+        r = W.population(c["genome"], c["win_start"], c["win_end"], c["hap_variants"], c["per_ind"], c["max_read_len"], hla,
+                         flank, use_em)
+        key = "p%d_" % seed
+        ho, hs = pack(r["hap_seq"])
+        out[key + "hap_off"], out[key + "hap"], out[key + "hap_start"] = ho, hs, np.int32(r["hap_start"])
+        for k in ("freq", "gl", "em", "gl_log_max", "gof"):
+            out[key + k] = np.array(r[k], np.float64)
+        out[key + "call"] = np.array(r["call"], np.int32)
+        # variants: (refPos, removed, added, phred under the flat prior, prior or None, phred under it or None, holders)
+        out[key + "variants"] = np.frombuffer(pickle.dumps(r["variants"], protocol=2), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "l3_pop_ref.npz"), n_cases=np.int32(n), **out)
+    print("l3_pop_ref.npz:", n, "windows")
+
+
 def make_window():
     batch = cases.edge_batch(seed=5)
     arrs, ll, sc, st = O.population_run(batch)
@@ -201,5 +225,6 @@ if __name__ == "__main__":
     make_align_tb()
     make_calign_modes()
     make_l3()
+    make_l3_pop()
     make_window()
     make_window_modes()

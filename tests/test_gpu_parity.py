@@ -473,3 +473,15 @@ def test_l3_golden_ref(engine, golden_dir):
             cases.check_l3(got["ll"], got, w_ll, w_geno)
             n += w_ll.size
     assert n > 9000
+
+
+def test_l3_population_golden_ref(engine, golden_dir):
+    """GPU window model (rescale, EM, genotype calls, variant posteriors) against outputs of the reference's own
+    Population class (tests/golden/l3_pop_ref.npz): 1-8 individuals, all mode combinations, both call rules."""
+    n = 0
+    for b, want, use_em, (hla, flank) in cases.l3_pop_golden_cases(golden_dir):
+        opt = _abi.PlbOptions.default(use_mapq_cap=hla, calc_flank_score=flank, use_em_likelihoods=use_em)
+        got = engine.population_run(b, opt=opt)
+        cases.check_l3_pop(got, want, rtol=RTOL_TIGHT)
+        n += 1
+    assert n >= 40

@@ -416,3 +416,35 @@ def test_vs_ref_l3_fuzz(oracle):
         b = cases.l3_case_batch(c, r["hap_seq"], r["hap_start"])
         arrs, ll, sc, _ = oracle.population_run(b, _abi.PlbOptions.default(use_mapq_cap=hla, calc_flank_score=flank))
         cases.check_l3(ll, arrs, np.array(r["ll"]), np.array([g[2:] for g in r["genotypes"]]))
+
+
+def test_golden_l3_population_ref(oracle, golden_dir):
+    """Rescaled genotype likelihoods, EM frequencies, EM genotype posteriors, genotype calls and variant posteriors
+    against outputs of the reference's own Population class (cpopulation.pyx setup() + call())."""
+    from platypus_b200 import _abi
+    n = 0
+    for b, want, use_em, (hla, flank) in cases.l3_pop_golden_cases(golden_dir):
+        opt = _abi.PlbOptions.default(use_mapq_cap=hla, calc_flank_score=flank, use_em_likelihoods=use_em)
+        arrs, _, _, _ = oracle.population_run(b, opt)
+        cases.check_l3_pop(arrs, want)
+        n += 1
+    assert n >= 40
+
+
+@pytest.mark.filterwarnings("ignore::pytest.PytestUnraisableExceptionWarning")   # the reference's indel PRIOR model
+def test_vs_ref_population_fuzz(oracle):                                          # (outside the path) fails under Python 3
+    W = oracle.ref_l3()
+    if W is None:
+        pytest.skip("oracle/_ref/l3_ref_wrap not built (no reference checkout)")
+    from platypus_b200 import _abi
+    for seed in range(2000, 2060):
+        c, n_ind, (hla, flank), use_em, flat = cases.l3_population_setup(seed)
+        r = W.population(c["genome"], c["win_start"], c["win_end"], c["hap_variants"], c["per_ind"], c["max_read_len"], hla,
+                         flank, use_em)
+        b, phred = cases.l3_population_batch(c, r, flat)
+        want = {k: np.array(r[k], np.float64) for k in ("freq", "gl", "em", "gl_log_max", "gof")}
+        want["call"] = np.array(r["call"], np.int32)
+        want["var_phred"] = phred
+        opt = _abi.PlbOptions.default(use_mapq_cap=hla, calc_flank_score=flank, use_em_likelihoods=use_em)
+        arrs, _, _, _ = oracle.population_run(b, opt)
+        cases.check_l3_pop(arrs, want)
