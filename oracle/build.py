@@ -128,7 +128,61 @@ def build_calign_ref(force=False):
 
 
 L3_MODULES = ["htslibWrapper", "fastafile", "cerrormodel", "variant", "chaplotype", "cgenotype", "vcfutils", "cwindow",
-              "cpopulation", "l3_ref_wrap"]
+              "cpopulation", "l3_ref_wrap", "n4_ref"]
+
+# N4: computeGenotypeCallAndLikelihoods (src/cython/vcfutils.pyx:163-334) cannot be reached through its module
+# (vcfutils.pyx imports the Python-2 VCF and BAM I/O stack), so the function's own source lines are excerpted at
+# build time into a scratch module between this header and this footer (nothing of it is stored in the repo).
+N4_HEADER = """# cython: language_level=2
+# scratch module: header (declarations) + the reference's computeGenotypeCallAndLikelihoods, verbatim + a forwarding def
+from libc.stdlib cimport malloc, calloc, free
+import logging
+logger = logging.getLogger("Log")
+from cgenotype cimport DiploidGenotype
+from chaplotype cimport Haplotype
+from variant cimport Variant
+
+"""
+N4_FOOTER = """
+
+def compute_genotype_call_and_likelihoods(int n_variants, int n_haps, freqs, gl_row, gof_col, var_in_hap, hap_is_ref,
+                                          int n_individuals):
+    \"\"\"Forwards to computeGenotypeCallAndLikelihoods for one (site, sample): gl_row[g] / gof_col[g] in genotype order
+    (i, j), i <= j; var_in_hap[h][v]; hap_is_ref[h].\"\"\"
+    cdef int H = n_haps, G = n_haps * (n_haps + 1) // 2, h, g, i, j, v
+    cdef double* f = <double*>calloc(H, sizeof(double))
+    cdef double** gls = <double**>calloc(1, sizeof(double*))
+    cdef double** gofs = <double**>calloc(G, sizeof(double*))
+    cdef int** idx = <int**>calloc(G, sizeof(int*))
+    cdef int** vih = <int**>calloc(H, sizeof(int*))
+    cdef int* isref = <int*>calloc(H, sizeof(int))
+    gls[0] = <double*>calloc(G, sizeof(double))
+    g = 0
+    for i in range(H):
+        for j in range(i, H):
+            idx[g] = <int*>calloc(2, sizeof(int))
+            idx[g][0] = i
+            idx[g][1] = j
+            gofs[g] = <double*>calloc(1, sizeof(double))
+            gofs[g][0] = gof_col[g]
+            gls[0][g] = gl_row[g]
+            g += 1
+    for h in range(H):
+        f[h] = freqs[h]
+        isref[h] = hap_is_ref[h]
+        vih[h] = <int*>calloc(max(1, n_variants), sizeof(int))
+        for v in range(n_variants):
+            vih[h][v] = var_in_hap[h][v]
+    try:
+        return computeGenotypeCallAndLikelihoods(0, [None] * H, [None] * G, 0, f, gls, gofs, idx, vih, [None] * n_variants,
+                                                 isref, n_individuals, b"s")
+    finally:
+        for g in range(G):
+            free(idx[g]); free(gofs[g])
+        for h in range(H):
+            free(vih[h])
+        free(gls[0]); free(gls); free(gofs); free(idx); free(vih); free(isref); free(f)
+"""
 
 
 def l3_ref_paths():
@@ -164,7 +218,7 @@ def build_l3_ref(force=False):
     except ImportError:
         return None
     cy = os.path.join(REF, "src", "cython")
-    srcs = [os.path.join(cy, f) for f in ("chaplotype.pyx", "cgenotype.pyx", "cpopulation.pyx", "cwindow.pyx", "variant.pyx",
+    srcs = [os.path.join(cy, f) for f in ("chaplotype.pyx", "cgenotype.pyx", "cpopulation.pyx", "cwindow.pyx", "variant.pyx", "vcfutils.pyx",
                                            "fastafile.pyx", "cerrormodel.pyx", "calign.pyx")] + [os.path.join(HERE, "l3_ref_wrap.pyx")]
     if not force and all(_newer(o, srcs) for o in outs):
         return outs
@@ -233,7 +287,14 @@ def build_l3_ref(force=False):
                  cwd=tmp)
         _run([sys.executable, "-m", "cython", "-3", "-I", tmp, "l3_ref_wrap.pyx", "-o", "l3_ref_wrap.c"], cwd=tmp)
         extra = {"cerrormodel": ["tandem.c"], "chaplotype": ["align.c"], "calign": ["align.c"]}
-        for m in ref_mods + ("l3_ref_wrap",):
+        # N4 excerpt: the function starts at its `cdef tuple` line and ends before the next rule of #'s
+        vlines = open(os.path.join(cy, "vcfutils.pyx")).read().split("\n")
+        a = [i for i, l in enumerate(vlines) if l.startswith("cdef tuple computeGenotypeCallAndLikelihoods(")][0]
+        b = [i for i in range(a, len(vlines)) if vlines[i].startswith("####")][0]
+        open(os.path.join(tmp, "n4_ref.pyx"), "w").write(N4_HEADER + "\n".join(vlines[a:b]) + N4_FOOTER)
+        _run([sys.executable, "-m", "cython", "-2", "-X", "legacy_implicit_noexcept=True", "-I", tmp, "n4_ref.pyx", "-o", "n4_ref.c"],
+             cwd=tmp)
+        for m in ref_mods + ("l3_ref_wrap", "n4_ref"):
             _run(["gcc"] + cflags + [m + ".c"] + extra.get(m, []) + ["-o", os.path.join(REF_OUT, m + _ext_suffix())], cwd=tmp)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

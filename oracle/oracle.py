@@ -205,6 +205,40 @@ def ref_l3():
         return None
 
 
+def ref_n4():
+    """computeGenotypeCallAndLikelihoods of the reference (vcfutils.pyx:163-334), excerpted at build time, or None."""
+    if ref_l3() is None:
+        return None
+    try:
+        return importlib.import_module("n4_ref")
+    except ImportError:
+        return None
+
+
+def ref_site_genotypes(batch, pop_arrs, sites):
+    """The reference's computeGenotypeCallAndLikelihoods for every (site, individual with reads) of a site batch:
+    dict (site, individual) -> (phasedIndex1, phasedIndex2, likelihoods, genotype / non-ref / ref posterior, GOF)."""
+    N = ref_n4()
+    nI = batch.n_individuals
+    Hm = pop_arrs["max_haps"]
+    out = {}
+    for s in range(sites.n_sites):
+        w = int(sites.site_win[s])
+        h0, h1 = int(batch.win_hap_off[w]), int(batch.win_hap_off[w + 1])
+        H = h1 - h0
+        G = H * (H + 1) // 2
+        vs = [int(v) for v in sites.site_var[sites.site_var_off[s]:sites.site_var_off[s + 1]]]
+        isref = [int(x) for x in sites.hap_is_ref[sites.site_hap_off[s]:sites.site_hap_off[s + 1]]]
+        vih = [[int((int(batch.hap_var_mask[h0 + h]) >> v) & 1) for v in vs] for h in range(H)]
+        for i in range(nI):
+            if batch.wi_n_good[w * nI + i] == 0:
+                continue
+            out[(s, i)] = N.compute_genotype_call_and_likelihoods(
+                len(vs), H, [float(x) for x in pop_arrs["freq"][w, :H]], [float(x) for x in pop_arrs["gl"][w, i, :G]],
+                [float(x) for x in pop_arrs["gof"][w, :G, i]], vih, isref, nI)
+    return out
+
+
 # ---- restatement entry points -----------------------------------------------------------------
 def band_align(hap_seg: bytes, read: bytes, qual: bytes, gap_open: bytes, ext=3, nuc=2):
     assert len(hap_seg) >= len(read) + 15 and len(gap_open) >= len(read) + 15

@@ -17,8 +17,13 @@
  *       calculatePosterior)                                   vs src/cython/chaplotype.pyx, cgenotype.pyx,
  *                                                             cpopulation.pyx (oracle/_ref/l3_ref_wrap*.so)
  * and the resulting inputs/outputs are committed as tests/golden/ *.npz.
- * Still restated without a reference run ("parity unpinned"): the per-site calls of vcfutils.pyx (row N4;
- * that module imports the reference's Python-2 VCF and BAM I/O stack and could not be built here).
+ *   N4  plo_site_genotypes: phased indices, marginal likelihoods, posteriors, best GOF
+ *                                                             vs computeGenotypeCallAndLikelihoods, the function's
+ *                                                             own lines of src/cython/vcfutils.pyx:163-334 excerpted
+ *                                                             at build time (oracle/_ref/n4_ref*.so)
+ * Still restated without a reference run ("parity unpinned"): only the few lines of outputCallToVCF that turn
+ * those posteriors into phred values, the GT fallback rules and log10 GLs (vcfutils.pyx:504-548; inline in a
+ * function that writes VCF through the reference's Python-2 I/O stack).
  */
 #ifndef PLATYPUS_ORACLE_H
 #define PLATYPUS_ORACLE_H

@@ -430,3 +430,23 @@ def check_l3_pop(got, want, rtol=1e-12):
     np.testing.assert_allclose(got["gl_log_max"][0][has], want["gl_log_max"][has], rtol=rtol, atol=0, err_msg="gl_log_max")
     assert list(got["call"][0]) == list(want["call"])
     assert list(got["var_phred"][0, :len(want["var_phred"])]) == list(want["var_phred"])
+
+
+def n4_cases():
+    """(batch, sites) pairs of the per-site genotype fixtures: 1, 3, 4 and 30 individuals (30 switches on the
+    EM-frequency weighting, vcfutils.pyx:264-267), bi- and multi-allelic sites."""
+    for n_ind, seed in ((1, 11), (3, 12), (30, 13), (4, 5)):
+        b = edge_batch(seed=seed, n_windows=16, n_individuals=n_ind)
+        yield b, sites_for_batch(b, seed=seed)
+
+
+def check_n4(got, g, k, rtol=1e-12):
+    """Site outputs against case k of tests/golden/n4_ref.npz (the reference's own function)."""
+    import numpy as np
+    have = g["n%d_have" % k].astype(bool)
+    assert have.sum() > 20
+    assert np.array_equal(got["phased"][have], g["n%d_phased" % k][have])
+    P = g["n%d_lik" % k].shape[2]
+    np.testing.assert_allclose(got["lik"][:, :, :P][have], g["n%d_lik" % k][have], rtol=rtol, atol=0)
+    np.testing.assert_allclose(got["post"][have], g["n%d_post" % k][have], rtol=rtol, atol=0, equal_nan=True)
+    np.testing.assert_allclose(got["gof"][have], g["n%d_gof" % k][have], rtol=rtol, atol=0)

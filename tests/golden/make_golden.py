@@ -19,6 +19,9 @@ Generates the golden fixtures in this directory.  Run in the BUILD container, wh
   l3_pop_ref.npz  the reference's own Population class (cpopulation.pyx setup() + call()): rescaled genotype
                   likelihoods, maxLogLikelihoods, GOF, EM haplotype frequencies, EM genotype posteriors, genotype
                   calls and calculatePosterior values for multi-individual windows (tests/cases.l3_population_setup)
+  n4_ref.npz      computeGenotypeCallAndLikelihoods of the reference (vcfutils.pyx:163-334, excerpted at build time into
+                  oracle/_ref/n4_ref*.so) for every (site, individual) of tests/cases.n4_cases: phased indices, marginal
+                  likelihoods, genotype / non-ref / ref posteriors, best GOF
   window_modes_restated.npz  the edge batch under --calculateFlankScore=1 / --HLATyping=1 from the
                   oracle (restated above the integer score)
   window_restated.npz  a small multi-individual batch with per-read LL, GL, EM frequencies and
@@ -211,6 +214,31 @@ def make_l3_pop(n=48):
     print("l3_pop_ref.npz:", n, "windows")
 
 
+def make_n4():
+    assert O.ref_n4() is not None
+    out = {}
+    tot = 0
+    for k, (b, sites) in enumerate(cases.n4_cases()):
+        pop, _, _, _ = O.population_run(b)
+        ref = O.ref_site_genotypes(b, pop, sites)
+        S, nI, P = sites.n_sites, b.n_individuals, sites.max_pairs()
+        phased = np.full((S, nI, 2), -1, np.int32)
+        lik = np.zeros((S, nI, P))
+        post = np.zeros((S, nI, 3))
+        gof = np.zeros((S, nI))
+        have = np.zeros((S, nI), np.uint8)
+        for (s_, i), (p1, p2, liks, gp, npo, rp, gf) in ref.items():
+            phased[s_, i] = (p1, p2)
+            lik[s_, i, :len(liks)] = liks
+            post[s_, i] = (gp, npo, rp)
+            gof[s_, i] = gf
+            have[s_, i] = 1
+        tot += int(have.sum())
+        out.update({"n%d_phased" % k: phased, "n%d_lik" % k: lik, "n%d_post" % k: post, "n%d_gof" % k: gof, "n%d_have" % k: have})
+    np.savez_compressed(os.path.join(HERE, "n4_ref.npz"), **out)
+    print("n4_ref.npz:", tot, "(site, individual) cases")
+
+
 def make_window():
     batch = cases.edge_batch(seed=5)
     arrs, ll, sc, st = O.population_run(batch)
@@ -226,5 +254,6 @@ if __name__ == "__main__":
     make_calign_modes()
     make_l3()
     make_l3_pop()
+    make_n4()
     make_window()
     make_window_modes()

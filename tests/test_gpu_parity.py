@@ -485,3 +485,11 @@ def test_l3_population_golden_ref(engine, golden_dir):
         cases.check_l3_pop(got, want, rtol=RTOL_TIGHT)
         n += 1
     assert n >= 40
+
+
+def test_n4_golden_ref(engine, golden_dir):
+    """k_site_genotypes against outputs of the reference's own computeGenotypeCallAndLikelihoods (n4_ref.npz)."""
+    g = np.load(os.path.join(golden_dir, "n4_ref.npz"))
+    for k, (b, sites) in enumerate(cases.n4_cases()):
+        pop = engine.population_run(b)
+        cases.check_n4(engine.site_genotypes(b, pop, sites), g, k, rtol=RTOL_TIGHT)

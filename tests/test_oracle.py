@@ -448,3 +448,25 @@ def test_vs_ref_population_fuzz(oracle):                                        
         opt = _abi.PlbOptions.default(use_mapq_cap=hla, calc_flank_score=flank, use_em_likelihoods=use_em)
         arrs, _, _, _ = oracle.population_run(b, opt)
         cases.check_l3_pop(arrs, want)
+
+
+def test_golden_n4_ref(oracle, golden_dir):
+    """Per-site genotype calls against outputs of the reference's own computeGenotypeCallAndLikelihoods."""
+    g = np.load(os.path.join(golden_dir, "n4_ref.npz"))
+    for k, (b, sites) in enumerate(cases.n4_cases()):
+        pop, _, _, _ = oracle.population_run(b)
+        cases.check_n4(oracle.site_genotypes(b, pop, sites), g, k)
+
+
+def test_vs_ref_n4_fuzz(oracle):
+    if oracle.ref_n4() is None:
+        pytest.skip("oracle/_ref/n4_ref not built (no reference checkout)")
+    for n_ind, seed in ((2, 21), (26, 22)):
+        b = cases.edge_batch(seed=seed, n_windows=10, n_individuals=n_ind)
+        pop, _, _, _ = oracle.population_run(b)
+        sites = cases.sites_for_batch(b, seed=seed)
+        ours = oracle.site_genotypes(b, pop, sites)
+        for (s, i), (p1, p2, liks, gp, npo, rp, gf) in oracle.ref_site_genotypes(b, pop, sites).items():
+            assert ours["phased"][s, i].tolist() == [p1, p2]
+            assert np.array_equal(ours["lik"][s, i, :len(liks)], np.array(liks))
+            assert np.array_equal(ours["post"][s, i], np.array([gp, npo, rp]), equal_nan=True) and ours["gof"][s, i] == gf
