@@ -360,14 +360,6 @@ int prof_row_words(int L) {
     return n;
 }
 
-int tab_bits(int len) {
-    int nk = len - kKmer;
-    if (nk < 1) nk = 1;
-    int bits = 6;
-    while ((1 << bits) < 2 * nk && bits < 14) ++bits;
-    return bits;
-}
-
 }  // namespace
 
 static int plan_tiles(const PlbWindowBatch* hb, int w_begin, int w_end, TileLists& tl, AnchorPlan& ap, DpPlan& dp,
@@ -417,9 +409,6 @@ static int plan_tiles(const PlbWindowBatch* hb, int w_begin, int w_end, TileList
                     hpk += ((len + 15) >> 4) + 2 * kPackPadWords;
                 }
                 ap.hpk_words = std::max(ap.hpk_words, hpk);
-                int bits = 6;
-                while ((1 << bits) < 2 * sum_nk && bits < 14) ++bits;
-                ap.tab_bits = std::max(ap.tab_bits, bits);
                 ap.next_halfs = std::max(ap.next_halfs, nh_);
                 ap.max_group = std::max(ap.max_group, g.second - g.first);
                 ap.heads_halfs = std::max(ap.heads_halfs, std::min(kHashSize, sum_nk) + 1);
@@ -716,7 +705,6 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
             A.max_slots = std::max(A.max_slots, q.max_slots);
             A.max_group = std::max(A.max_group, q.max_group);
             A.max_pairs = std::max(A.max_pairs, q.max_pairs);
-            A.tab_bits = std::max(A.tab_bits, q.tab_bits);
             A.next_halfs = std::max(A.next_halfs, q.next_halfs);
             A.heads_halfs = std::max(A.heads_halfs, q.heads_halfs);
             A.rpk_words = std::max(A.rpk_words, q.rpk_words);
@@ -744,7 +732,6 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
         ap.mult_halfs = (ap.heads_halfs + 7) & ~7;
         ap.heads_halfs = std::max(ap.heads_halfs, 4096);
         ap.heads_halfs = (ap.heads_halfs + 7) & ~7;
-        ap.tab_bits = std::max(ap.tab_bits, 6);
         ap.cnt_words = (((max_hap + max_read + 2) >> 1) + 3) & ~3;
         const int nwarps = kAnchorThreads / 32;
         ap.n_cnt = (int)std::max<size_t>(1, std::min<size_t>(nwarps, kAnchorCntBudget / ((size_t)ap.cnt_words * 4)));

@@ -286,19 +286,6 @@ PLB_HD u32 vmax2(u32 a, u32 b) {
 }
 #endif
 
-// Profile word straight from the read byte (no intermediate code, no branches): exact A/C/G/T bytes
-// get the match value in their own byte, every other byte mismatches all four haplotype bases.
-// Equals make_profile6(fast_code(ch), qual, K) for six = true and make_profile(fast_code(ch), qual)
-// for six = false.
-PLB_HD u32 profile_from_byte(u32 ch, u32 qual, int K, bool six) {
-    const u32 idx = (ch >> 1) & 3u;                        // A, C, T, G -> 0, 1, 2, 3
-    const u32 e = (0x47544341u >> (8 * idx)) & 0xFFu;      // the letter that index stands for
-    const u32 sh = (0x10180800u >> (8 * idx)) & 0xFFu;     // 8 * code: A 0, C 8, T 24, G 16
-    const u32 mis = six ? ((qual - (u32)K) & 0xFFu) : qual;
-    const u32 flip = six ? (mis ^ ((u32)(-K) & 0xFFu)) : qual;   // mis ^ match value
-    return (mis * 0x01010101u) ^ (e == ch ? flip << sh : 0u);
-}
-
 constexpr int kMaxFastLen = 2000;  // relative values reach -(2*ext+nuc)*L: stay far inside int16
 
 PLB_HD u32 make_sel6(int code_lo, int code_hi) {  // codes 0..3 only

@@ -28,7 +28,6 @@ constexpr int kScoreNone = 1000000;
 constexpr double kMLTOT = -0.23025850929940459;
 constexpr double kLog10E = 0.43429448190325182;
 constexpr double kLogHalf = -0.69314718055994529;
-constexpr u32 kTabEmpty = 0xFFFFFFFFu;
 constexpr int kRankWords = kHashSize / 32;            // one presence bit per possible 7-mer key
 constexpr size_t kRankTabBytes = kRankWords * 8;      // uint2 {bits, number of set bits in earlier words}
 
@@ -122,19 +121,6 @@ __device__ __forceinline__ PairClip pair_clip(const ScoreParams& sp, int read_po
     return c;
 }
 
-__device__ __forceinline__ u32 base_code(uint8_t ch) {  // calign.pyx:61-90
-    u32 c = ch & 7u;
-    if (c == 7u) c = 2u;
-    return c & 3u;
-}
-
-__device__ __forceinline__ u32 kmer_hash(const uint8_t* p) {
-    u32 h = 0;
-#pragma unroll
-    for (int i = 0; i < kKmer; ++i) h = (h << 2) + base_code(p[i]);
-    return h;
-}
-
 // homopolymer gap-open table evaluated from chaplotype.pyx:64-67 (see oracle for the formula)
 __constant__ uint8_t c_homopol_q[49] = {45, 42, 41, 39, 37, 32, 28, 23, 20, 19, 17, 16, 15, 14, 13, 12, 11,
                                         11, 10, 9,  9,  8,  8,  7,  7,  7,  6,  6,  6,  5,  5,  5,  4,  4,
@@ -167,10 +153,6 @@ __device__ __forceinline__ unsigned short cas_u16(uint16_t* arr, int idx, unsign
         if (old == cur) return expect;
         cur = old;
     }
-}
-
-__device__ __forceinline__ u32 tab_slot0(u32 key, int bits) {
-    return bits >= 14 ? key : ((key * 0x9E3779B1u) >> (32 - bits));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -227,7 +209,6 @@ struct AnchorPlan {
     int32_t max_slots;      // slots per tile upper bound
     int32_t max_group;      // haplotypes per tile upper bound
     int32_t max_pairs;      // slots*haplotypes per tile upper bound
-    int32_t tab_bits;       // log2(slots) of the union 7-mer table
     int32_t next_halfs;     // u16 entries for all next arrays of a group
     int32_t heads_halfs;    // u16 entries of the head area (>= largest union size + 1)
     int32_t mult_halfs;     // u16 entries of the per-id multiplicity bounds (>= largest union size + 1)
@@ -367,8 +348,7 @@ __device__ __forceinline__ u32 key_at(const u32* pk, int p) {
 // key -> dense id (1..U) over the union of the group's haplotype 7-mers, 0 when absent.  The table is a
 // 16384-bit presence map with a rank directory: id = (set bits before the key) + 1.  One LDS.64, a
 // popcount and no probing; built with atomicOr + one 512-entry scan (no CAS loops).
-__device__ __forceinline__ u32 tab_lookup(const u32* tab, int bits, u32 key) {
-    (void)bits;
+__device__ __forceinline__ u32 tab_lookup(const u32* tab, u32 key) {
     const uint2 e = ((const uint2*)tab)[key >> 5];
     const u32 bit = key & 31u;
     const u32 below = e.x & ((1u << bit) - 1u);
@@ -388,16 +368,16 @@ constexpr int kPairUndecided = 0x40000002;  // goes to the exact vote array
 
 struct LightArgs {
     u32 head_off, rpk_off, hpk_off, res_off;
-    int nk_read, nk_hap, vub, bits;
+    int nk_read, nk_hap, vub;
     int lp, hh;   // read 7-mers that vote exactly once (light) / possibly several times (heavy)
 };
 
 // offset implied by the first read 7-mer in [i0, i1) (walking by step) that occurs exactly once in
 // the haplotype; read 7-mer -> id through the tile's table (smem offset 0), id -> position through head
-__device__ __forceinline__ int unique_hit_offset(const u32* tab, int bits, const uint16_t* head, const u32* rpk, int i0,
+__device__ __forceinline__ int unique_hit_offset(const u32* tab, const uint16_t* head, const u32* rpk, int i0,
                                                  int i1, int step) {
     for (int i = i0; i != i1; i += step) {
-        const u32 hd = head[tab_lookup(tab, bits, key_at(rpk, i))];
+        const u32 hd = head[tab_lookup(tab, key_at(rpk, i))];
         if (hd && !(hd & 0x8000u)) return (int)hd - 1 - i;
     }
     return kNoCand;
@@ -444,7 +424,7 @@ __device__ __noinline__ int light_decide(LightArgs a) {
         g[j] = kNoCand;
         c[j] = 0;
         if (top > min(R, R2)) continue;        // already decided
-        const int gj = unique_hit_offset(tab, a.bits, head, rpk, i0, i1, step);
+        const int gj = unique_hit_offset(tab, head, rpk, i0, i1, step);
         bool dup = gj == kNoCand;
 #pragma unroll
         for (int k = 0; k < NG; ++k)
@@ -493,7 +473,6 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
     __shared__ int s_nid, s_nfb, s_scan[kAnchorThreads / 32];
 
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-    const int bits = 0;   // (the rank table needs no size parameter)
     unsigned long long st_pairs = 0, st_scored = 0, st_dp = 0, st_cells = 0, t_tile0 = 0;
     int w_prev = 0;
     __shared__ int s_tile;
@@ -642,7 +621,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 uint16_t* nxt = s_next + s_hmeta[3 * g + 1];
                 uint16_t* head = s_heads + (g - g0) * hstride;
                 for (int i = tid; i < len - kKmer; i += nthr) {
-                    const u32 id = tab_lookup(s_tab, bits, key_at(hpk, i));
+                    const u32 id = tab_lookup(s_tab, key_at(hpk, i));
                     unsigned short cur = head[id];
                     while (true) {  // push position i (stored as i+1); order inside a chain is irrelevant.
                         // bit 15 of the head marks chains with more than one element.
@@ -680,7 +659,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 int sum = 0, lh = 0;   // lh: light count | heavy count << 16
                 const u32* rpk = s_rpk + si.poff;   // read 7-mers 0..len-8 (calign.pyx:155-165)
                 for (int i = lane; i < nk; i += 32) {
-                    const int m = s_mult[tab_lookup(s_tab, bits, key_at(rpk, i))];
+                    const int m = s_mult[tab_lookup(s_tab, key_at(rpk, i))];
                     sum += m;
                     lh += (m == 1) + ((m > 1) << 16);
                 }
@@ -735,7 +714,6 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 la.vub = si.vub;
                 la.lp = si.lph & 0xFFFF;
                 la.hh = si.lph >> 16;
-                la.bits = bits;
                 if (!light_decide(la)) {
                     s_vlist[3 * p] = (u32)kPairUndecided;
                     s_fblist[atomicAdd(&s_nfb, 1)] = (u32)p;
@@ -809,7 +787,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 for (int k = lane; k < words; k += 32) cw[k] = 0;
                 __syncwarp();
                 for (int i = lane; i < nk; i += 32) {
-                    const u32 id = tab_lookup(s_tab, bits, key_at(rpk, i));
+                    const u32 id = tab_lookup(s_tab, key_at(rpk, i));
                     if (!id) continue;
                     u32 p1 = head[id] & 0x7FFFu;
                     while (p1) {
