@@ -15,8 +15,11 @@ EM, posteriors) over that batch.
             buffers: H2D of all inputs and D2H of all population outputs inside the timed region
   roofline  k_dp (the dominant kernel): algorithmic bytes per launch / mean launch duration measured
             with CUDA events inside the timed region, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the CPU oracle with the reference's own align.c for the band alignment
-            (oracle/_ref, kind "reference") on all host cores over a bounded sample of the workload
+  cpu_baseline  the REFERENCE'S OWN CODE on the host cores: its Haplotype / DiploidGenotype / Population classes
+            (chaplotype.pyx, cgenotype.pyx, cpopulation.pyx, calign.pyx, align.c with traceback, built for Python 3 into
+            oracle/_ref by oracle/build.py) over the whole workload, one process per core with windows dealt to them
+            the way runner.py:470-485 deals regions to its processes (kind "reference").  If those modules are missing
+            it falls back to the oracle's C restatement with the reference's align.c, then to the pure restatement.
 
 --impl reference times that CPU path alone (the reference has no GPU implementation).
 Nothing here reads /root/reference at run time.
@@ -134,11 +137,91 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_run(batch, n_windows, threads, steps=1, warmup=0):
-    """Times the CPU path (oracle anchoring/LL/GL/EM + reference align.c when oracle/_ref exists)
-    over the first n_windows windows.  Returns (gcups, kind, seconds per step, cells)."""
+_REF_ARGS = None    # per-window argument tuples of l3_ref_wrap.population_seq, inherited by the forked workers
+
+
+def _window_args(batch, n_windows):
+    """Windows of a single-individual batch as the Python objects the reference's classes take."""
+    b = batch
+    out = []
+    for w in range(min(n_windows, b.n_windows)):
+        h0, h1 = int(b.win_hap_off[w]), int(b.win_hap_off[w + 1])
+        haps = [b.hap_seq[b.hap_seq_off[h]:b.hap_seq_off[h + 1]].tobytes() for h in range(h0, h1)]
+        s0, s1 = int(b.wi_slot_off[w]), int(b.wi_slot_off[w + 1])
+        ng, nb = int(b.wi_n_good[w]), int(b.wi_n_bad[w])
+        reads = []
+        for s_ in range(s0, s1):
+            r = int(b.slot_read[s_])
+            o0, o1 = int(b.read_seq_off[r]), int(b.read_seq_off[r + 1])
+            reads.append((b.read_seq[o0:o1].tobytes(), b.read_qual[o0:o1].tobytes(), int(b.read_pos[r]), int(b.read_end[r]),
+                          int(b.read_mapq[r]), 512 if b.read_qcfail[r] else 0))
+        out.append((haps, int(b.win_start[w]), int(b.win_end[w]), int(b.hap_start[w]),
+                    [(reads[:ng], reads[ng:ng + nb], reads[ng + nb:])]))
+    return out
+
+
+def _ref_worker(span):
+    from oracle import oracle as O
+    W = O.ref_l3()
+    acc = 0.0
+    for w in range(span[0], span[1]):
+        acc += W.population_seq(*_REF_ARGS[w])["gl_log_max"][0]
+    return acc
+
+
+def true_reference_run(batch, n_windows, procs, steps=1, warmup=0):
+    """Times the reference's own classes (oracle/_ref/l3_ref_wrap) over the first n_windows windows with `procs`
+    processes.  Returns (gcups, seconds per step, cells, windows) or None when the modules are not there or the
+    workload cannot be expressed (several individuals, flank not of the form min(2*rlen, 500))."""
+    global _REF_ARGS
+    import multiprocessing as mp
     from oracle import oracle as O
     from platypus_b200 import synth
+    if O.ref_l3() is None or batch.n_individuals != 1:
+        return None
+    sub = batch.slice_windows(0, min(n_windows, batch.n_windows))
+    try:
+        _REF_ARGS = _window_args(sub, sub.n_windows)
+        O.ref_l3().population_seq(*_REF_ARGS[0])
+    except Exception:
+        return None
+    nw = len(_REF_ARGS)
+    cells = synth.algorithmic_cells(sub)
+    procs = max(1, min(procs, nw))
+    n_chunks = procs * 8     # round-robin-sized pieces: the pool balances them
+    spans = [(nw * i // n_chunks, nw * (i + 1) // n_chunks) for i in range(n_chunks)]
+    spans = [sp for sp in spans if sp[1] > sp[0]]
+    if procs == 1:
+        for _ in range(warmup):
+            _ref_worker((0, min(nw, 16)))
+        t0 = time.perf_counter()
+        for _ in range(max(1, steps)):
+            _ref_worker((0, nw))
+        dt = (time.perf_counter() - t0) / max(1, steps)
+        return cells / dt / 1e9, dt, cells, nw
+    with mp.get_context("fork").Pool(procs) as pool:
+        pool.map(_ref_worker, [(i, i + 1) for i in range(min(nw, procs))])     # workers up, modules imported
+        for _ in range(warmup):
+            pool.map(_ref_worker, spans)
+        t0 = time.perf_counter()
+        for _ in range(max(1, steps)):
+            pool.map(_ref_worker, spans)
+        dt = (time.perf_counter() - t0) / max(1, steps)
+    return cells / dt / 1e9, dt, cells, nw
+
+
+def cpu_reference_run(batch, n_windows, threads, steps=1, warmup=0):
+    """CPU path over the first n_windows windows.  Preferred: the reference's own classes (true_reference_run);
+    otherwise the oracle (anchoring/LL/GL/EM restated in C) with the reference's align.c when oracle/_ref has it.
+    Returns (gcups, kind, seconds per step, cells, windows, description)."""
+    from oracle import oracle as O
+    from platypus_b200 import synth
+    if not RAGGED:
+        r = true_reference_run(batch, n_windows, threads, steps, warmup)
+        if r is not None:
+            return r[0], "reference", r[1], r[2], r[3], ("the reference's own Haplotype / DiploidGenotype / Population classes "
+                                                        "(chaplotype.pyx, cgenotype.pyx, cpopulation.pyx, calign.pyx, align.c with "
+                                                        "traceback; oracle/_ref), %d process%s" % (threads, "" if threads == 1 else "es"))
     sub = batch.slice_windows(0, min(n_windows, batch.n_windows))
     kind = "reference" if O.use_reference_kernel(True, traceback=True) else "port"
     cells = synth.algorithmic_cells(sub)
@@ -149,7 +232,10 @@ def cpu_reference_run(batch, n_windows, threads, steps=1, warmup=0):
         O.population_run(sub, n_threads=threads, want_ll=False)
     dt = (time.perf_counter() - t0) / max(1, steps)
     O.use_reference_kernel(False)
-    return cells / dt / 1e9, kind, dt, cells, sub.n_windows
+    desc = ("oracle restatement of anchoring / LL / GL / EM in C with %s, %d OpenMP threads" %
+            ("the unmodified reference align.c (with traceback) for every band alignment" if kind == "reference"
+             else "its own band alignment", threads))
+    return cells / dt / 1e9, kind, dt, cells, sub.n_windows, desc
 
 
 def run_reference_arm(args, rank, world):
@@ -157,12 +243,10 @@ def run_reference_arm(args, rank, world):
         return
     windows = args.windows
     batch, _ = make_workload(0, min(windows, CPU_SAMPLE_WINDOWS))
-    cores = os.cpu_count() or 1
-    gcups, kind, dt, cells, nw = cpu_reference_run(batch, CPU_SAMPLE_WINDOWS, cores, steps=args.steps, warmup=args.warmup)
-    sample = "first %d windows of the config-2 workload per step (%d pairs, %.3g cells), %d OpenMP threads, " \
-             "band alignment = %s" % (nw, nw * N_HAPS * N_READS, cells, cores,
-                                      "unmodified reference align.c with traceback (oracle/_ref)" if kind == "reference"
-                                      else "oracle restatement")
+    cores = args.cpu_procs or (os.cpu_count() or 1)
+    gcups, kind, dt, cells, nw, desc = cpu_reference_run(batch, args.cpu_windows or CPU_SAMPLE_WINDOWS, cores,
+                                                         steps=args.steps, warmup=args.warmup)
+    sample = "first %d windows of the workload per step (%d pairs, %.3g cells); %s" % (nw, nw * N_HAPS * N_READS, cells, desc)
     line = {
         "impl": "reference", "metric": METRIC, "value": gcups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -316,15 +400,20 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if world == 1:
+        # The CPU baseline runs in a fresh process (this one holds a CUDA context; the baseline forks workers).
         cores = os.cpu_count() or 1
-        g, kind, dt, ccells, nw = cpu_reference_run(batch, CPU_SAMPLE_WINDOWS, cores, steps=1, warmup=0)
-        g1, _, dt1, c1, nw1 = cpu_reference_run(batch, 250, 1, steps=1, warmup=0)
-        cpu = {"value": g, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": "first %d windows (%.3g cells) in %.2f s on %d threads; band alignment = %s; "
-                         "single-thread: %.3f GCUPS on %d windows" %
-                         (nw, ccells, dt, cores, "unmodified reference align.c with traceback (oracle/_ref)"
-                          if kind == "reference" else "oracle restatement", g1, nw1),
-               "single_thread_value": g1}
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                   "--windows", str(args.windows), "--config", str(args.config)]
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+            ref = json.loads(r.stdout.strip().splitlines()[-1])
+            cpu = dict(ref["cpu_baseline"])
+            r1 = subprocess.run(cmd + ["--cpu-procs", "1", "--cpu-windows", "250"], capture_output=True, text=True, timeout=900)
+            one = json.loads(r1.stdout.strip().splitlines()[-1])
+            cpu["single_process_value"] = one["value"]
+            cpu["sample"] += "; single process: %.3f GCUPS on 250 windows" % one["value"]
+        except Exception as e:   # never lose the GPU line over the baseline
+            cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "unavailable", "sample": "cpu baseline failed: %r" % (e,)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -351,6 +440,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--windows", type=int, default=WINDOWS_PER_GPU, help="windows per GPU (default: config 2)")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="--impl reference: processes (default: all host cores)")
+    ap.add_argument("--cpu-windows", type=int, default=0, help="--impl reference: windows per step (default: the workload)")
     ap.add_argument("--mode", default="default", choices=["default", "flank", "hla"],
                     help="run-time mode of the path: --calculateFlankScore=1 / --HLATyping=1 (not the headline)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3],

@@ -86,7 +86,7 @@ class _Options(object):
         self.filterReadPairsWithSmallInserts = 1
 
 
-cdef cAlignedRead** _make_reads(list reads, list keep) except NULL:
+cdef cAlignedRead** _make_reads(list reads, list keep, int shift=0) except NULL:
     cdef int n = len(reads)
     cdef cAlignedRead** arr = <cAlignedRead**>calloc(n + 1, sizeof(cAlignedRead*))
     cdef cAlignedRead* r
@@ -100,8 +100,8 @@ cdef cAlignedRead** _make_reads(list reads, list keep) except NULL:
         r.seq = <char*>seq
         r.qual = <char*>qual
         r.rlen = len(seq)
-        r.pos = pos
-        r.end = end
+        r.pos = pos - shift
+        r.end = end - shift
         r.mapq = mapq
         r.bitFlag = flag
         r.hash = NULL
@@ -257,6 +257,76 @@ def population(bytes genome, int win_start, int win_end, list hap_variants, list
             holders = [h for h in range(H) if v in (<Haplotype>haps[h]).variants]
             vars_out.append((key[0], key[1], key[2], post_flat, prior, post, holders))
         out["variants"] = vars_out
+    finally:
+        pop = None
+        buffers = []
+        haps = []
+        for (a, n) in all_arrays:
+            _free_reads(<cAlignedRead**><size_t>a, n)
+    return out
+
+
+def population_seq(list hap_seqs, int win_start, int win_end, int hap_start, list per_ind_reads, int hla=0, int flank=0,
+                   int use_em=0, int max_iters=100):
+    """The same Population.setup + call, for haplotypes given as SEQUENCES (how the engine's batches carry them):
+    haplotype h becomes a variant-free Haplotype over its own in-memory reference that holds exactly that sequence
+    at [hap_start, hap_start + len), so Haplotype.__init__ cuts the very same bytes.  Needs
+    win_start - hap_start = endBufferSize = min(2 * maxReadLength, 500) for some maxReadLength, i.e. an even flank
+    <= 500, and len = (win_end - win_start) + 2 * flank.  Used by bench.py --impl reference to time the reference's
+    own classes on the synthetic workload, and by tests to compare them with the oracle on it.
+    Returns dict: freq, gl, em, gl_log_max, gof, call, ll (per haplotype, individual 0 only)."""
+    cdef bytes name = b"chr"
+    cdef int n_ind = len(per_ind_reads)
+    cdef int H = len(hap_seqs)
+    cdef int flank_len = win_start - hap_start
+    if flank_len <= 0 or flank_len % 2 or flank_len > 500:
+        raise ValueError("flank %d cannot be written as min(2 * maxReadLength, 500)" % flank_len)
+    cdef int max_read_len = flank_len // 2
+    # genomic coordinates only enter through differences: move the window next to the origin so that the
+    # in-memory references stay as short as the haplotypes
+    cdef int shift = hap_start - 8
+    win_start -= shift
+    win_end -= shift
+    hap_start -= shift
+    opts = _Options(flank, hla, n_ind, max(H, 2), use_em)
+    cdef list keep = [], haps = [], buffers = [], all_arrays = []
+    cdef Haplotype hap
+    cdef bamReadBuffer buf
+    cdef Population pop
+    cdef cAlignedRead** arr
+    cdef int i, g, h, k, n, G = H * (H + 1) // 2
+    cdef bytes seq
+    out = {}
+    try:
+        for seq in hap_seqs:
+            if len(seq) != (win_end - win_start) + 2 * flank_len:
+                raise ValueError("haplotype length %d != window + 2 * flank" % len(seq))
+            # one spare base after the sequence: FastaFile.getSequence clamps endPos to seqLength - 1
+            hap = Haplotype(name, win_start, win_end, (), MemFasta(name, b"N" * hap_start + seq + b"N"), max_read_len, opts)
+            assert hap.hapLen == len(seq) and hap.cHaplotypeSequence[:hap.hapLen] == seq
+            haps.append(hap)
+        for (good, bad, broken) in per_ind_reads:
+            buf = bamReadBuffer(name, win_start, win_end, opts)
+            buf.sample = b"s"
+            for lst, ra in ((good, buf.reads), (bad, buf.badReads), (broken, buf.brokenMates)):
+                n = len(lst)
+                arr = _make_reads(lst, keep, shift)
+                all_arrays.append((<size_t>arr, n))
+                for k in range(n):
+                    (<cwindow.ReadArray>ra).append(arr[k])
+                (<cwindow.ReadArray>ra).windowStart = (<cwindow.ReadArray>ra).array
+                (<cwindow.ReadArray>ra).windowEnd = (<cwindow.ReadArray>ra).array + n
+            buffers.append(buf)
+        genotypes = generateAllGenotypesFromHaplotypeList(haps)
+        pop = Population(opts)
+        pop.setup([], haps, genotypes, n_ind, 0, buffers)
+        pop.call(max_iters, 0)
+        out["freq"] = [pop.frequencies[h] for h in range(H)]
+        out["gl"] = [[pop.genotypeLikelihoods[i][g] for g in range(G)] for i in range(n_ind)]
+        out["em"] = [[pop.EMLikelihoods[i][g] for g in range(G)] for i in range(n_ind)]
+        out["gl_log_max"] = [pop.maxLogLikelihoods[i] for i in range(n_ind)]
+        out["gof"] = [[pop.goodnessOfFitValues[g][i] for i in range(n_ind)] for g in range(G)]
+        out["call"] = [-1 if gt is None else [x is gt for x in genotypes].index(True) for gt in pop.genotypeCalls]
     finally:
         pop = None
         buffers = []

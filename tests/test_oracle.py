@@ -470,3 +470,20 @@ def test_vs_ref_n4_fuzz(oracle):
             assert ours["phased"][s, i].tolist() == [p1, p2]
             assert np.array_equal(ours["lik"][s, i, :len(liks)], np.array(liks))
             assert np.array_equal(ours["post"][s, i], np.array([gp, npo, rp]), equal_nan=True) and ours["gof"][s, i] == gf
+
+
+def test_vs_ref_classes_on_synth_workload(oracle):
+    """The reference's own classes on config-2 shaped synthetic windows (the path bench.py --impl reference times)
+    give exactly the oracle's genotype likelihoods, frequencies and calls."""
+    W = oracle.ref_l3()
+    if W is None:
+        pytest.skip("oracle/_ref/l3_ref_wrap not built (no reference checkout)")
+    import bench
+    from platypus_b200 import synth
+    b = synth.make_batch(12)
+    arrs, _, _, _ = oracle.population_run(b)
+    for w, a in enumerate(bench._window_args(b, b.n_windows)):
+        r = W.population_seq(*a)
+        assert np.array_equal(arrs["gl"][w, 0, :36], np.array(r["gl"][0]))
+        assert np.array_equal(arrs["freq"][w, :8], np.array(r["freq"]))
+        assert arrs["gl_log_max"][w, 0] == r["gl_log_max"][0] and list(arrs["call"][w]) == r["call"]
