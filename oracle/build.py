@@ -128,7 +128,7 @@ def build_calign_ref(force=False):
 
 
 L3_MODULES = ["htslibWrapper", "fastafile", "cerrormodel", "variant", "chaplotype", "cgenotype", "vcfutils", "cwindow",
-              "cpopulation", "l3_ref_wrap", "n4_ref"]
+              "cpopulation", "l3_ref_wrap", "n4_ref", "n1_ref"]
 
 # N4: computeGenotypeCallAndLikelihoods (src/cython/vcfutils.pyx:163-334) cannot be reached through its module
 # (vcfutils.pyx imports the Python-2 VCF and BAM I/O stack), so the function's own source lines are excerpted at
@@ -185,6 +185,53 @@ def compute_genotype_call_and_likelihoods(int n_variants, int n_haps, freqs, gl_
 """
 
 
+# N1: the haplotype selection loop.  variantFilter.pyx cimports platypusutils (the BAM I/O stack), so - as for N4 -
+# the three functions' own source lines are excerpted at build time into a scratch module between this header and
+# this footer: isHaplotypeValid (src/cython/platypusutils.pyx:735-802), computeBestScoreForGenotype
+# (src/cython/variantFilter.pyx:237-283) and getFilteredHaplotypes (variantFilter.pyx:377-506).  Nothing of them is
+# stored in the repo.
+N1_HEADER = """# cython: language_level=2
+# scratch module: header (declarations) + three functions of the reference, verbatim + forwarding defs
+from __future__ import division
+StandardError = Exception
+import logging
+logger = logging.getLogger("Log")
+from variant cimport Variant
+from chaplotype cimport Haplotype
+from fastafile cimport FastaFile
+from cgenotype cimport DiploidGenotype
+from htslibWrapper cimport cAlignedRead
+from cwindow cimport bamReadBuffer
+from operator import attrgetter
+from itertools import combinations
+from heapq import heappush,heappop,heappushpop
+nSupportingReadsGetter = attrgetter("nSupportingReads")
+
+cdef extern from "math.h":
+    double exp(double)
+    double log(double)
+    double log2(double)
+
+"""
+N1_FOOTER = """
+
+def get_filtered_haplotypes(bytes chrom, int windowStart, int windowEnd, FastaFile refFile, options, list variants,
+                            Haplotype refHaplotype, list readBuffers):
+    \"\"\"Forwards to getFilteredHaplotypes; returns the variant tuple of every haplotype it returns, in order.\"\"\"
+    cdef Haplotype h
+    haps = getFilteredHaplotypes({}, chrom, windowStart, windowEnd, refFile, options, variants, refHaplotype, readBuffers)
+    return [(<Haplotype>h).variants for h in haps]
+
+
+def compute_best_score_for_genotype(list readBuffers, Haplotype hap1, Haplotype hap2, int windowSize, int targetCoverage):
+    return computeBestScoreForGenotype(readBuffers, DiploidGenotype(hap1, hap2), windowSize, targetCoverage)
+
+
+def is_haplotype_valid(tuple variants):
+    return bool(isHaplotypeValid(variants))
+"""
+
+
 def l3_ref_paths():
     return [os.path.join(REF_OUT, m + _ext_suffix()) for m in L3_MODULES]
 
@@ -219,7 +266,8 @@ def build_l3_ref(force=False):
         return None
     cy = os.path.join(REF, "src", "cython")
     srcs = [os.path.join(cy, f) for f in ("chaplotype.pyx", "cgenotype.pyx", "cpopulation.pyx", "cwindow.pyx", "variant.pyx", "vcfutils.pyx",
-                                           "fastafile.pyx", "cerrormodel.pyx", "calign.pyx")] + [os.path.join(HERE, "l3_ref_wrap.pyx")]
+                                           "fastafile.pyx", "cerrormodel.pyx", "calign.pyx", "variantFilter.pyx",
+                                           "platypusutils.pyx")] + [os.path.join(HERE, "l3_ref_wrap.pyx")]
     if not force and all(_newer(o, srcs) for o in outs):
         return outs
     os.makedirs(REF_OUT, exist_ok=True)
@@ -294,7 +342,20 @@ def build_l3_ref(force=False):
         open(os.path.join(tmp, "n4_ref.pyx"), "w").write(N4_HEADER + "\n".join(vlines[a:b]) + N4_FOOTER)
         _run([sys.executable, "-m", "cython", "-2", "-X", "legacy_implicit_noexcept=True", "-I", tmp, "n4_ref.pyx", "-o", "n4_ref.c"],
              cwd=tmp)
-        for m in ref_mods + ("l3_ref_wrap", "n4_ref"):
+        # N1 excerpts: each function runs from its `cdef` line to the next rule of #'s
+        def excerpt(lines, start):
+            a = [i for i, l in enumerate(lines) if l.startswith(start)][0]
+            b = [i for i in range(a, len(lines)) if lines[i].startswith("####")][0]
+            return "\n".join(lines[a:b])
+        flines = open(os.path.join(cy, "variantFilter.pyx")).read().split("\n")
+        ulines = open(os.path.join(cy, "platypusutils.pyx")).read().split("\n")
+        open(os.path.join(tmp, "n1_ref.pyx"), "w").write(
+            N1_HEADER + excerpt(ulines, "cdef int isHaplotypeValid(") + "\n\n" +
+            excerpt(flines, "cdef double computeBestScoreForGenotype(") + "\n\n" +
+            excerpt(flines, "cdef list getFilteredHaplotypes(") + N1_FOOTER)
+        _run([sys.executable, "-m", "cython", "-2", "-X", "legacy_implicit_noexcept=True", "-I", tmp, "n1_ref.pyx", "-o", "n1_ref.c"],
+             cwd=tmp)
+        for m in ref_mods + ("l3_ref_wrap", "n4_ref", "n1_ref"):
             _run(["gcc"] + cflags + [m + ".c"] + extra.get(m, []) + ["-o", os.path.join(REF_OUT, m + _ext_suffix())], cwd=tmp)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

@@ -334,3 +334,72 @@ def population_seq(list hap_seqs, int win_start, int win_end, int hap_start, lis
         for (a, n) in all_arrays:
             _free_reads(<cAlignedRead**><size_t>a, n)
     return out
+
+
+def select_haplotypes(bytes genome, int win_start, int win_end, list variants, list per_ind_good, int max_read_len=150,
+                      int max_haplotypes=50, int original_max_haplotypes=50, int max_variants=8, int filter_by_coverage=1,
+                      int coverage_sampling_level=30, int flank=0, list score_sets=None):
+    """One window through the reference's haplotype selection loop (src/cython/variantFilter.pyx:377-506
+    getFilteredHaplotypes, :237-283 computeBestScoreForGenotype; excerpted into oracle/_ref/n1_ref by oracle/build.py).
+    variants: [(refPos, removed, added, nSupportingReads)] in the window's order; per_ind_good: per individual the
+    reads.windowStart..windowEnd list of (seq, qual, pos, end, mapq, bitFlag).
+    Returns dict: selected = [tuple of variant indices per returned haplotype, in order], ref_seq (the reference
+    haplotype's sequence), hap_seqs (Haplotype.cHaplotypeSequence of the returned haplotypes) and, when score_sets (a list
+    of index tuples) is given, scores = computeBestScoreForGenotype(ref, Haplotype(set)) for each."""
+    import n1_ref
+    cdef bytes name = b"chr"
+    cdef MemFasta fa = MemFasta(name, genome)
+    cdef int n_ind = len(per_ind_good)
+    opts = _Options(flank, 0, n_ind, max_haplotypes, 0)
+    opts.rlen = max_read_len
+    opts.maxHaplotypes = max_haplotypes
+    opts.originalMaxHaplotypes = original_max_haplotypes
+    opts.maxVariants = max_variants
+    opts.filterVarsByCoverage = filter_by_coverage
+    opts.coverageSamplingLevel = coverage_sampling_level
+    cdef list keep = [], buffers = [], all_arrays = [], vobjs = []
+    cdef bamReadBuffer buf
+    cdef cAlignedRead** arr
+    cdef Haplotype ref_hap, hap
+    cdef int k, n
+    out = {}
+    try:
+        for (p, rem, add, nsup) in variants:
+            vobjs.append(Variant(name, p, rem, add, nsup, 1))
+        for good in per_ind_good:
+            buf = bamReadBuffer(name, win_start, win_end, opts)
+            buf.sample = b"s"
+            n = len(good)
+            arr = _make_reads(good, keep)
+            all_arrays.append((<size_t>arr, n))
+            for k in range(n):
+                buf.reads.append(arr[k])
+            buf.reads.windowStart = buf.reads.array
+            buf.reads.windowEnd = buf.reads.array + n
+            for ra in (buf.badReads, buf.brokenMates):
+                (<cwindow.ReadArray>ra).windowStart = (<cwindow.ReadArray>ra).array
+                (<cwindow.ReadArray>ra).windowEnd = (<cwindow.ReadArray>ra).array
+            buffers.append(buf)
+        ref_hap = Haplotype(name, win_start, win_end, (), fa, max_read_len, opts)
+        out["ref_seq"] = <bytes>ref_hap.cHaplotypeSequence[:ref_hap.hapLen]
+        out["hap_start"] = ref_hap.startPos - ref_hap.endBufferSize
+        sel = n1_ref.get_filtered_haplotypes(name, win_start, win_end, fa, opts, vobjs, ref_hap, buffers)
+        index_of = {id(v): i for i, v in enumerate(vobjs)}
+        out["selected"] = [tuple(index_of[id(v)] for v in vs) for vs in sel]
+        seqs = []
+        for vs in sel:
+            hap = Haplotype(name, win_start, win_end, tuple(vs), fa, max_read_len, opts)
+            seqs.append(<bytes>hap.cHaplotypeSequence[:hap.hapLen])
+        out["hap_seqs"] = seqs
+        if score_sets is not None:
+            scores = []
+            for idxs in score_sets:
+                hap = Haplotype(name, win_start, win_end, tuple(vobjs[i] for i in idxs), fa, max_read_len, opts)
+                scores.append(n1_ref.compute_best_score_for_genotype(buffers, ref_hap, hap, win_end - win_start,
+                                                                     coverage_sampling_level))
+            out["scores"] = scores
+    finally:
+        buffers = []
+        for (a, n) in all_arrays:
+            _free_reads(<cAlignedRead**><size_t>a, n)
+    return out

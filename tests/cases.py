@@ -450,3 +450,107 @@ def check_n4(got, g, k, rtol=1e-12):
     np.testing.assert_allclose(got["lik"][:, :, :P][have], g["n%d_lik" % k][have], rtol=rtol, atol=0)
     np.testing.assert_allclose(got["post"][have], g["n%d_post" % k][have], rtol=rtol, atol=0, equal_nan=True)
     np.testing.assert_allclose(got["gof"][have], g["n%d_gof" % k][have], rtol=rtol, atol=0)
+
+
+# ---- N1: haplotype selection loop ------------------------------------------------------------------------------
+
+def n1_window_case(seed):
+    """One window for getFilteredHaplotypes (variantFilter.pyx:377-506): 3-9 candidate variants (SNPs, 1-3 bp
+    insertions / deletions, multi-allelic SNPs at one position whose unseen alleles give exactly tied scores, adjacent
+    SNP + indel pairs, overlapping deletions that make some combinations invalid), nSupportingReads with ties, 1-3
+    individuals (one may have no reads) with 8-90 good reads drawn from two true haplotypes, and the option values
+    (small maxHaplotypes so that the heap overflows; coverage levels that switch sub-sampling on)."""
+    rng = random.Random(1000003 * seed + 17)
+    genome = _rand_seq(rng, 2400)
+    if seed % 4 == 0:
+        genome = genome[:1215] + bytes([rng.choice(ACGT)]) * rng.randint(5, 12) + genome[1227:]
+        genome = genome[:2400]
+    ws = 1200 if seed % 11 else 120          # a window near the contig start: the left buffer is clamped
+    we = ws + rng.randint(30, 70)
+    max_read_len = rng.choice([100, 150]) if ws > 400 else 100
+    n_var = rng.randint(3, 9)
+    variants, pos = [], ws + rng.randint(0, 3)
+    while len(variants) < n_var and pos < we - 3:
+        kind = rng.random()
+        if kind < 0.5:
+            alts = [c for c in ACGT if c != genome[pos]]
+            rng.shuffle(alts)
+            for alt in sorted(alts[:rng.choice([1, 1, 1, 2, 3])]):
+                variants.append((pos, genome[pos:pos + 1], bytes([alt])))
+        elif kind < 0.7:
+            variants.append((pos, b"", _rand_seq(rng, rng.randint(1, 3))))
+        elif kind < 0.9:
+            k = rng.randint(1, 4)
+            variants.append((pos, genome[pos:pos + k], b""))
+        else:
+            k = rng.randint(2, 3)
+            variants.append((pos, genome[pos:pos + k], _rand_seq(rng, k)))
+        pos += rng.choice([0, 1, 1, 2, 3, 5, 8, 12])
+    # the reference's window lists are sorted Variants (variant.pyx:304-315: position, type, nRemoved) without duplicates
+    seen, uniq = set(), []
+    for v in variants:
+        if v not in seen:
+            seen.add(v)
+            uniq.append(v)
+
+    def vtype(v):
+        nr, na = len(v[1]), len(v[2])
+        return (0 if na == 1 else 1) if nr == na else 2 if nr == 0 else 3 if na == 0 else 4
+    uniq.sort(key=lambda v: (v[0], vtype(v), len(v[1])))
+    variants = [(p, r, a, rng.choice([1, 2, 2, 3, 5, 8, 20])) for (p, r, a) in uniq[:n_var]]
+    flank = min(2 * max_read_len, 500)
+    lo = max(0, ws - flank)
+
+    def apply(idxs):
+        out, cur = bytearray(), lo
+        for i in idxs:
+            p, rem, add, _ = variants[i]
+            if p < cur:
+                continue
+            if len(rem) == len(add):
+                out += genome[cur:p] + add
+                cur = p + len(rem)
+            elif not rem:
+                out += genome[cur:p + 1] + add
+                cur = p + 1
+            else:
+                out += genome[cur:p + 1]
+                cur = p + 1 + len(rem)
+        out += genome[cur:we + flank]
+        return bytes(out)
+    truth = []
+    for _ in range(2):
+        truth.append(apply(sorted(i for i in range(len(variants)) if rng.random() < 0.4)))
+    n_ind = rng.choice([1, 1, 2, 3])
+    per_ind = []
+    for i in range(n_ind):
+        if n_ind > 1 and i == 1 and rng.random() < 0.3:
+            per_ind.append([])
+            continue
+        n = rng.choice([8, 15, 30, 60, 90])
+        L0 = rng.choice([60, max_read_len])
+        reads = []
+        for _ in range(n):
+            L = L0 if rng.random() < 0.8 else rng.choice([30, 45, 60])
+            src = rng.choice(truth)
+            a = max(0, ws - lo - L + 10)
+            b = max(a, min(len(src) - L - 16, we - lo - 10))
+            idx = rng.randint(a, b)
+            seq = mutate(rng, src[idx:], L, n_rate=0.002)
+            qual = bytes(rng.randint(2, 41) for _ in range(L))
+            p = lo + idx + rng.choice([0, 0, 0, rng.randint(-4, 4)])
+            reads.append((seq, qual, p, p + L, rng.choice([60, 60, 60, 40, 23, 0]), 512 if rng.random() < 0.03 else 0))
+        reads.sort(key=lambda t: t[2])
+        per_ind.append(reads)
+    opts = dict(max_haplotypes=rng.choice([4, 6, 9, 17, 50]), max_variants=8, filter_by_coverage=rng.choice([0, 0, 1]),
+                coverage_sampling_level=rng.choice([3, 10, 30]))
+    opts["original_max_haplotypes"] = opts["max_haplotypes"] if rng.random() < 0.7 else opts["max_haplotypes"] + rng.randint(1, 6)
+    return dict(genome=genome, win_start=ws, win_end=we, variants=variants, per_ind=per_ind, max_read_len=max_read_len,
+                opts=opts)
+
+
+def n1_select_window(case, ref_seq, hap_start):
+    """oracle.select_oracle.SelectWindow of an n1_window_case (ref_seq / hap_start as the reference built them)."""
+    from oracle.select_oracle import SelectWindow
+    good = [[Read(t[0], t[1], t[2], t[3], t[4], bool(t[5] & 512)) for t in ind] for ind in case["per_ind"]]
+    return SelectWindow(ref_seq, case["win_start"], case["win_end"], hap_start, case["variants"], good)
