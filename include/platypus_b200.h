@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PLB_ABI_VERSION 2
+#define PLB_ABI_VERSION 3
 
 /* status codes */
 #define PLB_OK              0
@@ -304,6 +304,94 @@ typedef struct PlbSiteOut {
  */
 int plb_site_genotypes_host(PlbContext* ctx, const PlbWindowBatch* batch, const PlbPopulationOut* pop,
                             const PlbSiteBatch* sites, PlbSiteOut* out);
+
+/* -- N1: haplotype construction and the haplotype selection loop (the step before the window model) -- */
+
+/*
+ * The candidate variants of a batch of windows: the fields of Variant (src/cython/variant.pyx:109-145) that
+ * Haplotype.getMutatedSequence (src/cython/chaplotype.pyx:397-449), isHaplotypeValid
+ * (src/cython/platypusutils.pyx:735-802) and Variant.__richcmp__ (variant.pyx:282-353) read.  Per window in the
+ * order of the window's `variants` list, which the reference keeps sorted (position, type, nRemoved) and free of
+ * duplicates; both are checked (PLB_ERR_ARG).  At most 64 variants per window (bit v of a haplotype mask = variant v).
+ */
+typedef struct PlbVariantSet {
+    const int32_t* win_var_off;    /* [n_windows+1] variant index range of each window                  */
+    const int32_t* var_pos;        /* Variant.refPos                                                     */
+    const int32_t* var_n_removed;  /* len(Variant.removed)                                               */
+    const int32_t* var_n_support;  /* Variant.nSupportingReads; only read by plb_select_haplotypes_host  */
+    const int64_t* var_added_off;  /* [n_vars+1] byte offsets into var_added                             */
+    const uint8_t* var_added;      /* Variant.added, ASCII                                               */
+} PlbVariantSet;
+
+/* The options getFilteredHaplotypes reads (src/python/runner.py:519-597, variantcaller.pyx:920). */
+typedef struct PlbSelectOptions {
+    int32_t max_haplotypes;           /* options.maxHaplotypes (50)                                      */
+    int32_t original_max_haplotypes;  /* options.originalMaxHaplotypes (= maxHaplotypes); the heap holds
+                                         original_max_haplotypes - 1 <= 63 entries                        */
+    int32_t max_variants;             /* options.maxVariants (8)                                         */
+    int32_t filter_vars_by_coverage;  /* options.filterVarsByCoverage (1)                                */
+    int32_t coverage_sampling_level;  /* options.coverageSamplingLevel (30), > 0                         */
+} PlbSelectOptions;
+
+/* Per window: the variant sets of the haplotypes getFilteredHaplotypes returns, in its order, as bit masks
+ * over the window's variants; the reference haplotype is NOT in the list (the caller adds it, as
+ * variantcaller.pyx:116-120 does). */
+typedef struct PlbSelectOut {
+    int32_t   max_sel;    /* stride of sel_mask / sel_score; a window with more haplotypes -> PLB_ERR_SHAPE */
+    int32_t*  n_sel;      /* [W]                                                                          */
+    uint64_t* sel_mask;   /* [W][max_sel]                                                                 */
+    double*   sel_score;  /* [W][max_sel] computeBestScoreForGenotype of the kept haplotype; NaN in the
+                             enumerate-all branch (variantFilter.pyx:411-438); may be NULL                 */
+    int32_t*  n_scored;   /* [W] trial haplotypes scored (nHapsDone); may be NULL                          */
+} PlbSelectOut;
+
+/*
+ * Replaces Haplotype.__init__'s sequence construction (src/cython/chaplotype.pyx:127-172, 397-449) for n_haps
+ * haplotypes at once: haplotype k = the reference haplotype of window hap_win[k] (`ref_batch` holds exactly ONE
+ * haplotype per window: Haplotype.referenceSequence = refFile.getSequence(startPos - endBufferSize, endPos +
+ * endBufferSize), with win_start / win_end / hap_start as everywhere) mutated by the variants in hap_mask[k]
+ * (mask 0 = the reference haplotype itself).  Variants must lie inside [win_start, win_end].  Only the window
+ * fields and the haplotype arrays of ref_batch are read.  hap_seq_off[n_haps+1] is always written (lengths are
+ * computed on the host); the sequences are built on the GPU and written to hap_seq unless it is NULL; `capacity`
+ * = bytes available in hap_seq.
+ */
+int plb_build_haplotypes_host(PlbContext* ctx, const PlbWindowBatch* ref_batch, const PlbVariantSet* vars,
+                              int32_t n_haps, const int32_t* hap_win, const uint64_t* hap_mask,
+                              int64_t* hap_seq_off, uint8_t* hap_seq, int64_t capacity);
+
+/*
+ * Replaces getFilteredHaplotypes (src/cython/variantFilter.pyx:377-506) with computeBestScoreForGenotype
+ * (:237-283) for every window of a batch.  `ref_batch`: ONE haplotype per window (the refHaplotype argument) and,
+ * per (window, individual), the good-read list reads.windowStart..windowEnd (wi_n_good; bad reads and broken
+ * mates are ignored, as the reference ignores them here).  windowSize = win_end - win_start.
+ * Windows with few variants return every valid combination (no GPU work); the others run the reference's rounds
+ * - one per variant in order of decreasing nSupportingReads - batched over all windows: per round the trial
+ * haplotypes of every window are built on the GPU, every sampled read is scored against them (the S2 kernels;
+ * Haplotype.alignSingleRead), sum_r log(0.5 (e^LL_ref + e^LL_trial)) is reduced per (trial, individual) on the
+ * GPU, and the host replays the reference's heap operations (heapq / sorted / tuple comparison of
+ * (score, variants), including their behaviour on tied scores) on the returned scores.
+ */
+int plb_select_haplotypes_host(PlbContext* ctx, const PlbWindowBatch* ref_batch, const PlbVariantSet* vars,
+                               const PlbSelectOptions* sel, const PlbOptions* opt, PlbSelectOut* out);
+
+/*
+ * The host-side bookkeeping of plb_select_haplotypes_host alone (trial sets per round, isHaplotypeValid, the heap /
+ * sort replay, the final ranking), with the score of every trial haplotype supplied by the caller: per round
+ * `score` receives the trial haplotypes (window of the caller's batch + variant mask) and fills score_out (nonzero
+ * return = abort).  No GPU work and no scoring arithmetic: a hook for callers that score elsewhere and for the CPU
+ * tests of the bookkeeping.  Only the window / haplotype arrays of ref_batch are read.
+ */
+typedef int (*plb_trial_score_fn)(void* user, int32_t n_haps, const int32_t* hap_win, const uint64_t* hap_mask,
+                                  double* score_out);
+int plb_select_replay_host(const PlbWindowBatch* ref_batch, const PlbVariantSet* vars, const PlbSelectOptions* sel,
+                           plb_trial_score_fn score, void* user, PlbSelectOut* out);
+
+/* Device milliseconds of the last plb_select_haplotypes_host on this context, by stage: [0] reference-haplotype
+ * pass, [1] haplotype construction, [2] scoring kernels (k_prep..k_dp), [3] score reduction; [4] = host
+ * milliseconds in the heap replay and round planning, [5] = rounds, [6] = trial haplotypes scored,
+ * [7] = (read, haplotype) pairs scored, [8] = algorithmic cells (16 * readLen per pair), [9] = windows that took
+ * the scoring rounds.  Writes min(n, 10) values. */
+int plb_select_stats(PlbContext* ctx, double* out, int n);
 
 /* -- device-resident variants (inputs already in HBM; used by the multi-GPU driver) -- */
 

@@ -59,6 +59,31 @@ class PlbSiteOut(C.Structure):
                 ("gt", _p), ("gl_log10", _p)]
 
 
+class PlbVariantSet(C.Structure):
+    _fields_ = [("win_var_off", _p), ("var_pos", _p), ("var_n_removed", _p), ("var_n_support", _p),
+                ("var_added_off", _p), ("var_added", _p)]
+
+
+class PlbSelectOptions(C.Structure):
+    _fields_ = [("max_haplotypes", C.c_int32), ("original_max_haplotypes", C.c_int32), ("max_variants", C.c_int32),
+                ("filter_vars_by_coverage", C.c_int32), ("coverage_sampling_level", C.c_int32)]
+
+    @classmethod
+    def default(cls, **kw):
+        """Defaults of src/python/runner.py:519-597 (originalMaxHaplotypes = maxHaplotypes, variantcaller.pyx:920)."""
+        o = cls(50, 50, 8, 1, 30)
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+
+class PlbSelectOut(C.Structure):
+    _fields_ = [("max_sel", C.c_int32), ("n_sel", _p), ("sel_mask", _p), ("sel_score", _p), ("n_scored", _p)]
+
+
+TRIAL_SCORE_FN = C.CFUNCTYPE(C.c_int, _p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_double))
+
+
 class PlbRunStats(C.Structure):
     _fields_ = [("n_pairs", C.c_int64), ("n_pairs_scored", C.c_int64), ("n_dp", C.c_int64), ("cells", C.c_int64),
                 ("n_anchor_heavy", C.c_int64), ("n_anchor_verify", C.c_int64), ("n_anchor_exact", C.c_int64)]
@@ -121,6 +146,16 @@ def declare(lib):
     lib.plb_set_timing.restype = C.c_int
     lib.plb_kernel_times.argtypes = [_p, P(C.c_float)]
     lib.plb_kernel_times.restype = C.c_int
+    lib.plb_build_haplotypes_host.argtypes = [_p, P(PlbWindowBatch), P(PlbVariantSet), C.c_int32, _p, _p, _p, _p, C.c_int64]
+    lib.plb_build_haplotypes_host.restype = C.c_int
+    lib.plb_select_haplotypes_host.argtypes = [_p, P(PlbWindowBatch), P(PlbVariantSet), P(PlbSelectOptions), P(PlbOptions),
+                                               P(PlbSelectOut)]
+    lib.plb_select_haplotypes_host.restype = C.c_int
+    lib.plb_select_replay_host.argtypes = [P(PlbWindowBatch), P(PlbVariantSet), P(PlbSelectOptions), TRIAL_SCORE_FN, _p,
+                                           P(PlbSelectOut)]
+    lib.plb_select_replay_host.restype = C.c_int
+    lib.plb_select_stats.argtypes = [_p, P(C.c_double), C.c_int]
+    lib.plb_select_stats.restype = C.c_int
     return lib
 
 
@@ -131,5 +166,7 @@ EXPORTED_SYMBOLS = [
     "plb_align_flank_batch_host", "plb_gap_open_host",
     "plb_window_loglik_host", "plb_population_run_host", "plb_site_genotypes_host", "plb_batch_upload", "plb_batch_free",
     "plb_run_device", "plb_last_stats", "plb_set_timing", "plb_kernel_times",
+    "plb_build_haplotypes_host", "plb_select_haplotypes_host", "plb_select_replay_host",
+    "plb_select_stats",
 ]
 KERNEL_NAMES = ["k_prep", "k_anchor", "k_general", "k_dp", "k_genotype", "k_population"]

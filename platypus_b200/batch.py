@@ -357,3 +357,44 @@ def site_out_struct(arrs):
     for k in ("phased", "lik", "post", "phred", "gof", "gt", "gl_log10"):
         setattr(o, k, _abi.ptr(arrs[k]))
     return o
+
+
+# ---- N1: candidate variants of a batch of windows ------------------------------------------------------------------
+
+@dataclass
+class VariantSet:
+    """The candidate variants of every window of a batch (PlbVariantSet in include/platypus_b200.h): the fields of the
+    reference's Variant that haplotype construction and the selection loop read (src/cython/variant.pyx:109-145).
+    Per window in the order of the window's sorted `variants` list."""
+    win_var_off: np.ndarray
+    var_pos: np.ndarray
+    var_n_removed: np.ndarray
+    var_n_support: np.ndarray
+    var_added_off: np.ndarray
+    var_added: np.ndarray
+
+    @classmethod
+    def from_lists(cls, per_window):
+        """per_window: for every window a list of (refPos, removed | len(removed), added, nSupportingReads)."""
+        off, pos, nrem, nsup, aoff, added = [0], [], [], [], [0], bytearray()
+        for vs in per_window:
+            for v in vs:
+                p, rem, add = v[0], v[1], v[2]
+                pos.append(p)
+                nrem.append(rem if isinstance(rem, int) else len(rem))
+                nsup.append(v[3] if len(v) > 3 else 1)
+                added += add
+                aoff.append(len(added))
+            off.append(len(pos))
+        return cls(np.asarray(off, np.int32), np.asarray(pos, np.int32), np.asarray(nrem, np.int32),
+                   np.asarray(nsup, np.int32), np.asarray(aoff, np.int64),
+                   np.frombuffer(bytes(added) + b"\0", np.uint8).copy())
+
+    def n_vars(self, w):
+        return int(self.win_var_off[w + 1] - self.win_var_off[w])
+
+    def as_struct(self):
+        s = _abi.PlbVariantSet()
+        for k in ("win_var_off", "var_pos", "var_n_removed", "var_n_support", "var_added_off", "var_added"):
+            setattr(s, k, _abi.ptr(getattr(self, k)))
+        return s

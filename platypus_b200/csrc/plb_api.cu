@@ -98,6 +98,7 @@ struct PlbDeviceBatch {
     int32_t max_haps = 0;              // largest H in the batch
     size_t em_scratch_elems = 0;
     bool have_var = false;
+    bool shares_reads = false;         // window / slot / read arrays belong to another batch (prepare_batch `share`)
     int64_t n_wi = 0;
     std::vector<ChunkPlan> chunks;     // plb_batch_upload plans one chunk covering every window
     int64_t* h_ll_off = nullptr;       // pinned
@@ -541,7 +542,11 @@ static ByteRanges byte_ranges(const PlbWindowBatch* hb, int w0, int w1) {
 }
 
 // Plans tiles, allocates one device block and lays every array out in it.  No copies.
-static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch** out) {
+// `share` (the selection rounds, plb_select.cuh): the batch covers a prefix of the windows of `share` with the very
+// same slots and reads but other haplotypes; the window-, slot- and read-side arrays are then those of `share`
+// (already on the device) and only the haplotype-side arrays and the scratch are laid out.
+static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch** out,
+                         const PlbDeviceBatch* share = nullptr) {
     if (!c || !hb || !out) return set_err(PLB_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(c->device));
     const int W = hb->n_windows, nInd = hb->n_individuals;
@@ -554,7 +559,7 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
 
     PlbDeviceBatch* db = new PlbDeviceBatch();
     db->n_wi = nwi;
-    pin_reset(c);
+    if (!share) pin_reset(c);   // the rounds of a selection keep the arena of their call
     db->h_ll_off = (int64_t*)pin_alloc(c, ((size_t)nwi + 1) * 8);
     if (!db->h_ll_off) {
         delete db;
@@ -569,20 +574,21 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
 
     // device layout
     Layout L;
-    const size_t o_win_hap_off = L.take((size_t)(W + 1) * 4), o_win_start = L.take((size_t)W * 4),
-                 o_win_end = L.take((size_t)W * 4), o_hap_start = L.take((size_t)W * 4),
+    const size_t own = share ? 0 : 1;   // 0: the array is the one of `share`
+    const size_t o_win_hap_off = L.take((size_t)(W + 1) * 4), o_win_start = L.take(own * W * 4),
+                 o_win_end = L.take(own * W * 4), o_hap_start = L.take(own * W * 4),
                  o_hap_seq_off = L.take((size_t)(n_haps + 1) * 8), o_hap_seq = L.take((size_t)hap_bytes + 64),
-                 o_wi_slot_off = L.take((size_t)(nwi + 1) * 8), o_wi_n_good = L.take((size_t)nwi * 4),
-                 o_wi_n_bad = L.take((size_t)nwi * 4), o_slot_read = L.take((size_t)n_slots * 4),
-                 o_read_seq_off = L.take((size_t)(n_reads + 1) * 8), o_read_seq = L.take((size_t)read_bytes + 64),
-                 o_read_qual = L.take((size_t)read_bytes + 64), o_read_pos = L.take((size_t)n_reads * 4),
-                 o_read_end = L.take((size_t)n_reads * 4), o_read_mapq = L.take((size_t)n_reads),
-                 o_read_qcfail = L.take((size_t)n_reads);
+                 o_wi_slot_off = L.take(own * (nwi + 1) * 8), o_wi_n_good = L.take(own * nwi * 4),
+                 o_wi_n_bad = L.take(own * nwi * 4), o_slot_read = L.take(own * n_slots * 4),
+                 o_read_seq_off = L.take(own * (n_reads + 1) * 8), o_read_seq = L.take(own * (read_bytes + 64)),
+                 o_read_qual = L.take(own * (read_bytes + 64)), o_read_pos = L.take(own * n_reads * 4),
+                 o_read_end = L.take(own * n_reads * 4), o_read_mapq = L.take(own * n_reads),
+                 o_read_qcfail = L.take(own * n_reads);
     const bool have_var = hb->max_variants > 0 && hb->win_n_var && hb->hap_var_mask && hb->var_prior;
     db->have_var = have_var;
     const size_t o_win_n_var = L.take(have_var ? (size_t)W * 4 : 0), o_hap_var_mask = L.take(have_var ? (size_t)n_haps * 8 : 0),
                  o_var_prior = L.take(have_var ? (size_t)W * hb->max_variants * 8 : 0);
-    const size_t o_slot_wi = L.take((size_t)n_slots * 4), o_hap_win = L.take((size_t)n_haps * 4),
+    const size_t o_slot_wi = L.take(own * n_slots * 4), o_hap_win = L.take((size_t)n_haps * 4),
                  o_ll_off = L.take((size_t)(nwi + 1) * 8);
     const size_t o_gap = L.take((size_t)hap_bytes + n_haps + 64), o_wgen = L.take((size_t)W * 4 + 64),
                  o_c0 = L.take((size_t)n_pairs * 4), o_c1 = L.take((size_t)n_pairs * 4),
@@ -593,7 +599,7 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
     const size_t o_q3 = L.take((size_t)qcap * sizeof(QueueEntry)), o_qcount3 = L.take(64);
     const size_t o_ll = L.take((size_t)n_pairs * 8);
     const int Gp = max_H * (max_H + 1) / 2;
-    db->em_scratch_elems = (size_t)W * nInd * Gp;
+    db->em_scratch_elems = share ? 0 : (size_t)W * nInd * Gp;   // the selection rounds never run the window model
     const size_t o_em = L.take(db->em_scratch_elems * 8);
 
     int rc = block_get(c, L.off + 256, &db->blk);
@@ -649,6 +655,25 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
     db->q3.cap = qcap;
     db->ll_scratch = at<double>(B, o_ll);
     db->em_scratch = at<double>(B, o_em);
+    if (share) {
+        const DevBatch& s = share->d;
+        d.win_start = s.win_start;
+        d.win_end = s.win_end;
+        d.hap_start = s.hap_start;
+        d.wi_slot_off = s.wi_slot_off;
+        d.wi_n_good = s.wi_n_good;
+        d.wi_n_bad = s.wi_n_bad;
+        d.slot_read = s.slot_read;
+        d.read_seq_off = s.read_seq_off;
+        d.read_seq = s.read_seq;
+        d.read_qual = s.read_qual;
+        d.read_pos = s.read_pos;
+        d.read_end = s.read_end;
+        d.read_mapq = s.read_mapq;
+        d.read_qcfail = s.read_qcfail;
+        d.slot_wi = s.slot_wi;
+        db->shares_reads = true;
+    }
     *out = db;
     return PLB_OK;
 }
@@ -840,10 +865,12 @@ static int copy_meta(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* hb
     const size_t h0 = (size_t)hb->win_hap_off[w0], nh = (size_t)hb->win_hap_off[w1] - h0;
     const size_t s0 = (size_t)hb->wi_slot_off[wi0], ns = (size_t)hb->wi_slot_off[wi0 + nwi] - s0;
     CUQ(cp(d.win_hap_off, hb->win_hap_off, w0, nw + 1, 4));
+    CUQ(cp(d.hap_seq_off, hb->hap_seq_off, h0, nh + 1, 8));
+    CUQ(cp(d.ll_off, db->h_ll_off, wi0, nwi + 1, 8));
+    if (db->shares_reads) return PLB_OK;
     CUQ(cp(d.win_start, hb->win_start, w0, nw, 4));
     CUQ(cp(d.win_end, hb->win_end, w0, nw, 4));
     CUQ(cp(d.hap_start, hb->hap_start, w0, nw, 4));
-    CUQ(cp(d.hap_seq_off, hb->hap_seq_off, h0, nh + 1, 8));
     CUQ(cp(d.wi_slot_off, hb->wi_slot_off, wi0, nwi + 1, 8));
     CUQ(cp(d.wi_n_good, hb->wi_n_good, wi0, nwi, 4));
     CUQ(cp(d.wi_n_bad, hb->wi_n_bad, wi0, nwi, 4));
@@ -853,7 +880,6 @@ static int copy_meta(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* hb
         CUQ(cp(d.hap_var_mask, hb->hap_var_mask, h0, nh, 8));
         CUQ(cp(d.var_prior, hb->var_prior, (size_t)w0 * hb->max_variants, nw * hb->max_variants, 8));
     }
-    CUQ(cp(d.ll_off, db->h_ll_off, wi0, nwi + 1, 8));
     // per-read arrays: the parts of [rmin, rmax] not uploaded yet
     if (rmax >= rmin) {
         auto reads = [&](size_t first, size_t count) -> int {
@@ -1789,3 +1815,6 @@ extern "C" int plb_gap_open_host(PlbContext* c, int32_t n_haps, const int64_t* o
     if (e2 != cudaSuccess) return set_err(PLB_ERR_CUDA, "plb_gap_open_host: %s", cudaGetErrorString(e2));
     return PLB_OK;
 }
+
+// ---- N1: haplotype construction + selection loop ------------------------------------------------
+#include "plb_select.cuh"

@@ -256,6 +256,79 @@ class Engine:
         _check(self.lib, self.lib.plb_site_genotypes_host(self.ctx, C.byref(s), C.byref(po), C.byref(ss), C.byref(so)))
         return arrs
 
+    # ---- N1 ---------------------------------------------------------------------------------
+    def build_haplotypes(self, ref_batch: WindowBatch, variants, hap_win, hap_mask):
+        """Haplotype.haplotypeSequence of haplotype k = the reference haplotype of window hap_win[k] (ref_batch holds
+        ONE haplotype per window) mutated by the window's variants in bit mask hap_mask[k] (reference:
+        src/cython/chaplotype.pyx:127-172, 397-449).  Returns a list of bytes."""
+        hap_win = np.ascontiguousarray(hap_win, np.int32)
+        hap_mask = np.ascontiguousarray(hap_mask, np.uint64)
+        n = len(hap_win)
+        off = np.zeros(n + 1, np.int64)
+        s, v = ref_batch.as_struct(), variants.as_struct()
+        _check(self.lib, self.lib.plb_build_haplotypes_host(self.ctx, C.byref(s), C.byref(v), n, _abi.ptr(hap_win),
+                                                            _abi.ptr(hap_mask), _abi.ptr(off), None, 0))
+        seq = np.zeros(int(off[-1]) + 1, np.uint8)
+        _check(self.lib, self.lib.plb_build_haplotypes_host(self.ctx, C.byref(s), C.byref(v), n, _abi.ptr(hap_win),
+                                                            _abi.ptr(hap_mask), _abi.ptr(off), _abi.ptr(seq), int(off[-1])))
+        return [seq[int(off[k]):int(off[k + 1])].tobytes() for k in range(n)]
+
+    def select_haplotypes(self, ref_batch: WindowBatch, variants, sel=None, opt=None, max_sel=None):
+        """getFilteredHaplotypes for every window of a batch (reference: src/cython/variantFilter.pyx:377-506,
+        237-283).  ref_batch: ONE haplotype per window (the reference haplotype) + the good reads per individual;
+        variants: batch.VariantSet.  Returns dict: n_sel [W], sel_mask [W][max_sel] (bit v = window variant v),
+        sel_score [W][max_sel], n_scored [W]."""
+        sel = sel or _abi.PlbSelectOptions.default()
+        opt = opt or _abi.PlbOptions.default()
+        W = ref_batch.n_windows
+        if max_sel is None:
+            nv = int(np.max(np.diff(variants.win_var_off))) if W else 0
+            max_sel = max(1, sel.max_haplotypes - 1, sel.original_max_haplotypes - 1, min(2 ** min(nv, 20) - 1, 1 << 16))
+        arrs = {"max_sel": max_sel, "n_sel": np.zeros(W, np.int32), "sel_mask": np.zeros((W, max_sel), np.uint64),
+                "sel_score": np.full((W, max_sel), np.nan), "n_scored": np.zeros(W, np.int32)}
+        o = _abi.PlbSelectOut(max_sel, _abi.ptr(arrs["n_sel"]), _abi.ptr(arrs["sel_mask"]), _abi.ptr(arrs["sel_score"]),
+                              _abi.ptr(arrs["n_scored"]))
+        s, v = ref_batch.as_struct(), variants.as_struct()
+        _check(self.lib, self.lib.plb_select_haplotypes_host(self.ctx, C.byref(s), C.byref(v), C.byref(sel), C.byref(opt),
+                                                             C.byref(o)))
+        return arrs
+
+    @staticmethod
+    def select_replay(ref_batch: WindowBatch, variants, score_fn, sel=None, max_sel=None, lib=None):
+        """The selection loop's bookkeeping alone (plb_select_replay_host): score_fn(hap_win, hap_mask) -> scores is
+        called once per round with numpy arrays.  No GPU work; needs no context."""
+        lib = lib or load_library()
+        sel = sel or _abi.PlbSelectOptions.default()
+        W = ref_batch.n_windows
+        if max_sel is None:
+            nv = int(np.max(np.diff(variants.win_var_off))) if W else 0
+            max_sel = max(1, sel.max_haplotypes - 1, sel.original_max_haplotypes - 1, min(2 ** min(nv, 20) - 1, 1 << 16))
+        arrs = {"max_sel": max_sel, "n_sel": np.zeros(W, np.int32), "sel_mask": np.zeros((W, max_sel), np.uint64),
+                "sel_score": np.full((W, max_sel), np.nan), "n_scored": np.zeros(W, np.int32)}
+        o = _abi.PlbSelectOut(max_sel, _abi.ptr(arrs["n_sel"]), _abi.ptr(arrs["sel_mask"]), _abi.ptr(arrs["sel_score"]),
+                              _abi.ptr(arrs["n_scored"]))
+
+        def cb(user, n, hw, hm, out):
+            try:
+                sc = score_fn(np.ctypeslib.as_array(hw, (n,)).copy(), np.ctypeslib.as_array(hm, (n,)).copy())
+                np.ctypeslib.as_array(out, (n,))[:] = sc
+                return 0
+            except Exception:   # surfaces as PLB_ERR_ARG
+                import traceback
+                traceback.print_exc()
+                return 1
+        s, v = ref_batch.as_struct(), variants.as_struct()
+        _check(lib, lib.plb_select_replay_host(C.byref(s), C.byref(v), C.byref(sel), _abi.TRIAL_SCORE_FN(cb), None, C.byref(o)))
+        return arrs
+
+    def select_stats(self):
+        """Stage times and counts of the last select_haplotypes (plb_select_stats)."""
+        a = (C.c_double * 10)()
+        _check(self.lib, self.lib.plb_select_stats(self.ctx, a, 10))
+        keys = ("ref_pass_ms", "build_ms", "score_ms", "reduce_ms", "host_ms", "rounds", "n_trials", "n_pairs", "cells",
+                "n_filter_windows")
+        return dict(zip(keys, [float(x) for x in a]))
+
     # ---- device-resident path -------------------------------------------------------------------
     def upload(self, batch: WindowBatch):
         h = C.c_void_p()

@@ -1,5 +1,8 @@
 """Deterministic test-case generators shared by the golden-vector script and the tests."""
+import os
 import random
+
+import numpy as np
 
 from platypus_b200.batch import Read, Window, WindowBatch
 
@@ -554,3 +557,38 @@ def n1_select_window(case, ref_seq, hap_start):
     from oracle.select_oracle import SelectWindow
     good = [[Read(t[0], t[1], t[2], t[3], t[4], bool(t[5] & 512)) for t in ind] for ind in case["per_ind"]]
     return SelectWindow(ref_seq, case["win_start"], case["win_end"], hap_start, case["variants"], good)
+
+
+def n1_batch(cases, ref_seqs, hap_starts):
+    """(WindowBatch with ONE reference haplotype per window + the good reads, VariantSet) of n1_window_cases that
+    share a number of individuals (windows with fewer individuals get empty read lists)."""
+    from platypus_b200.batch import VariantSet
+    n_ind = max(len(c["per_ind"]) for c in cases)
+    wins = []
+    for c, ref, hs in zip(cases, ref_seqs, hap_starts):
+        per = [([Read(t[0], t[1], t[2], t[3], t[4], bool(t[5] & 512)) for t in ind], [], []) for ind in c["per_ind"]]
+        per += [([], [], [])] * (n_ind - len(per))
+        wins.append(Window(c["win_start"], c["win_end"], hs, [ref], per))
+    return WindowBatch.from_windows(wins, n_ind, dedupe_reads=False), VariantSet.from_lists([c["variants"] for c in cases])
+
+
+def masks_of(sets):
+    return [sum(1 << i for i in s) for s in sets]
+
+
+def n1_golden_cases(golden_dir):
+    """The committed reference outputs for n1_window_case(seed) (tests/golden/make_n1_fixture.py): per seed
+    ref_seq, hap_start, selected masks, the sequences of the selected haplotypes, and the trial sets + scores of
+    every round."""
+    z = np.load(os.path.join(golden_dir, "n1_ref.npz"), allow_pickle=False)
+    out = []
+    for k, seed in enumerate(z["seeds"]):
+        a, b = z["sel_off"][k], z["sel_off"][k + 1]
+        t0, t1 = z["trial_off"][k], z["trial_off"][k + 1]
+        seqs = [z["hap_seq"][z["hap_seq_off"][j]:z["hap_seq_off"][j + 1]].tobytes() for j in range(a, b)]
+        out.append(dict(seed=int(seed), ref_seq=z["ref_seq"][z["ref_off"][k]:z["ref_off"][k + 1]].tobytes(),
+                        hap_start=int(z["hap_start"][k]), sel_mask=[int(m) for m in z["sel_mask"][a:b]], hap_seqs=seqs,
+                        trial_mask=[int(m) for m in z["trial_mask"][t0:t1]], trial_score=z["trial_score"][t0:t1],
+                        opts={k2: int(z["opt_" + k2][k]) for k2 in ("max_haplotypes", "original_max_haplotypes", "max_variants",
+                                                                   "filter_by_coverage", "coverage_sampling_level")}))
+    return out

@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_abi.EXPORTED_SYMBOLS), declared ^ set(_abi.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.plb_abi_version() == 2
+    assert lib.plb_abi_version() == 3
 
 
 def test_no_gpu_fails_loudly():
@@ -106,3 +106,50 @@ def test_synth_shapes_match_config2_accounting():
     assert lens.min() >= 100 and lens.max() <= 250
     hl = np.diff(v.hap_seq_off)
     assert (hl >= lens.max() + 16).all() and hl.max() <= 500
+
+
+def test_n1_selection_bookkeeping_replay(oracle, golden_dir):
+    """plb_select_replay_host (the library's trial sets / isHaplotypeValid / heap and sort replay / final ranking, no
+    GPU) fed with the reference's own trial scores reproduces the reference's selection on the golden windows: every
+    round asks for exactly the trial sets the reference scores, in its order, and the returned haplotypes match."""
+    from platypus_b200.engine import Engine
+    lib = _lib()
+    gold = cases.n1_golden_cases(golden_dir)
+    by_opts = {}
+    for g in gold:
+        by_opts.setdefault(tuple(sorted(g["opts"].items())), []).append(g)
+    n_windows = 0
+    for key, group in by_opts.items():
+        o = dict(key)
+        cs = [cases.n1_window_case(g["seed"]) for g in group]
+        batch, vset = cases.n1_batch(cs, [g["ref_seq"] for g in group], [g["hap_start"] for g in group])
+        table = [dict(zip(g["trial_mask"], g["trial_score"])) for g in group]
+        asked = [[] for _ in group]
+
+        def score(hap_win, hap_mask):
+            for w, m in zip(hap_win, hap_mask):
+                asked[int(w)].append(int(m))
+            return [table[int(w)][int(m)] for w, m in zip(hap_win, hap_mask)]
+        sel = _abi.PlbSelectOptions(o["max_haplotypes"], o["original_max_haplotypes"], o["max_variants"], o["filter_by_coverage"],
+                                    o["coverage_sampling_level"])
+        out = Engine.select_replay(batch, vset, score, sel, lib=lib)
+        for k, g in enumerate(group):
+            n = int(out["n_sel"][k])
+            assert [int(m) for m in out["sel_mask"][k, :n]] == g["sel_mask"], g["seed"]
+            assert asked[k] == g["trial_mask"], g["seed"]
+            assert int(out["n_scored"][k]) == len(g["trial_mask"])
+            n_windows += 1
+    assert n_windows == len(gold)
+
+
+def test_n1_selection_rejects_bad_variant_lists(golden_dir):
+    from platypus_b200.engine import Engine, PlbError
+    from platypus_b200.batch import VariantSet
+    lib = _lib()
+    g = cases.n1_golden_cases(golden_dir)[0]
+    c = cases.n1_window_case(g["seed"])
+    batch, _ = cases.n1_batch([c], [g["ref_seq"]], [g["hap_start"]])
+    vs = c["variants"]
+    for bad in ([vs[1], vs[0]] + vs[2:], vs + [vs[-1]], [(c["win_end"] + 5, b"A", b"C", 1)]):
+        with pytest.raises(PlbError):
+            Engine.select_replay(batch, VariantSet.from_lists([bad]), lambda w, m: [0.0] * len(w), lib=lib)

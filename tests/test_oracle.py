@@ -487,3 +487,51 @@ def test_vs_ref_classes_on_synth_workload(oracle):
         assert np.array_equal(arrs["gl"][w, 0, :36], np.array(r["gl"][0]))
         assert np.array_equal(arrs["freq"][w, :8], np.array(r["freq"]))
         assert arrs["gl_log_max"][w, 0] == r["gl_log_max"][0] and list(arrs["call"][w]) == r["call"]
+
+
+# ---- N1: haplotype construction + selection loop ------------------------------------------------------------------
+
+def _n1_oracle_run(c, ref_seq, hap_start):
+    from oracle import select_oracle as S
+    o = c["opts"]
+    w = cases.n1_select_window(c, ref_seq, hap_start)
+    tr = []
+    got = S.select_haplotypes(w, o["max_haplotypes"], o["original_max_haplotypes"], o["max_variants"], o["filter_by_coverage"],
+                              o["coverage_sampling_level"], trace=tr)
+    sel = [g[0] for g in got]
+    seqs = [S.build_haplotype(w.ref_seq, w.win_start, w.win_end, w.hap_start, tuple(w.vars[i] for i in s)) for s in sel]
+    return sel, seqs, [vs for rnd in tr for (vs, _) in rnd], [s for rnd in tr for (_, s) in rnd]
+
+
+def test_golden_n1_ref(oracle, golden_dir):
+    """Selection oracle vs the reference's getFilteredHaplotypes / computeBestScoreForGenotype / Haplotype outputs."""
+    gold = cases.n1_golden_cases(golden_dir)
+    assert len(gold) >= 60
+    n_filter = n_tied = 0
+    for g in gold:
+        c = cases.n1_window_case(g["seed"])
+        sel, seqs, sets, scores = _n1_oracle_run(c, g["ref_seq"], g["hap_start"])
+        assert cases.masks_of(sel) == g["sel_mask"], g["seed"]
+        assert seqs == g["hap_seqs"], g["seed"]
+        assert cases.masks_of(sets) == g["trial_mask"], g["seed"]
+        assert scores == list(g["trial_score"]), g["seed"]          # bit for bit: same libm, same order of additions
+        n_filter += bool(sets)
+        n_tied += len(scores) - len(set(scores))
+    assert n_filter >= 40 and n_tied >= 100    # the fixture exercises the heap rounds and exactly tied scores
+
+
+def test_vs_ref_n1_fuzz(oracle):
+    ref = oracle.ref_l3()
+    if ref is None:
+        pytest.skip("reference not available (oracle/_ref)")
+    for seed in range(200, 260):
+        c = cases.n1_window_case(seed)
+        o = c["opts"]
+        args = (c["genome"], c["win_start"], c["win_end"], c["variants"], c["per_ind"], c["max_read_len"], o["max_haplotypes"],
+                o["original_max_haplotypes"], o["max_variants"], o["filter_by_coverage"], o["coverage_sampling_level"])
+        r = ref.select_haplotypes(*args)
+        sel, seqs, sets, scores = _n1_oracle_run(c, r["ref_seq"], r["hap_start"])
+        assert sel == r["selected"], seed
+        assert seqs == r["hap_seqs"], seed
+        if sets:
+            assert ref.select_haplotypes(*args, 0, sets)["scores"] == scores, seed
