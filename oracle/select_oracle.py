@@ -226,3 +226,27 @@ def select_haplotypes(w, max_haplotypes=50, original_max_haplotypes=50, max_vari
         else:
             break
     return out
+
+
+def window_from_batch(batch, vset, w):
+    """SelectWindow of window w of a (WindowBatch with one reference haplotype per window, VariantSet) pair - the
+    inputs of plb_select_haplotypes_host."""
+    nI = batch.n_individuals
+    vs = []
+    for i in range(int(vset.win_var_off[w]), int(vset.win_var_off[w + 1])):
+        add = vset.var_added[int(vset.var_added_off[i]):int(vset.var_added_off[i + 1])].tobytes()
+        vs.append((int(vset.var_pos[i]), b"N" * int(vset.var_n_removed[i]), add, int(vset.var_n_support[i])))
+    good = []
+    for i in range(nI):
+        wi = w * nI + i
+        s0 = int(batch.wi_slot_off[wi])
+        reads = []
+        for s in range(s0, s0 + int(batch.wi_n_good[wi])):
+            r = int(batch.slot_read[s])
+            a, b = int(batch.read_seq_off[r]), int(batch.read_seq_off[r + 1])
+            reads.append(Read(batch.read_seq[a:b].tobytes(), batch.read_qual[a:b].tobytes(), int(batch.read_pos[r]),
+                              int(batch.read_end[r]), int(batch.read_mapq[r]), bool(batch.read_qcfail[r])))
+        good.append(reads)
+    h = int(batch.win_hap_off[w])
+    ref = batch.hap_seq[int(batch.hap_seq_off[h]):int(batch.hap_seq_off[h + 1])].tobytes()
+    return SelectWindow(ref, int(batch.win_start[w]), int(batch.win_end[w]), int(batch.hap_start[w]), vs, good)

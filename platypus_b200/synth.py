@@ -266,3 +266,138 @@ def make_batch_parallel(n_windows, window_offset=0, n_procs=None, **kw):
     with mp.get_context("fork").Pool(n_procs) as pool:
         parts = pool.map(_make_range, jobs)
     return concat_batches(parts)
+
+
+# ---- N1 workload: windows for the haplotype selection loop ("synth-select-v1") ---------------------------------------
+
+def make_select_batch(n_windows, n_vars=8, n_reads=64, read_len=150, hap_len=250, n_individuals=1, seed=SEED + 1,
+                      window_offset=0):
+    """Windows for getFilteredHaplotypes (src/cython/variantFilter.pyx:377-506), one RNG stream per window.
+
+    Per window: a reference segment of hap_len iid ACGT (15 % with a homopolymer run), interval = the central 50 bp,
+    n_vars candidate variants (SNP 70 % / 1-3 bp insertion 15 % / 1-3 bp deletion 15 %) at distinct positions of the
+    interval at least 4 bp apart (so every combination is a valid haplotype), nSupportingReads U[1,20]; two true
+    haplotypes carry each variant with probability 0.35; reads as in synth-v1 (same qualities, error rates, mapq mix
+    and position jitter), all good, sorted by position as a read buffer holds them.
+    Returns (WindowBatch with ONE reference haplotype per window, VariantSet)."""
+    from .batch import VariantSet
+    W, nI = n_windows, n_individuals
+    R = n_reads * nI
+    assert n_vars <= 12
+    c0 = (hap_len - 50) // 2
+    ref_chunks, read_seq_chunks, read_qual_chunks, per_window_vars = [], [], [], []
+    read_pos = np.zeros(W * R, np.int32)
+    read_mapq = np.zeros(W * R, np.uint8)
+    hap_start = np.zeros(W, np.int32)
+    win_start = np.zeros(W, np.int32)
+    for w in range(W):
+        wg = window_offset + w
+        rng = np.random.Generator(np.random.Philox(key=[seed, wg]))
+        ref = _ACGT[rng.integers(0, 4, hap_len)]
+        if rng.random() < 0.15:
+            run = int(rng.integers(4, 13))
+            p = int(rng.integers(hap_len // 3, 2 * hap_len // 3 - run))
+            ref[p:p + run] = ref[p]
+        hs = 100000 + wg * 1000
+        pos = np.sort(rng.choice(12, n_vars, replace=False)) * 4 + c0 + 1
+        variants = []
+        for p in pos:
+            p = int(p)
+            u = rng.random()
+            if u < 0.70:
+                alt = _ACGT[(int(np.searchsorted(_ACGT, ref[p])) + int(rng.integers(1, 4))) % 4]
+                variants.append((hs + p, 1, bytes([alt]), int(rng.integers(1, 21))))
+            elif u < 0.85:
+                variants.append((hs + p, 0, _ACGT[rng.integers(0, 4, int(rng.integers(1, 4)))].tobytes(), int(rng.integers(1, 21))))
+            else:
+                variants.append((hs + p, int(rng.integers(1, 4)), b"", int(rng.integers(1, 21))))
+        truth = []
+        for _ in range(2):
+            out, cur = [], 0
+            for (gp, nrem, add, _n) in variants:
+                if rng.random() >= 0.35:
+                    continue
+                p = gp - hs
+                if nrem == len(add):
+                    out += [ref[cur:p], np.frombuffer(add, np.uint8)]
+                    cur = p + nrem
+                elif nrem == 0:
+                    out += [ref[cur:p + 1], np.frombuffer(add, np.uint8)]
+                    cur = p + 1
+                else:
+                    out.append(ref[cur:p + 1])
+                    cur = p + 1 + nrem
+            out.append(ref[cur:])
+            truth.append(np.concatenate(out))
+        tl = min(len(t) for t in truth)
+        hap2d = np.stack([t[:tl] for t in truth])
+        L = read_len
+        src = rng.integers(0, 2, R)
+        idx = (rng.random(R) * (tl - L - 16 + 1)).astype(np.int64)
+        q = np.where(rng.random((R, L)) < 0.9, rng.integers(25, 41, (R, L)), rng.integers(2, 25, (R, L))).astype(np.uint8)
+        ev = rng.random((R, L))
+        ins = ev < 0.001
+        dele = (ev >= 0.001) & (ev < 0.002)
+        adv = np.ones((R, L), np.int64) - ins + dele
+        srcpos = np.minimum(idx[:, None] + np.cumsum(adv, axis=1) - adv, tl - 1)
+        bases = hap2d[src[:, None], srcpos]
+        bases = np.where(ins, _ACGT[rng.integers(0, 4, (R, L))], bases)
+        sub = rng.random((R, L)) < np.power(10.0, -q.astype(np.float64) / 10.0)
+        alt = _ACGT[(np.searchsorted(_ACGT, bases) + rng.integers(1, 4, (R, L))) % 4]
+        bases = np.where(sub, alt, bases).astype(np.uint8)
+        u = rng.random(R)
+        mq = np.where(u < 0.85, 60, np.where(u < 0.95, rng.integers(20, 60, R), rng.integers(0, 20, R)))
+        jit = np.where(rng.random(R) < 0.9, 0, rng.integers(-5, 6, R))
+        rp = hs + idx + jit
+        # per individual, reads sorted by position (stable)
+        order = np.concatenate([i * n_reads + np.argsort(rp[i * n_reads:(i + 1) * n_reads], kind="stable") for i in range(nI)])
+        read_seq_chunks.append(bases[order].reshape(-1))
+        read_qual_chunks.append(q[order].reshape(-1))
+        read_pos[w * R:(w + 1) * R] = rp[order]
+        read_mapq[w * R:(w + 1) * R] = mq[order]
+        hap_start[w] = hs
+        win_start[w] = hs + c0
+        ref_chunks.append(ref)
+        per_window_vars.append(variants)
+    b = WindowBatch(
+        n_windows=W, n_individuals=nI, win_hap_off=np.arange(W + 1, dtype=np.int32), win_start=win_start,
+        win_end=(win_start + 50).astype(np.int32), hap_start=hap_start,
+        hap_seq_off=np.arange(W + 1, dtype=np.int64) * hap_len,
+        hap_seq=np.concatenate(ref_chunks) if W else np.zeros(0, np.uint8),
+        wi_slot_off=np.arange(W * nI + 1, dtype=np.int64) * n_reads,
+        wi_n_good=np.full(W * nI, n_reads, np.int32), wi_n_bad=np.zeros(W * nI, np.int32),
+        slot_read=np.arange(W * R, dtype=np.int32), read_seq_off=np.arange(W * R + 1, dtype=np.int64) * read_len,
+        read_seq=np.concatenate(read_seq_chunks) if W else np.zeros(0, np.uint8),
+        read_qual=np.concatenate(read_qual_chunks) if W else np.zeros(0, np.uint8),
+        read_pos=read_pos, read_end=(read_pos + read_len).astype(np.int32), read_mapq=read_mapq,
+        read_qcfail=np.zeros(W * R, np.uint8))
+    return b, VariantSet.from_lists(per_window_vars)
+
+
+def _make_select_range(args):
+    lo, hi, kw = args
+    return make_select_batch(hi - lo, window_offset=lo, **kw)
+
+
+def make_select_batch_parallel(n_windows, window_offset=0, n_procs=None, **kw):
+    """make_select_batch() over a process pool (per-window RNG streams, so the bytes are identical)."""
+    import multiprocessing as mp
+    import os
+    from .batch import VariantSet, concat_batches
+    n_procs = n_procs or min(os.cpu_count() or 1, 32)
+    if n_procs <= 1 or n_windows <= 512:
+        return make_select_batch(n_windows, window_offset=window_offset, **kw)
+    cuts = np.linspace(window_offset, window_offset + n_windows, 2 * n_procs + 1).astype(int)
+    jobs = [(int(a), int(b), kw) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    with mp.get_context("fork").Pool(n_procs) as pool:
+        parts = pool.map(_make_select_range, jobs)
+    batch = concat_batches([p[0] for p in parts])
+    vs = [p[1] for p in parts]
+    nv = np.cumsum([0] + [len(v.var_pos) for v in vs])
+    na = np.cumsum([0] + [int(v.var_added_off[-1]) for v in vs])
+    return batch, VariantSet(
+        np.concatenate([vs[0].win_var_off] + [v.win_var_off[1:] + nv[i] for i, v in enumerate(vs) if i]).astype(np.int32),
+        np.concatenate([v.var_pos for v in vs]), np.concatenate([v.var_n_removed for v in vs]),
+        np.concatenate([v.var_n_support for v in vs]),
+        np.concatenate([vs[0].var_added_off] + [v.var_added_off[1:] + na[i] for i, v in enumerate(vs) if i]).astype(np.int64),
+        np.concatenate([v.var_added[:int(v.var_added_off[-1])] for v in vs] + [np.zeros(1, np.uint8)]))

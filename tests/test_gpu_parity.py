@@ -493,3 +493,118 @@ def test_n4_golden_ref(engine, golden_dir):
     for k, (b, sites) in enumerate(cases.n4_cases()):
         pop = engine.population_run(b)
         cases.check_n4(engine.site_genotypes(b, pop, sites), g, k, rtol=RTOL_TIGHT)
+
+
+# ---- N1: haplotype construction + selection loop ------------------------------------------------------------------
+
+def _n1_groups(golden_dir):
+    by_opts = {}
+    for g in cases.n1_golden_cases(golden_dir):
+        by_opts.setdefault(tuple(sorted(g["opts"].items())), []).append(g)
+    out = []
+    for key, group in by_opts.items():
+        cs = [cases.n1_window_case(g["seed"]) for g in group]
+        batch, vset = cases.n1_batch(cs, [g["ref_seq"] for g in group], [g["hap_start"] for g in group])
+        o = dict(key)
+        sel = _abi.PlbSelectOptions(o["max_haplotypes"], o["original_max_haplotypes"], o["max_variants"], o["filter_by_coverage"],
+                                    o["coverage_sampling_level"])
+        out.append((group, batch, vset, sel))
+    return out
+
+
+def test_n1_build_haplotypes_golden_ref(engine, golden_dir):
+    """k_build_haps vs Haplotype.cHaplotypeSequence of the reference (tests/golden/n1_ref.npz): every selected variant
+    set of every golden window, the reference haplotype (mask 0) and every trial set of the rounds."""
+    from oracle import select_oracle as S
+    n = 0
+    for group, batch, vset, _ in _n1_groups(golden_dir):
+        hap_win, hap_mask, want = [], [], []
+        for k, g in enumerate(group):
+            c = cases.n1_window_case(g["seed"])
+            w = cases.n1_select_window(c, g["ref_seq"], g["hap_start"])
+            hap_win.append(k)
+            hap_mask.append(0)
+            want.append(g["ref_seq"])
+            for m, seq in zip(g["sel_mask"], g["hap_seqs"]):
+                hap_win.append(k)
+                hap_mask.append(m)
+                want.append(seq)
+            for m in g["trial_mask"][:40]:     # trial sets: against the oracle's builder (itself pinned on the selected ones)
+                hap_win.append(k)
+                hap_mask.append(m)
+                want.append(S.build_haplotype(w.ref_seq, w.win_start, w.win_end, w.hap_start,
+                                              tuple(v for v in w.vars if m >> v.idx & 1)))
+        got = engine.build_haplotypes(batch, vset, hap_win, hap_mask)
+        assert got == want
+        n += len(want)
+    assert n > 2000
+
+
+def test_n1_select_golden_ref(engine, golden_dir):
+    """plb_select_haplotypes_host vs the reference's getFilteredHaplotypes on the golden windows: the same variant sets
+    in the same order (the fixture is full of exactly tied scores), scores within 1e-9 of computeBestScoreForGenotype."""
+    n_sel = 0
+    for group, batch, vset, sel in _n1_groups(golden_dir):
+        out = engine.select_haplotypes(batch, vset, sel)
+        for k, g in enumerate(group):
+            n = int(out["n_sel"][k])
+            assert [int(m) for m in out["sel_mask"][k, :n]] == g["sel_mask"], g["seed"]
+            assert int(out["n_scored"][k]) == len(g["trial_mask"])
+            table = dict(zip(g["trial_mask"], g["trial_score"]))
+            for j in range(n):
+                if g["trial_mask"]:
+                    np.testing.assert_allclose(out["sel_score"][k, j], table[int(out["sel_mask"][k, j])], rtol=RTOL_TIGHT)
+                else:
+                    assert np.isnan(out["sel_score"][k, j])
+            n_sel += n
+    assert n_sel > 500
+
+
+def test_n1_select_flank_mode_vs_oracle(engine, oracle):
+    """options.calculateFlankScore reaches alignSingleRead inside the selection loop as well (chaplotype.pyx:384)."""
+    from oracle import select_oracle as S
+    batch, vset = synth.make_select_batch(12, n_vars=7, n_reads=24, read_len=100, hap_len=250, seed=77)
+    opt = _abi.PlbOptions.default(calc_flank_score=1)
+    sel = _abi.PlbSelectOptions.default(max_haplotypes=12, original_max_haplotypes=12)
+    out = engine.select_haplotypes(batch, vset, sel, opt)
+    for w in range(batch.n_windows):
+        want = S.select_haplotypes(S.window_from_batch(batch, vset, w), 12, 12, 8, 1, 30, opt=opt)
+        n = int(out["n_sel"][w])
+        assert [int(m) for m in out["sel_mask"][w, :n]] == cases.masks_of([s for s, _ in want]), w
+        np.testing.assert_allclose(out["sel_score"][w, :n], [s for _, s in want], rtol=RTOL_TIGHT)
+
+
+def test_n1_select_synth_batch_vs_oracle(engine, oracle):
+    """The bench workload's shape (8 variants, 64 reads of 150 bp, 250 bp reference segment, default options: 163 trial
+    haplotypes per window in 8 rounds) on 600 windows with mixed variant counts and 2 individuals; 24 windows against
+    the oracle, all of them through size-independent properties."""
+    from oracle import select_oracle as S
+    b1, v1 = synth.make_select_batch(300, n_vars=8, n_individuals=2, n_reads=32)
+    b2, v2 = synth.make_select_batch(200, n_vars=6, n_individuals=2, n_reads=32, window_offset=300)
+    b3, v3 = synth.make_select_batch(100, n_vars=3, n_individuals=2, n_reads=32, window_offset=500)   # enumerate-all branch
+    from platypus_b200.batch import VariantSet, concat_batches
+    batch = concat_batches([b2, b1, b3])    # not sorted by variant count: the engine orders the rounds itself
+    parts = [v2, v1, v3]
+    nv = np.cumsum([0] + [len(v.var_pos) for v in parts])
+    na = np.cumsum([0] + [int(v.var_added_off[-1]) for v in parts])
+    vset = VariantSet(
+        np.concatenate([parts[0].win_var_off] + [v.win_var_off[1:] + nv[i] for i, v in enumerate(parts) if i]).astype(np.int32),
+        np.concatenate([v.var_pos for v in parts]), np.concatenate([v.var_n_removed for v in parts]),
+        np.concatenate([v.var_n_support for v in parts]),
+        np.concatenate([parts[0].var_added_off] + [v.var_added_off[1:] + na[i] for i, v in enumerate(parts) if i]).astype(np.int64),
+        np.concatenate([v.var_added[:int(v.var_added_off[-1])] for v in parts] + [np.zeros(1, np.uint8)]))
+    out = engine.select_haplotypes(batch, vset)
+    st = engine.select_stats()
+    assert st["rounds"] == 8 and st["n_filter_windows"] == 500
+    assert np.all(out["n_sel"][:200] == 49) and np.all(out["n_sel"][200:500] == 49) and np.all(out["n_sel"][500:] == 7)
+    assert np.all(out["n_scored"][:200] == 1 + 2 + 4 + 8 + 16 + 32) and np.all(out["n_scored"][200:500] == 163)
+    for w in range(500):
+        sc = out["sel_score"][w, :49]
+        assert np.all(np.diff(sc) <= 0)                       # best first
+        assert len(set(int(m) for m in out["sel_mask"][w, :49])) == 49
+    for w in list(range(0, 200, 25)) + list(range(200, 500, 25)) + [500, 550, 599, 1]:
+        want = S.select_haplotypes(S.window_from_batch(batch, vset, w))
+        n = int(out["n_sel"][w])
+        assert [int(m) for m in out["sel_mask"][w, :n]] == cases.masks_of([s for s, _ in want]), w
+        if w < 500:
+            np.testing.assert_allclose(out["sel_score"][w, :n], [s for _, s in want], rtol=RTOL_TIGHT)
