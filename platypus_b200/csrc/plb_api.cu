@@ -546,7 +546,7 @@ static ByteRanges byte_ranges(const PlbWindowBatch* hb, int w0, int w1) {
 // same slots and reads but other haplotypes; the window-, slot- and read-side arrays are then those of `share`
 // (already on the device) and only the haplotype-side arrays and the scratch are laid out.
 static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch** out,
-                         const PlbDeviceBatch* share = nullptr) {
+                         const PlbDeviceBatch* share = nullptr, bool reset_arena = true) {
     if (!c || !hb || !out) return set_err(PLB_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(c->device));
     const int W = hb->n_windows, nInd = hb->n_individuals;
@@ -559,7 +559,7 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
 
     PlbDeviceBatch* db = new PlbDeviceBatch();
     db->n_wi = nwi;
-    if (!share) pin_reset(c);   // the rounds of a selection keep the arena of their call
+    if (!share && reset_arena) pin_reset(c);   // the rounds of a selection keep the arena of their call
     db->h_ll_off = (int64_t*)pin_alloc(c, ((size_t)nwi + 1) * 8);
     if (!db->h_ll_off) {
         delete db;

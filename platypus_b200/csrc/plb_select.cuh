@@ -238,6 +238,17 @@ static void heap_pushpop(std::vector<SelEntry>& h, SelEntry e, const SelKeys& k)
 // above is not a strict weak order (see sel_lt), so the result depends on the algorithm.
 static void py_sort(std::vector<SelEntry>& a, const SelKeys& k, bool reverse) {
     const int n = (int)a.size();
+    {   // distinct scores: the order is total and every correct sort returns the same list
+        std::vector<SelEntry> b = a;
+        std::sort(b.begin(), b.end(), [](const SelEntry& x, const SelEntry& y) { return x.score < y.score; });
+        bool distinct = true;
+        for (int i = 1; i < n && distinct; ++i) distinct = b[(size_t)i - 1].score != b[(size_t)i].score;
+        if (distinct) {
+            if (reverse) std::reverse(b.begin(), b.end());
+            a.swap(b);
+            return;
+        }
+    }
     if (reverse) std::reverse(a.begin(), a.end());
     if (n >= 2) {
         int run = 2;
@@ -359,8 +370,8 @@ static thread_local SelStats g_sel_stats{};
 
 }  // namespace
 
-extern "C" int plb_select_stats(PlbContext* c, double* out, int n) {
-    if (!c || !out || n < 0) return set_err(PLB_ERR_ARG, "NULL argument");
+extern "C" int plb_select_stats(PlbContext*, double* out, int n) {   // the statistics are per host thread
+    if (!out || n < 0) return set_err(PLB_ERR_ARG, "NULL argument");
     for (int i = 0; i < n; ++i) out[i] = i < 10 ? g_sel_stats.v[i] : 0.0;
     return PLB_OK;
 }
@@ -438,8 +449,23 @@ extern "C" int plb_build_haplotypes_host(PlbContext* c, const PlbWindowBatch* rb
     return PLB_OK;
 }
 
-// One round of the selection as the scorer sees it: Wr windows (a prefix of the processing order), nh trial
-// haplotypes in window order.
+// Length of a VALID haplotype without walking it: every variant changes the length by nAdded - nRemoved (anchor
+// bases and reference stretches are copied one for one) unless the walk runs past the window end, where the right
+// buffer would repeat bases; a valid set keeps `cur` <= pos + 1 before each variant, so cur never exceeds
+// max(pos + nRemoved + 2).  Returns -1 when that bound crosses win_end (the caller walks instead).
+static inline int64_t fast_hap_length(uint64_t mask, int64_t ref_len, int win_end, const int32_t* pos, const int32_t* nrem,
+                                      const int32_t* nadd) {
+    int64_t len = ref_len;
+    for (uint64_t m = mask; m; m &= m - 1) {
+        const int v = __builtin_ctzll(m);
+        if (pos[v] + nrem[v] + 2 > win_end) return -1;
+        len += nadd[v] - nrem[v];
+    }
+    return len;
+}
+
+// One round of one group of windows as the scorer sees it: Wr windows (a prefix of the group's processing order), nh
+// trial haplotypes in window order.  The arrays live in pinned host memory when the scorer supplied it.
 struct SelRound {
     int Wr, nh;
     const int32_t* hap_off;     // [Wr+1]
@@ -448,9 +474,16 @@ struct SelRound {
     const int* n_trials;        // [Wr]
 };
 
-// Host-side inputs of the scoring rounds: the filter-branch windows in processing order (decreasing variant count).
+struct SelEntryState {
+    std::vector<int> order;       // variants by decreasing nSupportingReads (stable), window-local indices
+    std::vector<SelEntry> heap;
+    int n_done = 0;
+};
+
+// Host-side inputs and state of the scoring rounds of one GROUP of windows: filter-branch windows in processing
+// order (decreasing variant count, so that the windows of round r are a prefix).
 struct SelPlan {
-    int Wf = 0, nInd = 1, max_rounds = 0, max_trials = 0;
+    int gid = 0, Wf = 0, nInd = 1, max_rounds = 0, max_trials = 0;
     std::vector<int> filt;   // processing order -> window of the caller's batch
     std::vector<int32_t> ws, we, hs, hoff, zero;
     std::vector<int64_t> hsoff, slot_off;
@@ -461,13 +494,33 @@ struct SelPlan {
     std::vector<uint8_t> add;
     std::vector<int64_t> win_cells;   // 16 * readLen summed over the window's sampled reads
     PlbWindowBatch batch{};           // one reference haplotype per window + the sampled reads as broken mates
+    // rounds
+    std::vector<SelEntryState> state;
+    std::vector<uint64_t> trial_mask;
+    std::vector<int> n_trials;
+    int r = 0, Wr = 0, nh = 0;
+    bool active = false;
+    // per-round arrays handed to the scorer: pinned when the scorer provides memory (set in prepare), else own_*
+    int32_t* r_hoff = nullptr;
+    int64_t* r_hsoff = nullptr;
+    uint64_t* mask_c = nullptr;
+    double* scores = nullptr;
+    std::vector<int32_t> own_hoff;
+    std::vector<int64_t> own_hsoff;
+    std::vector<uint64_t> own_mask;
+    std::vector<double> own_scores;
 };
 
-// The reference's loop with the scoring of a round's trial haplotypes left to `score_round` (the GPU in
-// plb_select_haplotypes_host; the caller in plb_select_replay_host).  `prepare(plan)` runs once before the rounds.
-template <typename Prepare, typename ScoreRound>
+// The reference's loop with the scoring of a round's trial haplotypes left to the scorer (the GPU in
+// plb_select_haplotypes_host; the caller in plb_select_replay_host):
+//   prepare(plan)        once per group before its rounds (may point plan.r_hoff / r_hsoff / mask_c / scores at pinned memory)
+//   submit(plan, round)  start scoring the round's trial haplotypes into plan.scores (may return before they are there)
+//   wait(plan)           block until plan.scores is complete
+// Large batches are cut into two groups whose rounds alternate, so that the host's bookkeeping for one group runs
+// while the scorer works on the other.
+template <typename Prepare, typename Submit, typename Wait>
 static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const PlbSelectOptions* so, const PlbOptions* opt,
-                       PlbSelectOut* out, bool need_reads, Prepare&& prepare, ScoreRound&& score_round) {
+                       PlbSelectOut* out, bool need_reads, Prepare&& prepare, Submit&& submit, Wait&& wait) {
     if (!so || !out || !out->n_sel || !out->sel_mask) return set_err(PLB_ERR_ARG, "NULL argument");
     SelHost sh;
     int rc = check_variants(rb, vs, sh);
@@ -484,10 +537,10 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
     memset(&g_sel_stats, 0, sizeof g_sel_stats);
     const double log2cap = std::log2((double)cap);
     const double nan_v = std::nan("");
+    static const bool check_len = getenv("PLB_SELECT_CHECK") != nullptr;
 
     // ---- windows with few variants: every valid combination, in itertools.combinations order (:411-438)
-    SelPlan P;
-    std::vector<int>& filt = P.filt;   // windows that take the scoring rounds
+    std::vector<int> filt;   // windows that take the scoring rounds
     for (int w = 0; w < W; ++w) {
         const int v0 = vs->win_var_off[w], n = vs->win_var_off[w + 1] - v0;
         if (out->n_scored) out->n_scored[w] = 0;
@@ -520,133 +573,162 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
         }
         out->n_sel[w] = k_out;
     }
-    const int Wf = (int)filt.size();
-    if (Wf == 0) return PLB_OK;
+    const int Wf_all = (int)filt.size();
+    if (Wf_all == 0) return PLB_OK;
     if (out->max_sel < std::min(cap, orig_cap))
         return set_err(PLB_ERR_SHAPE, "max_sel = %d < min(max_haplotypes, original_max_haplotypes) - 1", out->max_sel);
 
-    // ---- processing order: decreasing variant count, so that the windows of round r are a prefix
+    // ---- processing order: decreasing variant count; two groups (alternate windows of that order) when the batch is
+    //      large enough for each group to fill the GPU
     std::stable_sort(filt.begin(), filt.end(), [&](int a, int b) {
         return vs->win_var_off[a + 1] - vs->win_var_off[a] > vs->win_var_off[b + 1] - vs->win_var_off[b];
     });
-    P.Wf = Wf;
-    P.nInd = nInd;
-    P.max_rounds = vs->win_var_off[filt[0] + 1] - vs->win_var_off[filt[0]];
-    P.max_trials = orig_cap + 1;
-    const int max_trials = P.max_trials;
+    int n_groups = Wf_all >= 2048 ? 2 : 1;
+    if (const char* e = getenv("PLB_SELECT_GROUPS")) n_groups = std::max(1, std::min({atoi(e), 2, Wf_all}));   // tests
+    std::vector<SelPlan> groups((size_t)n_groups);
+    for (int i = 0; i < Wf_all; ++i) groups[(size_t)(i % n_groups)].filt.push_back(filt[(size_t)i]);
+    const int max_trials = orig_cap + 1;
+    double cells_total = 0;
 
-    // ---- the sampled-read batch (variantFilter.pyx:253-277: every sampleRate-th good read), reads as broken mates
-    P.ws.resize((size_t)Wf);
-    P.we.resize((size_t)Wf);
-    P.hs.resize((size_t)Wf);
-    P.hoff.resize((size_t)Wf + 1);
-    P.zero.assign((size_t)Wf * nInd, 0);
-    P.hsoff.resize((size_t)Wf + 1);
-    P.slot_off.resize((size_t)Wf * nInd + 1);
-    P.voff.resize((size_t)Wf + 1);
-    P.aoff.assign(1, 0);
-    P.win_cells.assign((size_t)Wf, 0);
-    P.hoff[0] = 0;
-    P.hsoff[0] = 0;
-    P.slot_off[0] = 0;
-    P.voff[0] = 0;
-    for (int k = 0; k < Wf; ++k) {
-        const int w = filt[(size_t)k];
-        P.ws[(size_t)k] = rb->win_start[w];
-        P.we[(size_t)k] = rb->win_end[w];
-        P.hs[(size_t)k] = rb->hap_start[w];
-        P.hoff[(size_t)k + 1] = k + 1;
-        const int64_t r0 = rb->hap_seq_off[w], r1 = rb->hap_seq_off[w + 1];
-        P.ref.insert(P.ref.end(), rb->hap_seq + r0, rb->hap_seq + r1);
-        P.hsoff[(size_t)k + 1] = (int64_t)P.ref.size();
-        const int size = rb->win_end[w] - rb->win_start[w];
-        for (int i = 0; i < nInd && need_reads; ++i) {
-            const int64_t wi = (int64_t)w * nInd + i;
-            const int64_t b0 = rb->wi_slot_off[wi];
-            const int n_good = rb->wi_n_good[wi];
-            if (n_good > 0) {
-                const int r_first = rb->slot_read[b0];
-                const int64_t rlen = rb->read_seq_off[r_first + 1] - rb->read_seq_off[r_first];
-                const int64_t mean_cov = rlen * n_good / size;
-                const int rate = (int)std::max<int64_t>(1, mean_cov / so->coverage_sampling_level);
-                for (int t = 0; t < n_good; t += rate) {
-                    const int r = rb->slot_read[b0 + t];
-                    P.slot.push_back(r);
-                    P.win_cells[(size_t)k] += 16 * (rb->read_seq_off[r + 1] - rb->read_seq_off[r]);
+    // ---- per group: the sampled-read batch (variantFilter.pyx:253-277: every sampleRate-th good read), reads as
+    //      broken mates, and the variant tables
+    for (int g = 0; g < n_groups; ++g) {
+        SelPlan& P = groups[(size_t)g];
+        const int Wf = (int)P.filt.size();
+        P.gid = g;
+        P.Wf = Wf;
+        P.nInd = nInd;
+        P.max_rounds = vs->win_var_off[P.filt[0] + 1] - vs->win_var_off[P.filt[0]];
+        P.max_trials = max_trials;
+        P.ws.resize((size_t)Wf);
+        P.we.resize((size_t)Wf);
+        P.hs.resize((size_t)Wf);
+        P.hoff.resize((size_t)Wf + 1);
+        P.zero.assign((size_t)Wf * nInd, 0);
+        P.hsoff.resize((size_t)Wf + 1);
+        P.slot_off.resize((size_t)Wf * nInd + 1);
+        P.voff.resize((size_t)Wf + 1);
+        P.aoff.assign(1, 0);
+        P.win_cells.assign((size_t)Wf, 0);
+        P.hoff[0] = 0;
+        P.hsoff[0] = 0;
+        P.slot_off[0] = 0;
+        P.voff[0] = 0;
+        for (int k = 0; k < Wf; ++k) {
+            const int w = P.filt[(size_t)k];
+            P.ws[(size_t)k] = rb->win_start[w];
+            P.we[(size_t)k] = rb->win_end[w];
+            P.hs[(size_t)k] = rb->hap_start[w];
+            P.hoff[(size_t)k + 1] = k + 1;
+            const int64_t r0 = rb->hap_seq_off[w], r1 = rb->hap_seq_off[w + 1];
+            P.ref.insert(P.ref.end(), rb->hap_seq + r0, rb->hap_seq + r1);
+            P.hsoff[(size_t)k + 1] = (int64_t)P.ref.size();
+            const int size = rb->win_end[w] - rb->win_start[w];
+            for (int i = 0; i < nInd && need_reads; ++i) {
+                const int64_t wi = (int64_t)w * nInd + i;
+                const int64_t b0 = rb->wi_slot_off[wi];
+                const int n_good = rb->wi_n_good[wi];
+                if (n_good > 0) {
+                    const int r_first = rb->slot_read[b0];
+                    if (r_first < 0 || r_first >= rb->n_reads) return set_err(PLB_ERR_ARG, "slot %lld: read index out of range", (long long)b0);
+                    const int64_t rlen = rb->read_seq_off[r_first + 1] - rb->read_seq_off[r_first];
+                    const int64_t mean_cov = rlen * n_good / size;
+                    const int rate = (int)std::max<int64_t>(1, mean_cov / so->coverage_sampling_level);
+                    for (int t = 0; t < n_good; t += rate) {
+                        const int r = rb->slot_read[b0 + t];
+                        if (r < 0 || r >= rb->n_reads) return set_err(PLB_ERR_ARG, "slot %lld: read index out of range", (long long)(b0 + t));
+                        P.slot.push_back(r);
+                        P.win_cells[(size_t)k] += 16 * (rb->read_seq_off[r + 1] - rb->read_seq_off[r]);
+                    }
                 }
+                P.slot_off[(size_t)k * nInd + i + 1] = (int64_t)P.slot.size();
             }
-            P.slot_off[(size_t)k * nInd + i + 1] = (int64_t)P.slot.size();
+            for (int v = vs->win_var_off[w]; v < vs->win_var_off[w + 1]; ++v) {
+                P.pos.push_back(vs->var_pos[v]);
+                P.nrem.push_back(vs->var_n_removed[v]);
+                P.nadd.push_back(sh.nadd[(size_t)v]);
+                P.type.push_back(sh.type[(size_t)v]);
+                P.nsup.push_back(vs->var_n_support[v]);
+                P.add.insert(P.add.end(), vs->var_added + vs->var_added_off[v], vs->var_added + vs->var_added_off[v + 1]);
+                P.aoff.push_back((int64_t)P.add.size());
+            }
+            P.voff[(size_t)k + 1] = (int32_t)P.pos.size();
+            cells_total += (double)P.win_cells[(size_t)k];   // the reference-haplotype pass
         }
-        for (int v = vs->win_var_off[w]; v < vs->win_var_off[w + 1]; ++v) {
-            P.pos.push_back(vs->var_pos[v]);
-            P.nrem.push_back(vs->var_n_removed[v]);
-            P.nadd.push_back(sh.nadd[(size_t)v]);
-            P.type.push_back(sh.type[(size_t)v]);
-            P.nsup.push_back(vs->var_n_support[v]);
-            P.add.insert(P.add.end(), vs->var_added + vs->var_added_off[v], vs->var_added + vs->var_added_off[v + 1]);
-            P.aoff.push_back((int64_t)P.add.size());
+        PlbWindowBatch& hsb = P.batch;
+        hsb = *rb;   // read pool pointers stay the caller's
+        hsb.n_windows = Wf;
+        hsb.n_haps = Wf;
+        hsb.n_slots = (int64_t)P.slot.size();
+        hsb.win_hap_off = P.hoff.data();
+        hsb.win_start = P.ws.data();
+        hsb.win_end = P.we.data();
+        hsb.hap_start = P.hs.data();
+        hsb.hap_seq_off = P.hsoff.data();
+        hsb.hap_seq = P.ref.data();
+        hsb.wi_slot_off = P.slot_off.data();
+        hsb.wi_n_good = P.zero.data();
+        hsb.wi_n_bad = P.zero.data();
+        hsb.slot_read = P.slot.data();
+        hsb.max_variants = 0;
+        hsb.win_n_var = nullptr;
+        hsb.hap_var_mask = nullptr;
+        hsb.var_prior = nullptr;
+        if (need_reads) {
+            if (hsb.n_slots > 0 && (!rb->slot_read || !rb->read_seq_off || !rb->read_seq || !rb->read_qual || !rb->read_pos ||
+                                    !rb->read_end || !rb->read_mapq || !rb->read_qcfail))
+                return set_err(PLB_ERR_ARG, "NULL read array in batch");
+            if (opt && opt->calc_flank_score)
+                for (int k = 0; k < Wf; ++k)
+                    if (P.ws[(size_t)k] - P.hs[(size_t)k] <= 0)
+                        return set_err(PLB_ERR_ARG, "window %d: calc_flank_score needs a positive flank", P.filt[(size_t)k]);
         }
-        P.voff[(size_t)k + 1] = (int32_t)P.pos.size();
+        P.state.resize((size_t)Wf);
+        for (int k = 0; k < Wf; ++k) {
+            const int n = P.voff[(size_t)k + 1] - P.voff[(size_t)k];
+            SelEntryState& s = P.state[(size_t)k];
+            s.order.resize((size_t)n);
+            for (int j = 0; j < n; ++j) s.order[(size_t)j] = j;
+            const int32_t* ns = P.nsup.data() + P.voff[(size_t)k];
+            std::stable_sort(s.order.begin(), s.order.end(), [&](int a, int b) { return ns[a] > ns[b]; });
+            s.heap.reserve((size_t)orig_cap + 1);
+        }
+        P.trial_mask.resize((size_t)Wf * max_trials);
+        P.n_trials.resize((size_t)Wf);
     }
-    PlbWindowBatch& hsb = P.batch;
-    hsb = *rb;   // read pool pointers stay the caller's
-    hsb.n_windows = Wf;
-    hsb.n_haps = Wf;
-    hsb.n_slots = (int64_t)P.slot.size();
-    hsb.win_hap_off = P.hoff.data();
-    hsb.win_start = P.ws.data();
-    hsb.win_end = P.we.data();
-    hsb.hap_start = P.hs.data();
-    hsb.hap_seq_off = P.hsoff.data();
-    hsb.hap_seq = P.ref.data();
-    hsb.wi_slot_off = P.slot_off.data();
-    hsb.wi_n_good = P.zero.data();
-    hsb.wi_n_bad = P.zero.data();
-    hsb.slot_read = P.slot.data();
-    hsb.max_variants = 0;
-    hsb.win_n_var = nullptr;
-    hsb.hap_var_mask = nullptr;
-    hsb.var_prior = nullptr;
-    if (need_reads && (rc = plb_validate(&hsb, opt, 1))) return rc;
-    if ((rc = prepare(P))) return rc;
+    for (int g = 0; g < n_groups; ++g) {
+        SelPlan& P = groups[(size_t)g];
+        if ((rc = prepare(P))) return rc;
+        if (!P.r_hoff) {   // the scorer did not supply (pinned) memory for the per-round arrays
+            P.own_hoff.resize((size_t)P.Wf + 1);
+            P.own_hsoff.resize((size_t)P.Wf * max_trials + 1);
+            P.own_mask.resize((size_t)P.Wf * max_trials);
+            P.own_scores.resize((size_t)P.Wf * max_trials);
+            P.r_hoff = P.own_hoff.data();
+            P.r_hsoff = P.own_hsoff.data();
+            P.mask_c = P.own_mask.data();
+            P.scores = P.own_scores.data();
+        }
+    }
 
-    // ---- rounds
-    struct WinState {
-        std::vector<int> order;       // variants by decreasing nSupportingReads (stable), window-local indices
-        std::vector<SelEntry> heap;
-        int n_done = 0;
-    };
-    std::vector<WinState> state((size_t)Wf);
-    for (int k = 0; k < Wf; ++k) {
-        const int n = P.voff[(size_t)k + 1] - P.voff[(size_t)k];
-        WinState& s = state[(size_t)k];
-        s.order.resize((size_t)n);
-        for (int j = 0; j < n; ++j) s.order[(size_t)j] = j;
-        const int32_t* ns = P.nsup.data() + P.voff[(size_t)k];
-        std::stable_sort(s.order.begin(), s.order.end(), [&](int a, int b) { return ns[a] > ns[b]; });
-        s.heap.reserve((size_t)orig_cap + 1);
-    }
-    std::vector<int32_t> r_hoff((size_t)Wf + 1);
-    std::vector<int64_t> r_hsoff;
-    std::vector<uint64_t> trial_mask((size_t)Wf * max_trials), mask_c;
-    std::vector<double> scores;
-    double t_host = 0, n_trials_total = 0, cells_total = 0;
-    for (int k = 0; k < Wf; ++k) cells_total += (double)P.win_cells[(size_t)k];   // the reference-haplotype pass
+    double t_host = 0, n_trials_total = 0, tb_trials = 0, tb_len = 0, tb_heap = 0;
     int rounds = 0;
-    for (int r = 0; r < P.max_rounds; ++r) {
+    // host phase 1 of a group's next round: the trial haplotypes (variantFilter.pyx:452-476: {v_r}, then v_r joined to
+    // every kept set in sorted(heap) order) and their lengths.  Returns 1 when there is a round to score.
+    auto begin_round = [&](SelPlan& P) -> int {
         const double th0 = now_ms();
+        const int r = P.r;
         int Wr = 0;
-        while (Wr < Wf && P.voff[(size_t)Wr + 1] - P.voff[(size_t)Wr] > r) ++Wr;
-        if (Wr == 0) break;
-        // trial haplotypes of the round (variantFilter.pyx:452-476): {v_r}, then v_r joined to every kept set in
-        // sorted(heap) order
-        std::vector<int> n_trials((size_t)Wr);
+        if (r < P.max_rounds)
+            while (Wr < P.Wf && P.voff[(size_t)Wr + 1] - P.voff[(size_t)Wr] > r) ++Wr;
+        P.Wr = Wr;
+        if (Wr == 0) return 0;
 #pragma omp parallel for schedule(static) num_threads(host_threads()) if (Wr > 256)
         for (int k = 0; k < Wr; ++k) {
-            WinState& s = state[(size_t)k];
+            SelEntryState& s = P.state[(size_t)k];
             const int v0 = P.voff[(size_t)k];
             const SelKeys keys{P.pos.data() + v0, P.type.data() + v0, P.nrem.data() + v0};
-            uint64_t* m = trial_mask.data() + (size_t)k * max_trials;
+            uint64_t* m = P.trial_mask.data() + (size_t)k * max_trials;
             const uint64_t bit = 1ull << s.order[(size_t)r];
             int n = 0;
             m[n++] = bit;
@@ -656,27 +738,36 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
                 const uint64_t both = e.mask | bit;
                 if (sel_valid(both, keys.pos, keys.nrem, P.nadd.data() + v0)) m[n++] = both;
             }
-            n_trials[(size_t)k] = n;
+            P.n_trials[(size_t)k] = n;
         }
-        r_hoff[0] = 0;
-        for (int k = 0; k < Wr; ++k) r_hoff[(size_t)k + 1] = r_hoff[(size_t)k] + n_trials[(size_t)k];
-        const int nh = r_hoff[(size_t)Wr];
+        const double th_a = now_ms();
+        tb_trials += th_a - th0;
+        P.r_hoff[0] = 0;
+        for (int k = 0; k < Wr; ++k) P.r_hoff[(size_t)k + 1] = P.r_hoff[(size_t)k] + P.n_trials[(size_t)k];
+        const int nh = P.r_hoff[(size_t)Wr];
+        P.nh = nh;
         // the masks in haplotype order, and the sequence lengths
-        mask_c.resize((size_t)nh);
-        r_hsoff.assign((size_t)nh + 1, 0);
         int bad_shape = 0;
+        P.r_hsoff[0] = 0;
 #pragma omp parallel for schedule(static) num_threads(host_threads()) if (Wr > 256)
         for (int k = 0; k < Wr; ++k) {
             const int ws = P.ws[(size_t)k], we = P.we[(size_t)k];
             const int left = std::min(ws - P.hs[(size_t)k], ws);
             int64_t min_hap = INT64_MAX;
-            for (int j = 0; j < n_trials[(size_t)k]; ++j) {
-                const uint64_t mk = trial_mask[(size_t)k * max_trials + j];
-                mask_c[(size_t)r_hoff[(size_t)k] + j] = mk;
-                int64_t len = 0;
-                walk_haplotype(ws, we, ws - left, (int)(P.hsoff[(size_t)k + 1] - P.hsoff[(size_t)k]), mk, P.voff[(size_t)k],
-                               P.pos.data(), P.nrem.data(), P.aoff.data(), [&](int, int, int n) { len += n; });
-                r_hsoff[(size_t)r_hoff[(size_t)k] + j + 1] = len;
+            const int v0 = P.voff[(size_t)k];
+            for (int j = 0; j < P.n_trials[(size_t)k]; ++j) {
+                const uint64_t mk = P.trial_mask[(size_t)k * max_trials + j];
+                P.mask_c[(size_t)P.r_hoff[(size_t)k] + j] = mk;
+                int64_t len = fast_hap_length(mk, P.hsoff[(size_t)k + 1] - P.hsoff[(size_t)k], we, P.pos.data() + v0,
+                                              P.nrem.data() + v0, P.nadd.data() + v0);
+                if (len < 0 || check_len) {
+                    const int64_t fast = len;
+                    len = 0;
+                    walk_haplotype(ws, we, ws - left, (int)(P.hsoff[(size_t)k + 1] - P.hsoff[(size_t)k]), mk, v0, P.pos.data(),
+                                   P.nrem.data(), P.aoff.data(), [&](int, int, int n) { len += n; });
+                    if (fast >= 0 && fast != len) bad_shape = 3;   // PLB_SELECT_CHECK=1: the shortcut must agree with the walk
+                }
+                P.r_hsoff[(size_t)P.r_hoff[(size_t)k] + j + 1] = len;
                 if (len > PLB_MAX_HAP_LEN) bad_shape = 1;
                 min_hap = std::min(min_hap, len);
             }
@@ -687,57 +778,93 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
                 if (rl >= PLB_KMER && rl + 15 > min_hap) bad_shape = 2;
             }
         }
+        if (bad_shape == 3) return set_err(PLB_ERR_ARG, "internal: fast haplotype length disagrees with the walk");
         if (bad_shape)
             return set_err(PLB_ERR_SHAPE, bad_shape == 1 ? "a trial haplotype is longer than 16384 (chaplotype.pyx:180-183)"
                                                          : "a trial haplotype is shorter than readLen + 15 (calign.pyx:256-259)");
-        for (int h = 0; h < nh; ++h) r_hsoff[(size_t)h + 1] += r_hsoff[(size_t)h];
-        scores.assign((size_t)nh, 0.0);
-        t_host += now_ms() - th0;
-        const SelRound R{Wr, nh, r_hoff.data(), r_hsoff.data(), mask_c.data(), n_trials.data()};
-        if ((rc = score_round(P, R, scores.data()))) return rc;
-        n_trials_total += nh;
-        for (int k = 0; k < Wr; ++k) cells_total += (double)P.win_cells[(size_t)k] * n_trials[(size_t)k];
-        // heap updates in the reference's order (:459-486)
+        for (int h = 0; h < nh; ++h) P.r_hsoff[(size_t)h + 1] += P.r_hsoff[(size_t)h];
+        const double th_b = now_ms();
+        tb_len += th_b - th_a;
+        t_host += th_b - th0;
+        return 1;
+    };
+    // host phase 2: heap updates in the reference's order (:459-486)
+    auto end_round = [&](SelPlan& P) {
         const double th1 = now_ms();
+        const int Wr = P.Wr;
 #pragma omp parallel for schedule(static) num_threads(host_threads()) if (Wr > 256)
         for (int k = 0; k < Wr; ++k) {
-            WinState& s = state[(size_t)k];
+            SelEntryState& s = P.state[(size_t)k];
             const int v0 = P.voff[(size_t)k];
             const SelKeys keys{P.pos.data() + v0, P.type.data() + v0, P.nrem.data() + v0};
-            for (int j = 0; j < n_trials[(size_t)k]; ++j) {
-                const SelEntry e{scores[(size_t)r_hoff[(size_t)k] + j], mask_c[(size_t)r_hoff[(size_t)k] + j]};
+            for (int j = 0; j < P.n_trials[(size_t)k]; ++j) {
+                const SelEntry e{P.scores[(size_t)P.r_hoff[(size_t)k] + j], P.mask_c[(size_t)P.r_hoff[(size_t)k] + j]};
                 if ((int)s.heap.size() < orig_cap)
                     heap_push(s.heap, e, keys);
                 else
                     heap_pushpop(s.heap, e, keys);
             }
-            s.n_done += n_trials[(size_t)k];
+            s.n_done += P.n_trials[(size_t)k];
         }
-        t_host += now_ms() - th1;
-        ++rounds;
+        n_trials_total += P.nh;
+        for (int k = 0; k < Wr; ++k) cells_total += (double)P.win_cells[(size_t)k] * P.n_trials[(size_t)k];
+        ++P.r;
+        const double th2 = now_ms();
+        tb_heap += th2 - th1;
+        t_host += th2 - th1;
+    };
+    auto start = [&](SelPlan& P) -> int {   // begin the group's next round and hand it to the scorer
+        const int b = begin_round(P);
+        if (b < 0) return b;
+        P.active = b == 1;
+        if (!P.active) return PLB_OK;
+        const SelRound R{P.Wr, P.nh, P.r_hoff, P.r_hsoff, P.mask_c, P.n_trials.data()};
+        return submit(P, R);
+    };
+    for (auto& P : groups)
+        if ((rc = start(P))) return rc;
+    for (bool any = true; any;) {
+        any = false;
+        for (auto& P : groups) {
+            if (!P.active) continue;
+            if ((rc = wait(P))) return rc;
+            end_round(P);
+            if (P.gid == 0) ++rounds;
+            if ((rc = start(P))) return rc;
+            any = any || P.active;
+        }
+        for (auto& P : groups) any = any || P.active;
     }
     // ---- the best max_haplotypes - 1 sets, best first (:497-503)
-    for (int k = 0; k < Wf; ++k) {
-        const int w = filt[(size_t)k];
-        WinState& s = state[(size_t)k];
-        const int v0 = P.voff[(size_t)k];
-        const SelKeys keys{P.pos.data() + v0, P.type.data() + v0, P.nrem.data() + v0};
-        std::vector<SelEntry> fin = s.heap;
-        py_sort(fin, keys, true);
-        const int n = std::min((int)fin.size(), cap);
-        if (n > out->max_sel) return set_err(PLB_ERR_SHAPE, "window %d returns more than max_sel = %d haplotypes", w, out->max_sel);
-        for (int j = 0; j < n; ++j) {
-            out->sel_mask[(size_t)w * out->max_sel + j] = fin[(size_t)j].mask;
-            if (out->sel_score) out->sel_score[(size_t)w * out->max_sel + j] = fin[(size_t)j].score;
+    const double th2 = now_ms();
+    for (auto& P : groups) {
+        const int Wf = P.Wf;
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (Wf > 256)
+        for (int k = 0; k < Wf; ++k) {
+            const int w = P.filt[(size_t)k];
+            SelEntryState& s = P.state[(size_t)k];
+            const int v0 = P.voff[(size_t)k];
+            const SelKeys keys{P.pos.data() + v0, P.type.data() + v0, P.nrem.data() + v0};
+            std::vector<SelEntry> fin = s.heap;
+            py_sort(fin, keys, true);
+            const int n = std::min((int)fin.size(), cap);
+            for (int j = 0; j < n; ++j) {
+                out->sel_mask[(size_t)w * out->max_sel + j] = fin[(size_t)j].mask;
+                if (out->sel_score) out->sel_score[(size_t)w * out->max_sel + j] = fin[(size_t)j].score;
+            }
+            out->n_sel[w] = n;
+            if (out->n_scored) out->n_scored[w] = s.n_done;
         }
-        out->n_sel[w] = n;
-        if (out->n_scored) out->n_scored[w] = s.n_done;
     }
+    t_host += now_ms() - th2;
+    if (getenv("PLB_TRACE"))
+        fprintf(stderr, "[plb select] bookkeeping: trial sets %.2f, lengths %.2f, heap updates %.2f, final ranking %.2f ms\n", tb_trials,
+                tb_len, tb_heap, now_ms() - th2);
     g_sel_stats.v[4] = t_host;
     g_sel_stats.v[5] = rounds;
     g_sel_stats.v[6] = n_trials_total;
     g_sel_stats.v[8] = cells_total;
-    g_sel_stats.v[9] = Wf;
+    g_sel_stats.v[9] = Wf_all;
     return PLB_OK;
 }
 
@@ -747,13 +874,24 @@ extern "C" int plb_select_replay_host(const PlbWindowBatch* rb, const PlbVariant
     std::vector<int32_t> hw;
     return select_core(
         rb, vs, so, nullptr, out, false, [](SelPlan&) { return PLB_OK; },
-        [&](SelPlan& P, const SelRound& R, double* scores) -> int {
+        [&](SelPlan& P, const SelRound& R) -> int {
             hw.resize((size_t)R.nh);
             for (int k = 0; k < R.Wr; ++k)
                 for (int h = R.hap_off[k]; h < R.hap_off[k + 1]; ++h) hw[(size_t)h] = P.filt[(size_t)k];
-            const int rc = score(user, R.nh, hw.data(), R.mask, scores);
+            const int rc = score(user, R.nh, hw.data(), R.mask, P.scores);
             return rc ? set_err(PLB_ERR_ARG, "trial score callback failed (%d)", rc) : PLB_OK;
-        });
+        },
+        [](SelPlan&) { return PLB_OK; });
+}
+
+// Releases a round's batch whose work is known to be complete (no stream synchronisation: the other group's round
+// may be running).
+static void batch_release_done(PlbContext* c, PlbDeviceBatch* b) {
+    if (!b) return;
+    for (auto& ch : b->chunks) block_put(c, ch.tiles_blk);
+    if (b->mode_blk.p) block_put(c, b->mode_blk);
+    block_put(c, b->blk);
+    delete b;
 }
 
 extern "C" int plb_select_haplotypes_host(PlbContext* c, const PlbWindowBatch* rb, const PlbVariantSet* vs,
@@ -765,26 +903,33 @@ extern "C" int plb_select_haplotypes_host(PlbContext* c, const PlbWindowBatch* r
     opt.use_mapq_cap = 0;   // alignSingleRead(read, False), variantFilter.pyx:274-275
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
-    PlbDeviceBatch* base = nullptr;   // reference haplotypes + reads / slots, resident for all rounds
-    PlbDeviceBatch* rd = nullptr;     // the current round's batch
-    Block VB{nullptr, 0};
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    double* d_llref = nullptr;
-    uint64_t* d_mask = nullptr;
-    double* d_score = nullptr;
-    SelVars sv{};
+    struct GroupDev {   // device side of one group
+        PlbDeviceBatch* base = nullptr;   // reference haplotypes + reads / slots, resident for all rounds
+        PlbDeviceBatch* rd = nullptr;     // the round in flight
+        Block VB{nullptr, 0};
+        cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        double* d_llref = nullptr;
+        uint64_t* d_mask = nullptr;
+        double* d_score = nullptr;
+        SelVars sv{};
+    };
+    GroupDev gd[2];
     const bool modes = opt.calc_flank_score != 0;
-    double t_build = 0, t_score = 0, t_reduce = 0, n_pairs_total = 0;
+    double t_build = 0, t_score = 0, t_reduce = 0, t_refpass = 0, n_pairs_total = 0;
+    double tr_prepare = 0, tr_setup = 0, tr_plan = 0, tr_wait = 0;   // PLB_TRACE: host milliseconds by phase
+    bool arena_reset = false;
     auto cleanup = [&]() {
         cudaStreamSynchronize(st);
-        if (rd) plb_batch_free(c, rd);
-        if (base) plb_batch_free(c, base);
-        rd = base = nullptr;
-        if (VB.p) block_put(c, VB);
-        VB.p = nullptr;
-        for (auto& e : ev) {
-            if (e) cudaEventDestroy(e);
-            e = nullptr;
+        for (auto& G : gd) {
+            if (G.rd) plb_batch_free(c, G.rd);
+            if (G.base) plb_batch_free(c, G.base);
+            G.rd = G.base = nullptr;
+            if (G.VB.p) block_put(c, G.VB);
+            G.VB.p = nullptr;
+            for (auto& e : G.ev) {
+                if (e) cudaEventDestroy(e);
+                e = nullptr;
+            }
         }
     };
 #define SEL_TRY(expr)        \
@@ -798,44 +943,58 @@ extern "C" int plb_select_haplotypes_host(PlbContext* c, const PlbWindowBatch* r
         if (e_ != cudaSuccess)                                                                                        \
             return set_err(PLB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
-    // reference-haplotype pass: uploads reads / slots once and leaves ll_ref[slot] on the device
+    // reference-haplotype pass of a group: uploads its reads / slots once and leaves ll_ref[slot] on the device
     auto prepare = [&](SelPlan& P) -> int {
+        const double tp0 = now_ms();
+        GroupDev& G = gd[P.gid];
         const int Wf = P.Wf, nvar = (int)P.pos.size();
-        SEL_TRY(prepare_batch(c, &P.batch, &base));
+        // the second group keeps the pinned arena of the first (prepare_batch resets it unless the batch shares)
+        SEL_TRY(prepare_batch(c, &P.batch, &G.base, nullptr, !arena_reset));
+        arena_reset = true;
         Layout L;
         const size_t o_llref = L.take((size_t)P.batch.n_slots * 8 + 64), o_voff = L.take((size_t)(Wf + 1) * 4),
                      o_vpos = L.take((size_t)nvar * 4), o_vnr = L.take((size_t)nvar * 4),
                      o_vaoff = L.take((size_t)(nvar + 1) * 8), o_vadd = L.take(P.add.size() + 64),
                      o_mask = L.take((size_t)Wf * P.max_trials * 8), o_score = L.take((size_t)Wf * P.max_trials * 8);
-        SEL_TRY(block_get(c, L.off + 256, &VB));
-        for (auto& e : ev) SEL_CU(cudaEventCreate(&e));
-        d_llref = at<double>(VB, o_llref);
-        d_mask = at<uint64_t>(VB, o_mask);
-        d_score = at<double>(VB, o_score);
-        SEL_CU(cudaMemcpyAsync(at<uint8_t>(VB, o_voff), P.voff.data(), (size_t)(Wf + 1) * 4, cudaMemcpyHostToDevice, st));
+        SEL_TRY(block_get(c, L.off + 256, &G.VB));
+        for (auto& e : G.ev) SEL_CU(cudaEventCreate(&e));
+        G.d_llref = at<double>(G.VB, o_llref);
+        G.d_mask = at<uint64_t>(G.VB, o_mask);
+        G.d_score = at<double>(G.VB, o_score);
+        // per-round host arrays in pinned memory: the copies must not block the host while the other group runs
+        const size_t nt = (size_t)Wf * P.max_trials;
+        P.r_hoff = (int32_t*)pin_alloc(c, ((size_t)Wf + 1) * 4);
+        P.r_hsoff = (int64_t*)pin_alloc(c, (nt + 1) * 8);
+        P.mask_c = (uint64_t*)pin_alloc(c, nt * 8);
+        P.scores = (double*)pin_alloc(c, nt * 8);
+        if (!P.r_hoff || !P.r_hsoff || !P.mask_c || !P.scores) return set_err(PLB_ERR_NOMEM, "pinned host allocation failed");
+        SEL_CU(cudaMemcpyAsync(at<uint8_t>(G.VB, o_voff), P.voff.data(), (size_t)(Wf + 1) * 4, cudaMemcpyHostToDevice, st));
         if (nvar) {
-            SEL_CU(cudaMemcpyAsync(at<uint8_t>(VB, o_vpos), P.pos.data(), (size_t)nvar * 4, cudaMemcpyHostToDevice, st));
-            SEL_CU(cudaMemcpyAsync(at<uint8_t>(VB, o_vnr), P.nrem.data(), (size_t)nvar * 4, cudaMemcpyHostToDevice, st));
+            SEL_CU(cudaMemcpyAsync(at<uint8_t>(G.VB, o_vpos), P.pos.data(), (size_t)nvar * 4, cudaMemcpyHostToDevice, st));
+            SEL_CU(cudaMemcpyAsync(at<uint8_t>(G.VB, o_vnr), P.nrem.data(), (size_t)nvar * 4, cudaMemcpyHostToDevice, st));
             if (!P.add.empty())
-                SEL_CU(cudaMemcpyAsync(at<uint8_t>(VB, o_vadd), P.add.data(), P.add.size(), cudaMemcpyHostToDevice, st));
+                SEL_CU(cudaMemcpyAsync(at<uint8_t>(G.VB, o_vadd), P.add.data(), P.add.size(), cudaMemcpyHostToDevice, st));
         }
-        SEL_CU(cudaMemcpyAsync(at<uint8_t>(VB, o_vaoff), P.aoff.data(), (size_t)(nvar + 1) * 8, cudaMemcpyHostToDevice, st));
-        sv = SelVars{at<int32_t>(VB, o_voff), at<int32_t>(VB, o_vpos), at<int32_t>(VB, o_vnr), at<int64_t>(VB, o_vaoff),
-                     at<uint8_t>(VB, o_vadd)};
-        SEL_CU(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), st));
-        SEL_TRY(copy_seq_for_windows(c, base, &P.batch, 0, Wf, st));
-        SEL_TRY(plan_chunk(c, base, &P.batch, 0, Wf, st));
-        SEL_TRY(derive_all(c, base, st));
-        if (modes) SEL_TRY(mode_queues(c, base, false));
-        PlbLoglikOut llo{nullptr, d_llref, nullptr};
-        SEL_CU(cudaEventRecord(ev[0], st));
-        SEL_TRY(launch_windows(c, base, base->chunks[0], &opt, nullptr, &llo, st, false, modes ? base->mq : base->q));
-        SEL_CU(cudaEventRecord(ev[1], st));
-        n_pairs_total += (double)base->d.n_pairs;
+        SEL_CU(cudaMemcpyAsync(at<uint8_t>(G.VB, o_vaoff), P.aoff.data(), (size_t)(nvar + 1) * 8, cudaMemcpyHostToDevice, st));
+        G.sv = SelVars{at<int32_t>(G.VB, o_voff), at<int32_t>(G.VB, o_vpos), at<int32_t>(G.VB, o_vnr), at<int64_t>(G.VB, o_vaoff),
+                       at<uint8_t>(G.VB, o_vadd)};
+        if (P.gid == 0) SEL_CU(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), st));
+        SEL_TRY(copy_seq_for_windows(c, G.base, &P.batch, 0, Wf, st));
+        SEL_TRY(plan_chunk(c, G.base, &P.batch, 0, Wf, st));
+        SEL_TRY(derive_all(c, G.base, st));
+        if (modes) SEL_TRY(mode_queues(c, G.base, false));
+        PlbLoglikOut llo{nullptr, G.d_llref, nullptr};
+        SEL_CU(cudaEventRecord(G.ev[0], st));
+        SEL_TRY(launch_windows(c, G.base, G.base->chunks[0], &opt, nullptr, &llo, st, false, modes ? G.base->mq : G.base->q));
+        SEL_CU(cudaEventRecord(G.ev[1], st));
+        n_pairs_total += (double)G.base->d.n_pairs;
+        tr_prepare += now_ms() - tp0;
         return PLB_OK;
     };
-    // one round on the device: build the trial haplotypes, score every sampled read against them, reduce
-    auto score_round = [&](SelPlan& P, const SelRound& R, double* scores) -> int {
+    // one round of a group on the device: build the trial haplotypes, score every sampled read against them, reduce,
+    // send the scores back; asynchronous - `wait` below completes it
+    auto submit = [&](SelPlan& P, const SelRound& R) -> int {
+        GroupDev& G = gd[P.gid];
         PlbWindowBatch hr = P.batch;
         hr.n_windows = R.Wr;
         hr.n_haps = R.nh;
@@ -843,49 +1002,66 @@ extern "C" int plb_select_haplotypes_host(PlbContext* c, const PlbWindowBatch* r
         hr.win_hap_off = R.hap_off;
         hr.hap_seq_off = R.hap_seq_off;
         hr.hap_seq = nullptr;   // built on the device
-        SEL_TRY(prepare_batch(c, &hr, &rd, base));
-        SEL_TRY(copy_meta(c, rd, &hr, 0, R.Wr, 0, -1, st));
-        SEL_CU(cudaMemcpyAsync(d_mask, R.mask, (size_t)R.nh * 8, cudaMemcpyHostToDevice, st));
-        SEL_TRY(plan_chunk(c, rd, &hr, 0, R.Wr, st));
-        SEL_TRY(derive_all(c, rd, st));
-        if (modes) SEL_TRY(mode_queues(c, rd, false));
-        SEL_CU(cudaEventRecord(ev[2], st));
+        const double ts0 = now_ms();
+        SEL_TRY(prepare_batch(c, &hr, &G.rd, G.base));
+        SEL_TRY(copy_meta(c, G.rd, &hr, 0, R.Wr, 0, -1, st));
+        SEL_CU(cudaMemcpyAsync(G.d_mask, R.mask, (size_t)R.nh * 8, cudaMemcpyHostToDevice, st));
+        const double ts1 = now_ms();
+        SEL_TRY(plan_chunk(c, G.rd, &hr, 0, R.Wr, st));
+        const double ts2 = now_ms();
+        tr_setup += ts1 - ts0;
+        tr_plan += ts2 - ts1;
+        SEL_TRY(derive_all(c, G.rd, st));
+        if (modes) SEL_TRY(mode_queues(c, G.rd, false));
+        SEL_CU(cudaEventRecord(G.ev[2], st));
         const int grid = std::max(1, std::min((R.nh + kBuildWarps - 1) / kBuildWarps, c->n_sm * 16));
-        k_build_haps<<<grid, 32 * kBuildWarps, 0, st>>>(R.nh, rd->d.hap_win, d_mask, base->d.hap_seq_off, base->d.hap_seq,
-                                                       rd->d.win_start, rd->d.win_end, rd->d.hap_start, sv, rd->d.hap_seq_off,
-                                                       (uint8_t*)rd->d.hap_seq);
+        k_build_haps<<<grid, 32 * kBuildWarps, 0, st>>>(R.nh, G.rd->d.hap_win, G.d_mask, G.base->d.hap_seq_off, G.base->d.hap_seq,
+                                                       G.rd->d.win_start, G.rd->d.win_end, G.rd->d.hap_start, G.sv,
+                                                       G.rd->d.hap_seq_off, (uint8_t*)G.rd->d.hap_seq);
         SEL_TRY(launch_check(c, "k_build_haps"));
-        SEL_CU(cudaEventRecord(ev[3], st));
-        SEL_TRY(launch_windows(c, rd, rd->chunks[0], &opt, nullptr, nullptr, st, false, modes ? rd->mq : rd->q));
-        SEL_CU(cudaEventRecord(ev[4], st));
-        k_trial_score<<<(R.nh + 3) / 4, 128, 0, st>>>(rd->d, rd->ll_scratch, d_llref, R.nh, d_score);
+        SEL_CU(cudaEventRecord(G.ev[3], st));
+        SEL_TRY(launch_windows(c, G.rd, G.rd->chunks[0], &opt, nullptr, nullptr, st, c->timing, modes ? G.rd->mq : G.rd->q));
+        SEL_CU(cudaEventRecord(G.ev[4], st));
+        k_trial_score<<<(R.nh + 3) / 4, 128, 0, st>>>(G.rd->d, G.rd->ll_scratch, G.d_llref, R.nh, G.d_score);
         SEL_TRY(launch_check(c, "k_trial_score"));
-        SEL_CU(cudaEventRecord(ev[5], st));
-        SEL_CU(cudaMemcpyAsync(scores, d_score, (size_t)R.nh * 8, cudaMemcpyDeviceToHost, st));
-        SEL_CU(cudaStreamSynchronize(st));
+        SEL_CU(cudaEventRecord(G.ev[5], st));
+        SEL_CU(cudaMemcpyAsync(P.scores, G.d_score, (size_t)R.nh * 8, cudaMemcpyDeviceToHost, st));
+        SEL_CU(cudaEventRecord(G.ev[6], st));
+        tr_wait += now_ms() - ts2;
+        return PLB_OK;
+    };
+    auto wait = [&](SelPlan& P) -> int {
+        GroupDev& G = gd[P.gid];
+        const double tw0 = now_ms();
+        SEL_CU(cudaEventSynchronize(G.ev[6]));
         float ms = 0;
-        cudaEventElapsedTime(&ms, ev[2], ev[3]);
+        cudaEventElapsedTime(&ms, G.ev[2], G.ev[3]);
         t_build += ms;
-        cudaEventElapsedTime(&ms, ev[3], ev[4]);
+        cudaEventElapsedTime(&ms, G.ev[3], G.ev[4]);
         t_score += ms;
-        cudaEventElapsedTime(&ms, ev[4], ev[5]);
+        cudaEventElapsedTime(&ms, G.ev[4], G.ev[5]);
         t_reduce += ms;
-        n_pairs_total += (double)rd->d.n_pairs;
-        plb_batch_free(c, rd);
-        rd = nullptr;
+        if (P.r == 0) {
+            cudaEventElapsedTime(&ms, G.ev[0], G.ev[1]);
+            t_refpass += ms;
+        }
+        n_pairs_total += (double)G.rd->d.n_pairs;
+        batch_release_done(c, G.rd);
+        G.rd = nullptr;
+        tr_wait += now_ms() - tw0;
         return PLB_OK;
     };
 #undef SEL_TRY
 #undef SEL_CU
-    rc = select_core(rb, vs, so, &opt, out, true, prepare, score_round);
-    float ms_ref = 0;
-    if (rc == PLB_OK && ev[1]) {
-        cudaStreamSynchronize(st);
-        cudaEventElapsedTime(&ms_ref, ev[0], ev[1]);
-    }
+    static const bool trace = getenv("PLB_TRACE") != nullptr;
+    const double t_call0 = now_ms();
+    rc = select_core(rb, vs, so, &opt, out, true, prepare, submit, wait);
+    if (trace)
+        fprintf(stderr, "[plb select] total %.2f ms: prepare %.2f | rounds: batch setup %.2f, plan %.2f, launch+wait %.2f | host bookkeeping %.2f\n",
+                now_ms() - t_call0, tr_prepare, tr_setup, tr_plan, tr_wait, g_sel_stats.v[4]);
     cleanup();
     if (rc) return rc;
-    g_sel_stats.v[0] = ms_ref;
+    g_sel_stats.v[0] = t_refpass;
     g_sel_stats.v[1] = t_build;
     g_sel_stats.v[2] = t_score;
     g_sel_stats.v[3] = t_reduce;

@@ -153,3 +153,28 @@ def test_n1_selection_rejects_bad_variant_lists(golden_dir):
     for bad in ([vs[1], vs[0]] + vs[2:], vs + [vs[-1]], [(c["win_end"] + 5, b"A", b"C", 1)]):
         with pytest.raises(PlbError):
             Engine.select_replay(batch, VariantSet.from_lists([bad]), lambda w, m: [0.0] * len(w), lib=lib)
+
+
+def test_n1_two_group_pipeline_matches_single_group(monkeypatch):
+    """Large batches run as two groups of windows whose rounds alternate (host bookkeeping of one overlaps the scoring
+    of the other); the result must not depend on the grouping.  Replay with a deterministic, tie-rich score."""
+    from platypus_b200.engine import Engine
+    lib = _lib()
+    b1, v1 = synth.make_select_batch(40, n_vars=8, n_reads=8)
+    b2, v2 = synth.make_select_batch(30, n_vars=6, n_reads=8, window_offset=40)
+
+    def score(hw, hm):
+        return -((hm * np.uint64(2654435761) + hw.astype(np.uint64) * np.uint64(97)) % np.uint64(23)).astype(np.float64)
+    sel = _abi.PlbSelectOptions.default(max_haplotypes=12, original_max_haplotypes=14)
+    outs = []
+    for b, v in ((b1, v1), (b2, v2)):
+        res = []
+        for groups in ("1", "2"):
+            monkeypatch.setenv("PLB_SELECT_GROUPS", groups)
+            monkeypatch.setenv("PLB_SELECT_CHECK", "1")
+            res.append(Engine.select_replay(b, v, score, sel, lib=lib))
+        for k in ("n_sel", "sel_mask", "n_scored"):
+            assert np.array_equal(res[0][k], res[1][k]), k
+        assert np.array_equal(np.nan_to_num(res[0]["sel_score"]), np.nan_to_num(res[1]["sel_score"]))
+        assert np.all(res[0]["n_sel"] == 11)
+        outs.append(res[0])
