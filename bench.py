@@ -259,6 +259,191 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ---- --stage select: the haplotype selection loop, the step before the window model ----------------
+
+SEL_VARS = 8
+_SEL_ARGS = None
+
+
+def select_config(windows):
+    return {"workload": "synth-select-v1: %d windows x %d candidate variants x %d reads, %d bp reads x %d bp reference segment; "
+                        "default options (maxHaplotypes 50, coverageSamplingLevel 30): 163 trial haplotypes per window in 8 "
+                        "rounds, every 6th read sampled" % (windows, SEL_VARS, N_READS, READ_LEN, HAP_LEN),
+            "stage": "select (getFilteredHaplotypes; not the headline)", "windows_per_gpu": windows, "n_gpus": 1,
+            "cells_per_pair": "16*readLen per (sampled read, trial haplotype) pair + one reference-haplotype pass",
+            "l2": "per-round working set (reads + trial haplotypes + LL) exceeds the 126 MB L2; no explicit flush"}
+
+
+def _select_window_args(batch, vset, n_windows):
+    """Windows of the select workload as the arguments of l3_ref_wrap.select_haplotypes (coordinates moved next to the
+    origin; the reference segment becomes the in-memory genome)."""
+    out = []
+    for w in range(min(n_windows, batch.n_windows)):
+        hs = int(batch.hap_start[w])
+        shift = hs - 8
+        ref = batch.hap_seq[batch.hap_seq_off[w]:batch.hap_seq_off[w + 1]].tobytes()
+        genome = b"N" * 8 + ref + b"N"
+        vs = []
+        for i in range(int(vset.win_var_off[w]), int(vset.win_var_off[w + 1])):
+            p, nr = int(vset.var_pos[i]) - shift, int(vset.var_n_removed[i])
+            add = vset.var_added[int(vset.var_added_off[i]):int(vset.var_added_off[i + 1])].tobytes()
+            rem = genome[p:p + nr] if len(add) == nr else genome[p + 1:p + 1 + nr]
+            vs.append((p, rem, add, int(vset.var_n_support[i])))
+        per_ind = []
+        for i in range(batch.n_individuals):
+            wi = w * batch.n_individuals + i
+            s0 = int(batch.wi_slot_off[wi])
+            reads = []
+            for s_ in range(s0, s0 + int(batch.wi_n_good[wi])):
+                r = int(batch.slot_read[s_])
+                o0, o1 = int(batch.read_seq_off[r]), int(batch.read_seq_off[r + 1])
+                reads.append((batch.read_seq[o0:o1].tobytes(), batch.read_qual[o0:o1].tobytes(), int(batch.read_pos[r]) - shift,
+                              int(batch.read_end[r]) - shift, int(batch.read_mapq[r]), 0))
+            per_ind.append(reads)
+        flank = int(batch.win_start[w]) - hs
+        out.append((genome, int(batch.win_start[w]) - shift, int(batch.win_end[w]) - shift, vs, per_ind, flank // 2))
+    return out
+
+
+def _sel_worker(span):
+    from oracle import oracle as O
+    W = O.ref_l3()
+    n = 0
+    for w in range(span[0], span[1]):
+        n += len(W.select_haplotypes(*_SEL_ARGS[w])["selected"])
+    return n
+
+
+def select_reference_run(batch, vset, n_windows, procs, steps=1, warmup=0):
+    """The reference's own getFilteredHaplotypes / computeBestScoreForGenotype / Haplotype classes (oracle/_ref/n1_ref +
+    l3_ref_wrap) over the first n_windows windows, one process per core.  Returns (seconds per step, windows) or None."""
+    global _SEL_ARGS
+    import multiprocessing as mp
+    from oracle import oracle as O
+    if O.ref_l3() is None or not hasattr(O.ref_l3(), "select_haplotypes"):
+        return None
+    _SEL_ARGS = _select_window_args(batch, vset, n_windows)
+    nw = len(_SEL_ARGS)
+    procs = max(1, min(procs, nw))
+    spans = [(nw * i // (procs * 4), nw * (i + 1) // (procs * 4)) for i in range(procs * 4)]
+    spans = [sp for sp in spans if sp[1] > sp[0]]
+    with mp.get_context("fork").Pool(procs) as pool:
+        pool.map(_sel_worker, [(i, i + 1) for i in range(min(nw, procs))])
+        for _ in range(warmup):
+            pool.map(_sel_worker, spans)
+        t0 = time.perf_counter()
+        for _ in range(max(1, steps)):
+            pool.map(_sel_worker, spans)
+        dt = (time.perf_counter() - t0) / max(1, steps)
+    return dt, nw
+
+
+def run_select(args):
+    """bench.py --stage select: plb_select_haplotypes_host on the synth-select-v1 workload (one GPU)."""
+    import torch
+    from platypus_b200 import synth
+    from platypus_b200.engine import Engine
+    W = args.windows
+    batch, vset = synth.make_select_batch_parallel(W, n_vars=SEL_VARS, n_reads=N_READS, read_len=READ_LEN, hap_len=HAP_LEN)
+    if args.impl == "reference":
+        cores = args.cpu_procs or (os.cpu_count() or 1)
+        nw = args.cpu_windows or min(W, 40 * cores)
+        r = select_reference_run(batch, vset, nw, cores, steps=args.steps, warmup=min(args.warmup, 1))
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/n1_ref (the reference's selection loop) is not built"}))
+            return
+        dt, nw = r
+        cells = SEL_CELLS_PER_WINDOW * nw
+        g = cells / dt / 1e9
+        sample = ("first %d windows per step; the reference's own getFilteredHaplotypes / computeBestScoreForGenotype / Haplotype "
+                  "classes (variantFilter.pyx, chaplotype.pyx, calign.pyx, align.c; oracle/_ref), %d processes; cells counted as for "
+                  "the GPU arm (the reference re-scores the reference haplotype for every trial: not credited)" % (nw, cores))
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": g, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "int16 scores / f64 likelihoods", "data": "synthetic (synth-select-v1)",
+                          "config": select_config(W), "windows_per_s": nw / dt,
+                          "cpu_baseline": {"value": g, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+                          "e2e": {"value": g, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}),
+              flush=True)
+        return
+    keep = []
+    for name in ("hap_seq", "read_seq", "read_qual", "read_pos", "read_end", "read_mapq", "read_qcfail", "read_seq_off",
+                 "slot_read", "wi_slot_off", "wi_n_good", "hap_seq_off", "win_start", "win_end", "hap_start"):
+        t = torch.from_numpy(np.ascontiguousarray(getattr(batch, name))).pin_memory()
+        keep.append(t)
+        setattr(batch, name, t.numpy())
+    torch.cuda.set_device(0)
+    eng = Engine(0)
+    eng.set_timing(True)
+    out = None
+    for _ in range(max(3, args.warmup)):
+        out = eng.select_haplotypes(batch, vset, max_sel=64, out=out)
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = eng.launch_count
+    eng.set_timing(True)
+    wall, dev = [], []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        out = eng.select_haplotypes(batch, vset, max_sel=64, out=out)
+        wall.append(time.perf_counter() - t0)
+        st = eng.select_stats()
+        dev.append((st["ref_pass_ms"] + st["build_ms"] + st["score_ms"] + st["reduce_ms"]) * 1e-3)
+    launches = eng.launch_count - l0
+    clocks = sampler.stop()
+    kt, n_runs = eng.kernel_times()
+    st = eng.select_stats()
+    cells = st["cells"]
+    t_wall, t_dev = sum(wall) / len(wall), sum(dev) / len(dev)
+    assert abs(cells / W - SEL_CELLS_PER_WINDOW) < 1e-6 * SEL_CELLS_PER_WINDOW, (cells / W, SEL_CELLS_PER_WINDOW)
+    # algorithmic bytes of the scoring rounds (SURVEY 8d layout): per pair-producing launch the sampled reads, the trial
+    # haplotypes and one f64 log-likelihood per pair
+    reads_per_w = st["n_pairs"] / (st["n_trials"] + W)           # sampled reads per window
+    rd_bytes = (READ_LEN + 3) // 4 + READ_LEN + 8
+    alg_bytes = (st["rounds"] + 1) * W * reads_per_w * rd_bytes + (st["n_trials"] + W) * ((HAP_LEN + 3) // 4 + 8) + 8 * st["n_pairs"]
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
+    if os.path.exists(peaks_path):
+        try:
+            peak = float(json.load(open(peaks_path))["hbm_gbs"])
+            peak_src = "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+    dp_ms_total = kt["k_dp"] * n_runs / max(1, args.steps)       # k_dp time per step (all rounds)
+    ach = alg_bytes / (dp_ms_total * 1e-3) / 1e9 if dp_ms_total > 0 else None
+    line = {
+        "metric": METRIC, "value": cells / t_dev / 1e9, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": t_dev * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16 scores / f64 likelihoods", "data": "synthetic (synth-select-v1)", "config": select_config(W),
+        "value_definition": "cells / GPU-busy time of a call (reference pass + haplotype construction + scoring kernels + score "
+                            "reduction, CUDA events); reads are uploaded once per call, the rounds run from HBM",
+        "e2e": {"value": cells / t_wall / 1e9, "unit": UNIT, "ms_per_step": t_wall * 1e3, "ms_each_step": [x * 1e3 for x in wall],
+                "h2d_bytes_per_step": int(batch.input_nbytes()), "d2h_bytes_per_step": int(8 * st["n_trials"]),
+                "windows_per_s": W / t_wall,
+                "api": "plb_select_haplotypes_host (pinned host buffers in, variant masks + scores out, all rounds inside)"},
+        "select_stats": st, "kernel_ms_mean_per_launch": kt,
+        "roofline": {"bound": "hbm", "kernel": "k_dp (all rounds of a step)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak if ach else None, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": dp_ms_total,
+                     "note": "integer-issue bound like the headline path (DESIGN.md 4)"},
+        "gpu_launches": launches, "clocks": clocks,
+        "check": {"n_sel_min": int(out["n_sel"].min()), "n_sel_max": int(out["n_sel"].max()), "n_scored": int(out["n_scored"][0])},
+    }
+    cores = os.cpu_count() or 1
+    r = select_reference_run(batch, vset, min(W, 40 * cores), cores, steps=1, warmup=0) if not args.no_cpu else None
+    if r is not None:
+        dt, nw = r
+        line["cpu_baseline"] = {"value": SEL_CELLS_PER_WINDOW * nw / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
+                                "windows_per_s": nw / dt,
+                                "sample": "first %d windows, the reference's own getFilteredHaplotypes (oracle/_ref/n1_ref), %d processes" % (nw, cores)}
+    print(json.dumps(line), flush=True)
+
+
+# cells per window of synth-select-v1 with the default options: 163 trial haplotypes + the reference haplotype, 11 sampled
+# reads (every 6th of 64) of 150 bp, 16 cells per base
+SEL_CELLS_PER_WINDOW = 164 * 11 * 16 * 150
+
+
 def pin(a):
     import torch
     if a is None:
@@ -446,7 +631,14 @@ def main():
                     help="run-time mode of the path: --calculateFlankScore=1 / --HLATyping=1 (not the headline)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3],
                     help="2 = BASELINE config 2 (headline); 3 = ragged read/haplotype lengths (profiling only)")
+    ap.add_argument("--stage", default="path", choices=["path", "select"],
+                    help="path = the headline likelihood path; select = the haplotype selection loop before it (N1, one GPU)")
+    ap.add_argument("--no-cpu", action="store_true", help="--stage select: skip the CPU baseline leg")
     args = ap.parse_args()
+    if args.stage == "select":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_select(args)
+        return
     global RAGGED, OPT, MODE
     RAGGED = args.config == 3
     MODE = args.mode

@@ -273,7 +273,7 @@ class Engine:
                                                             _abi.ptr(hap_mask), _abi.ptr(off), _abi.ptr(seq), int(off[-1])))
         return [seq[int(off[k]):int(off[k + 1])].tobytes() for k in range(n)]
 
-    def select_haplotypes(self, ref_batch: WindowBatch, variants, sel=None, opt=None, max_sel=None):
+    def select_haplotypes(self, ref_batch: WindowBatch, variants, sel=None, opt=None, max_sel=None, out=None):
         """getFilteredHaplotypes for every window of a batch (reference: src/cython/variantFilter.pyx:377-506,
         237-283).  ref_batch: ONE haplotype per window (the reference haplotype) + the good reads per individual;
         variants: batch.VariantSet.  Returns dict: n_sel [W], sel_mask [W][max_sel] (bit v = window variant v),
@@ -284,8 +284,9 @@ class Engine:
         if max_sel is None:
             nv = int(np.max(np.diff(variants.win_var_off))) if W else 0
             max_sel = max(1, sel.max_haplotypes - 1, sel.original_max_haplotypes - 1, min(2 ** min(nv, 20) - 1, 1 << 16))
-        arrs = {"max_sel": max_sel, "n_sel": np.zeros(W, np.int32), "sel_mask": np.zeros((W, max_sel), np.uint64),
-                "sel_score": np.full((W, max_sel), np.nan), "n_scored": np.zeros(W, np.int32)}
+        arrs = out if out is not None and out["max_sel"] == max_sel else {
+            "max_sel": max_sel, "n_sel": np.zeros(W, np.int32), "sel_mask": np.zeros((W, max_sel), np.uint64),
+            "sel_score": np.full((W, max_sel), np.nan), "n_scored": np.zeros(W, np.int32)}
         o = _abi.PlbSelectOut(max_sel, _abi.ptr(arrs["n_sel"]), _abi.ptr(arrs["sel_mask"]), _abi.ptr(arrs["sel_score"]),
                               _abi.ptr(arrs["n_scored"]))
         s, v = ref_batch.as_struct(), variants.as_struct()
