@@ -400,7 +400,7 @@ def run_select(args):
     # haplotypes and one f64 log-likelihood per pair
     reads_per_w = st["n_pairs"] / (st["n_trials"] + W)           # sampled reads per window
     rd_bytes = (READ_LEN + 3) // 4 + READ_LEN + 8
-    alg_bytes = (st["rounds"] + 1) * W * reads_per_w * rd_bytes + (st["n_trials"] + W) * ((HAP_LEN + 3) // 4 + 8) + 8 * st["n_pairs"]
+    alg_bytes = (SEL_VARS + 1) * W * reads_per_w * rd_bytes + (st["n_trials"] + W) * ((HAP_LEN + 3) // 4 + 8) + 8 * st["n_pairs"]
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
     if os.path.exists(peaks_path):
@@ -409,7 +409,7 @@ def run_select(args):
             peak_src = "MEASURED_PEAKS.json hbm_gbs"
         except Exception:
             pass
-    dp_ms_total = kt["k_dp"] * n_runs / max(1, args.steps)       # k_dp time per step (all rounds)
+    dp_ms_total = kt["k_dp"] * st["rounds"]                      # k_dp time per step: mean launch x round launches of a step
     ach = alg_bytes / (dp_ms_total * 1e-3) / 1e9 if dp_ms_total > 0 else None
     line = {
         "metric": METRIC, "value": cells / t_dev / 1e9, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),

@@ -388,7 +388,7 @@ int plb_select_replay_host(const PlbWindowBatch* ref_batch, const PlbVariantSet*
 
 /* Device milliseconds of the last plb_select_haplotypes_host on this context, by stage: [0] reference-haplotype
  * pass, [1] haplotype construction, [2] scoring kernels (k_prep..k_dp), [3] score reduction; [4] = host
- * milliseconds in the heap replay and round planning, [5] = rounds, [6] = trial haplotypes scored,
+ * milliseconds in the heap replay and round planning, [5] = round launches (rounds summed over the window groups), [6] = trial haplotypes scored,
  * [7] = (read, haplotype) pairs scored, [8] = algorithmic cells (16 * readLen per pair), [9] = windows that took
  * the scoring rounds.  Writes min(n, 10) values. */
 int plb_select_stats(PlbContext* ctx, double* out, int n);

@@ -829,7 +829,7 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
             if (!P.active) continue;
             if ((rc = wait(P))) return rc;
             end_round(P);
-            if (P.gid == 0) ++rounds;
+            ++rounds;   // group-rounds: one launch sequence each
             if ((rc = start(P))) return rc;
             any = any || P.active;
         }
