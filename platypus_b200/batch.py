@@ -393,6 +393,15 @@ class VariantSet:
     def n_vars(self, w):
         return int(self.win_var_off[w + 1] - self.win_var_off[w])
 
+    def slice_windows(self, lo: int, hi: int) -> "VariantSet":
+        """The variants of windows [lo, hi) (offsets rebased)."""
+        v0, v1 = int(self.win_var_off[lo]), int(self.win_var_off[hi])
+        a0, a1 = int(self.var_added_off[v0]), int(self.var_added_off[v1])
+        return VariantSet((self.win_var_off[lo:hi + 1] - v0).astype(np.int32), self.var_pos[v0:v1].copy(),
+                          self.var_n_removed[v0:v1].copy(), self.var_n_support[v0:v1].copy(),
+                          (self.var_added_off[v0:v1 + 1] - a0).astype(np.int64),
+                          np.concatenate([self.var_added[a0:a1], np.zeros(1, np.uint8)]))
+
     def as_struct(self):
         s = _abi.PlbVariantSet()
         for k in ("win_var_off", "var_pos", "var_n_removed", "var_n_support", "var_added_off", "var_added"):

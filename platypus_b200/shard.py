@@ -57,3 +57,38 @@ def run_sharded(batch: WindowBatch, compute: Callable[[WindowBatch], Dict[str, n
             loc = torch.zeros((0,) + tail, dtype=torch.float64, device=device)
         out[k] = gather_blocks(loc, counts).cpu().numpy()
     return out
+
+
+def run_select_sharded(ref_batch: WindowBatch, variants, compute, device: str = "cpu") -> Dict[str, np.ndarray]:
+    """The haplotype selection loop over the ranks: windows are independent here too
+    (getFilteredHaplotypes sees one window's variants and reads), so every rank runs `compute(ref_shard, variant_shard)`
+    -> {"n_sel", "sel_mask", "sel_score", "n_scored"} on its contiguous block of windows and the per-window results are
+    all-gathered in window order (masks travel as int64 bit patterns)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    bounds = shard_bounds(ref_batch.n_windows, world)
+    counts = [bounds[r + 1] - bounds[r] for r in range(world)]
+    lo, hi = bounds[rank], bounds[rank + 1]
+    res = compute(ref_batch.slice_windows(lo, hi), variants.slice_windows(lo, hi)) if hi > lo else None
+    width = torch.tensor([res["sel_mask"].shape[1] if res is not None else 0], dtype=torch.int64, device=device)
+    dist.all_reduce(width, op=dist.ReduceOp.MAX)      # ranks may have sized max_sel differently
+    ms = int(width.item())
+
+    def block(name, dtype, wide):
+        shape = (hi - lo, ms) if wide else (hi - lo,)
+        a = np.zeros(shape, dtype)
+        if res is not None:
+            src = res[name]
+            if wide:
+                a[:, :src.shape[1]] = src
+            else:
+                a[:] = src
+        return a
+    out = {}
+    for name, dtype, wide in (("n_sel", np.int32, False), ("n_scored", np.int32, False), ("sel_mask", np.uint64, True),
+                              ("sel_score", np.float64, True)):
+        a = block(name, dtype, wide)
+        t = torch.as_tensor(a.view(np.int64) if dtype == np.uint64 else a, device=device)
+        g = gather_blocks(t, counts).cpu().numpy()
+        out[name] = g.view(np.uint64) if dtype == np.uint64 else g
+    out["max_sel"] = ms
+    return out

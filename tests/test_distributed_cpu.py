@@ -59,3 +59,50 @@ def test_shard_bounds_cover_all_windows():
         for w in (1, 2, 4, 8):
             b = shard_bounds(n, w)
             assert b[0] == 0 and b[-1] == n and all(0 <= b[i + 1] - b[i] <= (n + w - 1) // w for i in range(w))
+
+
+def _select_compute(b, v):
+    """Stand-in for Engine.select_haplotypes on a shard: the Python oracle, packed like PlbSelectOut."""
+    from oracle import select_oracle as S
+    ms = 16
+    out = {"n_sel": np.zeros(b.n_windows, np.int32), "n_scored": np.zeros(b.n_windows, np.int32),
+           "sel_mask": np.zeros((b.n_windows, ms), np.uint64), "sel_score": np.full((b.n_windows, ms), np.nan)}
+    for w in range(b.n_windows):
+        tr = []
+        got = S.select_haplotypes(S.window_from_batch(b, v, w), 9, 9, 8, 1, 30, trace=tr)
+        out["n_sel"][w] = len(got)
+        out["n_scored"][w] = sum(len(r) for r in tr)
+        for j, (s_, sc) in enumerate(got):
+            out["sel_mask"][w, j] = sum(1 << i for i in s_)
+            out["sel_score"][w, j] = np.nan if sc is None else sc
+    return out
+
+
+def _select_worker(rank, world, port, n_windows, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from platypus_b200 import shard, synth
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b, v = synth.make_select_batch(n_windows, n_vars=5, n_reads=10, read_len=60, hap_len=160)
+        got = shard.run_select_sharded(b, v, _select_compute)
+        if rank == 0:
+            np.savez(out_path, **got)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_windows", [5, 1])
+def test_sharded_selection_equals_single_process(tmp_path, n_windows, oracle):
+    """N1 over two ranks (window blocks + all-gather of masks / scores) = the same windows on one process."""
+    from platypus_b200 import synth
+    out = str(tmp_path / "sel.npz")
+    mp.spawn(_select_worker, args=(2, _free_port(), n_windows, out), nprocs=2, join=True)
+    got = np.load(out)
+    b, v = synth.make_select_batch(n_windows, n_vars=5, n_reads=10, read_len=60, hap_len=160)
+    want = _select_compute(b, v)
+    assert np.array_equal(got["n_sel"], want["n_sel"]) and np.all(want["n_sel"] == 8)
+    assert np.array_equal(got["n_scored"], want["n_scored"])
+    assert np.array_equal(got["sel_mask"], want["sel_mask"])
+    assert np.array_equal(np.nan_to_num(got["sel_score"]), np.nan_to_num(want["sel_score"]))
