@@ -343,7 +343,10 @@ T* at(const Block& b, size_t off) {
     return (T*)((uint8_t*)b.p + off);
 }
 
-constexpr size_t kAnchorNextBudget = 24 * 1024;  // position chains of one haplotype group
+// position chains of one haplotype group.  The chain heads and multiplicity rows grow with the group as well (about
+// 6 bytes per haplotype base in all), so 8 KB of chains keeps a tile near 40 KB of shared memory = 4 CTAs per SM; with
+// 24 KB the 48-haplotype groups of the selection rounds needed 98 KB (2 CTAs per SM, 25 % of the warps active)
+constexpr size_t kAnchorNextBudget = 8 * 1024;
 constexpr size_t kAnchorHashBudget = 24 * 1024;  // read 7-mer ids of one tile
 constexpr size_t kAnchorCntBudget = 48 * 1024;   // per-warp vote arrays of the exact (tie) path
 constexpr int kAnchorMaxSlots = 256;
@@ -387,20 +390,31 @@ static int plan_tiles(const PlbWindowBatch* hb, int w_begin, int w_end, TileList
         }
         // ---- anchor tiles
         {
-            int g0 = h0;
-            size_t next_bytes = 0;
-            for (int h = h0; h < h1; ++h) {
-                const int len = (int)(hb->hap_seq_off[h + 1] - hb->hap_seq_off[h]);
-                max_hap = std::max(max_hap, len);
-                const size_t need = 2 * (size_t)((len + 2) & ~1);
-                if (h > g0 && (next_bytes + need > kAnchorNextBudget || h - g0 >= 64)) {
-                    groups.push_back({g0, h});
-                    g0 = h;
-                    next_bytes = 0;
+            // greedy grouping under the budget, then the same number of groups with the haplotypes spread evenly
+            // (50 trial haplotypes: 13 + 13 + 13 + 11 rather than 16 + 16 + 16 + 2)
+            auto build = [&](int cap) {
+                groups.clear();
+                int g0 = h0;
+                size_t next_bytes = 0;
+                for (int h = h0; h < h1; ++h) {
+                    const int len = (int)(hb->hap_seq_off[h + 1] - hb->hap_seq_off[h]);
+                    max_hap = std::max(max_hap, len);
+                    const size_t need = 2 * (size_t)((len + 2) & ~1);
+                    if (h > g0 && (next_bytes + need > kAnchorNextBudget || h - g0 >= cap)) {
+                        groups.push_back({g0, h});
+                        g0 = h;
+                        next_bytes = 0;
+                    }
+                    next_bytes += need;
                 }
-                next_bytes += need;
+                groups.push_back({g0, h1});
+            };
+            build(64);
+            const int ng = (int)groups.size();
+            if (ng > 1) {
+                build((h1 - h0 + ng - 1) / ng);
+                if ((int)groups.size() > ng) build(64);   // uneven lengths: the even split needed more groups
             }
-            groups.push_back({g0, h1});
             for (auto& g : groups) {
                 int nh_ = 0, sum_nk = 0, hpk = 0;
                 for (int h = g.first; h < g.second; ++h) {
