@@ -344,9 +344,11 @@ T* at(const Block& b, size_t off) {
 }
 
 // position chains of one haplotype group.  The chain heads and multiplicity rows grow with the group as well (about
-// 6 bytes per haplotype base in all), so 8 KB of chains keeps a tile near 40 KB of shared memory = 4 CTAs per SM; with
-// 24 KB the 48-haplotype groups of the selection rounds needed 98 KB (2 CTAs per SM, 25 % of the warps active)
-constexpr size_t kAnchorNextBudget = 8 * 1024;
+// 6 bytes per haplotype base in all), so 12 KB of chains keeps a tile near 45 KB of shared memory = 4 CTAs per SM; with
+// 24 KB the 48-haplotype groups of the selection rounds needed 98 KB (2 CTAs per SM, 25 % of the warps active).
+// Measured on the selection workload (k_anchor per round launch): 24 KB 0.82 ms, 12 KB 0.58, 8 KB 0.60, 6 KB 0.63, 4 KB 0.69.
+// PLB_ANCHOR_BUDGET overrides it for such sweeps.
+static const size_t kAnchorNextBudget = getenv("PLB_ANCHOR_BUDGET") ? (size_t)atoi(getenv("PLB_ANCHOR_BUDGET")) : 12 * 1024;
 constexpr size_t kAnchorHashBudget = 24 * 1024;  // read 7-mer ids of one tile
 constexpr size_t kAnchorCntBudget = 48 * 1024;   // per-warp vote arrays of the exact (tie) path
 constexpr int kAnchorMaxSlots = 256;

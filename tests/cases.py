@@ -457,12 +457,13 @@ def check_n4(got, g, k, rtol=1e-12):
 
 # ---- N1: haplotype selection loop ------------------------------------------------------------------------------
 
-def n1_window_case(seed):
+def n1_window_case(seed, drop=0):
     """One window for getFilteredHaplotypes (variantFilter.pyx:377-506): 3-9 candidate variants (SNPs, 1-3 bp
     insertions / deletions, multi-allelic SNPs at one position whose unseen alleles give exactly tied scores, adjacent
     SNP + indel pairs, overlapping deletions that make some combinations invalid), nSupportingReads with ties, 1-3
     individuals (one may have no reads) with 8-90 good reads drawn from two true haplotypes, and the option values
-    (small maxHaplotypes so that the heap overflows; coverage levels that switch sub-sampling on)."""
+    (small maxHaplotypes so that the heap overflows; coverage levels that switch sub-sampling on).  drop = 1 / 2 removes
+    all reads / the first individual's reads afterwards (same variants and options)."""
     rng = random.Random(1000003 * seed + 17)
     genome = _rand_seq(rng, 2400)
     if seed % 4 == 0:
@@ -545,6 +546,10 @@ def n1_window_case(seed):
             reads.append((seq, qual, p, p + L, rng.choice([60, 60, 60, 40, 23, 0]), 512 if rng.random() < 0.03 else 0))
         reads.sort(key=lambda t: t[2])
         per_ind.append(reads)
+    if drop == 1:      # no reads at all: every trial scores -1e20 and only the tuple order of the variant sets decides
+        per_ind = [[] for _ in per_ind]
+    elif drop == 2:    # the first individual has no reads
+        per_ind = [[]] + per_ind[1:]
     opts = dict(max_haplotypes=rng.choice([4, 6, 9, 17, 50]), max_variants=8, filter_by_coverage=rng.choice([0, 0, 1]),
                 coverage_sampling_level=rng.choice([3, 10, 30]))
     opts["original_max_haplotypes"] = opts["max_haplotypes"] if rng.random() < 0.7 else opts["max_haplotypes"] + rng.randint(1, 6)
@@ -586,7 +591,7 @@ def n1_golden_cases(golden_dir):
         a, b = z["sel_off"][k], z["sel_off"][k + 1]
         t0, t1 = z["trial_off"][k], z["trial_off"][k + 1]
         seqs = [z["hap_seq"][z["hap_seq_off"][j]:z["hap_seq_off"][j + 1]].tobytes() for j in range(a, b)]
-        out.append(dict(seed=int(seed), ref_seq=z["ref_seq"][z["ref_off"][k]:z["ref_off"][k + 1]].tobytes(),
+        out.append(dict(seed=int(seed), drop=int(z["drop"][k]), ref_seq=z["ref_seq"][z["ref_off"][k]:z["ref_off"][k + 1]].tobytes(),
                         hap_start=int(z["hap_start"][k]), sel_mask=[int(m) for m in z["sel_mask"][a:b]], hap_seqs=seqs,
                         trial_mask=[int(m) for m in z["trial_mask"][t0:t1]], trial_score=z["trial_score"][t0:t1],
                         opts={k2: int(z["opt_" + k2][k]) for k2 in ("max_haplotypes", "original_max_haplotypes", "max_variants",

@@ -3,7 +3,7 @@ Golden vectors for SURVEY §8f row N1 (haplotype construction + the haplotype se
 
 Run in the BUILD container (needs /root/reference and oracle/_ref/n1_ref, built by oracle/build.py from the
 reference's own getFilteredHaplotypes / computeBestScoreForGenotype / isHaplotypeValid source lines).  The inputs
-are tests/cases.py n1_window_case(seed); this file stores what the REFERENCE returns for them:
+are tests/cases.py n1_window_case(seed, drop); this file stores what the REFERENCE returns for them:
   ref_seq / hap_start   the reference haplotype (Haplotype(..., variants=()))
   sel_mask, hap_seq     the variant sets getFilteredHaplotypes returns, in order, and Haplotype.cHaplotypeSequence of each
   trial_mask / score    every trial set the rounds score (in the order they are scored) with the reference's
@@ -21,7 +21,8 @@ from oracle import select_oracle as S  # noqa: E402
 from tests import cases  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SEEDS = list(range(72))
+SEEDS = list(range(72)) + list(range(100, 112)) + list(range(100, 112))
+DROP = [0] * 72 + [1] * 12 + [2] * 12      # cases.n1_window_case(seed, drop): all reads / the first individual's reads removed
 
 
 def main():
@@ -30,8 +31,8 @@ def main():
     d = {k: [] for k in ("ref_seq", "hap_start", "sel_mask", "hap_seq", "trial_mask", "trial_score")}
     ref_off, sel_off, hs_off, trial_off = [0], [0], [0], [0]
     opts = {k: [] for k in ("max_haplotypes", "original_max_haplotypes", "max_variants", "filter_by_coverage", "coverage_sampling_level")}
-    for seed in SEEDS:
-        c = cases.n1_window_case(seed)
+    for seed, drop in zip(SEEDS, DROP):
+        c = cases.n1_window_case(seed, drop)
         o = c["opts"]
         args = (c["genome"], c["win_start"], c["win_end"], c["variants"], c["per_ind"], c["max_read_len"], o["max_haplotypes"],
                 o["original_max_haplotypes"], o["max_variants"], o["filter_by_coverage"], o["coverage_sampling_level"])
@@ -59,7 +60,7 @@ def main():
         for k in opts:
             opts[k].append(o[k])
     np.savez_compressed(
-        os.path.join(HERE, "n1_ref.npz"), seeds=np.asarray(SEEDS, np.int32), ref_seq=np.concatenate(d["ref_seq"]),
+        os.path.join(HERE, "n1_ref.npz"), seeds=np.asarray(SEEDS, np.int32), drop=np.asarray(DROP, np.int32), ref_seq=np.concatenate(d["ref_seq"]),
         ref_off=np.asarray(ref_off, np.int64), hap_start=np.asarray(d["hap_start"], np.int32),
         sel_mask=np.asarray(d["sel_mask"], np.uint64), sel_off=np.asarray(sel_off, np.int64),
         hap_seq=np.concatenate(d["hap_seq"]), hap_seq_off=np.asarray(hs_off, np.int64),

@@ -503,7 +503,7 @@ def _n1_groups(golden_dir):
         by_opts.setdefault(tuple(sorted(g["opts"].items())), []).append(g)
     out = []
     for key, group in by_opts.items():
-        cs = [cases.n1_window_case(g["seed"]) for g in group]
+        cs = [cases.n1_window_case(g["seed"], g["drop"]) for g in group]
         batch, vset = cases.n1_batch(cs, [g["ref_seq"] for g in group], [g["hap_start"] for g in group])
         o = dict(key)
         sel = _abi.PlbSelectOptions(o["max_haplotypes"], o["original_max_haplotypes"], o["max_variants"], o["filter_by_coverage"],
@@ -520,7 +520,7 @@ def test_n1_build_haplotypes_golden_ref(engine, golden_dir):
     for group, batch, vset, _ in _n1_groups(golden_dir):
         hap_win, hap_mask, want = [], [], []
         for k, g in enumerate(group):
-            c = cases.n1_window_case(g["seed"])
+            c = cases.n1_window_case(g["seed"], g["drop"])
             w = cases.n1_select_window(c, g["ref_seq"], g["hap_start"])
             hap_win.append(k)
             hap_mask.append(0)

@@ -121,7 +121,7 @@ def test_n1_selection_bookkeeping_replay(oracle, golden_dir):
     n_windows = 0
     for key, group in by_opts.items():
         o = dict(key)
-        cs = [cases.n1_window_case(g["seed"]) for g in group]
+        cs = [cases.n1_window_case(g["seed"], g["drop"]) for g in group]
         batch, vset = cases.n1_batch(cs, [g["ref_seq"] for g in group], [g["hap_start"] for g in group])
         table = [dict(zip(g["trial_mask"], g["trial_score"])) for g in group]
         asked = [[] for _ in group]
@@ -147,7 +147,7 @@ def test_n1_selection_rejects_bad_variant_lists(golden_dir):
     from platypus_b200.batch import VariantSet
     lib = _lib()
     g = cases.n1_golden_cases(golden_dir)[0]
-    c = cases.n1_window_case(g["seed"])
+    c = cases.n1_window_case(g["seed"], g["drop"])
     batch, _ = cases.n1_batch([c], [g["ref_seq"]], [g["hap_start"]])
     vs = c["variants"]
     for bad in ([vs[1], vs[0]] + vs[2:], vs + [vs[-1]], [(c["win_end"] + 5, b"A", b"C", 1)]):

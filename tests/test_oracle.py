@@ -509,7 +509,7 @@ def test_golden_n1_ref(oracle, golden_dir):
     assert len(gold) >= 60
     n_filter = n_tied = 0
     for g in gold:
-        c = cases.n1_window_case(g["seed"])
+        c = cases.n1_window_case(g["seed"], g["drop"])
         sel, seqs, sets, scores = _n1_oracle_run(c, g["ref_seq"], g["hap_start"])
         assert cases.masks_of(sel) == g["sel_mask"], g["seed"]
         assert seqs == g["hap_seqs"], g["seed"]
