@@ -500,6 +500,7 @@ struct SelPlan {
     std::vector<int> n_trials;
     int r = 0, Wr = 0, nh = 0;
     bool active = false;
+    bool in_prologue = false;   // the launch in flight scores the trial sets of rounds 0 .. prologue-1 together
     // per-round arrays handed to the scorer: pinned when the scorer provides memory (set in prepare), else own_*
     int32_t* r_hoff = nullptr;
     int64_t* r_hsoff = nullptr;
@@ -713,6 +714,14 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
 
     double t_host = 0, n_trials_total = 0, tb_trials = 0, tb_len = 0, tb_heap = 0;
     int rounds = 0;
+    // While the heap is not full nothing is evicted, so the trial SETS of the first rounds do not depend on any score:
+    // round r tries v_r alone and v_r joined to every earlier (valid) trial.  The first K rounds, K = the largest with
+    // 2^K - 1 <= originalMaxHaplotypes - 1 (5 for the default 49: at most 31 sets), are therefore scored in ONE launch;
+    // their heap pushes are replayed afterwards in the reference's order (which does depend on the scores, through
+    // sorted(heap)).  That removes the latency-bound launches with 1, 2, 4 ... trials per window.
+    int prologue = 0;
+    while (prologue < 6 && (1 << (prologue + 1)) - 1 <= orig_cap) ++prologue;
+    if (getenv("PLB_SELECT_NO_PROLOGUE")) prologue = 0;   // tests: the plain round-by-round schedule
     // host phase 1 of a group's next round: the trial haplotypes (variantFilter.pyx:452-476: {v_r}, then v_r joined to
     // every kept set in sorted(heap) order) and their lengths.  Returns 1 when there is a round to score.
     auto begin_round = [&](SelPlan& P) -> int {
@@ -723,12 +732,28 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
             while (Wr < P.Wf && P.voff[(size_t)Wr + 1] - P.voff[(size_t)Wr] > r) ++Wr;
         P.Wr = Wr;
         if (Wr == 0) return 0;
+        P.in_prologue = r == 0 && prologue > 1;
 #pragma omp parallel for schedule(static) num_threads(host_threads()) if (Wr > 256)
         for (int k = 0; k < Wr; ++k) {
             SelEntryState& s = P.state[(size_t)k];
             const int v0 = P.voff[(size_t)k];
             const SelKeys keys{P.pos.data() + v0, P.type.data() + v0, P.nrem.data() + v0};
             uint64_t* m = P.trial_mask.data() + (size_t)k * max_trials;
+            if (P.in_prologue) {   // every trial set of rounds 0 .. min(prologue, nVar) - 1
+                const int nr = std::min(prologue, P.voff[(size_t)k + 1] - v0);
+                int n = 0;
+                for (int q = 0; q < nr; ++q) {
+                    const uint64_t bit = 1ull << s.order[(size_t)q];
+                    const int n_prev = n;
+                    m[n++] = bit;
+                    for (int j = 0; j < n_prev; ++j) {
+                        const uint64_t both = m[j] | bit;
+                        if (sel_valid(both, keys.pos, keys.nrem, P.nadd.data() + v0)) m[n++] = both;
+                    }
+                }
+                P.n_trials[(size_t)k] = n;
+                continue;
+            }
             const uint64_t bit = 1ull << s.order[(size_t)r];
             int n = 0;
             m[n++] = bit;
@@ -797,6 +822,37 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
             SelEntryState& s = P.state[(size_t)k];
             const int v0 = P.voff[(size_t)k];
             const SelKeys keys{P.pos.data() + v0, P.type.data() + v0, P.nrem.data() + v0};
+            if (P.in_prologue) {   // replay rounds 0 .. nr-1 with the scores of the one launch
+                const int nr = std::min(prologue, P.voff[(size_t)k + 1] - v0);
+                const int nt = P.n_trials[(size_t)k];
+                const uint64_t* tm = P.mask_c + (size_t)P.r_hoff[(size_t)k];
+                const double* ts = P.scores + (size_t)P.r_hoff[(size_t)k];
+                auto score_of = [&](uint64_t mk) {
+                    for (int j = 0; j < nt; ++j)
+                        if (tm[j] == mk) return ts[j];
+                    return -1e20;   // unreachable: every set the replay forms was enumerated
+                };
+                std::vector<SelEntry> old;
+                for (int q = 0; q < nr; ++q) {
+                    const uint64_t bit = 1ull << s.order[(size_t)q];
+                    old = s.heap;
+                    py_sort(old, keys, false);
+                    auto push = [&](uint64_t mk) {
+                        const SelEntry e{score_of(mk), mk};
+                        if ((int)s.heap.size() < orig_cap)
+                            heap_push(s.heap, e, keys);
+                        else
+                            heap_pushpop(s.heap, e, keys);
+                    };
+                    push(bit);
+                    for (const SelEntry& e : old) {
+                        const uint64_t both = e.mask | bit;
+                        if (sel_valid(both, keys.pos, keys.nrem, P.nadd.data() + v0)) push(both);
+                    }
+                }
+                s.n_done += nt;
+                continue;
+            }
             for (int j = 0; j < P.n_trials[(size_t)k]; ++j) {
                 const SelEntry e{P.scores[(size_t)P.r_hoff[(size_t)k] + j], P.mask_c[(size_t)P.r_hoff[(size_t)k] + j]};
                 if ((int)s.heap.size() < orig_cap)
@@ -808,7 +864,8 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
         }
         n_trials_total += P.nh;
         for (int k = 0; k < Wr; ++k) cells_total += (double)P.win_cells[(size_t)k] * P.n_trials[(size_t)k];
-        ++P.r;
+        P.r = P.in_prologue ? prologue : P.r + 1;
+        P.in_prologue = false;
         const double th2 = now_ms();
         tb_heap += th2 - th1;
         t_host += th2 - th1;

@@ -595,7 +595,7 @@ def test_n1_select_synth_batch_vs_oracle(engine, oracle):
         np.concatenate([v.var_added[:int(v.var_added_off[-1])] for v in parts] + [np.zeros(1, np.uint8)]))
     out = engine.select_haplotypes(batch, vset)
     st = engine.select_stats()
-    assert st["rounds"] == 8 and st["n_filter_windows"] == 500      # one group of windows (< 2048): 8 round launches
+    assert st["rounds"] == 4 and st["n_filter_windows"] == 500      # one group of windows (< 2048); rounds 0-4 in one launch
     assert np.all(out["n_sel"][:200] == 49) and np.all(out["n_sel"][200:500] == 49) and np.all(out["n_sel"][500:] == 7)
     assert np.all(out["n_scored"][:200] == 1 + 2 + 4 + 8 + 16 + 32) and np.all(out["n_scored"][200:500] == 163)
     for w in range(500):

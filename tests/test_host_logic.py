@@ -108,12 +108,17 @@ def test_synth_shapes_match_config2_accounting():
     assert (hl >= lens.max() + 16).all() and hl.max() <= 500
 
 
-def test_n1_selection_bookkeeping_replay(oracle, golden_dir):
+@pytest.mark.parametrize("prologue", [True, False])
+def test_n1_selection_bookkeeping_replay(oracle, golden_dir, prologue, monkeypatch):
     """plb_select_replay_host (the library's trial sets / isHaplotypeValid / heap and sort replay / final ranking, no
     GPU) fed with the reference's own trial scores reproduces the reference's selection on the golden windows: every
-    round asks for exactly the trial sets the reference scores, in its order, and the returned haplotypes match."""
+    round asks for exactly the trial sets the reference scores, in its order, and the returned haplotypes match.  With the
+    prologue (default) the score-independent trial sets of the first rounds are requested in one go."""
     from platypus_b200.engine import Engine
     lib = _lib()
+    monkeypatch.setenv("PLB_SELECT_CHECK", "1")
+    if not prologue:   # plain schedule: one scoring request per round, in the reference's order
+        monkeypatch.setenv("PLB_SELECT_NO_PROLOGUE", "1")
     gold = cases.n1_golden_cases(golden_dir)
     by_opts = {}
     for g in gold:
@@ -136,7 +141,10 @@ def test_n1_selection_bookkeeping_replay(oracle, golden_dir):
         for k, g in enumerate(group):
             n = int(out["n_sel"][k])
             assert [int(m) for m in out["sel_mask"][k, :n]] == g["sel_mask"], g["seed"]
-            assert asked[k] == g["trial_mask"], g["seed"]
+            if prologue:   # the first rounds' trial sets are requested together (they do not depend on the scores)
+                assert sorted(asked[k]) == sorted(g["trial_mask"]), g["seed"]
+            else:
+                assert asked[k] == g["trial_mask"], g["seed"]
             assert int(out["n_scored"][k]) == len(g["trial_mask"])
             n_windows += 1
     assert n_windows == len(gold)
