@@ -522,7 +522,7 @@ static int plan_tiles(const PlbWindowBatch* hb, int w_begin, int w_end, TileList
 // Bytes of the big sequence arrays (hap_seq / read_seq / read_qual) that windows [w0, w1) need.
 // One OpenMP team size for every host-side parallel region of the library.
 static int host_threads() {
-    static const int n = std::max(1, std::min(omp_get_max_threads(), 8));
+    static const int n = std::max(1, std::min(omp_get_max_threads(), getenv("PLB_HOST_THREADS") ? atoi(getenv("PLB_HOST_THREADS")) : 16));
     return n;
 }
 
