@@ -32,11 +32,17 @@ def raw(rep):
 
 
 def main():
-    out_md, reps = sys.argv[1], sys.argv[2:]
+    args = sys.argv[1:]
+    what = ("`python bench.py --steps 1 --warmup 3` (config 2: 10,000 windows x 8 haplotypes x 64 reads)")
+    if args and args[0] == "--select":   # the haplotype selection stage (tools/gpu_select_profile.sh)
+        args = args[1:]
+        what = ("`python tools/select_bench.py 10000 1 --pin` (synth-select-v1: 10,000 windows x 8 candidate variants, one "
+                "launch of a late round: ~50 trial haplotypes x 11 sampled reads per window, half of the windows)")
+    out_md, reps = args[0], args[1:]
+    assert out_md.endswith(".md"), "usage: ncu_summary.py [--select] OUT.md report.ncu-rep ..."
     with open(out_md, "w") as f:
         f.write("# ncu summaries (`ncu --set full --clock-control none --import-source on`, one launch per kernel)\n\n")
-        f.write("Captured on a B200 under gpurun while running `python bench.py --steps 1 --warmup 3` "
-                "(config 2: 10,000 windows x 8 haplotypes x 64 reads).  Times under the profiler are "
+        f.write("Captured on a B200 under gpurun while running " + what + ".  Times under the profiler are "
                 "cold-cache and serialised; bench.py's numbers come from CUDA events outside the profiler.\n\n")
         for rep in reps:
             for name, vals in raw(rep):
