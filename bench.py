@@ -418,7 +418,13 @@ def run_select(args):
         "value_definition": "cells / GPU-busy time of a call (reference pass + haplotype construction + scoring kernels + score "
                             "reduction, CUDA events); reads are uploaded once per call, the rounds run from HBM",
         "e2e": {"value": cells / t_wall / 1e9, "unit": UNIT, "ms_per_step": t_wall * 1e3, "ms_each_step": [x * 1e3 for x in wall],
-                "h2d_bytes_per_step": int(batch.input_nbytes()), "d2h_bytes_per_step": int(8 * st["n_trials"]),
+                # what the call copies: the compact pool of sampled reads (bases, qualities, 18 B of fields each), the reference
+                # segments, the variant table, and per trial haplotype its mask, sequence offset and window map (tile lists are
+                # read zero-copy from pinned memory and not counted)
+                "h2d_bytes_per_step": int(W * reads_per_w * (2 * READ_LEN + 18) + W * (HAP_LEN + 24) + len(vset.var_pos) * 16
+                                          + int(vset.var_added_off[-1]) + 24 * st["n_trials"]),
+                "d2h_bytes_per_step": int(8 * st["n_trials"]),
+                "host_buffer_bytes": int(batch.input_nbytes()),
                 "windows_per_s": W / t_wall,
                 "api": "plb_select_haplotypes_host (pinned host buffers in, variant masks + scores out, all rounds inside)"},
         "select_stats": st, "kernel_ms_mean_per_launch": kt,

@@ -519,9 +519,9 @@ struct SelPlan {
 //   wait(plan)           block until plan.scores is complete
 // Large batches are cut into two groups whose rounds alternate, so that the host's bookkeeping for one group runs
 // while the scorer works on the other.
-template <typename Prepare, typename Submit, typename Wait>
+template <typename Alloc, typename Prepare, typename Submit, typename Wait>
 static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const PlbSelectOptions* so, const PlbOptions* opt,
-                       PlbSelectOut* out, bool need_reads, Prepare&& prepare, Submit&& submit, Wait&& wait) {
+                       PlbSelectOut* out, bool need_reads, Alloc&& alloc, Prepare&& prepare, Submit&& submit, Wait&& wait) {
     if (!so || !out || !out->n_sel || !out->sel_mask) return set_err(PLB_ERR_ARG, "NULL argument");
     SelHost sh;
     int rc = check_variants(rb, vs, sh);
@@ -529,6 +529,9 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
     const int W = rb->n_windows, nInd = rb->n_individuals;
     if (W == 0) return PLB_OK;
     if (nInd < 1 || (need_reads && (!rb->wi_slot_off || !rb->wi_n_good))) return set_err(PLB_ERR_ARG, "ref_batch: NULL slot arrays");
+    if (need_reads && rb->n_slots > 0 && (!rb->slot_read || !rb->read_seq_off || !rb->read_seq || !rb->read_qual || !rb->read_pos ||
+                                          !rb->read_end || !rb->read_mapq || !rb->read_qcfail))
+        return set_err(PLB_ERR_ARG, "NULL read array in batch");
     const int orig_cap = so->original_max_haplotypes - 1, cap = so->max_haplotypes - 1;
     if (cap < 1 || orig_cap < 1 || so->coverage_sampling_level <= 0) return set_err(PLB_ERR_ARG, "bad PlbSelectOptions");
     if (orig_cap > 63)
@@ -609,55 +612,137 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
         P.hsoff.resize((size_t)Wf + 1);
         P.slot_off.resize((size_t)Wf * nInd + 1);
         P.voff.resize((size_t)Wf + 1);
-        P.aoff.assign(1, 0);
         P.win_cells.assign((size_t)Wf, 0);
+        // pass 1 (serial, light): sizes -> offsets.  The sampled reads are COPIED into a compact pool of their own
+        // (pinned when the scorer provides memory): only every sampleRate-th read is scored, so uploading the caller's
+        // whole pool would move several times the bytes the rounds touch.
+        std::vector<int> rate((size_t)Wf * nInd, 1);
+        std::vector<int64_t> byte_off((size_t)Wf + 1, 0), add_off((size_t)Wf + 1, 0);
         P.hoff[0] = 0;
         P.hsoff[0] = 0;
         P.slot_off[0] = 0;
         P.voff[0] = 0;
         for (int k = 0; k < Wf; ++k) {
             const int w = P.filt[(size_t)k];
+            P.hoff[(size_t)k + 1] = k + 1;
+            P.hsoff[(size_t)k + 1] = P.hsoff[(size_t)k] + (rb->hap_seq_off[w + 1] - rb->hap_seq_off[w]);
+            const int size = rb->win_end[w] - rb->win_start[w];
+            int64_t bytes = 0;
+            for (int i = 0; i < nInd; ++i) {
+                int64_t n_s = 0;
+                if (need_reads) {
+                    const int64_t wi = (int64_t)w * nInd + i;
+                    const int64_t b0 = rb->wi_slot_off[wi];
+                    const int n_good = rb->wi_n_good[wi];
+                    if (n_good > 0) {
+                        const int r_first = rb->slot_read[b0];
+                        if (r_first < 0 || r_first >= rb->n_reads)
+                            return set_err(PLB_ERR_ARG, "slot %lld: read index out of range", (long long)b0);
+                        const int64_t rlen = rb->read_seq_off[r_first + 1] - rb->read_seq_off[r_first];
+                        const int64_t mean_cov = rlen * n_good / size;
+                        const int rt = (int)std::max<int64_t>(1, mean_cov / so->coverage_sampling_level);
+                        rate[(size_t)k * nInd + i] = rt;
+                        for (int t = 0; t < n_good; t += rt) {
+                            const int r = rb->slot_read[b0 + t];
+                            if (r < 0 || r >= rb->n_reads)
+                                return set_err(PLB_ERR_ARG, "slot %lld: read index out of range", (long long)(b0 + t));
+                            const int64_t L = rb->read_seq_off[r + 1] - rb->read_seq_off[r];
+                            if (L < 0 || L > 32767) return set_err(PLB_ERR_SHAPE, "read %d length %lld out of range", r, (long long)L);
+                            bytes += L;
+                            ++n_s;
+                        }
+                    }
+                }
+                P.slot_off[(size_t)k * nInd + i + 1] = P.slot_off[(size_t)k * nInd + i] + n_s;
+            }
+            byte_off[(size_t)k + 1] = byte_off[(size_t)k] + bytes;
+            P.win_cells[(size_t)k] = 16 * bytes;
+            cells_total += (double)P.win_cells[(size_t)k];   // the reference-haplotype pass
+            const int v0 = vs->win_var_off[w], v1 = vs->win_var_off[w + 1];
+            P.voff[(size_t)k + 1] = P.voff[(size_t)k] + (v1 - v0);
+            add_off[(size_t)k + 1] = add_off[(size_t)k] + (vs->var_added_off[v1] - vs->var_added_off[v0]);
+        }
+        const int64_t n_s_all = P.slot_off[(size_t)Wf * nInd], n_bytes = byte_off[(size_t)Wf];
+        const int nvar_g = P.voff[(size_t)Wf];
+        if (n_s_all > INT32_MAX) return set_err(PLB_ERR_SHAPE, "too many sampled reads in one group");
+        P.ref.resize((size_t)P.hsoff[(size_t)Wf]);
+        P.slot.resize((size_t)n_s_all);
+        P.pos.resize((size_t)nvar_g);
+        P.nrem.resize((size_t)nvar_g);
+        P.nadd.resize((size_t)nvar_g);
+        P.type.resize((size_t)nvar_g);
+        P.nsup.resize((size_t)nvar_g);
+        P.aoff.resize((size_t)nvar_g + 1);
+        P.add.resize((size_t)add_off[(size_t)Wf]);
+        P.aoff[0] = 0;
+        int64_t* c_off = nullptr;
+        uint8_t *c_seq = nullptr, *c_qual = nullptr, *c_mapq = nullptr, *c_qc = nullptr;
+        int32_t *c_pos = nullptr, *c_end = nullptr;
+        if (need_reads) {
+            c_off = (int64_t*)alloc(((size_t)n_s_all + 1) * 8);
+            c_seq = (uint8_t*)alloc((size_t)n_bytes + 64);
+            c_qual = (uint8_t*)alloc((size_t)n_bytes + 64);
+            c_pos = (int32_t*)alloc((size_t)n_s_all * 4 + 4);
+            c_end = (int32_t*)alloc((size_t)n_s_all * 4 + 4);
+            c_mapq = (uint8_t*)alloc((size_t)n_s_all + 4);
+            c_qc = (uint8_t*)alloc((size_t)n_s_all + 4);
+            if (!c_off || !c_seq || !c_qual || !c_pos || !c_end || !c_mapq || !c_qc)
+                return set_err(PLB_ERR_NOMEM, "host allocation for the sampled reads failed");
+            c_off[0] = 0;
+        }
+        // pass 2 (parallel): copies
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (Wf > 256)
+        for (int k = 0; k < Wf; ++k) {
+            const int w = P.filt[(size_t)k];
             P.ws[(size_t)k] = rb->win_start[w];
             P.we[(size_t)k] = rb->win_end[w];
             P.hs[(size_t)k] = rb->hap_start[w];
-            P.hoff[(size_t)k + 1] = k + 1;
-            const int64_t r0 = rb->hap_seq_off[w], r1 = rb->hap_seq_off[w + 1];
-            P.ref.insert(P.ref.end(), rb->hap_seq + r0, rb->hap_seq + r1);
-            P.hsoff[(size_t)k + 1] = (int64_t)P.ref.size();
-            const int size = rb->win_end[w] - rb->win_start[w];
+            memcpy(P.ref.data() + P.hsoff[(size_t)k], rb->hap_seq + rb->hap_seq_off[w], (size_t)(P.hsoff[(size_t)k + 1] - P.hsoff[(size_t)k]));
+            int64_t bo = byte_off[(size_t)k];
             for (int i = 0; i < nInd && need_reads; ++i) {
                 const int64_t wi = (int64_t)w * nInd + i;
                 const int64_t b0 = rb->wi_slot_off[wi];
-                const int n_good = rb->wi_n_good[wi];
-                if (n_good > 0) {
-                    const int r_first = rb->slot_read[b0];
-                    if (r_first < 0 || r_first >= rb->n_reads) return set_err(PLB_ERR_ARG, "slot %lld: read index out of range", (long long)b0);
-                    const int64_t rlen = rb->read_seq_off[r_first + 1] - rb->read_seq_off[r_first];
-                    const int64_t mean_cov = rlen * n_good / size;
-                    const int rate = (int)std::max<int64_t>(1, mean_cov / so->coverage_sampling_level);
-                    for (int t = 0; t < n_good; t += rate) {
-                        const int r = rb->slot_read[b0 + t];
-                        if (r < 0 || r >= rb->n_reads) return set_err(PLB_ERR_ARG, "slot %lld: read index out of range", (long long)(b0 + t));
-                        P.slot.push_back(r);
-                        P.win_cells[(size_t)k] += 16 * (rb->read_seq_off[r + 1] - rb->read_seq_off[r]);
-                    }
+                const int n_good = rb->wi_n_good[wi], rt = rate[(size_t)k * nInd + i];
+                int64_t sl = P.slot_off[(size_t)k * nInd + i];
+                for (int t = 0; t < n_good; t += rt, ++sl) {
+                    const int r = rb->slot_read[b0 + t];
+                    const int64_t o = rb->read_seq_off[r], L = rb->read_seq_off[r + 1] - o;
+                    memcpy(c_seq + bo, rb->read_seq + o, (size_t)L);
+                    memcpy(c_qual + bo, rb->read_qual + o, (size_t)L);
+                    bo += L;
+                    c_off[sl + 1] = bo;
+                    c_pos[sl] = rb->read_pos[r];
+                    c_end[sl] = rb->read_end[r];
+                    c_mapq[sl] = rb->read_mapq[r];
+                    c_qc[sl] = rb->read_qcfail[r];
+                    P.slot[(size_t)sl] = (int32_t)sl;
                 }
-                P.slot_off[(size_t)k * nInd + i + 1] = (int64_t)P.slot.size();
             }
-            for (int v = vs->win_var_off[w]; v < vs->win_var_off[w + 1]; ++v) {
-                P.pos.push_back(vs->var_pos[v]);
-                P.nrem.push_back(vs->var_n_removed[v]);
-                P.nadd.push_back(sh.nadd[(size_t)v]);
-                P.type.push_back(sh.type[(size_t)v]);
-                P.nsup.push_back(vs->var_n_support[v]);
-                P.add.insert(P.add.end(), vs->var_added + vs->var_added_off[v], vs->var_added + vs->var_added_off[v + 1]);
-                P.aoff.push_back((int64_t)P.add.size());
+            const int v0 = vs->win_var_off[w], nv = vs->win_var_off[w + 1] - v0;
+            const int q0 = P.voff[(size_t)k];
+            const int64_t a0 = add_off[(size_t)k], src0 = vs->var_added_off[v0];
+            for (int j = 0; j < nv; ++j) {
+                P.pos[(size_t)q0 + j] = vs->var_pos[v0 + j];
+                P.nrem[(size_t)q0 + j] = vs->var_n_removed[v0 + j];
+                P.nadd[(size_t)q0 + j] = sh.nadd[(size_t)v0 + j];
+                P.type[(size_t)q0 + j] = sh.type[(size_t)v0 + j];
+                P.nsup[(size_t)q0 + j] = vs->var_n_support[v0 + j];
+                P.aoff[(size_t)q0 + j + 1] = a0 + (vs->var_added_off[v0 + j + 1] - src0);
             }
-            P.voff[(size_t)k + 1] = (int32_t)P.pos.size();
-            cells_total += (double)P.win_cells[(size_t)k];   // the reference-haplotype pass
+            if (add_off[(size_t)k + 1] > a0) memcpy(P.add.data() + a0, vs->var_added + src0, (size_t)(add_off[(size_t)k + 1] - a0));
         }
         PlbWindowBatch& hsb = P.batch;
-        hsb = *rb;   // read pool pointers stay the caller's
+        hsb = *rb;
+        if (need_reads) {   // the compact pool of sampled reads
+            hsb.n_reads = (int32_t)n_s_all;
+            hsb.read_seq_off = c_off;
+            hsb.read_seq = c_seq;
+            hsb.read_qual = c_qual;
+            hsb.read_pos = c_pos;
+            hsb.read_end = c_end;
+            hsb.read_mapq = c_mapq;
+            hsb.read_qcfail = c_qc;
+        }
         hsb.n_windows = Wf;
         hsb.n_haps = Wf;
         hsb.n_slots = (int64_t)P.slot.size();
@@ -798,8 +883,7 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
             }
             // every scored read needs hapLen >= readLen + 15 (calign.pyx:256-259)
             for (int64_t sl = P.slot_off[(size_t)k * nInd]; need_reads && sl < P.slot_off[(size_t)(k + 1) * nInd]; ++sl) {
-                const int rdx = P.slot[(size_t)sl];
-                const int64_t rl = rb->read_seq_off[rdx + 1] - rb->read_seq_off[rdx];
+                const int64_t rl = P.batch.read_seq_off[sl + 1] - P.batch.read_seq_off[sl];
                 if (rl >= PLB_KMER && rl + 15 > min_hap) bad_shape = 2;
             }
         }
@@ -930,7 +1014,7 @@ extern "C" int plb_select_replay_host(const PlbWindowBatch* rb, const PlbVariant
     if (!score) return set_err(PLB_ERR_ARG, "NULL argument");
     std::vector<int32_t> hw;
     return select_core(
-        rb, vs, so, nullptr, out, false, [](SelPlan&) { return PLB_OK; },
+        rb, vs, so, nullptr, out, false, [](size_t) -> void* { return nullptr; }, [](SelPlan&) { return PLB_OK; },
         [&](SelPlan& P, const SelRound& R) -> int {
             hw.resize((size_t)R.nh);
             for (int k = 0; k < R.Wr; ++k)
@@ -974,7 +1058,6 @@ extern "C" int plb_select_haplotypes_host(PlbContext* c, const PlbWindowBatch* r
     const bool modes = opt.calc_flank_score != 0;
     double t_build = 0, t_score = 0, t_reduce = 0, t_refpass = 0, n_pairs_total = 0;
     double tr_prepare = 0, tr_setup = 0, tr_plan = 0, tr_wait = 0;   // PLB_TRACE: host milliseconds by phase
-    bool arena_reset = false;
     auto cleanup = [&]() {
         cudaStreamSynchronize(st);
         for (auto& G : gd) {
@@ -1005,9 +1088,7 @@ extern "C" int plb_select_haplotypes_host(PlbContext* c, const PlbWindowBatch* r
         const double tp0 = now_ms();
         GroupDev& G = gd[P.gid];
         const int Wf = P.Wf, nvar = (int)P.pos.size();
-        // the second group keeps the pinned arena of the first (prepare_batch resets it unless the batch shares)
-        SEL_TRY(prepare_batch(c, &P.batch, &G.base, nullptr, !arena_reset));
-        arena_reset = true;
+        SEL_TRY(prepare_batch(c, &P.batch, &G.base, nullptr, false));
         Layout L;
         const size_t o_llref = L.take((size_t)P.batch.n_slots * 8 + 64), o_voff = L.take((size_t)(Wf + 1) * 4),
                      o_vpos = L.take((size_t)nvar * 4), o_vnr = L.take((size_t)nvar * 4),
@@ -1112,7 +1193,8 @@ extern "C" int plb_select_haplotypes_host(PlbContext* c, const PlbWindowBatch* r
 #undef SEL_CU
     static const bool trace = getenv("PLB_TRACE") != nullptr;
     const double t_call0 = now_ms();
-    rc = select_core(rb, vs, so, &opt, out, true, prepare, submit, wait);
+    pin_reset(c);   // one arena for the whole call: sampled reads, per-round arrays, tile lists
+    rc = select_core(rb, vs, so, &opt, out, true, [&](size_t bytes) { return pin_alloc(c, bytes); }, prepare, submit, wait);
     if (trace)
         fprintf(stderr, "[plb select] total %.2f ms: prepare %.2f | rounds: batch setup %.2f, plan %.2f, launch+wait %.2f | host bookkeeping %.2f\n",
                 now_ms() - t_call0, tr_prepare, tr_setup, tr_plan, tr_wait, g_sel_stats.v[4]);
