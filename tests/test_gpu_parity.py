@@ -574,6 +574,28 @@ def test_n1_select_flank_mode_vs_oracle(engine, oracle):
         np.testing.assert_allclose(out["sel_score"][w, :n], [s for _, s in want], rtol=RTOL_TIGHT)
 
 
+def test_n1_select_schedules_agree(engine, monkeypatch):
+    """The two-group pipeline (batches >= 2048 windows; forced here) and the plain round-by-round schedule (no fused
+    prologue) return bit for bit what the default schedule returns: same masks, same order, same scores."""
+    b1, v1 = synth.make_select_batch(160, n_vars=8, n_reads=32)
+    b2, v2 = synth.make_select_batch(90, n_vars=6, n_reads=32, window_offset=160)
+    sel = _abi.PlbSelectOptions.default(max_haplotypes=20, original_max_haplotypes=24)
+    for b, v in ((b1, v1), (b2, v2)):
+        base = engine.select_haplotypes(b, v, sel)
+        for env in ({"PLB_SELECT_GROUPS": "2"}, {"PLB_SELECT_NO_PROLOGUE": "1"}, {"PLB_SELECT_GROUPS": "2", "PLB_SELECT_NO_PROLOGUE": "1"}):
+            for k in ("PLB_SELECT_GROUPS", "PLB_SELECT_NO_PROLOGUE"):
+                monkeypatch.delenv(k, raising=False)
+            for k, val in env.items():
+                monkeypatch.setenv(k, val)
+            got = engine.select_haplotypes(b, v, sel)
+            for key in ("n_sel", "sel_mask", "n_scored"):
+                assert np.array_equal(got[key], base[key]), (env, key)
+            assert np.array_equal(got["sel_score"], base["sel_score"], equal_nan=True), env
+        for k in ("PLB_SELECT_GROUPS", "PLB_SELECT_NO_PROLOGUE"):
+            monkeypatch.delenv(k, raising=False)
+        assert np.all(base["n_sel"] == 19)
+
+
 def test_n1_select_synth_batch_vs_oracle(engine, oracle):
     """The bench workload's shape (8 variants, 64 reads of 150 bp, 250 bp reference segment, default options: 163 trial
     haplotypes per window in 8 rounds) on 600 windows with mixed variant counts and 2 individuals; 24 windows against
