@@ -352,8 +352,8 @@ typedef struct PlbSelectOut {
  * endBufferSize), with win_start / win_end / hap_start as everywhere) mutated by the variants in hap_mask[k]
  * (mask 0 = the reference haplotype itself).  Variants must lie inside [win_start, win_end].  Only the window
  * fields and the haplotype arrays of ref_batch are read.  hap_seq_off[n_haps+1] is always written (lengths are
- * computed on the host); the sequences are built on the GPU and written to hap_seq unless it is NULL; `capacity`
- * = bytes available in hap_seq.
+ * computed on the host); the sequences are built on the GPU and written to hap_seq unless it is NULL (ctx may then be
+ * NULL as well: no GPU work); `capacity` = bytes available in hap_seq.
  */
 int plb_build_haplotypes_host(PlbContext* ctx, const PlbWindowBatch* ref_batch, const PlbVariantSet* vars,
                               int32_t n_haps, const int32_t* hap_win, const uint64_t* hap_mask,

@@ -21,6 +21,10 @@
  *                                                             vs computeGenotypeCallAndLikelihoods, the function's
  *                                                             own lines of src/cython/vcfutils.pyx:163-334 excerpted
  *                                                             at build time (oracle/_ref/n4_ref*.so)
+ *   N1  oracle/select_oracle.py (Python: haplotype construction, isHaplotypeValid, computeBestScoreForGenotype,
+ *       getFilteredHaplotypes)                                vs the functions' own lines of src/cython/variantFilter.pyx:237-283,
+ *                                                             377-506 and platypusutils.pyx:735-802 excerpted at build time
+ *                                                             (oracle/_ref/n1_ref*.so), on the reference's Variant / Haplotype objects
  * Still restated without a reference run ("parity unpinned"): only the few lines of outputCallToVCF that turn
  * those posteriors into phred values, the GT fallback rules and log10 GLs (vcfutils.pyx:504-548; inline in a
  * function that writes VCF through the reference's Python-2 I/O stack).

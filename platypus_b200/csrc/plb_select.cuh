@@ -379,7 +379,9 @@ extern "C" int plb_select_stats(PlbContext*, double* out, int n) {   // the stat
 extern "C" int plb_build_haplotypes_host(PlbContext* c, const PlbWindowBatch* rb, const PlbVariantSet* vs, int32_t n_haps,
                                          const int32_t* hap_win, const uint64_t* hap_mask, int64_t* hap_seq_off,
                                          uint8_t* hap_seq, int64_t capacity) {
-    if (!c || n_haps < 0 || (n_haps > 0 && (!hap_win || !hap_mask)) || !hap_seq_off) return set_err(PLB_ERR_ARG, "NULL / bad argument");
+    // ctx may be NULL when only the offsets are wanted (hap_seq == NULL): the lengths are computed on the host
+    if ((!c && hap_seq) || n_haps < 0 || (n_haps > 0 && (!hap_win || !hap_mask)) || !hap_seq_off)
+        return set_err(PLB_ERR_ARG, "NULL / bad argument");
     SelHost sh;
     int rc = check_variants(rb, vs, sh);
     if (rc) return rc;

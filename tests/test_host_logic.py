@@ -186,3 +186,28 @@ def test_n1_two_group_pipeline_matches_single_group(monkeypatch):
         assert np.array_equal(np.nan_to_num(res[0]["sel_score"]), np.nan_to_num(res[1]["sel_score"]))
         assert np.all(res[0]["n_sel"] == 11)
         outs.append(res[0])
+
+
+def test_n1_haplotype_lengths_on_host(golden_dir):
+    """plb_build_haplotypes_host with hap_seq = NULL only sizes the haplotypes (host walk of getMutatedSequence, no GPU):
+    the offsets must be the lengths of the reference's own Haplotype.cHaplotypeSequence (tests/golden/n1_ref.npz)."""
+    lib = _lib()
+    gold = cases.n1_golden_cases(golden_dir)
+    cs = [cases.n1_window_case(g["seed"], g["drop"]) for g in gold]
+    batch, vset = cases.n1_batch(cs, [g["ref_seq"] for g in gold], [g["hap_start"] for g in gold])
+    hap_win, hap_mask, want = [], [], []
+    for k, g in enumerate(gold):
+        hap_win.append(k)
+        hap_mask.append(0)
+        want.append(len(g["ref_seq"]))
+        for m, seq in zip(g["sel_mask"], g["hap_seqs"]):
+            hap_win.append(k)
+            hap_mask.append(m)
+            want.append(len(seq))
+    hw, hm = np.asarray(hap_win, np.int32), np.asarray(hap_mask, np.uint64)
+    off = np.zeros(len(hw) + 1, np.int64)
+    s_, v_ = batch.as_struct(), vset.as_struct()
+    rc = lib.plb_build_haplotypes_host(None, C.byref(s_), C.byref(v_), len(hw), _abi.ptr(hw), _abi.ptr(hm), _abi.ptr(off), None, 0)
+    assert rc == 0, lib.plb_last_error()
+    assert np.array_equal(np.diff(off), want)
+    assert len(want) > 1000
