@@ -187,7 +187,7 @@ def best_scores(w, var_sets, target_coverage=30, opt=None):
 
 
 def select_haplotypes(w, max_haplotypes=50, original_max_haplotypes=50, max_variants=8, filter_by_coverage=1,
-                      target_coverage=30, opt=None, trace=None):
+                      target_coverage=30, opt=None, trace=None, score_fn=None):
     """getFilteredHaplotypes (variantFilter.pyx:377-506).  Returns the variant-index tuple of every haplotype it
     returns, in order, and the score it was kept with (None in the enumerate-everything branch)."""
     orig_cap = original_max_haplotypes - 1
@@ -211,7 +211,8 @@ def select_haplotypes(w, max_haplotypes=50, original_max_haplotypes=50, max_vari
                 trials.append(both)
         # scoring a trial does not depend on the heap, so the round's trials are scored together; the heap
         # operations below then run in the reference's order
-        scores = best_scores(w, trials, target_coverage, opt)
+        # score_fn (tests of the bookkeeping alone): a stand-in for computeBestScoreForGenotype, called per variant tuple
+        scores = [score_fn(vs) for vs in trials] if score_fn else best_scores(w, trials, target_coverage, opt)
         if trace is not None:
             trace.append([(tuple(v.idx for v in vs), s) for vs, s in zip(trials, scores)])
         for vs, s in zip(trials, scores):

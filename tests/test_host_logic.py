@@ -211,3 +211,64 @@ def test_n1_haplotype_lengths_on_host(golden_dir):
     assert rc == 0, lib.plb_last_error()
     assert np.array_equal(np.diff(off), want)
     assert len(want) > 1000
+
+
+def test_n1_bookkeeping_stress_with_tied_scores(oracle):
+    """The library's heap / sort / tuple-order replay against CPython's own heapq and sorted (oracle/select_oracle.py) on
+    random windows built to provoke the awkward cases: scores drawn from a handful of values (ties everywhere), several
+    alleles at one position (unequal variants of which neither is 'less'), SNP + indel at one base, overlapping deletions
+    (invalid combinations), heap capacities from 2 to 63 with maxHaplotypes above and below originalMaxHaplotypes."""
+    import random
+    from oracle import select_oracle as S
+    from platypus_b200.batch import VariantSet, Window, WindowBatch
+    from platypus_b200.engine import Engine
+    lib = _lib()
+    rng = random.Random(11)
+    n_checked = 0
+    for trial in range(250):
+        ws = 1000
+        we = ws + 40
+        variants, pos = [], ws + 1
+        while len(variants) < rng.randint(4, 10) and pos < we - 6:
+            kind = rng.random()
+            if kind < 0.45:
+                for alt in sorted(rng.sample([b"A", b"C", b"G", b"T"], rng.choice([1, 2, 3]))):
+                    variants.append((pos, b"N", alt))
+            elif kind < 0.65:
+                variants.append((pos, b"", b"ACG"[:rng.randint(1, 3)]))
+            elif kind < 0.85:
+                variants.append((pos, b"N" * rng.randint(1, 5), b""))
+            else:
+                variants.append((pos, b"NN", b"AC"))
+            pos += rng.choice([0, 0, 1, 2, 3, 6])
+
+        def vtype(v):
+            nr, na = len(v[1]), len(v[2])
+            return (0 if na == 1 else 1) if nr == na else 2 if nr == 0 else 3 if na == 0 else 4
+        uniq = sorted(set(variants), key=lambda v: (v[0], vtype(v), len(v[1])))
+        # equal keys keep a fixed order; drop exact duplicates of (pos, nRemoved, added)
+        seen, vs = set(), []
+        for v in uniq:
+            k = (v[0], len(v[1]), v[2])
+            if k not in seen:
+                seen.add(k)
+                vs.append((v[0], v[1], v[2], rng.choice([1, 1, 2, 3, 5])))
+        vs = vs[:12]
+        orig = rng.choice([3, 4, 6, 9, 17, 33, 50, 64])
+        mx = rng.choice([orig, orig, max(2, orig - rng.randint(1, 3)), orig + rng.randint(1, 4)])
+        levels = rng.choice([1, 2, 3, 7])
+        salt = rng.randrange(1 << 30)
+
+        def score_of_mask(m):
+            return -float((m * 2654435761 + salt) % (1 << 32) % levels)
+        ref = bytes(rng.choice(b"ACGT") for _ in range(240))
+        w = S.SelectWindow(ref, ws, we, ws - 100, vs, [[]])
+        want = S.select_haplotypes(w, mx, orig, 8, 0, 30, score_fn=lambda t: score_of_mask(sum(1 << v.idx for v in t)))
+        batch = WindowBatch.from_windows([Window(ws, we, ws - 100, [ref], [([], [], [])])], 1)
+        sel = _abi.PlbSelectOptions(mx, orig, 8, 0, 30)
+        got = Engine.select_replay(batch, VariantSet.from_lists([vs]), lambda hw, hm: [score_of_mask(int(m)) for m in hm], sel,
+                                   max_sel=4096, lib=lib)
+        n = int(got["n_sel"][0])
+        assert [int(m) for m in got["sel_mask"][0, :n]] == cases.masks_of([s_ for s_, _ in want]), (trial, orig, mx, levels)
+        n_checked += n
+    assert n_checked > 1500
