@@ -598,7 +598,7 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
 
     // ---- per group: the sampled-read batch (variantFilter.pyx:253-277: every sampleRate-th good read), reads as
     //      broken mates, and the variant tables
-    for (int g = 0; g < n_groups; ++g) {
+    auto build_group = [&](int g) -> int {
         SelPlan& P = groups[(size_t)g];
         const int Wf = (int)P.filt.size();
         P.gid = g;
@@ -783,10 +783,8 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
         }
         P.trial_mask.resize((size_t)Wf * max_trials);
         P.n_trials.resize((size_t)Wf);
-    }
-    for (int g = 0; g < n_groups; ++g) {
-        SelPlan& P = groups[(size_t)g];
-        if ((rc = prepare(P))) return rc;
+        int rc_ = prepare(P);
+        if (rc_) return rc_;
         if (!P.r_hoff) {   // the scorer did not supply (pinned) memory for the per-round arrays
             P.own_hoff.resize((size_t)P.Wf + 1);
             P.own_hsoff.resize((size_t)P.Wf * max_trials + 1);
@@ -797,7 +795,8 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
             P.mask_c = P.own_mask.data();
             P.scores = P.own_scores.data();
         }
-    }
+        return PLB_OK;
+    };
 
     double t_host = 0, n_trials_total = 0, tb_trials = 0, tb_len = 0, tb_heap = 0;
     int rounds = 0;
@@ -964,8 +963,9 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
         const SelRound R{P.Wr, P.nh, P.r_hoff, P.r_hsoff, P.mask_c, P.n_trials.data()};
         return submit(P, R);
     };
-    for (auto& P : groups)
-        if ((rc = start(P))) return rc;
+    // group by group: the first group's launch is on the GPU while the second group's plan and read pool are built
+    for (int g = 0; g < n_groups; ++g)
+        if ((rc = build_group(g)) || (rc = start(groups[(size_t)g]))) return rc;
     for (bool any = true; any;) {
         any = false;
         for (auto& P : groups) {
