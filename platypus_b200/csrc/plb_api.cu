@@ -84,7 +84,6 @@ struct ChunkPlan {
     size_t a_smem = 0, d_smem = 0;
     int a_occ = 1, d_occ = 1;
     Block tiles_blk{nullptr, 0};
-    TileLists tl;
 };
 
 struct PlbDeviceBatch {
@@ -715,11 +714,13 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
     ch.h0 = hb->win_hap_off[w0];
     ch.h1 = hb->win_hap_off[w1];
     int max_read = 0, max_hap = 0, max_H = 0;
+    // plan sub-ranges of the chunk on several host threads; their tile lists are concatenated in window order
+    // straight into the pinned staging buffer below (no intermediate vector: the lists of a selection call are ~10 MB)
+    const int nw = w1 - w0;
+    const int parts = std::max(1, std::min(2 * host_threads(), nw / 128));
+    std::vector<TileLists> tls(parts);
+    std::vector<size_t> off_a((size_t)parts + 1, 0), off_d((size_t)parts + 1, 0);
     {
-        // plan sub-ranges of the chunk on several host threads, then concatenate in window order
-        const int nw = w1 - w0;
-        const int parts = std::max(1, std::min(2 * host_threads(), nw / 128));
-        std::vector<TileLists> tls(parts);
         std::vector<AnchorPlan> aps(parts);
         std::vector<DpPlan> dps(parts);
         std::vector<int> mr(parts, 0), mh(parts, 0), mH(parts, 0);
@@ -731,16 +732,9 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
         }
         memset(&ch.ap, 0, sizeof ch.ap);
         memset(&ch.dp, 0, sizeof ch.dp);
-        size_t na_ = 0, nd_ = 0;
         for (int p = 0; p < parts; ++p) {
-            na_ += tls[p].a.size();
-            nd_ += tls[p].d.size();
-        }
-        ch.tl.a.reserve(na_);
-        ch.tl.d.reserve(nd_);
-        for (int p = 0; p < parts; ++p) {
-            ch.tl.a.insert(ch.tl.a.end(), tls[p].a.begin(), tls[p].a.end());
-            ch.tl.d.insert(ch.tl.d.end(), tls[p].d.begin(), tls[p].d.end());
+            off_a[(size_t)p + 1] = off_a[(size_t)p] + tls[p].a.size();
+            off_d[(size_t)p + 1] = off_d[(size_t)p] + tls[p].d.size();
             AnchorPlan& A = ch.ap;
             const AnchorPlan& q = aps[p];
             A.max_slots = std::max(A.max_slots, q.max_slots);
@@ -761,8 +755,8 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
             max_hap = std::max(max_hap, mh[p]);
             max_H = std::max(max_H, mH[p]);
         }
-        ch.ap.n_tiles = (int)ch.tl.a.size();
-        ch.dp.n_tiles = (int)ch.tl.d.size();
+        ch.ap.n_tiles = (int)off_a[(size_t)parts];
+        ch.dp.n_tiles = (int)off_d[(size_t)parts];
     }
     {
         AnchorPlan& ap = ch.ap;
@@ -792,9 +786,11 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
     // Tail splitting: the tiles left over after the last full wave of the persistent DP grid would keep a
     // few CTAs busy for a whole tile time while the others idle.  Cut each of them into k pieces by slot
     // range (k <= 3: a piece still fills the CTA's threads about once) when that shortens the last wave.
+    std::vector<Tile> extra;   // the pieces of the split tail tiles
+    size_t keep_d = off_d[(size_t)parts];   // DP tiles taken as planned (the rest is replaced by `extra`)
     {
         const int G = c->n_sm * ch.d_occ;
-        const int T = (int)ch.tl.d.size();
+        const int T = (int)off_d[(size_t)parts];
         const int r = T % G;
         if (r > 0 && T > 0) {
             int best_k = 1;
@@ -807,30 +803,38 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
                 }
             }
             if (best_k > 1) {
-                std::vector<Tile> tail(ch.tl.d.end() - r, ch.tl.d.end());
-                ch.tl.d.resize((size_t)(T - r));
-                for (const Tile& t : tail) {
-                    const int64_t n = t.s1 - t.s0;
-                    const int k = (int)std::min<int64_t>(best_k, std::max<int64_t>(1, n));
-                    for (int j = 0; j < k; ++j) {
-                        Tile p = t;
-                        p.s0 = t.s0 + n * j / k;
-                        p.s1 = t.s0 + n * (j + 1) / k;
-                        if (p.s1 > p.s0) ch.tl.d.push_back(p);
+                keep_d = (size_t)(T - r);
+                for (int p = 0; p < parts; ++p) {   // the last r tiles, in order
+                    const size_t lo = std::max(keep_d, off_d[(size_t)p]), hi = off_d[(size_t)p + 1];
+                    for (size_t i = lo; i < hi; ++i) {
+                        const Tile& t = tls[p].d[i - off_d[(size_t)p]];
+                        const int64_t n = t.s1 - t.s0;
+                        const int k = (int)std::min<int64_t>(best_k, std::max<int64_t>(1, n));
+                        for (int j = 0; j < k; ++j) {
+                            Tile q = t;
+                            q.s0 = t.s0 + n * j / k;
+                            q.s1 = t.s0 + n * (j + 1) / k;
+                            if (q.s1 > q.s0) extra.push_back(q);
+                        }
                     }
                 }
-                ch.dp.n_tiles = (int)ch.tl.d.size();
+                ch.dp.n_tiles = (int)(keep_d + extra.size());
             }
         }
     }
-    const size_t na = ch.tl.a.size() * sizeof(Tile), nd = ch.tl.d.size() * sizeof(Tile);
+    const size_t na = off_a[(size_t)parts] * sizeof(Tile), nd = (keep_d + extra.size()) * sizeof(Tile);
     const size_t na_al = (na + 255) & ~(size_t)255;
     // stage through pinned memory: a copy from a pageable std::vector would block the host until
     // everything queued earlier on the stream (the sequence bytes) has been transferred
     uint8_t* stage = (uint8_t*)pin_alloc(c, na_al + nd + 16);
     if (!stage) return set_err(PLB_ERR_NOMEM, "pinned host allocation failed");
-    if (na) memcpy(stage, ch.tl.a.data(), na);
-    if (nd) memcpy(stage + na_al, ch.tl.d.data(), nd);
+#pragma omp parallel for schedule(static, 1) num_threads(host_threads()) if (parts > 1)
+    for (int p = 0; p < parts; ++p) {
+        if (!tls[p].a.empty()) memcpy(stage + off_a[(size_t)p] * sizeof(Tile), tls[p].a.data(), tls[p].a.size() * sizeof(Tile));
+        const size_t lo = off_d[(size_t)p], hi = std::min(off_d[(size_t)p + 1], keep_d);
+        if (hi > lo) memcpy(stage + na_al + lo * sizeof(Tile), tls[p].d.data(), (hi - lo) * sizeof(Tile));
+    }
+    if (!extra.empty()) memcpy(stage + na_al + keep_d * sizeof(Tile), extra.data(), extra.size() * sizeof(Tile));
     if (zero_copy) {
         ch.ap.tiles = (const Tile*)stage;
         ch.dp.tiles = (const Tile*)(stage + na_al);
