@@ -500,6 +500,7 @@ struct SelPlan {
     std::vector<SelEntryState> state;
     std::vector<uint64_t> trial_mask;
     std::vector<int> n_trials;
+    std::vector<int64_t> win_base;    // scratch of the offset computation
     int r = 0, Wr = 0, nh = 0;
     bool active = false;
     bool in_prologue = false;   // the launch in flight scores the trial sets of rounds 0 .. prologue-1 together
@@ -892,7 +893,37 @@ static int select_core(const PlbWindowBatch* rb, const PlbVariantSet* vs, const 
         if (bad_shape)
             return set_err(PLB_ERR_SHAPE, bad_shape == 1 ? "a trial haplotype is longer than 16384 (chaplotype.pyx:180-183)"
                                                          : "a trial haplotype is shorter than readLen + 15 (calign.pyx:256-259)");
-        for (int h = 0; h < nh; ++h) P.r_hsoff[(size_t)h + 1] += P.r_hsoff[(size_t)h];
+        // lengths -> offsets: per-window totals, a prefix over the windows, then every window's own running sum
+        {
+            std::vector<int64_t> lens_check;
+            if (check_len) lens_check.assign(P.r_hsoff + 1, P.r_hsoff + 1 + nh);
+            std::vector<int64_t>& base = P.win_base;
+            base.resize((size_t)Wr + 1);
+            base[0] = 0;
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (Wr > 256)
+            for (int k = 0; k < Wr; ++k) {
+                int64_t sum = 0;
+                for (int h = P.r_hoff[(size_t)k]; h < P.r_hoff[(size_t)k + 1]; ++h) sum += P.r_hsoff[(size_t)h + 1];
+                base[(size_t)k + 1] = sum;
+            }
+            for (int k = 0; k < Wr; ++k) base[(size_t)k + 1] += base[(size_t)k];
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (Wr > 256)
+            for (int k = 0; k < Wr; ++k) {
+                int64_t run = base[(size_t)k];
+                for (int h = P.r_hoff[(size_t)k]; h < P.r_hoff[(size_t)k + 1]; ++h) {
+                    run += P.r_hsoff[(size_t)h + 1];
+                    P.r_hsoff[(size_t)h + 1] = run;
+                }
+            }
+            if (check_len) {   // PLB_SELECT_CHECK=1: offsets must be the running sum of the lengths, window by window
+                int64_t run = 0;
+                for (int h = 0; h < nh; ++h) {
+                    run += lens_check[(size_t)h];
+                    if (P.r_hsoff[(size_t)h + 1] != run) return set_err(PLB_ERR_ARG, "internal: haplotype offsets inconsistent");
+                }
+                if (P.r_hsoff[0] != 0) return set_err(PLB_ERR_ARG, "internal: haplotype offsets inconsistent");
+            }
+        }
         const double th_b = now_ms();
         tb_len += th_b - th_a;
         t_host += th_b - th0;
