@@ -236,6 +236,28 @@ class WindowBatch:
         )
 
 
+def with_haplotypes(ref_batch: "WindowBatch", win_hap_off, hap_seqs, hap_masks, variants=None, var_prior=None) -> "WindowBatch":
+    """The batch of the window model after haplotype selection: the windows, slots and reads of `ref_batch`, with the
+    haplotype arrays replaced by `hap_seqs` (list of bytes in window order, the reference haplotype first - what
+    variantcaller.pyx:116-120 hands to Population.setup) and `hap_masks` (bit v = window variant v) as hap_var_mask."""
+    import dataclasses
+    lens = np.fromiter((len(h) for h in hap_seqs), np.int64, len(hap_seqs))
+    off = np.zeros(len(hap_seqs) + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    W = ref_batch.n_windows
+    b = dataclasses.replace(
+        ref_batch, win_hap_off=np.asarray(win_hap_off, np.int32), hap_seq_off=off,
+        hap_seq=np.frombuffer(b"".join(hap_seqs) + b"\0", np.uint8).copy(), _keep=[])
+    if variants is not None:
+        n_var = np.diff(variants.win_var_off).astype(np.int32)
+        mv = max(1, int(n_var.max()) if W else 1)
+        b.max_variants = mv
+        b.win_n_var = n_var
+        b.hap_var_mask = np.asarray(hap_masks, np.uint64)
+        b.var_prior = np.full((W, mv), 0.5) if var_prior is None else np.asarray(var_prior, np.float64)
+    return b
+
+
 def concat_batches(parts: Sequence["WindowBatch"]) -> "WindowBatch":
     """Concatenate batches window-wise (read pools are concatenated and re-indexed)."""
     parts = [p for p in parts if p.n_windows > 0]

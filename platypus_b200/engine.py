@@ -294,6 +294,24 @@ class Engine:
                                                              C.byref(o)))
         return arrs
 
+    def call_windows(self, ref_batch: WindowBatch, variants, sel=None, opt=None, var_prior=None):
+        """callVariantsInWindow for a batch of windows (reference: src/cython/variantcaller.pyx:74-141): haplotype
+        selection (getHaplotypesInWindow), haplotype construction, then Population.setup + call on
+        [reference haplotype] + selected haplotypes.  Returns (selection dict, the window-model batch, population dict)."""
+        from .batch import with_haplotypes
+        sel_out = self.select_haplotypes(ref_batch, variants, sel, opt)
+        W = ref_batch.n_windows
+        n_sel = sel_out["n_sel"].astype(np.int64)
+        hap_off = np.zeros(W + 1, np.int64)
+        np.cumsum(n_sel + 1, out=hap_off[1:])
+        hap_win = np.repeat(np.arange(W, dtype=np.int32), n_sel + 1)
+        hap_mask = np.zeros(int(hap_off[-1]), np.uint64)          # mask 0 = the reference haplotype, first in every window
+        for w in range(W):
+            hap_mask[hap_off[w] + 1:hap_off[w + 1]] = sel_out["sel_mask"][w, :n_sel[w]]
+        seqs = self.build_haplotypes(ref_batch, variants, hap_win, hap_mask)
+        batch = with_haplotypes(ref_batch, hap_off, seqs, hap_mask, variants, var_prior)
+        return sel_out, batch, self.population_run(batch, opt)
+
     @staticmethod
     def select_replay(ref_batch: WindowBatch, variants, score_fn, sel=None, max_sel=None, lib=None):
         """The selection loop's bookkeeping alone (plb_select_replay_host): score_fn(hap_win, hap_mask) -> scores is

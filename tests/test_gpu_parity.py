@@ -630,3 +630,32 @@ def test_n1_select_synth_batch_vs_oracle(engine, oracle):
         assert [int(m) for m in out["sel_mask"][w, :n]] == cases.masks_of([s for s, _ in want]), w
         if w < 500:
             np.testing.assert_allclose(out["sel_score"][w, :n], [s for _, s in want], rtol=RTOL_TIGHT)
+
+
+def test_call_windows_select_build_population_vs_oracle(engine, oracle):
+    """The chained flow of callVariantsInWindow on the GPU - selection loop, haplotype construction, window model - against
+    the same chain through the oracle: same haplotype lists, same sequences, genotype likelihoods / frequencies / calls /
+    variant posteriors within the tolerance."""
+    from oracle import select_oracle as S
+    from platypus_b200.batch import with_haplotypes
+    ref_batch, vset = synth.make_select_batch(24, n_vars=7, n_reads=20, read_len=100, n_individuals=2, seed=4242)
+    sel = _abi.PlbSelectOptions.default(max_haplotypes=10, original_max_haplotypes=10)
+    sel_out, batch, pop = engine.call_windows(ref_batch, vset, sel)
+    hap_off, seqs, masks = [0], [], []
+    for w in range(ref_batch.n_windows):
+        sw = S.window_from_batch(ref_batch, vset, w)
+        chosen = [()] + [s_ for s_, _ in S.select_haplotypes(sw, 10, 10, 8, 1, 30)]
+        for s_ in chosen:
+            seqs.append(S.build_haplotype(sw.ref_seq, sw.win_start, sw.win_end, sw.hap_start, tuple(sw.vars[i] for i in s_)))
+            masks.append(sum(1 << i for i in s_))
+        hap_off.append(len(seqs))
+    want_batch = with_haplotypes(ref_batch, hap_off, seqs, masks, vset)
+    assert np.array_equal(batch.win_hap_off, want_batch.win_hap_off)
+    assert np.array_equal(batch.hap_var_mask, want_batch.hap_var_mask)
+    assert np.array_equal(batch.hap_seq, want_batch.hap_seq) and np.array_equal(batch.hap_seq_off, want_batch.hap_seq_off)
+    want, _, _, _ = oracle.population_run(want_batch, max_haps=pop["max_haps"])
+    for k in ("gl", "freq", "em_post", "gof"):
+        np.testing.assert_allclose(pop[k], want[k], rtol=RTOL_TIGHT, atol=1e-300, err_msg=k)
+    assert np.array_equal(pop["call"], want["call"])
+    assert np.array_equal(pop["var_phred"], want["var_phred"])
+    assert np.all(sel_out["n_sel"] == 9) and batch.max_haps() == 10
