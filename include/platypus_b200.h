@@ -375,6 +375,14 @@ int plb_select_haplotypes_host(PlbContext* ctx, const PlbWindowBatch* ref_batch,
                                const PlbSelectOptions* sel, const PlbOptions* opt, PlbSelectOut* out);
 
 /*
+ * Replaces computeBestScoreForHaplotype (src/cython/variantFilter.pyx:212-234; used by getAllHLAHaplotypesInRegion, :698-706)
+ * for every haplotype of a batch: per individual the sum of Haplotype.alignSingleRead(read, False) over the good reads
+ * reads.windowStart..windowEnd (bad reads and broken mates are ignored), best individual; an individual without reads
+ * sums to 0.0, as in the reference.  score_out[n_haps].
+ */
+int plb_best_score_haplotypes_host(PlbContext* ctx, const PlbWindowBatch* batch, const PlbOptions* opt, double* score_out);
+
+/*
  * The host-side bookkeeping of plb_select_haplotypes_host alone (trial sets per round, isHaplotypeValid, the heap /
  * sort replay, the final ranking), with the score of every trial haplotype supplied by the caller: per round
  * `score` receives the trial haplotypes (window of the caller's batch + variant mask) and fills score_out (nonzero

@@ -187,8 +187,8 @@ def compute_genotype_call_and_likelihoods(int n_variants, int n_haps, freqs, gl_
 
 # N1: the haplotype selection loop.  variantFilter.pyx cimports platypusutils (the BAM I/O stack), so - as for N4 -
 # the three functions' own source lines are excerpted at build time into a scratch module between this header and
-# this footer: isHaplotypeValid (src/cython/platypusutils.pyx:735-802), computeBestScoreForGenotype
-# (src/cython/variantFilter.pyx:237-283) and getFilteredHaplotypes (variantFilter.pyx:377-506).  Nothing of them is
+# this footer: isHaplotypeValid (src/cython/platypusutils.pyx:735-802), computeBestScoreForHaplotype
+# (src/cython/variantFilter.pyx:212-234), computeBestScoreForGenotype (:237-283) and getFilteredHaplotypes (:377-506).  Nothing of them is
 # stored in the repo.
 N1_HEADER = """# cython: language_level=2
 # scratch module: header (declarations) + three functions of the reference, verbatim + forwarding defs
@@ -229,6 +229,10 @@ def compute_best_score_for_genotype(list readBuffers, Haplotype hap1, Haplotype 
 
 def is_haplotype_valid(tuple variants):
     return bool(isHaplotypeValid(variants))
+
+
+def compute_best_score_for_haplotype(list readBuffers, Haplotype hap):
+    return computeBestScoreForHaplotype(readBuffers, hap)
 """
 
 
@@ -351,6 +355,7 @@ def build_l3_ref(force=False):
         ulines = open(os.path.join(cy, "platypusutils.pyx")).read().split("\n")
         open(os.path.join(tmp, "n1_ref.pyx"), "w").write(
             N1_HEADER + excerpt(ulines, "cdef int isHaplotypeValid(") + "\n\n" +
+            excerpt(flines, "cdef double computeBestScoreForHaplotype(") + "\n\n" +
             excerpt(flines, "cdef double computeBestScoreForGenotype(") + "\n\n" +
             excerpt(flines, "cdef list getFilteredHaplotypes(") + N1_FOOTER)
         _run([sys.executable, "-m", "cython", "-2", "-X", "legacy_implicit_noexcept=True", "-I", tmp, "n1_ref.pyx", "-o", "n1_ref.c"],

@@ -338,7 +338,7 @@ def population_seq(list hap_seqs, int win_start, int win_end, int hap_start, lis
 
 def select_haplotypes(bytes genome, int win_start, int win_end, list variants, list per_ind_good, int max_read_len=150,
                       int max_haplotypes=50, int original_max_haplotypes=50, int max_variants=8, int filter_by_coverage=1,
-                      int coverage_sampling_level=30, int flank=0, list score_sets=None):
+                      int coverage_sampling_level=30, int flank=0, list score_sets=None, list hap_score_sets=None):
     """One window through the reference's haplotype selection loop (src/cython/variantFilter.pyx:377-506
     getFilteredHaplotypes, :237-283 computeBestScoreForGenotype; excerpted into oracle/_ref/n1_ref by oracle/build.py).
     variants: [(refPos, removed, added, nSupportingReads)] in the window's order; per_ind_good: per individual the
@@ -398,6 +398,12 @@ def select_haplotypes(bytes genome, int win_start, int win_end, list variants, l
                 scores.append(n1_ref.compute_best_score_for_genotype(buffers, ref_hap, hap, win_end - win_start,
                                                                      coverage_sampling_level))
             out["scores"] = scores
+        if hap_score_sets is not None:   # computeBestScoreForHaplotype (variantFilter.pyx:212-234) of Haplotype(set)
+            hscores = []
+            for idxs in hap_score_sets:
+                hap = Haplotype(name, win_start, win_end, tuple(vobjs[i] for i in idxs), fa, max_read_len, opts)
+                hscores.append(n1_ref.compute_best_score_for_haplotype(buffers, hap))
+            out["hap_scores"] = hscores
     finally:
         buffers = []
         for (a, n) in all_arrays:

@@ -10,6 +10,7 @@ Follows
     Variant.__init__ / __richcmp__            src/cython/variant.pyx:109-145, 282-353
     isHaplotypeValid                          src/cython/platypusutils.pyx:735-802
     Haplotype.__init__ / getMutatedSequence   src/cython/chaplotype.pyx:127-191, 397-449
+    computeBestScoreForHaplotype              src/cython/variantFilter.pyx:212-234
     computeBestScoreForGenotype               src/cython/variantFilter.pyx:237-283
     getFilteredHaplotypes                     src/cython/variantFilter.pyx:377-506
 Per-read log-likelihoods come from the C oracle (plo_window_loglik; the sampled reads are passed as broken mates, the
@@ -184,6 +185,24 @@ def best_scores(w, var_sets, target_coverage=30, opt=None):
             best = max(best, tot)
         scores.append(best)
     return scores
+
+
+def best_score_haplotypes(w, var_sets, opt=None):
+    """computeBestScoreForHaplotype(readBuffers, Haplotype(set)) (variantFilter.pyx:212-234) for every variant set: the
+    sum of alignSingleRead over ALL good reads of an individual, best individual (one without reads sums to 0.0)."""
+    reads = [list(r) for r in w.good]
+    seqs = [build_haplotype(w.ref_seq, w.win_start, w.win_end, w.hap_start, vs) for vs in var_sets]
+    ll = _loglik(w, reads, seqs, opt) if seqs else []
+    out = []
+    for k in range(len(var_sets)):
+        best = -1e20
+        for i, r in enumerate(reads):
+            tot = 0.0
+            for t in range(len(r)):
+                tot += ll[k][i][t]
+            best = max(best, tot)
+        out.append(best)
+    return out
 
 
 def select_haplotypes(w, max_haplotypes=50, original_max_haplotypes=50, max_variants=8, filter_by_coverage=1,

@@ -151,6 +151,8 @@ def declare(lib):
     lib.plb_select_haplotypes_host.argtypes = [_p, P(PlbWindowBatch), P(PlbVariantSet), P(PlbSelectOptions), P(PlbOptions),
                                                P(PlbSelectOut)]
     lib.plb_select_haplotypes_host.restype = C.c_int
+    lib.plb_best_score_haplotypes_host.argtypes = [_p, P(PlbWindowBatch), P(PlbOptions), _p]
+    lib.plb_best_score_haplotypes_host.restype = C.c_int
     lib.plb_select_replay_host.argtypes = [P(PlbWindowBatch), P(PlbVariantSet), P(PlbSelectOptions), TRIAL_SCORE_FN, _p,
                                            P(PlbSelectOut)]
     lib.plb_select_replay_host.restype = C.c_int
@@ -166,7 +168,7 @@ EXPORTED_SYMBOLS = [
     "plb_align_flank_batch_host", "plb_gap_open_host",
     "plb_window_loglik_host", "plb_population_run_host", "plb_site_genotypes_host", "plb_batch_upload", "plb_batch_free",
     "plb_run_device", "plb_last_stats", "plb_set_timing", "plb_kernel_times",
-    "plb_build_haplotypes_host", "plb_select_haplotypes_host", "plb_select_replay_host",
+    "plb_build_haplotypes_host", "plb_select_haplotypes_host", "plb_select_replay_host", "plb_best_score_haplotypes_host",
     "plb_select_stats",
 ]
 KERNEL_NAMES = ["k_prep", "k_anchor", "k_general", "k_dp", "k_genotype", "k_population"]

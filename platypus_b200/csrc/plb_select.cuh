@@ -153,6 +153,33 @@ __global__ void __launch_bounds__(128) k_trial_score(DevBatch b, const double* _
     if (lane == 0) out[h] = best;
 }
 
+// computeBestScoreForHaplotype (variantFilter.pyx:212-234) for every haplotype of a batch whose slots are the good reads:
+// per individual the per-read log-likelihoods are added in read order, best individual (one without reads sums to 0.0).
+__global__ void __launch_bounds__(128) k_hap_score(DevBatch b, const double* __restrict__ ll, int n_haps,
+                                                   double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int h = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (h >= n_haps) return;
+    const int w = b.hap_win[h];
+    const int hl = h - b.win_hap_off[w];
+    const int nInd = b.n_individuals;
+    double best = -1e20;
+    for (int i = 0; i < nInd; ++i) {
+        const int64_t wi = (int64_t)w * nInd + i;
+        const int T = (int)(b.wi_slot_off[wi + 1] - b.wi_slot_off[wi]);
+        const double* l = ll + b.ll_off[wi] + (int64_t)hl * T;
+        double tot = 0.0;
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int t = t0 + lane;
+            const double term = t < T ? l[t] : 0.0;
+            const int n = min(32, T - t0);
+            for (int k = 0; k < n; ++k) tot += __shfl_sync(0xffffffffu, term, k);
+        }
+        if (tot > best) best = tot;
+    }
+    if (lane == 0) out[h] = best;
+}
+
 }  // namespace plb
 
 namespace {
@@ -1238,5 +1265,56 @@ extern "C" int plb_select_haplotypes_host(PlbContext* c, const PlbWindowBatch* r
     g_sel_stats.v[2] = t_score;
     g_sel_stats.v[3] = t_reduce;
     g_sel_stats.v[7] = n_pairs_total;
+    return PLB_OK;
+}
+
+extern "C" int plb_best_score_haplotypes_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* opt_in,
+                                              double* score_out) {
+    if (!c || !hb || !score_out) return set_err(PLB_ERR_ARG, "NULL argument");
+    int rc = check_options(opt_in);
+    if (rc) return rc;
+    PlbOptions opt = *opt_in;
+    opt.use_mapq_cap = 0;   // alignSingleRead(read, False)
+    const int W = hb->n_windows, nInd = hb->n_individuals;
+    if (W <= 0 || hb->n_haps <= 0) return PLB_OK;
+    if ((rc = plb_validate(hb, &opt, 0))) return rc;
+    CU(cudaSetDevice(c->device));
+    // the good reads of every (window, individual), as broken mates: a bare alignReadToHaplotype per read
+    const int64_t nwi = (int64_t)W * nInd;
+    std::vector<int64_t> slot_off((size_t)nwi + 1, 0);
+    for (int64_t wi = 0; wi < nwi; ++wi) slot_off[(size_t)wi + 1] = slot_off[(size_t)wi] + hb->wi_n_good[wi];
+    std::vector<int32_t> slots((size_t)slot_off[(size_t)nwi]), zero((size_t)nwi, 0);
+    for (int64_t wi = 0; wi < nwi; ++wi)
+        for (int t = 0; t < hb->wi_n_good[wi]; ++t) slots[(size_t)slot_off[(size_t)wi] + t] = hb->slot_read[hb->wi_slot_off[wi] + t];
+    PlbWindowBatch g = *hb;
+    g.n_slots = slot_off[(size_t)nwi];
+    g.wi_slot_off = slot_off.data();
+    g.slot_read = slots.data();
+    g.wi_n_good = zero.data();
+    g.wi_n_bad = zero.data();
+    g.max_variants = 0;
+    g.win_n_var = nullptr;
+    g.hap_var_mask = nullptr;
+    g.var_prior = nullptr;
+    PlbDeviceBatch* db = nullptr;
+    if ((rc = plb_batch_upload(c, &g, &db))) return rc;
+    cudaStream_t st = c->stream;
+    Block out{nullptr, 0};
+    const bool modes = opt.calc_flank_score != 0;
+    rc = block_get(c, (size_t)g.n_haps * 8 + 256, &out);
+    if (!rc && modes) rc = mode_queues(c, db, false);
+    if (!rc) rc = launch_windows(c, db, db->chunks[0], &opt, nullptr, nullptr, st, false, modes ? db->mq : db->q);
+    if (!rc) {
+        k_hap_score<<<(g.n_haps + 3) / 4, 128, 0, st>>>(db->d, db->ll_scratch, g.n_haps, (double*)out.p);
+        rc = launch_check(c, "k_hap_score");
+    }
+    cudaError_t e = cudaSuccess;
+    if (!rc) e = cudaMemcpyAsync(score_out, out.p, (size_t)g.n_haps * 8, cudaMemcpyDeviceToHost, st);
+    const cudaError_t e2 = cudaStreamSynchronize(st);
+    if (out.p) block_put(c, out);
+    plb_batch_free(c, db);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess)
+        return set_err(PLB_ERR_CUDA, "plb_best_score_haplotypes_host: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
     return PLB_OK;
 }

@@ -294,6 +294,15 @@ class Engine:
                                                              C.byref(o)))
         return arrs
 
+    def best_score_haplotypes(self, batch: WindowBatch, opt=None):
+        """computeBestScoreForHaplotype for every haplotype of the batch (reference: src/cython/variantFilter.pyx:212-234):
+        sum of alignSingleRead over an individual's good reads, best individual.  Returns [n_haps] float64."""
+        opt = opt or _abi.PlbOptions.default()
+        out = np.zeros(max(batch.n_haps, 1), np.float64)
+        s = batch.as_struct()
+        _check(self.lib, self.lib.plb_best_score_haplotypes_host(self.ctx, C.byref(s), C.byref(opt), _abi.ptr(out)))
+        return out[:batch.n_haps]
+
     def call_windows(self, ref_batch: WindowBatch, variants, sel=None, opt=None, var_prior=None):
         """callVariantsInWindow for a batch of windows (reference: src/cython/variantcaller.pyx:74-141): haplotype
         selection (getHaplotypesInWindow), haplotype construction, then Population.setup + call on

@@ -594,6 +594,7 @@ def n1_golden_cases(golden_dir):
         out.append(dict(seed=int(seed), drop=int(z["drop"][k]), ref_seq=z["ref_seq"][z["ref_off"][k]:z["ref_off"][k + 1]].tobytes(),
                         hap_start=int(z["hap_start"][k]), sel_mask=[int(m) for m in z["sel_mask"][a:b]], hap_seqs=seqs,
                         trial_mask=[int(m) for m in z["trial_mask"][t0:t1]], trial_score=z["trial_score"][t0:t1],
+                        hap_score=z["hap_score"][a:b], ref_hap_score=float(z["ref_hap_score"][k]),
                         opts={k2: int(z["opt_" + k2][k]) for k2 in ("max_haplotypes", "original_max_haplotypes", "max_variants",
                                                                    "filter_by_coverage", "coverage_sampling_level")}))
     return out

@@ -6,6 +6,7 @@ reference's own getFilteredHaplotypes / computeBestScoreForGenotype / isHaplotyp
 are tests/cases.py n1_window_case(seed, drop); this file stores what the REFERENCE returns for them:
   ref_seq / hap_start   the reference haplotype (Haplotype(..., variants=()))
   sel_mask, hap_seq     the variant sets getFilteredHaplotypes returns, in order, and Haplotype.cHaplotypeSequence of each
+  hap_score             computeBestScoreForHaplotype of the reference haplotype (ref_hap_score) and of every selected one
   trial_mask / score    every trial set the rounds score (in the order they are scored) with the reference's
                         computeBestScoreForGenotype value
 """
@@ -28,7 +29,7 @@ DROP = [0] * 72 + [1] * 12 + [2] * 12      # cases.n1_window_case(seed, drop): a
 def main():
     ref = O.ref_l3()
     assert ref is not None, "needs /root/reference (oracle/build.py)"
-    d = {k: [] for k in ("ref_seq", "hap_start", "sel_mask", "hap_seq", "trial_mask", "trial_score")}
+    d = {k: [] for k in ("ref_seq", "hap_start", "sel_mask", "hap_seq", "trial_mask", "trial_score", "hap_score", "ref_hap_score")}
     ref_off, sel_off, hs_off, trial_off = [0], [0], [0], [0]
     opts = {k: [] for k in ("max_haplotypes", "original_max_haplotypes", "max_variants", "filter_by_coverage", "coverage_sampling_level")}
     for seed, drop in zip(SEEDS, DROP):
@@ -46,6 +47,11 @@ def main():
         sets = [vs for rnd in tr for (vs, _) in rnd]
         scores = ref.select_haplotypes(*args, 0, sets)["scores"] if sets else []
         assert scores == [s for rnd in tr for (_, s) in rnd], seed
+        # computeBestScoreForHaplotype (variantFilter.pyx:212-234) of the reference haplotype and of every selected one
+        hs = ref.select_haplotypes(*args, 0, None, [()] + r["selected"])["hap_scores"]
+        assert hs == S.best_score_haplotypes(w, [()] + [tuple(w.vars[i] for i in s_) for s_ in r["selected"]]), seed
+        d["ref_hap_score"].append(hs[0])
+        d["hap_score"] += hs[1:]
         d["ref_seq"].append(np.frombuffer(r["ref_seq"], np.uint8))
         ref_off.append(ref_off[-1] + len(r["ref_seq"]))
         d["hap_start"].append(r["hap_start"])
@@ -65,7 +71,8 @@ def main():
         sel_mask=np.asarray(d["sel_mask"], np.uint64), sel_off=np.asarray(sel_off, np.int64),
         hap_seq=np.concatenate(d["hap_seq"]), hap_seq_off=np.asarray(hs_off, np.int64),
         trial_mask=np.asarray(d["trial_mask"], np.uint64), trial_score=np.asarray(d["trial_score"], np.float64),
-        trial_off=np.asarray(trial_off, np.int64), **{"opt_" + k: np.asarray(v, np.int32) for k, v in opts.items()})
+        trial_off=np.asarray(trial_off, np.int64), hap_score=np.asarray(d["hap_score"], np.float64),
+        ref_hap_score=np.asarray(d["ref_hap_score"], np.float64), **{"opt_" + k: np.asarray(v, np.int32) for k, v in opts.items()})
     print("windows", len(SEEDS), "selected", sel_off[-1], "trials", trial_off[-1])
 
 

@@ -560,6 +560,23 @@ def test_n1_select_golden_ref(engine, golden_dir):
     assert n_sel > 500
 
 
+def test_n1_best_score_haplotypes_golden_ref(engine, golden_dir):
+    """plb_best_score_haplotypes_host vs the reference's computeBestScoreForHaplotype (variantFilter.pyx:212-234) on the
+    reference haplotype and every selected haplotype of the golden windows (some individuals / windows have no reads)."""
+    from platypus_b200.batch import with_haplotypes
+    n = 0
+    for group, batch, vset, _ in _n1_groups(golden_dir):
+        hap_off, seqs, want = [0], [], []
+        for g in group:
+            seqs += [g["ref_seq"]] + g["hap_seqs"]
+            want += [g["ref_hap_score"]] + list(g["hap_score"])
+            hap_off.append(len(seqs))
+        got = engine.best_score_haplotypes(with_haplotypes(batch, hap_off, seqs, None))
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+        n += len(want)
+    assert n > 1000
+
+
 def test_n1_select_flank_mode_vs_oracle(engine, oracle):
     """options.calculateFlankScore reaches alignSingleRead inside the selection loop as well (chaplotype.pyx:384)."""
     from oracle import select_oracle as S

@@ -505,6 +505,7 @@ def _n1_oracle_run(c, ref_seq, hap_start):
 
 def test_golden_n1_ref(oracle, golden_dir):
     """Selection oracle vs the reference's getFilteredHaplotypes / computeBestScoreForGenotype / Haplotype outputs."""
+    from oracle.select_oracle import best_score_haplotypes as S_best
     gold = cases.n1_golden_cases(golden_dir)
     assert len(gold) >= 60
     n_filter = n_tied = 0
@@ -515,6 +516,9 @@ def test_golden_n1_ref(oracle, golden_dir):
         assert seqs == g["hap_seqs"], g["seed"]
         assert cases.masks_of(sets) == g["trial_mask"], g["seed"]
         assert scores == list(g["trial_score"]), g["seed"]          # bit for bit: same libm, same order of additions
+        w = cases.n1_select_window(c, g["ref_seq"], g["hap_start"])
+        hs = S_best(w, [()] + [tuple(w.vars[i] for i in s_) for s_ in sel])
+        assert hs == [g["ref_hap_score"]] + list(g["hap_score"]), g["seed"]      # computeBestScoreForHaplotype, bit for bit
         n_filter += bool(sets)
         n_tied += len(scores) - len(set(scores))
     assert n_filter >= 40 and n_tied >= 100    # the fixture exercises the heap rounds and exactly tied scores
