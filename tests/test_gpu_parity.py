@@ -500,12 +500,15 @@ def test_n4_golden_ref(engine, golden_dir):
 def _n1_groups(golden_dir):
     by_opts = {}
     for g in cases.n1_golden_cases(golden_dir):
-        by_opts.setdefault(tuple(sorted(g["opts"].items())), []).append(g)
+        # windows of one batch share the options and the number of individuals (no padding individuals: one without reads
+        # scores 0.0 in computeBestScoreForHaplotype)
+        n_ind = len(cases.n1_window_case(g["seed"], g["drop"])["per_ind"])
+        by_opts.setdefault((n_ind,) + tuple(sorted(g["opts"].items())), []).append(g)
     out = []
     for key, group in by_opts.items():
         cs = [cases.n1_window_case(g["seed"], g["drop"]) for g in group]
         batch, vset = cases.n1_batch(cs, [g["ref_seq"] for g in group], [g["hap_start"] for g in group])
-        o = dict(key)
+        o = dict(key[1:])
         sel = _abi.PlbSelectOptions(o["max_haplotypes"], o["original_max_haplotypes"], o["max_variants"], o["filter_by_coverage"],
                                     o["coverage_sampling_level"])
         out.append((group, batch, vset, sel))
@@ -572,7 +575,7 @@ def test_n1_best_score_haplotypes_golden_ref(engine, golden_dir):
             want += [g["ref_hap_score"]] + list(g["hap_score"])
             hap_off.append(len(seqs))
         got = engine.best_score_haplotypes(with_haplotypes(batch, hap_off, seqs, None))
-        np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+        np.testing.assert_allclose(got, want, rtol=1e-10, atol=0)
         n += len(want)
     assert n > 1000
 
