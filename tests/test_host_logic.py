@@ -272,3 +272,32 @@ def test_n1_bookkeeping_stress_with_tied_scores(oracle):
         assert [int(m) for m in got["sel_mask"][0, :n]] == cases.masks_of([s_ for s_, _ in want]), (trial, orig, mx, levels)
         n_checked += n
     assert n_checked > 1500
+
+
+def test_with_haplotypes_builds_a_valid_window_model_batch(oracle):
+    """batch.with_haplotypes (the window-model batch after selection: reads of the reference batch, [reference] + selected
+    haplotypes, masks as hap_var_mask) passes the library's host-side validation and runs through the oracle's window model."""
+    from oracle import select_oracle as S
+    from platypus_b200.batch import with_haplotypes
+    lib = _lib()
+    ref_batch, vset = synth.make_select_batch(5, n_vars=6, n_reads=12, read_len=80, n_individuals=2, seed=99)
+    hap_off, seqs, masks = [0], [], []
+    for w in range(ref_batch.n_windows):
+        sw = S.window_from_batch(ref_batch, vset, w)
+        for s_ in [()] + [x for x, _ in S.select_haplotypes(sw, 6, 6, 8, 1, 30)]:
+            seqs.append(S.build_haplotype(sw.ref_seq, sw.win_start, sw.win_end, sw.hap_start, tuple(sw.vars[i] for i in s_)))
+            masks.append(sum(1 << i for i in s_))
+        hap_off.append(len(seqs))
+    b = with_haplotypes(ref_batch, hap_off, seqs, masks, vset)
+    assert b.n_haps == 30 and b.max_haps() == 6 and b.max_variants == 6
+    assert b.read_seq is ref_batch.read_seq and b.slot_read is ref_batch.slot_read      # reads are shared, not copied
+    s_ = b.as_struct()
+    opt = _abi.PlbOptions.default()
+    assert lib.plb_validate(C.byref(s_), C.byref(opt), 6) == 0, lib.plb_last_error()
+    want, _, _, _ = oracle.population_run(b, max_haps=6)
+    assert want["gl"].shape == (5, 2, 21) and np.all(np.isfinite(want["freq"]))
+    np.testing.assert_allclose(want["freq"].sum(axis=1), 1.0, rtol=1e-12)
+    # the sharded view of the variants used by run_select_sharded
+    part = vset.slice_windows(2, 5)
+    assert part.win_var_off[0] == 0 and part.n_vars(0) == vset.n_vars(2)
+    assert np.array_equal(part.var_pos, vset.var_pos[vset.win_var_off[2]:vset.win_var_off[5]])
