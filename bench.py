@@ -27,6 +27,10 @@ Nothing here reads /root/reference at run time.
 import argparse
 import json
 import os
+
+# the library's host threads (tile planning) sleep between calls instead of spinning next to the other ranks' threads;
+# libgomp reads this when it is loaded, i.e. before torch / numpy are imported
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 import statistics
 import subprocess
 import sys
@@ -529,15 +533,41 @@ def run_ours(args, rank, world, local_rank):
         ll = torch.zeros((n_pairs,), dtype=torch.float64, device=dev)
         ptrs = {k: v.data_ptr() for k, v in out.items()}
         ptrs["max_haps"] = Hm
+        # The one collective of the path: all-gather of the per-window genotype likelihoods.  It runs on a side stream
+        # behind an event, so the next step's kernels start while this step's block travels; the likelihoods alternate
+        # between two buffers (step k+2 reuses step k's buffer and waits for that gather).
         gl_all = torch.zeros((world, W, nI, Gm), dtype=torch.float64, device=dev) if world > 1 else None
+        gl_bufs = [out["gl"], torch.zeros_like(out["gl"])] if world > 1 else [out["gl"]]
+        ptr_sets = []
+        for g in gl_bufs:
+            q = dict(ptrs)
+            q["gl"] = g.data_ptr()
+            ptr_sets.append(q)
+        side = torch.cuda.Stream(device=dev) if world > 1 else None
+        computed = [torch.cuda.Event() for _ in gl_bufs]
+        gathered = [torch.cuda.Event() for _ in gl_bufs]
+        n_step = [0]
 
         def step():
-            eng.run_device(handle, ptrs, ll_ptr=ll.data_ptr(), opt=OPT)
-            if world > 1:  # the one collective of the path: gather per-window genotype likelihoods
-                dist.all_gather_into_tensor(gl_all, out["gl"])
+            k = n_step[0] % len(gl_bufs)
+            if world > 1 and n_step[0] >= len(gl_bufs):
+                stream.wait_event(gathered[k])
+            eng.run_device(handle, ptr_sets[k], ll_ptr=ll.data_ptr(), opt=OPT)
+            if world > 1:
+                computed[k].record(stream)
+                side.wait_event(computed[k])
+                with torch.cuda.stream(side):
+                    dist.all_gather_into_tensor(gl_all, gl_bufs[k])
+                    gathered[k].record(side)
+            n_step[0] += 1
+
+        def join_side():
+            if world > 1:
+                stream.wait_stream(side)
 
         for _ in range(max(args.warmup, 3)):
             step()
+        join_side()
         stream.synchronize()
         if world > 1:
             dist.barrier()
@@ -551,6 +581,7 @@ def run_ours(args, rank, world, local_rank):
         e0.record(stream)
         for _ in range(args.steps):
             step()
+        join_side()          # the timed region ends when the last gather has landed
         e1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
@@ -566,30 +597,75 @@ def run_ours(args, rank, world, local_rank):
             cells = stats["cells"]
         assert stats["cells"] == cells, (stats, cells)
 
-        # ---- e2e: C-ABI host entry point, pinned host buffers, copies inside the timed region ----
+        # ---- e2e: the C-ABI host entry points, pinned HOST buffers, every copy inside the timed region ----
+        # A region loop keeps two batches in flight (plb_population_submit / plb_population_wait): batch k+1 travels
+        # over PCIe while batch k computes.  Inputs are the staged form of the reads (2-bit bases + 8-bit qualities,
+        # batch.pack(): what the N3 staging step produces from BAM nibbles); --ascii sends the byte-per-base arrays.
+        if world > 1:
+            assert torch.equal(gl_all[rank], gl_bufs[(n_step[0] - 1) % len(gl_bufs)])   # the gathered block is this rank's block
+        src = batch if args.ascii else batch.pack()
         pinned = {}
-        hb = type(batch)(**{f: (pin(getattr(batch, f)).numpy() if isinstance(getattr(batch, f), np.ndarray) else getattr(batch, f))
+        hb = type(batch)(**{f: (pin(getattr(src, f)).numpy() if isinstance(getattr(src, f), np.ndarray) else getattr(src, f))
                             for f in batch.__dataclass_fields__ if f != "_keep"})
-        host_out = {"max_haps": Hm}
-        for k, v in out.items():
-            pinned[k] = torch.zeros(v.shape, dtype=v.dtype).pin_memory()
-            host_out[k] = pinned[k].numpy()
+        host_outs = []
+        for j in range(2):
+            ho = {"max_haps": Hm}
+            for k, v in out.items():
+                pinned[(k, j)] = torch.zeros(v.shape, dtype=v.dtype).pin_memory()
+                ho[k] = pinned[(k, j)].numpy()
+            host_outs.append(ho)
         h2d = hb.input_nbytes()
-        d2h = sum(int(v.numel() * v.element_size()) for v in pinned.values())
-        for _ in range(2):
-            eng.population_run(hb, out=host_out, opt=OPT)
+        d2h = sum(int(v.numel() * v.element_size()) for (k, j), v in pinned.items() if j == 0)
+        gl_dev = [torch.zeros_like(out["gl"]) for _ in range(2)]
+        e2e_gathered = [torch.cuda.Event() for _ in range(2)]
+
+        def finish(job, j, n_done):
+            eng.population_wait(job)
+            if world > 1:   # the step's genotype likelihoods join the other ranks' (side stream; next job keeps running)
+                if n_done >= 2:
+                    e2e_gathered[j].synchronize()
+                with torch.cuda.stream(side):
+                    gl_dev[j].copy_(pinned[("gl", j)], non_blocking=True)
+                    dist.all_gather_into_tensor(gl_all, gl_dev[j])
+                    e2e_gathered[j].record(side)
+
+        def e2e_run(n):
+            jobs, each, t_prev, n_done = [], [], time.perf_counter(), 0
+            for i in range(n):
+                jobs.append((eng.population_submit(hb, out=host_outs[i % 2], opt=OPT), i % 2))
+                if len(jobs) == 2:
+                    finish(*jobs.pop(0), n_done)
+                    n_done += 1
+                    t = time.perf_counter()
+                    each.append(round((t - t_prev) * 1e3, 3))
+                    t_prev = t
+            while jobs:
+                finish(*jobs.pop(0), n_done)
+                n_done += 1
+                t = time.perf_counter()
+                each.append(round((t - t_prev) * 1e3, 3))
+                t_prev = t
+            if world > 1:
+                side.synchronize()
+            return each
+
+        e2e_run(3)
+        single = []
+        for _ in range(3):   # one call alone (no second batch in flight): the latency of plb_population_run_host
+            t1 = time.perf_counter()
+            eng.population_run(hb, out=host_outs[0], opt=OPT)
+            single.append(round((time.perf_counter() - t1) * 1e3, 3))
         if world > 1:
             dist.barrier()
+        e2e_steps = max(4, min(args.steps, 20))
         t0 = time.perf_counter()
-        e2e_steps = max(3, min(args.steps, 10))
-        e2e_each = []
-        for _ in range(e2e_steps):
-            t1 = time.perf_counter()
-            eng.population_run(hb, out=host_out, opt=OPT)
-            e2e_each.append(round((time.perf_counter() - t1) * 1e3, 3))
+        e2e_each = e2e_run(e2e_steps)
         e2e_s = (time.perf_counter() - t0) / e2e_steps
         # parity guard: the host path and the device path must agree bit for bit
-        assert np.array_equal(host_out["gl"], out["gl"].cpu().numpy())
+        for ho in host_outs:
+            assert np.array_equal(ho["gl"], out["gl"].cpu().numpy())
+        if world > 1:
+            assert torch.equal(gl_all[rank], out["gl"])
 
     ms_step = ms_total / args.steps
     t_max = torch.tensor([ms_step, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -626,7 +702,7 @@ def run_ours(args, rank, world, local_rank):
                 "note": "integer-issue bound by construction (0.014 B/cell); see DESIGN.md for the issue-rate roofline"}
 
     cpu = None
-    if world == 1:
+    if world == 1 and not args.no_cpu:
         # The CPU baseline runs in a fresh process (this one holds a CUDA context; the baseline forks workers).
         cores = os.cpu_count() or 1
         try:
@@ -649,8 +725,10 @@ def run_ours(args, rank, world, local_rank):
         "config": workload_config(world, windows),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_ms, "ms_each_step": e2e_each,
-                "api": "plb_population_run_host (pinned host buffers)"},
+                "ms_per_step": e2e_ms, "ms_each_step": e2e_each, "steps": e2e_steps,
+                "single_call_ms": single, "input_format": "ascii" if args.ascii else "2-bit bases + 8-bit qualities (batch.pack)",
+                "api": "plb_population_submit / plb_population_wait, two batches in flight (pinned host buffers)%s"
+                       % ("; per step the likelihood block is all-gathered over NCCL" if world > 1 else "")},
         "gpu_launches": total_launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -675,7 +753,8 @@ def main():
                     help="2 = BASELINE config 2 (headline); 3 = ragged read/haplotype lengths (profiling only)")
     ap.add_argument("--stage", default="path", choices=["path", "select"],
                     help="path = the headline likelihood path; select = the haplotype selection loop before it (N1, one GPU)")
-    ap.add_argument("--no-cpu", action="store_true", help="--stage select: skip the CPU baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--ascii", action="store_true", help="e2e leg: send byte-per-base sequences instead of the packed form")
     args = ap.parse_args()
     if args.stage == "select":
         if int(os.environ.get("RANK", "0")) == 0:

@@ -21,14 +21,15 @@
 extern "C" {
 #endif
 
-#define PLB_ABI_VERSION 3
+#define PLB_ABI_VERSION 4
 
 /* status codes */
 #define PLB_OK              0
 #define PLB_ERR_ARG        -1   /* NULL pointer / inconsistent offsets                         */
 #define PLB_ERR_SHAPE      -2   /* limit exceeded (haplotype > 16384 bp, H > max_haps, ...)     */
 #define PLB_ERR_CUDA       -3   /* CUDA runtime error, no device, or kernel image missing       */
-#define PLB_ERR_UNSUPPORTED -4  /* option not implemented (none at present; kept for ABI stability) */
+#define PLB_ERR_UNSUPPORTED -4  /* entry point does not take this input format (2-bit packed batches: only the S2 / S3
+                                   window calls and the device-resident path read them)              */
 #define PLB_ERR_NOMEM      -5
 
 /* limits inherited from the reference */
@@ -117,7 +118,26 @@ typedef struct PlbWindowBatch {
     const uint64_t* hap_var_mask;/* [n_haps] bit v set iff window variant v is in hap.variants
                                     (the `var not in vsf` test, cpopulation.pyx:509-516)    */
     const double* var_prior;    /* [n_windows*max_variants] Variant.calculatePrior value    */
+
+    /* Packed bases (ABI 4; zero = the byte-per-base layout above).  With seq_format = PLB_SEQ_2BIT hap_seq and read_seq
+     * hold 2 bits per base - A 0, C 1, G 2, T 3; base i of the (concatenated) array sits at bits 2*(i & 3) of byte
+     * i >> 2 - which is what BAM's 4-bit nibbles (src/cython/htslibWrapper.pyx:414-416) pack into without ever
+     * becoming ASCII.  hap_seq_off / read_seq_off are unchanged: they count BASES (read_qual keeps one byte per base at
+     * the same offsets).  Every base that is not exactly 'A', 'C', 'G' or 'T' (N, IUPAC codes, lower case) is listed
+     * with its base index and its original byte; the packed code at that position is ignored.  Results are
+     * bit-identical to the ASCII call: the bytes are restored on the GPU before anything reads them.
+     * plb_pack_bases_host / plb_pack_nibbles_host produce this layout. */
+    int32_t seq_format;
+    int64_t n_read_exc;          /* exceptions of read_seq, ascending positions             */
+    const int64_t* read_exc_pos; /* [n_read_exc] base index into the read pool               */
+    const uint8_t* read_exc_chr; /* [n_read_exc] the byte the reference would see           */
+    int64_t n_hap_exc;
+    const int64_t* hap_exc_pos;
+    const uint8_t* hap_exc_chr;
 } PlbWindowBatch;
+
+#define PLB_SEQ_ASCII 0
+#define PLB_SEQ_2BIT  1
 
 /*
  * Per-read outputs of the scoring stage (seam S2): what
@@ -236,6 +256,25 @@ int plb_align_flank_batch_host(PlbContext* ctx, int32_t n,
 int plb_gap_open_host(PlbContext* ctx, int32_t n_haps, const int64_t* hap_seq_off,
                       const uint8_t* hap_seq, uint8_t* out);
 
+/* -- packing helpers (host only) ---------------------------------------------------------- */
+
+/*
+ * Packs n ASCII bases (src) as bases dst_base .. dst_base+n-1 of the 2-bit array dst (bits are OR-ed in: dst must be
+ * zero-initialised; any dst_base, so reads can be appended one at a time) and appends every base that is not exactly
+ * A/C/G/T to exc_pos / exc_chr as (dst_base + i, byte), starting at *n_exc; PLB_ERR_SHAPE when more than exc_cap entries
+ * would be needed.  This is the staging step of row N3 (BAM record -> device read pool) for callers that hold ASCII
+ * reads, as Platypus does after ReadIterator.get (src/cython/htslibWrapper.pyx:328-406).
+ */
+int plb_pack_bases_host(const uint8_t* src, int64_t n, uint8_t* dst, int64_t dst_base,
+                        int64_t* exc_pos, uint8_t* exc_chr, int64_t exc_cap, int64_t* n_exc);
+/*
+ * Same from BAM's own 4-bit encoding (two bases per byte, high nibble first, codes "=ACMGRSVTWYHKDBN",
+ * htslibWrapper.pyx:414-416): the read never exists as ASCII on the host.  Exceptions carry the letter htslib's
+ * lookup table gives the nibble.
+ */
+int plb_pack_nibbles_host(const uint8_t* bam_seq, int64_t n, uint8_t* dst, int64_t dst_base,
+                          int64_t* exc_pos, uint8_t* exc_chr, int64_t exc_cap, int64_t* n_exc);
+
 /* -- S2: per-read scoring seam ----------------------------------------------------- */
 
 /*
@@ -258,6 +297,22 @@ int plb_window_loglik_host(PlbContext* ctx, const PlbWindowBatch* host_batch,
 int plb_population_run_host(PlbContext* ctx, const PlbWindowBatch* host_batch,
                             const PlbOptions* opt, PlbPopulationOut* host_out,
                             PlbLoglikOut* host_ll);
+
+/*
+ * The same call split in two so that a region loop (src/cython/variantcaller.pyx:566-615) can keep the GPU and the PCIe
+ * link busy at once: plb_population_submit queues the uploads, kernels and downloads of one batch and returns without
+ * waiting; plb_population_wait blocks until that batch's outputs are in the caller's buffers (and returns its status).
+ * Up to PLB_MAX_JOBS batches may be in flight per context - batch k+1 travels over PCIe while batch k computes; a further
+ * submit returns PLB_ERR_ARG.  Input and output buffers must stay valid and untouched until the job has been waited
+ * for; they should be pinned (cudaHostAlloc / cudaHostRegister), pageable buffers make the copies synchronous.  Jobs
+ * complete in submission order.  plb_population_run_host == submit + wait.  `host_out` may be NULL (per-read outputs
+ * only: the S2 call).
+ */
+#define PLB_MAX_JOBS 2
+typedef struct PlbJob PlbJob;
+int plb_population_submit(PlbContext* ctx, const PlbWindowBatch* host_batch, const PlbOptions* opt,
+                          PlbPopulationOut* host_out, PlbLoglikOut* host_ll, PlbJob** job);
+int plb_population_wait(PlbContext* ctx, PlbJob* job);
 
 /* -- N4: per-site genotype calls (the step after the window model) --------------------- */
 

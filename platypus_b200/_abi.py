@@ -12,6 +12,9 @@ PLB_ERR_NOMEM = -5
 PLB_SCORE_NONE = 1000000
 PLB_LL_CAP = -300.0
 PLB_MAX_HAP_LEN = 16384
+PLB_SEQ_ASCII = 0
+PLB_SEQ_2BIT = 1
+PLB_MAX_JOBS = 2
 
 _p = C.c_void_p
 
@@ -37,7 +40,9 @@ class PlbWindowBatch(C.Structure):
                 ("slot_read", _p),
                 ("read_seq_off", _p), ("read_seq", _p), ("read_qual", _p), ("read_pos", _p), ("read_end", _p),
                 ("read_mapq", _p), ("read_qcfail", _p),
-                ("max_variants", C.c_int32), ("win_n_var", _p), ("hap_var_mask", _p), ("var_prior", _p)]
+                ("max_variants", C.c_int32), ("win_n_var", _p), ("hap_var_mask", _p), ("var_prior", _p),
+                ("seq_format", C.c_int32), ("n_read_exc", C.c_int64), ("read_exc_pos", _p), ("read_exc_chr", _p),
+                ("n_hap_exc", C.c_int64), ("hap_exc_pos", _p), ("hap_exc_chr", _p)]
 
 
 class PlbLoglikOut(C.Structure):
@@ -132,6 +137,14 @@ def declare(lib):
     lib.plb_window_loglik_host.restype = C.c_int
     lib.plb_population_run_host.argtypes = [_p, P(PlbWindowBatch), P(PlbOptions), P(PlbPopulationOut), P(PlbLoglikOut)]
     lib.plb_population_run_host.restype = C.c_int
+    lib.plb_population_submit.argtypes = [_p, P(PlbWindowBatch), P(PlbOptions), P(PlbPopulationOut), P(PlbLoglikOut), P(_p)]
+    lib.plb_population_submit.restype = C.c_int
+    lib.plb_population_wait.argtypes = [_p, _p]
+    lib.plb_population_wait.restype = C.c_int
+    lib.plb_pack_bases_host.argtypes = [_p, C.c_int64, _p, C.c_int64, _p, _p, C.c_int64, P(C.c_int64)]
+    lib.plb_pack_bases_host.restype = C.c_int
+    lib.plb_pack_nibbles_host.argtypes = [_p, C.c_int64, _p, C.c_int64, _p, _p, C.c_int64, P(C.c_int64)]
+    lib.plb_pack_nibbles_host.restype = C.c_int
     lib.plb_site_genotypes_host.argtypes = [_p, P(PlbWindowBatch), P(PlbPopulationOut), P(PlbSiteBatch), P(PlbSiteOut)]
     lib.plb_site_genotypes_host.restype = C.c_int
     lib.plb_batch_upload.argtypes = [_p, P(PlbWindowBatch), P(_p)]
@@ -169,6 +182,6 @@ EXPORTED_SYMBOLS = [
     "plb_window_loglik_host", "plb_population_run_host", "plb_site_genotypes_host", "plb_batch_upload", "plb_batch_free",
     "plb_run_device", "plb_last_stats", "plb_set_timing", "plb_kernel_times",
     "plb_build_haplotypes_host", "plb_select_haplotypes_host", "plb_select_replay_host", "plb_best_score_haplotypes_host",
-    "plb_select_stats",
+    "plb_select_stats", "plb_population_submit", "plb_population_wait", "plb_pack_bases_host", "plb_pack_nibbles_host",
 ]
 KERNEL_NAMES = ["k_prep", "k_anchor", "k_general", "k_dp", "k_genotype", "k_population"]

@@ -67,6 +67,13 @@ class WindowBatch:
     win_n_var: Optional[np.ndarray] = None
     hap_var_mask: Optional[np.ndarray] = None
     var_prior: Optional[np.ndarray] = None
+    # 2-bit packed bases (PLB_SEQ_2BIT, include/platypus_b200.h): hap_seq / read_seq then hold 4 bases per byte and the
+    # bases outside ACGT travel in the exception lists; offsets keep counting bases
+    seq_format: int = 0
+    read_exc_pos: Optional[np.ndarray] = None
+    read_exc_chr: Optional[np.ndarray] = None
+    hap_exc_pos: Optional[np.ndarray] = None
+    hap_exc_chr: Optional[np.ndarray] = None
     _keep: list = field(default_factory=list, repr=False)
 
     # ---- construction -------------------------------------------------------------------
@@ -175,7 +182,39 @@ class WindowBatch:
         return [self.win_hap_off, self.win_start, self.win_end, self.hap_start, self.hap_seq_off, self.hap_seq,
                 self.wi_slot_off, self.wi_n_good, self.wi_n_bad, self.slot_read, self.read_seq_off, self.read_seq,
                 self.read_qual, self.read_pos, self.read_end, self.read_mapq, self.read_qcfail, self.win_n_var,
-                self.hap_var_mask, self.var_prior]
+                self.hap_var_mask, self.var_prior, self.read_exc_pos, self.read_exc_chr, self.hap_exc_pos, self.hap_exc_chr]
+
+    def n_bases(self):
+        """(haplotype bases, read bases) of the batch, whatever the sequence format."""
+        return int(self.hap_seq_off[-1]), int(self.read_seq_off[-1])
+
+    def pack(self, lib=None) -> "WindowBatch":
+        """The same batch with 2-bit packed bases (PLB_SEQ_2BIT): what the staging step hands to the GPU instead of
+        ASCII (BAM's 4-bit nibbles pack straight into it, htslibWrapper.pyx:414-416).  Packing is done
+        by the library's host helper plb_pack_bases_host; no GPU work."""
+        import ctypes as C
+        import dataclasses
+        if self.seq_format == _abi.PLB_SEQ_2BIT:
+            return self
+        if lib is None:
+            from .engine import load_library
+            lib = load_library()
+
+        def pack(seq, n):
+            src = np.ascontiguousarray(seq[:n], np.uint8)
+            dst = np.zeros((n + 3) // 4 + 1, np.uint8)
+            cap = max(16, int(np.count_nonzero(~np.isin(src, np.frombuffer(b"ACGT", np.uint8)))))
+            pos, chr_ = np.zeros(cap, np.int64), np.zeros(cap, np.uint8)
+            k = C.c_int64(0)
+            rc = lib.plb_pack_bases_host(_abi.ptr(src), n, _abi.ptr(dst), 0, _abi.ptr(pos), _abi.ptr(chr_), cap, C.byref(k))
+            if rc:
+                raise RuntimeError("plb_pack_bases_host failed: %s" % lib.plb_last_error().decode())
+            return dst, pos[:k.value].copy(), chr_[:k.value].copy()
+        nh, nr = self.n_bases()
+        hs, hp, hc = pack(self.hap_seq, nh)
+        rs, rp, rc_ = pack(self.read_seq, nr)
+        return dataclasses.replace(self, hap_seq=hs, read_seq=rs, seq_format=_abi.PLB_SEQ_2BIT, read_exc_pos=rp,
+                                   read_exc_chr=rc_, hap_exc_pos=hp, hap_exc_chr=hc, _keep=[])
 
     # ---- ABI ----------------------------------------------------------------------------
     def as_struct(self):
@@ -199,6 +238,13 @@ class WindowBatch:
                          ("hap_var_mask", np.uint64), ("var_prior", np.float64)):
             setattr(s, name, _abi.ptr(c(getattr(self, name), dt)))
         s.max_variants = int(self.max_variants)
+        s.seq_format = int(self.seq_format)
+        if self.seq_format:
+            s.n_read_exc = 0 if self.read_exc_pos is None else len(self.read_exc_pos)
+            s.n_hap_exc = 0 if self.hap_exc_pos is None else len(self.hap_exc_pos)
+            for name, dt in (("read_exc_pos", np.int64), ("read_exc_chr", np.uint8), ("hap_exc_pos", np.int64),
+                             ("hap_exc_chr", np.uint8)):
+                setattr(s, name, _abi.ptr(c(getattr(self, name), dt)))
         return s
 
     # ---- sharding (contiguous blocks of windows per GPU) ---------------------
@@ -206,6 +252,7 @@ class WindowBatch:
         """Sub-batch with windows [lo, hi); the read pool is re-indexed to the reads the
         shard touches (reads straddling a shard boundary are duplicated into both shards, as
         the reference duplicates them across regions)."""
+        assert self.seq_format == 0, "slice the ASCII batch, then pack()"
         nI = self.n_individuals
         h0, h1 = int(self.win_hap_off[lo]), int(self.win_hap_off[hi])
         s0, s1 = int(self.wi_slot_off[lo * nI]), int(self.wi_slot_off[hi * nI])

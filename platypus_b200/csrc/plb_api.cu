@@ -31,6 +31,25 @@ static int set_err(int code, const char* fmt, ...) {
     return code;
 }
 
+// One OpenMP team size for every host-side parallel region of the library (libgomp rebuilds its team whenever the
+// size changes).  Default: the cores this process may run on, divided among the ranks of the node when launched by
+// torchrun (LOCAL_WORLD_SIZE), at most 16; PLB_HOST_THREADS overrides.  OMP_NUM_THREADS is deliberately not the cap:
+// torchrun exports OMP_NUM_THREADS=1 to every rank, which would leave tile planning on one thread.
+static int host_threads() {
+    static const int n = [] {
+        int v;
+        if (getenv("PLB_HOST_THREADS")) {
+            v = atoi(getenv("PLB_HOST_THREADS"));
+        } else {
+            const int cores = omp_get_num_procs();   // honours the affinity mask
+            const int ranks = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
+            v = std::min(16, cores / ranks);
+        }
+        return std::max(1, std::min(v, 64));
+    }();
+    return n;
+}
+
 #define CU(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -48,27 +67,51 @@ struct Block {
     size_t cap;
 };
 
+constexpr int kMaxJobs = 2;            // host-path jobs in flight per context (plb_population_submit / _wait)
+
+// Pinned host staging memory of one job slot (tile lists read zero-copy by the kernels, ll offsets, per-round arrays of a
+// selection call): valid until the slot's next pin_reset.
+struct PinArena {
+    std::vector<std::pair<uint8_t*, size_t>> blocks;
+    size_t off = 0;
+};
+
+// What one in-flight host-path job owns exclusively: its arena, its statistics counters and the events that order its
+// copies against its kernels.  Slot 0 also serves the synchronous entry points (device-resident runs, the selection loop).
+struct JobSlot {
+    PinArena pin;
+    Counters* d_ctr = nullptr;
+    Counters* h_ctr = nullptr;              // pinned
+    cudaEvent_t ev_chunk[kMaxChunks + 1];   // H2D of chunk k done
+    cudaEvent_t ev_unpack[kMaxChunks];      // packed input: chunk k's bases are ASCII again
+    cudaEvent_t ev_done[3];                 // last work of the job on compute stream k
+    cudaEvent_t ev_ctr;                     // counters are back in h_ctr
+    bool busy = false;
+};
+
 struct PlbContext {
     int device;
     cudaStream_t stream;
     cudaStream_t copy_stream;   // H2D of the pipelined host path
     cudaStream_t stream2;       // further compute streams: chunk k of the pipelined host path runs on
     cudaStream_t stream3;       // stream k mod 3, so one chunk's latency-bound tails overlap the next chunks
+    cudaStream_t aux_stream;    // fetches a job's counters once its three compute streams are done
     cudaEvent_t ev_s2, ev_s3;
-    std::vector<std::pair<uint8_t*, size_t>> pin_blocks;   // pinned staging for planner outputs
-    size_t pin_off = 0;
-    cudaEvent_t ev_chunk[kMaxChunks + 1];
+    JobSlot slot[kMaxJobs];
+    int cur = 0;                // slot whose arena / counters the code below is working with
+    int last_done = 0;          // slot of the most recently finished run (plb_last_stats)
+    int64_t jobs_submitted = 0;
     bool own_stream;
     int64_t launches;
     int n_sm;
     int smem_optin;
     std::vector<Block> cache;   // free device blocks, reused by size
-    Counters* d_ctr;
-    Counters* h_ctr;            // pinned
     cudaEvent_t ev;
     bool timing;
     int n_timed;                                        // runs recorded since plb_set_timing(1)
     cudaEvent_t kev[kTimingRing][PLB_N_KERNELS + 1];    // ring of per-run event sets
+    Counters* d_ctr() { return slot[cur].d_ctr; }
+    Counters* h_ctr() { return slot[cur].h_ctr; }
 };
 
 struct TileLists {
@@ -103,6 +146,18 @@ struct PlbDeviceBatch {
     int64_t* h_ll_off = nullptr;       // pinned
     int64_t hap_done[2] = {0, 0}, read_done[2] = {0, 0};  // byte intervals already on the device
     int64_t readmeta_done[2] = {0, 0};                    // read-index interval whose per-read arrays are on the device
+    // 2-bit packed input (PLB_SEQ_2BIT): the packed bytes land in pk_*, k_unpack2 restores the ASCII arrays of `d`
+    bool packed = false;
+    uint8_t* pk_hap = nullptr;
+    uint8_t* pk_read = nullptr;
+    int64_t n_read_exc = 0, n_hap_exc = 0;
+    int64_t* d_read_exc_pos = nullptr;
+    uint8_t* d_read_exc_chr = nullptr;
+    int64_t* d_hap_exc_pos = nullptr;
+    uint8_t* d_hap_exc_chr = nullptr;
+    bool exc_uploaded = false;
+    struct Fresh { int which; int64_t lo, hi; };          // base interval just uploaded: 0 = haplotypes, 1 = reads
+    std::vector<Fresh> fresh[kMaxChunks + 1];             // per chunk of the host path ([0] for whole-batch uploads)
 };
 
 extern "C" const char* plb_last_error(void) { return g_err; }
@@ -134,16 +189,23 @@ extern "C" int plb_context_create(int device, void* stream, PlbContext** out) {
     if (prop.major < 10)
         return set_err(PLB_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", device,
                        prop.major, prop.minor);
-    CU(cudaMalloc(&c->d_ctr, sizeof(Counters)));
-    CU(cudaMallocHost(&c->h_ctr, sizeof(Counters)));
-    memset(c->h_ctr, 0, sizeof(Counters));
+    for (int j = 0; j < kMaxJobs; ++j) {
+        JobSlot& js = c->slot[j];
+        CU(cudaMalloc(&js.d_ctr, sizeof(Counters)));
+        CU(cudaMallocHost(&js.h_ctr, sizeof(Counters)));
+        memset(js.h_ctr, 0, sizeof(Counters));
+        for (int i = 0; i <= kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&js.ev_chunk[i], cudaEventDisableTiming));
+        for (int i = 0; i < kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&js.ev_unpack[i], cudaEventDisableTiming));
+        for (int i = 0; i < 3; ++i) CU(cudaEventCreateWithFlags(&js.ev_done[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&js.ev_ctr, cudaEventDisableTiming));
+    }
     CU(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_s2, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_s3, cudaEventDisableTiming));
-    for (int i = 0; i <= kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
     c->timing = false;
     c->n_timed = 0;
     for (int r = 0; r < kTimingRing; ++r)
@@ -156,20 +218,28 @@ extern "C" void plb_context_destroy(PlbContext* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (auto& b : c->cache) cudaFree(b.p);
-    cudaFree(c->d_ctr);
-    cudaFreeHost(c->h_ctr);
-    cudaEventDestroy(c->ev);
     cudaStreamSynchronize(c->copy_stream);
-    cudaStreamDestroy(c->copy_stream);
     cudaStreamSynchronize(c->stream2);
-    cudaStreamDestroy(c->stream2);
     cudaStreamSynchronize(c->stream3);
+    cudaStreamSynchronize(c->aux_stream);
+    for (auto& b : c->cache) cudaFree(b.p);
+    for (int j = 0; j < kMaxJobs; ++j) {
+        JobSlot& js = c->slot[j];
+        cudaFree(js.d_ctr);
+        cudaFreeHost(js.h_ctr);
+        for (auto& pb : js.pin.blocks) cudaFreeHost(pb.first);
+        for (int i = 0; i <= kMaxChunks; ++i) cudaEventDestroy(js.ev_chunk[i]);
+        for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(js.ev_unpack[i]);
+        for (int i = 0; i < 3; ++i) cudaEventDestroy(js.ev_done[i]);
+        cudaEventDestroy(js.ev_ctr);
+    }
+    cudaEventDestroy(c->ev);
+    cudaStreamDestroy(c->copy_stream);
+    cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream3);
+    cudaStreamDestroy(c->aux_stream);
     cudaEventDestroy(c->ev_s2);
     cudaEventDestroy(c->ev_s3);
-    for (auto& pb : c->pin_blocks) cudaFreeHost(pb.first);
-    for (int i = 0; i <= kMaxChunks; ++i) cudaEventDestroy(c->ev_chunk[i]);
     for (int r = 0; r < kTimingRing; ++r)
         for (int i = 0; i <= PLB_N_KERNELS; ++i) cudaEventDestroy(c->kev[r][i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -203,27 +273,38 @@ static void block_put(PlbContext* c, Block b) {
     if (b.p) c->cache.push_back(b);
 }
 
-// Pinned host staging memory (valid until the next pin_reset; every API call synchronises its
-// streams before returning, so one arena per context is enough).
-static void pin_reset(PlbContext* c) { c->pin_off = 0; }
+// Pinned host staging memory of the current job slot (valid until the slot's next pin_reset: a slot is reused only after
+// its job has been waited for, so nothing in flight can still read it).
+static void pin_reset(PlbContext* c) { c->slot[c->cur].pin.off = 0; }
 
 static void* pin_alloc(PlbContext* c, size_t bytes) {
+    PinArena& A = c->slot[c->cur].pin;
     bytes = (bytes + 255) & ~(size_t)255;
-    if (!c->pin_blocks.empty()) {
-        auto& last = c->pin_blocks.back();
-        if (c->pin_off + bytes <= last.second) {
-            void* p = last.first + c->pin_off;
-            c->pin_off += bytes;
+    if (!A.blocks.empty()) {
+        auto& last = A.blocks.back();
+        if (A.off + bytes <= last.second) {
+            void* p = last.first + A.off;
+            A.off += bytes;
             return p;
         }
     }
     // grow: a new block twice the size; older blocks stay alive (copies from them may be in flight)
-    size_t cap = std::max<size_t>(bytes * 2, c->pin_blocks.empty() ? (size_t)(4 << 20) : c->pin_blocks.back().second * 2);
+    size_t cap = std::max<size_t>(bytes * 2, A.blocks.empty() ? (size_t)(4 << 20) : A.blocks.back().second * 2);
     void* p = nullptr;
     if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
-    c->pin_blocks.push_back({(uint8_t*)p, cap});
-    c->pin_off = bytes;
+    A.blocks.push_back({(uint8_t*)p, cap});
+    A.off = bytes;
     return p;
+}
+
+// Entry points that use the context's streams synchronously (device-resident runs, uploads, the selection loop, the S1
+// batches) must not interleave with host-path jobs that are still in flight.
+static int require_idle(PlbContext* c, const char* what) {
+    for (int j = 0; j < kMaxJobs; ++j)
+        if (c->slot[j].busy)
+            return set_err(PLB_ERR_ARG, "%s: a submitted job is still in flight on this context (plb_population_wait it first)", what);
+    c->cur = 0;
+    return PLB_OK;
 }
 
 // ---- host helpers -----------------------------------------------------------------------------
@@ -252,7 +333,20 @@ static int check_options(const PlbOptions* o) {
     return PLB_OK;
 }
 
-extern "C" int plb_validate(const PlbWindowBatch* b, const PlbOptions* opt, int32_t max_haps) {
+// The read-length rule applies to the reads the kernels will actually score: good / bad reads that fail QC or overlap
+// the window by fewer than 7 bases are short-circuited to LL = 0 (chaplotype.pyx:343-361) exactly as in k_anchor.
+static bool slot_is_scored(const PlbWindowBatch* b, int w, int64_t wi, int64_t s, int r) {
+    const int64_t t = s - b->wi_slot_off[wi];
+    if (t >= (int64_t)b->wi_n_good[wi] + b->wi_n_bad[wi]) return true;   // broken mates are always scored
+    if (b->read_qcfail[r]) return false;
+    const int ws = b->win_start[w], we = b->win_end[w], rp = b->read_pos[r], re = b->read_end[r];
+    const int lo = ws > rp ? ws : rp, hi = we < re ? we : re;
+    return hi > lo && hi - lo >= PLB_KMER;
+}
+
+// Checks a HOST batch.  O(windows + haplotypes + slots), spread over the library's host threads; `bytes` adds the scan
+// of every base quality (the run paths leave that to the kernels, which flag it while they build their profiles).
+static int validate_batch(const PlbWindowBatch* b, const PlbOptions* opt, int32_t max_haps, bool bytes) {
     if (!b) return set_err(PLB_ERR_ARG, "batch is NULL");
     if (opt) {
         int rc = check_options(opt);
@@ -272,38 +366,73 @@ extern "C" int plb_validate(const PlbWindowBatch* b, const PlbOptions* opt, int3
                            !b->read_mapq || !b->read_qcfail))
         return set_err(PLB_ERR_ARG, "NULL read array in batch");
     if (b->n_haps > 0 && !b->hap_seq) return set_err(PLB_ERR_ARG, "hap_seq is NULL");
+    if (b->max_variants > 64) return set_err(PLB_ERR_SHAPE, "max_variants %d > 64", b->max_variants);
+    if (b->seq_format != PLB_SEQ_ASCII && b->seq_format != PLB_SEQ_2BIT)
+        return set_err(PLB_ERR_ARG, "seq_format %d unknown", b->seq_format);
+    if (b->seq_format == PLB_SEQ_2BIT) {
+        if (b->n_read_exc < 0 || b->n_hap_exc < 0 || (b->n_read_exc > 0 && (!b->read_exc_pos || !b->read_exc_chr)) ||
+            (b->n_hap_exc > 0 && (!b->hap_exc_pos || !b->hap_exc_chr)))
+            return set_err(PLB_ERR_ARG, "packed batch: bad exception lists");
+        const int64_t rb = b->n_reads ? b->read_seq_off[b->n_reads] : 0, hbts = b->n_haps ? b->hap_seq_off[b->n_haps] : 0;
+        for (int64_t i = 0; i < b->n_read_exc; ++i)
+            if (b->read_exc_pos[i] < 0 || b->read_exc_pos[i] >= rb)
+                return set_err(PLB_ERR_ARG, "packed batch: read exception %lld out of range", (long long)i);
+        for (int64_t i = 0; i < b->n_hap_exc; ++i)
+            if (b->hap_exc_pos[i] < 0 || b->hap_exc_pos[i] >= hbts)
+                return set_err(PLB_ERR_ARG, "packed batch: haplotype exception %lld out of range", (long long)i);
+    }
+    // first failing window wins, as in a serial scan (messages name the lowest window)
+    int bad_w = b->n_windows;
+    int bad_code = PLB_OK;
+    char bad_msg[400] = "";
+    const bool hla = opt && opt->use_mapq_cap;
+#pragma omp parallel for schedule(static, 256) num_threads(host_threads()) if (b->n_windows > 2048)
     for (int w = 0; w < b->n_windows; ++w) {
+        if (w > bad_w) continue;
+        char msg[400] = "";
+        int code = PLB_OK;
+        auto fail = [&](int cde, const char* fmt, ...) {
+            if (code != PLB_OK) return;
+            code = cde;
+            va_list ap;
+            va_start(ap, fmt);
+            vsnprintf(msg, sizeof msg, fmt, ap);
+            va_end(ap);
+        };
         const int H = b->win_hap_off[w + 1] - b->win_hap_off[w];
-        if (H < 1) return set_err(PLB_ERR_SHAPE, "window %d has no haplotypes", w);
+        if (H < 1) fail(PLB_ERR_SHAPE, "window %d has no haplotypes", w);
         if (max_haps > 0 && H > max_haps)
-            return set_err(PLB_ERR_SHAPE, "window %d has %d haplotypes > max_haps %d (cpopulation.pyx:221)", w, H,
-                           max_haps);
+            fail(PLB_ERR_SHAPE, "window %d has %d haplotypes > max_haps %d (cpopulation.pyx:221)", w, H, max_haps);
         if (opt && opt->calc_flank_score && b->win_start[w] - b->hap_start[w] <= 0)
-            return set_err(PLB_ERR_ARG, "window %d: calc_flank_score needs a positive flank (win_start - hap_start)", w);
-        const bool hla = opt && opt->use_mapq_cap;
+            fail(PLB_ERR_ARG, "window %d: calc_flank_score needs a positive flank (win_start - hap_start)", w);
         int min_len = 1 << 30;
-        for (int h = b->win_hap_off[w]; h < b->win_hap_off[w + 1]; ++h) {
+        for (int h = b->win_hap_off[w]; h < b->win_hap_off[w + 1] && code == PLB_OK; ++h) {
             const int64_t len = b->hap_seq_off[h + 1] - b->hap_seq_off[h];
-            if (len < 0) return set_err(PLB_ERR_ARG, "hap_seq_off not monotone at %d", h);
+            if (len < 0) fail(PLB_ERR_ARG, "hap_seq_off not monotone at %d", h);
             if (len > PLB_MAX_HAP_LEN)
-                return set_err(PLB_ERR_SHAPE, "haplotype %d is %lld bp > %d (chaplotype.pyx:180)", h, (long long)len,
-                               PLB_MAX_HAP_LEN);
+                fail(PLB_ERR_SHAPE, "haplotype %d is %lld bp > %d (chaplotype.pyx:180)", h, (long long)len, PLB_MAX_HAP_LEN);
             min_len = std::min<int>(min_len, (int)len);
         }
-        for (int i = 0; i < b->n_individuals; ++i) {
+        for (int i = 0; i < b->n_individuals && code == PLB_OK; ++i) {
             const int64_t wi = (int64_t)w * b->n_individuals + i;
             const int64_t T = b->wi_slot_off[wi + 1] - b->wi_slot_off[wi];
-            if (T < 0 || b->wi_n_good[wi] < 0 || b->wi_n_bad[wi] < 0 || b->wi_n_good[wi] + b->wi_n_bad[wi] > T)
-                return set_err(PLB_ERR_ARG, "read counts inconsistent for window %d individual %d", w, i);
-            for (int64_t s = b->wi_slot_off[wi]; s < b->wi_slot_off[wi + 1]; ++s) {
+            if (T < 0 || b->wi_n_good[wi] < 0 || b->wi_n_bad[wi] < 0 || b->wi_n_good[wi] + b->wi_n_bad[wi] > T) {
+                fail(PLB_ERR_ARG, "read counts inconsistent for window %d individual %d", w, i);
+                break;
+            }
+            for (int64_t s = b->wi_slot_off[wi]; s < b->wi_slot_off[wi + 1] && code == PLB_OK; ++s) {
                 const int r = b->slot_read[s];
-                if (r < 0 || r >= b->n_reads) return set_err(PLB_ERR_ARG, "slot %lld: read index out of range", (long long)s);
+                if (r < 0 || r >= b->n_reads) {
+                    fail(PLB_ERR_ARG, "slot %lld: read index out of range", (long long)s);
+                    break;
+                }
                 const int64_t L = b->read_seq_off[r + 1] - b->read_seq_off[r];
-                if (L < 0 || L > 32767) return set_err(PLB_ERR_SHAPE, "read %d length %lld out of range", r, (long long)L);
+                if (L < 0 || L > 32767) fail(PLB_ERR_SHAPE, "read %d length %lld out of range", r, (long long)L);
+                if (code != PLB_OK || L < PLB_KMER || !slot_is_scored(b, w, wi, s, r)) continue;
                 // the reference would read past the haplotype (calign.pyx:256-259); refuse instead
-                if (!hla && L >= PLB_KMER && L + 15 > min_len)
-                    return set_err(PLB_ERR_SHAPE, "window %d: read %d (%lld bp) + 15 exceeds haplotype length %d", w, r,
-                                   (long long)L, min_len);
+                if (!hla && L + 15 > min_len)
+                    fail(PLB_ERR_SHAPE, "window %d: read %d (%lld bp) + 15 exceeds haplotype length %d", w, r, (long long)L,
+                         min_len);
                 if (hla) {  // same rule on the read as clipped to each haplotype (chaplotype.pyx:647-655)
                     for (int h = b->win_hap_off[w]; h < b->win_hap_off[w + 1]; ++h) {
                         const int hl = (int)(b->hap_seq_off[h + 1] - b->hap_seq_off[h]);
@@ -311,17 +440,34 @@ extern "C" int plb_validate(const PlbWindowBatch* b, const PlbOptions* opt, int3
                         const int o2 = std::max(0, b->read_pos[r] + (int)L - b->win_start[w] - hl);
                         const int Lc = (int)L - o1 - o2;
                         if (Lc >= PLB_KMER && Lc + 15 > hl)
-                            return set_err(PLB_ERR_SHAPE, "window %d: clipped read %d (%d bp) + 15 exceeds haplotype length %d",
-                                           w, r, Lc, hl);
+                            fail(PLB_ERR_SHAPE, "window %d: clipped read %d (%d bp) + 15 exceeds haplotype length %d", w, r, Lc, hl);
                     }
                 }
             }
         }
+        if (code != PLB_OK) {
+#pragma omp critical(plb_validate_err)
+            if (w < bad_w) {
+                bad_w = w;
+                bad_code = code;
+                memcpy(bad_msg, msg, sizeof bad_msg);
+            }
+        }
     }
-    for (int64_t i = 0; i < b->read_seq_off[b->n_reads]; ++i)
-        if (b->read_qual[i] > 93) return set_err(PLB_ERR_ARG, "base quality %d > 93 at byte %lld", b->read_qual[i], (long long)i);
-    if (b->max_variants > 64) return set_err(PLB_ERR_SHAPE, "max_variants %d > 64", b->max_variants);
+    if (bad_code != PLB_OK) return set_err(bad_code, "%s", bad_msg);
+    if (bytes) {
+        const int64_t nb = b->n_reads ? b->read_seq_off[b->n_reads] : 0;
+        int64_t bad = -1;
+#pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(max : bad) if (nb > (1 << 20))
+        for (int64_t i = 0; i < nb; ++i)
+            if (b->read_qual[i] > 93) bad = std::max(bad, i);
+        if (bad >= 0) return set_err(PLB_ERR_ARG, "base quality %d > 93 at byte %lld", b->read_qual[bad], (long long)bad);
+    }
     return PLB_OK;
+}
+
+extern "C" int plb_validate(const PlbWindowBatch* b, const PlbOptions* opt, int32_t max_haps) {
+    return validate_batch(b, opt, max_haps, true);
 }
 
 // ---- upload + planning ----------------------------------------------------------------------
@@ -519,12 +665,6 @@ static int plan_tiles(const PlbWindowBatch* hb, int w_begin, int w_end, TileList
 }
 
 // Bytes of the big sequence arrays (hap_seq / read_seq / read_qual) that windows [w0, w1) need.
-// One OpenMP team size for every host-side parallel region of the library.
-static int host_threads() {
-    static const int n = std::max(1, std::min(omp_get_max_threads(), getenv("PLB_HOST_THREADS") ? atoi(getenv("PLB_HOST_THREADS")) : 16));
-    return n;
-}
-
 struct ByteRanges {
     int64_t hap0, hap1;    // byte range of hap_seq
     int64_t read0, read1;  // byte range of read_seq / read_qual (hull over the reads the slots refer to)
@@ -603,6 +743,18 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
     db->have_var = have_var;
     const size_t o_win_n_var = L.take(have_var ? (size_t)W * 4 : 0), o_hap_var_mask = L.take(have_var ? (size_t)n_haps * 8 : 0),
                  o_var_prior = L.take(have_var ? (size_t)W * hb->max_variants * 8 : 0);
+    const bool packed = hb->seq_format == PLB_SEQ_2BIT;
+    if (packed && share) {
+        delete db;
+        return set_err(PLB_ERR_UNSUPPORTED, "packed batches are not taken by the selection rounds");
+    }
+    db->packed = packed;
+    db->n_read_exc = packed ? hb->n_read_exc : 0;
+    db->n_hap_exc = packed ? hb->n_hap_exc : 0;
+    const size_t o_pk_hap = L.take(packed ? (size_t)(hap_bytes + 3) / 4 + 64 : 0),
+                 o_pk_read = L.take(packed ? (size_t)(read_bytes + 3) / 4 + 64 : 0),
+                 o_rexc_pos = L.take((size_t)db->n_read_exc * 8), o_rexc_chr = L.take((size_t)db->n_read_exc),
+                 o_hexc_pos = L.take((size_t)db->n_hap_exc * 8), o_hexc_chr = L.take((size_t)db->n_hap_exc);
     const size_t o_slot_wi = L.take(own * n_slots * 4), o_hap_win = L.take((size_t)n_haps * 4),
                  o_ll_off = L.take((size_t)(nwi + 1) * 8);
     const size_t o_gap = L.take((size_t)hap_bytes + n_haps + 64), o_wgen = L.take((size_t)W * 4 + 64),
@@ -670,6 +822,14 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
     db->q3.cap = qcap;
     db->ll_scratch = at<double>(B, o_ll);
     db->em_scratch = at<double>(B, o_em);
+    if (packed) {
+        db->pk_hap = at<uint8_t>(B, o_pk_hap);
+        db->pk_read = at<uint8_t>(B, o_pk_read);
+        db->d_read_exc_pos = at<int64_t>(B, o_rexc_pos);
+        db->d_read_exc_chr = at<uint8_t>(B, o_rexc_chr);
+        db->d_hap_exc_pos = at<int64_t>(B, o_hexc_pos);
+        db->d_hap_exc_chr = at<uint8_t>(B, o_hexc_chr);
+    }
     if (share) {
         const DevBatch& s = share->d;
         d.win_start = s.win_start;
@@ -934,41 +1094,118 @@ static int copy_meta(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* hb
     return PLB_OK;
 }
 
-// Copies the parts of [lo, hi) of a byte array that are not on the device yet; `done` is the
-// interval already uploaded (kept as one interval: a gap between intervals is simply filled).
-static int copy_bytes(uint8_t* dst, const uint8_t* src, int64_t lo, int64_t hi, int64_t done[2], cudaStream_t st) {
+// Copies the parts of [lo, hi) of a base array that are not on the device yet; `done` is the interval already uploaded
+// (kept as one interval: a gap between intervals is simply filled).  shift = 2 for 2-bit packed arrays (4 bases per
+// byte; boundary bytes are simply sent again).  The base intervals sent are appended to `fresh`.
+static int copy_bytes(uint8_t* dst, const uint8_t* src, int64_t lo, int64_t hi, int64_t done[2], cudaStream_t st,
+                      int shift = 0, int which = 0, std::vector<PlbDeviceBatch::Fresh>* fresh = nullptr) {
     if (hi <= lo) return PLB_OK;
+    auto send = [&](int64_t a, int64_t b) -> cudaError_t {
+        if (fresh) fresh->push_back({which, a, b});
+        const int64_t b0 = a >> shift, b1 = (b + ((int64_t)1 << shift) - 1) >> shift;
+        return cudaMemcpyAsync(dst + b0, src + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st);
+    };
     if (done[1] <= done[0]) {
-        CUQ(cudaMemcpyAsync(dst + lo, src + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
+        CUQ(send(lo, hi));
         done[0] = lo;
         done[1] = hi;
         return PLB_OK;
     }
     if (lo < done[0]) {
-        CUQ(cudaMemcpyAsync(dst + lo, src + lo, (size_t)(done[0] - lo), cudaMemcpyHostToDevice, st));
+        CUQ(send(lo, done[0]));
         done[0] = lo;
     }
     if (hi > done[1]) {
-        CUQ(cudaMemcpyAsync(dst + done[1], src + done[1], (size_t)(hi - done[1]), cudaMemcpyHostToDevice, st));
+        CUQ(send(done[1], hi));
         done[1] = hi;
     }
     return PLB_OK;
 }
 
-// Metadata first (small), then the sequence bytes of windows [w0, w1).
+// Metadata first (small), then the sequence bytes of windows [w0, w1).  `chunk` = which fresh-interval list of the
+// batch records what has to be unpacked (packed batches only).
 static int copy_seq_for_windows(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* hb, int w0, int w1,
-                                cudaStream_t st) {
+                                cudaStream_t st, int chunk = 0) {
     const ByteRanges r = byte_ranges(hb, w0, w1);
     int rc;
     if ((rc = copy_meta(c, db, hb, w0, w1, r.rmin, r.rmax, st))) return rc;
-    if ((rc = copy_bytes((uint8_t*)db->d.hap_seq, hb->hap_seq, r.hap0, r.hap1, db->hap_done, st))) return rc;
     int64_t qdone[2] = {db->read_done[0], db->read_done[1]};
-    if ((rc = copy_bytes((uint8_t*)db->d.read_seq, hb->read_seq, r.read0, r.read1, db->read_done, st))) return rc;
+    if (db->packed) {
+        if (!db->exc_uploaded) {   // the exception lists are small: all of them with the first chunk
+            if (db->n_read_exc) {
+                CUQ(cudaMemcpyAsync(db->d_read_exc_pos, hb->read_exc_pos, (size_t)db->n_read_exc * 8, cudaMemcpyHostToDevice, st));
+                CUQ(cudaMemcpyAsync(db->d_read_exc_chr, hb->read_exc_chr, (size_t)db->n_read_exc, cudaMemcpyHostToDevice, st));
+            }
+            if (db->n_hap_exc) {
+                CUQ(cudaMemcpyAsync(db->d_hap_exc_pos, hb->hap_exc_pos, (size_t)db->n_hap_exc * 8, cudaMemcpyHostToDevice, st));
+                CUQ(cudaMemcpyAsync(db->d_hap_exc_chr, hb->hap_exc_chr, (size_t)db->n_hap_exc, cudaMemcpyHostToDevice, st));
+            }
+            db->exc_uploaded = true;
+        }
+        auto* fr = &db->fresh[chunk];
+        if ((rc = copy_bytes(db->pk_hap, hb->hap_seq, r.hap0, r.hap1, db->hap_done, st, 2, 0, fr))) return rc;
+        if ((rc = copy_bytes(db->pk_read, hb->read_seq, r.read0, r.read1, db->read_done, st, 2, 1, fr))) return rc;
+    } else {
+        if ((rc = copy_bytes((uint8_t*)db->d.hap_seq, hb->hap_seq, r.hap0, r.hap1, db->hap_done, st))) return rc;
+        if ((rc = copy_bytes((uint8_t*)db->d.read_seq, hb->read_seq, r.read0, r.read1, db->read_done, st))) return rc;
+    }
     if ((rc = copy_bytes((uint8_t*)db->d.read_qual, hb->read_qual, r.read0, r.read1, qdone, st))) return rc;
     return PLB_OK;
 }
 
+namespace plb {
+// 2-bit packed bases -> the ASCII bytes every kernel reads (A 0, C 1, G 2, T 3; base i at bits 2*(i & 3) of byte i >> 2).
+// One thread per packed byte; writes ONLY bases b0 <= i < b1, so a byte shared with a neighbouring interval (unpacked by
+// another chunk, possibly already patched and in use) is never touched twice.
+__global__ void __launch_bounds__(256) k_unpack2(const uint8_t* __restrict__ pk, uint8_t* __restrict__ dst, int64_t b0,
+                                                 int64_t b1) {
+    const int64_t q = (b0 >> 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t base = q << 2;
+    if (base >= b1) return;
+    const u32 c = pk[q];
+    const u32 sel = (c & 3u) | ((c & 0xCu) << 2) | ((c & 0x30u) << 4) | ((c & 0xC0u) << 6);
+    const u32 v = __byte_perm(0x54474341u /* "ACGT" */, 0u, sel);
+    if (base >= b0 && base + 4 <= b1) {
+        *(u32*)(dst + base) = v;
+    } else {
+        for (int k = 0; k < 4; ++k)
+            if (base + k >= b0 && base + k < b1) dst[base + k] = (uint8_t)(v >> (8 * k));
+    }
+}
+// ... then the bases that are not A/C/G/T get their original byte back
+__global__ void __launch_bounds__(256) k_patch_exceptions(const int64_t* __restrict__ pos, const uint8_t* __restrict__ chr,
+                                                          int64_t n, uint8_t* __restrict__ dst, int64_t b0, int64_t b1) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t p = pos[i];
+    if (p >= b0 && p < b1) dst[p] = chr[i];
+}
+}  // namespace plb
+
 static int launch_check(PlbContext* c, const char* what);
+
+// Restores the ASCII arrays of the base intervals that `chunk`'s copies brought in (packed batches; no-op otherwise).
+static int unpack_fresh(PlbContext* c, PlbDeviceBatch* db, int chunk, cudaStream_t st) {
+    if (!db->packed) return PLB_OK;
+    int rc;
+    for (const auto& f : db->fresh[chunk]) {
+        const uint8_t* pk = f.which ? db->pk_read : db->pk_hap;
+        uint8_t* dst = (uint8_t*)(f.which ? db->d.read_seq : db->d.hap_seq);
+        const int64_t nq = ((f.hi + 3) >> 2) - (f.lo >> 2);
+        if (nq <= 0) continue;
+        k_unpack2<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(pk, dst, f.lo, f.hi);
+        if ((rc = launch_check(c, "k_unpack2"))) return rc;
+        const int64_t ne = f.which ? db->n_read_exc : db->n_hap_exc;
+        if (ne > 0) {
+            k_patch_exceptions<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(f.which ? db->d_read_exc_pos : db->d_hap_exc_pos,
+                                                                             f.which ? db->d_read_exc_chr : db->d_hap_exc_chr, ne,
+                                                                             dst, f.lo, f.hi);
+            if ((rc = launch_check(c, "k_patch_exceptions"))) return rc;
+        }
+    }
+    db->fresh[chunk].clear();
+    return PLB_OK;
+}
 
 static int derive_all(PlbContext* c, PlbDeviceBatch* db, cudaStream_t st) {
     const DevBatch& d = db->d;
@@ -979,11 +1216,16 @@ static int derive_all(PlbContext* c, PlbDeviceBatch* db, cudaStream_t st) {
 }
 
 extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch** out) {
-    PlbDeviceBatch* db = nullptr;
-    int rc = prepare_batch(c, hb, &db);
+    if (!c || !hb || !out) return set_err(PLB_ERR_ARG, "NULL argument");
+    int rc = require_idle(c, "plb_batch_upload");
     if (rc) return rc;
+    // the kernels index the read pool and the haplotypes unchecked: refuse inconsistent batches here (the scoring options
+    // are not known yet; the run-time modes' extra rules are checked by plb_run_device's caller through plb_validate)
+    if ((rc = validate_batch(hb, nullptr, 0, false))) return rc;
+    PlbDeviceBatch* db = nullptr;
+    if ((rc = prepare_batch(c, hb, &db))) return rc;
     cudaStream_t st = c->stream;
-    if ((rc = copy_seq_for_windows(c, db, hb, 0, hb->n_windows, st)) ||
+    if ((rc = copy_seq_for_windows(c, db, hb, 0, hb->n_windows, st)) || (rc = unpack_fresh(c, db, 0, st)) ||
         (rc = plan_chunk(c, db, hb, 0, hb->n_windows, st)) || (rc = derive_all(c, db, st))) {
         cudaStreamSynchronize(st);
         plb_batch_free(c, db);
@@ -1078,9 +1320,9 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
             return rc;
         const int grid = std::max(1, std::min(ap.n_tiles, c->n_sm * ch.a_occ));
         if (modes)
-            k_anchor<true><<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr);
+            k_anchor<true><<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr());
         else
-            k_anchor<false><<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr);
+            k_anchor<false><<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr());
         if ((rc = launch_check(c, "k_anchor"))) return rc;
         mark(2);
         if (modes)
@@ -1098,7 +1340,7 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
         const DpPlan& dp = ch.dp;
         if ((rc = opt_in_smem(k_dp<kDpThreads>, ch.d_smem))) return rc;
         const int grid = std::max(1, std::min(dp.n_tiles, c->n_sm * ch.d_occ));
-        k_dp<kDpThreads><<<grid, kDpThreads, ch.d_smem, st>>>(d, dp, sp, ll, sc, q.count + 2);
+        k_dp<kDpThreads><<<grid, kDpThreads, ch.d_smem, st>>>(d, dp, sp, ll, sc, q.count + 2, c->d_ctr());
         if ((rc = launch_check(c, "k_dp"))) return rc;
     }
     mark(4);
@@ -1153,31 +1395,47 @@ extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOption
     if (!c || !db) return set_err(PLB_ERR_ARG, "NULL argument");
     int rc = check_options(opt);
     if (rc) return rc;
+    if ((rc = require_idle(c, "plb_run_device"))) return rc;
+    c->last_done = 0;
     CU(cudaSetDevice(c->device));
     if (db->d.n_windows == 0) return PLB_OK;
     if ((rc = check_pop(db, pop))) return rc;
     cudaStream_t st = c->stream;
-    CU(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), st));
+    CU(cudaMemsetAsync(c->d_ctr(), 0, sizeof(Counters), st));
     const bool modes = opt->calc_flank_score || opt->use_mapq_cap;
     if (modes && (rc = mode_queues(c, db, false))) return rc;
     for (const ChunkPlan& ch : db->chunks)
         if ((rc = launch_windows(c, db, ch, opt, pop, llo, st, db->chunks.size() == 1, modes ? db->mq : db->q))) return rc;
-    CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_ctr(), c->d_ctr(), sizeof(Counters), cudaMemcpyDeviceToHost, st));
     return PLB_OK;
+}
+
+static const char* const kErrBitText[] = {
+    "a scored read is longer than its haplotype allows (readLen + 15 > hapLen, calign.pyx:256-259)",
+    "a base quality above 93",
+};
+
+static int counters_status(const Counters* h) {
+    if (!h->err) return PLB_OK;
+    for (int b = 0; b < 2; ++b)
+        if (h->err & (1ull << b)) return set_err(b == 0 ? PLB_ERR_SHAPE : PLB_ERR_ARG, "the kernels refused the batch: %s", kErrBitText[b]);
+    return set_err(PLB_ERR_ARG, "the kernels refused the batch (flags %llx)", h->err);
 }
 
 extern "C" int plb_last_stats(PlbContext* c, PlbRunStats* out) {
     if (!c || !out) return set_err(PLB_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(c->device));
-    CU(cudaStreamSynchronize(c->stream));
-    out->n_pairs = (int64_t)c->h_ctr->n_pairs;
-    out->n_pairs_scored = (int64_t)c->h_ctr->n_scored;
-    out->n_dp = (int64_t)c->h_ctr->n_dp;
-    out->cells = (int64_t)c->h_ctr->cells;
-    out->n_anchor_heavy = (int64_t)c->h_ctr->n_heavy;
-    out->n_anchor_verify = (int64_t)c->h_ctr->n_verify;
-    out->n_anchor_exact = (int64_t)c->h_ctr->n_exact;
-    return PLB_OK;
+    const JobSlot& js = c->slot[c->last_done];
+    if (!js.busy) CU(cudaStreamSynchronize(c->stream));   // device-resident runs fetch their counters on the stream
+    const Counters* h = js.h_ctr;
+    out->n_pairs = (int64_t)h->n_pairs;
+    out->n_pairs_scored = (int64_t)h->n_scored;
+    out->n_dp = (int64_t)h->n_dp;
+    out->cells = (int64_t)h->cells;
+    out->n_anchor_heavy = (int64_t)h->n_heavy;
+    out->n_anchor_verify = (int64_t)h->n_verify;
+    out->n_anchor_exact = (int64_t)h->n_exact;
+    return counters_status(h);
 }
 
 extern "C" int plb_set_timing(PlbContext* c, int on) {
@@ -1215,20 +1473,61 @@ static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* opt, PlbPopulationOut* hpop,
-                    PlbLoglikOut* hll) {
+// Releases a batch whose work is known to be complete (no stream synchronisation: other work may be running).
+static void batch_release_done(PlbContext* c, PlbDeviceBatch* b) {
+    if (!b) return;
+    for (auto& ch : b->chunks) block_put(c, ch.tiles_blk);
+    if (b->mode_blk.p) block_put(c, b->mode_blk);
+    block_put(c, b->blk);
+    delete b;
+}
+
+// One host-path call in flight (plb_population_submit .. plb_population_wait).
+struct PlbJob {
+    int slot = 0;
+    PlbDeviceBatch* db = nullptr;
+    Block ob{nullptr, 0};
+    int n_chunks = 0;
+    int rc = PLB_OK;              // error met while queueing (reported by wait, after the queued work has drained)
+    char msg[512] = "";
+    double t_start = 0, t_prep = 0, t_issue = 0;
+    std::vector<cudaEvent_t> tev;     // PLB_TRACE: device timeline
+    std::vector<const char*> ttag;
+};
+
+static int submit_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* opt, PlbPopulationOut* hpop,
+                       PlbLoglikOut* hll, PlbJob** job_out) {
     int rc = check_options(opt);
     if (rc) return rc;
     if (!hb) return set_err(PLB_ERR_ARG, "batch is NULL");
-    if (hb->n_windows == 0) return PLB_OK;
+    int slot = -1, busy = 0;
+    for (int j = 0; j < kMaxJobs; ++j) {
+        if (c->slot[j].busy) ++busy;
+        else if (slot < 0) slot = j;
+    }
+    if (slot < 0) return set_err(PLB_ERR_ARG, "%d jobs already in flight on this context (PLB_MAX_JOBS); wait for one first", kMaxJobs);
+    CU(cudaSetDevice(c->device));
+    // O(slots) consistency check (the kernels index the pool unchecked); base qualities are checked on the GPU
+    if ((rc = validate_batch(hb, opt, hpop ? hpop->max_haps : 0, false))) return rc;
+    PlbJob* job = new PlbJob();
+    job->slot = slot;
+    *job_out = job;
+    if (hb->n_windows == 0) return PLB_OK;   // nothing queued; wait() returns at once
+    c->cur = slot;
+    JobSlot& js = c->slot[slot];
     static const bool trace = getenv("PLB_TRACE") != nullptr;
-    const double t_start = now_ms();
+    job->t_start = now_ms();
     PlbDeviceBatch* db = nullptr;
-    if ((rc = prepare_batch(c, hb, &db))) return rc;
-    const double t_prep = now_ms();
+    if ((rc = prepare_batch(c, hb, &db))) {
+        delete job;
+        *job_out = nullptr;
+        return rc;
+    }
+    job->db = db;
+    job->t_prep = now_ms();
     const int W = hb->n_windows, nInd = hb->n_individuals;
     const int64_t n_pairs = db->d.n_pairs;
-    Block ob{nullptr, 0};
+    Block& ob = job->ob;
     PlbPopulationOut dpop;
     PlbLoglikOut dll;
     memset(&dpop, 0, sizeof dpop);
@@ -1237,13 +1536,18 @@ static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* o
     size_t o_gl = 0, o_glmax = 0, o_gof = 0, o_hl = 0, o_freq = 0, o_em = 0, o_call = 0, o_vp = 0, o_it = 0, o_ll = 0,
            o_sc = 0;
     int Hm = 0, Gm = 0, V = hb->max_variants;
+    auto abandon = [&](int code) {
+        batch_release_done(c, db);
+        if (ob.p) block_put(c, ob);
+        delete job;
+        *job_out = nullptr;
+        return code;
+    };
     if (hpop) {
         Hm = hpop->max_haps;
-        if (Hm < db->max_haps) {
-            plb_batch_free(c, db);
-            return set_err(PLB_ERR_SHAPE, "max_haps %d < largest window (%d haplotypes) (cpopulation.pyx:221)", Hm,
-                           db->max_haps);
-        }
+        if (Hm < db->max_haps)
+            return abandon(set_err(PLB_ERR_SHAPE, "max_haps %d < largest window (%d haplotypes) (cpopulation.pyx:221)", Hm,
+                                   db->max_haps));
         Gm = Hm * (Hm + 1) / 2;
         o_gl = L.take((size_t)W * nInd * Gm * 8);
         o_glmax = L.take((size_t)W * nInd * 8);
@@ -1258,10 +1562,7 @@ static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* o
     const bool want_ll = hll && hll->ll, want_sc = hll && hll->score;
     if (want_ll) o_ll = L.take((size_t)n_pairs * 8);
     if (want_sc) o_sc = L.take((size_t)n_pairs * 4);
-    if ((rc = block_get(c, L.off + 256, &ob))) {
-        plb_batch_free(c, db);
-        return rc;
-    }
+    if ((rc = block_get(c, L.off + 256, &ob))) return abandon(rc);
     if (hpop) {
         dpop.max_haps = Hm;
         dpop.gl = at<double>(ob, o_gl);
@@ -1278,37 +1579,36 @@ static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* o
     dll.score = want_sc ? at<int32_t>(ob, o_sc) : nullptr;
 
     cudaStream_t cs = c->copy_stream, st = c->stream;
-    cudaStream_t kst = st;   // compute stream of the current chunk (chunks alternate between two streams
-                             // so that one chunk's kernel tails overlap the next chunk's kernels)
+    cudaStream_t kst = st;   // compute stream of the current chunk (chunks rotate over three streams so that one
+                             // chunk's kernel tails overlap the next chunk's kernels)
     cudaError_t e = cudaSuccess;
     auto d2h = [&](void* dst, const void* src, size_t off, size_t bytes) {
         if (rc == PLB_OK && e == cudaSuccess && dst && src && bytes)
             e = cudaMemcpyAsync((uint8_t*)dst + off, (const uint8_t*)src + off, bytes, cudaMemcpyDeviceToHost, kst);
     };
-    // chunking: enough chunks to overlap, few enough to keep launches cheap
+    // Chunking.  A lone call wants its first kernels early: up to six chunks whose sizes grow x1.3.  When another job
+    // is still computing, this job's bytes travel behind that job's kernels anyway, so it is cut into few chunks (each
+    // chunk costs ~0.25 ms of kernel tails); PLB_PIPE_CHUNKS overrides that number.
+    static const int pipe_chunks = getenv("PLB_PIPE_CHUNKS") ? std::max(1, std::min(kMaxChunks, atoi(getenv("PLB_PIPE_CHUNKS")))) : 2;
     int n_chunks = std::max(1, std::min(kMaxChunks, W / kMinChunkWindows));
+    const bool pipelined = busy > 0;
+    if (pipelined) n_chunks = std::min(n_chunks, pipe_chunks);
+    job->n_chunks = n_chunks;
     db->chunks.reserve(n_chunks);
     const bool modes = opt->calc_flank_score || opt->use_mapq_cap;
     rc = modes ? mode_queues(c, db, n_chunks > 1) : PLB_OK;
     // PLB_TRACE: device timeline of the pipeline (events with timing, created per call)
-    std::vector<cudaEvent_t> tev;
-    std::vector<const char*> ttag;
     auto tmark_t = [&](cudaStream_t s_, const char* tag) {
         if (!trace) return;
         cudaEvent_t ev_;
         cudaEventCreate(&ev_);
         cudaEventRecord(ev_, s_);
-        tev.push_back(ev_);
-        ttag.push_back(tag);
+        job->tev.push_back(ev_);
+        job->ttag.push_back(tag);
     };
     auto tmark = [&](cudaStream_t s_) { tmark_t(s_, s_ == cs ? "h2d:" : "k:"); };
     tmark(cs);
-    if (rc == PLB_OK) e = cudaEventRecord(c->ev_chunk[0], cs);
-    if (rc == PLB_OK && e == cudaSuccess) e = cudaStreamWaitEvent(st, c->ev_chunk[0], 0);
-    if (rc == PLB_OK && e == cudaSuccess) e = cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), st);
-    if (rc == PLB_OK && e == cudaSuccess) e = cudaEventRecord(c->ev_s2, st);
-    if (rc == PLB_OK && e == cudaSuccess) e = cudaStreamWaitEvent(c->stream2, c->ev_s2, 0);
-    if (rc == PLB_OK && e == cudaSuccess) e = cudaStreamWaitEvent(c->stream3, c->ev_s2, 0);
+    if (rc == PLB_OK) e = cudaMemsetAsync(js.d_ctr, 0, sizeof(Counters), cs);
     cudaStream_t kstreams[3] = {st, c->stream2, c->stream3};
     const Queue* kqueues[3] = {modes ? &db->mq : &db->q, modes ? &db->mq2 : &db->q2, modes ? &db->mq3 : &db->q3};
     // Chunk sizes grow geometrically (x1.3): the first kernels start after a small upload, and because
@@ -1318,7 +1618,7 @@ static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* o
     auto cut = [&](int i) -> int {
         if (i <= 0) return 0;
         if (i >= n_chunks) return W;
-        const double r = 1.3;
+        const double r = pipelined ? 1.0 : 1.3;
         double tot = 0.0, part = 0.0, term = 1.0;
         for (int j = 0; j < n_chunks; ++j, term *= r) {
             tot += term;
@@ -1335,8 +1635,8 @@ static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* o
     auto queue_copies = [&](int upto) {
         for (; copies_queued < upto && copies_queued < n_chunks && rc == PLB_OK && e == cudaSuccess; ++copies_queued) {
             const int a = cut(copies_queued), b2 = cut(copies_queued + 1);
-            if (b2 > a) rc = copy_seq_for_windows(c, db, hb, a, b2, cs);
-            if (rc == PLB_OK) e = cudaEventRecord(c->ev_chunk[1 + copies_queued], cs);
+            if (b2 > a) rc = copy_seq_for_windows(c, db, hb, a, b2, cs, 1 + copies_queued);
+            if (rc == PLB_OK) e = cudaEventRecord(js.ev_chunk[1 + copies_queued], cs);
             tmark(cs);
         }
     };
@@ -1348,8 +1648,17 @@ static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* o
         kst = kstreams[k % 3];
         // tile lists are read from pinned host memory (a small H2D copy would wait behind the sequence bytes)
         if ((rc = plan_chunk(c, db, hb, w0, w1, kst, true))) break;
-        e = cudaStreamWaitEvent(kst, c->ev_chunk[1 + k], 0);
+        e = cudaStreamWaitEvent(kst, js.ev_chunk[1 + k], 0);
         if (e != cudaSuccess) break;
+        if (db->packed) {
+            // reads are shared between chunks: chunk k may score reads that chunk k-1's copies brought in, so its
+            // kernels also wait for that chunk's unpacking (which waited for the one before it)
+            if (k > 0) e = cudaStreamWaitEvent(kst, js.ev_unpack[k - 1], 0);
+            if (e != cudaSuccess) break;
+            if ((rc = unpack_fresh(c, db, 1 + k, kst))) break;
+            e = cudaEventRecord(js.ev_unpack[k], kst);
+            if (e != cudaSuccess) break;
+        }
         tmark(kst);
         if ((rc = launch_windows(c, db, db->chunks.back(), opt, hpop ? &dpop : nullptr, &dll, kst, false,
                                  *kqueues[k % 3], true)))
@@ -1372,37 +1681,90 @@ static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* o
         if (want_sc) d2h(hll->score, dll.score, (size_t)p0 * 4, (size_t)(p1 - p0) * 4);
         tmark(kst);
     }
-    // join the second compute stream into the first, then fetch the counters
-    if (e == cudaSuccess) e = cudaEventRecord(c->ev_s2, c->stream2);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, c->ev_s2, 0);
-    if (e == cudaSuccess) e = cudaEventRecord(c->ev_s3, c->stream3);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, c->ev_s3, 0);
-    if (rc == PLB_OK && e == cudaSuccess)
-        e = cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st);
-    const double t_issue = now_ms();
-    cudaError_t e2 = cudaStreamSynchronize(cs);
-    const double t_copy = now_ms();
-    cudaError_t e3 = cudaStreamSynchronize(st);
-    if (trace && !tev.empty()) {
-        // events in issue order; copy-stream marks are tagged by position: print all as ms after the first
-        fprintf(stderr, "[plb] timeline (ms):");
-        for (size_t i = 1; i < tev.size(); ++i) {
-            float t = 0;
-            cudaEventElapsedTime(&t, tev[0], tev[i]);
-            fprintf(stderr, " %s%.2f", ttag[i], t);
-        }
-        fprintf(stderr, "\n");
-        for (cudaEvent_t ev_ : tev) cudaEventDestroy(ev_);
+    // completion: one event per compute stream (no join through the first stream - the next job's first chunk must not
+    // wait for this job's last chunks on the other two), the counters come back on the side stream once all three fired
+    for (int i = 0; i < 3; ++i) {
+        if (e == cudaSuccess) e = cudaEventRecord(js.ev_done[i], kstreams[i]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->aux_stream, js.ev_done[i], 0);
     }
-    if (trace)
-        fprintf(stderr, "[plb] run_host: prepare %.2f ms, issue %.2f ms, copy-stream drain +%.2f ms, compute drain +%.2f ms (%d chunks)\n",
-                t_prep - t_start, t_issue - t_prep, t_copy - t_issue, now_ms() - t_copy, n_chunks);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(js.h_ctr, js.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, c->aux_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(js.ev_ctr, c->aux_stream);
+    job->t_issue = now_ms();
     if (rc == PLB_OK && e != cudaSuccess) rc = set_err(PLB_ERR_CUDA, "pipelined run failed: %s", cudaGetErrorString(e));
-    if (rc == PLB_OK && e2 != cudaSuccess) rc = set_err(PLB_ERR_CUDA, "copy stream: %s", cudaGetErrorString(e2));
-    if (rc == PLB_OK && e3 != cudaSuccess) rc = set_err(PLB_ERR_CUDA, "compute stream: %s", cudaGetErrorString(e3));
-    block_put(c, ob);
-    plb_batch_free(c, db);
+    job->rc = rc;
+    if (rc != PLB_OK) snprintf(job->msg, sizeof job->msg, "%s", g_err);
+    js.busy = true;
+    c->jobs_submitted++;
+    return PLB_OK;   // queueing errors are reported by wait, after what was queued has drained
+}
+
+static int wait_job(PlbContext* c, PlbJob* job) {
+    if (!job) return set_err(PLB_ERR_ARG, "job is NULL");
+    static const bool trace = getenv("PLB_TRACE") != nullptr;
+    int rc = job->rc;
+    if (job->db) {
+        JobSlot& js = c->slot[job->slot];
+        cudaSetDevice(c->device);
+        const double t_w0 = now_ms();
+        // the copy stream only carries this job's uploads up to ev_chunk[n]; the compute side ends with ev_ctr
+        cudaError_t e2 = cudaEventSynchronize(js.ev_chunk[job->n_chunks]);
+        const double t_copy = now_ms();
+        cudaError_t e3 = cudaEventSynchronize(js.ev_ctr);
+        for (int i = 0; i < 3 && e3 == cudaSuccess; ++i) e3 = cudaEventSynchronize(js.ev_done[i]);
+        if (rc != PLB_OK) {   // a queueing error: drain everything so that nothing still reads the caller's buffers
+            cudaStreamSynchronize(c->copy_stream);
+            cudaStreamSynchronize(c->stream);
+            cudaStreamSynchronize(c->stream2);
+            cudaStreamSynchronize(c->stream3);
+            cudaStreamSynchronize(c->aux_stream);
+        }
+        if (trace && !job->tev.empty()) {
+            fprintf(stderr, "[plb] timeline (ms):");
+            for (size_t i = 1; i < job->tev.size(); ++i) {
+                float t = 0;
+                cudaEventElapsedTime(&t, job->tev[0], job->tev[i]);
+                fprintf(stderr, " %s%.2f", job->ttag[i], t);
+            }
+            fprintf(stderr, "\n");
+        }
+        for (cudaEvent_t ev_ : job->tev) cudaEventDestroy(ev_);
+        if (trace)
+            fprintf(stderr, "[plb] job slot %d: prepare %.2f ms, issue %.2f ms, submit->wait %.2f ms, copy drain +%.2f ms, compute drain +%.2f ms (%d chunks)\n",
+                    job->slot, job->t_prep - job->t_start, job->t_issue - job->t_prep, t_w0 - job->t_issue, t_copy - t_w0,
+                    now_ms() - t_copy, job->n_chunks);
+        if (rc == PLB_OK && e2 != cudaSuccess) rc = set_err(PLB_ERR_CUDA, "copy stream: %s", cudaGetErrorString(e2));
+        if (rc == PLB_OK && e3 != cudaSuccess) rc = set_err(PLB_ERR_CUDA, "compute stream: %s", cudaGetErrorString(e3));
+        else if (rc != PLB_OK && job->msg[0]) set_err(rc, "%s", job->msg);
+        if (rc == PLB_OK) rc = counters_status(js.h_ctr);
+        block_put(c, job->ob);
+        batch_release_done(c, job->db);
+        js.busy = false;
+        c->last_done = job->slot;
+    }
+    delete job;
     return rc;
+}
+
+extern "C" int plb_population_submit(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* opt, PlbPopulationOut* out,
+                                     PlbLoglikOut* ll, PlbJob** job) {
+    if (!c || !job) return set_err(PLB_ERR_ARG, "NULL argument");
+    *job = nullptr;
+    if (!out && !(ll && (ll->ll || ll->score))) return set_err(PLB_ERR_ARG, "no output requested");
+    if (out && !out->gl) return set_err(PLB_ERR_ARG, "PlbPopulationOut.gl is required");
+    return submit_host(c, hb, opt, out, ll, job);
+}
+
+extern "C" int plb_population_wait(PlbContext* c, PlbJob* job) {
+    if (!c) return set_err(PLB_ERR_ARG, "NULL argument");
+    return wait_job(c, job);
+}
+
+static int run_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* opt, PlbPopulationOut* hpop,
+                    PlbLoglikOut* hll) {
+    PlbJob* job = nullptr;
+    int rc = submit_host(c, hb, opt, hpop, hll, &job);
+    if (rc) return rc;
+    return wait_job(c, job);
 }
 
 extern "C" int plb_window_loglik_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* opt,
@@ -1416,6 +1778,70 @@ extern "C" int plb_population_run_host(PlbContext* c, const PlbWindowBatch* hb, 
     if (!c || !out) return set_err(PLB_ERR_ARG, "NULL argument");
     if (!out->gl) return set_err(PLB_ERR_ARG, "PlbPopulationOut.gl is required");
     return run_host(c, hb, opt, out, ll);
+}
+
+// ---- packing helpers (host) ------------------------------------------------------------------------
+
+namespace {
+// code of a byte: 0..3 for exactly 'A','C','G','T', 4 otherwise
+inline int acgt_code(uint8_t ch) { return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4; }
+
+// Shared body: base i of the source is get(i) (an ASCII byte).  Bits are OR-ed into dst, so a partial first byte that
+// already holds earlier bases is preserved.  Big arrays are cut at byte boundaries of dst and packed in parallel; the
+// exceptions of the pieces are concatenated in order.
+template <typename Get>
+int pack_2bit(Get get, int64_t n, uint8_t* dst, int64_t dst_base, int64_t* exc_pos, uint8_t* exc_chr, int64_t exc_cap,
+              int64_t* n_exc) {
+    if (n < 0 || dst_base < 0 || !dst || !n_exc || *n_exc < 0) return set_err(PLB_ERR_ARG, "NULL / bad argument");
+    const int parts = n >= (1 << 20) ? host_threads() : 1;
+    std::vector<std::vector<std::pair<int64_t, uint8_t>>> exc((size_t)parts);
+#pragma omp parallel for schedule(static, 1) num_threads(host_threads()) if (parts > 1)
+    for (int p = 0; p < parts; ++p) {
+        // piece boundaries on multiples of 4 of the destination index
+        auto bound = [&](int q) -> int64_t {
+            if (q <= 0) return 0;
+            if (q >= parts) return n;
+            const int64_t t = (dst_base + n * q / parts) & ~(int64_t)3;
+            return std::min(n, std::max<int64_t>(0, t - dst_base));
+        };
+        const int64_t i0 = bound(p), i1 = bound(p + 1);
+        for (int64_t i = i0; i < i1; ++i) {
+            const uint8_t ch = get(i);
+            int code = acgt_code(ch);
+            const int64_t j = dst_base + i;
+            if (code > 3) {
+                exc[(size_t)p].push_back({j, ch});
+                code = 0;
+            }
+            dst[j >> 2] |= (uint8_t)(code << (2 * (j & 3)));
+        }
+    }
+    int64_t k = *n_exc;
+    for (auto& v : exc)
+        for (auto& e : v) {
+            if (k >= exc_cap || !exc_pos || !exc_chr)
+                return set_err(PLB_ERR_SHAPE, "more than %lld bases outside ACGT: exception arrays too small", (long long)exc_cap);
+            exc_pos[k] = e.first;
+            exc_chr[k] = e.second;
+            ++k;
+        }
+    *n_exc = k;
+    return PLB_OK;
+}
+}  // namespace
+
+extern "C" int plb_pack_bases_host(const uint8_t* src, int64_t n, uint8_t* dst, int64_t dst_base, int64_t* exc_pos,
+                                   uint8_t* exc_chr, int64_t exc_cap, int64_t* n_exc) {
+    if (n > 0 && !src) return set_err(PLB_ERR_ARG, "src is NULL");
+    return pack_2bit([&](int64_t i) { return src[i]; }, n, dst, dst_base, exc_pos, exc_chr, exc_cap, n_exc);
+}
+
+extern "C" int plb_pack_nibbles_host(const uint8_t* bam_seq, int64_t n, uint8_t* dst, int64_t dst_base, int64_t* exc_pos,
+                                     uint8_t* exc_chr, int64_t exc_cap, int64_t* n_exc) {
+    if (n > 0 && !bam_seq) return set_err(PLB_ERR_ARG, "bam_seq is NULL");
+    static const char* const kNib = "=ACMGRSVTWYHKDBN";   // htslibWrapper.pyx:414-416
+    return pack_2bit([&](int64_t i) { return (uint8_t)kNib[(bam_seq[i >> 1] >> (4 * (1 - (i & 1)))) & 15]; }, n, dst, dst_base,
+                     exc_pos, exc_chr, exc_cap, n_exc);
 }
 
 // ---- N4: per-site genotype calls ------------------------------------------------------------------

@@ -91,7 +91,9 @@ struct Queue {
 struct Counters {  // device-side statistics
     unsigned long long n_pairs, n_scored, n_dp, cells;
     unsigned long long n_heavy, n_verify, n_exact;  // n_exact: anchor pairs that needed the exact vote array
+    unsigned long long err;   // bit 0: a scored read with readLen + 15 > hapLen; bit 1: a base quality above 93
 };
+constexpr unsigned long long kErrReadTooLong = 1ull, kErrQuality = 2ull;
 
 struct ScoreParams {
     int32_t ext, nuc;
@@ -691,6 +693,17 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 const SlotInfo si = s_slot[s];
                 const PairClip pc = pair_clip(sp, si.pos, si.len, hap_start_w, win_start_w, s_hmeta[3 * g]);
                 ++st_pairs;
+                // a scored read must fit the haplotype (the reference would read past it, calign.pyx:256-259); the host
+                // entry points refuse such batches, device-resident callers get the error flag and the sentinel score
+                const bool too_long = !(si.flags & 1) && pc.L >= kKmer && pc.L + 15 > s_hmeta[3 * g];
+                if (too_long) {
+                    if (ctr) atomicOr(&ctr->err, kErrReadTooLong);
+                    b.cand0[pair] = -1;
+                    b.cand1[pair] = -1;
+                    b.score[pair] = kScoreNone;
+                    s_vlist[3 * p] = (u32)kPairSkip;
+                    continue;
+                }
                 if ((si.flags & 1) || pc.L < kKmer) {  // LL forced to 0, or calign.pyx:182-183 (score 0)
                     b.cand0[pair] = -1;
                     b.cand1[pair] = -1;
@@ -1043,9 +1056,27 @@ struct DpSlot {
     double ll_right; // log(1 - exp(mLTOT*mapq)), chaplotype.pyx:622
 };
 
+// End of a read's profile row (all lanes of the warp): `qs` = the lane's share of the quality sum, with 2^20 added per
+// quality above 93.  The packed int16 recurrences are exact while every path cost stays inside the reference's own range
+// (pos_inf >> 2 = 15,872 phred, align.c:97; a score never exceeds the sum of the read's qualities plus gap costs that the
+// same margin covers); a read whose qualities add up beyond that takes the 32-bit recurrence instead (flag bit 1).
+constexpr int kMaxPackedQualSum = 15871 - 256;
+__device__ __forceinline__ void row_quality_check(int qs, int32_t* flags, Counters* ctr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(0xFFFFFFFFu, qs, o);
+    if ((threadIdx.x & 31) == 0) {
+        if (qs >= (1 << 20)) {
+            if (ctr) atomicOr(&ctr->err, kErrQuality);
+            qs &= (1 << 20) - 1;
+        }
+        if (qs > kMaxPackedQualSum) *flags |= 2;
+    }
+}
+
 template <int NTHR>
 __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParams sp, double* __restrict__ ll_out,
-                                             int32_t* __restrict__ score_out, int* __restrict__ tile_counter) {
+                                             int32_t* __restrict__ score_out, int* __restrict__ tile_counter,
+                                             Counters* __restrict__ ctr) {
     extern __shared__ __align__(16) uint8_t smem[];
     u32* s_prof = (u32*)smem;
     HapRec* s_rec = (HapRec*)(s_prof + plan.prof_words);
@@ -1217,11 +1248,13 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                     const uint8_t* rs = row_end - 2 * NB + (int)(o & 15);
                     const uint8_t* rq = row_end - NB + (int)(o & 15);
                     uint8_t cb[6], qb[6];
+                    int qs = 0;
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
                         const int y = lane + 32 * k;
                         cb[k] = y < ds.len ? rs[y] : (uint8_t)0;
                         qb[k] = y < ds.len ? rq[y] : (uint8_t)0;
+                        qs += qb[k] > 93 ? (1 << 20) : (int)qb[k];
                     }
                     __syncwarp();
 #pragma unroll
@@ -1231,10 +1264,12 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                             row[y] = y < ds.len ? s_ptab[((u32)s_code[cb[k]] << 7) | (qb[k] & 127u)] : 0u;
                         }
                     }
+                    row_quality_check(qs, &s_slot[s].flags, ctr);
                     continue;
                 }
                 const uint8_t* rs = b.read_seq + o;
                 const uint8_t* rq = b.read_qual + o;
+                int qs = 0;
                 for (int y0 = 0; y0 < n; y0 += 192) {   // long reads: plain loads, 6 rows per lane
                     uint8_t cb[6], qb[6];
 #pragma unroll
@@ -1242,6 +1277,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                         const int y = y0 + lane + 32 * k;
                         cb[k] = y < ds.len ? rs[y] : (uint8_t)0;
                         qb[k] = y < ds.len ? rq[y] : (uint8_t)0;
+                        qs += qb[k] > 93 ? (1 << 20) : (int)qb[k];
                     }
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
@@ -1251,6 +1287,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                         }
                     }
                 }
+                row_quality_check(qs, &s_slot[s].flags, ctr);
             }
         }
         // best scores start from what the general path produced; compact packed-path tasks
@@ -1292,9 +1329,17 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
             const int p = (int)(tk >> 15), start = (int)(tk & 0x7FFFu);
             const int s = s_order[p / nh], g = p % nh;
             const DpSlot ds = s_slot[s];
-            const int v = five  ? band_dp_fast5(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc)
-                          : six ? band_dp_fast6(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc)
-                                : band_dp_fast(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc);
+            int v;
+            if (ds.flags & 2) {   // the read's qualities add up beyond the int16 range: exact 32-bit recurrence
+                const int h = tile.h0 + g;
+                v = band_dp_general(b.hap_seq + b.hap_seq_off[h] + start, b.gap_open + b.hap_seq_off[h] + h + start,
+                                    b.read_seq + b.read_seq_off[ds.read], b.read_qual + b.read_seq_off[ds.read], ds.len,
+                                    sp.ext, sp.nuc);
+            } else {
+                v = five  ? band_dp_fast5(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc)
+                    : six ? band_dp_fast6(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc)
+                          : band_dp_fast(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc);
+            }
             atomicMin(&s_best[p], v);
         }
         __syncthreads();

@@ -409,6 +409,8 @@ extern "C" int plb_build_haplotypes_host(PlbContext* c, const PlbWindowBatch* rb
     // ctx may be NULL when only the offsets are wanted (hap_seq == NULL): the lengths are computed on the host
     if ((!c && hap_seq) || n_haps < 0 || (n_haps > 0 && (!hap_win || !hap_mask)) || !hap_seq_off)
         return set_err(PLB_ERR_ARG, "NULL / bad argument");
+    if (rb && rb->seq_format != PLB_SEQ_ASCII)
+        return set_err(PLB_ERR_UNSUPPORTED, "plb_build_haplotypes_host takes ASCII reference segments only");
     SelHost sh;
     int rc = check_variants(rb, vs, sh);
     if (rc) return rc;
@@ -1085,21 +1087,14 @@ extern "C" int plb_select_replay_host(const PlbWindowBatch* rb, const PlbVariant
         [](SelPlan&) { return PLB_OK; });
 }
 
-// Releases a round's batch whose work is known to be complete (no stream synchronisation: the other group's round
-// may be running).
-static void batch_release_done(PlbContext* c, PlbDeviceBatch* b) {
-    if (!b) return;
-    for (auto& ch : b->chunks) block_put(c, ch.tiles_blk);
-    if (b->mode_blk.p) block_put(c, b->mode_blk);
-    block_put(c, b->blk);
-    delete b;
-}
-
 extern "C" int plb_select_haplotypes_host(PlbContext* c, const PlbWindowBatch* rb, const PlbVariantSet* vs,
                                           const PlbSelectOptions* so, const PlbOptions* opt_in, PlbSelectOut* out) {
     if (!c) return set_err(PLB_ERR_ARG, "NULL argument");
     int rc = check_options(opt_in);
     if (rc) return rc;
+    if ((rc = require_idle(c, "plb_select_haplotypes_host"))) return rc;
+    if (rb && rb->seq_format != PLB_SEQ_ASCII)
+        return set_err(PLB_ERR_UNSUPPORTED, "plb_select_haplotypes_host samples the reads on the host: it takes ASCII batches only");
     PlbOptions opt = *opt_in;
     opt.use_mapq_cap = 0;   // alignSingleRead(read, False), variantFilter.pyx:274-275
     CU(cudaSetDevice(c->device));
@@ -1176,7 +1171,7 @@ extern "C" int plb_select_haplotypes_host(PlbContext* c, const PlbWindowBatch* r
         SEL_CU(cudaMemcpyAsync(at<uint8_t>(G.VB, o_vaoff), P.aoff.data(), (size_t)(nvar + 1) * 8, cudaMemcpyHostToDevice, st));
         G.sv = SelVars{at<int32_t>(G.VB, o_voff), at<int32_t>(G.VB, o_vpos), at<int32_t>(G.VB, o_vnr), at<int64_t>(G.VB, o_vaoff),
                        at<uint8_t>(G.VB, o_vadd)};
-        if (P.gid == 0) SEL_CU(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), st));
+        if (P.gid == 0) SEL_CU(cudaMemsetAsync(c->d_ctr(), 0, sizeof(Counters), st));
         SEL_TRY(copy_seq_for_windows(c, G.base, &P.batch, 0, Wf, st));
         SEL_TRY(plan_chunk(c, G.base, &P.batch, 0, Wf, st));
         SEL_TRY(derive_all(c, G.base, st));

@@ -243,6 +243,27 @@ class Engine:
             arrs["ll"], arrs["score"] = ll[:n], sc[:n]
         return arrs
 
+    def population_submit(self, batch: WindowBatch, opt=None, max_haps=None, out=None):
+        """First half of population_run for a region loop (variantcaller.pyx:566-615): queues the uploads, kernels and
+        downloads of `batch` and returns a job handle without waiting.  Up to two jobs may be in flight per engine -
+        batch k+1 is uploaded while batch k computes.  The arrays of `batch` and `out` must stay alive and untouched
+        until population_wait(job); they should live in pinned memory (torch .pin_memory())."""
+        opt = opt or _abi.PlbOptions.default()
+        arrs = out or self.alloc_population_out(batch, max_haps)
+        po = self._pop_struct(arrs)
+        s = batch.as_struct()
+        job = C.c_void_p()
+        _check(self.lib, self.lib.plb_population_submit(self.ctx, C.byref(s), C.byref(opt), C.byref(po), None, C.byref(job)))
+        return {"job": job, "out": arrs, "keep": (batch, s, po, opt)}
+
+    def population_wait(self, handle):
+        """Second half: blocks until the job's outputs are in its `out` arrays and returns them."""
+        job, handle["job"] = handle["job"], None
+        if job is not None:
+            _check(self.lib, self.lib.plb_population_wait(self.ctx, job))
+        handle["keep"] = None
+        return handle["out"]
+
     # ---- N4 ---------------------------------------------------------------------------------
     def site_genotypes(self, batch: WindowBatch, pop: dict, sites):
         """computeGenotypeCallAndLikelihoods + the per-sample derivations of outputCallToVCF for every

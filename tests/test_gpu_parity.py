@@ -679,3 +679,132 @@ def test_call_windows_select_build_population_vs_oracle(engine, oracle):
     assert np.array_equal(pop["call"], want["call"])
     assert np.array_equal(pop["var_phred"], want["var_phred"])
     assert np.all(sel_out["n_sel"] == 9) and batch.max_haps() == 10
+
+
+# ---- round 2: packed input, pipelined submit / wait, kernel-side refusals ------------------------------------------
+
+def _pinned_copy(b):
+    """The batch with every array in pinned host memory (what plb_population_submit wants)."""
+    import dataclasses
+    import torch
+    kw, keep = {}, []
+    for f in b.__dataclass_fields__:
+        v = getattr(b, f)
+        if isinstance(v, np.ndarray):
+            t = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+            keep.append(t)
+            kw[f] = t.numpy()
+    nb = dataclasses.replace(b, **kw)
+    nb._keep = []
+    nb._pins = keep
+    return nb
+
+
+@pytest.mark.parametrize("mode", [dict(), dict(use_mapq_cap=1), dict(calc_flank_score=1)])
+def test_packed_input_is_bit_identical(engine, mode):
+    """PLB_SEQ_2BIT batches (2-bit bases + exception lists, the staging format of row N3) give the very same bytes out as
+    the ASCII call: edge batches (N, IUPAC, lower case -> exceptions), ragged synth windows, every run-time mode."""
+    opt = _abi.PlbOptions.default(**mode)
+    for b in (cases.edge_batch(seed=5), cases.edge_batch(seed=2),
+              synth.make_batch(1500, read_len_range=(100, 250), hap_len_range=(200, 500)), synth.make_batch(3000)):
+        p = b.pack()
+        assert p.input_nbytes() < b.input_nbytes()
+        a = engine.population_run(b, opt=opt, want_ll=True)
+        c = engine.population_run(p, opt=opt, want_ll=True)
+        for k in ("score", "ll", "gl", "gl_log_max", "gof", "hap_like", "freq", "em_post", "call", "var_phred", "em_iters"):
+            assert np.array_equal(a[k], c[k]), k
+    # the device-resident path takes packed batches too
+    b = cases.edge_batch(seed=3)
+    want = engine.population_run(b, opt=opt)
+    import torch
+    h = engine.upload(b.pack())
+    out = {k: torch.zeros(v.shape, dtype=torch.float64 if v.dtype == np.float64 else torch.int32, device="cuda")
+           for k, v in want.items() if isinstance(v, np.ndarray)}
+    ptrs = {k: v.data_ptr() for k, v in out.items()}
+    ptrs["max_haps"] = want["max_haps"]
+    engine.run_device(h, ptrs, opt=opt)
+    torch.cuda.synchronize()
+    engine.last_stats()
+    engine.free(h)
+    for k in ("gl", "freq", "call", "var_phred"):
+        assert np.array_equal(out[k].cpu().numpy(), want[k]), k
+
+
+def test_submit_wait_two_jobs_in_flight(engine):
+    """plb_population_submit / plb_population_wait: batch k+1 is queued while batch k computes (the region loop of
+    variantcaller.pyx:566-615).  Results equal the one-call path bit for bit, in any interleaving; a third job in flight
+    is refused; synchronous entry points refuse to run under in-flight jobs."""
+    from platypus_b200.engine import PlbError
+    batches = [synth.make_batch(2600, window_offset=7000 * i) for i in range(4)] + [cases.edge_batch(seed=4)]
+    want = [engine.population_run(b) for b in batches]
+    pinned = [_pinned_copy(b.pack() if i % 2 else b) for i, b in enumerate(batches)]
+    keys = ("gl", "gl_log_max", "gof", "hap_like", "freq", "em_post", "call", "var_phred", "em_iters")
+    for rounds in range(2):
+        jobs = [engine.population_submit(pinned[0])]
+        got = []
+        for i in range(1, len(pinned)):
+            jobs.append(engine.population_submit(pinned[i]))
+            if i == 1:
+                with pytest.raises(PlbError) as e:     # PLB_MAX_JOBS = 2
+                    engine.population_submit(pinned[2])
+                assert e.value.code == _abi.PLB_ERR_ARG
+                with pytest.raises(PlbError):
+                    engine.upload(batches[0])
+            got.append(engine.population_wait(jobs.pop(0)))
+        got.append(engine.population_wait(jobs.pop(0)))
+        for g, w in zip(got, want):
+            for k in keys:
+                assert np.array_equal(g[k], w[k]), k
+    st = engine.last_stats()
+    assert st["n_pairs"] == int(batches[-1].ll_offsets()[-1])
+    # an empty batch and waiting twice are harmless
+    j = engine.population_submit(synth.make_batch(0), out=engine.alloc_population_out(synth.make_batch(1)))
+    engine.population_wait(j)
+    engine.population_wait(j)
+    engine.population_run(batches[-1])
+
+
+def test_kernels_refuse_bad_qualities_and_overlong_reads(engine):
+    """What the O(slots) host check cannot see is flagged by the kernels and reported by the call: a base quality above
+    93 (the reference asserts it, htslibWrapper.pyx:518-519), and - on the device-resident path, which keeps no host
+    batch to re-check against the mode - a scored read that does not fit its haplotype (calign.pyx:256-259)."""
+    from platypus_b200.engine import PlbError
+    b = synth.make_batch(40)
+    b.read_qual = b.read_qual.copy()
+    b.read_qual[12345] = 94
+    with pytest.raises(PlbError) as e:
+        engine.population_run(b)
+    assert e.value.code == _abi.PLB_ERR_ARG and "quality" in str(e.value)
+    b.read_qual[12345] = 93
+    engine.population_run(b)
+    hap = (b"ACGTTGCA" * 8)[:60]
+    r = Read(b"ACGTTGCAAC" * 5, bytes([30] * 50), 100, 150)
+    bad = WindowBatch.from_windows([Window(100, 130, 90, [hap], [([], [], [r])])], 1)
+    with pytest.raises(PlbError) as e:
+        engine.population_run(bad)                     # host path: refused up front
+    assert e.value.code == _abi.PLB_ERR_SHAPE
+    engine.population_run(synth.make_batch(8))         # the context is still usable
+
+
+def test_reads_beyond_int16_score_range_take_the_exact_path(engine, oracle):
+    """A read whose qualities add up beyond the reference's own score range (15,871 phred, align.c:97) cannot use the
+    packed int16 recurrence; it is scored with the 32-bit one and still agrees with the oracle wherever the reference's
+    result is defined (scores below the range: a read that matches its haplotype up to a few errors)."""
+    rng = random.Random(9)
+    wins = []
+    for i in range(12):
+        L = rng.choice([180, 420, 700])
+        hap = cases.random_hap(rng, L + 120)
+        at = rng.randint(20, 80)
+        read = bytearray(hap[at:at + L])
+        for _ in range(rng.randint(0, 4)):
+            read[rng.randrange(L)] = ord(rng.choice("ACGT"))
+        q = bytes([rng.choice([90, 93, 60])] * L)       # 180 x 93 = 16,740 > 15,871
+        r = Read(bytes(read), q, 1000 + at, 1000 + at + L)
+        wins.append(Window(1000 + 40, 1000 + 100, 1000, [hap, cases.random_hap(rng, L + 120)[:L + 100] + hap[-20:]], [([r], [], [])]))
+    b = WindowBatch.from_windows(wins, 1)
+    ll, sc = engine.window_loglik(b)
+    ll0, sc0, _ = oracle.window_loglik(b)
+    ok = sc0 < 15871                                     # beyond that the reference itself is undefined
+    assert ok.sum() >= 12
+    assert np.array_equal(sc[ok], sc0[ok])

@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_abi.EXPORTED_SYMBOLS), declared ^ set(_abi.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.plb_abi_version() == 3
+    assert lib.plb_abi_version() == 4
 
 
 def test_no_gpu_fails_loudly():
@@ -75,7 +75,8 @@ def test_ll_offsets_and_validate():
     # haplotype shorter than read + 15: the reference would read out of bounds (calign.pyx:256-259)
     from platypus_b200.batch import Read, Window
     w = Window(100, 140, 50, [b"ACGT" * 10], [([Read(b"A" * 30, bytes([30] * 30), 100, 130)], [], [])])
-    s2 = WindowBatch.from_windows([w], 1).as_struct()
+    b2 = WindowBatch.from_windows([w], 1)   # keep the batch alive: the struct points into its arrays
+    s2 = b2.as_struct()
     assert lib.plb_validate(C.byref(s2), C.byref(opt), 0) == _abi.PLB_ERR_SHAPE
 
 
@@ -301,3 +302,76 @@ def test_with_haplotypes_builds_a_valid_window_model_batch(oracle):
     part = vset.slice_windows(2, 5)
     assert part.win_var_off[0] == 0 and part.n_vars(0) == vset.n_vars(2)
     assert np.array_equal(part.var_pos, vset.var_pos[vset.win_var_off[2]:vset.win_var_off[5]])
+
+
+def test_pack_bases_and_nibbles_match_numpy():
+    """plb_pack_bases_host / plb_pack_nibbles_host (staging row N3): 2-bit codes at any base offset, exceptions in order;
+    BAM nibbles (htslibWrapper.pyx:414-416) give the same bytes as packing the decoded ASCII."""
+    lib = _lib()
+    rng = np.random.default_rng(11)
+    nib_tab = np.frombuffer(b"=ACMGRSVTWYHKDBN", np.uint8)
+    code = {65: 0, 67: 1, 71: 2, 84: 3}
+    for n, base in ((0, 0), (1, 3), (37, 0), (150, 6), (1001, 2), (3 << 20, 1)):
+        nib = rng.choice(np.array([1, 2, 4, 8, 15, 3, 0], np.uint8), size=n, p=[.24, .24, .24, .24, .02, .01, .01])
+        ascii_ = nib_tab[nib]
+        bam = np.zeros((n + 1) // 2 + 1, np.uint8)
+        bam[:(n + 1) // 2] = (np.pad(nib, (0, n % 2))[0::2] << 4) | np.pad(nib, (0, n % 2))[1::2]
+        want = np.zeros((base + n + 3) // 4 + 1, np.uint8)
+        for jj in range(base):                             # earlier bases (all 'C') already packed in front
+            want[jj >> 2] |= 1 << (2 * (jj & 3))
+        pre = want.copy()
+        exc = [(base + i, int(ch)) for i, ch in enumerate(ascii_) if int(ch) not in code]
+        cd = np.array([code.get(int(ch), 0) for ch in ascii_], np.uint8) if n < 5000 else \
+            np.select([ascii_ == 65, ascii_ == 67, ascii_ == 71, ascii_ == 84], [0, 1, 2, 3], 0).astype(np.uint8)
+        j = base + np.arange(n)
+        np.bitwise_or.at(want, j >> 2, (cd << (2 * (j & 3))).astype(np.uint8))
+        for fn, src in ((lib.plb_pack_bases_host, ascii_), (lib.plb_pack_nibbles_host, bam)):
+            dst = pre.copy()
+            cap = len(exc) + 2
+            pos, chr_ = np.full(cap, -1, np.int64), np.zeros(cap, np.uint8)
+            k = C.c_int64(1)                                 # one entry already there: appended after it
+            src = np.ascontiguousarray(src)
+            assert fn(src.ctypes.data, n, dst.ctypes.data, base, pos.ctypes.data, chr_.ctypes.data, cap, C.byref(k)) == 0
+            assert np.array_equal(dst, want), (n, base)
+            assert k.value == 1 + len(exc)
+            assert [(int(a), int(b)) for a, b in zip(pos[1:k.value], chr_[1:k.value])] == exc
+            if exc:   # too small an exception array is an error, not an overrun
+                k = C.c_int64(0)
+                assert fn(src.ctypes.data, n, np.zeros_like(want).ctypes.data, base, pos.ctypes.data, chr_.ctypes.data,
+                          len(exc) - 1, C.byref(k)) == _abi.PLB_ERR_SHAPE
+
+
+def test_packed_batch_struct_and_validate():
+    lib = _lib()
+    b = cases.edge_batch(seed=5)
+    p = b.pack(lib)
+    assert p.seq_format == _abi.PLB_SEQ_2BIT and len(p.read_seq) == (int(b.read_seq_off[-1]) + 3) // 4 + 1
+    assert len(p.read_exc_pos) == int(np.count_nonzero(~np.isin(b.read_seq[:int(b.read_seq_off[-1])], np.frombuffer(b"ACGT", np.uint8))))
+    # unpacking on the host gives the original bytes back
+    for pk, exc_p, exc_c, orig, n in ((p.read_seq, p.read_exc_pos, p.read_exc_chr, b.read_seq, int(b.read_seq_off[-1])),
+                                      (p.hap_seq, p.hap_exc_pos, p.hap_exc_chr, b.hap_seq, int(b.hap_seq_off[-1]))):
+        i = np.arange(n)
+        back = np.frombuffer(b"ACGT", np.uint8)[(pk[i >> 2] >> (2 * (i & 3))) & 3].copy()
+        back[exc_p] = exc_c
+        assert np.array_equal(back, orig[:n])
+    s = p.as_struct()
+    assert lib.plb_validate(C.byref(s), C.byref(_abi.PlbOptions.default()), 0) == 0
+    assert p.input_nbytes() < b.input_nbytes()
+    bad = p.as_struct()
+    bad.seq_format = 7
+    assert lib.plb_validate(C.byref(bad), None, 0) == _abi.PLB_ERR_ARG
+
+
+def test_validate_skips_unscored_reads():
+    """A QC-fail read (or one that misses the window) is never aligned (chaplotype.pyx:343-361), so its length cannot
+    make a batch invalid; the same read as a broken mate is scored and does."""
+    from platypus_b200.batch import Read, Window
+    lib = _lib()
+    opt = _abi.PlbOptions.default()
+    hap = b"ACGT" * 10
+    long_qc = Read(b"A" * 30, bytes([30] * 30), 100, 130, 60, True)
+    far = Read(b"A" * 30, bytes([30] * 30), 400, 430, 60, False)
+    ok = WindowBatch.from_windows([Window(100, 140, 50, [hap], [([long_qc, far], [], [])])], 1)
+    assert lib.plb_validate(C.byref(ok.as_struct()), C.byref(opt), 0) == 0
+    bad = WindowBatch.from_windows([Window(100, 140, 50, [hap], [([], [], [far])])], 1)
+    assert lib.plb_validate(C.byref(bad.as_struct()), C.byref(opt), 0) == _abi.PLB_ERR_SHAPE
