@@ -516,55 +516,13 @@ def run_ours(args, rank, world, local_rank):
 
     stream = torch.cuda.Stream(device=dev)
     eng = Engine(local_rank, stream=stream.cuda_stream)
+    # The shard resident on this GPU and the path's one collective (all-gather of the per-window genotype likelihoods on a
+    # side stream, overlapped with the next step): platypus_b200.shard.DeviceShard - the multi-GPU API the package ships.
+    from platypus_b200.shard import DeviceShard
+    ds = DeviceShard(eng, batch, stream, opt=OPT)
+    handle, out, ll, gl_all, side = ds.handle, ds.out, ds.ll, ds.gl_all, ds.side
+    step, join_side = ds.step, ds.join
     with torch.cuda.stream(stream):
-        handle = eng.upload(batch)
-        out = {
-            "gl": torch.zeros((W, nI, Gm), dtype=torch.float64, device=dev),
-            "gl_log_max": torch.zeros((W, nI), dtype=torch.float64, device=dev),
-            "gof": torch.zeros((W, Gm, nI), dtype=torch.float64, device=dev),
-            "hap_like": torch.zeros((W, nI, Hm), dtype=torch.float64, device=dev),
-            "freq": torch.zeros((W, Hm), dtype=torch.float64, device=dev),
-            "em_post": torch.zeros((W, nI, Gm), dtype=torch.float64, device=dev),
-            "call": torch.zeros((W, nI), dtype=torch.int32, device=dev),
-            "var_phred": torch.zeros((W, V), dtype=torch.float64, device=dev),
-            "em_iters": torch.zeros((W,), dtype=torch.int32, device=dev),
-        }
-        n_pairs = int(batch.ll_offsets()[-1])
-        ll = torch.zeros((n_pairs,), dtype=torch.float64, device=dev)
-        ptrs = {k: v.data_ptr() for k, v in out.items()}
-        ptrs["max_haps"] = Hm
-        # The one collective of the path: all-gather of the per-window genotype likelihoods.  It runs on a side stream
-        # behind an event, so the next step's kernels start while this step's block travels; the likelihoods alternate
-        # between two buffers (step k+2 reuses step k's buffer and waits for that gather).
-        gl_all = torch.zeros((world, W, nI, Gm), dtype=torch.float64, device=dev) if world > 1 else None
-        gl_bufs = [out["gl"], torch.zeros_like(out["gl"])] if world > 1 else [out["gl"]]
-        ptr_sets = []
-        for g in gl_bufs:
-            q = dict(ptrs)
-            q["gl"] = g.data_ptr()
-            ptr_sets.append(q)
-        side = torch.cuda.Stream(device=dev) if world > 1 else None
-        computed = [torch.cuda.Event() for _ in gl_bufs]
-        gathered = [torch.cuda.Event() for _ in gl_bufs]
-        n_step = [0]
-
-        def step():
-            k = n_step[0] % len(gl_bufs)
-            if world > 1 and n_step[0] >= len(gl_bufs):
-                stream.wait_event(gathered[k])
-            eng.run_device(handle, ptr_sets[k], ll_ptr=ll.data_ptr(), opt=OPT)
-            if world > 1:
-                computed[k].record(stream)
-                side.wait_event(computed[k])
-                with torch.cuda.stream(side):
-                    dist.all_gather_into_tensor(gl_all, gl_bufs[k])
-                    gathered[k].record(side)
-            n_step[0] += 1
-
-        def join_side():
-            if world > 1:
-                stream.wait_stream(side)
-
         for _ in range(max(args.warmup, 3)):
             step()
         join_side()
@@ -602,7 +560,7 @@ def run_ours(args, rank, world, local_rank):
         # over PCIe while batch k computes.  Inputs are the staged form of the reads (2-bit bases + 8-bit qualities,
         # batch.pack(): what the N3 staging step produces from BAM nibbles); --ascii sends the byte-per-base arrays.
         if world > 1:
-            assert torch.equal(gl_all[rank], gl_bufs[(n_step[0] - 1) % len(gl_bufs)])   # the gathered block is this rank's block
+            assert torch.equal(gl_all[rank], ds.last_gl())   # the gathered block holds this rank's block
         src = batch if args.ascii else batch.pack()
         pinned = {}
         hb = type(batch)(**{f: (pin(getattr(src, f)).numpy() if isinstance(getattr(src, f), np.ndarray) else getattr(src, f))

@@ -58,7 +58,7 @@ static int host_threads() {
                            __LINE__);                                                              \
     } while (0)
 
-constexpr int kTimingRing = 64;
+constexpr int kTimingRing = 32;
 constexpr int kMaxChunks = 6;           // pipelined host path: chunks of windows per call
 constexpr int kMinChunkWindows = 1024;
 
@@ -84,6 +84,7 @@ struct JobSlot {
     Counters* h_ctr = nullptr;              // pinned
     cudaEvent_t ev_chunk[kMaxChunks + 1];   // H2D of chunk k done
     cudaEvent_t ev_unpack[kMaxChunks];      // packed input: chunk k's bases are ASCII again
+    cudaEvent_t ev_anchor[kMaxChunks];      // chunk k's anchor kernel has finished (software pipeline of the chunks)
     cudaEvent_t ev_done[3];                 // last work of the job on compute stream k
     cudaEvent_t ev_ctr;                     // counters are back in h_ctr
     bool busy = false;
@@ -109,7 +110,8 @@ struct PlbContext {
     cudaEvent_t ev;
     bool timing;
     int n_timed;                                        // runs recorded since plb_set_timing(1)
-    cudaEvent_t kev[kTimingRing][PLB_N_KERNELS + 1];    // ring of per-run event sets
+    cudaEvent_t kev[kTimingRing][kMaxChunks][PLB_N_KERNELS + 1];   // ring of per-run, per-chunk event sets
+    int kev_chunks[kTimingRing];                        // chunks recorded in each ring entry
     Counters* d_ctr() { return slot[cur].d_ctr; }
     Counters* h_ctr() { return slot[cur].h_ctr; }
 };
@@ -196,6 +198,7 @@ extern "C" int plb_context_create(int device, void* stream, PlbContext** out) {
         memset(js.h_ctr, 0, sizeof(Counters));
         for (int i = 0; i <= kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&js.ev_chunk[i], cudaEventDisableTiming));
         for (int i = 0; i < kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&js.ev_unpack[i], cudaEventDisableTiming));
+        for (int i = 0; i < kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&js.ev_anchor[i], cudaEventDisableTiming));
         for (int i = 0; i < 3; ++i) CU(cudaEventCreateWithFlags(&js.ev_done[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&js.ev_ctr, cudaEventDisableTiming));
     }
@@ -209,7 +212,8 @@ extern "C" int plb_context_create(int device, void* stream, PlbContext** out) {
     c->timing = false;
     c->n_timed = 0;
     for (int r = 0; r < kTimingRing; ++r)
-        for (int i = 0; i <= PLB_N_KERNELS; ++i) CU(cudaEventCreate(&c->kev[r][i]));
+        for (int k = 0; k < kMaxChunks; ++k)
+            for (int i = 0; i <= PLB_N_KERNELS; ++i) CU(cudaEventCreate(&c->kev[r][k][i]));
     *out = c;
     return PLB_OK;
 }
@@ -230,6 +234,7 @@ extern "C" void plb_context_destroy(PlbContext* c) {
         for (auto& pb : js.pin.blocks) cudaFreeHost(pb.first);
         for (int i = 0; i <= kMaxChunks; ++i) cudaEventDestroy(js.ev_chunk[i]);
         for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(js.ev_unpack[i]);
+        for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(js.ev_anchor[i]);
         for (int i = 0; i < 3; ++i) cudaEventDestroy(js.ev_done[i]);
         cudaEventDestroy(js.ev_ctr);
     }
@@ -241,7 +246,8 @@ extern "C" void plb_context_destroy(PlbContext* c) {
     cudaEventDestroy(c->ev_s2);
     cudaEventDestroy(c->ev_s3);
     for (int r = 0; r < kTimingRing; ++r)
-        for (int i = 0; i <= PLB_N_KERNELS; ++i) cudaEventDestroy(c->kev[r][i]);
+        for (int k = 0; k < kMaxChunks; ++k)
+            for (int i = 0; i <= PLB_N_KERNELS; ++i) cudaEventDestroy(c->kev[r][k][i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -937,12 +943,20 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
         return set_err(PLB_ERR_SHAPE, "anchor tile needs %zu bytes of shared memory", ch.a_smem);
     // k_anchor is compiled for 4 resident CTAs per SM (__launch_bounds__(256, 4): 64 registers per thread)
     ch.a_occ = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / (ch.a_smem + 1024)));
+    // Resident CTAs per SM of the two persistent kernels.  When the chunks of a batch are pipelined over several streams
+    // (chunk k+1's anchor kernel next to chunk k's band alignment) the grids are capped so that both fit an SM at once:
+    // k_dp 80 registers x 256 threads and ~70 KB of shared memory per CTA, k_anchor 64 x 256 and ~42 KB.
+    const int cap_a = getenv("PLB_ANCHOR_OCC") ? std::max(1, atoi(getenv("PLB_ANCHOR_OCC"))) : 0;
+    const int cap_d = getenv("PLB_DP_OCC") ? std::max(1, atoi(getenv("PLB_DP_OCC"))) : 0;
+    if (cap_a) ch.a_occ = std::min(ch.a_occ, cap_a);
     ch.d_smem = (size_t)ch.dp.prof_words * 4 + (size_t)ch.dp.rec_count * sizeof(HapRec) +
                 (size_t)ch.dp.max_slots * (sizeof(DpSlot) + 4) + (size_t)ch.dp.max_group * 4 + (size_t)ch.dp.max_pairs * 12 +
                 (size_t)kProfTabWords * 4 + 256 + 64;
     if (ch.d_smem + 1024 > (size_t)c->smem_optin)
         return set_err(PLB_ERR_SHAPE, "dp tile needs %zu bytes of shared memory", ch.d_smem);
     ch.d_occ = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (ch.d_smem + 1024)));
+    ch.d_occ = std::min(ch.d_occ, 3);   // __launch_bounds__(256, 3)
+    if (cap_d) ch.d_occ = std::min(ch.d_occ, cap_d);
     // Tail splitting: the tiles left over after the last full wave of the persistent DP grid would keep a
     // few CTAs busy for a whole tile time while the others idle.  Cut each of them into k pieces by slot
     // range (k <= 3: a piece still fills the CTA's threads about once) when that shortens the last wave.
@@ -1225,8 +1239,23 @@ extern "C" int plb_batch_upload(PlbContext* c, const PlbWindowBatch* hb, PlbDevi
     PlbDeviceBatch* db = nullptr;
     if ((rc = prepare_batch(c, hb, &db))) return rc;
     cudaStream_t st = c->stream;
-    if ((rc = copy_seq_for_windows(c, db, hb, 0, hb->n_windows, st)) || (rc = unpack_fresh(c, db, 0, st)) ||
-        (rc = plan_chunk(c, db, hb, 0, hb->n_windows, st)) || (rc = derive_all(c, db, st))) {
+    // The device-resident run may cut the batch into chunks that run software-pipelined on the context's streams
+    // (PLB_DEVICE_CHUNKS; default one chunk = plain kernel sequence).
+    const int dev_chunks = getenv("PLB_DEVICE_CHUNKS") ? std::max(1, std::min(kMaxChunks, atoi(getenv("PLB_DEVICE_CHUNKS")))) : 1;
+    const int nch = std::max(1, std::min(dev_chunks, hb->n_windows / kMinChunkWindows));
+    db->chunks.reserve(nch);
+    rc = copy_seq_for_windows(c, db, hb, 0, hb->n_windows, st);
+    if (!rc) rc = unpack_fresh(c, db, 0, st);
+    for (int k = 0; k < nch && !rc; ++k) {
+        const int wave = c->n_sm * 3;
+        auto cutw = [&](int i) {
+            int64_t v = (int64_t)hb->n_windows * i / nch;
+            if (i > 0 && i < nch && hb->n_windows / nch >= 2 * wave) v = (v + wave / 2) / wave * wave;
+            return (int)v;
+        };
+        if (cutw(k + 1) > cutw(k)) rc = plan_chunk(c, db, hb, cutw(k), cutw(k + 1), st);
+    }
+    if (rc || (rc = derive_all(c, db, st))) {
         cudaStreamSynchronize(st);
         plb_batch_free(c, db);
         return rc;
@@ -1286,9 +1315,13 @@ static int mode_queues(PlbContext* c, PlbDeviceBatch* db, bool multi) {
 
 // Launches the whole kernel sequence for one planned chunk of windows on stream st.  `timed` records
 // the per-kernel events of plb_kernel_times (whole-batch launches only).
+// `anchor_after` / `anchor_done`: when the chunks of a batch run on several streams they are software-pipelined - chunk
+// k+1's anchor kernel starts when chunk k's has finished, i.e. next to chunk k's band-alignment kernel (the two kernels
+// are sized to share an SM, see plan_chunk) instead of next to chunk k's anchor kernel.
 static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch, const PlbOptions* opt,
                           PlbPopulationOut* pop, PlbLoglikOut* llo, cudaStream_t st, bool timed, const Queue& q,
-                          bool derive = false) {
+                          bool derive = false, int timed_chunk = 0, cudaEvent_t anchor_after = nullptr,
+                          cudaEvent_t anchor_done = nullptr) {
     int rc;
     DevBatch& d = db->d;
     const int w0 = ch.w0, w1 = ch.w1;
@@ -1305,7 +1338,7 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
     CU(cudaMemsetAsync(q.count, 0, 12, st));   // queue fill + the tile counters of k_anchor and k_dp
     const int tslot = c->n_timed % kTimingRing;
     auto mark = [&](int i) {
-        if (timed && c->timing) cudaEventRecord(c->kev[tslot][i], st);
+        if (timed && c->timing) cudaEventRecord(c->kev[tslot][timed_chunk][i], st);
     };
     mark(0);
     if (h1 > h0) {
@@ -1319,11 +1352,13 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
         if ((rc = opt_in_smem(k_anchor<false>, ch.a_smem)) || (modes && (rc = opt_in_smem(k_anchor<true>, ch.a_smem))))
             return rc;
         const int grid = std::max(1, std::min(ap.n_tiles, c->n_sm * ch.a_occ));
+        if (anchor_after) CU(cudaStreamWaitEvent(st, anchor_after, 0));
         if (modes)
             k_anchor<true><<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr());
         else
             k_anchor<false><<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr());
         if ((rc = launch_check(c, "k_anchor"))) return rc;
+        if (anchor_done) CU(cudaEventRecord(anchor_done, st));
         mark(2);
         if (modes)
             k_general<true><<<c->n_sm * 4, 128, 0, st>>>(d, q, sp);
@@ -1375,7 +1410,6 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
         mark(5);
     }
     mark(6);
-    if (timed && c->timing) c->n_timed++;
     return PLB_OK;
 }
 
@@ -1403,9 +1437,32 @@ extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOption
     cudaStream_t st = c->stream;
     CU(cudaMemsetAsync(c->d_ctr(), 0, sizeof(Counters), st));
     const bool modes = opt->calc_flank_score || opt->use_mapq_cap;
-    if (modes && (rc = mode_queues(c, db, false))) return rc;
-    for (const ChunkPlan& ch : db->chunks)
-        if ((rc = launch_windows(c, db, ch, opt, pop, llo, st, db->chunks.size() == 1, modes ? db->mq : db->q))) return rc;
+    if (modes && (rc = mode_queues(c, db, db->chunks.size() > 1))) return rc;
+    const int nch = (int)db->chunks.size();
+    if (nch == 1) {
+        if ((rc = launch_windows(c, db, db->chunks[0], opt, pop, llo, st, true, modes ? db->mq : db->q))) return rc;
+    } else {
+        // chunk k on stream k mod 3, forked from / joined into the context's stream; anchor kernels chained
+        if (modes && (rc = mode_queues(c, db, true))) return rc;
+        JobSlot& js = c->slot[0];
+        cudaStream_t ks[3] = {st, c->stream2, c->stream3};
+        const Queue* qs[3] = {modes ? &db->mq : &db->q, modes ? &db->mq2 : &db->q2, modes ? &db->mq3 : &db->q3};
+        CU(cudaEventRecord(c->ev_s2, st));
+        CU(cudaStreamWaitEvent(c->stream2, c->ev_s2, 0));
+        CU(cudaStreamWaitEvent(c->stream3, c->ev_s2, 0));
+        for (int k = 0; k < nch; ++k)
+            if ((rc = launch_windows(c, db, db->chunks[k], opt, pop, llo, ks[k % 3], true, *qs[k % 3], false, k,
+                                     k > 0 ? js.ev_anchor[k - 1] : nullptr, js.ev_anchor[k])))
+                return rc;
+        CU(cudaEventRecord(c->ev_s2, c->stream2));
+        CU(cudaStreamWaitEvent(st, c->ev_s2, 0));
+        CU(cudaEventRecord(c->ev_s3, c->stream3));
+        CU(cudaStreamWaitEvent(st, c->ev_s3, 0));
+    }
+    if (c->timing) {
+        c->kev_chunks[c->n_timed % kTimingRing] = nch;
+        c->n_timed++;
+    }
     CU(cudaMemcpyAsync(c->h_ctr(), c->d_ctr(), sizeof(Counters), cudaMemcpyDeviceToHost, st));
     return PLB_OK;
 }
@@ -1452,11 +1509,12 @@ extern "C" int plb_kernel_times(PlbContext* c, float* ms) {
     const int n = c->n_timed < kTimingRing ? c->n_timed : kTimingRing;
     for (int i = 0; i < PLB_N_KERNELS; ++i) {
         double sum = 0.0;
-        for (int r = 0; r < n; ++r) {
-            float t = 0.f;
-            CU(cudaEventElapsedTime(&t, c->kev[r][i], c->kev[r][i + 1]));
-            sum += t;
-        }
+        for (int r = 0; r < n; ++r)
+            for (int k = 0; k < c->kev_chunks[r]; ++k) {   // chunks of a pipelined run overlap: their kernel times add up
+                float t = 0.f;
+                CU(cudaEventElapsedTime(&t, c->kev[r][k][i], c->kev[r][k][i + 1]));
+                sum += t;
+            }
         ms[i] = n ? (float)(sum / n) : 0.f;
     }
     return n;
@@ -1589,7 +1647,7 @@ static int submit_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions
     // Chunking.  A lone call wants its first kernels early: up to six chunks whose sizes grow x1.3.  When another job
     // is still computing, this job's bytes travel behind that job's kernels anyway, so it is cut into few chunks (each
     // chunk costs ~0.25 ms of kernel tails); PLB_PIPE_CHUNKS overrides that number.
-    static const int pipe_chunks = getenv("PLB_PIPE_CHUNKS") ? std::max(1, std::min(kMaxChunks, atoi(getenv("PLB_PIPE_CHUNKS")))) : 2;
+    const int pipe_chunks = getenv("PLB_PIPE_CHUNKS") ? std::max(1, std::min(kMaxChunks, atoi(getenv("PLB_PIPE_CHUNKS")))) : 2;
     int n_chunks = std::max(1, std::min(kMaxChunks, W / kMinChunkWindows));
     const bool pipelined = busy > 0;
     if (pipelined) n_chunks = std::min(n_chunks, pipe_chunks);
@@ -1631,6 +1689,7 @@ static int submit_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions
     };
     // The DMA must never wait for the host: the copies of chunk k+1 are queued BEFORE chunk k is planned,
     // and once the first chunk is launched all remaining copies are queued at once.
+    const bool chain_anchors = !getenv("PLB_NO_ANCHOR_CHAIN");
     int copies_queued = 0;
     auto queue_copies = [&](int upto) {
         for (; copies_queued < upto && copies_queued < n_chunks && rc == PLB_OK && e == cudaSuccess; ++copies_queued) {
@@ -1661,7 +1720,8 @@ static int submit_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions
         }
         tmark(kst);
         if ((rc = launch_windows(c, db, db->chunks.back(), opt, hpop ? &dpop : nullptr, &dll, kst, false,
-                                 *kqueues[k % 3], true)))
+                                 *kqueues[k % 3], true, 0, (chain_anchors && k > 0) ? js.ev_anchor[k - 1] : nullptr,
+                                 js.ev_anchor[k])))
             break;
         tmark(kst);
         if (hpop) {

@@ -1061,20 +1061,23 @@ struct DpSlot {
 // (pos_inf >> 2 = 15,872 phred, align.c:97; a score never exceeds the sum of the read's qualities plus gap costs that the
 // same margin covers); a read whose qualities add up beyond that takes the 32-bit recurrence instead (flag bit 1).
 constexpr int kMaxPackedQualSum = 15871 - 256;
-__device__ __forceinline__ void row_quality_check(int qs, int32_t* flags, Counters* ctr) {
+__device__ __forceinline__ void row_quality_check(int qs, int32_t* flags, int* n_exact, Counters* ctr) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(0xFFFFFFFFu, qs, o);
-    if ((threadIdx.x & 31) == 0) {
+    if ((threadIdx.x & 31) == 0 && qs > kMaxPackedQualSum) {
         if (qs >= (1 << 20)) {
             if (ctr) atomicOr(&ctr->err, kErrQuality);
             qs &= (1 << 20) - 1;
         }
-        if (qs > kMaxPackedQualSum) *flags |= 2;
+        if (qs > kMaxPackedQualSum) {
+            *flags |= 2;
+            *n_exact = 1;
+        }
     }
 }
 
 template <int NTHR>
-__global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParams sp, double* __restrict__ ll_out,
+__global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScoreParams sp, double* __restrict__ ll_out,
                                              int32_t* __restrict__ score_out, int* __restrict__ tile_counter,
                                              Counters* __restrict__ ctr) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -1087,7 +1090,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
     u32* s_task = (u32*)(s_best + plan.max_pairs);               // compacted tasks
     u32* s_ptab = s_task + 2 * plan.max_pairs;                   // profile word by (base code, quality): [5][128]
     uint8_t* s_code = (uint8_t*)(s_ptab + kProfTabWords);        // byte -> base code 0..3 (exact A/C/G/T) or 4
-    __shared__ int s_ntask;
+    __shared__ int s_ntask, s_nexact;
     __shared__ __align__(8) uint64_t s_bar;   // counts the bytes of the tile's TMA copies
 
     const int tid = threadIdx.x;
@@ -1112,6 +1115,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
         const int ns = (int)(tile.s1 - tile.s0);
         if (tid == 0) {
             s_ntask = 0;
+            s_nexact = 0;
             int ro = 0;
             for (int g = 0; g < nh; ++g) {
                 const int h = tile.h0 + g;
@@ -1264,7 +1268,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                             row[y] = y < ds.len ? s_ptab[((u32)s_code[cb[k]] << 7) | (qb[k] & 127u)] : 0u;
                         }
                     }
-                    row_quality_check(qs, &s_slot[s].flags, ctr);
+                    row_quality_check(qs, &s_slot[s].flags, &s_nexact, ctr);
                     continue;
                 }
                 const uint8_t* rs = b.read_seq + o;
@@ -1287,7 +1291,7 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
                         }
                     }
                 }
-                row_quality_check(qs, &s_slot[s].flags, ctr);
+                row_quality_check(qs, &s_slot[s].flags, &s_nexact, ctr);
             }
         }
         // best scores start from what the general path produced; compact packed-path tasks
@@ -1329,18 +1333,21 @@ __global__ void __launch_bounds__(NTHR) k_dp(DevBatch b, DpPlan plan, ScoreParam
             const int p = (int)(tk >> 15), start = (int)(tk & 0x7FFFu);
             const int s = s_order[p / nh], g = p % nh;
             const DpSlot ds = s_slot[s];
-            int v;
-            if (ds.flags & 2) {   // the read's qualities add up beyond the int16 range: exact 32-bit recurrence
-                const int h = tile.h0 + g;
-                v = band_dp_general(b.hap_seq + b.hap_seq_off[h] + start, b.gap_open + b.hap_seq_off[h] + h + start,
-                                    b.read_seq + b.read_seq_off[ds.read], b.read_qual + b.read_seq_off[ds.read], ds.len,
-                                    sp.ext, sp.nuc);
-            } else {
-                v = five  ? band_dp_fast5(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc)
-                    : six ? band_dp_fast6(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc)
-                          : band_dp_fast(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc);
-            }
+            if (ds.flags & 2) continue;   // qualities beyond the int16 range: second pass below
+            const int v = five  ? band_dp_fast5(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc)
+                          : six ? band_dp_fast6(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc)
+                                : band_dp_fast(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc);
             atomicMin(&s_best[p], v);
+        }
+        if (s_nexact) {   // block-uniform (written before the barrier above): the exact 32-bit recurrence, out of line
+            for (int k = tid; k < ntask; k += NTHR) {
+                const u32 tk = s_task[k];
+                const int p = (int)(tk >> 15), start = (int)(tk & 0x7FFFu);
+                const int s = s_order[p / nh], g = p % nh;
+                if (!(s_slot[s].flags & 2)) continue;
+                const int v = general_dp_now<false>(b, tile.h0 + g, s_slot[s].read, start, 0, s_slot[s].len, sp);
+                atomicMin(&s_best[p], v);
+            }
         }
         __syncthreads();
         // score -> log-likelihood (chaplotype.pyx:675-676) and output

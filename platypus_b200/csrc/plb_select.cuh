@@ -74,7 +74,9 @@ __host__ __device__ __forceinline__ void walk_haplotype(int win_start, int win_e
 }
 
 constexpr int kBuildWarps = 4;
-constexpr int kBuildMaxPieces = 2 * 64 + 4;
+// walk_haplotype emits up to three pieces per variant (reference stretch, anchor base, added bases) plus the two flanks
+// and the window's tail: 3 * 64 + 3 for the 64 variants a mask can name
+constexpr int kBuildMaxPieces = 3 * 64 + 3;
 
 // One warp per haplotype: lane 0 lists the pieces, all lanes copy them.
 __global__ void __launch_bounds__(32 * kBuildWarps) k_build_haps(int n_haps, const int32_t* __restrict__ hap_win,
@@ -1214,6 +1216,10 @@ extern "C" int plb_select_haplotypes_host(PlbContext* c, const PlbWindowBatch* r
         SEL_TRY(launch_check(c, "k_build_haps"));
         SEL_CU(cudaEventRecord(G.ev[3], st));
         SEL_TRY(launch_windows(c, G.rd, G.rd->chunks[0], &opt, nullptr, nullptr, st, c->timing, modes ? G.rd->mq : G.rd->q));
+        if (c->timing) {   // one ring entry per round launch (plb_kernel_times averages them)
+            c->kev_chunks[c->n_timed % kTimingRing] = 1;
+            c->n_timed++;
+        }
         SEL_CU(cudaEventRecord(G.ev[4], st));
         k_trial_score<<<(R.nh + 3) / 4, 128, 0, st>>>(G.rd->d, G.rd->ll_scratch, G.d_llref, R.nh, G.d_score);
         SEL_TRY(launch_check(c, "k_trial_score"));

@@ -53,6 +53,49 @@ def test_sharded_gather_equals_single_process(tmp_path, n_windows, oracle):
     assert np.array_equal(got["var_phred"][:, :nv], want["var_phred"])
 
 
+def _ragged_batch(n_windows):
+    """Windows with 2..5 haplotypes (what the selection loop leaves), fewest first, so the ranks' local maxima differ."""
+    from platypus_b200 import synth
+    from platypus_b200.batch import concat_batches
+    parts = [synth.make_batch(1, n_haps=2 + (4 * w) // max(1, n_windows), n_reads=6, read_len=60, hap_len=130, window_offset=w)
+             for w in range(n_windows)]
+    return concat_batches(parts)
+
+
+def _ragged_worker(rank, world, port, n_windows, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from oracle import oracle as O
+    from platypus_b200 import shard
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        batch = _ragged_batch(n_windows)
+
+        def compute(b):   # like Engine.population_run(b): strides by the largest haplotype count of THIS shard
+            arrs, _, _, _ = O.population_run(b)
+            return arrs
+
+        got = shard.run_sharded(batch, compute, keys=("gl", "gof", "freq", "call", "em_iters"))
+        if rank == 0:
+            np.savez(out_path, **got)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_windows", [9, 1])
+def test_sharded_gather_ragged_haplotype_counts(tmp_path, n_windows, oracle):
+    """Ranks whose windows have different haplotype counts stride their blocks differently; run_sharded pads to the
+    common shape, keeps integer outputs integer, and an empty rank (1 window on 2 ranks) adopts shape and dtype."""
+    out = str(tmp_path / "ragged.npz")
+    mp.spawn(_ragged_worker, args=(2, _free_port(), n_windows, out), nprocs=2, join=True)
+    got = np.load(out)
+    batch = _ragged_batch(n_windows)
+    want, _, _, _ = oracle.population_run(batch)
+    for k in ("gl", "gof", "freq", "call", "em_iters"):
+        assert got[k].dtype == want[k].dtype and np.array_equal(got[k], want[k]), k
+
+
 def test_shard_bounds_cover_all_windows():
     from platypus_b200.batch import shard_bounds
     for n in (0, 1, 5, 8, 10001):
