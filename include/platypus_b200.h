@@ -456,6 +456,81 @@ int plb_select_replay_host(const PlbWindowBatch* ref_batch, const PlbVariantSet*
  * the scoring rounds.  Writes min(n, 10) values. */
 int plb_select_stats(PlbContext* ctx, double* out, int n);
 
+/* -- N3: read staging (the step before the window model) ------------------------------------------------ */
+
+/*
+ * n alignment records of a BAM file in file order, as arrays of the record's own fields (SAM specification 4.2):
+ * what a BGZF / BAM reader has in hand before anything is decoded.  Sequences stay in BAM's 4-bit encoding.
+ */
+typedef struct PlbBamRecords {
+    int32_t n;
+    const int32_t*  ref_id;      /* [n] refID                                                         */
+    const int32_t*  pos;         /* [n] 0-based leftmost mapped coordinate                            */
+    const uint8_t*  mapq;        /* [n]                                                               */
+    const uint16_t* flag;        /* [n] bitwise FLAG                                                  */
+    const int32_t*  mate_ref_id; /* [n] next refID                                                    */
+    const int32_t*  mate_pos;    /* [n] next pos                                                      */
+    const int32_t*  tlen;        /* [n] template length (cAlignedRead.insertSize)                     */
+    const int64_t*  cigar_off;   /* [n+1] offsets into cigar                                          */
+    const uint32_t* cigar;       /* BAM encoding: op_len << 4 | op                                    */
+    const int64_t*  seq_off;     /* [n+1] BASE offsets: l_seq = seq_off[i+1] - seq_off[i]; qual is indexed by them */
+    const int64_t*  nib_off;     /* [n+1] BYTE offsets of each record's 4-bit packed sequence in nib   */
+    const uint8_t*  nib;         /* two bases per byte, high nibble first, codes "=ACMGRSVTWYHKDBN"    */
+    const uint8_t*  qual;        /* raw phred; a record whose first quality byte is 0xFF has none       */
+} PlbBamRecords;
+
+/* The read-filter options of bamReadBuffer (src/cython/cwindow.pyx:490-528; defaults of src/python/runner.py:551-580). */
+typedef struct PlbReadFilterOptions {
+    int32_t min_good_qual_bases;   /* minGoodQualBases 20                 */
+    int32_t min_map_qual;          /* minMapQual 20                       */
+    int32_t min_base_qual;         /* minBaseQual 20                      */
+    int32_t trim_read_flank;       /* trimReadFlank 0                     */
+    int32_t trim_overlapping;      /* trimOverlapping 1                   */
+    int32_t trim_adapter;          /* trimAdapter 1                       */
+    int32_t trim_soft_clipped;     /* trimSoftClipped 1                   */
+    int32_t filter_duplicates;     /* filterDuplicates 1                  */
+    int32_t filter_mate_unmapped;  /* filterReadsWithUnmappedMates 1      */
+    int32_t filter_mate_distant;   /* filterReadsWithDistantMates 1       */
+    int32_t filter_small_insert;   /* filterReadPairsWithSmallInserts 1   */
+} PlbReadFilterOptions;
+
+/* Outputs of plb_stage_reads_host, caller-allocated, one entry per input record unless noted. */
+typedef struct PlbStagedReads {
+    uint8_t*  kept;       /* 1 = the record is a read (ReadIterator.get returned one), 0 = no sequence / no qualities */
+    uint8_t*  good;       /* 1 = bamReadBuffer.reads, 0 = bamReadBuffer.badReads                       */
+    int32_t*  read_pos;   /* cAlignedRead.pos: first base of the read (leading soft clip subtracted)    */
+    int32_t*  read_end;   /* cAlignedRead.end: bam_endpos                                              */
+    uint16_t* flag_out;   /* bitFlag after Read_SetQCFail                                              */
+    uint8_t*  qual_out;   /* [seq_off[n]] qualities after trimming                                     */
+    uint8_t*  seq2;       /* [(seq_off[n] + 3) / 4 + 1] bases as 2-bit codes at the records' base offsets: with
+                             seq_off as read_seq_off this IS the read_seq of a PLB_SEQ_2BIT batch       */
+    int64_t   exc_cap;    /* capacity of exc_pos / exc_chr                                             */
+    int64_t   n_exc;      /* out: bases that are not A/C/G/T (ascending)                               */
+    int64_t*  exc_pos;
+    uint8_t*  exc_chr;
+    int32_t   counts[7];  /* filteredReadCountsByType: low-quality bases, unmapped, mate unmapped, mate distant,
+                             small insert, duplicate, low mapping quality (cwindow.pyx:40-46); -1 for a
+                             filter that is switched off, as in the reference (cwindow.pyx:516-526)     */
+} PlbStagedReads;
+
+/*
+ * Replaces, for every record of a buffer at once, ReadIterator.get (src/cython/htslibWrapper.pyx:328-406),
+ * bamReadBuffer.addReadToBuffer and checkAndTrimRead (src/cython/cwindow.pyx:560-595, 332-481): which list the read
+ * joins, its QC-fail flag, its trimmed qualities, its pos / end - and packs the bases from BAM nibbles into the 2-bit
+ * read pool of a PLB_SEQ_2BIT batch.  Host only (no GPU work; ctx-free).
+ */
+int plb_stage_reads_host(const PlbBamRecords* records, const PlbReadFilterOptions* opt, PlbStagedReads* out);
+
+/*
+ * Replaces ReadArray.setWindowPointers (src/cython/cwindow.pyx:208-236) for many windows: over a position-sorted read
+ * list, window w gets the contiguous slice [lo_out[w], hi_out[w]) from the first read with pos >= max(1, start -
+ * longestRead) (skipping leading reads that end at or before start) up to the first read with pos >= end.  The
+ * bisection is the reference's own (bisectReadsLeft, cwindow.pyx:276-300), so a list that is slightly out of order - pos
+ * has a leading soft clip subtracted, file order does not - yields the reference's slices too.
+ */
+int plb_window_slices_host(int32_t n_reads, const int32_t* read_pos, const int32_t* read_end, int32_t n_windows,
+                           const int32_t* win_start, const int32_t* win_end, int32_t* lo_out, int32_t* hi_out);
+
 /* -- device-resident variants (inputs already in HBM; used by the multi-GPU driver) -- */
 
 /* Copies a HOST batch into device memory owned by the context and returns an opaque

@@ -409,3 +409,82 @@ def select_haplotypes(bytes genome, int win_start, int win_end, list variants, l
         for (a, n) in all_arrays:
             _free_reads(<cAlignedRead**><size_t>a, n)
     return out
+
+
+def stage_reads(list reads, int region_start, int region_end, list windows, dict overrides=None):
+    """Read staging (SURVEY 8f N3) through the reference's own bamReadBuffer: every read goes through
+    addReadToBuffer -> checkAndTrimRead (src/cython/cwindow.pyx:560-595, 332-481), then
+    ReadArray.setWindowPointers (cwindow.pyx:208-236) is asked for each window.
+
+    reads      BAM records in file order as (seq, qual, [(cigar op, length), ...], chromID, pos, end, mapq, bitFlag,
+               mateChromID, matePos, insertSize) - pos / end already as ReadIterator.get derives them
+               (htslibWrapper.pyx:383-401; the decoder is the caller's)
+    windows    [(start, end), ...]
+    overrides  option values other than the defaults of runner.py:551-580
+    Returns dict: good [n] (1 = reads list, 0 = badReads list), qual [n] (bytes after trimming), flag [n] (bitFlag after
+    Read_SetQCFail), counts [7] (filteredReadCountsByType) and windows [(good_lo, good_hi, bad_lo, bad_hi)] as indices
+    into the good / bad lists."""
+    opts = _Options(0)
+    for k, v in (overrides or {}).items():
+        setattr(opts, k, v)
+    cdef bytes name = b"chr"
+    cdef bamReadBuffer buf = bamReadBuffer(name, region_start, region_end, opts)
+    cdef int n = len(reads), i, j, nc
+    cdef cAlignedRead** arr = <cAlignedRead**>calloc(n + 1, sizeof(cAlignedRead*))
+    cdef cAlignedRead* r
+    cdef bytes seq, qual
+    cdef list keep = []
+    cdef cwindow.ReadArray ga, ba
+    out = {"good": [], "qual": [], "flag": [], "counts": [], "windows": []}
+    try:
+        for i in range(n):
+            seq, qual, cigar, chrom_id, pos, end, mapq, flag, mate_chrom, mate_pos, isize = reads[i]
+            keep.append(seq)
+            r = <cAlignedRead*>calloc(1, sizeof(cAlignedRead))
+            r.seq = <char*>seq
+            r.rlen = len(seq)
+            r.qual = <char*>malloc(r.rlen + 1)
+            memcpy(r.qual, <char*>qual, r.rlen)
+            r.qual[r.rlen] = 0
+            nc = len(cigar)
+            r.cigarLen = nc
+            r.cigarOps = <short*>malloc(2 * max(nc, 1) * sizeof(short))
+            for j in range(nc):
+                r.cigarOps[2 * j] = cigar[j][0]
+                r.cigarOps[2 * j + 1] = cigar[j][1]
+            r.chromID = chrom_id
+            r.pos = pos
+            r.end = end
+            r.mapq = mapq
+            r.bitFlag = flag
+            r.mateChromID = mate_chrom
+            r.matePos = mate_pos
+            r.insertSize = isize
+            r.hash = NULL
+            arr[i] = r
+        for i in range(n):
+            buf.addReadToBuffer(arr[i])
+        ga = buf.reads
+        ba = buf.badReads
+        is_good = {}
+        for i in range(ga.getSize()):
+            is_good[<size_t>ga.array[i]] = 1
+        for i in range(n):
+            out["good"].append(1 if (<size_t>arr[i]) in is_good else 0)
+            out["qual"].append(<bytes>arr[i].qual[:arr[i].rlen])
+            out["flag"].append(arr[i].bitFlag)
+        out["counts"] = [buf.filteredReadCountsByType[i] for i in range(7)]
+        for (ws, we) in windows:
+            ga.setWindowPointers(ws, we)
+            ba.setWindowPointers(ws, we)
+            out["windows"].append((ga.windowStart - ga.array, ga.windowEnd - ga.array,
+                                   ba.windowStart - ba.array, ba.windowEnd - ba.array))
+    finally:
+        # the buffers' arrays hold borrowed pointers (destroyRead is a no-op in this build): free the reads here
+        for i in range(n):
+            if arr[i] != NULL:
+                free(arr[i].qual)
+                free(arr[i].cigarOps)
+                free(arr[i])
+        free(arr)
+    return out

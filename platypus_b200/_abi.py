@@ -86,6 +86,32 @@ class PlbSelectOut(C.Structure):
     _fields_ = [("max_sel", C.c_int32), ("n_sel", _p), ("sel_mask", _p), ("sel_score", _p), ("n_scored", _p)]
 
 
+class PlbBamRecords(C.Structure):
+    _fields_ = [("n", C.c_int32), ("ref_id", _p), ("pos", _p), ("mapq", _p), ("flag", _p), ("mate_ref_id", _p),
+                ("mate_pos", _p), ("tlen", _p), ("cigar_off", _p), ("cigar", _p), ("seq_off", _p), ("nib_off", _p),
+                ("nib", _p), ("qual", _p)]
+
+
+class PlbReadFilterOptions(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("min_good_qual_bases", "min_map_qual", "min_base_qual", "trim_read_flank",
+                                         "trim_overlapping", "trim_adapter", "trim_soft_clipped", "filter_duplicates",
+                                         "filter_mate_unmapped", "filter_mate_distant", "filter_small_insert")]
+
+    @classmethod
+    def default(cls, **kw):
+        """Defaults of src/python/runner.py:551-580."""
+        o = cls(20, 20, 20, 0, 1, 1, 1, 1, 1, 1, 1)
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+
+class PlbStagedReads(C.Structure):
+    _fields_ = [("kept", _p), ("good", _p), ("read_pos", _p), ("read_end", _p), ("flag_out", _p), ("qual_out", _p),
+                ("seq2", _p), ("exc_cap", C.c_int64), ("n_exc", C.c_int64), ("exc_pos", _p), ("exc_chr", _p),
+                ("counts", C.c_int32 * 7)]
+
+
 TRIAL_SCORE_FN = C.CFUNCTYPE(C.c_int, _p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_double))
 
 
@@ -145,6 +171,10 @@ def declare(lib):
     lib.plb_pack_bases_host.restype = C.c_int
     lib.plb_pack_nibbles_host.argtypes = [_p, C.c_int64, _p, C.c_int64, _p, _p, C.c_int64, P(C.c_int64)]
     lib.plb_pack_nibbles_host.restype = C.c_int
+    lib.plb_stage_reads_host.argtypes = [P(PlbBamRecords), P(PlbReadFilterOptions), P(PlbStagedReads)]
+    lib.plb_stage_reads_host.restype = C.c_int
+    lib.plb_window_slices_host.argtypes = [C.c_int32, _p, _p, C.c_int32, _p, _p, _p, _p]
+    lib.plb_window_slices_host.restype = C.c_int
     lib.plb_site_genotypes_host.argtypes = [_p, P(PlbWindowBatch), P(PlbPopulationOut), P(PlbSiteBatch), P(PlbSiteOut)]
     lib.plb_site_genotypes_host.restype = C.c_int
     lib.plb_batch_upload.argtypes = [_p, P(PlbWindowBatch), P(_p)]
@@ -183,5 +213,6 @@ EXPORTED_SYMBOLS = [
     "plb_run_device", "plb_last_stats", "plb_set_timing", "plb_kernel_times",
     "plb_build_haplotypes_host", "plb_select_haplotypes_host", "plb_select_replay_host", "plb_best_score_haplotypes_host",
     "plb_select_stats", "plb_population_submit", "plb_population_wait", "plb_pack_bases_host", "plb_pack_nibbles_host",
+    "plb_stage_reads_host", "plb_window_slices_host",
 ]
 KERNEL_NAMES = ["k_prep", "k_anchor", "k_general", "k_dp", "k_genotype", "k_population"]

@@ -1452,7 +1452,7 @@ extern "C" int plb_run_device(PlbContext* c, PlbDeviceBatch* db, const PlbOption
         CU(cudaStreamWaitEvent(c->stream3, c->ev_s2, 0));
         for (int k = 0; k < nch; ++k)
             if ((rc = launch_windows(c, db, db->chunks[k], opt, pop, llo, ks[k % 3], true, *qs[k % 3], false, k,
-                                     k > 0 ? js.ev_anchor[k - 1] : nullptr, js.ev_anchor[k])))
+                                     (k > 0 && getenv("PLB_ANCHOR_CHAIN")) ? js.ev_anchor[k - 1] : nullptr, js.ev_anchor[k])))
                 return rc;
         CU(cudaEventRecord(c->ev_s2, c->stream2));
         CU(cudaStreamWaitEvent(st, c->ev_s2, 0));
@@ -1689,7 +1689,7 @@ static int submit_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions
     };
     // The DMA must never wait for the host: the copies of chunk k+1 are queued BEFORE chunk k is planned,
     // and once the first chunk is launched all remaining copies are queued at once.
-    const bool chain_anchors = !getenv("PLB_NO_ANCHOR_CHAIN");
+    const bool chain_anchors = getenv("PLB_ANCHOR_CHAIN") != nullptr;   // measured: no gain (profiles/sweep_overlap_r02.txt)
     int copies_queued = 0;
     auto queue_copies = [&](int upto) {
         for (; copies_queued < upto && copies_queued < n_chunks && rc == PLB_OK && e == cudaSuccess; ++copies_queued) {
@@ -2324,3 +2324,6 @@ extern "C" int plb_gap_open_host(PlbContext* c, int32_t n_haps, const int64_t* o
 
 // ---- N1: haplotype construction + selection loop ------------------------------------------------
 #include "plb_select.cuh"
+
+// ---- N3: read staging (host) ----------------------------------------------------------------------
+#include "plb_stage.cuh"

@@ -808,3 +808,161 @@ def test_reads_beyond_int16_score_range_take_the_exact_path(engine, oracle):
     ok = sc0 < 15871                                     # beyond that the reference itself is undefined
     assert ok.sum() >= 12
     assert np.array_equal(sc[ok], sc0[ok])
+
+
+# ---- the Platypus-shaped objects above the seam (platypus_b200/compat.py) ---------------------------------------------
+
+def _shim_window(case_batch, ref, engine, opts):
+    """compat.Haplotype / Variant / WindowReads objects for one l3 population fixture window."""
+    from platypus_b200 import compat
+    b = case_batch
+    vs = [compat.Variant("chr", v[0], v[1], v[2], prior=(0.5 if v[4] is None else v[4])) for v in ref["variants"]]
+    H = len(ref["hap_seq"])
+    haps = []
+    for h in range(H):
+        hv = tuple(vs[i] for i, v in enumerate(ref["variants"]) if h in v[6])
+        hp = compat.Haplotype("chr", int(b.win_start[0]), int(b.win_end[0]), hv, None, 150, opts, engine,
+                              haplotypeSequence=ref["hap_seq"][h])
+        hp.hapStart = ref["hap_start"]
+        haps.append(hp)
+    bufs = []
+    for i in range(b.n_individuals):
+        s0, s1 = int(b.wi_slot_off[i]), int(b.wi_slot_off[i + 1])
+        ng, nb = int(b.wi_n_good[i]), int(b.wi_n_bad[i])
+        rd = []
+        for s_ in range(s0, s1):
+            r = int(b.slot_read[s_])
+            o0, o1 = int(b.read_seq_off[r]), int(b.read_seq_off[r + 1])
+            rd.append((b.read_seq[o0:o1].tobytes(), b.read_qual[o0:o1].tobytes(), int(b.read_pos[r]), int(b.read_end[r]),
+                       int(b.read_mapq[r]), 512 if b.read_qcfail[r] else 0))
+        bufs.append(compat.WindowReads(rd[:ng], rd[ng:ng + nb], rd[ng + nb:], sample="s%d" % i))
+    return vs, haps, bufs
+
+
+def test_compat_population_shim_matches_reference(engine, golden_dir):
+    """The reference's window loop (variantcaller.pyx:74-141, 566-615) written against platypus_b200.compat:
+    Population.reset / setup / call per window, one flush for all of them; every field outputCallToVCF reads equals the
+    reference's own Population (tests/golden/l3_pop_ref.npz: 48 windows, 1-8 individuals, all four mode combinations)."""
+    import pickle
+    from platypus_b200 import compat
+    g = np.load(os.path.join(golden_dir, "l3_pop_ref.npz"))
+    pops, expect = {}, []
+    for seed in range(int(g["n_cases"])):
+        c, n_ind, mode, use_em, flat = cases.l3_population_setup(seed)
+        key = "p%d_" % seed
+        off, hs = g[key + "hap_off"], g[key + "hap"]
+        ref = {"hap_seq": [hs[off[k]:off[k + 1]].tobytes() for k in range(len(off) - 1)],
+               "hap_start": int(g[key + "hap_start"]), "variants": pickle.loads(g[key + "variants"].tobytes())}
+        if flat:
+            ref["variants"] = [v[:4] + (None,) + v[5:] for v in ref["variants"]]
+        b, phred = cases.l3_population_batch(c, ref, flat)
+        pk = (mode, use_em)
+        if pk not in pops:
+            pops[pk] = compat.Population(compat.Options(HLATyping=mode[0], calculateFlankScore=mode[1], useEMLikelihoods=use_em,
+                                                        minPosterior=0), engine, batch_windows=64)
+        pop = pops[pk]
+        vs, haps, bufs = _shim_window(b, ref, engine, pop.options)
+        pop.reset()
+        pop.setup(vs, haps, compat.generateAllGenotypesFromHaplotypeList(haps), n_ind, 0, bufs)
+        pop.call(100, 1)
+        expect.append((pk, {k: g[key + k] for k in ("freq", "gl", "em", "gl_log_max", "gof", "call")}, phred, vs, haps))
+    results = {pk: iter(pop.flush()) for pk, pop in pops.items()}
+    n = 0
+    for pk, want, phred, vs, haps in expect:
+        r = next(results[pk])
+        nI, G = want["gl"].shape
+        np.testing.assert_allclose(r.genotypeLikelihoods, want["gl"], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(r.goodnessOfFitValues, want["gof"], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(r.frequencies, want["freq"], rtol=1e-9, atol=0)
+        np.testing.assert_allclose(r.EMLikelihoods, want["em"], rtol=1e-9, atol=1e-300)
+        # genotypes are (hap_i, hap_j) pairs; equal haplotype objects would alias, so compare through identity
+        calls = [-1 if gt is None else next(k for k, x in enumerate(r.genotypes) if x[0] is gt[0] and x[1] is gt[1])
+                 for gt in r.genotypeCalls]
+        assert calls == list(want["call"])
+        assert [r.variantPosteriors.get(v) for v in vs] == [float(x) for x in phred]
+        assert r.haplotypeIndexes.shape == (G, 2) and list(r.nReads) == [len(x.reads) for x in r.readBuffers]
+        n += 1
+    assert n == 48
+    # limits raise like the reference (cpopulation.pyx:209-225)
+    small = compat.Population(compat.Options(maxHaplotypes=2), engine, batch_windows=1)
+    with pytest.raises(compat.PlatypusError):
+        small.setup(vs, haps + haps + haps, compat.generateAllGenotypesFromHaplotypeList(haps + haps + haps), 1, 0, [None])
+
+
+def test_compat_haplotype_alignreads_sentinel_and_immediate_population(engine, golden_dir):
+    """Haplotype.alignReads returns the likelihood array of chaplotype.pyx:306-377 - good | bad | broken, closed by the
+    sentinel 999 - equal to the reference's own values (tests/golden/l3_ref.npz); alignSingleRead skips the QC / overlap
+    rule; batch_windows=1 gives the reference's immediate behaviour (results on the population object); haplotype
+    sequences built through the GPU constructor equal the reference's."""
+    from platypus_b200 import compat
+    for k, (b, want) in enumerate(cases.l3_golden_cases(golden_dir)):
+        if k >= 12:
+            break
+        c = cases.l3_window_case(k)
+        w_ll, _ = want[(0, 0)]
+        H, T = w_ll.shape
+        opts = compat.Options()
+        genome = c["genome"]
+
+        class Ref:
+            def getSequence(self, name, a, e):
+                return genome[a:e]
+        all_vs = {}
+        haps = []
+        for hv in c["hap_variants"]:
+            vt = tuple(all_vs.setdefault(v, compat.Variant("chr", v[0], v[1], v[2])) for v in hv)
+            haps.append(compat.Haplotype("chr", c["win_start"], c["win_end"], vt, Ref(), c["max_read_len"], opts, engine))
+        compat.Haplotype.build_sequences(haps, engine)
+        seqs = [b.hap_seq[b.hap_seq_off[h]:b.hap_seq_off[h + 1]].tobytes() for h in range(H)]
+        assert [h.haplotypeSequence for h in haps] == seqs          # reference-built sequences (l3_ref.npz)
+        for h, hp in enumerate(haps):
+            arr = hp.alignReads(0, c["good"], c["bad"], c["broken"], 0)
+            assert arr[-1] == compat.SENTINEL and len(arr) == T + 1
+            np.testing.assert_allclose(arr[:-1], w_ll[h], rtol=1e-12, atol=0)
+            assert hp.alignReads(0, [], [], [], 0) is arr                 # cached per individual index
+        # a QC-fail good read scores 0 in alignReads but is aligned by alignSingleRead
+        qc = [r for r in c["good"] if r[5] & 512 and r[4] > 0]
+        if qc:
+            assert haps[0].alignSingleRead(qc[0]) < 0.0
+        pop = compat.Population(opts, engine, batch_windows=1)
+        pop.reset()
+        vs = sorted(all_vs.values())
+        pop.setup(vs, haps, compat.generateAllGenotypesFromHaplotypeList(haps), 1, 0,
+                  [compat.WindowReads(c["good"], c["bad"], c["broken"])])
+        pop.call(100, 1)
+        direct = engine.population_run(b)
+        G = H * (H + 1) // 2
+        assert np.array_equal(pop.genotypeLikelihoods, direct["gl"][0, :, :G])
+        assert np.array_equal(pop.frequencies, direct["freq"][0, :H]) and len(pop.genotypeCalls) == 1
+
+
+def test_n3_bam_records_to_packed_batch_to_calls(engine, golden_dir):
+    """Rows N3 -> S2/S3 end to end without an ASCII read: the raw records of the reference's test BAM (n3_ref.npz) are
+    filtered, trimmed and packed by plb_stage_reads_host, windows are cut by plb_window_slices_host, and the resulting
+    PLB_SEQ_2BIT batch over the shared read pool gives bit for bit what BASELINE config 1's ASCII batch gives (whose reads
+    went through the Python mirror), i.e. the reference's calign.pyx scores of tests/golden/hla_window_ref.npz."""
+    from platypus_b200 import reads as R
+    from tests.test_oracle import _n3_records
+    g = np.load(os.path.join(golden_dir, "n3_ref.npz"))
+    rec = _n3_records(g)
+    nb = int(g["n_bam"])
+    bam = R.BamRecords(rec.ref_names, *[getattr(rec, k)[:nb] for k in ("ref_id", "pos", "mapq", "flag", "mate_ref_id", "mate_pos", "tlen")],
+                       rec.cigar_off[:nb + 1], rec.cigar, rec.seq_off[:nb + 1], rec.nib_off[:nb + 1], rec.nib, rec.qual)
+    pool = R.stage_records(bam)
+    b_ascii, h = cases.hla_fixture_batch(golden_dir)
+    wins, k = [], 0
+    for ws, we, hs, nh, ng, nbad in h["windows"]:
+        haps = [h["hap"][h["hap_off"][k + j]:h["hap_off"][k + j + 1]].tobytes() for j in range(nh)]
+        wins.append((int(ws), int(we), int(hs), haps))
+        k += nh
+    b = pool.window_batch(wins)
+    assert b.seq_format == _abi.PLB_SEQ_2BIT
+    assert list(b.wi_n_good) == [int(x[4]) for x in h["windows"]] and list(b.wi_n_bad) == [int(x[5]) for x in h["windows"]]
+    assert b.n_reads == nb and b.n_slots == b_ascii.n_slots          # one pool for all windows, slots index into it
+    for kw in ({}, dict(use_mapq_cap=1), dict(calc_flank_score=1)):
+        opt = _abi.PlbOptions.default(**kw)
+        got = engine.population_run(b, opt=opt, want_ll=True)
+        want = engine.population_run(b_ascii, opt=opt, want_ll=True)
+        for key in ("score", "ll", "gl", "freq", "call", "gof"):
+            assert np.array_equal(got[key], want[key]), key
+    assert np.array_equal(engine.window_loglik(b)[1], h["score_default"])      # the reference's own calign.pyx scores

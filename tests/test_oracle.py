@@ -539,3 +539,106 @@ def test_vs_ref_n1_fuzz(oracle):
         assert seqs == r["hap_seqs"], seed
         if sets:
             assert ref.select_haplotypes(*args, 0, sets)["scores"] == scores, seed
+
+
+# ---- N3 pinned by the reference's own bamReadBuffer (tests/golden/n3_ref.npz) ---------------------------------------------
+
+_N3_OPTS = [
+    {},
+    {"trim_read_flank": 4, "min_map_qual": 30, "min_base_qual": 25, "min_good_qual_bases": 60},
+    {"filter_duplicates": 0, "filter_mate_unmapped": 0, "filter_mate_distant": 0, "filter_small_insert": 0},
+    {"trim_overlapping": 0, "trim_adapter": 0, "trim_soft_clipped": 0},
+]
+
+
+def _n3_records(g):
+    from platypus_b200 import reads as R
+    return R.BamRecords(["6"], *[g["rec_" + k] for k in ("ref_id", "pos", "mapq", "flag", "mate_ref_id", "mate_pos", "tlen", "cigar_off",
+                                                          "cigar", "seq_off", "nib_off", "nib", "qual")])
+
+
+def test_n3_native_staging_golden_ref(golden_dir):
+    """plb_stage_reads_host = the reference's ReadIterator.get + addReadToBuffer + checkAndTrimRead (cwindow.pyx:332-481,
+    560-595) on all 2115 records of the reference's test BAM and 600 synthetic records that reach the remaining branches,
+    for four option sets: list membership, QC-fail flags, trimmed qualities, filter counts - bit for bit; and
+    plb_window_slices_host = ReadArray.setWindowPointers (cwindow.pyx:208-236) on 400 windows."""
+    import ctypes as C
+    from platypus_b200 import _abi, reads as R
+    from __graft_entry__ import build
+    build()
+    from platypus_b200.engine import load_library
+    lib = load_library()
+    g = np.load(os.path.join(golden_dir, "n3_ref.npz"))
+    rec = _n3_records(g)
+    assert int(g["n_bam"]) == 2115 and rec.n == 2715
+    for s, kw in enumerate(_N3_OPTS):
+        pool = R.stage_records(rec, R.ReadFilterOptions(**kw), lib)
+        assert np.array_equal(pool.kept, g["kept"])
+        assert np.array_equal(pool.good, g["o%d_good" % s]) and np.array_equal(pool.flag, g["o%d_flag" % s]), s
+        want_q = g["rec_qual"].copy()
+        want_q[g["o%d_zeroed" % s]] = 0
+        nb = int(rec.seq_off[-1])
+        live = np.repeat(g["kept"], np.diff(rec.seq_off)).astype(bool)
+        assert np.array_equal(pool.qual[:nb][live], want_q[:nb][live]), s
+        assert pool.counts == list(g["o%d_counts" % s]), (pool.counts, list(g["o%d_counts" % s]))
+    pool = R.stage_records(rec, None, lib)
+    # bases: the 2-bit pool + exceptions decode to the letters htslib's table gives the nibbles
+    nb = int(rec.seq_off[-1])
+    i = np.arange(nb)
+    back = np.frombuffer(b"ACGT", np.uint8)[(pool.seq2[i >> 2] >> (2 * (i & 3))) & 3].copy()
+    back[pool.exc_pos] = pool.exc_chr
+    nib = np.zeros(nb, np.uint8)
+    for r in range(rec.n):
+        b0, L = int(rec.seq_off[r]), int(rec.seq_off[r + 1] - rec.seq_off[r])
+        k = np.arange(L)
+        nib[b0:b0 + L] = (rec.nib[int(rec.nib_off[r]) + (k >> 1)] >> (4 * (1 - (k & 1)))) & 15
+    live = np.repeat(g["kept"], np.diff(rec.seq_off)).astype(bool)
+    assert np.array_equal(back[live], np.frombuffer(b"=ACMGRSVTWYHKDBN", np.uint8)[nib][live])
+    assert len(pool.exc_pos) == int(np.count_nonzero(~np.isin(nib[live], [1, 2, 4, 8])))
+    # window slices of the good and the bad list
+    wins, want = g["windows"], g["slices"]
+    for col, idx in ((0, pool.good_index()), (2, pool.bad_index())):
+        pos, end = np.ascontiguousarray(pool.read_pos[idx]), np.ascontiguousarray(pool.read_end[idx])
+        lo, hi = np.zeros(len(wins), np.int32), np.zeros(len(wins), np.int32)
+        ws, we = np.ascontiguousarray(wins[:, 0]), np.ascontiguousarray(wins[:, 1])
+        assert lib.plb_window_slices_host(len(idx), _abi.ptr(pos), _abi.ptr(end), len(wins), _abi.ptr(ws), _abi.ptr(we),
+                                          _abi.ptr(lo), _abi.ptr(hi)) == 0
+        assert np.array_equal(lo, want[:, col]) and np.array_equal(hi, want[:, col + 1])
+        assert (hi > lo).any()
+
+
+def test_n3_python_mirror_golden_ref(golden_dir):
+    """The Python mirror of the same steps (platypus_b200/reads.py: decode_bam's field derivation, check_and_trim_read,
+    window_slice) against the same reference-made fixture."""
+    from platypus_b200 import reads as R
+    g = np.load(os.path.join(golden_dir, "n3_ref.npz"))
+    rec = _n3_records(g)
+    nibtab = b"=ACMGRSVTWYHKDBN"
+    for s, kw in enumerate(_N3_OPTS[:2]):
+        buf = R.ReadBuffer(R.ReadFilterOptions(**kw))
+        objs = {}
+        for i in range(rec.n):
+            b0, b1 = int(rec.seq_off[i]), int(rec.seq_off[i + 1])
+            if b1 == b0 or rec.qual[b0] == 0xFF:
+                continue
+            nb = rec.nib[int(rec.nib_off[i]):int(rec.nib_off[i + 1])]
+            seq = bytes(nibtab[(nb[k >> 1] >> (4 * (1 - (k & 1)))) & 15] for k in range(b1 - b0))
+            cg = [(int(w) & 15, int(w) >> 4) for w in rec.cigar[int(rec.cigar_off[i]):int(rec.cigar_off[i + 1])]]
+            pos = int(rec.pos[i]) - (cg[0][1] if cg and cg[0][0] == 4 else 0)
+            ref_len = sum(n for op, n in cg if op in (0, 2, 3, 7, 8))
+            r = R.AlignedRead(seq, bytearray(rec.qual[b0:b1].tobytes()), cg, int(rec.ref_id[i]), pos,
+                              int(rec.pos[i]) + (ref_len if ref_len > 0 else 1), int(rec.mapq[i]), int(rec.flag[i]),
+                              int(rec.mate_ref_id[i]), int(rec.mate_pos[i]), int(rec.tlen[i]))
+            buf.add(r)
+            objs[i] = r
+        good_ids = {id(r) for r in buf.reads}
+        want_q = g["rec_qual"].copy()
+        want_q[g["o%d_zeroed" % s]] = 0
+        for i, r in objs.items():
+            assert (id(r) in good_ids) == bool(g["o%d_good" % s][i]), i
+            assert r.flag == int(g["o%d_flag" % s][i]), i
+            assert bytes(r.qual) == want_q[int(rec.seq_off[i]):int(rec.seq_off[i + 1])].tobytes(), i
+        if s == 0:
+            for (ws, we), (gl, gh, bl, bh) in zip(g["windows"], g["slices"]):
+                assert [id(x) for x in R.window_slice(buf.reads, int(ws), int(we))] == [id(x) for x in buf.reads[gl:gh]]
+                assert [id(x) for x in R.window_slice(buf.bad_reads, int(ws), int(we))] == [id(x) for x in buf.bad_reads[bl:bh]]

@@ -41,9 +41,9 @@ def main():
             os.environ["PLB_DP_OCC"] = str(docc)
             os.environ["PLB_ANCHOR_OCC"] = str(aocc)
             if chain:
-                os.environ.pop("PLB_NO_ANCHOR_CHAIN", None)
+                os.environ["PLB_ANCHOR_CHAIN"] = "1"
             else:
-                os.environ["PLB_NO_ANCHOR_CHAIN"] = "1"
+                os.environ.pop("PLB_ANCHOR_CHAIN", None)
             ds = DeviceShard(eng, batch, stream, gather=False)
             with torch.cuda.stream(stream):
                 for _ in range(3):
@@ -85,9 +85,9 @@ def main():
             os.environ["PLB_DP_OCC"] = str(docc)
             os.environ["PLB_ANCHOR_OCC"] = str(aocc)
             if chain:
-                os.environ.pop("PLB_NO_ANCHOR_CHAIN", None)
+                os.environ["PLB_ANCHOR_CHAIN"] = "1"
             else:
-                os.environ["PLB_NO_ANCHOR_CHAIN"] = "1"
+                os.environ.pop("PLB_ANCHOR_CHAIN", None)
 
             def run(n):
                 jobs = []
