@@ -1394,12 +1394,11 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
                 d, po, db->em_scratch, opt->max_em_iters, opt->use_em_likelihoods, w0, w1);
             if ((rc = launch_check(c, "k_population_few"))) return rc;
         } else {
-            // thread per individual: as many threads as shared memory allows partial-frequency rows for
-            size_t nt = std::min<size_t>(kPopMaxThreads, ((size_t)(96 * 1024) / (8 * (size_t)Hm)) - 3);
-            nt = std::min<size_t>(nt, (size_t)((d.n_individuals + 31) / 32) * 32);
+            // thread per individual
+            size_t nt = std::min<size_t>(kPopMaxThreads, (size_t)((d.n_individuals + 31) / 32) * 32);
             nt = std::max<size_t>(32, nt / 32 * 32);
-            const size_t smem = (size_t)(3 + nt) * Hm * 8;
-            if (smem + 8192 > (size_t)c->smem_optin)
+            const size_t smem = (size_t)3 * Hm * 8;
+            if (smem + 16384 > (size_t)c->smem_optin)
                 return set_err(PLB_ERR_SHAPE, "population model needs %zu bytes of shared memory for %d haplotypes", smem, Hm);
             if ((rc = opt_in_smem(k_population, smem))) return rc;
             k_population<<<w1 - w0, (unsigned)nt, smem, st>>>(d, po, db->em_scratch, opt->max_em_iters,

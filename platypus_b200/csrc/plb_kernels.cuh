@@ -1539,30 +1539,21 @@ __global__ void __launch_bounds__(64) k_genotype(DevBatch b, const double* __res
 // k_population: one block per window, a THREAD PER INDIVIDUAL (many-sample batches; k_population_few
 // handles batches with a handful of individuals).  EM (cpopulation.pyx:384-457, 678-703), genotype calls
 // (:623-676), variant posteriors (:459-594).  blockDim.x = NT threads (a multiple of 32, up to 512);
-// thread t owns individuals t, t+NT, ...  Per individual every sum runs in the reference's order; sums
-// ACROSS individuals (new haplotype frequencies, the posterior's sums of logs) are reduced in a fixed
-// two-level order (32 per warp, then the warps), which differs from the reference's sequential order by
-// rounding only (<= 1e-13 relative).
-// Shared memory: (3 + NT) * Hmax doubles (freq, new, fp, per-thread partial frequencies).
+// thread t owns individuals t, t+NT, ...
+//
+// Everything per individual is independent and runs across the threads in the reference's own order of
+// operations.  The sums ACROSS individuals are floating-point chains whose order the reference fixes -
+//   newFreqs[k]:  individuals ascending, inside one its genotypes ascending, `+= csr` once per haplotype slot
+//                 (twice for the homozygous genotype)                                  (cpopulation.pyx:436-447)
+//   sum of log P(variant) / log P(no variant) over the individuals, ascending          (:546-581)
+// - and a different association changes the last bits, which can flip the EM's stop test (one iteration more or
+// fewer) or a rounded phred value.  So each chain is walked by ONE thread in exactly that order (haplotype k's chain by
+// thread k; the posterior's by thread 0 over values the other threads have laid out in shared memory).  With 2000
+// individuals and 8 haplotypes that is 18,000 dependent additions per EM iteration per window - microseconds next to
+// the alignment work of the same window - and it makes call / em_iters / var_phred equal to the reference's bit for bit.
+// Shared memory: 3 * Hmax doubles.
 // ---------------------------------------------------------------------------------------------
 constexpr int kPopMaxThreads = 512;
-
-// sum of one double per thread, deterministic: lanes of a warp in order, then the warps in order
-__device__ __forceinline__ double block_sum_ordered(double v, double* s_red /* [NT] */, double* s_w /* [NT/32] */) {
-    const int tid = threadIdx.x, NT = blockDim.x;
-    s_red[tid] = v;
-    __syncthreads();
-    if ((tid & 31) == 0) {
-        double a = 0.0;
-        for (int k = 0; k < 32; ++k) a += s_red[tid + k];
-        s_w[tid >> 5] = a;
-    }
-    __syncthreads();
-    double tot = 0.0;
-    for (int k = 0; k < (NT >> 5); ++k) tot += s_w[k];
-    __syncthreads();
-    return tot;
-}
 
 __global__ void __launch_bounds__(kPopMaxThreads) k_population(DevBatch b, PopOut out, double* __restrict__ em_scratch,
                                                                int max_iters, int use_em, int nthr_em, int w_base) {
@@ -1576,10 +1567,9 @@ __global__ void __launch_bounds__(kPopMaxThreads) k_population(DevBatch b, PopOu
     double* s_freq = (double*)smem;             // [Hmax]
     double* s_new = s_freq + Hmax;              // [Hmax]
     double* s_fp = s_new + Hmax;                // [Hmax] frequencies without one variant's haplotypes
-    double* s_part = s_fp + Hmax;               // [NT][Hmax]
-    __shared__ double s_red[kPopMaxThreads];
-    __shared__ double s_w[kPopMaxThreads / 32];
-    __shared__ double s_change;
+    __shared__ double s_lv[kPopMaxThreads], s_ln[kPopMaxThreads];   // one tile of per-individual log terms
+    __shared__ double s_change, s_slv;
+    __shared__ int s_nwith;
     const int tid = threadIdx.x;
     (void)nthr_em;
     const double* gl = out.gl + (size_t)w * nInd * Gmax;
@@ -1588,6 +1578,11 @@ __global__ void __launch_bounds__(kPopMaxThreads) k_population(DevBatch b, PopOu
 
     const double eps = fmin(1e-3, 1.0 / (nInd * 2 * 2));  // cpopulation.pyx:684
     for (int k = tid; k < Hmax; k += NT) s_freq[k] = k < H ? 1.0 / H : 0.0;
+    if (tid == 0) {
+        s_nwith = 0;
+        s_change = eps + 1;
+    }
+    __syncthreads();
     int my_with = 0;
     for (int i = tid; i < nInd; i += NT) {
         if (ngood[i] == 0) {
@@ -1597,13 +1592,12 @@ __global__ void __launch_bounds__(kPopMaxThreads) k_population(DevBatch b, PopOu
             for (int g = G; g < Gmax; ++g) emp[(size_t)i * Gmax + g] = 0.0;
         }
     }
-    const int n_with = (int)(block_sum_ordered((double)my_with, s_red, s_w) + 0.5);   // individuals with reads
-    if (tid == 0) s_change = eps + 1;
+    if (my_with) atomicAdd(&s_nwith, my_with);   // an integer count: order does not matter
     __syncthreads();
+    const int n_with = s_nwith;                  // individuals with reads
     int iters = 0;
     while (s_change > eps && iters < max_iters) {  // uniform: s_change only changes between barriers
-        double* part = s_part + (size_t)tid * Hmax;
-        for (int k = 0; k < H; ++k) part[k] = 0.0;
+        // E step, one individual per thread (cpopulation.pyx:407-430)
         for (int i = tid; i < nInd; i += NT) {
             if (ngood[i] == 0) continue;
             const double* gli = gl + (size_t)i * Gmax;
@@ -1616,47 +1610,37 @@ __global__ void __launch_bounds__(kPopMaxThreads) k_population(DevBatch b, PopOu
                     csr[g] = v;
                     sum += v;
                 }
-            g = 0;
-            for (int s = 0; s < H; ++s)
-                for (int r = s; r < H; ++r, ++g) {
-                    double v = csr[g];
-                    if (sum > 0.0) {
-                        v /= sum;
-                        csr[g] = v;
-                    }
-                    part[s] += v;
-                    part[r] += v;
-                }
+            if (sum > 0.0)
+                for (g = 0; g < G; ++g) csr[g] /= sum;
         }
-        __syncthreads();
-        // new frequency of haplotype k: partial sums of the threads, 32 per warp then the warps, in order
-        for (int k0 = 0; k0 < H; k0 += NT / 32) {     // warp j reduces haplotype k0 + j over its 32-thread groups
-            const int k = k0 + (tid >> 5);
-            double a = 0.0;
-            if (k < H) {
-                for (int t = (tid & 31); t < NT; t += 32) {   // lane l sums threads l, l+32, ... (order fixed)
-                    a += s_part[(size_t)t * Hmax + k];
-                }
-            }
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xFFFFFFFFu, a, o);
-            if (k < H && (tid & 31) == 0) s_new[k] = a;
-        }
-        __syncthreads();
-        double mych = 0.0;
+        __syncthreads();   // the rows written above are read by other threads of this block below
+        // M step: haplotype k's chain by thread k, in the reference's order (see the header comment)
         for (int k = tid; k < H; k += NT) {
-            double nf = s_new[k];
-            if (n_with > 0) nf = nf / (2 * n_with); else nf = s_freq[k];
-            const double ch = fabs(s_freq[k] - nf);
-            if (ch > mych) mych = ch;
-            s_new[k] = nf;
+            double acc = 0.0;
+            for (int i = 0; i < nInd; ++i) {
+                if (ngood[i] == 0) continue;
+                const double* csr = emp + (size_t)i * Gmax;
+                int g = k;                                   // g(0, k)
+                for (int s = 0; s < k; ++s) {                // genotypes (s, k), s < k: g(s+1, k) = g(s, k) + H - s - 1
+                    acc += csr[g];
+                    g += H - s - 1;
+                }
+                const double hom = csr[g];                   // g(k, k): both slots are haplotype k
+                acc += hom;
+                acc += hom;
+                for (int r = k + 1; r < H; ++r) acc += csr[g + (r - k)];
+            }
+            s_new[k] = acc;
         }
-        s_red[tid] = mych;
         __syncthreads();
-        for (int k = tid; k < H; k += NT) s_freq[k] = s_new[k];
-        if (tid == 0) {
+        if (tid == 0) {   // cpopulation.pyx:449-455
             double m = 0.0;
-            const int lim = H < NT ? H : NT;
-            for (int k = 0; k < lim; ++k) m = s_red[k] > m ? s_red[k] : m;
+            for (int k = 0; k < H; ++k) {
+                const double nf = s_new[k] / (2 * n_with);
+                const double ch = fabs(s_freq[k] - nf);
+                if (ch > m) m = ch;
+                s_freq[k] = nf;
+            }
             s_change = m;
         }
         ++iters;
@@ -1681,15 +1665,17 @@ __global__ void __launch_bounds__(kPopMaxThreads) k_population(DevBatch b, PopOu
             out.call[(size_t)w * nInd + i] = bestg;
         }
     }
-    // calculatePosterior, cpopulation.pyx:459-594: variants one after the other, individuals across threads
+    // calculatePosterior, cpopulation.pyx:459-594.  Per individual P(variant) does not depend on the variant, so the
+    // sum of its logs is formed once (pass v = -1); per variant the individuals' log P(no variant) are laid out a tile
+    // at a time and thread 0 adds them in order.
     if (out.var_phred && b.max_variants > 0 && b.win_n_var) {
         const int nvar = b.win_n_var[w];
         const uint64_t* masks = b.hap_var_mask + b.win_hap_off[w];
-        for (int v = 0; v < b.max_variants; ++v) {
+        for (int v = -1; v < b.max_variants; ++v) {
             double ph = 0.0;
-            if (v < nvar) {   // uniform over the block
+            if (v < nvar && (v >= 0 || nvar > 0)) {   // uniform over the block
                 __syncthreads();
-                if (tid == 0) {
+                if (tid == 0 && v >= 0) {
                     double sumf = 0.0;
                     for (int k = 0; k < H; ++k) {
                         if (!((masks[k] >> v) & 1ull)) {
@@ -1703,30 +1689,46 @@ __global__ void __launch_bounds__(kPopMaxThreads) k_population(DevBatch b, PopOu
                         for (int k = 0; k < H; ++k) s_fp[k] /= sumf;
                 }
                 __syncthreads();
-                double slv = 0.0, sln = 0.0;
-                for (int i = tid; i < nInd; i += NT) {
-                    if (ngood[i] == 0) continue;
-                    const double* gli = gl + (size_t)i * Gmax;
-                    double pv = 0.0, pn = 0.0;
-                    int g = 0;
-                    for (int r = 0; r < H; ++r)
-                        for (int s = r; s < H; ++s, ++g) {
-                            const double l = gli[g];
-                            const double factor = (r != s) ? 2.0 : 1.0;
-                            pv += (factor * s_freq[r] * s_freq[s] * l);
-                            pn += (factor * s_fp[r] * s_fp[s] * l);
-                        }
-                    slv += pv > 0 ? log(pv) : -708.0;
-                    sln += pn > 0 ? log(pn) : -708.0;
+                const double* fq = v < 0 ? s_freq : s_fp;
+                double chain = 0.0;   // thread 0 only
+                for (int base = 0; base < nInd; base += NT) {
+                    const int i = base + tid;
+                    double term = 0.0;
+                    bool have = false;
+                    if (i < nInd && ngood[i] != 0) {
+                        const double* gli = gl + (size_t)i * Gmax;
+                        double p = 0.0;
+                        int g = 0;
+                        for (int r = 0; r < H; ++r)
+                            for (int s = r; s < H; ++s, ++g) {
+                                const double factor = (r != s) ? 2.0 : 1.0;
+                                p += (factor * fq[r] * fq[s] * gli[g]);
+                            }
+                        term = p > 0 ? log(p) : -708.0;
+                        have = true;
+                    }
+                    s_lv[tid] = term;
+                    s_ln[tid] = have ? 1.0 : 0.0;
+                    __syncthreads();
+                    if (tid == 0) {
+                        const int lim = min(NT, nInd - base);
+                        for (int t = 0; t < lim; ++t)
+                            if (s_ln[t] != 0.0) chain += s_lv[t];
+                    }
+                    __syncthreads();
                 }
-                slv = block_sum_ordered(slv, s_red, s_w);
-                sln = block_sum_ordered(sln, s_red, s_w);
-                double ratio = exp(sln - slv);
-                if (!(ratio > 1e-300)) ratio = 1e-300;
-                const double prior = b.var_prior[(size_t)w * b.max_variants + v];
-                ph = round(-10.0 * (log10(ratio * (1.0 - prior)) - log10(prior + ratio * (1.0 - prior))));
+                if (tid == 0) {
+                    if (v < 0) {
+                        s_slv = chain;
+                    } else {
+                        double ratio = exp(chain - s_slv);
+                        if (!(ratio > 1e-300)) ratio = 1e-300;
+                        const double prior = b.var_prior[(size_t)w * b.max_variants + v];
+                        ph = round(-10.0 * (log10(ratio * (1.0 - prior)) - log10(prior + ratio * (1.0 - prior))));
+                    }
+                }
             }
-            if (tid == 0) out.var_phred[(size_t)w * b.max_variants + v] = ph;
+            if (tid == 0 && v >= 0) out.var_phred[(size_t)w * b.max_variants + v] = ph;
         }
     }
 }

@@ -421,6 +421,44 @@ def l3_pop_golden_cases(golden_dir):
         yield b, want, use_em, mode
 
 
+MANY_CASES = [(9001, 300), (9002, 300), (9003, 2000), (9004, 2000)]   # as tests/golden/make_golden.py
+
+
+def l3_pop_many_cases(golden_dir):
+    """Yields (batch, expected dict, use_em) for the many-sample windows of tests/golden/l3_pop_many_ref.npz (300 and 2000
+    individuals through the reference's own Population class; BASELINE config 5's individual count)."""
+    import os
+    import pickle
+    import numpy as np
+    g = np.load(os.path.join(golden_dir, "l3_pop_many_ref.npz"))
+    for k, (seed, n_ind) in enumerate(MANY_CASES):
+        c = l3_window_case(seed, n_ind)
+        key = "m%d_" % k
+        off, hs = g[key + "hap_off"], g[key + "hap"]
+        ref = {"hap_seq": [hs[off[j]:off[j + 1]].tobytes() for j in range(len(off) - 1)],
+               "hap_start": int(g[key + "hap_start"]), "variants": pickle.loads(g[key + "variants"].tobytes())}
+        b, phred = l3_population_batch(c, ref, True)
+        want = {x: g[key + x] for x in ("freq", "gl", "em", "gl_log_max", "call")}
+        want["stride"] = int(g[key + "stride"])
+        want["var_phred"] = phred
+        yield b, want, k % 2
+
+
+def check_l3_pop_many(got, want):
+    """Integer outputs equal the reference's; frequencies / posteriors to 1e-9 (they are equal unless exp / log of the two
+    math libraries differ in a last bit)."""
+    import numpy as np
+    st = want["stride"]
+    H, G = len(want["freq"]), want["gl"].shape[1]
+    assert list(got["call"][0]) == list(want["call"]), "genotype calls"
+    assert list(got["var_phred"][0, :len(want["var_phred"])]) == list(want["var_phred"]), "variant posteriors"
+    np.testing.assert_allclose(got["freq"][0, :H], want["freq"], rtol=1e-9, atol=0, err_msg="freq")
+    np.testing.assert_allclose(got["gl"][0, ::st, :G], want["gl"], rtol=1e-12, atol=0, err_msg="gl")
+    np.testing.assert_allclose(got["em_post"][0, ::st, :G], want["em"], rtol=1e-9, atol=1e-300, err_msg="em")
+    has = want["call"] >= 0
+    np.testing.assert_allclose(got["gl_log_max"][0][has], want["gl_log_max"][has], rtol=1e-12, atol=0)
+
+
 def check_l3_pop(got, want, rtol=1e-12):
     import numpy as np
     nI, G = want["gl"].shape

@@ -214,6 +214,38 @@ def make_l3_pop(n=48):
     print("l3_pop_ref.npz:", n, "windows")
 
 
+MANY_CASES = [(9001, 300), (9002, 300), (9003, 2000), (9004, 2000)]   # (seed, individuals) of l3_pop_many_ref.npz
+
+
+def make_l3_pop_many():
+    """Many-sample windows (BASELINE config 5: 2000 individuals) through the reference's own Population class: the EM's
+    sums over individuals are long floating-point chains whose order matters for the last bits (cpopulation.pyx:384-457),
+    so calls, posteriors and frequencies are pinned at that size too.  Inputs are regenerated from the seed
+    (tests/cases.l3_window_case); stored: frequencies, calls, max log-likelihoods, variant posteriors, and every
+    `stride`-th row of the genotype likelihoods / EM posteriors."""
+    import pickle
+    W = O.ref_l3()
+    assert W is not None
+    out = {}
+    for k, (seed, n_ind) in enumerate(MANY_CASES):
+        c = cases.l3_window_case(seed, n_ind)
+        r = W.population(c["genome"], c["win_start"], c["win_end"], c["hap_variants"], c["per_ind"], c["max_read_len"], 0, 0, k % 2)
+        key = "m%d_" % k
+        ho, hs = pack(r["hap_seq"])
+        out[key + "hap_off"], out[key + "hap"], out[key + "hap_start"] = ho, hs, np.int32(r["hap_start"])
+        stride = 1 if n_ind <= 300 else 25
+        out[key + "stride"] = np.int32(stride)
+        out[key + "freq"] = np.array(r["freq"], np.float64)
+        out[key + "gl_log_max"] = np.array(r["gl_log_max"], np.float64)
+        out[key + "gl"] = np.array(r["gl"], np.float64)[::stride]
+        out[key + "em"] = np.array(r["em"], np.float64)[::stride]
+        out[key + "call"] = np.array(r["call"], np.int32)
+        out[key + "variants"] = np.frombuffer(pickle.dumps(r["variants"], protocol=2), np.uint8)
+        print("many-sample case %d: %d individuals, %d haplotypes, freq %s" % (k, n_ind, len(r["freq"]), np.round(r["freq"], 4)))
+    np.savez_compressed(os.path.join(HERE, "l3_pop_many_ref.npz"), n_cases=np.int32(len(MANY_CASES)), **out)
+    print("l3_pop_many_ref.npz:", os.path.getsize(os.path.join(HERE, "l3_pop_many_ref.npz")), "bytes")
+
+
 def make_n4():
     assert O.ref_n4() is not None
     out = {}
@@ -254,6 +286,7 @@ if __name__ == "__main__":
     make_calign_modes()
     make_l3()
     make_l3_pop()
+    make_l3_pop_many()
     make_n4()
     make_window()
     make_window_modes()

@@ -163,11 +163,24 @@ def test_s3_many_individuals(engine, oracle):
     np.testing.assert_allclose(got["ll"], ll0, rtol=RTOL_TIGHT, atol=0)
     for k in ("gl", "gof", "hap_like"):
         np.testing.assert_allclose(got[k], want[k], rtol=RTOL_TIGHT, atol=1e-300, err_msg=k)
-    # sums over 300 individuals are reduced per thread: compare at the contract's tolerance
-    np.testing.assert_allclose(got["freq"], want["freq"], rtol=RTOL, atol=1e-12)
-    np.testing.assert_allclose(got["em_post"], want["em_post"], rtol=RTOL, atol=1e-12)
-    assert np.array_equal(got["call"], want["call"])
-    assert np.abs(got["var_phred"] - want["var_phred"]).max() <= 1.0   # rounded phred of a 300-term log sum
+    # the sums over the 300 individuals run in the reference's order: integer outputs are equal, the rest to 1e-9
+    np.testing.assert_allclose(got["freq"], want["freq"], rtol=RTOL_TIGHT, atol=0)
+    np.testing.assert_allclose(got["em_post"], want["em_post"], rtol=RTOL_TIGHT, atol=1e-300)
+    assert np.array_equal(got["call"], want["call"]) and np.array_equal(got["em_iters"], want["em_iters"])
+    assert np.array_equal(got["var_phred"], want["var_phred"])
+
+
+def test_s3_many_samples_golden_ref(engine, oracle, golden_dir):
+    """k_population (thread per individual) at 300 and 2000 individuals - BASELINE config 5's sample count - against the
+    reference's own Population class: the cross-individual sums run in the reference's order (cpopulation.pyx:436-447,
+    546-581), so genotype calls, rounded variant posteriors AND the EM iteration count are equal, not merely close."""
+    for b, want, use_em in cases.l3_pop_many_cases(golden_dir):
+        opt = _abi.PlbOptions.default(use_em_likelihoods=use_em)
+        got = engine.population_run(b, opt=opt)
+        cases.check_l3_pop_many(got, want)
+        ref, _, _, _ = oracle.population_run(b, opt)
+        assert np.array_equal(got["em_iters"], ref["em_iters"]) and np.array_equal(got["call"], ref["call"])
+        np.testing.assert_allclose(got["freq"], ref["freq"], rtol=1e-12, atol=0)
 
 
 def test_long_haplotypes_and_reads(engine, oracle):
@@ -965,4 +978,6 @@ def test_n3_bam_records_to_packed_batch_to_calls(engine, golden_dir):
         want = engine.population_run(b_ascii, opt=opt, want_ll=True)
         for key in ("score", "ll", "gl", "freq", "call", "gof"):
             assert np.array_equal(got[key], want[key]), key
-    assert np.array_equal(engine.window_loglik(b)[1], h["score_default"])      # the reference's own calign.pyx scores
+    sc = engine.window_loglik(b)[1]
+    scored = sc >= 0          # -1 = short-circuited by the QC-fail / overlap rule (the fixture scores every pair)
+    assert scored.sum() > 500 and np.array_equal(sc[scored], h["score_default"][scored])      # the reference's own calign.pyx scores

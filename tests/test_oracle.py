@@ -642,3 +642,15 @@ def test_n3_python_mirror_golden_ref(golden_dir):
             for (ws, we), (gl, gh, bl, bh) in zip(g["windows"], g["slices"]):
                 assert [id(x) for x in R.window_slice(buf.reads, int(ws), int(we))] == [id(x) for x in buf.reads[gl:gh]]
                 assert [id(x) for x in R.window_slice(buf.bad_reads, int(ws), int(we))] == [id(x) for x in buf.bad_reads[bl:bh]]
+
+
+def test_golden_l3_population_many_samples(oracle, golden_dir):
+    """The oracle's Population restatement at BASELINE config 5's sample count: 300 and 2000 individuals against outputs of
+    the reference's own cpopulation.pyx (tests/golden/l3_pop_many_ref.npz)."""
+    from platypus_b200 import _abi
+    n = 0
+    for b, want, use_em in cases.l3_pop_many_cases(golden_dir):
+        arrs, _, _, _ = oracle.population_run(b, _abi.PlbOptions.default(use_em_likelihoods=use_em))
+        cases.check_l3_pop_many(arrs, want)
+        n += b.n_individuals
+    assert n == 4600
