@@ -60,6 +60,14 @@ def workload_config(n_gpus, windows):
 
 
 def _workload_config(n_gpus, windows):
+    if CONFIG == 4:
+        return {"workload": "synth-v1 config4 (chr22-sized: ~500k windows over 8 GPUs): %d windows x %d haplotypes x %d reads per GPU, "
+                            "%d bp reads x %d bp haplotypes; all-gather of gl[W][36] f64 (%.0f MB over %d ranks)"
+                            % (windows, N_HAPS, N_READS, READ_LEN, HAP_LEN, windows * n_gpus * 36 * 8 / 1e6, n_gpus),
+                "windows_per_gpu": windows, "n_gpus": n_gpus, "haplotypes": N_HAPS, "reads": N_READS, "read_len": READ_LEN,
+                "hap_len": HAP_LEN, "individuals": 1, "cells_per_pair": "16*readLen (algorithmic band cells, SURVEY 8d)",
+                "l2": "inputs of one step (~1.4 GB per GPU) exceed the 126 MB L2; no explicit flush",
+                "parallelism": "contiguous blocks of windows per GPU, one process per GPU, one NCCL all-gather per step"}
     if RAGGED:
         return {"workload": "synth-v1 config3 shapes: %d windows x %d haplotypes x %d reads per GPU, reads 100-250 bp, "
                             "haplotypes 200-500 bp (profiling configuration, not the headline)" % (windows, N_HAPS, N_READS),
@@ -77,6 +85,7 @@ def _workload_config(n_gpus, windows):
 
 
 OPT = None       # --mode flank / hla: PlbOptions with the run-time mode switched on
+CONFIG = 2
 RAGGED = False   # --config 3: read length U{100..250}, haplotype length U[max(200, Lmax+16), 500]
 
 
@@ -84,7 +93,8 @@ def make_workload(rank, windows):
     from platypus_b200 import synth
     t0 = time.time()
     kw = dict(read_len_range=(100, 250), hap_len_range=(200, 500)) if RAGGED else dict(read_len=READ_LEN, hap_len=HAP_LEN)
-    b = synth.make_batch_parallel(windows, window_offset=rank * windows, n_haps=N_HAPS, n_reads=N_READS, **kw)
+    procs = max(1, min(32, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    b = synth.make_batch_parallel(windows, window_offset=rank * windows, n_procs=procs, n_haps=N_HAPS, n_reads=N_READS, **kw)
     return b, time.time() - t0
 
 
@@ -516,6 +526,7 @@ def run_ours(args, rank, world, local_rank):
 
     stream = torch.cuda.Stream(device=dev)
     eng = Engine(local_rank, stream=stream.cuda_stream)
+    eng_check = Engine(local_rank) if (world > 1 and rank == 0) else None     # own context for the gather check
     # The shard resident on this GPU and the path's one collective (all-gather of the per-window genotype likelihoods on a
     # side stream, overlapped with the next step): platypus_b200.shard.DeviceShard - the multi-GPU API the package ships.
     from platypus_b200.shard import DeviceShard
@@ -546,6 +557,21 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
         ms_total = e0.elapsed_time(e1)
+        gather_check = None
+        if world > 1 and rank == 0:
+            # the gathered tensor against a recomputation here of sampled windows of OTHER ranks' blocks (their inputs are
+            # regenerated from the window ids; the engine's host path recomputes them on this GPU)
+            rng = np.random.default_rng(4)
+            n_ok = 0
+            for r in sorted(set([1, world - 1, world // 2])):
+                for k in rng.choice(windows, 4, replace=False):
+                    one = synth.make_batch(1, window_offset=r * windows + int(k), n_haps=N_HAPS, n_reads=N_READS,
+                                           **(dict(read_len_range=(100, 250), hap_len_range=(200, 500)) if RAGGED else
+                                              dict(read_len=READ_LEN, hap_len=HAP_LEN)))
+                    again = eng_check.population_run(one, opt=OPT, max_haps=Hm)["gl"][0]
+                    assert np.array_equal(gl_all[r, int(k)].cpu().numpy(), again), ("gathered block differs", r, int(k))
+                    n_ok += 1
+            gather_check = {"windows_recomputed": n_ok, "bytes_gathered_per_step": int(gl_all.numel() * 8), "equal": True}
         launches = eng.launch_count - launches0 + (args.steps if world > 1 else 0)
         ktimes, n_timed = eng.kernel_times()
         eng.set_timing(False)
@@ -692,6 +718,173 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "stats": stats, "gen_seconds": gen_s,
     }
+    if gather_check:
+        line["gather_check"] = gather_check
+    print(json.dumps(line), flush=True)
+    eng.free(handle)
+
+
+# ---- --config 5: multi-sample mode (BASELINE config 5) ------------------------------------------------------------------
+
+C5_WINDOWS, C5_IND, C5_READS = 30000, 2000, 50     # the stated 1/1000 subsample of ~30 M windows; 2000 samples x ~50 reads
+
+
+def c5_template(n_windows):
+    """A batch of the config-5 SHAPE (offsets and counts only; the bytes are generated on the device)."""
+    from platypus_b200.batch import WindowBatch
+    W, nI, R, H = n_windows, C5_IND, C5_READS, N_HAPS
+    n_reads = W * nI * R
+    mv = 2 * (H - 1)
+    return WindowBatch(
+        n_windows=W, n_individuals=nI, win_hap_off=np.arange(W + 1, dtype=np.int32) * H,
+        win_start=np.zeros(W, np.int32), win_end=np.full(W, 50, np.int32), hap_start=np.zeros(W, np.int32),
+        hap_seq_off=np.arange(W * H + 1, dtype=np.int64) * HAP_LEN, hap_seq=np.full(W * H * HAP_LEN + 1, 65, np.uint8),
+        wi_slot_off=np.arange(W * nI + 1, dtype=np.int64) * R, wi_n_good=np.full(W * nI, R, np.int32),
+        wi_n_bad=np.zeros(W * nI, np.int32), slot_read=np.arange(n_reads, dtype=np.int32),
+        read_seq_off=np.arange(n_reads + 1, dtype=np.int64) * READ_LEN, read_seq=np.full(n_reads * READ_LEN + 1, 65, np.uint8),
+        read_qual=np.zeros(n_reads * READ_LEN + 1, np.uint8), read_pos=np.zeros(n_reads, np.int32),
+        read_end=np.full(n_reads, READ_LEN, np.int32), read_mapq=np.zeros(n_reads, np.uint8),
+        read_qcfail=np.ones(n_reads, np.uint8),     # the template itself is never scored (every read "fails QC")
+        max_variants=mv, win_n_var=np.zeros(W, np.int32), hap_var_mask=np.zeros(W * H, np.uint64),
+        var_prior=np.zeros((W, mv), np.float64))
+
+
+def run_config5(args, rank, world, local_rank):
+    """BASELINE config 5: ~30 M windows x 2000 samples is ~6e16 cells and ~1 PB of inputs, so - as SURVEY 8d lays down - a
+    fixed 1/1000 subsample (30,000 windows, the same ones at every N: strong scaling) is generated ON THE DEVICE chunk by
+    chunk (plb_synth_fill_device, "synth-v1d"), scored and reduced to genotype calls / variant posteriors / haplotype
+    frequencies on the device, and only those are gathered (one all-gather at the end).  A step = one chunk of windows."""
+    import torch
+    import torch.distributed as dist
+    from platypus_b200 import _abi
+    from platypus_b200.engine import Engine
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    total = args.c5_windows
+    chunk = args.c5_chunk
+    lo, hi = total * rank // world, total * (rank + 1) // world
+    nI, R, H = C5_IND, C5_READS, N_HAPS
+    Gm, V = H * (H + 1) // 2, 2 * (H - 1)
+    stream = torch.cuda.Stream(device=dev)
+    eng = Engine(local_rank, stream=stream.cuda_stream)
+    tmpl = c5_template(chunk)
+    cells_per_window = nI * R * H * 16 * READ_LEN
+    f64, i32 = torch.float64, torch.int32
+    n_mine = hi - lo
+    n_pad = (total + world - 1) // world
+    with torch.cuda.stream(stream):
+        handle = eng.upload(tmpl)
+        out = {"gl": torch.zeros((chunk, nI, Gm), dtype=f64, device=dev), "gl_log_max": torch.zeros((chunk, nI), dtype=f64, device=dev),
+               "freq": torch.zeros((chunk, H), dtype=f64, device=dev), "em_post": torch.zeros((chunk, nI, Gm), dtype=f64, device=dev),
+               "call": torch.zeros((chunk, nI), dtype=i32, device=dev), "var_phred": torch.zeros((chunk, V), dtype=f64, device=dev),
+               "em_iters": torch.zeros((chunk,), dtype=i32, device=dev)}
+        ptrs = {k: v.data_ptr() for k, v in out.items()}
+        ptrs["max_haps"] = H
+        # per-rank results: what is gathered at the end (calls as bytes: G = 36 < 256)
+        calls = torch.zeros((n_pad, nI), dtype=torch.uint8, device=dev)
+        phred = torch.zeros((n_pad, V), dtype=f64, device=dev)
+        freq = torch.zeros((n_pad, H), dtype=f64, device=dev)
+
+        def do_chunk(first, n_live, store_at):
+            eng.synth_fill(handle, first)
+            eng.run_device(handle, ptrs, opt=OPT)
+            if store_at is not None and n_live > 0:
+                calls[store_at:store_at + n_live] = (out["call"][:n_live] + 1).to(torch.uint8)      # 0 = no call
+                phred[store_at:store_at + n_live] = out["var_phred"][:n_live]
+                freq[store_at:store_at + n_live] = out["freq"][:n_live]
+
+        for k in range(max(3, args.warmup)):
+            do_chunk(lo + k * chunk, 0, None)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        eng.set_timing(True)
+        l0 = eng.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        n_chunks = 0
+        for first in range(lo, hi, chunk):
+            do_chunk(first, min(chunk, hi - first), first - lo)
+            n_chunks += 1
+        if world > 1:   # the one collective: calls, posteriors and frequencies of every window to every rank
+            g_calls = torch.zeros((world, n_pad, nI), dtype=torch.uint8, device=dev)
+            g_phred = torch.zeros((world, n_pad, V), dtype=f64, device=dev)
+            g_freq = torch.zeros((world, n_pad, H), dtype=f64, device=dev)
+            dist.all_gather_into_tensor(g_calls, calls)
+            dist.all_gather_into_tensor(g_phred, phred)
+            dist.all_gather_into_tensor(g_freq, freq)
+        e1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        ms_total = e0.elapsed_time(e1)
+        launches = eng.launch_count - l0
+        ktimes, n_timed = eng.kernel_times()
+        eng.set_timing(False)
+        clocks = sampler.stop() if rank == 0 else None
+        stats = eng.last_stats()
+
+        # parity: regenerate sampled windows, download their inputs and run the CPU oracle on them
+        check = None
+        if rank == 0 and not args.no_cpu:
+            from oracle import oracle as O
+            rng = np.random.default_rng(5)
+            picks = sorted(int(x) for x in rng.choice(max(1, n_mine), min(2, n_mine), replace=False))
+            n_checked = 0
+            for k in picks:
+                first = lo + (k // chunk) * chunk
+                eng.synth_fill(handle, first)
+                eng.run_device(handle, ptrs, opt=OPT)
+                stream.synchronize()
+                host = eng.download(handle, tmpl)
+                one = host.slice_windows(k % chunk, k % chunk + 1)
+                want, _, _, _ = O.population_run(one, OPT, n_threads=os.cpu_count() or 1, max_haps=H)
+                got_call = out["call"][k % chunk].cpu().numpy()
+                assert np.array_equal(got_call, want["call"][0]), "config 5: genotype calls differ from the oracle"
+                assert np.array_equal(out["var_phred"][k % chunk].cpu().numpy()[:want["var_phred"].shape[1]], want["var_phred"][0])
+                np.testing.assert_allclose(out["freq"][k % chunk].cpu().numpy(), want["freq"][0], rtol=1e-9)
+                assert np.array_equal(calls[k].cpu().numpy(), (got_call + 1).astype(np.uint8))
+                n_checked += 1
+            check = {"windows_vs_oracle": n_checked, "individuals": nI, "calls_equal": True, "var_phred_equal": True}
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(n_mine) * cells_per_window, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        eng.free(handle)
+        return
+    ms = float(t[0])
+    cells = float(tot[0])
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    # algorithmic bytes of one chunk (SURVEY 8d layout): reads, haplotypes, per-read LL, GL
+    alg = chunk * (nI * R * ((READ_LEN + 3) // 4 + READ_LEN + 8) + H * ((HAP_LEN + 3) // 4 + 8) + 8 * H * nI * R + 8 * nI * Gm)
+    ach = alg / (ktimes["k_dp"] * 1e-3) / 1e9 if ktimes["k_dp"] > 0 else None
+    line = {
+        "metric": METRIC, "value": cells / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": n_chunks,
+        "warmup": max(3, args.warmup), "ms_per_step": ms / max(1, n_chunks), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int16 scores / f64 likelihoods", "data": "synthetic, generated on the device (synth-v1d, seed 20261017)",
+        "config": {"workload": "config5 multi-sample: fixed 1/1000 subsample = %d windows x %d individuals x %d reads x %d haplotypes, "
+                               "%d bp reads x %d bp haplotypes; the same windows at every N, %d windows per chunk; calls / posteriors / "
+                               "frequencies reduced on the device and gathered once" % (total, nI, R, H, READ_LEN, HAP_LEN, chunk),
+                   "windows_total": total, "windows_per_gpu": n_mine, "individuals": nI, "reads_per_individual": R, "n_gpus": world,
+                   "extrapolation": "30 M windows = 1000 x this job: %.1f GPU-hours at this rate" % (1000 * ms * 1e-3 * world / 3600.0),
+                   "l2": "one chunk's inputs (~%.1f GB) exceed the 126 MB L2; no explicit flush" % (chunk * nI * R * 2 * READ_LEN / 1e9)},
+        "total_ms": ms, "cells": cells, "clocks": clocks, "gpu_launches": int(tot[1]),
+        "e2e": {"value": cells / (ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "note": "inputs are generated on the device (they do not fit PCIe at this scale); the timed region includes generation, "
+                        "scoring, the window model and the final gather"},
+        "roofline": {"bound": "hbm", "kernel": "k_dp", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if ach else None,
+                     "traffic": None, "algorithmic_bytes_per_launch": alg, "kernel_ms": ktimes["k_dp"], "kernel_ms_all": ktimes,
+                     "launches_averaged": n_timed},
+        "gathered_bytes": int(world * n_pad * (nI + 8 * V + 8 * H)) if world > 1 else 0,
+        "oracle_check": check, "stats_last_chunk": stats,
+    }
     print(json.dumps(line), flush=True)
     eng.free(handle)
 
@@ -702,23 +895,30 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--windows", type=int, default=WINDOWS_PER_GPU, help="windows per GPU (default: config 2)")
+    ap.add_argument("--windows", type=int, default=0, help="windows per GPU (default: 10,000 = config 2; 62,500 for --config 4)")
     ap.add_argument("--cpu-procs", type=int, default=0, help="--impl reference: processes (default: all host cores)")
     ap.add_argument("--cpu-windows", type=int, default=0, help="--impl reference: windows per step (default: the workload)")
     ap.add_argument("--mode", default="default", choices=["default", "flank", "hla"],
                     help="run-time mode of the path: --calculateFlankScore=1 / --HLATyping=1 (not the headline)")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
-                    help="2 = BASELINE config 2 (headline); 3 = ragged read/haplotype lengths (profiling only)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="2 = BASELINE config 2 (headline); 3 = ragged read/haplotype lengths (profiling only); 4 = 62,500 "
+                         "windows per GPU (chr22-sized over 8 GPUs) with the gathered likelihoods checked; 5 = multi-sample "
+                         "mode, 2000 individuals, device-generated windows, strong scaling")
     ap.add_argument("--stage", default="path", choices=["path", "select"],
                     help="path = the headline likelihood path; select = the haplotype selection loop before it (N1, one GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--c5-windows", type=int, default=C5_WINDOWS, help="--config 5: windows of the whole job (all GPUs together)")
+    ap.add_argument("--c5-chunk", type=int, default=32, help="--config 5: windows generated and scored per step")
     ap.add_argument("--ascii", action="store_true", help="e2e leg: send byte-per-base sequences instead of the packed form")
     args = ap.parse_args()
     if args.stage == "select":
         if int(os.environ.get("RANK", "0")) == 0:
             run_select(args)
         return
-    global RAGGED, OPT, MODE
+    global RAGGED, OPT, MODE, CONFIG
+    CONFIG = args.config
+    if not args.windows:
+        args.windows = 62500 if args.config == 4 else WINDOWS_PER_GPU
     RAGGED = args.config == 3
     MODE = args.mode
     if args.mode != "default":
@@ -737,7 +937,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.config == 5:
+            run_config5(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -545,6 +545,19 @@ void plb_batch_free(PlbContext* ctx, PlbDeviceBatch* b);
 int plb_run_device(PlbContext* ctx, PlbDeviceBatch* batch, const PlbOptions* opt,
                    PlbPopulationOut* dev_pop, PlbLoglikOut* dev_ll);
 
+/* Copies the INPUT arrays of a resident batch back into `host_batch`, which must have the shape (counts and offsets) of
+ * the batch that was uploaded: sequences, qualities, read fields, window coordinates, variant masks and priors. */
+int plb_batch_download(PlbContext* ctx, PlbDeviceBatch* batch, PlbWindowBatch* host_batch);
+
+/*
+ * Measurement support (BASELINE config 5, SURVEY 8d: "generated on device"): overwrites the inputs of a resident ASCII
+ * batch in place with the synthetic windows first_window, first_window + 1, ... ("synth-v1d": the recipe of the host
+ * generator with a counter-based hash as random source, platypus_b200/csrc/plb_synth.cuh).  Shapes stay those of the
+ * uploaded batch - every window's haplotypes of one length, slot s = read s, all reads good - so the launch plan made at
+ * upload time serves every refill.  Asynchronous on the context's stream.
+ */
+int plb_synth_fill_device(PlbContext* ctx, PlbDeviceBatch* batch, uint64_t seed, int64_t first_window);
+
 /* Statistics of the last plb_run_device / *_host call on this context (after a stream
  * synchronise): number of scored (read,haplotype) pairs, band-DP executions, and
  * algorithmic cells = 16 * readLen summed over scored pairs. */

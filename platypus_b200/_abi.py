@@ -181,6 +181,10 @@ def declare(lib):
     lib.plb_batch_upload.restype = C.c_int
     lib.plb_batch_free.argtypes = [_p, _p]
     lib.plb_batch_free.restype = None
+    lib.plb_batch_download.argtypes = [_p, _p, P(PlbWindowBatch)]
+    lib.plb_batch_download.restype = C.c_int
+    lib.plb_synth_fill_device.argtypes = [_p, _p, C.c_uint64, C.c_int64]
+    lib.plb_synth_fill_device.restype = C.c_int
     lib.plb_run_device.argtypes = [_p, _p, P(PlbOptions), P(PlbPopulationOut), P(PlbLoglikOut)]
     lib.plb_run_device.restype = C.c_int
     lib.plb_last_stats.argtypes = [_p, P(PlbRunStats)]
@@ -213,6 +217,6 @@ EXPORTED_SYMBOLS = [
     "plb_run_device", "plb_last_stats", "plb_set_timing", "plb_kernel_times",
     "plb_build_haplotypes_host", "plb_select_haplotypes_host", "plb_select_replay_host", "plb_best_score_haplotypes_host",
     "plb_select_stats", "plb_population_submit", "plb_population_wait", "plb_pack_bases_host", "plb_pack_nibbles_host",
-    "plb_stage_reads_host", "plb_window_slices_host",
+    "plb_stage_reads_host", "plb_window_slices_host", "plb_batch_download", "plb_synth_fill_device",
 ]
 KERNEL_NAMES = ["k_prep", "k_anchor", "k_general", "k_dp", "k_genotype", "k_population"]

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), "libplatypus_b200.so")
 SRCS = ["plb_api.cu"]
-DEPS = ["plb_api.cu", "plb_kernels.cuh", "plb_dp.cuh", os.path.join("..", "..", "include", "platypus_b200.h"), "plb_kmer.cuh", "plb_select.cuh", "plb_stage.cuh"]
+DEPS = ["plb_api.cu", "plb_kernels.cuh", "plb_dp.cuh", os.path.join("..", "..", "include", "platypus_b200.h"), "plb_kmer.cuh", "plb_select.cuh", "plb_stage.cuh", "plb_synth.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--extended-lambda",
               "-shared", "-Xcompiler", "-fPIC,-fopenmp", "-lgomp"]
 

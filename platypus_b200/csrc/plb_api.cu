@@ -140,6 +140,8 @@ struct PlbDeviceBatch {
     double* ll_scratch = nullptr;
     double* em_scratch = nullptr;      // [W][nInd][Gmax_plan]
     int32_t max_haps = 0;              // largest H in the batch
+    int32_t max_hap_len = 0;
+    int64_t hap_bytes = 0, read_bytes = 0;
     size_t em_scratch_elems = 0;
     bool have_var = false;
     bool shares_reads = false;         // window / slot / read arrays belong to another batch (prepare_batch `share`)
@@ -732,6 +734,9 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
     int max_H = 0;
     for (int w = 0; w < W; ++w) max_H = std::max(max_H, hb->win_hap_off[w + 1] - hb->win_hap_off[w]);
     db->max_haps = max_H;
+    for (int h = 0; h < n_haps; ++h) db->max_hap_len = std::max<int32_t>(db->max_hap_len, (int32_t)(hb->hap_seq_off[h + 1] - hb->hap_seq_off[h]));
+    db->hap_bytes = hap_bytes;
+    db->read_bytes = read_bytes;
 
     // device layout
     Layout L;
@@ -2326,3 +2331,6 @@ extern "C" int plb_gap_open_host(PlbContext* c, int32_t n_haps, const int64_t* o
 
 // ---- N3: read staging (host) ----------------------------------------------------------------------
 #include "plb_stage.cuh"
+
+// ---- measurement support: synthetic windows generated on the device (BASELINE config 5) -----------------
+#include "plb_synth.cuh"

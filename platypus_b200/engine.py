@@ -388,6 +388,17 @@ class Engine:
     def free(self, handle):
         self.lib.plb_batch_free(self.ctx, handle)
 
+    def synth_fill(self, handle, first_window, seed=20261017):
+        """Measurement support: refill a resident batch in place with device-generated synthetic windows
+        (plb_synth_fill_device, "synth-v1d"); asynchronous on the context stream."""
+        _check(self.lib, self.lib.plb_synth_fill_device(self.ctx, handle, int(seed), int(first_window)))
+
+    def download(self, handle, batch: WindowBatch):
+        """Copy the input arrays of a resident batch back into `batch` (same shape as the uploaded one), in place."""
+        s = batch.as_struct()
+        _check(self.lib, self.lib.plb_batch_download(self.ctx, handle, C.byref(s)))
+        return batch
+
     def run_device(self, handle, pop_ptrs=None, ll_ptr=None, score_ptr=None, ll_off_ptr=None, opt=None):
         """Launch the whole path on a device-resident batch; asynchronous on the context stream.
         pop_ptrs: dict name -> device pointer (int) incl. 'max_haps'."""

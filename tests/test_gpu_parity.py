@@ -981,3 +981,60 @@ def test_n3_bam_records_to_packed_batch_to_calls(engine, golden_dir):
     sc = engine.window_loglik(b)[1]
     scored = sc >= 0          # -1 = short-circuited by the QC-fail / overlap rule (the fixture scores every pair)
     assert scored.sum() > 500 and np.array_equal(sc[scored], h["score_default"][scored])      # the reference's own calign.pyx scores
+
+
+def test_device_generated_windows_roundtrip_and_parity(engine, oracle):
+    """plb_synth_fill_device ("synth-v1d", the device-side generator BASELINE config 5 needs) + plb_batch_download: the
+    windows depend on (seed, window id) only - not on how they are chunked - are valid inputs, have the recipe's
+    statistics, and the resident results equal the CPU oracle run on the downloaded inputs."""
+    import ctypes as C
+    import dataclasses
+    import torch
+    import bench
+    old = (bench.C5_IND, bench.C5_READS)
+    bench.C5_IND, bench.C5_READS = 5, 12
+    try:
+        tmpl = bench.c5_template(6)
+        tmpl2 = bench.c5_template(2)
+    finally:
+        bench.C5_IND, bench.C5_READS = old
+    h = engine.upload(tmpl)
+    engine.synth_fill(h, 1000)
+    a = dataclasses.replace(engine.download(h, tmpl), _keep=[])
+    a = dataclasses.replace(a, **{f: getattr(a, f).copy() for f in a.__dataclass_fields__ if isinstance(getattr(a, f), np.ndarray)})
+    # run the resident batch and compare with the oracle on the downloaded bytes
+    W, nI, H = 6, 5, 8
+    Gm, V = 36, 14
+    out = {"gl": torch.zeros((W, nI, Gm), dtype=torch.float64, device="cuda"), "freq": torch.zeros((W, H), dtype=torch.float64, device="cuda"),
+           "em_post": torch.zeros((W, nI, Gm), dtype=torch.float64, device="cuda"), "call": torch.zeros((W, nI), dtype=torch.int32, device="cuda"),
+           "var_phred": torch.zeros((W, V), dtype=torch.float64, device="cuda")}
+    ptrs = {k: v.data_ptr() for k, v in out.items()}
+    ptrs["max_haps"] = H
+    engine.run_device(h, ptrs)
+    torch.cuda.synchronize()
+    engine.last_stats()
+    assert engine.lib.plb_validate(C.byref(a.as_struct()), C.byref(_abi.PlbOptions.default()), 0) == 0
+    want, _, _, _ = oracle.population_run(a, max_haps=H)
+    assert np.array_equal(out["call"].cpu().numpy(), want["call"])
+    assert np.array_equal(out["var_phred"].cpu().numpy()[:, :want["var_phred"].shape[1]], want["var_phred"])
+    np.testing.assert_allclose(out["gl"].cpu().numpy(), want["gl"], rtol=RTOL_TIGHT, atol=1e-300)
+    np.testing.assert_allclose(out["freq"].cpu().numpy(), want["freq"], rtol=RTOL_TIGHT)
+    engine.free(h)
+    # the recipe: haplotypes distinct, reads mostly match their source, variants declared
+    hs = a.hap_seq[:6 * 8 * 250].reshape(6, 8, 250)
+    for w in range(6):
+        assert len({hs[w, g].tobytes() for g in range(8)}) == 8
+    assert set(np.unique(a.read_seq[:-1])) <= set(b"ACGT") and a.read_qual[:-1].min() >= 2 and a.read_qual[:-1].max() <= 40
+    assert (a.win_n_var >= 7).all() and (a.win_n_var <= 14).all() and (a.hap_var_mask.reshape(6, 8)[:, 0] == 0).all()
+    assert 0.80 < (a.read_mapq == 60).mean() < 0.90
+    sc = oracle.window_loglik(a)[1].reshape(6, 5, 8, 12)
+    assert np.median(sc.min(axis=2)) < 60          # every read has a haplotype it matches up to sequencing errors
+    # chunk independence: windows 1002..1003 generated as their own chunk are the same bytes
+    h2 = engine.upload(tmpl2)
+    engine.synth_fill(h2, 1002)
+    b2 = engine.download(h2, tmpl2)
+    engine.free(h2)
+    n = 5 * 12 * 150
+    assert np.array_equal(b2.read_seq[:2 * n], a.read_seq[2 * n:4 * n]) and np.array_equal(b2.read_qual[:2 * n], a.read_qual[2 * n:4 * n])
+    assert np.array_equal(b2.hap_seq[:2 * 8 * 250], a.hap_seq[2 * 8 * 250:4 * 8 * 250])
+    assert np.array_equal(b2.read_pos, a.read_pos[2 * 60:4 * 60]) and np.array_equal(b2.hap_var_mask, a.hap_var_mask[16:32])
