@@ -908,7 +908,7 @@ def main():
                     help="path = the headline likelihood path; select = the haplotype selection loop before it (N1, one GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--c5-windows", type=int, default=C5_WINDOWS, help="--config 5: windows of the whole job (all GPUs together)")
-    ap.add_argument("--c5-chunk", type=int, default=32, help="--config 5: windows generated and scored per step")
+    ap.add_argument("--c5-chunk", type=int, default=148, help="--config 5: windows generated and scored per step")
     ap.add_argument("--ascii", action="store_true", help="e2e leg: send byte-per-base sequences instead of the packed form")
     args = ap.parse_args()
     if args.stage == "select":

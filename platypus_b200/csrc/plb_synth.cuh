@@ -103,10 +103,14 @@ __global__ void __launch_bounds__(128) k_synth_windows(DevBatch b, uint64_t seed
         for (int v = n_var + tid; v < b.max_variants; v += blockDim.x) ((double*)b.var_prior)[(size_t)w * b.max_variants + v] = 0.0;
 }
 
-// One thread per read (slot s of the batch = read s of the pool).
+// One WARP per read (slot s of the batch = read s of the pool): lanes along the read, 32 bases per round, so that the
+// stores coalesce.  Indel errors make a base's source position depend on the events before it; that is an exclusive
+// prefix sum of (deletion ? 2 : insertion ? 0 : 1) over the earlier bases - a warp scan with a carry between rounds.
 __global__ void __launch_bounds__(128) k_synth_reads(DevBatch b, uint64_t seed, int64_t first_window) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= b.n_slots) return;
+    const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= b.n_slots) return;   // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xFFFFFFFFu;
     const int wi = b.slot_wi[s];
     const int nInd = b.n_individuals;
     const int w = wi / nInd, ind = wi % nInd;
@@ -128,34 +132,46 @@ __global__ void __launch_bounds__(128) k_synth_reads(DevBatch b, uint64_t seed, 
     uint8_t* rs = (uint8_t*)b.read_seq + ro;
     uint8_t* rq = (uint8_t*)b.read_qual + ro;
     const char* acgt = "ACGT";
-    int x = idx;
-    for (int k = 0; k < L; ++k) {
+    int carry = idx;   // source position of the round's first base, before its own deletion
+    for (int k0 = 0; k0 < L; k0 += 32) {
+        const int k = k0 + lane;
         const uint32_t u = rnd32(seed, wg, stream + (1u << 20), base_ctr + (uint32_t)k);   // quality
         const uint32_t e = rnd32(seed, wg, stream + (2u << 20), base_ctr + (uint32_t)k);   // event
         const uint32_t v = rnd32(seed, wg, stream + (3u << 20), base_ctr + (uint32_t)k);   // substitution / random base
         const int q = (u % 10u) ? 25 + (int)((u >> 8) % 16u) : 2 + (int)((u >> 8) % 23u);
-        const bool ins = e < 4294967u;                                 // 0.1 %
-        const bool del = !ins && e < 2u * 4294967u;                    // 0.1 %
-        if (del) ++x;
-        uint8_t c = ins ? (uint8_t)acgt[v & 3] : hap[min(x, hl - 1)];
-        if (!ins) ++x;
-        if ((v >> 2 << 2) < c_sub_thresh[q]) {                         // substitution: one of the three other bases
-            const int code = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3;
-            c = (uint8_t)acgt[(code + 1 + (int)((e >> 12) % 3u)) & 3];
+        const bool ins = k < L && e < 4294967u;                        // 0.1 %
+        const bool del = k < L && !ins && e < 2u * 4294967u;           // 0.1 %
+        const int step = k < L ? (del ? 2 : ins ? 0 : 1) : 0;          // source bases this base consumes
+        int incl = step;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += n;
         }
-        rs[k] = c;
-        rq[k] = (uint8_t)q;
+        const int x = carry + incl - step + (del ? 1 : 0);             // a deletion skips one source base first
+        carry += __shfl_sync(FULL, incl, 31);
+        if (k < L) {
+            uint8_t c = ins ? (uint8_t)acgt[v & 3] : hap[min(x, hl - 1)];
+            if ((v >> 2 << 2) < c_sub_thresh[q]) {                     // substitution: one of the three other bases
+                const int code = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3;
+                c = (uint8_t)acgt[(code + 1 + (int)((e >> 12) % 3u)) & 3];
+            }
+            rs[k] = c;
+            rq[k] = (uint8_t)q;
+        }
     }
-    const uint32_t m = rnd32(seed, wg, stream, base_ctr + 2);
-    const uint32_t mm = m % 100u;
-    const int mapq = mm < 85u ? 60 : mm < 95u ? 20 + (int)((m >> 8) % 40u) : (int)((m >> 8) % 20u);
-    const uint32_t j = rnd32(seed, wg, stream, base_ctr + 3);
-    const int jit = (j % 10u) ? 0 : -5 + (int)((j >> 8) % 11u);
-    const int hs = 100000 + (int)(wg % 2000000ull) * 1000;
-    ((int32_t*)b.read_pos)[s] = hs + idx + jit;
-    ((int32_t*)b.read_end)[s] = hs + idx + jit + L;
-    ((uint8_t*)b.read_mapq)[s] = (uint8_t)mapq;
-    ((uint8_t*)b.read_qcfail)[s] = 0;
+    if (lane == 0) {
+        const uint32_t m = rnd32(seed, wg, stream, base_ctr + 2);
+        const uint32_t mm = m % 100u;
+        const int mapq = mm < 85u ? 60 : mm < 95u ? 20 + (int)((m >> 8) % 40u) : (int)((m >> 8) % 20u);
+        const uint32_t j = rnd32(seed, wg, stream, base_ctr + 3);
+        const int jit = (j % 10u) ? 0 : -5 + (int)((j >> 8) % 11u);
+        const int hs = 100000 + (int)(wg % 2000000ull) * 1000;
+        ((int32_t*)b.read_pos)[s] = hs + idx + jit;
+        ((int32_t*)b.read_end)[s] = hs + idx + jit + L;
+        ((uint8_t*)b.read_mapq)[s] = (uint8_t)mapq;
+        ((uint8_t*)b.read_qcfail)[s] = 0;
+    }
 }
 
 }  // namespace plb
@@ -185,7 +201,7 @@ extern "C" int plb_synth_fill_device(PlbContext* c, PlbDeviceBatch* db, uint64_t
     cudaStream_t st = c->stream;
     k_synth_windows<<<d.n_windows, 128, (size_t)db->max_hap_len + 32, st>>>(d, seed, first_window);
     if ((rc = launch_check(c, "k_synth_windows"))) return rc;
-    k_synth_reads<<<(unsigned)((d.n_slots + 127) / 128), 128, 0, st>>>(d, seed, first_window);
+    k_synth_reads<<<(unsigned)((d.n_slots * 32 + 127) / 128), 128, 0, st>>>(d, seed, first_window);
     return launch_check(c, "k_synth_reads");
 }
 

@@ -645,3 +645,98 @@ def n1_golden_cases(golden_dir):
                         opts={k2: int(z["opt_" + k2][k]) for k2 in ("max_haplotypes", "original_max_haplotypes", "max_variants",
                                                                    "filter_by_coverage", "coverage_sampling_level")}))
     return out
+
+
+# ---- large differential test: adversarial windows ------------------------------------------------------------------
+
+def adversarial_batch(seed, n_windows, n_haps=8, n_reads=60):
+    """Windows built to reach every branch of mapAndAlignReadToHaplotype (calign.pyx:170-272) and every form of the band
+    alignment through the WINDOW path: tandem repeats (tied vote maxima, many candidates), homopolymer runs of 30-60 bp
+    (gap-open below gap-extend: the 6-op recurrence), haplotype N's (8-op form), IUPAC / lower-case bytes (byte-exact
+    path), reads of 9-600 bp and one family above 2000 bp, reads unrelated to every haplotype, reads with N's, zeroed
+    qualities, and BAM positions off by up to +-300.  Deterministic in (seed, n_windows)."""
+    rng = random.Random(seed)
+    rnd = np.random.default_rng(seed)
+
+    def rseq(n):
+        return ACGT_ARR[rnd.integers(0, 4, n)].tobytes()
+
+    wins = []
+    for w in range(n_windows):
+        fam = w % 11
+        long_reads = fam == 7
+        huge = fam == 8 and w % 44 == 8
+        Lmax = 2100 if huge else (rng.choice([300, 450, 600]) if long_reads else rng.choice([30, 100, 150, 150, 250]))
+        hl = max(Lmax + rng.randint(40, 260), 130)
+        base = bytearray(rseq(hl + 8))
+        if fam in (0, 1):      # tandem repeat in the middle
+            unit = rseq(rng.randint(1, 12))
+            a = rng.randint(10, max(11, hl // 3))
+            n_rep = rng.randint(20, max(21, (hl // 2) // len(unit)))
+            rep = (unit * n_rep)[:hl - a - 10]
+            base[a:a + len(rep)] = rep
+        if fam in (2, 3):      # long homopolymer: gap-open drops below gap-extend inside runs >= 40
+            a = rng.randint(10, hl - 80)
+            base[a:a + rng.randint(30, 60)] = bytes([rng.choice(ACGT)]) * 60
+            base = base[:hl + 8]
+        if fam == 4:           # N's in the haplotypes
+            for _ in range(rng.randint(1, 8)):
+                p = rng.randrange(hl)
+                base[p:p + rng.choice([1, 1, 2, 5])] = b"N" * 5
+            base = base[:hl + 8]
+        if fam == 5:           # bytes outside ACGTN
+            for _ in range(rng.randint(1, 4)):
+                base[rng.randrange(hl)] = rng.choice(b"RYKMSWacgtn")
+        haps = [bytes(base[:hl])]
+        c0 = hl // 2 - 25
+        while len(haps) < n_haps:
+            h = bytearray(base)
+            for _ in range(rng.randint(1, 3)):
+                p = c0 + rng.randrange(50)
+                u = rng.random()
+                if u < 0.6:
+                    h[p] = rng.choice(ACGT)
+                elif u < 0.8:
+                    h[p:p] = rseq(rng.randint(1, 4))
+                else:
+                    del h[p:p + rng.randint(1, 4)]
+            hb = bytes(h[:hl])
+            if len(hb) == hl and hb not in haps:
+                haps.append(hb)
+            elif rng.random() < 0.05:
+                haps.append(bytes(base[:hl - 1]) + bytes([rng.choice(ACGT)]))   # give up on distinct variants
+        hs = 50000 + 3000 * w
+        reads = []
+        for _ in range(n_reads):
+            if huge:
+                L = rng.choice([2001, 2050, 2100])
+            elif long_reads:
+                L = rng.randint(250, Lmax)
+            else:
+                L = rng.choice([9, 10, 12, 20, 36, 50, 76, Lmax, Lmax, Lmax, rng.randint(9, Lmax)])
+            L = min(L, hl - 16)
+            src = rng.choice(haps)
+            u = rng.random()
+            idx = rng.randint(0, hl - L - 16)
+            if u < 0.08 and L <= 450:
+                seq = rseq(L)                                       # unrelated read (its score stays inside the int16 range)
+            else:
+                seq = mutate(rng, src[idx:] + rseq(8), L, sub=rng.choice([0.0, 0.01, 0.05]), ins=0.004, dele=0.004,
+                             n_rate=0.003 if fam != 9 else 0.02)
+            q = rnd.integers(2, 42, L).astype(np.uint8)
+            if rng.random() < 0.1:
+                q[rnd.integers(0, L, max(1, L // 10))] = 0
+            jit = rng.choice([0, 0, 0, 0, rng.randint(-8, 8), rng.randint(-300, 300)])
+            pos = hs + idx + jit
+            reads.append(Read(seq, q.tobytes(), pos, pos + L, rng.choice([60, 60, 60, 37, 12, 0]), rng.random() < 0.02))
+        ng = rng.randint(n_reads // 2, n_reads)
+        nb = rng.randint(0, n_reads - ng)
+        if w % 5 == 4:       # a 50 bp interval: the overlap < 7 rule short-circuits many good / bad reads
+            ws, we = hs + c0, hs + c0 + 50
+        else:                # the interval spans the haplotype: nearly every read is scored
+            ws, we = hs + 5, hs + hl - 5
+        wins.append(Window(ws, we, hs, haps, [(reads[:ng], reads[ng:ng + nb], reads[ng + nb:])]))
+    return WindowBatch.from_windows(wins, 1)
+
+
+ACGT_ARR = np.frombuffer(ACGT, np.uint8)

@@ -1038,3 +1038,54 @@ def test_device_generated_windows_roundtrip_and_parity(engine, oracle):
     assert np.array_equal(b2.read_seq[:2 * n], a.read_seq[2 * n:4 * n]) and np.array_equal(b2.read_qual[:2 * n], a.read_qual[2 * n:4 * n])
     assert np.array_equal(b2.hap_seq[:2 * 8 * 250], a.hap_seq[2 * 8 * 250:4 * 8 * 250])
     assert np.array_equal(b2.read_pos, a.read_pos[2 * 60:4 * 60]) and np.array_equal(b2.hap_var_mask, a.hap_var_mask[16:32])
+
+
+def test_large_differential_scores_vs_reference_alignc(engine, oracle):
+    """>= 1 M adversarial (read, haplotype) pairs through the window path, integer scores bit for bit against the CPU
+    oracle's mapAndAlignReadToHaplotype (calign.pyx:170-272) with every band alignment done by the REFERENCE'S OWN
+    align.c (oracle/_ref/libalign_ref.so, when present) under OpenMP.  The windows (tests/cases.adversarial_batch) put the
+    5-op, 6-op (homopolymers >= 40 bp) and 8-op (haplotype N) recurrences, the byte-exact path, the exact tied-vote path,
+    reads of 9-600 bp and > 2000 bp and BAM positions off by +-300 on the path the headline benchmark measures."""
+    import time
+    n_thr = os.cpu_count() or 1
+    t0 = time.time()
+    b = cases.adversarial_batch(20261017, 2300)
+    n_pairs = int(b.ll_offsets()[-1])
+    assert n_pairs >= 1000000
+    t1 = time.time()
+    ll, sc = engine.window_loglik(b)
+    st = engine.last_stats()
+    kind = oracle.use_reference_kernel(True, traceback=False)
+    try:
+        ll0, sc0, st0 = oracle.window_loglik(b, n_threads=n_thr)
+    finally:
+        oracle.use_reference_kernel(False)
+    t2 = time.time()
+    defined = sc0 < 15871                 # beyond the reference's own int16 range its result is undefined (align.c:81, 97)
+    assert defined.mean() > 0.999
+    bad = np.nonzero((sc != sc0) & defined)[0]
+    assert len(bad) == 0, "scores differ at pairs %s: %s vs %s" % (bad[:8], sc[bad[:8]], sc0[bad[:8]])
+    np.testing.assert_allclose(ll[defined], ll0[defined], rtol=RTOL_TIGHT, atol=0)
+    assert st["n_pairs"] == st0["n_pairs"] and st["n_pairs_scored"] == st0["n_pairs_scored"] > 700000
+    assert st["n_anchor_exact"] > 1000            # the exact tied-vote path did run
+    flags = {int(x) for x in np.unique(sc0[sc0 >= 0] == 1000000)}
+    print("large differential: %d pairs (%d scored, %d band alignments, %d exact-vote pairs), generated in %.1f s, "
+          "GPU + oracle (%s align kernel, %d threads) %.1f s" % (n_pairs, st["n_pairs_scored"], st["n_dp"], st["n_anchor_exact"],
+                                                                 t1 - t0, "reference" if kind else "oracle", n_thr, t2 - t1), flags)
+
+
+def test_full_config2_every_window_vs_oracle(engine, oracle):
+    """All 10,000 windows of BASELINE config 2 - 5.12 M pairs - against the oracle with the reference's align.c: integer
+    scores bit for bit, per-read LL, genotype likelihoods, EM frequencies, calls and posteriors (not a sample)."""
+    n_thr = os.cpu_count() or 1
+    b = synth.make_batch_parallel(10000)
+    got = engine.population_run(b, want_ll=True)
+    oracle.use_reference_kernel(True, traceback=False)
+    try:
+        want, ll0, sc0, st0 = oracle.population_run(b, n_threads=n_thr)
+    finally:
+        oracle.use_reference_kernel(False)
+    assert np.array_equal(got["score"], sc0)
+    np.testing.assert_allclose(got["ll"], ll0, rtol=RTOL_TIGHT, atol=0)
+    _check_population(got, want)
+    assert engine.last_stats()["cells"] == st0["cells"] == synth.algorithmic_cells(b)
