@@ -785,8 +785,16 @@ def run_config5(args, rank, world, local_rank):
         phred = torch.zeros((n_pad, V), dtype=f64, device=dev)
         freq = torch.zeros((n_pad, H), dtype=f64, device=dev)
 
+        gen_events = []
+
         def do_chunk(first, n_live, store_at):
+            if store_at is not None:
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(stream)
             eng.synth_fill(handle, first)
+            if store_at is not None:
+                g1.record(stream)
+                gen_events.append((g0, g1))
             eng.run_device(handle, ptrs, opt=OPT)
             if store_at is not None and n_live > 0:
                 calls[store_at:store_at + n_live] = (out["call"][:n_live] + 1).to(torch.uint8)      # 0 = no call
@@ -821,6 +829,7 @@ def run_config5(args, rank, world, local_rank):
         stream.synchronize()
         torch.cuda.synchronize()
         ms_total = e0.elapsed_time(e1)
+        ms_gen = sum(a.elapsed_time(b_) for a, b_ in gen_events)
         launches = eng.launch_count - l0
         ktimes, n_timed = eng.kernel_times()
         eng.set_timing(False)
@@ -850,7 +859,7 @@ def run_config5(args, rank, world, local_rank):
                 n_checked += 1
             check = {"windows_vs_oracle": n_checked, "individuals": nI, "calls_equal": True, "var_phred_equal": True}
 
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_total - ms_gen], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(n_mine) * cells_per_window, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -858,7 +867,7 @@ def run_config5(args, rank, world, local_rank):
     if rank != 0:
         eng.free(handle)
         return
-    ms = float(t[0])
+    ms, ms_score = float(t[0]), float(t[1])
     cells = float(tot[0])
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
@@ -866,8 +875,10 @@ def run_config5(args, rank, world, local_rank):
     alg = chunk * (nI * R * ((READ_LEN + 3) // 4 + READ_LEN + 8) + H * ((HAP_LEN + 3) // 4 + 8) + 8 * H * nI * R + 8 * nI * Gm)
     ach = alg / (ktimes["k_dp"] * 1e-3) / 1e9 if ktimes["k_dp"] > 0 else None
     line = {
-        "metric": METRIC, "value": cells / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": n_chunks,
-        "warmup": max(3, args.warmup), "ms_per_step": ms / max(1, n_chunks), "higher_is_better": True, "scaling": "strong",
+        # value: a chunk's inputs are resident when its scoring starts (generation time excluded, max over ranks);
+        # e2e: everything - generation, scoring, window model, final gather
+        "metric": METRIC, "value": cells / (ms_score * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": n_chunks,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_score / max(1, n_chunks), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int16 scores / f64 likelihoods", "data": "synthetic, generated on the device (synth-v1d, seed 20261017)",
         "config": {"workload": "config5 multi-sample: fixed 1/1000 subsample = %d windows x %d individuals x %d reads x %d haplotypes, "
                                "%d bp reads x %d bp haplotypes; the same windows at every N, %d windows per chunk; calls / posteriors / "
@@ -875,7 +886,7 @@ def run_config5(args, rank, world, local_rank):
                    "windows_total": total, "windows_per_gpu": n_mine, "individuals": nI, "reads_per_individual": R, "n_gpus": world,
                    "extrapolation": "30 M windows = 1000 x this job: %.1f GPU-hours at this rate" % (1000 * ms * 1e-3 * world / 3600.0),
                    "l2": "one chunk's inputs (~%.1f GB) exceed the 126 MB L2; no explicit flush" % (chunk * nI * R * 2 * READ_LEN / 1e9)},
-        "total_ms": ms, "cells": cells, "clocks": clocks, "gpu_launches": int(tot[1]),
+        "total_ms": ms, "scoring_ms": ms_score, "cells": cells, "clocks": clocks, "gpu_launches": int(tot[1]),
         "e2e": {"value": cells / (ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": "inputs are generated on the device (they do not fit PCIe at this scale); the timed region includes generation, "
                         "scoring, the window model and the final gather"},

@@ -27,6 +27,10 @@ __device__ __forceinline__ uint32_t rnd32(uint64_t seed, uint64_t win, uint32_t 
     return (uint32_t)(mix64(mix64(seed ^ (win * 0x9E3779B97F4A7C15ull)) ^ ((uint64_t)stream << 32 | ctr)) >> 32);
 }
 
+__device__ __forceinline__ uint64_t rnd64(uint64_t seed, uint64_t win, uint32_t stream, uint32_t ctr) {
+    return mix64(mix64(seed ^ (win * 0x9E3779B97F4A7C15ull)) ^ ((uint64_t)stream << 32 | ctr));
+}
+
 __constant__ uint32_t c_sub_thresh[48];   // P(substitution | quality q) * 2^32, q = 0..47
 
 constexpr int kSynthCentre = 50;
@@ -135,9 +139,10 @@ __global__ void __launch_bounds__(128) k_synth_reads(DevBatch b, uint64_t seed, 
     int carry = idx;   // source position of the round's first base, before its own deletion
     for (int k0 = 0; k0 < L; k0 += 32) {
         const int k = k0 + lane;
+        // two hashes per base: 64 bits for the event (e) and the substitution test / random base (v), 32 for the quality
+        const uint64_t hv = rnd64(seed, wg, stream + (2u << 20), base_ctr + (uint32_t)k);
+        const uint32_t e = (uint32_t)(hv >> 32), v = (uint32_t)hv;
         const uint32_t u = rnd32(seed, wg, stream + (1u << 20), base_ctr + (uint32_t)k);   // quality
-        const uint32_t e = rnd32(seed, wg, stream + (2u << 20), base_ctr + (uint32_t)k);   // event
-        const uint32_t v = rnd32(seed, wg, stream + (3u << 20), base_ctr + (uint32_t)k);   // substitution / random base
         const int q = (u % 10u) ? 25 + (int)((u >> 8) % 16u) : 2 + (int)((u >> 8) % 23u);
         const bool ins = k < L && e < 4294967u;                        // 0.1 %
         const bool del = k < L && !ins && e < 2u * 4294967u;           // 0.1 %
