@@ -603,19 +603,23 @@ def run_ours(args, rank, world, local_rank):
         gl_dev = [torch.zeros_like(out["gl"]) for _ in range(2)]
         e2e_gathered = [torch.cuda.Event() for _ in range(2)]
 
+        if world > 1:   # the likelihood block stays on the GPU for the collective (output pointers may be device pointers)
+            for j in range(2):
+                host_outs[j]["gl"] = gl_dev[j]
+
         def finish(job, j, n_done):
             eng.population_wait(job)
             if world > 1:   # the step's genotype likelihoods join the other ranks' (side stream; next job keeps running)
-                if n_done >= 2:
-                    e2e_gathered[j].synchronize()
                 with torch.cuda.stream(side):
-                    gl_dev[j].copy_(pinned[("gl", j)], non_blocking=True)
+                    pinned[("gl", j)].copy_(gl_dev[j], non_blocking=True)     # ... and reaches the host like every output
                     dist.all_gather_into_tensor(gl_all, gl_dev[j])
                     e2e_gathered[j].record(side)
 
         def e2e_run(n):
             jobs, each, t_prev, n_done = [], [], time.perf_counter(), 0
             for i in range(n):
+                if world > 1 and i >= 2:
+                    e2e_gathered[i % 2].synchronize()      # the job writes gl_dev[i % 2]: its previous gather must be through
                 jobs.append((eng.population_submit(hb, out=host_outs[i % 2], opt=OPT), i % 2))
                 if len(jobs) == 2:
                     finish(*jobs.pop(0), n_done)
@@ -646,8 +650,10 @@ def run_ours(args, rank, world, local_rank):
         e2e_each = e2e_run(e2e_steps)
         e2e_s = (time.perf_counter() - t0) / e2e_steps
         # parity guard: the host path and the device path must agree bit for bit
-        for ho in host_outs:
-            assert np.array_equal(ho["gl"], out["gl"].cpu().numpy())
+        if world > 1:
+            side.synchronize()
+        for j in range(2):
+            assert np.array_equal(pinned[("gl", j)].numpy(), out["gl"].cpu().numpy())
         if world > 1:
             assert torch.equal(gl_all[rank], out["gl"])
 
@@ -710,7 +716,7 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms, "ms_each_step": e2e_each, "steps": e2e_steps,
-                "single_call_ms": single, "input_format": "ascii" if args.ascii else "2-bit bases + 8-bit qualities (batch.pack)",
+                "single_call_ms": single, "input_format": "ascii" if args.ascii else "2-bit bases + %d-bit quality codes (batch.pack)" % (hb.qual_bits or 8),
                 "api": "plb_population_submit / plb_population_wait, two batches in flight (pinned host buffers)%s"
                        % ("; per step the likelihood block is all-gathered over NCCL" if world > 1 else "")},
         "gpu_launches": total_launches,

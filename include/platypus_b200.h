@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PLB_ABI_VERSION 4
+#define PLB_ABI_VERSION 5
 
 /* status codes */
 #define PLB_OK              0
@@ -134,6 +134,15 @@ typedef struct PlbWindowBatch {
     int64_t n_hap_exc;
     const int64_t* hap_exc_pos;
     const uint8_t* hap_exc_chr;
+
+    /* Packed qualities (ABI 5; zero = one byte per base).  qual_bits = 4 or 6: read_qual holds qual_bits-bit codes into
+     * qual_table, the code of base i of the read pool at bit i * qual_bits of the byte stream (bit b = bit b & 7 of byte
+     * b >> 3).  Base qualities take few distinct values - at most 42 with Illumina's scale, a handful with binned
+     * qualities - so this is lossless whenever a batch has <= 64 (<= 16) of them; plb_pack_quals_host builds table and
+     * codes, or reports that the batch has to stay at 8 bits.  Offsets are unchanged (they count bases); results are
+     * bit-identical: the bytes are restored on the GPU before anything reads them. */
+    int32_t qual_bits;
+    uint8_t qual_table[64];
 } PlbWindowBatch;
 
 #define PLB_SEQ_ASCII 0
@@ -275,6 +284,13 @@ int plb_pack_bases_host(const uint8_t* src, int64_t n, uint8_t* dst, int64_t dst
 int plb_pack_nibbles_host(const uint8_t* bam_seq, int64_t n, uint8_t* dst, int64_t dst_base,
                           int64_t* exc_pos, uint8_t* exc_chr, int64_t exc_cap, int64_t* n_exc);
 
+/*
+ * Packs n raw base qualities into 4- or 6-bit codes (see PlbWindowBatch.qual_bits): qual_table receives the distinct
+ * values in ascending order, *qual_bits 4 when there are <= 16 of them, 6 when <= 64; dst needs (n * 6 + 7) / 8 + 4 bytes.
+ * More than 64 distinct values, or a value above 93: PLB_ERR_SHAPE and nothing is written (send the bytes as they are).
+ */
+int plb_pack_quals_host(const uint8_t* src, int64_t n, uint8_t* dst, int32_t* qual_bits, uint8_t* qual_table);
+
 /* -- S2: per-read scoring seam ----------------------------------------------------- */
 
 /*
@@ -306,7 +322,8 @@ int plb_population_run_host(PlbContext* ctx, const PlbWindowBatch* host_batch,
  * submit returns PLB_ERR_ARG.  Input and output buffers must stay valid and untouched until the job has been waited
  * for; they should be pinned (cudaHostAlloc / cudaHostRegister), pageable buffers make the copies synchronous.  Jobs
  * complete in submission order.  plb_population_run_host == submit + wait.  `host_out` may be NULL (per-read outputs
- * only: the S2 call).
+ * only: the S2 call).  Any OUTPUT pointer may also be a device pointer of the context's GPU (unified addressing): that
+ * block then stays in HBM - e.g. the genotype likelihoods a multi-GPU caller all-gathers next.
  */
 #define PLB_MAX_JOBS 2
 typedef struct PlbJob PlbJob;

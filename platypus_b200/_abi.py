@@ -42,7 +42,8 @@ class PlbWindowBatch(C.Structure):
                 ("read_mapq", _p), ("read_qcfail", _p),
                 ("max_variants", C.c_int32), ("win_n_var", _p), ("hap_var_mask", _p), ("var_prior", _p),
                 ("seq_format", C.c_int32), ("n_read_exc", C.c_int64), ("read_exc_pos", _p), ("read_exc_chr", _p),
-                ("n_hap_exc", C.c_int64), ("hap_exc_pos", _p), ("hap_exc_chr", _p)]
+                ("n_hap_exc", C.c_int64), ("hap_exc_pos", _p), ("hap_exc_chr", _p),
+                ("qual_bits", C.c_int32), ("qual_table", C.c_uint8 * 64)]
 
 
 class PlbLoglikOut(C.Structure):
@@ -171,6 +172,8 @@ def declare(lib):
     lib.plb_pack_bases_host.restype = C.c_int
     lib.plb_pack_nibbles_host.argtypes = [_p, C.c_int64, _p, C.c_int64, _p, _p, C.c_int64, P(C.c_int64)]
     lib.plb_pack_nibbles_host.restype = C.c_int
+    lib.plb_pack_quals_host.argtypes = [_p, C.c_int64, _p, P(C.c_int32), _p]
+    lib.plb_pack_quals_host.restype = C.c_int
     lib.plb_stage_reads_host.argtypes = [P(PlbBamRecords), P(PlbReadFilterOptions), P(PlbStagedReads)]
     lib.plb_stage_reads_host.restype = C.c_int
     lib.plb_window_slices_host.argtypes = [C.c_int32, _p, _p, C.c_int32, _p, _p, _p, _p]
@@ -216,7 +219,7 @@ EXPORTED_SYMBOLS = [
     "plb_window_loglik_host", "plb_population_run_host", "plb_site_genotypes_host", "plb_batch_upload", "plb_batch_free",
     "plb_run_device", "plb_last_stats", "plb_set_timing", "plb_kernel_times",
     "plb_build_haplotypes_host", "plb_select_haplotypes_host", "plb_select_replay_host", "plb_best_score_haplotypes_host",
-    "plb_select_stats", "plb_population_submit", "plb_population_wait", "plb_pack_bases_host", "plb_pack_nibbles_host",
+    "plb_select_stats", "plb_population_submit", "plb_population_wait", "plb_pack_bases_host", "plb_pack_nibbles_host", "plb_pack_quals_host",
     "plb_stage_reads_host", "plb_window_slices_host", "plb_batch_download", "plb_synth_fill_device",
 ]
 KERNEL_NAMES = ["k_prep", "k_anchor", "k_general", "k_dp", "k_genotype", "k_population"]

@@ -74,6 +74,9 @@ class WindowBatch:
     read_exc_chr: Optional[np.ndarray] = None
     hap_exc_pos: Optional[np.ndarray] = None
     hap_exc_chr: Optional[np.ndarray] = None
+    # packed qualities (PlbWindowBatch.qual_bits): read_qual then holds 4- or 6-bit codes into qual_table
+    qual_bits: int = 0
+    qual_table: Optional[np.ndarray] = None
     _keep: list = field(default_factory=list, repr=False)
 
     # ---- construction -------------------------------------------------------------------
@@ -188,14 +191,14 @@ class WindowBatch:
         """(haplotype bases, read bases) of the batch, whatever the sequence format."""
         return int(self.hap_seq_off[-1]), int(self.read_seq_off[-1])
 
-    def pack(self, lib=None) -> "WindowBatch":
-        """The same batch with 2-bit packed bases (PLB_SEQ_2BIT): what the staging step hands to the GPU instead of
-        ASCII (BAM's 4-bit nibbles pack straight into it, htslibWrapper.pyx:414-416).  Packing is done
-        by the library's host helper plb_pack_bases_host; no GPU work."""
+    def pack(self, lib=None, quals=True) -> "WindowBatch":
+        """The same batch with 2-bit packed bases (PLB_SEQ_2BIT) and, with `quals`, 4- / 6-bit packed qualities: what
+        the staging step hands to the GPU instead of ASCII (BAM's 4-bit nibbles pack straight into it,
+        htslibWrapper.pyx:414-416).  Packing is done by the library's host helpers; no GPU work."""
         import ctypes as C
         import dataclasses
         if self.seq_format == _abi.PLB_SEQ_2BIT:
-            return self
+            return self.pack_quals(lib) if quals else self
         if lib is None:
             from .engine import load_library
             lib = load_library()
@@ -213,8 +216,31 @@ class WindowBatch:
         nh, nr = self.n_bases()
         hs, hp, hc = pack(self.hap_seq, nh)
         rs, rp, rc_ = pack(self.read_seq, nr)
-        return dataclasses.replace(self, hap_seq=hs, read_seq=rs, seq_format=_abi.PLB_SEQ_2BIT, read_exc_pos=rp,
-                                   read_exc_chr=rc_, hap_exc_pos=hp, hap_exc_chr=hc, _keep=[])
+        out = dataclasses.replace(self, hap_seq=hs, read_seq=rs, seq_format=_abi.PLB_SEQ_2BIT, read_exc_pos=rp,
+                                  read_exc_chr=rc_, hap_exc_pos=hp, hap_exc_chr=hc, _keep=[])
+        return out.pack_quals(lib) if quals else out
+
+    def pack_quals(self, lib=None) -> "WindowBatch":
+        """The same batch with the base qualities as 4- or 6-bit codes into a table of the batch's distinct values
+        (plb_pack_quals_host; lossless).  A batch with more than 64 distinct qualities is returned unchanged."""
+        import ctypes as C
+        import dataclasses
+        if self.qual_bits:
+            return self
+        if lib is None:
+            from .engine import load_library
+            lib = load_library()
+        nr = int(self.read_seq_off[-1])
+        src = np.ascontiguousarray(self.read_qual[:nr], np.uint8)
+        dst = np.zeros((nr * 6 + 7) // 8 + 8, np.uint8)
+        table, bits = np.zeros(64, np.uint8), C.c_int32(0)
+        rc = lib.plb_pack_quals_host(_abi.ptr(src), nr, _abi.ptr(dst), C.byref(bits), _abi.ptr(table))
+        if rc == _abi.PLB_ERR_SHAPE:
+            return self
+        if rc:
+            raise RuntimeError("plb_pack_quals_host failed: %s" % lib.plb_last_error().decode())
+        return dataclasses.replace(self, read_qual=dst[:(nr * bits.value + 7) // 8 + 4].copy(), qual_bits=bits.value, qual_table=table,
+                                   _keep=[])
 
     # ---- ABI ----------------------------------------------------------------------------
     def as_struct(self):
@@ -239,6 +265,10 @@ class WindowBatch:
             setattr(s, name, _abi.ptr(c(getattr(self, name), dt)))
         s.max_variants = int(self.max_variants)
         s.seq_format = int(self.seq_format)
+        s.qual_bits = int(self.qual_bits)
+        if self.qual_bits:
+            C_ = __import__("ctypes")
+            C_.memmove(s.qual_table, np.ascontiguousarray(self.qual_table, np.uint8).ctypes.data, 64)
         if self.seq_format:
             s.n_read_exc = 0 if self.read_exc_pos is None else len(self.read_exc_pos)
             s.n_hap_exc = 0 if self.hap_exc_pos is None else len(self.hap_exc_pos)
@@ -252,7 +282,7 @@ class WindowBatch:
         """Sub-batch with windows [lo, hi); the read pool is re-indexed to the reads the
         shard touches (reads straddling a shard boundary are duplicated into both shards, as
         the reference duplicates them across regions)."""
-        assert self.seq_format == 0, "slice the ASCII batch, then pack()"
+        assert self.seq_format == 0 and self.qual_bits == 0, "slice the ASCII batch, then pack()"
         nI = self.n_individuals
         h0, h1 = int(self.win_hap_off[lo]), int(self.win_hap_off[hi])
         s0, s1 = int(self.wi_slot_off[lo * nI]), int(self.wi_slot_off[hi * nI])

@@ -160,6 +160,9 @@ struct PlbDeviceBatch {
     int64_t* d_hap_exc_pos = nullptr;
     uint8_t* d_hap_exc_chr = nullptr;
     bool exc_uploaded = false;
+    int qual_bits = 0;                 // packed qualities: codes land in pk_qual, k_unpack_qual restores d.read_qual
+    uint8_t* pk_qual = nullptr;
+    QualTable qtab{};
     struct Fresh { int which; int64_t lo, hi; };          // base interval just uploaded: 0 = haplotypes, 1 = reads
     std::vector<Fresh> fresh[kMaxChunks + 1];             // per chunk of the host path ([0] for whole-batch uploads)
 };
@@ -377,6 +380,9 @@ static int validate_batch(const PlbWindowBatch* b, const PlbOptions* opt, int32_
     if (b->max_variants > 64) return set_err(PLB_ERR_SHAPE, "max_variants %d > 64", b->max_variants);
     if (b->seq_format != PLB_SEQ_ASCII && b->seq_format != PLB_SEQ_2BIT)
         return set_err(PLB_ERR_ARG, "seq_format %d unknown", b->seq_format);
+    if (b->qual_bits != 0 && b->qual_bits != 4 && b->qual_bits != 6) return set_err(PLB_ERR_ARG, "qual_bits %d: must be 0, 4 or 6", b->qual_bits);
+    for (int i = 0; i < (b->qual_bits ? 1 << b->qual_bits : 0); ++i)
+        if (b->qual_table[i] > 93) return set_err(PLB_ERR_ARG, "qual_table[%d] = %d > 93", i, b->qual_table[i]);
     if (b->seq_format == PLB_SEQ_2BIT) {
         if (b->n_read_exc < 0 || b->n_hap_exc < 0 || (b->n_read_exc > 0 && (!b->read_exc_pos || !b->read_exc_chr)) ||
             (b->n_hap_exc > 0 && (!b->hap_exc_pos || !b->hap_exc_chr)))
@@ -463,7 +469,7 @@ static int validate_batch(const PlbWindowBatch* b, const PlbOptions* opt, int32_
         }
     }
     if (bad_code != PLB_OK) return set_err(bad_code, "%s", bad_msg);
-    if (bytes) {
+    if (bytes && b->qual_bits == 0) {   // packed qualities: the table was checked above
         const int64_t nb = b->n_reads ? b->read_seq_off[b->n_reads] : 0;
         int64_t bad = -1;
 #pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(max : bad) if (nb > (1 << 20))
@@ -762,6 +768,14 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
     db->packed = packed;
     db->n_read_exc = packed ? hb->n_read_exc : 0;
     db->n_hap_exc = packed ? hb->n_hap_exc : 0;
+    const int qbits = hb->qual_bits;
+    if (qbits && share) {
+        delete db;
+        return set_err(PLB_ERR_UNSUPPORTED, "packed batches are not taken by the selection rounds");
+    }
+    db->qual_bits = qbits;
+    if (qbits) memcpy(db->qtab.v, hb->qual_table, 64);
+    const size_t o_pk_qual = L.take(qbits ? (size_t)(read_bytes * qbits + 7) / 8 + 64 : 0);
     const size_t o_pk_hap = L.take(packed ? (size_t)(hap_bytes + 3) / 4 + 64 : 0),
                  o_pk_read = L.take(packed ? (size_t)(read_bytes + 3) / 4 + 64 : 0),
                  o_rexc_pos = L.take((size_t)db->n_read_exc * 8), o_rexc_chr = L.take((size_t)db->n_read_exc),
@@ -833,6 +847,7 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
     db->q3.cap = qcap;
     db->ll_scratch = at<double>(B, o_ll);
     db->em_scratch = at<double>(B, o_em);
+    if (qbits) db->pk_qual = at<uint8_t>(B, o_pk_qual);
     if (packed) {
         db->pk_hap = at<uint8_t>(B, o_pk_hap);
         db->pk_read = at<uint8_t>(B, o_pk_read);
@@ -1113,15 +1128,16 @@ static int copy_meta(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* hb
     return PLB_OK;
 }
 
-// Copies the parts of [lo, hi) of a base array that are not on the device yet; `done` is the interval already uploaded
-// (kept as one interval: a gap between intervals is simply filled).  shift = 2 for 2-bit packed arrays (4 bases per
-// byte; boundary bytes are simply sent again).  The base intervals sent are appended to `fresh`.
+// Copies the parts of [lo, hi) of a per-base array that are not on the device yet; `done` is the interval already
+// uploaded (kept as one interval: a gap between intervals is simply filled).  bits = size of an element in the array as
+// it travels: 8 (bytes), 2 (packed bases), 4 / 6 (packed qualities); boundary bytes are simply sent again.  The element
+// intervals sent are appended to `fresh`.
 static int copy_bytes(uint8_t* dst, const uint8_t* src, int64_t lo, int64_t hi, int64_t done[2], cudaStream_t st,
-                      int shift = 0, int which = 0, std::vector<PlbDeviceBatch::Fresh>* fresh = nullptr) {
+                      int bits = 8, int which = 0, std::vector<PlbDeviceBatch::Fresh>* fresh = nullptr) {
     if (hi <= lo) return PLB_OK;
     auto send = [&](int64_t a, int64_t b) -> cudaError_t {
         if (fresh) fresh->push_back({which, a, b});
-        const int64_t b0 = a >> shift, b1 = (b + ((int64_t)1 << shift) - 1) >> shift;
+        const int64_t b0 = a * bits / 8, b1 = (b * bits + 7) / 8;
         return cudaMemcpyAsync(dst + b0, src + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st);
     };
     if (done[1] <= done[0]) {
@@ -1168,7 +1184,11 @@ static int copy_seq_for_windows(PlbContext* c, PlbDeviceBatch* db, const PlbWind
         if ((rc = copy_bytes((uint8_t*)db->d.hap_seq, hb->hap_seq, r.hap0, r.hap1, db->hap_done, st))) return rc;
         if ((rc = copy_bytes((uint8_t*)db->d.read_seq, hb->read_seq, r.read0, r.read1, db->read_done, st))) return rc;
     }
-    if ((rc = copy_bytes((uint8_t*)db->d.read_qual, hb->read_qual, r.read0, r.read1, qdone, st))) return rc;
+    if (db->qual_bits) {
+        if ((rc = copy_bytes(db->pk_qual, hb->read_qual, r.read0, r.read1, qdone, st, db->qual_bits, 2, &db->fresh[chunk]))) return rc;
+    } else {
+        if ((rc = copy_bytes((uint8_t*)db->d.read_qual, hb->read_qual, r.read0, r.read1, qdone, st))) return rc;
+    }
     return PLB_OK;
 }
 
@@ -1191,6 +1211,27 @@ __global__ void __launch_bounds__(256) k_unpack2(const uint8_t* __restrict__ pk,
             if (base + k >= b0 && base + k < b1) dst[base + k] = (uint8_t)(v >> (8 * k));
     }
 }
+// Packed qualities -> bytes: code i at bit i * BITS of the stream, value = table[code].  One thread per group of four
+// qualities (3 bytes at 6 bits, 2 bytes at 4 bits); like k_unpack2 it writes only elements b0 <= i < b1.
+template <int BITS>
+__global__ void __launch_bounds__(256) k_unpack_qual(const uint8_t* __restrict__ pk, uint8_t* __restrict__ dst, int64_t b0,
+                                                     int64_t b1, QualTable tab) {
+    const int64_t g = (b0 >> 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t base = g << 2;
+    if (base >= b1) return;
+    const uint8_t* p = pk + g * (BITS / 2);                     // 4 * BITS / 8 bytes per group
+    u32 v = (u32)p[0] | ((u32)p[1] << 8);
+    if (BITS == 6) v |= (u32)p[2] << 16;
+    u32 out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out |= (u32)tab.v[(v >> (BITS * k)) & ((1u << BITS) - 1u)] << (8 * k);
+    if (base >= b0 && base + 4 <= b1) {
+        *(u32*)(dst + base) = out;
+    } else {
+        for (int k = 0; k < 4; ++k)
+            if (base + k >= b0 && base + k < b1) dst[base + k] = (uint8_t)(out >> (8 * k));
+    }
+}
 // ... then the bases that are not A/C/G/T get their original byte back
 __global__ void __launch_bounds__(256) k_patch_exceptions(const int64_t* __restrict__ pos, const uint8_t* __restrict__ chr,
                                                           int64_t n, uint8_t* __restrict__ dst, int64_t b0, int64_t b1) {
@@ -1205,9 +1246,19 @@ static int launch_check(PlbContext* c, const char* what);
 
 // Restores the ASCII arrays of the base intervals that `chunk`'s copies brought in (packed batches; no-op otherwise).
 static int unpack_fresh(PlbContext* c, PlbDeviceBatch* db, int chunk, cudaStream_t st) {
-    if (!db->packed) return PLB_OK;
+    if (!db->packed && !db->qual_bits) return PLB_OK;
     int rc;
     for (const auto& f : db->fresh[chunk]) {
+        if (f.which == 2) {   // qualities
+            const int64_t ng = ((f.hi + 3) >> 2) - (f.lo >> 2);
+            if (ng <= 0) continue;
+            if (db->qual_bits == 6)
+                k_unpack_qual<6><<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(db->pk_qual, (uint8_t*)db->d.read_qual, f.lo, f.hi, db->qtab);
+            else
+                k_unpack_qual<4><<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(db->pk_qual, (uint8_t*)db->d.read_qual, f.lo, f.hi, db->qtab);
+            if ((rc = launch_check(c, "k_unpack_qual"))) return rc;
+            continue;
+        }
         const uint8_t* pk = f.which ? db->pk_read : db->pk_hap;
         uint8_t* dst = (uint8_t*)(f.which ? db->d.read_seq : db->d.hap_seq);
         const int64_t nq = ((f.hi + 3) >> 2) - (f.lo >> 2);
@@ -1646,7 +1697,7 @@ static int submit_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions
     cudaError_t e = cudaSuccess;
     auto d2h = [&](void* dst, const void* src, size_t off, size_t bytes) {
         if (rc == PLB_OK && e == cudaSuccess && dst && src && bytes)
-            e = cudaMemcpyAsync((uint8_t*)dst + off, (const uint8_t*)src + off, bytes, cudaMemcpyDeviceToHost, kst);
+            e = cudaMemcpyAsync((uint8_t*)dst + off, (const uint8_t*)src + off, bytes, cudaMemcpyDefault, kst);   // dst: host or device
     };
     // Chunking.  A lone call wants its first kernels early: up to six chunks whose sizes grow x1.3.  When another job
     // is still computing, this job's bytes travel behind that job's kernels anyway, so it is cut into few chunks (each
@@ -1713,7 +1764,7 @@ static int submit_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions
         if ((rc = plan_chunk(c, db, hb, w0, w1, kst, true))) break;
         e = cudaStreamWaitEvent(kst, js.ev_chunk[1 + k], 0);
         if (e != cudaSuccess) break;
-        if (db->packed) {
+        if (db->packed || db->qual_bits) {
             // reads are shared between chunks: chunk k may score reads that chunk k-1's copies brought in, so its
             // kernels also wait for that chunk's unpacking (which waited for the one before it)
             if (k > 0) e = cudaStreamWaitEvent(kst, js.ev_unpack[k - 1], 0);
@@ -1893,6 +1944,47 @@ int pack_2bit(Get get, int64_t n, uint8_t* dst, int64_t dst_base, int64_t* exc_p
     return PLB_OK;
 }
 }  // namespace
+
+extern "C" int plb_pack_quals_host(const uint8_t* src, int64_t n, uint8_t* dst, int32_t* qual_bits, uint8_t* qual_table) {
+    if (n < 0 || (n > 0 && !src) || !dst || !qual_bits || !qual_table) return set_err(PLB_ERR_ARG, "NULL / bad argument");
+    // distinct values (a histogram per thread, then merged)
+    const int nt = n >= (1 << 20) ? host_threads() : 1;
+    std::vector<uint8_t> seen((size_t)nt * 256, 0);
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (nt > 1)
+    for (int t = 0; t < nt; ++t) {
+        uint8_t* sn = seen.data() + (size_t)t * 256;
+        const int64_t a = n * t / nt, b = n * (t + 1) / nt;
+        for (int64_t i = a; i < b; ++i) sn[src[i]] = 1;
+    }
+    uint8_t code[256];
+    int nd = 0;
+    for (int v = 0; v < 256; ++v) {
+        bool any = false;
+        for (int t = 0; t < nt; ++t) any |= seen[(size_t)t * 256 + v] != 0;
+        if (!any) continue;
+        if (v > 93) return set_err(PLB_ERR_SHAPE, "base quality %d > 93", v);
+        if (nd == 64) return set_err(PLB_ERR_SHAPE, "more than 64 distinct base qualities: the batch stays at 8 bits");
+        code[v] = (uint8_t)nd;
+        qual_table[nd++] = (uint8_t)v;
+    }
+    for (int i = nd; i < 64; ++i) qual_table[i] = 0;
+    const int bits = nd <= 16 ? 4 : 6;
+    *qual_bits = bits;
+    const int64_t ng = (n + 3) / 4;   // groups of four qualities = bits / 2 bytes each
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (ng > (1 << 18))
+    for (int64_t g = 0; g < ng; ++g) {
+        uint32_t v = 0;
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = 4 * g + k;
+            if (i < n) v |= (uint32_t)code[src[i]] << (bits * k);
+        }
+        uint8_t* p = dst + g * (bits / 2);
+        p[0] = (uint8_t)v;
+        p[1] = (uint8_t)(v >> 8);
+        if (bits == 6) p[2] = (uint8_t)(v >> 16);
+    }
+    return PLB_OK;
+}
 
 extern "C" int plb_pack_bases_host(const uint8_t* src, int64_t n, uint8_t* dst, int64_t dst_base, int64_t* exc_pos,
                                    uint8_t* exc_chr, int64_t exc_cap, int64_t* n_exc) {

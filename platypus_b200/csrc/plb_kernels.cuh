@@ -68,6 +68,10 @@ struct DevBatch {
     int32_t* score;            // [n_pairs] running min over general-path alignments
 };
 
+struct QualTable {   // value of every packed quality code (PlbWindowBatch.qual_table), passed to kernels by value
+    uint8_t v[64];
+};
+
 struct Tile {
     int32_t w;        // window
     int32_t h0, h1;   // haplotype range (global indices)

@@ -1095,7 +1095,7 @@ extern "C" int plb_select_haplotypes_host(PlbContext* c, const PlbWindowBatch* r
     int rc = check_options(opt_in);
     if (rc) return rc;
     if ((rc = require_idle(c, "plb_select_haplotypes_host"))) return rc;
-    if (rb && rb->seq_format != PLB_SEQ_ASCII)
+    if (rb && (rb->seq_format != PLB_SEQ_ASCII || rb->qual_bits != 0))
         return set_err(PLB_ERR_UNSUPPORTED, "plb_select_haplotypes_host samples the reads on the host: it takes ASCII batches only");
     PlbOptions opt = *opt_in;
     opt.use_mapq_cap = 0;   // alignSingleRead(read, False), variantFilter.pyx:274-275

@@ -187,7 +187,7 @@ extern "C" int plb_synth_fill_device(PlbContext* c, PlbDeviceBatch* db, uint64_t
     if (rc) return rc;
     const DevBatch& d = db->d;
     if (d.n_windows == 0) return PLB_OK;
-    if (db->packed || db->shares_reads) return set_err(PLB_ERR_UNSUPPORTED, "plb_synth_fill_device needs an ASCII batch that owns its reads");
+    if (db->packed || db->qual_bits || db->shares_reads) return set_err(PLB_ERR_UNSUPPORTED, "plb_synth_fill_device needs an ASCII batch that owns its reads");
     if (d.n_slots != d.n_reads) return set_err(PLB_ERR_ARG, "plb_synth_fill_device: slot s must be read s (one slot per pool read)");
     if (db->have_var && d.max_variants < 2 * (db->max_haps - 1))
         return set_err(PLB_ERR_SHAPE, "plb_synth_fill_device: max_variants %d < 2 * (haplotypes - 1)", d.max_variants);
@@ -216,7 +216,7 @@ extern "C" int plb_batch_download(PlbContext* c, PlbDeviceBatch* db, PlbWindowBa
     if (!c || !db || !hb) return set_err(PLB_ERR_ARG, "NULL argument");
     const DevBatch& d = db->d;
     if (hb->n_windows != d.n_windows || hb->n_haps != d.n_haps || hb->n_reads != d.n_reads || hb->n_slots != d.n_slots ||
-        hb->seq_format != PLB_SEQ_ASCII)
+        hb->seq_format != PLB_SEQ_ASCII || hb->qual_bits != 0)
         return set_err(PLB_ERR_ARG, "plb_batch_download: the host batch must have the shape of the resident one (ASCII)");
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;

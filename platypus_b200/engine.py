@@ -215,7 +215,16 @@ class Engine:
                 "var_phred": np.zeros((W, V)), "em_iters": np.zeros(W, np.int32)}
 
     @staticmethod
-    def _pop_struct(arrs, ptr_of=_abi.ptr):
+    def _any_ptr(a):
+        """Pointer of a numpy array (host) or of anything with data_ptr() (a torch tensor, host or device)."""
+        if a is not None and not isinstance(a, np.ndarray) and hasattr(a, "data_ptr"):
+            assert a.is_contiguous()
+            return a.data_ptr()
+        return _abi.ptr(a)
+
+    @staticmethod
+    def _pop_struct(arrs, ptr_of=None):
+        ptr_of = ptr_of or Engine._any_ptr
         o = _abi.PlbPopulationOut()
         o.max_haps = arrs["max_haps"]
         for k in ("gl", "gl_log_max", "gof", "hap_like", "freq", "em_post", "call", "var_phred", "em_iters"):

@@ -718,14 +718,18 @@ def test_packed_input_is_bit_identical(engine, mode):
     """PLB_SEQ_2BIT batches (2-bit bases + exception lists, the staging format of row N3) give the very same bytes out as
     the ASCII call: edge batches (N, IUPAC, lower case -> exceptions), ragged synth windows, every run-time mode."""
     opt = _abi.PlbOptions.default(**mode)
-    for b in (cases.edge_batch(seed=5), cases.edge_batch(seed=2),
-              synth.make_batch(1500, read_len_range=(100, 250), hap_len_range=(200, 500)), synth.make_batch(3000)):
-        p = b.pack()
-        assert p.input_nbytes() < b.input_nbytes()
+    binned = synth.make_batch(1200)
+    binned.read_qual = np.array([2, 12, 23, 37], np.uint8)[binned.read_qual % 4]       # four quality bins: 4-bit codes
+    for b, qbits in ((cases.edge_batch(seed=5), None), (cases.edge_batch(seed=2), None), (binned, 4),
+                     (synth.make_batch(1500, read_len_range=(100, 250), hap_len_range=(200, 500)), 6), (synth.make_batch(3000), 6)):
         a = engine.population_run(b, opt=opt, want_ll=True)
-        c = engine.population_run(p, opt=opt, want_ll=True)
-        for k in ("score", "ll", "gl", "gl_log_max", "gof", "hap_like", "freq", "em_post", "call", "var_phred", "em_iters"):
-            assert np.array_equal(a[k], c[k]), k
+        for p in (b.pack(), b.pack(quals=False), b.pack_quals()):
+            assert p.input_nbytes() < b.input_nbytes() or p.qual_bits == 0
+            assert qbits is None or p.qual_bits in (0, qbits)
+            c = engine.population_run(p, opt=opt, want_ll=True)
+            for k in ("score", "ll", "gl", "gl_log_max", "gof", "hap_like", "freq", "em_post", "call", "var_phred", "em_iters"):
+                assert np.array_equal(a[k], c[k]), k
+        assert qbits is None or b.pack().qual_bits == qbits
     # the device-resident path takes packed batches too
     b = cases.edge_batch(seed=3)
     want = engine.population_run(b, opt=opt)

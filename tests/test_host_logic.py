@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_abi.EXPORTED_SYMBOLS), declared ^ set(_abi.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.plb_abi_version() == 4
+    assert lib.plb_abi_version() == 5
 
 
 def test_no_gpu_fails_loudly():
@@ -375,3 +375,37 @@ def test_validate_skips_unscored_reads():
     assert lib.plb_validate(C.byref(ok.as_struct()), C.byref(opt), 0) == 0
     bad = WindowBatch.from_windows([Window(100, 140, 50, [hap], [([], [], [far])])], 1)
     assert lib.plb_validate(C.byref(bad.as_struct()), C.byref(opt), 0) == _abi.PLB_ERR_SHAPE
+
+
+def test_pack_quals_roundtrip_and_limits():
+    """plb_pack_quals_host: 4 bits for <= 16 distinct qualities, 6 bits for <= 64, refused beyond (the batch stays at 8 bits);
+    codes decode back to the bytes; WindowBatch.pack() carries table and width into the struct."""
+    lib = _lib()
+    rng = np.random.default_rng(3)
+    for n, vals, want_bits in ((1, [30], 4), (1003, [2, 12, 23, 37], 4), (5 << 18, list(range(2, 41)), 6), (777, list(range(0, 64)), 6)):
+        src = np.array(vals, np.uint8)[rng.integers(0, len(vals), n)]
+        src[:len(vals)] = vals[:n]
+        dst = np.zeros((n * 6 + 7) // 8 + 8, np.uint8)
+        tab, bits = np.zeros(64, np.uint8), C.c_int32(0)
+        assert lib.plb_pack_quals_host(src.ctypes.data, n, dst.ctypes.data, C.byref(bits), tab.ctypes.data) == 0
+        assert bits.value == want_bits and list(tab[:len(set(src.tolist()))]) == sorted(set(src.tolist()))
+        i = np.arange(n, dtype=np.int64)
+        bit = i * bits.value
+        word = dst[bit >> 3].astype(np.uint32) | (dst[(bit >> 3) + 1].astype(np.uint32) << 8)
+        back = tab[(word >> (bit & 7).astype(np.uint32)) & ((1 << bits.value) - 1)]
+        assert np.array_equal(back, src)
+    too_many = np.arange(70, dtype=np.uint8)
+    assert lib.plb_pack_quals_host(too_many.ctypes.data, 70, np.zeros(80, np.uint8).ctypes.data, C.byref(C.c_int32()),
+                                   np.zeros(64, np.uint8).ctypes.data) == _abi.PLB_ERR_SHAPE
+    bad = np.array([10, 94], np.uint8)
+    assert lib.plb_pack_quals_host(bad.ctypes.data, 2, np.zeros(16, np.uint8).ctypes.data, C.byref(C.c_int32()),
+                                   np.zeros(64, np.uint8).ctypes.data) == _abi.PLB_ERR_SHAPE
+    b = synth.make_batch(3)
+    p = b.pack(lib)
+    assert p.qual_bits == 6 and p.seq_format == _abi.PLB_SEQ_2BIT and p.input_nbytes() < 0.6 * b.input_nbytes()
+    s = p.as_struct()
+    assert s.qual_bits == 6 and list(s.qual_table[:3]) == list(p.qual_table[:3])
+    assert lib.plb_validate(C.byref(s), None, 0) == 0
+    s.qual_bits = 5
+    assert lib.plb_validate(C.byref(s), None, 0) == _abi.PLB_ERR_ARG
+    assert b.pack(lib, quals=False).qual_bits == 0
