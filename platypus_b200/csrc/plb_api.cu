@@ -124,6 +124,7 @@ struct TileLists {
 struct ChunkPlan {
     int w0 = 0, w1 = 0;
     int h0 = 0, h1 = 0;   // haplotype range of the chunk
+    int r0 = 0, r1 = 0;   // read-index hull of the chunk's slots (k_read_check)
     AnchorPlan ap{};
     DpPlan dp{};
     size_t a_smem = 0, d_smem = 0;
@@ -782,6 +783,7 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
                  o_hexc_pos = L.take((size_t)db->n_hap_exc * 8), o_hexc_chr = L.take((size_t)db->n_hap_exc);
     const size_t o_slot_wi = L.take(own * n_slots * 4), o_hap_win = L.take((size_t)n_haps * 4),
                  o_ll_off = L.take((size_t)(nwi + 1) * 8);
+    const size_t o_rflags = L.take(own * ((size_t)n_reads + 64));
     const size_t o_gap = L.take((size_t)hap_bytes + n_haps + 64), o_wgen = L.take((size_t)W * 4 + 64),
                  o_c0 = L.take((size_t)n_pairs * 4), o_c1 = L.take((size_t)n_pairs * 4),
                  o_score = L.take((size_t)n_pairs * 4);
@@ -836,6 +838,7 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
     d.cand0 = at<int32_t>(B, o_c0);
     d.cand1 = at<int32_t>(B, o_c1);
     d.score = at<int32_t>(B, o_score);
+    d.read_flags = at<uint8_t>(B, o_rflags);
     db->q.e = at<QueueEntry>(B, o_q);
     db->q.count = at<int32_t>(B, o_qcount);
     db->q.cap = qcap;
@@ -873,6 +876,7 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
         d.read_mapq = s.read_mapq;
         d.read_qcfail = s.read_qcfail;
         d.slot_wi = s.slot_wi;
+        d.read_flags = s.read_flags;
         db->shares_reads = true;
     }
     *out = db;
@@ -899,6 +903,11 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
     ch.w1 = w1;
     ch.h0 = hb->win_hap_off[w0];
     ch.h1 = hb->win_hap_off[w1];
+    {
+        const ByteRanges br = byte_ranges(hb, w0, w1);
+        ch.r0 = br.rmax >= br.rmin ? br.rmin : 0;
+        ch.r1 = br.rmax >= br.rmin ? br.rmax + 1 : 0;
+    }
     int max_read = 0, max_hap = 0, max_H = 0;
     // plan sub-ranges of the chunk on several host threads; their tile lists are concatenated in window order
     // straight into the pinned staging buffer below (no intermediate vector: the lists of a selection call are ~10 MB)
@@ -1211,25 +1220,39 @@ __global__ void __launch_bounds__(256) k_unpack2(const uint8_t* __restrict__ pk,
             if (base + k >= b0 && base + k < b1) dst[base + k] = (uint8_t)(v >> (8 * k));
     }
 }
-// Packed qualities -> bytes: code i at bit i * BITS of the stream, value = table[code].  One thread per group of four
-// qualities (3 bytes at 6 bits, 2 bytes at 4 bits); like k_unpack2 it writes only elements b0 <= i < b1.
+// Packed qualities -> bytes: code i at bit i * BITS of the stream, value = table[code].  One thread per group of sixteen
+// qualities (three 32-bit words at 6 bits, two at 4 bits -> one 16-byte store); the table sits in shared memory (indexing
+// the by-value argument with a per-lane index would serialise in the constant cache).  Like k_unpack2 it writes only
+// elements b0 <= i < b1.
 template <int BITS>
 __global__ void __launch_bounds__(256) k_unpack_qual(const uint8_t* __restrict__ pk, uint8_t* __restrict__ dst, int64_t b0,
                                                      int64_t b1, QualTable tab) {
-    const int64_t g = (b0 >> 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t base = g << 2;
+    __shared__ uint8_t s_tab[64];
+    if (threadIdx.x < 16) ((u32*)s_tab)[threadIdx.x] = ((const u32*)tab.v)[threadIdx.x];
+    __syncthreads();
+    const int64_t g = (b0 >> 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t base = g << 4;
     if (base >= b1) return;
-    const uint8_t* p = pk + g * (BITS / 2);                     // 4 * BITS / 8 bytes per group
-    u32 v = (u32)p[0] | ((u32)p[1] << 8);
-    if (BITS == 6) v |= (u32)p[2] << 16;
-    u32 out = 0;
+    constexpr int NW = BITS / 2;                                 // 16 * BITS / 32 words per group
+    const u32* p = (const u32*)(pk + g * (2 * BITS));            // 16 * BITS / 8 bytes per group: 4-byte aligned
+    u32 w[NW];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) out |= (u32)tab.v[(v >> (BITS * k)) & ((1u << BITS) - 1u)] << (8 * k);
-    if (base >= b0 && base + 4 <= b1) {
-        *(u32*)(dst + base) = out;
+    for (int k = 0; k < NW; ++k) w[k] = p[k];
+    u32 out[4];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int bit = BITS * k, wi = bit >> 5, sh = bit & 31;
+        u32 code = w[wi] >> sh;
+        if (sh + BITS > 32) code |= w[wi + 1] << (32 - sh);
+        const u32 q = s_tab[code & ((1u << BITS) - 1u)];
+        if ((k & 3) == 0) out[k >> 2] = q;
+        else out[k >> 2] |= q << (8 * (k & 3));
+    }
+    if (base >= b0 && base + 16 <= b1) {
+        *(uint4*)(dst + base) = make_uint4(out[0], out[1], out[2], out[3]);
     } else {
-        for (int k = 0; k < 4; ++k)
-            if (base + k >= b0 && base + k < b1) dst[base + k] = (uint8_t)(out >> (8 * k));
+        for (int k = 0; k < 16; ++k)
+            if (base + k >= b0 && base + k < b1) dst[base + k] = (uint8_t)(out[k >> 2] >> (8 * (k & 3)));
     }
 }
 // ... then the bases that are not A/C/G/T get their original byte back
@@ -1250,7 +1273,7 @@ static int unpack_fresh(PlbContext* c, PlbDeviceBatch* db, int chunk, cudaStream
     int rc;
     for (const auto& f : db->fresh[chunk]) {
         if (f.which == 2) {   // qualities
-            const int64_t ng = ((f.hi + 3) >> 2) - (f.lo >> 2);
+            const int64_t ng = ((f.hi + 15) >> 4) - (f.lo >> 4);
             if (ng <= 0) continue;
             if (db->qual_bits == 6)
                 k_unpack_qual<6><<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(db->pk_qual, (uint8_t*)db->d.read_qual, f.lo, f.hi, db->qtab);
@@ -1400,6 +1423,10 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
     if (h1 > h0) {
         k_prep<<<h1 - h0, 128, 0, st>>>(d, h0, sp.ext);
         if ((rc = launch_check(c, "k_prep"))) return rc;
+    }
+    if (ch.r1 > ch.r0) {   // per-read quality sum / range check (inside the k_prep timing slot)
+        k_read_check<<<(unsigned)(((int64_t)(ch.r1 - ch.r0) * 32 + 255) / 256), 256, 0, st>>>(d, ch.r0, ch.r1, c->d_ctr());
+        if ((rc = launch_check(c, "k_read_check"))) return rc;
     }
     mark(1);
     if (ch.ap.n_tiles > 0) {

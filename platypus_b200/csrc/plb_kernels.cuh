@@ -66,6 +66,7 @@ struct DevBatch {
     int32_t* cand0;            // [n_pairs] first / second packed-path start offset, -1 = none
     int32_t* cand1;
     int32_t* score;            // [n_pairs] running min over general-path alignments
+    uint8_t* read_flags;       // [n_reads] k_read_check: bit 1 = qualities add up beyond the packed recurrence's range
 };
 
 struct QualTable {   // value of every packed quality code (PlbWindowBatch.qual_table), passed to kernels by value
@@ -223,7 +224,7 @@ struct AnchorPlan {
     int32_t cnt_words;      // u32 words of one warp's counter array (2 counters per word)
     int32_t n_cnt;          // counter arrays available in shared memory (>= 1)
     // byte offsets of the shared-memory areas (laid out by the host planner, 16-byte aligned)
-    uint32_t o_cnt, o_fb, o_vl, o_rpk, o_hpk, o_next, o_mult, o_heads, o_slot, o_hmeta, smem_bytes;
+    uint32_t o_cnt, o_fb, o_ul, o_vl, o_rpk, o_hpk, o_next, o_mult, o_heads, o_slot, o_hmeta, smem_bytes;
 };
 
 // host + device: lays out the shared memory of k_anchor from the plan's element counts
@@ -232,6 +233,7 @@ inline void anchor_layout(AnchorPlan& ap, size_t slot_bytes) {
     size_t o = kRankTabBytes;   // 7-mer key -> dense id: 512 x {presence bits, rank prefix}
     ap.o_cnt = (uint32_t)o;    o = al(o + (size_t)ap.n_cnt * ap.cnt_words * 4);
     ap.o_fb = (uint32_t)o;     o = al(o + (size_t)ap.max_pairs * 4);
+    ap.o_ul = (uint32_t)o;     o = al(o + (size_t)ap.max_pairs * 4);
     ap.o_vl = (uint32_t)o;     o = al(o + (size_t)ap.max_pairs * 12);
     ap.o_rpk = (uint32_t)o;    o = al(o + (size_t)ap.rpk_words * 4);
     ap.o_hpk = (uint32_t)o;    o = al(o + (size_t)ap.hpk_words * 4);
@@ -389,7 +391,15 @@ __device__ __forceinline__ int unique_hit_offset(const u32* tab, const uint16_t*
     return kNoCand;
 }
 
-__device__ __noinline__ int light_decide(LightArgs a) {
+// The decision runs in two steps so that warps stay full.  Step one - every pair, one thread each - tries the single
+// guess that settles most pairs (the offset implied by the first unique 7-mer of the read).  The pairs it leaves open
+// (votes split by an indel, a first guess on the minority side: about a third of them) are compacted into a list, and
+// step two works through that list with the remaining guesses.  Run as one loop per pair, nearly every warp held a lane
+// that needed three or four guesses and the other lanes idled through them (21 of 32 threads active per instruction).
+//
+// light_first: returns 1 when decided (res[0..2] written), else 0 with res[0] = the guess (or kNoCand) and res[1] = its
+// count, from which light_rest resumes.
+__device__ __noinline__ int light_first(LightArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint16_t* head = (const uint16_t*)(smem + a.head_off);
     const u32* tab = (const u32*)smem;
@@ -401,29 +411,59 @@ __device__ __noinline__ int light_decide(LightArgs a) {
         res[0] = res[1] = res[2] = (u32)kNoCand;
         return 1;
     }
-    // Guesses are generated lazily: read 7-mers near the start, the end, the middle, then the quarters and
-    // eighths (reads that differ from the haplotype by several indels split their votes over several
-    // offsets; each extra exact count is ~100x cheaper than the warp-wide vote array).
+    const int g0 = unique_hit_offset(tab, head, rpk, 0, min(nk, 24), 1);
+    int c0 = 0;
+    if (g0 != kNoCand) {
+        c0 = count_offset_bits(rpk, hpk, nk, a.nk_hap, g0);
+        const int R = a.vub - c0, R2 = a.hh + a.lp - max(0, c0 - a.hh);
+        if (c0 > min(R, R2) && c0 > 0) {
+            res[0] = (u32)(g0 + 1);
+            res[1] = res[2] = (u32)kNoCand;
+            return 1;
+        }
+    }
+    res[0] = (u32)g0;
+    res[1] = (u32)c0;
+    return 0;
+}
+
+__device__ __noinline__ int count_offset_call(u32 rpk_off, u32 hpk_off, int nk_read, int nk_hap, int idx) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    return count_offset_bits((const u32*)(smem + rpk_off), (const u32*)(smem + hpk_off), nk_read, nk_hap, idx);
+}
+
+// The remaining guesses of a pair light_first left open: read 7-mers near the end, the middle, then the quarters and
+// eighths (reads that differ from the haplotype by several indels split their votes over several offsets; each extra
+// exact count is ~100x cheaper than the warp-wide vote array).
+__device__ __noinline__ int light_rest(LightArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint16_t* head = (const uint16_t*)(smem + a.head_off);
+    const u32* tab = (const u32*)smem;
+    const u32* rpk = (const u32*)(smem + a.rpk_off);
+    u32* res = (u32*)(smem + a.res_off);
+    const int nk = a.nk_read;
     const int lim = min(nk, 24);
     constexpr int NG = 7;
     int g[NG], c[NG];
+    g[0] = (int)res[0];
+    c[0] = (int)res[1];
     // Two bounds on the votes of any offset not counted yet:
     //   R  = (all votes the read can cast) - (votes counted so far)
     //   R2 = heavy + (light - light votes counted so far): every read 7-mer gives an offset at most ONE vote,
     //        light 7-mers vote exactly once in total, and a counted offset with c votes holds at least
     //        c - heavy light ones.  R2 is what decides reads over long homopolymers, whose repeated 7-mer
     //        sprays hundreds of votes over neighbouring offsets.
-    int R = a.vub, top = 0, R2 = a.hh + a.lp;
+    int R = a.vub - c[0], top = c[0], R2 = a.hh + a.lp - max(0, c[0] - a.hh);
 #pragma unroll
-    for (int j = 0; j < NG; ++j) {
+    for (int j = 1; j < NG; ++j) {
         int i0, i1, step = 1;
         if (j == 1) {
             i0 = nk - 1;
             i1 = nk - 1 - lim;
             step = -1;
         } else {
-            // j = 0: start; 2: middle; 3, 4: quarters; 5, 6: eighths next to the ends
-            const int num = j == 0 ? 0 : j == 2 ? 4 : j == 3 ? 2 : j == 4 ? 6 : j == 5 ? 1 : 7;
+            // j = 2: middle; 3, 4: quarters; 5, 6: eighths next to the ends
+            const int num = j == 2 ? 4 : j == 3 ? 2 : j == 4 ? 6 : j == 5 ? 1 : 7;
             i0 = (nk * num) >> 3;
             i1 = min(nk, i0 + lim);
         }
@@ -437,7 +477,7 @@ __device__ __noinline__ int light_decide(LightArgs a) {
             if (k < j && g[k] == gj) dup = true;
         if (dup) continue;
         g[j] = gj;
-        c[j] = count_offset_bits(rpk, hpk, nk, a.nk_hap, gj);
+        c[j] = count_offset_call(a.rpk_off, a.hpk_off, nk, a.nk_hap, gj);
         R -= c[j];
         R2 -= max(0, c[j] - a.hh);
         top = max(top, c[j]);
@@ -467,7 +507,8 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
     // address; generic-pointer arithmetic costs an S2R/LEA sequence per use)
     u32* s_tab = (u32*)smem;
     u32* s_cnt = (u32*)(smem + plan.o_cnt);
-    u32* s_fblist = (u32*)(smem + plan.o_fb);
+    u32* s_fblist = (u32*)(smem + plan.o_fb);                 // pairs for the exact vote array
+    u32* s_ulist = (u32*)(smem + plan.o_ul);                  // pairs the first guess left open
     u32* s_vlist = (u32*)(smem + plan.o_vl);                  // per pair: up to three tied-maximum offsets
     u32* s_rpk = (u32*)(smem + plan.o_rpk);                   // 2-bit packed reads
     u32* s_hpk = (u32*)(smem + plan.o_hpk);                   // 2-bit packed haplotypes (padded both sides)
@@ -476,7 +517,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
     uint16_t* s_heads = (uint16_t*)(smem + plan.o_heads);
     SlotInfo* s_slot = (SlotInfo*)(smem + plan.o_slot);
     int32_t* s_hmeta = (int32_t*)(smem + plan.o_hmeta);      // per hap: len, next offset, packed offset
-    __shared__ int s_nid, s_nfb, s_scan[kAnchorThreads / 32];
+    __shared__ int s_nid, s_nfb, s_nul, s_scan[kAnchorThreads / 32];
 
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     unsigned long long st_pairs = 0, st_scored = 0, st_dp = 0, st_cells = 0, t_tile0 = 0;
@@ -516,6 +557,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 poff += ((len + 15) >> 4) + 2 * kPackPadWords;
             }
             s_nfb = 0;
+            s_nul = 0;
         }
         for (int i = tid; i < kRankWords; i += nthr) ((uint2*)s_tab)[i] = make_uint2(0u, 0u);
         // slot metadata + skip rule (chaplotype.pyx:343-361)
@@ -684,9 +726,11 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             const int hloc0 = tile.h0 - b.win_hap_off[w];   // index of the tile's first haplotype in its window
             const int hap_start_w = b.hap_start[w], win_start_w = b.win_start[w];
             // the flank score needs the scalar path for every alignment; HLA mode only for the pairs it clips
+            const float inv_ns = 1.0f / (float)ns;   // p < 4096, ns <= 256: the float quotient is exact after truncation
             auto pair_id = [&](int p, int& s, int& g, int64_t& gs, int64_t& pair) {
-                s = p % ns;
-                g = g0 + p / ns;
+                const int qd = (int)(((float)p + 0.5f) * inv_ns);
+                s = p - qd * ns;
+                g = g0 + qd;
                 gs = tile.s0 + s;
                 pair = s_slot[s].pair0 + (int64_t)(hloc0 + g) * s_slot[s].T;
             };
@@ -731,7 +775,29 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 la.vub = si.vub;
                 la.lp = si.lph & 0xFFFF;
                 la.hh = si.lph >> 16;
-                if (!light_decide(la)) {
+                if (!light_first(la)) s_ulist[atomicAdd(&s_nul, 1)] = (u32)p;
+            }
+            __syncthreads();
+            // ---- step two: the pairs left open, compacted (their order in the list does not matter) ----
+            const int nul = s_nul;
+            for (int k = tid; k < nul; k += nthr) {
+                const int p = (int)s_ulist[k];
+                int s, g;
+                int64_t gs, pair;
+                pair_id(p, s, g, gs, pair);
+                const SlotInfo si = s_slot[s];
+                const PairClip pc = pair_clip(sp, si.pos, si.len, hap_start_w, win_start_w, s_hmeta[3 * g]);
+                LightArgs la;
+                la.head_off = plan.o_heads + 2u * (u32)((g - g0) * hstride);
+                la.rpk_off = plan.o_rpk + 4u * (u32)si.poff;
+                la.hpk_off = plan.o_hpk + 4u * (u32)s_hmeta[3 * g + 2];
+                la.res_off = plan.o_vl + 12u * (u32)p;
+                la.nk_read = pc.L - kKmer;
+                la.nk_hap = s_hmeta[3 * g] - kKmer;
+                la.vub = si.vub;
+                la.lp = si.lph & 0xFFFF;
+                la.hh = si.lph >> 16;
+                if (!light_rest(la)) {
                     s_vlist[3 * p] = (u32)kPairUndecided;
                     s_fblist[atomicAdd(&s_nfb, 1)] = (u32)p;
                 }
@@ -787,7 +853,8 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             const int n_fbw = min(nwarp, plan.n_cnt);  // warps that own a counter array
             for (int f = warp; f < nfb && warp < n_fbw; f += n_fbw) {
                 const int p = (int)s_fblist[f];
-                const int s = p % ns, g = g0 + p / ns;
+                const int qd = (int)(((float)p + 0.5f) * inv_ns);
+                const int s = p - qd * ns, g = g0 + qd;
                 const SlotInfo si = s_slot[s];
                 const int h = tile.h0 + g;
                 const int64_t gs = tile.s0 + s;
@@ -858,7 +925,10 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 __syncwarp();
             }
             __syncthreads();
-            if (tid == 0) s_nfb = 0;
+            if (tid == 0) {
+                s_nfb = 0;
+                s_nul = 0;
+            }
         }
     }
     if (ctr) {  // statistics
@@ -1060,23 +1130,33 @@ struct DpSlot {
     double ll_right; // log(1 - exp(mLTOT*mapq)), chaplotype.pyx:622
 };
 
-// End of a read's profile row (all lanes of the warp): `qs` = the lane's share of the quality sum, with 2^20 added per
-// quality above 93.  The packed int16 recurrences are exact while every path cost stays inside the reference's own range
+// k_read_check: one warp per read of the pool, ONCE per read (a read shared by several windows is scored in several
+// tiles).  The packed int16 recurrences are exact while every path cost stays inside the reference's own range
 // (pos_inf >> 2 = 15,872 phred, align.c:97; a score never exceeds the sum of the read's qualities plus gap costs that the
-// same margin covers); a read whose qualities add up beyond that takes the 32-bit recurrence instead (flag bit 1).
+// margin below covers); a read whose qualities add up beyond that takes the 32-bit recurrence instead (flag bit 1).  A
+// quality above 93 is an input error (the reference asserts it, htslibWrapper.pyx:518-519).
 constexpr int kMaxPackedQualSum = 15871 - 256;
-__device__ __forceinline__ void row_quality_check(int qs, int32_t* flags, int* n_exact, Counters* ctr) {
+__global__ void __launch_bounds__(256) k_read_check(DevBatch b, int r0, int r1, Counters* __restrict__ ctr) {
+    const int r = r0 + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (r >= r1) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t o = b.read_seq_off[r];
+    const int L = (int)(b.read_seq_off[r + 1] - o);
+    const uint8_t* q = b.read_qual + o;
+    int sum = 0, mx = 0;
+    for (int i = lane; i < L; i += 32) {
+        const int v = q[i];
+        sum += v;
+        mx = max(mx, v);
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(0xFFFFFFFFu, qs, o);
-    if ((threadIdx.x & 31) == 0 && qs > kMaxPackedQualSum) {
-        if (qs >= (1 << 20)) {
-            if (ctr) atomicOr(&ctr->err, kErrQuality);
-            qs &= (1 << 20) - 1;
-        }
-        if (qs > kMaxPackedQualSum) {
-            *flags |= 2;
-            *n_exact = 1;
-        }
+    for (int k = 16; k > 0; k >>= 1) {
+        sum += __shfl_xor_sync(0xFFFFFFFFu, sum, k);
+        mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, k));
+    }
+    if (lane == 0) {
+        b.read_flags[r] = sum > kMaxPackedQualSum ? 2 : 0;
+        if (mx > 93 && ctr) atomicOr(&ctr->err, kErrQuality);
     }
 }
 
@@ -1094,7 +1174,7 @@ __global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScorePa
     u32* s_task = (u32*)(s_best + plan.max_pairs);               // compacted tasks
     u32* s_ptab = s_task + 2 * plan.max_pairs;                   // profile word by (base code, quality): [5][128]
     uint8_t* s_code = (uint8_t*)(s_ptab + kProfTabWords);        // byte -> base code 0..3 (exact A/C/G/T) or 4
-    __shared__ int s_ntask, s_nexact;
+    __shared__ int s_ntask;
     __shared__ __align__(8) uint64_t s_bar;   // counts the bytes of the tile's TMA copies
 
     const int tid = threadIdx.x;
@@ -1119,7 +1199,6 @@ __global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScorePa
         const int ns = (int)(tile.s1 - tile.s0);
         if (tid == 0) {
             s_ntask = 0;
-            s_nexact = 0;
             int ro = 0;
             for (int g = 0; g < nh; ++g) {
                 const int h = tile.h0 + g;
@@ -1127,6 +1206,7 @@ __global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScorePa
                 ro += (int)(b.hap_seq_off[h + 1] - b.hap_seq_off[h]) + kRecPad;
             }
         }
+        int my_exact = 0;
         for (int s = tid; s < ns; s += NTHR) {
             const int64_t gs = tile.s0 + s;
             const int r = b.slot_read[gs];
@@ -1140,12 +1220,16 @@ __global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScorePa
                 const int ov = read_overlap(b.win_start[w], b.win_end[w], b.read_pos[r], b.read_end[r]);
                 if (b.read_qcfail[r] || ov < kKmer) ds.flags = 1;
             }
+            if (b.read_flags[r] & 2) {   // qualities beyond the int16 range (k_read_check): exact 32-bit recurrence
+                ds.flags |= 2;
+                my_exact = 1;
+            }
             ds.flags |= (int)b.read_mapq[r] << 8;
             ds.ll_right = log(1.0 - exp(kMLTOT * (double)b.read_mapq[r]));
             ds.poff = 0;
             s_slot[s] = ds;
         }
-        __syncthreads();
+        const int any_exact = __syncthreads_or(my_exact);   // block-uniform
         // Tasks are enumerated slot-major in order of decreasing read length, so that the 32 alignments
         // of a warp have (almost) the same number of steps and the longest ones start first.
         for (int s = tid; s < ns; s += NTHR) {
@@ -1256,13 +1340,11 @@ __global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScorePa
                     const uint8_t* rs = row_end - 2 * NB + (int)(o & 15);
                     const uint8_t* rq = row_end - NB + (int)(o & 15);
                     uint8_t cb[6], qb[6];
-                    int qs = 0;
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
                         const int y = lane + 32 * k;
                         cb[k] = y < ds.len ? rs[y] : (uint8_t)0;
                         qb[k] = y < ds.len ? rq[y] : (uint8_t)0;
-                        qs += qb[k] > 93 ? (1 << 20) : (int)qb[k];
                     }
                     __syncwarp();
 #pragma unroll
@@ -1272,12 +1354,10 @@ __global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScorePa
                             row[y] = y < ds.len ? s_ptab[((u32)s_code[cb[k]] << 7) | (qb[k] & 127u)] : 0u;
                         }
                     }
-                    row_quality_check(qs, &s_slot[s].flags, &s_nexact, ctr);
                     continue;
                 }
                 const uint8_t* rs = b.read_seq + o;
                 const uint8_t* rq = b.read_qual + o;
-                int qs = 0;
                 for (int y0 = 0; y0 < n; y0 += 192) {   // long reads: plain loads, 6 rows per lane
                     uint8_t cb[6], qb[6];
 #pragma unroll
@@ -1285,7 +1365,6 @@ __global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScorePa
                         const int y = y0 + lane + 32 * k;
                         cb[k] = y < ds.len ? rs[y] : (uint8_t)0;
                         qb[k] = y < ds.len ? rq[y] : (uint8_t)0;
-                        qs += qb[k] > 93 ? (1 << 20) : (int)qb[k];
                     }
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
@@ -1295,7 +1374,6 @@ __global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScorePa
                         }
                     }
                 }
-                row_quality_check(qs, &s_slot[s].flags, &s_nexact, ctr);
             }
         }
         // best scores start from what the general path produced; compact packed-path tasks
@@ -1343,7 +1421,7 @@ __global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScorePa
                                 : band_dp_fast(s_prof + ds.poff, s_rec + s_roff[g] + start, ds.len, sp.ext, sp.nuc);
             atomicMin(&s_best[p], v);
         }
-        if (s_nexact) {   // block-uniform (written before the barrier above): the exact 32-bit recurrence, out of line
+        if (any_exact) {   // block-uniform: the exact 32-bit recurrence, out of line
             for (int k = tid; k < ntask; k += NTHR) {
                 const u32 tk = s_task[k];
                 const int p = (int)(tk >> 15), start = (int)(tk & 0x7FFFu);

@@ -50,6 +50,8 @@ PLB_HD int count_offset_bits(const u32* __restrict__ rpk, const u32* __restrict_
         return ~(e | (e >> 1)) & 0x55555555u;
     };
     int c = 0;
+    const u32 mlo = 0xFFFFFFFFu << (2 * (lo - 16 * w0));            // lo - 16 w0 in [0, 15]
+    const u32 mhi = 0xFFFFFFFFu >> (2 * (16 * w1 + 16 - hi));        // 16 w1 + 16 - hi in [0, 15]
     u32 m0 = match_word(w0), m1 = match_word(w0 + 1);
     u32 a0 = m0 & fsr(m0, m1, 2);                 // bases i, i+1
     for (int w = w0; w <= w1; ++w) {
@@ -58,10 +60,9 @@ PLB_HD int count_offset_bits(const u32* __restrict__ rpk, const u32* __restrict_
         const u32 b = a0 & fsr(a0, a1, 4);        // i .. i+3
         const u32 cc = b & fsr(a0, a1, 8);        // i .. i+5
         u32 d = cc & fsr(m0, m1, 12);             // i .. i+6
-        // keep 7-mer starts in [lo, hi)
-        const int base = 16 * w;
-        if (lo > base) d &= 0xFFFFFFFFu << (2 * (lo - base));
-        if (hi < base + 16) d &= 0xFFFFFFFFu >> (2 * (base + 16 - hi));
+        // keep 7-mer starts in [lo, hi): only the first and the last word can hold starts outside it
+        if (w == w0) d &= mlo;
+        if (w == w1) d &= mhi;
         c += popc32(d);
         m0 = m1;
         m1 = m2;
