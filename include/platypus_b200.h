@@ -583,7 +583,7 @@ typedef struct PlbRunStats {
     int64_t n_pairs_scored;
     int64_t n_dp;
     int64_t cells;
-    int64_t n_anchor_heavy;   /* diagnostic: anchor tiles with >= 64 pairs on the exact vote path */
+    int64_t n_anchor_heavy;   /* diagnostic: pairs the first anchor guess left open (second step)  */
     int64_t n_anchor_verify;  /* diagnostic: longest anchor tile: microseconds << 32 | window    */
     int64_t n_anchor_exact;   /* pairs without a strict majority (exact tied-maximum scan)     */
 } PlbRunStats;

@@ -1425,7 +1425,7 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
         if ((rc = launch_check(c, "k_prep"))) return rc;
     }
     if (ch.r1 > ch.r0) {   // per-read quality sum / range check (inside the k_prep timing slot)
-        k_read_check<<<(unsigned)(((int64_t)(ch.r1 - ch.r0) * 32 + 255) / 256), 256, 0, st>>>(d, ch.r0, ch.r1, c->d_ctr());
+        k_read_check<<<(unsigned)((ch.r1 - ch.r0 + 255) / 256), 256, 0, st>>>(d, ch.r0, ch.r1, c->d_ctr());
         if ((rc = launch_check(c, "k_read_check"))) return rc;
     }
     mark(1);

@@ -780,6 +780,7 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             __syncthreads();
             // ---- step two: the pairs left open, compacted (their order in the list does not matter) ----
             const int nul = s_nul;
+            if (tid == 0 && ctr) atomicAdd(&ctr->n_heavy, (unsigned long long)nul);   // diagnostic: pairs needing step two
             for (int k = tid; k < nul; k += nthr) {
                 const int p = (int)s_ulist[k];
                 int s, g;
@@ -848,7 +849,6 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             const int nfb = s_nfb;
             if (tid == 0 && ctr) {
                 atomicAdd(&ctr->n_exact, (unsigned long long)nfb);
-                if (nfb >= 64) atomicAdd(&ctr->n_heavy, 1ull);   // tiles with many exact-path pairs
             }
             const int n_fbw = min(nwarp, plan.n_cnt);  // warps that own a counter array
             for (int f = warp; f < nfb && warp < n_fbw; f += n_fbw) {
@@ -1137,27 +1137,30 @@ struct DpSlot {
 // quality above 93 is an input error (the reference asserts it, htslibWrapper.pyx:518-519).
 constexpr int kMaxPackedQualSum = 15871 - 256;
 __global__ void __launch_bounds__(256) k_read_check(DevBatch b, int r0, int r1, Counters* __restrict__ ctr) {
-    const int r = r0 + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int r = r0 + (int)((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
     if (r >= r1) return;
-    const int lane = threadIdx.x & 31;
+    // one thread per read: aligned 32-bit loads, bytes outside the read masked off, four qualities summed / maximised per
+    // instruction (the arrays are padded by 64 bytes, so the last word may be read whole)
     const int64_t o = b.read_seq_off[r];
     const int L = (int)(b.read_seq_off[r + 1] - o);
-    const uint8_t* q = b.read_qual + o;
-    int sum = 0, mx = 0;
-    for (int i = lane; i < L; i += 32) {
-        const int v = q[i];
-        sum += v;
-        mx = max(mx, v);
+    const uintptr_t a0 = (uintptr_t)(b.read_qual + o);
+    const u32* wp = (const u32*)(a0 & ~(uintptr_t)3);
+    const int head = (int)(a0 & 3);                  // bytes of the first word that belong to the previous read
+    const int nw = (head + L + 3) >> 2;
+    u32 sum = 0, mx = 0;
+    for (int k = 0; k < nw; ++k) {
+        u32 v = __ldg(wp + k);
+        if (k == 0) v &= 0xFFFFFFFFu << (8 * head);
+        if (k == nw - 1) {
+            const int tail = 4 * nw - (head + L);    // bytes of the last word past the read
+            v &= 0xFFFFFFFFu >> (8 * tail);
+        }
+        sum += __vsadu4(v, 0u);
+        mx = __vmaxu4(mx, v);
     }
-#pragma unroll
-    for (int k = 16; k > 0; k >>= 1) {
-        sum += __shfl_xor_sync(0xFFFFFFFFu, sum, k);
-        mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, k));
-    }
-    if (lane == 0) {
-        b.read_flags[r] = sum > kMaxPackedQualSum ? 2 : 0;
-        if (mx > 93 && ctr) atomicOr(&ctr->err, kErrQuality);
-    }
+    const u32 m2 = max(max(mx & 0xFFu, (mx >> 8) & 0xFFu), max((mx >> 16) & 0xFFu, mx >> 24));
+    b.read_flags[r] = (L > 0 && sum > (u32)kMaxPackedQualSum) ? 2 : 0;
+    if (m2 > 93u && ctr) atomicOr(&ctr->err, kErrQuality);
 }
 
 template <int NTHR>
