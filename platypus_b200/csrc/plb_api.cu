@@ -130,7 +130,6 @@ struct ChunkPlan {
     size_t a_smem = 0, d_smem = 0;
     int a_occ = 1, d_occ = 1;
     Block tiles_blk{nullptr, 0};
-    Block light_blk{nullptr, 0};   // k_anchor's between-round pair states
 };
 
 struct PlbDeviceBatch {
@@ -960,7 +959,7 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
         ap.rpk_words = (ap.rpk_words + 3) & ~3;
         ap.hpk_words = (ap.hpk_words + 3) & ~3;
         ap.next_halfs = (ap.next_halfs + 7) & ~7;
-        ap.mult_halfs = (ap.heads_halfs + 7) & ~7;
+        ap.mult_halfs = 2 * kRankWords;   // the heavy-key bitmap: one bit per 14-bit key
         ap.heads_halfs = std::max(ap.heads_halfs, 4096);
         ap.heads_halfs = (ap.heads_halfs + 7) & ~7;
         ap.cnt_words = (((max_hap + max_read + 2) >> 1) + 3) & ~3;
@@ -973,12 +972,6 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
         return set_err(PLB_ERR_SHAPE, "anchor tile needs %zu bytes of shared memory", ch.a_smem);
     // k_anchor is compiled for 4 resident CTAs per SM (__launch_bounds__(256, 4): 64 registers per thread)
     ch.a_occ = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / (ch.a_smem + 1024)));
-    {   // scratch for the pairs that k_anchor carries from one guess round to the next: max_pairs states per CTA
-        const size_t ctas = (size_t)std::max(1, std::min(ch.ap.n_tiles, c->n_sm * ch.a_occ));
-        int rc2 = block_get(c, ctas * (size_t)ch.ap.max_pairs * sizeof(LightState) + 256, &ch.light_blk);
-        if (rc2) return rc2;
-        ch.ap.light_state = (LightState*)ch.light_blk.p;
-    }
     // Resident CTAs per SM of the two persistent kernels.  When the chunks of a batch are pipelined over several streams
     // (chunk k+1's anchor kernel next to chunk k's band alignment) the grids are capped so that both fit an SM at once:
     // k_dp 80 registers x 256 threads and ~70 KB of shared memory per CTA, k_anchor 64 x 256 and ~42 KB.
@@ -1357,10 +1350,7 @@ extern "C" void plb_batch_free(PlbContext* c, PlbDeviceBatch* b) {
     cudaStreamSynchronize(c->stream2);
     cudaStreamSynchronize(c->stream3);
     cudaStreamSynchronize(c->copy_stream);
-    for (auto& ch : b->chunks) {
-        block_put(c, ch.tiles_blk);
-        block_put(c, ch.light_blk);
-    }
+    for (auto& ch : b->chunks) block_put(c, ch.tiles_blk);
     if (b->mode_blk.p) block_put(c, b->mode_blk);
     block_put(c, b->blk);
     delete b;
@@ -1626,10 +1616,7 @@ static double now_ms() {
 // Releases a batch whose work is known to be complete (no stream synchronisation: other work may be running).
 static void batch_release_done(PlbContext* c, PlbDeviceBatch* b) {
     if (!b) return;
-    for (auto& ch : b->chunks) {
-        block_put(c, ch.tiles_blk);
-        block_put(c, ch.light_blk);
-    }
+    for (auto& ch : b->chunks) block_put(c, ch.tiles_blk);
     if (b->mode_blk.p) block_put(c, b->mode_blk);
     block_put(c, b->blk);
     delete b;

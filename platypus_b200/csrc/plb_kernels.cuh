@@ -210,7 +210,6 @@ __global__ void __launch_bounds__(128) k_prep(DevBatch b, int h_base, int ext) {
 //     list and are re-voted by a whole warp with a real counter array, reproducing the tied-maximum
 //     scan of calign.pyx:222-247.
 // ---------------------------------------------------------------------------------------------
-struct LightState;
 struct AnchorPlan {
     const Tile* tiles;
     int32_t n_tiles;
@@ -219,14 +218,13 @@ struct AnchorPlan {
     int32_t max_pairs;      // slots*haplotypes per tile upper bound
     int32_t next_halfs;     // u16 entries for all next arrays of a group
     int32_t heads_halfs;    // u16 entries of the head area (>= largest union size + 1)
-    int32_t mult_halfs;     // u16 entries of the per-id multiplicity bounds (>= largest union size + 1)
+    int32_t mult_halfs;     // u16 entries of the heavy-key bitmap area (kRankWords * 2)
     int32_t rpk_words;      // u32 words for the 2-bit packed reads of a tile
     int32_t hpk_words;      // u32 words for the 2-bit packed haplotypes of a group
     int32_t cnt_words;      // u32 words of one warp's counter array (2 counters per word)
     int32_t n_cnt;          // counter arrays available in shared memory (>= 1)
     // byte offsets of the shared-memory areas (laid out by the host planner, 16-byte aligned)
-    struct LightState* light_state;   // global scratch: max_pairs states per CTA of the grid (pairs between guess rounds)
-    uint32_t o_cnt, o_fb, o_ul, o_ul2, o_vl, o_rpk, o_hpk, o_next, o_mult, o_heads, o_slot, o_hmeta, smem_bytes;
+    uint32_t o_cnt, o_fb, o_ul, o_vl, o_rpk, o_hpk, o_next, o_mult, o_heads, o_slot, o_hmeta, smem_bytes;
 };
 
 // host + device: lays out the shared memory of k_anchor from the plan's element counts
@@ -236,7 +234,6 @@ inline void anchor_layout(AnchorPlan& ap, size_t slot_bytes) {
     ap.o_cnt = (uint32_t)o;    o = al(o + (size_t)ap.n_cnt * ap.cnt_words * 4);
     ap.o_fb = (uint32_t)o;     o = al(o + (size_t)ap.max_pairs * 4);
     ap.o_ul = (uint32_t)o;     o = al(o + (size_t)ap.max_pairs * 4);
-    ap.o_ul2 = (uint32_t)o;    o = al(o + (size_t)ap.max_pairs * 4);
     ap.o_vl = (uint32_t)o;     o = al(o + (size_t)ap.max_pairs * 12);
     ap.o_rpk = (uint32_t)o;    o = al(o + (size_t)ap.rpk_words * 4);
     ap.o_hpk = (uint32_t)o;    o = al(o + (size_t)ap.hpk_words * 4);
@@ -377,6 +374,11 @@ constexpr int kNoCand = 0x40000000;
 constexpr int kPairSkip = 0x40000001;       // nothing to decide (LL forced to 0 / read shorter than 7)
 constexpr int kPairUndecided = 0x40000002;  // goes to the exact vote array
 
+struct LightArgs {
+    u32 head_off, rpk_off, hpk_off, res_off;
+    int nk_read, nk_hap, vub;
+    int lp, hh;   // read 7-mers that vote exactly once (light) / possibly several times (heavy)
+};
 
 // offset implied by the first read 7-mer in [i0, i1) (walking by step) that occurs exactly once in
 // the haplotype; read 7-mer -> id through the tile's table (smem offset 0), id -> position through head
@@ -389,35 +391,14 @@ __device__ __forceinline__ int unique_hit_offset(const u32* tab, const uint16_t*
     return kNoCand;
 }
 
-// The decision runs in ROUNDS so that warps stay full.  Round 0 - every pair, one thread each - tries the single guess
-// that settles most pairs (the offset implied by the first unique 7-mer of the read).  The pairs it leaves open (votes
-// split by an indel, a first guess on the minority side: about 40 % of them) are compacted into a list; round j works
-// through the list of round j-1 with guess j and compacts again.  Run as one loop per pair, nearly every warp held a
-// lane that needed three or four guesses and the other lanes idled through them (12 of 32 threads active in the vote
-// count).  What a pair carries from round to round lives in a global scratch slot (40 bytes, L2-resident).
+// The decision runs in two steps so that warps stay full.  Step one - every pair, one thread each - tries the single
+// guess that settles most pairs (the offset implied by the first unique 7-mer of the read).  The pairs it leaves open
+// (votes split by an indel, a first guess on the minority side: about a third of them) are compacted into a list, and
+// step two works through that list with the remaining guesses.  Run as one loop per pair, nearly every warp held a lane
+// that needed three or four guesses and the other lanes idled through them (21 of 32 threads active per instruction).
 //
-// Two bounds on the votes of any offset not counted yet:
-//   R  = (all votes the read can cast) - (votes counted so far)
-//   R2 = heavy + (light - light votes counted so far): every read 7-mer gives an offset at most ONE vote, light 7-mers
-//        vote exactly once in total, and a counted offset with c votes holds at least c - heavy light ones.  R2 is what
-//        decides reads over long homopolymers, whose repeated 7-mer sprays hundreds of votes over neighbouring offsets.
-// As soon as the best counted offset beats min(R, R2) it is provably the maximum of the reference's vote array
-// (calign.pyx:206-220) - unique, or tied among the counted ones.
-constexpr int kLightGuesses = 7;
-constexpr int kNoGuess16 = -32768;
-struct LightState {
-    int32_t R, R2, top;
-    int16_t g[kLightGuesses], c[kLightGuesses];
-};
-
-struct LightArgs {
-    u32 head_off, rpk_off, hpk_off, res_off;
-    int nk_read, nk_hap, vub;
-    int lp, hh;   // read 7-mers that vote exactly once (light) / possibly several times (heavy)
-    LightState* st;
-};
-
-// round 0.  Returns 1 when decided (res[0..2] = tied-maximum offsets + 1, kNoCand where unused), else 0 with *st set.
+// light_first: returns 1 when decided (res[0..2] written), else 0 with res[0] = the guess (or kNoCand) and res[1] = its
+// count, from which light_rest resumes.
 __device__ __noinline__ int light_first(LightArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint16_t* head = (const uint16_t*)(smem + a.head_off);
@@ -432,77 +413,87 @@ __device__ __noinline__ int light_first(LightArgs a) {
     }
     const int g0 = unique_hit_offset(tab, head, rpk, 0, min(nk, 24), 1);
     int c0 = 0;
-    if (g0 != kNoCand) c0 = count_offset_bits(rpk, hpk, nk, a.nk_hap, g0);
-    const int R = a.vub - c0, R2 = a.hh + a.lp - max(0, c0 - a.hh);
-    if (c0 > min(R, R2) && c0 > 0) {
-        res[0] = (u32)(g0 + 1);
-        res[1] = res[2] = (u32)kNoCand;
-        return 1;
+    if (g0 != kNoCand) {
+        c0 = count_offset_bits(rpk, hpk, nk, a.nk_hap, g0);
+        const int R = a.vub - c0, R2 = a.hh + a.lp - max(0, c0 - a.hh);
+        if (c0 > min(R, R2) && c0 > 0) {
+            res[0] = (u32)(g0 + 1);
+            res[1] = res[2] = (u32)kNoCand;
+            return 1;
+        }
     }
-    LightState* st = a.st;
-    st->R = R;
-    st->R2 = R2;
-    st->top = c0;
-    st->g[0] = (int16_t)(g0 == kNoCand ? kNoGuess16 : g0);
-    st->c[0] = (int16_t)c0;
+    res[0] = (u32)g0;
+    res[1] = (u32)c0;
     return 0;
 }
 
-// round j >= 1: read 7-mers near the end, the middle, then the quarters and eighths (reads that differ from the haplotype
-// by several indels split their votes over several offsets; each extra exact count is ~100x cheaper than the warp-wide
-// vote array).  Returns 1 decided (res written), 0 still open (state updated), 2 give up: exact vote array.
-__device__ __noinline__ int light_round(LightArgs a, int j) {
+__device__ __noinline__ int count_offset_call(u32 rpk_off, u32 hpk_off, int nk_read, int nk_hap, int idx) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    return count_offset_bits((const u32*)(smem + rpk_off), (const u32*)(smem + hpk_off), nk_read, nk_hap, idx);
+}
+
+// The remaining guesses of a pair light_first left open: read 7-mers near the end, the middle, then the quarters and
+// eighths (reads that differ from the haplotype by several indels split their votes over several offsets; each extra
+// exact count is ~100x cheaper than the warp-wide vote array).
+__device__ __noinline__ int light_rest(LightArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint16_t* head = (const uint16_t*)(smem + a.head_off);
     const u32* tab = (const u32*)smem;
     const u32* rpk = (const u32*)(smem + a.rpk_off);
-    const u32* hpk = (const u32*)(smem + a.hpk_off);
     u32* res = (u32*)(smem + a.res_off);
-    LightState* st = a.st;
     const int nk = a.nk_read;
     const int lim = min(nk, 24);
-    int i0, i1, step = 1;
-    if (j == 1) {
-        i0 = nk - 1;
-        i1 = nk - 1 - lim;
-        step = -1;
-    } else {
-        // j = 2: middle; 3, 4: quarters; 5, 6: eighths next to the ends
-        const int num = j == 2 ? 4 : j == 3 ? 2 : j == 4 ? 6 : j == 5 ? 1 : 7;
-        i0 = (nk * num) >> 3;
-        i1 = min(nk, i0 + lim);
+    constexpr int NG = 7;
+    int g[NG], c[NG];
+    g[0] = (int)res[0];
+    c[0] = (int)res[1];
+    // Two bounds on the votes of any offset not counted yet:
+    //   R  = (all votes the read can cast) - (votes counted so far)
+    //   R2 = heavy + (light - light votes counted so far): every read 7-mer gives an offset at most ONE vote,
+    //        light 7-mers vote exactly once in total, and a counted offset with c votes holds at least
+    //        c - heavy light ones.  R2 is what decides reads over long homopolymers, whose repeated 7-mer
+    //        sprays hundreds of votes over neighbouring offsets.
+    int R = a.vub - c[0], top = c[0], R2 = a.hh + a.lp - max(0, c[0] - a.hh);
+#pragma unroll
+    for (int j = 1; j < NG; ++j) {
+        int i0, i1, step = 1;
+        if (j == 1) {
+            i0 = nk - 1;
+            i1 = nk - 1 - lim;
+            step = -1;
+        } else {
+            // j = 2: middle; 3, 4: quarters; 5, 6: eighths next to the ends
+            const int num = j == 2 ? 4 : j == 3 ? 2 : j == 4 ? 6 : j == 5 ? 1 : 7;
+            i0 = (nk * num) >> 3;
+            i1 = min(nk, i0 + lim);
+        }
+        g[j] = kNoCand;
+        c[j] = 0;
+        if (top > min(R, R2)) continue;        // already decided
+        const int gj = unique_hit_offset(tab, head, rpk, i0, i1, step);
+        bool dup = gj == kNoCand;
+#pragma unroll
+        for (int k = 0; k < NG; ++k)
+            if (k < j && g[k] == gj) dup = true;
+        if (dup) continue;
+        g[j] = gj;
+        c[j] = count_offset_call(a.rpk_off, a.hpk_off, nk, a.nk_hap, gj);
+        R -= c[j];
+        R2 -= max(0, c[j] - a.hh);
+        top = max(top, c[j]);
     }
-    int R = st->R, R2 = st->R2, top = st->top;
-    const int gj = unique_hit_offset(tab, head, rpk, i0, i1, step);
-    bool dup = gj == kNoCand;
-    for (int k = 0; k < j; ++k) dup |= (int)st->g[k] == gj;
-    int cj = 0;
-    if (!dup) {
-        cj = count_offset_bits(rpk, hpk, nk, a.nk_hap, gj);
-        R -= cj;
-        R2 -= max(0, cj - a.hh);
-        top = max(top, cj);
-    }
-    st->g[j] = (int16_t)(dup ? kNoGuess16 : gj);
-    st->c[j] = (int16_t)cj;
-    if (top > min(R, R2)) {
-        if (top == 0) return 2;
-        int nt = 0;
-        res[0] = res[1] = res[2] = (u32)kNoCand;
-        for (int k = 0; k <= j; ++k)
-            if (st->g[k] != kNoGuess16 && (int)st->c[k] == top) {
-                if (nt < 3) res[nt] = (u32)((int)st->g[k] + 1);
-                ++nt;
-            }
-        // more tied maxima than the result holds: exact path.  (The order of the tied offsets is irrelevant: the score is
-        // a min over the set, calign.pyx:239-247.)
-        return nt > 3 ? 2 : 1;
-    }
-    if (j == kLightGuesses - 1) return 2;
-    st->R = R;
-    st->R2 = R2;
-    st->top = top;
-    return 0;
+    if (!(top > min(R, R2)) || top == 0) return 0;
+    int nt = 0;
+    res[0] = res[1] = res[2] = (u32)kNoCand;
+#pragma unroll
+    for (int j = 0; j < NG; ++j)
+        if (g[j] != kNoCand && c[j] == top) {
+            if (nt < 3) res[nt] = (u32)(g[j] + 1);
+            ++nt;
+        }
+    if (nt > 3) return 0;   // more tied maxima than the result holds: exact path
+    // (the order of the tied offsets is irrelevant: the score is a min over the set, calign.pyx:239-247)
+    return 1;
 }
 
 // kModes = false is the default instance (no flank score, no HLA clipping): the mode logic compiles away.
@@ -517,18 +508,16 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
     u32* s_tab = (u32*)smem;
     u32* s_cnt = (u32*)(smem + plan.o_cnt);
     u32* s_fblist = (u32*)(smem + plan.o_fb);                 // pairs for the exact vote array
-    u32* s_ulist = (u32*)(smem + plan.o_ul);                  // pairs still open after a guess round (ping-pong
-    u32* s_ulist2 = (u32*)(smem + plan.o_ul2);                // with s_ulist2)
-    LightState* light_state = plan.light_state + (size_t)blockIdx.x * plan.max_pairs;
+    u32* s_ulist = (u32*)(smem + plan.o_ul);                  // pairs the first guess left open
     u32* s_vlist = (u32*)(smem + plan.o_vl);                  // per pair: up to three tied-maximum offsets
     u32* s_rpk = (u32*)(smem + plan.o_rpk);                   // 2-bit packed reads
     u32* s_hpk = (u32*)(smem + plan.o_hpk);                   // 2-bit packed haplotypes (padded both sides)
     uint16_t* s_next = (uint16_t*)(smem + plan.o_next);
-    uint16_t* s_mult = (uint16_t*)(smem + plan.o_mult);       // per id: upper bound of its multiplicity in a haplotype
+    u32* s_heavy = (u32*)(smem + plan.o_mult);                // bit per 7-mer key: repeats inside a haplotype of the sub-group
     uint16_t* s_heads = (uint16_t*)(smem + plan.o_heads);
     SlotInfo* s_slot = (SlotInfo*)(smem + plan.o_slot);
     int32_t* s_hmeta = (int32_t*)(smem + plan.o_hmeta);      // per hap: len, next offset, packed offset
-    __shared__ int s_nid, s_nfb, s_nul, s_nul2, s_scan[kAnchorThreads / 32];
+    __shared__ int s_nid, s_nfb, s_nul, s_mmax, s_scan[kAnchorThreads / 32];
 
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     unsigned long long st_pairs = 0, st_scored = 0, st_dp = 0, st_cells = 0, t_tile0 = 0;
@@ -569,7 +558,6 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             }
             s_nfb = 0;
             s_nul = 0;
-            s_nul2 = 0;
         }
         for (int i = tid; i < kRankWords; i += nthr) ((uint2*)s_tab)[i] = make_uint2(0u, 0u);
         // slot metadata + skip rule (chaplotype.pyx:343-361)
@@ -673,7 +661,8 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             __syncthreads();
             // ---- chains of this haplotype sub-group (calign.pyx:94-124) ----
             for (int i = tid; i < (g1 - g0) * hstride; i += nthr) s_heads[i] = 0;
-            for (int i = tid; i < hstride; i += nthr) s_mult[i] = i ? 1 : 0;
+            for (int i = tid; i < kRankWords; i += nthr) s_heavy[i] = 0u;
+            if (tid == 0) s_mmax = 1;
             __syncthreads();
             for (int g = g0; g < g1; ++g) {
                 const int len = s_hmeta[3 * g];
@@ -681,7 +670,8 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 uint16_t* nxt = s_next + s_hmeta[3 * g + 1];
                 uint16_t* head = s_heads + (g - g0) * hstride;
                 for (int i = tid; i < len - kKmer; i += nthr) {
-                    const u32 id = tab_lookup(s_tab, key_at(hpk, i));
+                    const u32 key = key_at(hpk, i);
+                    const u32 id = tab_lookup(s_tab, key);
                     unsigned short cur = head[id];
                     while (true) {  // push position i (stored as i+1); order inside a chain is irrelevant.
                         // bit 15 of the head marks chains with more than one element.
@@ -691,45 +681,57 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                         if (old == cur) break;
                         cur = old;
                     }
+                    // a 7-mer that repeats inside a haplotype of the sub-group is "heavy": it can vote several times
+                    if (cur) atomicOr(&s_heavy[key >> 5], 1u << (key & 31u));
                 }
             }
             __syncthreads();
-            // multiplicity bound per id (1 unless some haplotype repeats the 7-mer), then per read the
-            // bound V_ub >= number of votes it can cast on any haplotype of this sub-group
+            // largest multiplicity of a 7-mer inside one haplotype of the sub-group (chains with bit 15 only)
             for (int i = tid; i < (g1 - g0) * hstride; i += nthr) {
                 const u32 hd = s_heads[i];
                 if (hd & 0x8000u) {
-                    const int g = g0 + i / hstride, id = i % hstride;
+                    const int g = g0 + i / hstride;
                     const uint16_t* nxt = s_next + s_hmeta[3 * g + 1];
-                    unsigned short len = 0;
+                    int len = 0;
                     for (u32 p1 = hd & 0x7FFFu; p1; p1 = nxt[p1]) ++len;
-                    unsigned short cur = s_mult[id];
-                    while (cur < len) {
-                        const unsigned short old = cas_u16(s_mult, id, cur, len);
-                        if (old == cur) break;
-                        cur = old;
-                    }
+                    atomicMax(&s_mmax, len);
                 }
             }
             __syncthreads();
+            // Per read: how many of its 7-mers (0..len-8, calign.pyx:155-165) occur in the group at all and how many are
+            // heavy - two bitmap tests per 7-mer, five consecutive 7-mers per lane out of one 64-bit window of the packed
+            // read.  light = present - heavy votes at most once on a haplotype; a heavy one votes at most s_mmax times:
+            // V_ub = light + heavy * s_mmax bounds the votes the read can cast on any haplotype of the sub-group.
+            const int mmax = s_mmax;
             for (int s = warp; s < ns; s += nwarp) {
                 const SlotInfo si = s_slot[s];
                 const int nk = si.len - kKmer;
                 if ((si.flags & 1) || nk <= 0) continue;
-                int sum = 0, lh = 0;   // lh: light count | heavy count << 16
-                const u32* rpk = s_rpk + si.poff;   // read 7-mers 0..len-8 (calign.pyx:155-165)
-                for (int i = lane; i < nk; i += 32) {
-                    const int m = s_mult[tab_lookup(s_tab, key_at(rpk, i))];
-                    sum += m;
-                    lh += (m == 1) + ((m > 1) << 16);
+                int np = 0, nhv = 0;
+                const u32* rpk = s_rpk + si.poff;
+                for (int base = 0; base < nk; base += 160) {
+                    const int p0 = base + 5 * lane;
+                    if (p0 < nk) {
+                        const unsigned long long x =
+                            (((unsigned long long)rpk[(p0 >> 4) + 1] << 32) | rpk[p0 >> 4]) >> (2 * (p0 & 15));
+#pragma unroll
+                        for (int t = 0; t < 5; ++t) {
+                            if (p0 + t < nk) {
+                                const u32 key = (u32)(x >> (2 * t)) & 0x3FFFu;
+                                np += (int)((s_tab[2 * (key >> 5)] >> (key & 31u)) & 1u);
+                                nhv += (int)((s_heavy[key >> 5] >> (key & 31u)) & 1u);
+                            }
+                        }
+                    }
                 }
                 for (int o = 16; o > 0; o >>= 1) {
-                    sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-                    lh += __shfl_xor_sync(0xFFFFFFFFu, lh, o);
+                    np += __shfl_xor_sync(0xFFFFFFFFu, np, o);
+                    nhv += __shfl_xor_sync(0xFFFFFFFFu, nhv, o);
                 }
                 if (lane == 0) {
-                    s_slot[s].vub = sum;
-                    s_slot[s].lph = lh;
+                    const int light = np - nhv;
+                    s_slot[s].vub = light + nhv * mmax;
+                    s_slot[s].lph = light | (nhv << 16);
                 }
             }
             __syncthreads();
@@ -787,49 +789,35 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
                 la.vub = si.vub;
                 la.lp = si.lph & 0xFFFF;
                 la.hh = si.lph >> 16;
-                la.st = light_state + p;
                 if (!light_first(la)) s_ulist[atomicAdd(&s_nul, 1)] = (u32)p;
             }
             __syncthreads();
-            // ---- further rounds: the pairs still open, compacted after every guess (their order does not matter) ----
-            if (tid == 0 && ctr) atomicAdd(&ctr->n_heavy, (unsigned long long)s_nul);   // diagnostic: pairs past round 0
-            for (int j = 1; j < kLightGuesses; ++j) {
-                u32* cur = (j & 1) ? s_ulist : s_ulist2;
-                u32* nxt = (j & 1) ? s_ulist2 : s_ulist;
-                int* n_cur = (j & 1) ? &s_nul : &s_nul2;
-                int* n_nxt = (j & 1) ? &s_nul2 : &s_nul;
-                const int n = *n_cur;
-                if (n == 0) break;   // block-uniform
-                for (int k = tid; k < n; k += nthr) {
-                    const int p = (int)cur[k];
-                    int s, g;
-                    int64_t gs, pair;
-                    pair_id(p, s, g, gs, pair);
-                    const SlotInfo si = s_slot[s];
-                    const PairClip pc = pair_clip(sp, si.pos, si.len, hap_start_w, win_start_w, s_hmeta[3 * g]);
-                    LightArgs la;
-                    la.head_off = plan.o_heads + 2u * (u32)((g - g0) * hstride);
-                    la.rpk_off = plan.o_rpk + 4u * (u32)si.poff;
-                    la.hpk_off = plan.o_hpk + 4u * (u32)s_hmeta[3 * g + 2];
-                    la.res_off = plan.o_vl + 12u * (u32)p;
-                    la.nk_read = pc.L - kKmer;
-                    la.nk_hap = s_hmeta[3 * g] - kKmer;
-                    la.vub = si.vub;
-                    la.lp = si.lph & 0xFFFF;
-                    la.hh = si.lph >> 16;
-                    la.st = light_state + p;
-                    const int r = light_round(la, j);
-                    if (r == 0) {
-                        nxt[atomicAdd(n_nxt, 1)] = (u32)p;
-                    } else if (r == 2) {
-                        s_vlist[3 * p] = (u32)kPairUndecided;
-                        s_fblist[atomicAdd(&s_nfb, 1)] = (u32)p;
-                    }
+            // ---- step two: the pairs left open, compacted (their order in the list does not matter) ----
+            const int nul = s_nul;
+            if (tid == 0 && ctr) atomicAdd(&ctr->n_heavy, (unsigned long long)nul);   // diagnostic: pairs needing step two
+            for (int k = tid; k < nul; k += nthr) {
+                const int p = (int)s_ulist[k];
+                int s, g;
+                int64_t gs, pair;
+                pair_id(p, s, g, gs, pair);
+                const SlotInfo si = s_slot[s];
+                const PairClip pc = pair_clip(sp, si.pos, si.len, hap_start_w, win_start_w, s_hmeta[3 * g]);
+                LightArgs la;
+                la.head_off = plan.o_heads + 2u * (u32)((g - g0) * hstride);
+                la.rpk_off = plan.o_rpk + 4u * (u32)si.poff;
+                la.hpk_off = plan.o_hpk + 4u * (u32)s_hmeta[3 * g + 2];
+                la.res_off = plan.o_vl + 12u * (u32)p;
+                la.nk_read = pc.L - kKmer;
+                la.nk_hap = s_hmeta[3 * g] - kKmer;
+                la.vub = si.vub;
+                la.lp = si.lph & 0xFFFF;
+                la.hh = si.lph >> 16;
+                if (!light_rest(la)) {
+                    s_vlist[3 * p] = (u32)kPairUndecided;
+                    s_fblist[atomicAdd(&s_nfb, 1)] = (u32)p;
                 }
-                __syncthreads();
-                if (tid == 0) *n_cur = 0;
-                __syncthreads();
             }
+            __syncthreads();
             // ---- emit the band starts of the decided pairs ----
             for (int p = tid; p < npairs; p += nthr) {
                 const int c0 = (int)s_vlist[3 * p];
@@ -954,7 +942,6 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
             if (tid == 0) {
                 s_nfb = 0;
                 s_nul = 0;
-                s_nul2 = 0;
             }
         }
     }
