@@ -23,7 +23,7 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRCS
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("PLB_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRCS
     r = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
