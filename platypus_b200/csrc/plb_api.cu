@@ -85,6 +85,7 @@ struct JobSlot {
     cudaEvent_t ev_chunk[kMaxChunks + 1];   // H2D of chunk k done
     cudaEvent_t ev_unpack[kMaxChunks];      // packed input: chunk k's bases are ASCII again
     cudaEvent_t ev_anchor[kMaxChunks];      // chunk k's anchor kernel has finished (software pipeline of the chunks)
+    cudaEvent_t ev_kdone[kMaxChunks];       // chunk k's kernels have finished: its outputs may go back
     cudaEvent_t ev_done[3];                 // last work of the job on compute stream k
     cudaEvent_t ev_ctr;                     // counters are back in h_ctr
     bool busy = false;
@@ -96,7 +97,8 @@ struct PlbContext {
     cudaStream_t copy_stream;   // H2D of the pipelined host path
     cudaStream_t stream2;       // further compute streams: chunk k of the pipelined host path runs on
     cudaStream_t stream3;       // stream k mod 3, so one chunk's latency-bound tails overlap the next chunks
-    cudaStream_t aux_stream;    // fetches a job's counters once its three compute streams are done
+    cudaStream_t aux_stream;    // D2H of the host path: a chunk's outputs and, last, the job's counters (kept off the
+                                // compute streams, where the copies would sit between one job's kernels and the next's)
     cudaEvent_t ev_s2, ev_s3;
     JobSlot slot[kMaxJobs];
     int cur = 0;                // slot whose arena / counters the code below is working with
@@ -205,6 +207,7 @@ extern "C" int plb_context_create(int device, void* stream, PlbContext** out) {
         for (int i = 0; i <= kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&js.ev_chunk[i], cudaEventDisableTiming));
         for (int i = 0; i < kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&js.ev_unpack[i], cudaEventDisableTiming));
         for (int i = 0; i < kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&js.ev_anchor[i], cudaEventDisableTiming));
+        for (int i = 0; i < kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&js.ev_kdone[i], cudaEventDisableTiming));
         for (int i = 0; i < 3; ++i) CU(cudaEventCreateWithFlags(&js.ev_done[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&js.ev_ctr, cudaEventDisableTiming));
     }
@@ -241,6 +244,7 @@ extern "C" void plb_context_destroy(PlbContext* c) {
         for (int i = 0; i <= kMaxChunks; ++i) cudaEventDestroy(js.ev_chunk[i]);
         for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(js.ev_unpack[i]);
         for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(js.ev_anchor[i]);
+        for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(js.ev_kdone[i]);
         for (int i = 0; i < 3; ++i) cudaEventDestroy(js.ev_done[i]);
         cudaEventDestroy(js.ev_ctr);
     }
@@ -1724,7 +1728,7 @@ static int submit_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions
     cudaError_t e = cudaSuccess;
     auto d2h = [&](void* dst, const void* src, size_t off, size_t bytes) {
         if (rc == PLB_OK && e == cudaSuccess && dst && src && bytes)
-            e = cudaMemcpyAsync((uint8_t*)dst + off, (const uint8_t*)src + off, bytes, cudaMemcpyDefault, kst);   // dst: host or device
+            e = cudaMemcpyAsync((uint8_t*)dst + off, (const uint8_t*)src + off, bytes, cudaMemcpyDefault, c->aux_stream);   // dst: host or device
     };
     // Chunking.  A lone call wants its first kernels early: up to six chunks whose sizes grow x1.3.  When another job
     // is still computing, this job's bytes travel behind that job's kernels anyway, so it is cut into few chunks (each
@@ -1806,6 +1810,9 @@ static int submit_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions
                                  js.ev_anchor[k])))
             break;
         tmark(kst);
+        // the chunk's outputs go back on the D2H stream, behind an event: the compute stream is free for the next kernels
+        if (e == cudaSuccess) e = cudaEventRecord(js.ev_kdone[k], kst);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->aux_stream, js.ev_kdone[k], 0);
         if (hpop) {
             const size_t wq = (size_t)w0, wn = (size_t)(w1 - w0);
             d2h(hpop->gl, dpop.gl, wq * nInd * Gm * 8, wn * nInd * Gm * 8);
@@ -1821,7 +1828,7 @@ static int submit_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions
         const int64_t p0 = db->h_ll_off[(size_t)w0 * nInd], p1 = db->h_ll_off[(size_t)w1 * nInd];
         if (want_ll) d2h(hll->ll, dll.ll, (size_t)p0 * 8, (size_t)(p1 - p0) * 8);
         if (want_sc) d2h(hll->score, dll.score, (size_t)p0 * 4, (size_t)(p1 - p0) * 4);
-        tmark(kst);
+        tmark_t(c->aux_stream, "d2h:");
     }
     // completion: one event per compute stream (no join through the first stream - the next job's first chunk must not
     // wait for this job's last chunks on the other two), the counters come back on the side stream once all three fired

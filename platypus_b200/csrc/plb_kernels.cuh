@@ -603,15 +603,12 @@ __global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, Anchor
         // ---- the only pass over the raw bases: pack reads and haplotypes 2 bits per base (the
         //      reference's hash digit, calign.pyx:69-74).  7-mer keys, read ids and vote counts all
         //      derive from these words. ----
-        // (a warp per read.  Sixteen lanes per read - a 150 bp read is 13 words - measured 5 % faster but gave wrong
-        // candidates for one read of a 1974-window batch in 3 runs of 4, with no hazard reported by racecheck / memcheck /
-        // initcheck; until that is understood the slower loop stays.)
-        for (int s = warp; s < ns; s += nwarp) {
+        for (int s = tid >> 4; s < ns; s += nthr >> 4) {   // 16 lanes per read: a 150 bp read is 13 words
             const SlotInfo si = s_slot[s];
             if ((si.flags & 1) || si.len <= kKmer) continue;
             const uint8_t* rs = b.read_seq + b.read_seq_off[si.read];
             const int nw = ((si.len + 15) >> 4) + kPackPadWords;
-            for (int wd = lane; wd < nw; wd += 32) s_rpk[si.poff + wd] = pack16_codes(rs, 16 * wd, si.len);
+            for (int wd = tid & 15; wd < nw; wd += 16) s_rpk[si.poff + wd] = pack16_codes(rs, 16 * wd, si.len);
         }
         for (int g = 0; g < nh; ++g) {
             const int len = s_hmeta[3 * g];
@@ -1374,6 +1371,10 @@ __global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScorePa
                             row[y] = y < ds.len ? s_ptab[((u32)s_code[cb[k]] << 7) | (qb[k] & 127u)] : 0u;
                         }
                     }
+                    // reads of 177-192 bp need rows beyond the 192 handled above: the recurrence reads dp_steps(L) + 4 rows
+                    // and the rows past the read MUST be zero (stale words there can wrap a masked lane negative, and a
+                    // negative value survives the last-row mask: found by the 1974-window differential case)
+                    for (int y = 192 + lane; y < n; y += 32) row[y] = 0u;
                     continue;
                 }
                 const uint8_t* rs = b.read_seq + o;
