@@ -84,6 +84,7 @@ struct JobSlot {
     Counters* h_ctr = nullptr;              // pinned
     cudaEvent_t ev_chunk[kMaxChunks + 1];   // H2D of chunk k done
     cudaEvent_t ev_unpack[kMaxChunks];      // packed input: chunk k's bases are ASCII again
+    cudaEvent_t ev_tiles[kMaxChunks];       // chunk k's tile lists are on the device (jobs queued behind another job)
     cudaEvent_t ev_anchor[kMaxChunks];      // chunk k's anchor kernel has finished (software pipeline of the chunks)
     cudaEvent_t ev_kdone[kMaxChunks];       // chunk k's kernels have finished: its outputs may go back
     cudaEvent_t ev_done[3];                 // last work of the job on compute stream k
@@ -92,6 +93,7 @@ struct JobSlot {
 };
 
 struct PlbContext {
+    cudaEvent_t trace_prev_end = nullptr;   // PLB_TRACE: last compute mark of the previous job
     int device;
     cudaStream_t stream;
     cudaStream_t copy_stream;   // H2D of the pipelined host path
@@ -206,6 +208,7 @@ extern "C" int plb_context_create(int device, void* stream, PlbContext** out) {
         memset(js.h_ctr, 0, sizeof(Counters));
         for (int i = 0; i <= kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&js.ev_chunk[i], cudaEventDisableTiming));
         for (int i = 0; i < kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&js.ev_unpack[i], cudaEventDisableTiming));
+        for (int i = 0; i < kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&js.ev_tiles[i], cudaEventDisableTiming));
         for (int i = 0; i < kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&js.ev_anchor[i], cudaEventDisableTiming));
         for (int i = 0; i < kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&js.ev_kdone[i], cudaEventDisableTiming));
         for (int i = 0; i < 3; ++i) CU(cudaEventCreateWithFlags(&js.ev_done[i], cudaEventDisableTiming));
@@ -243,6 +246,7 @@ extern "C" void plb_context_destroy(PlbContext* c) {
         for (auto& pb : js.pin.blocks) cudaFreeHost(pb.first);
         for (int i = 0; i <= kMaxChunks; ++i) cudaEventDestroy(js.ev_chunk[i]);
         for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(js.ev_unpack[i]);
+        for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(js.ev_tiles[i]);
         for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(js.ev_anchor[i]);
         for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(js.ev_kdone[i]);
         for (int i = 0; i < 3; ++i) cudaEventDestroy(js.ev_done[i]);
@@ -779,7 +783,7 @@ static int prepare_batch(PlbContext* c, const PlbWindowBatch* hb, PlbDeviceBatch
         return set_err(PLB_ERR_UNSUPPORTED, "packed batches are not taken by the selection rounds");
     }
     db->qual_bits = qbits;
-    if (qbits) memcpy(db->qtab.v, hb->qual_table, 64);
+    if (qbits) memcpy(db->qtab.w, hb->qual_table, 64);
     const size_t o_pk_qual = L.take(qbits ? (size_t)(read_bytes * qbits + 7) / 8 + 64 : 0);
     const size_t o_pk_hap = L.take(packed ? (size_t)(hap_bytes + 3) / 4 + 64 : 0),
                  o_pk_read = L.take(packed ? (size_t)(read_bytes + 3) / 4 + 64 : 0),
@@ -1207,21 +1211,26 @@ static int copy_seq_for_windows(PlbContext* c, PlbDeviceBatch* db, const PlbWind
 
 namespace plb {
 // 2-bit packed bases -> the ASCII bytes every kernel reads (A 0, C 1, G 2, T 3; base i at bits 2*(i & 3) of byte i >> 2).
-// One thread per packed byte; writes ONLY bases b0 <= i < b1, so a byte shared with a neighbouring interval (unpacked by
-// another chunk, possibly already patched and in use) is never touched twice.
+// One thread per packed 32-bit word = sixteen bases = one 16-byte store; writes ONLY bases b0 <= i < b1, so a byte shared
+// with a neighbouring interval (unpacked by another chunk, possibly already patched and in use) is never touched twice.
 __global__ void __launch_bounds__(256) k_unpack2(const uint8_t* __restrict__ pk, uint8_t* __restrict__ dst, int64_t b0,
                                                  int64_t b1) {
-    const int64_t q = (b0 >> 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t base = q << 2;
+    const int64_t g = (b0 >> 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t base = g << 4;
     if (base >= b1) return;
-    const u32 c = pk[q];
-    const u32 sel = (c & 3u) | ((c & 0xCu) << 2) | ((c & 0x30u) << 4) | ((c & 0xC0u) << 6);
-    const u32 v = __byte_perm(0x54474341u /* "ACGT" */, 0u, sel);
-    if (base >= b0 && base + 4 <= b1) {
-        *(u32*)(dst + base) = v;
+    const u32 word = ((const u32*)pk)[g];          // the staging area is 256-byte aligned and padded to whole words
+    u32 out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const u32 c = (word >> (8 * k)) & 0xFFu;
+        const u32 sel = (c & 3u) | ((c & 0xCu) << 2) | ((c & 0x30u) << 4) | ((c & 0xC0u) << 6);
+        out[k] = __byte_perm(0x54474341u /* "ACGT" */, 0u, sel);
+    }
+    if (base >= b0 && base + 16 <= b1) {
+        *(uint4*)(dst + base) = make_uint4(out[0], out[1], out[2], out[3]);
     } else {
-        for (int k = 0; k < 4; ++k)
-            if (base + k >= b0 && base + k < b1) dst[base + k] = (uint8_t)(v >> (8 * k));
+        for (int k = 0; k < 16; ++k)
+            if (base + k >= b0 && base + k < b1) dst[base + k] = (uint8_t)(out[k >> 2] >> (8 * (k & 3)));
     }
 }
 // Packed qualities -> bytes: code i at bit i * BITS of the stream, value = table[code].  One thread per group of sixteen
@@ -1231,8 +1240,8 @@ __global__ void __launch_bounds__(256) k_unpack2(const uint8_t* __restrict__ pk,
 template <int BITS>
 __global__ void __launch_bounds__(256) k_unpack_qual(const uint8_t* __restrict__ pk, uint8_t* __restrict__ dst, int64_t b0,
                                                      int64_t b1, QualTable tab) {
-    __shared__ uint8_t s_tab[64];
-    if (threadIdx.x < 16) ((u32*)s_tab)[threadIdx.x] = ((const u32*)tab.v)[threadIdx.x];
+    __shared__ __align__(16) uint8_t s_tab[64];
+    if (threadIdx.x < 16) ((u32*)s_tab)[threadIdx.x] = tab.w[threadIdx.x];
     __syncthreads();
     const int64_t g = (b0 >> 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t base = g << 4;
@@ -1288,7 +1297,7 @@ static int unpack_fresh(PlbContext* c, PlbDeviceBatch* db, int chunk, cudaStream
         }
         const uint8_t* pk = f.which ? db->pk_read : db->pk_hap;
         uint8_t* dst = (uint8_t*)(f.which ? db->d.read_seq : db->d.hap_seq);
-        const int64_t nq = ((f.hi + 3) >> 2) - (f.lo >> 2);
+        const int64_t nq = ((f.hi + 15) >> 4) - (f.lo >> 4);
         if (nq <= 0) continue;
         k_unpack2<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(pk, dst, f.lo, f.hi);
         if ((rc = launch_check(c, "k_unpack2"))) return rc;
@@ -1731,9 +1740,10 @@ static int submit_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions
             e = cudaMemcpyAsync((uint8_t*)dst + off, (const uint8_t*)src + off, bytes, cudaMemcpyDefault, c->aux_stream);   // dst: host or device
     };
     // Chunking.  A lone call wants its first kernels early: up to six chunks whose sizes grow x1.3.  When another job
-    // is still computing, this job's bytes travel behind that job's kernels anyway, so it is cut into few chunks (each
-    // chunk costs ~0.25 ms of kernel tails); PLB_PIPE_CHUNKS overrides that number.
-    const int pipe_chunks = getenv("PLB_PIPE_CHUNKS") ? std::max(1, std::min(kMaxChunks, atoi(getenv("PLB_PIPE_CHUNKS")))) : 2;
+    // is still computing, this job's bytes travel behind that job's kernels anyway, so it is cut into three equal chunks
+    // on the three compute streams (one chunk's kernel tails and unpacking run under the next chunk's kernels; measured
+    // 4.58 / 4.51 / 4.46 ms per step with 1 / 2 / 3 chunks); PLB_PIPE_CHUNKS overrides that number.
+    const int pipe_chunks = getenv("PLB_PIPE_CHUNKS") ? std::max(1, std::min(kMaxChunks, atoi(getenv("PLB_PIPE_CHUNKS")))) : 3;
     int n_chunks = std::max(1, std::min(kMaxChunks, W / kMinChunkWindows));
     const bool pipelined = busy > 0;
     if (pipelined) n_chunks = std::min(n_chunks, pipe_chunks);
@@ -1791,10 +1801,20 @@ static int submit_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions
         const int w0 = cut(k), w1 = cut(k + 1);
         if (w1 <= w0) continue;
         kst = kstreams[k % 3];
-        // tile lists are read from pinned host memory (a small H2D copy would wait behind the sequence bytes)
-        if ((rc = plan_chunk(c, db, hb, w0, w1, kst, true))) break;
+        // A lone job's kernels read their tile lists from pinned host memory (a small H2D copy would wait behind the
+        // sequence bytes).  A job queued behind another one has time: its lists follow its bytes on the copy stream, so its
+        // persistent kernels fetch tiles from HBM instead of across a PCIe link that the next job's upload keeps busy.
+        // (For a lone job, sending the lists on another stream was measured: the copy engine serves them behind the queued
+        // sequence bytes all the same, 6.2 -> 9.6 ms per call.)
+        if ((rc = plan_chunk(c, db, hb, w0, w1, cs, !pipelined))) break;
+        if (pipelined) {
+            e = cudaEventRecord(js.ev_tiles[k], cs);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(kst, js.ev_tiles[k], 0);
+            if (e != cudaSuccess) break;
+        }
         e = cudaStreamWaitEvent(kst, js.ev_chunk[1 + k], 0);
         if (e != cudaSuccess) break;
+        tmark_t(kst, "u:");
         if (db->packed || db->qual_bits) {
             // reads are shared between chunks: chunk k may score reads that chunk k-1's copies brought in, so its
             // kernels also wait for that chunk's unpacking (which waited for the one before it)
@@ -1874,9 +1894,27 @@ static int wait_job(PlbContext* c, PlbJob* job) {
                 cudaEventElapsedTime(&t, job->tev[0], job->tev[i]);
                 fprintf(stderr, " %s%.2f", job->ttag[i], t);
             }
+            // idle time of the compute side between jobs: from the previous job's last compute mark to this job's first
+            int first_k = -1, last_k = -1;
+            for (size_t i = 1; i < job->tev.size(); ++i)
+                if (job->ttag[i][0] == 'u' || job->ttag[i][0] == 'k') {
+                    if (first_k < 0) first_k = (int)i;
+                    last_k = (int)i;
+                }
+            if (c->trace_prev_end && first_k >= 0) {
+                float t = 0;
+                if (cudaEventElapsedTime(&t, c->trace_prev_end, job->tev[first_k]) == cudaSuccess)
+                    fprintf(stderr, "  [previous job's last kernel mark -> this job's first: %+.2f ms]", t);
+            }
+            if (last_k >= 0) {
+                if (c->trace_prev_end) cudaEventDestroy(c->trace_prev_end);
+                c->trace_prev_end = job->tev[last_k];
+                job->tev[last_k] = nullptr;
+            }
             fprintf(stderr, "\n");
         }
-        for (cudaEvent_t ev_ : job->tev) cudaEventDestroy(ev_);
+        for (cudaEvent_t ev_ : job->tev)
+            if (ev_) cudaEventDestroy(ev_);
         if (trace)
             fprintf(stderr, "[plb] job slot %d: prepare %.2f ms, issue %.2f ms, submit->wait %.2f ms, copy drain +%.2f ms, compute drain +%.2f ms (%d chunks)\n",
                     job->slot, job->t_prep - job->t_start, job->t_issue - job->t_prep, t_w0 - job->t_issue, t_copy - t_w0,

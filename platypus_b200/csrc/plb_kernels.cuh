@@ -70,8 +70,8 @@ struct DevBatch {
 };
 
 struct QualTable {   // value of every packed quality code (PlbWindowBatch.qual_table), passed to kernels by value
-    uint8_t v[64];
-};
+    uint32_t w[16];  // as words: a kernel indexes the parameter directly (a byte array cast to words is first copied to
+};                   // local memory byte by byte: 64 LDC.U8 + 64 STL.U8 per thread)
 
 struct Tile {
     int32_t w;        // window
