@@ -1796,7 +1796,10 @@ static int submit_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions
         }
     };
     for (int k = 0; k < n_chunks && rc == PLB_OK && e == cudaSuccess; ++k) {
-        queue_copies(k == 0 ? 2 : n_chunks);
+        // lone job: the DMA must not wait for the host (two chunks queued ahead, then all of them); queued job: the DMA
+        // still works on the previous job's bytes, so chunk k's bytes and tile lists are queued in turn and chunk k's
+        // kernels need nothing that travels behind chunk k+1
+        queue_copies(pipelined ? k + 1 : (k == 0 ? 2 : n_chunks));
         if (rc != PLB_OK || e != cudaSuccess) break;
         const int w0 = cut(k), w1 = cut(k + 1);
         if (w1 <= w0) continue;
