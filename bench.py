@@ -28,9 +28,11 @@ import argparse
 import json
 import os
 
-# the library's host threads (tile planning) sleep between calls instead of spinning next to the other ranks' threads;
-# libgomp reads this when it is loaded, i.e. before torch / numpy are imported
-os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+# with several ranks on the box, the library's host threads (tile planning) sleep between calls instead of spinning next
+# to the other ranks' threads; libgomp reads this when it is loaded, i.e. before torch / numpy are imported.  A single
+# rank keeps libgomp's default (spin briefly, then sleep): the selection loop has many short parallel regions per call.
+if int(os.environ.get("LOCAL_WORLD_SIZE", "1")) > 1:
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 import statistics
 import subprocess
 import sys
@@ -929,6 +931,7 @@ def main():
     ap.add_argument("--ascii", action="store_true", help="e2e leg: send byte-per-base sequences instead of the packed form")
     args = ap.parse_args()
     if args.stage == "select":
+        args.windows = args.windows or WINDOWS_PER_GPU
         if int(os.environ.get("RANK", "0")) == 0:
             run_select(args)
         return

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise ncu reports into profiles/: key raw metrics per kernel + top source lines.
-usage: ncu_summary.py OUT.md report1.ncu-rep [report2.ncu-rep ...]"""
+usage: ncu_summary.py [--select | --what "command ..."] OUT.md report1.ncu-rep [report2.ncu-rep ...]"""
 import csv
 import subprocess
 import sys
@@ -38,6 +38,9 @@ def main():
         args = args[1:]
         what = ("`python tools/select_bench.py 10000 1 --pin` (synth-select-v1: 10,000 windows x 8 candidate variants, one "
                 "launch of a late round: ~50 trial haplotypes x 11 sampled reads per window, half of the windows)")
+    if args and args[0] == "--what":    # free text: the command the reports were captured under
+        what = args[1]
+        args = args[2:]
     out_md, reps = args[0], args[1:]
     assert out_md.endswith(".md"), "usage: ncu_summary.py [--select] OUT.md report.ncu-rep ..."
     with open(out_md, "w") as f:
