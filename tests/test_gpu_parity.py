@@ -752,7 +752,8 @@ def test_submit_wait_two_jobs_in_flight(engine):
     variantcaller.pyx:566-615).  Results equal the one-call path bit for bit, in any interleaving; a third job in flight
     is refused; synchronous entry points refuse to run under in-flight jobs."""
     from platypus_b200.engine import PlbError
-    batches = [synth.make_batch(2600, window_offset=7000 * i) for i in range(4)] + [cases.edge_batch(seed=4)]
+    # 2600 windows: two chunks per queued job, 3300 / 4200: three (tile lists in HBM, one chunk per compute stream)
+    batches = [synth.make_batch(n, window_offset=7000 * i) for i, n in enumerate((2600, 3300, 2600, 4200))] + [cases.edge_batch(seed=4)]
     want = [engine.population_run(b) for b in batches]
     pinned = [_pinned_copy(b.pack() if i % 2 else b) for i, b in enumerate(batches)]
     keys = ("gl", "gl_log_max", "gof", "hap_like", "freq", "em_post", "call", "var_phred", "em_iters")
