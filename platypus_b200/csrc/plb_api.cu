@@ -960,6 +960,8 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
         }
         ch.ap.n_tiles = (int)off_a[(size_t)parts];
         ch.dp.n_tiles = (int)off_d[(size_t)parts];
+        static const int tma_max = getenv("PLB_DP_TMA_MAX") ? std::min(kTmaMaxLen, atoi(getenv("PLB_DP_TMA_MAX"))) : kTmaMaxLen;
+        ch.dp.tma_max = tma_max;
     }
     {
         AnchorPlan& ap = ch.ap;

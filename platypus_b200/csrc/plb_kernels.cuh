@@ -1134,6 +1134,7 @@ struct DpPlan {
     int32_t prof_words;   // smem u32 words for all profile rows of a tile
     int32_t rec_count;    // smem HapRec entries for a haplotype group
     int32_t max_pairs;    // max slots*group per tile
+    int32_t tma_max;      // reads up to this length are staged by TMA (<= kTmaMaxLen; PLB_DP_TMA_MAX, experiments)
 };
 
 struct DpSlot {
@@ -1299,7 +1300,7 @@ __global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScorePa
             bool issued = false;
             if (!general && tid < ns) {
                 const DpSlot ds = s_slot[tid];
-                if (!(ds.flags & 1) && ds.len >= kMinFastLen && ds.len <= kTmaMaxLen) {
+                if (!(ds.flags & 1) && ds.len >= kMinFastLen && ds.len <= plan.tma_max) {
                     const int64_t o = b.read_seq_off[ds.read];
                     const int64_t a0 = o & ~(int64_t)15;
                     const u32 nb = (u32)(((o + ds.len + 15) & ~(int64_t)15) - a0);   // <= tma_raw_bytes(len)
@@ -1350,7 +1351,7 @@ __global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScorePa
                 const int64_t o = b.read_seq_off[ds.read];
                 int n = dp_steps(ds.len) + 4;
                 u32* row = s_prof + ds.poff;
-                if (ds.len <= kTmaMaxLen) {
+                if (ds.len <= plan.tma_max) {
                     // raw bytes sit in the row's own tail: pull all of them into registers, then overwrite
                     const uint8_t* row_end = (const uint8_t*)(row + prof_row_words_dev(ds.len));
                     const int NB = tma_raw_bytes(ds.len);
