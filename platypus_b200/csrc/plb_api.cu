@@ -974,14 +974,17 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
         ap.heads_halfs = (ap.heads_halfs + 7) & ~7;
         ap.cnt_words = (((max_hap + max_read + 2) >> 1) + 3) & ~3;
         const int nwarps = kAnchorThreads / 32;
+        // (a vote array for every warp: with two arrays per CTA the rare exact path serialises, 0.98 -> 1.14 ms; a smaller
+        // heads area splits the haplotype group more often, 1.14 -> 1.31 ms - both measured while trying to fit six CTAs)
         ap.n_cnt = (int)std::max<size_t>(1, std::min<size_t>(nwarps, kAnchorCntBudget / ((size_t)ap.cnt_words * 4)));
         anchor_layout(ap, sizeof(SlotInfo));
         ch.a_smem = ap.smem_bytes;
     }
     if (ch.a_smem + 1024 > (size_t)c->smem_optin)
         return set_err(PLB_ERR_SHAPE, "anchor tile needs %zu bytes of shared memory", ch.a_smem);
-    // k_anchor is compiled for 4 resident CTAs per SM (__launch_bounds__(256, 4): 64 registers per thread)
-    ch.a_occ = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / (ch.a_smem + 1024)));
+    // k_anchor exists for 5 resident CTAs per SM (48 registers per thread) and for 4 (64 registers): launch_windows picks
+    // the five-CTA build when this many fit (the run-time modes always take the four-CTA build)
+    ch.a_occ = (int)std::max<size_t>(1, std::min<size_t>(5, (size_t)(220 * 1024) / (ch.a_smem + 1024)));
     // Resident CTAs per SM of the two persistent kernels.  When the chunks of a batch are pipelined over several streams
     // (chunk k+1's anchor kernel next to chunk k's band alignment) the grids are capped so that both fit an SM at once:
     // k_dp 80 registers x 256 threads and ~70 KB of shared memory per CTA, k_anchor 64 x 256 and ~42 KB.
@@ -1447,14 +1450,19 @@ static int launch_windows(PlbContext* c, PlbDeviceBatch* db, const ChunkPlan& ch
     if (ch.ap.n_tiles > 0) {
         const AnchorPlan& ap = ch.ap;
         const bool modes = sp.flank || sp.hla;
-        if ((rc = opt_in_smem(k_anchor<false>, ch.a_smem)) || (modes && (rc = opt_in_smem(k_anchor<true>, ch.a_smem))))
+        const bool five = !modes && ch.a_occ >= 5;
+        const int occ = five ? ch.a_occ : std::min(ch.a_occ, 4);
+        if ((rc = five ? opt_in_smem(k_anchor<false, 5>, ch.a_smem)
+                       : modes ? opt_in_smem(k_anchor<true, 4>, ch.a_smem) : opt_in_smem(k_anchor<false, 4>, ch.a_smem)))
             return rc;
-        const int grid = std::max(1, std::min(ap.n_tiles, c->n_sm * ch.a_occ));
+        const int grid = std::max(1, std::min(ap.n_tiles, c->n_sm * occ));
         if (anchor_after) CU(cudaStreamWaitEvent(st, anchor_after, 0));
         if (modes)
-            k_anchor<true><<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr());
+            k_anchor<true, 4><<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr());
+        else if (five)
+            k_anchor<false, 5><<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr());
         else
-            k_anchor<false><<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr());
+            k_anchor<false, 4><<<grid, kAnchorThreads, ch.a_smem, st>>>(d, ap, q, sp, c->d_ctr());
         if ((rc = launch_check(c, "k_anchor"))) return rc;
         if (anchor_done) CU(cudaEventRecord(anchor_done, st));
         mark(2);

@@ -264,6 +264,9 @@ __device__ __forceinline__ int read_overlap(int ws, int we, int rp, int re) {  /
 }
 
 constexpr int kAnchorThreads = 256;
+// k_anchor is latency- and barrier-bound, so resident warps count more than registers: it is compiled twice, for 5 CTAs per
+// SM (48 registers per thread) where a tile's shared memory lets five fit - BASELINE config 2: 0.98 ms against 1.03 - and
+// for 4 CTAs (64 registers) otherwise (3 CTAs with 80 registers: 1.16 ms).
 
 // One band alignment on the scalar path: any bytes, any length, both run-time modes.  `roff` = bases
 // clipped off the read front (HLA mode), L = (clipped) read length.
@@ -497,8 +500,8 @@ __device__ __noinline__ int light_rest(LightArgs a) {
 }
 
 // kModes = false is the default instance (no flank score, no HLA clipping): the mode logic compiles away.
-template <bool kModes>
-__global__ void __launch_bounds__(kAnchorThreads, 4) k_anchor(DevBatch b, AnchorPlan plan, Queue q, ScoreParams sp_in,
+template <bool kModes, int kMinBlocks>
+__global__ void __launch_bounds__(kAnchorThreads, kMinBlocks) k_anchor(DevBatch b, AnchorPlan plan, Queue q, ScoreParams sp_in,
                                                            Counters* ctr) {
     ScoreParams sp = sp_in;
     if (!kModes) sp.flank = sp.hla = 0;

@@ -14,7 +14,8 @@ from . import _abi
 from .batch import WindowBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplatypus_b200.so")
+# PLB_LIBRARY: another build of the same CUDA library (A/B experiments: tools build variants next to the default one)
+LIB_PATH = os.environ.get("PLB_LIBRARY") or os.path.join(_HERE, "libplatypus_b200.so")
 _lib = None
 
 
