@@ -982,8 +982,9 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
     }
     if (ch.a_smem + 1024 > (size_t)c->smem_optin)
         return set_err(PLB_ERR_SHAPE, "anchor tile needs %zu bytes of shared memory", ch.a_smem);
-    // k_anchor exists for 5 resident CTAs per SM (48 registers per thread) and for 4 (64 registers): launch_windows picks
-    // the five-CTA build when this many fit (the run-time modes always take the four-CTA build)
+    // k_anchor exists for 5 and for 4 resident CTAs per SM (48 / 64 registers per thread): launch_windows picks the
+    // five-CTA build when this many fit (the run-time modes always take the four-CTA build; a 6 x 40-register build
+    // gave the same time as five once the shared memory allowed it, 0.957 vs 0.958 ms)
     ch.a_occ = (int)std::max<size_t>(1, std::min<size_t>(5, (size_t)(220 * 1024) / (ch.a_smem + 1024)));
     // Resident CTAs per SM of the two persistent kernels.  When the chunks of a batch are pipelined over several streams
     // (chunk k+1's anchor kernel next to chunk k's band alignment) the grids are capped so that both fit an SM at once:

@@ -231,10 +231,16 @@ struct AnchorPlan {
 inline void anchor_layout(AnchorPlan& ap, size_t slot_bytes) {
     auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
     size_t o = kRankTabBytes;   // 7-mer key -> dense id: 512 x {presence bits, rank prefix}
-    ap.o_cnt = (uint32_t)o;    o = al(o + (size_t)ap.n_cnt * ap.cnt_words * 4);
     ap.o_fb = (uint32_t)o;     o = al(o + (size_t)ap.max_pairs * 4);
-    ap.o_ul = (uint32_t)o;     o = al(o + (size_t)ap.max_pairs * 4);
-    ap.o_vl = (uint32_t)o;     o = al(o + (size_t)ap.max_pairs * 12);
+    // The per-warp vote arrays of the exact path share their bytes with the two lists of the decision passes: the exact
+    // path runs after the decided pairs have been emitted, when neither list is read any more (a block barrier lies
+    // between), and the next haplotype sub-group rewrites both lists from scratch.
+    const size_t lists = al((size_t)ap.max_pairs * 4) + al((size_t)ap.max_pairs * 12);
+    const size_t votes = al((size_t)ap.n_cnt * ap.cnt_words * 4);
+    ap.o_cnt = (uint32_t)o;
+    ap.o_ul = (uint32_t)o;
+    ap.o_vl = (uint32_t)(o + al((size_t)ap.max_pairs * 4));
+    o += lists > votes ? lists : votes;
     ap.o_rpk = (uint32_t)o;    o = al(o + (size_t)ap.rpk_words * 4);
     ap.o_hpk = (uint32_t)o;    o = al(o + (size_t)ap.hpk_words * 4);
     ap.o_next = (uint32_t)o;   o = al(o + (size_t)ap.next_halfs * 2);
@@ -264,9 +270,10 @@ __device__ __forceinline__ int read_overlap(int ws, int we, int rp, int re) {  /
 }
 
 constexpr int kAnchorThreads = 256;
-// k_anchor is latency- and barrier-bound, so resident warps count more than registers: it is compiled twice, for 5 CTAs per
-// SM (48 registers per thread) where a tile's shared memory lets five fit - BASELINE config 2: 0.98 ms against 1.03 - and
-// for 4 CTAs (64 registers) otherwise (3 CTAs with 80 registers: 1.16 ms).
+// k_anchor is latency- and barrier-bound, so resident warps count more than registers: it is compiled for 5 and for 4 CTAs
+// per SM (48 / 64 registers per thread) and launch_windows takes the five-CTA build where the tile's shared memory lets
+// five fit (BASELINE config 2, measured: 3 CTAs with 80 registers 1.16 ms, 4 x 64 1.03 ms, 5 x 48 0.98 ms, and 0.96 ms
+// once the vote arrays shared their bytes with the decision lists; 6 x 40 the same as five).
 
 // One band alignment on the scalar path: any bytes, any length, both run-time modes.  `roff` = bases
 // clipped off the read front (HLA mode), L = (clipped) read length.
