@@ -978,6 +978,18 @@ static int plan_chunk(PlbContext* c, PlbDeviceBatch* db, const PlbWindowBatch* h
         // heads area splits the haplotype group more often, 1.14 -> 1.31 ms - both measured while trying to fit six CTAs)
         ap.n_cnt = (int)std::max<size_t>(1, std::min<size_t>(nwarps, kAnchorCntBudget / ((size_t)ap.cnt_words * 4)));
         anchor_layout(ap, sizeof(SlotInfo));
+        // ... but one more resident CTA is worth more than the last one or two vote arrays: give up to two of them away
+        // when that is what lets another CTA fit (BASELINE config 3: 44.4 KB per tile, four CTAs; 42.8 KB, five)
+        auto ctas = [](size_t smem) { return std::min<size_t>(5, (size_t)(220 * 1024) / (smem + 1024)); };
+        for (int drop = 1; drop <= 2 && ap.n_cnt - drop >= 6; ++drop) {
+            AnchorPlan t = ap;
+            t.n_cnt = ap.n_cnt - drop;
+            anchor_layout(t, sizeof(SlotInfo));
+            if (ctas(t.smem_bytes) > ctas(ap.smem_bytes)) {
+                ap = t;
+                break;
+            }
+        }
         ch.a_smem = ap.smem_bytes;
     }
     if (ch.a_smem + 1024 > (size_t)c->smem_optin)
