@@ -613,19 +613,36 @@ __global__ void __launch_bounds__(kAnchorThreads, kMinBlocks) k_anchor(DevBatch 
         // ---- the only pass over the raw bases: pack reads and haplotypes 2 bits per base (the
         //      reference's hash digit, calign.pyx:69-74).  7-mer keys, read ids and vote counts all
         //      derive from these words. ----
-        for (int s = tid >> 4; s < ns; s += nthr >> 4) {   // 16 lanes per read: a 150 bp read is 13 words
-            const SlotInfo si = s_slot[s];
-            if ((si.flags & 1) || si.len <= kKmer) continue;
-            const uint8_t* rs = b.read_seq + b.read_seq_off[si.read];
-            const int nw = ((si.len + 15) >> 4) + kPackPadWords;
-            for (int wd = tid & 15; wd < nw; wd += 16) s_rpk[si.poff + wd] = pack16_codes(rs, 16 * wd, si.len);
+        // (the loads of a pass are what this phase waits for, so every pass keeps as many of them in flight as it can: two
+        // reads per 16 lanes at a time, and the haplotypes of the group as ONE index space - one haplotype after the other
+        // left 22 of 256 threads busy per round trip to HBM)
+        for (int s = tid >> 4; s < ns; s += nthr >> 3) {   // 16 lanes per read: a 150 bp read is 13 words
+            const int s2 = s + (nthr >> 4);
+            const SlotInfo sa = s_slot[s];
+            const SlotInfo sb = s_slot[s2 < ns ? s2 : s];
+            const bool va = !((sa.flags & 1) || sa.len <= kKmer);
+            const bool vb = s2 < ns && !((sb.flags & 1) || sb.len <= kKmer);
+            const uint8_t* ra = b.read_seq + b.read_seq_off[sa.read];
+            const uint8_t* rb = b.read_seq + b.read_seq_off[sb.read];
+            const int nwa = va ? ((sa.len + 15) >> 4) + kPackPadWords : 0;
+            const int nwb = vb ? ((sb.len + 15) >> 4) + kPackPadWords : 0;
+            for (int wd = tid & 15; wd < max(nwa, nwb); wd += 16) {
+                const u32 xa = wd < nwa ? pack16_codes(ra, 16 * wd, sa.len) : 0u;
+                const u32 xb = wd < nwb ? pack16_codes(rb, 16 * wd, sb.len) : 0u;
+                if (wd < nwa) s_rpk[sa.poff + wd] = xa;
+                if (wd < nwb) s_rpk[sb.poff + wd] = xb;
+            }
         }
-        for (int g = 0; g < nh; ++g) {
-            const int len = s_hmeta[3 * g];
-            const uint8_t* hap = b.hap_seq + b.hap_seq_off[tile.h0 + g];
-            u32* dst = s_hpk + s_hmeta[3 * g + 2] - kPackPadWords;
-            const int nw = ((len + 15) >> 4) + 2 * kPackPadWords;
-            for (int wd = tid; wd < nw; wd += nthr) dst[wd] = pack16_codes(hap, 16 * (wd - kPackPadWords), len);
+        {
+            const int last = nh - 1;
+            const int total = s_hmeta[3 * last + 2] + ((s_hmeta[3 * last] + 15) >> 4) + kPackPadWords;   // words of the group
+            for (int k = tid; k < total; k += nthr) {
+                int g = 0;
+                while (g < last && k >= s_hmeta[3 * (g + 1) + 2] - kPackPadWords) ++g;
+                const int len = s_hmeta[3 * g];
+                const int wd = k - (s_hmeta[3 * g + 2] - kPackPadWords);
+                s_hpk[k] = pack16_codes(b.hap_seq + b.hap_seq_off[tile.h0 + g], 16 * (wd - kPackPadWords), len);
+            }
         }
         __syncthreads();
         // ---- union table: mark the key of every indexed haplotype position
