@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PLB_ABI_VERSION 5
+#define PLB_ABI_VERSION 6   /* 6: plb_best_score_genotypes_host */
 
 /* status codes */
 #define PLB_OK              0
@@ -453,6 +453,19 @@ int plb_select_haplotypes_host(PlbContext* ctx, const PlbWindowBatch* ref_batch,
  * sums to 0.0, as in the reference.  score_out[n_haps].
  */
 int plb_best_score_haplotypes_host(PlbContext* ctx, const PlbWindowBatch* batch, const PlbOptions* opt, double* score_out);
+
+/*
+ * Replaces computeBestScoreForGenotype (src/cython/variantFilter.pyx:237-283) for arbitrary pairs of haplotypes of a batch -
+ * the second pass of getAllHLAHaplotypesInRegion scores every haplotype as a genotype with the best one (:723-733):
+ * per individual the sum of log(0.5 (exp(s1) + exp(s2))) over every sampleRate-th good read, s = alignSingleRead(read, False),
+ * sampleRate = max(1, (rlen of the first read * nReads // (win_end - win_start)) // target_coverage); best individual
+ * (one without reads is skipped; -1e20 when none has any).  hap1[k], hap2[k]: haplotype indices of the batch, both in
+ * one window.  score_out[n_pairs].  The --HLATyping loop itself (heap of (score, haplotype) tuples, the two passes, the
+ * output order) is host bookkeeping on top of this call and plb_best_score_haplotypes_host:
+ * platypus_b200/compat.py get_all_hla_haplotypes.
+ */
+int plb_best_score_genotypes_host(PlbContext* ctx, const PlbWindowBatch* batch, const PlbOptions* opt, int32_t target_coverage,
+                                  int32_t n_pairs, const int32_t* hap1, const int32_t* hap2, double* score_out);
 
 /*
  * The host-side bookkeeping of plb_select_haplotypes_host alone (trial sets per round, isHaplotypeValid, the heap /

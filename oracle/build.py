@@ -188,7 +188,8 @@ def compute_genotype_call_and_likelihoods(int n_variants, int n_haps, freqs, gl_
 # N1: the haplotype selection loop.  variantFilter.pyx cimports platypusutils (the BAM I/O stack), so - as for N4 -
 # the three functions' own source lines are excerpted at build time into a scratch module between this header and
 # this footer: isHaplotypeValid (src/cython/platypusutils.pyx:735-802), computeBestScoreForHaplotype
-# (src/cython/variantFilter.pyx:212-234), computeBestScoreForGenotype (:237-283) and getFilteredHaplotypes (:377-506).  Nothing of them is
+# (src/cython/variantFilter.pyx:212-234), computeBestScoreForGenotype (:237-283), getFilteredHaplotypes (:377-506) and
+# getAllHLAHaplotypesInRegion (:655-736).  Nothing of them is
 # stored in the repo.
 N1_HEADER = """# cython: language_level=2
 # scratch module: header (declarations) + three functions of the reference, verbatim + forwarding defs
@@ -196,7 +197,7 @@ from __future__ import division
 StandardError = Exception
 import logging
 logger = logging.getLogger("Log")
-from variant cimport Variant
+from variant cimport Variant, FILE_VAR
 from chaplotype cimport Haplotype
 from fastafile cimport FastaFile
 from cgenotype cimport DiploidGenotype
@@ -233,6 +234,15 @@ def is_haplotype_valid(tuple variants):
 
 def compute_best_score_for_haplotype(list readBuffers, Haplotype hap):
     return computeBestScoreForHaplotype(readBuffers, hap)
+
+
+def get_all_hla_haplotypes(bytes chrom, int windowStart, int windowEnd, FastaFile refFile, options, list variants,
+                           Haplotype refHaplotype, list readBuffers):
+    \"\"\"Forwards to getAllHLAHaplotypesInRegion (the --HLATyping selection, variantFilter.pyx:655-736); returns the
+    variant tuple of every haplotype it returns, in order (the list may name a haplotype twice).\"\"\"
+    cdef Haplotype h
+    haps = getAllHLAHaplotypesInRegion(chrom, windowStart, windowEnd, refFile, options, variants, refHaplotype, readBuffers)
+    return [(<Haplotype>h).variants for h in haps]
 """
 
 
@@ -357,7 +367,8 @@ def build_l3_ref(force=False):
             N1_HEADER + excerpt(ulines, "cdef int isHaplotypeValid(") + "\n\n" +
             excerpt(flines, "cdef double computeBestScoreForHaplotype(") + "\n\n" +
             excerpt(flines, "cdef double computeBestScoreForGenotype(") + "\n\n" +
-            excerpt(flines, "cdef list getFilteredHaplotypes(") + N1_FOOTER)
+            excerpt(flines, "cdef list getFilteredHaplotypes(") + "\n\n" +
+            excerpt(flines, "cdef list getAllHLAHaplotypesInRegion(") + N1_FOOTER)
         _run([sys.executable, "-m", "cython", "-2", "-X", "legacy_implicit_noexcept=True", "-I", tmp, "n1_ref.pyx", "-o", "n1_ref.c"],
              cwd=tmp)
         for m in ref_mods + ("l3_ref_wrap", "n4_ref", "n1_ref"):

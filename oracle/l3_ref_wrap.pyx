@@ -411,6 +411,70 @@ def select_haplotypes(bytes genome, int win_start, int win_end, list variants, l
     return out
 
 
+def hla_haplotypes(bytes genome, int win_start, int win_end, list variants, list per_ind_good, int max_read_len=150,
+                   int original_max_haplotypes=50, int coverage_sampling_level=30):
+    """One window through the reference's --HLATyping haplotype selection (src/cython/variantFilter.pyx:655-736
+    getAllHLAHaplotypesInRegion; excerpted into oracle/_ref/n1_ref by oracle/build.py).
+    variants: [(refPos, removed, added, nSupportingReads, varSource)] in the window's order (varSource 2 = FILE_VAR: only
+    those get a haplotype); per_ind_good as for select_haplotypes.
+    Returns dict: haps = [variant index of every returned single-variant haplotype, in order - the list may repeat one],
+    hap_scores / gt_scores = computeBestScoreForHaplotype of every FILE_VAR haplotype and computeBestScoreForGenotype of
+    (best haplotype, it), hap_seqs = their sequences, ref_seq / hap_start as for select_haplotypes."""
+    import n1_ref
+    cdef bytes name = b"chr"
+    cdef MemFasta fa = MemFasta(name, genome)
+    cdef int n_ind = len(per_ind_good)
+    opts = _Options(0, 1, n_ind, 50, 0)
+    opts.rlen = max_read_len
+    opts.maxHaplotypes = 50
+    opts.originalMaxHaplotypes = original_max_haplotypes
+    opts.coverageSamplingLevel = coverage_sampling_level
+    cdef list keep = [], buffers = [], all_arrays = [], vobjs = []
+    cdef bamReadBuffer buf
+    cdef cAlignedRead** arr
+    cdef Haplotype ref_hap, hap
+    cdef int k, n
+    out = {}
+    try:
+        for (p, rem, add, nsup, src) in variants:
+            vobjs.append(Variant(name, p, rem, add, nsup, src))
+        for good in per_ind_good:
+            buf = bamReadBuffer(name, win_start, win_end, opts)
+            buf.sample = b"s"
+            n = len(good)
+            arr = _make_reads(good, keep)
+            all_arrays.append((<size_t>arr, n))
+            for k in range(n):
+                buf.reads.append(arr[k])
+            buf.reads.windowStart = buf.reads.array
+            buf.reads.windowEnd = buf.reads.array + n
+            for ra in (buf.badReads, buf.brokenMates):
+                (<cwindow.ReadArray>ra).windowStart = (<cwindow.ReadArray>ra).array
+                (<cwindow.ReadArray>ra).windowEnd = (<cwindow.ReadArray>ra).array
+            buffers.append(buf)
+        ref_hap = Haplotype(name, win_start, win_end, (), fa, max_read_len, opts)
+        out["ref_seq"] = <bytes>ref_hap.cHaplotypeSequence[:ref_hap.hapLen]
+        out["hap_start"] = ref_hap.startPos - ref_hap.endBufferSize
+        sel = n1_ref.get_all_hla_haplotypes(name, win_start, win_end, fa, opts, vobjs, ref_hap, buffers)
+        index_of = {id(v): i for i, v in enumerate(vobjs)}
+        out["haps"] = [index_of[id(vs[0])] for vs in sel]
+        file_vars = [i for i, v in enumerate(variants) if v[4] == 2]
+        haps = [Haplotype(name, win_start, win_end, (vobjs[i],), fa, max_read_len, opts) for i in file_vars]
+        out["file_vars"] = file_vars
+        out["hap_seqs"] = [<bytes>(<Haplotype>h).cHaplotypeSequence[:(<Haplotype>h).hapLen] for h in haps]
+        hs = [n1_ref.compute_best_score_for_haplotype(buffers, h) for h in haps]
+        out["hap_scores"] = hs
+        if haps:
+            best = max(zip(hs, haps))[1]            # the tuple order the reference's sorted(..., reverse=True)[0] uses
+            out["gt_scores"] = [n1_ref.compute_best_score_for_genotype(buffers, best, h, win_end - win_start,
+                                                                       coverage_sampling_level) for h in haps]
+    finally:
+        buffers = []
+        for (a, n) in all_arrays:
+            _free_reads(<cAlignedRead**><size_t>a, n)
+    return out
+
+
 def stage_reads(list reads, int region_start, int region_end, list windows, dict overrides=None):
     """Read staging (SURVEY 8f N3) through the reference's own bamReadBuffer: every read goes through
     addReadToBuffer -> checkAndTrimRead (src/cython/cwindow.pyx:560-595, 332-481), then

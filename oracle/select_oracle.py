@@ -205,6 +205,105 @@ def best_score_haplotypes(w, var_sets, opt=None):
     return out
 
 
+def best_score_genotype_pairs(w, sets1, sets2, target_coverage=30, opt=None):
+    """computeBestScoreForGenotype(readBuffers, DiploidGenotype(Haplotype(s1), Haplotype(s2)), windowSize, targetCoverage)
+    (variantFilter.pyx:237-283) for every pair of variant sets."""
+    sampled = _sampled(w, target_coverage)
+    uniq = {}
+    for vs in list(sets1) + list(sets2):
+        uniq.setdefault(tuple(v.idx for v in vs), vs)
+    keys = list(uniq)
+    seqs = [build_haplotype(w.ref_seq, w.win_start, w.win_end, w.hap_start, uniq[k]) for k in keys]
+    ll = _loglik(w, sampled, seqs, opt) if seqs else []
+    at = {k: i for i, k in enumerate(keys)}
+    scores = []
+    for a, b in zip(sets1, sets2):
+        ia, ib = at[tuple(v.idx for v in a)], at[tuple(v.idx for v in b)]
+        best = -1e20
+        for i, smp in enumerate(sampled):
+            if not w.good[i]:
+                continue
+            tot = 0.0
+            for t in range(len(smp)):
+                tot += math.log(0.5 * (math.exp(ll[ia][i][t]) + math.exp(ll[ib][i][t])))
+            best = max(best, tot)
+        scores.append(best)
+    return scores
+
+
+class _HapKey:
+    """Order and equality of the reference's Haplotype objects inside its (score, haplotype) tuples
+    (chaplotype.pyx:218-287): same contig and window start here, so the sequence decides."""
+    __slots__ = ("seq", "idx")
+
+    def __init__(self, seq, idx):
+        self.seq, self.idx = seq, idx
+
+    def __lt__(self, o):
+        return self.seq < o.seq
+
+    def __gt__(self, o):
+        return self.seq > o.seq
+
+    def __le__(self, o):
+        return not self.seq > o.seq
+
+    def __ge__(self, o):
+        return not self.seq < o.seq
+
+    def __eq__(self, o):
+        return self.seq == o.seq
+
+    def __ne__(self, o):
+        return self.seq != o.seq
+
+    __hash__ = None
+
+
+def hla_haplotypes(w, sources, original_max_haplotypes=50, target_coverage=30, opt=None, scores=None):
+    """getAllHLAHaplotypesInRegion (variantFilter.pyx:655-736): one haplotype per FILE_VAR variant (sources[i] == 2);
+    up to 150 of them are returned as they are, otherwise a heap keeps the originalMaxHaplotypes - 1 best by
+    computeBestScoreForHaplotype, the best 75 of the heap are output, every haplotype is scored once more as a genotype
+    with the best one, pushed onto the SAME heap, and the best 75 of the heap are output again.
+    Returns the variant index of every returned haplotype, in order.  scores = (hap_scores, gt_score_fn) replaces the
+    oracle's own scoring (gt_score_fn(best position in the FILE_VAR list) -> genotype scores)."""
+    from heapq import heappush, heappushpop
+    file_vars = [i for i, s_ in enumerate(sources) if s_ == 2]
+    n = len(file_vars)
+    max_haps = 150                                    # variantFilter.pyx:699 overrides options.maxHaplotypes
+    if n <= max_haps:
+        return list(file_vars)
+    cap = original_max_haplotypes - 1
+    sets = [(w.vars[i],) for i in file_vars]
+    keys = [_HapKey(build_haplotype(w.ref_seq, w.win_start, w.win_end, w.hap_start, vs), i) for vs, i in zip(sets, file_vars)]
+    hs = scores[0] if scores else best_score_haplotypes(w, sets, opt)
+    heap, out = [], []
+
+    def push(item):
+        if len(heap) < cap:
+            heappush(heap, item)
+        else:
+            heappushpop(heap, item)
+    for k in range(n):
+        push((hs[k], keys[k]))
+    for index, (sc, key) in enumerate(sorted(heap, reverse=True)):
+        if index < max_haps / 2:
+            out.append(key.idx)
+        else:
+            break
+    best = sorted(heap, reverse=True)[0][1]
+    pos = file_vars.index(best.idx)
+    gs = scores[1](pos) if scores else best_score_genotype_pairs(w, [sets[pos]] * n, sets, target_coverage, opt)
+    for k in range(n):
+        push((gs[k], keys[k]))
+    for index, (sc, key) in enumerate(sorted(heap, reverse=True)):
+        if index < max_haps / 2:
+            out.append(key.idx)
+        else:
+            break
+    return out
+
+
 def select_haplotypes(w, max_haplotypes=50, original_max_haplotypes=50, max_variants=8, filter_by_coverage=1,
                       target_coverage=30, opt=None, trace=None, score_fn=None):
     """getFilteredHaplotypes (variantFilter.pyx:377-506).  Returns the variant-index tuple of every haplotype it

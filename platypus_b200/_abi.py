@@ -203,6 +203,8 @@ def declare(lib):
     lib.plb_select_haplotypes_host.restype = C.c_int
     lib.plb_best_score_haplotypes_host.argtypes = [_p, P(PlbWindowBatch), P(PlbOptions), _p]
     lib.plb_best_score_haplotypes_host.restype = C.c_int
+    lib.plb_best_score_genotypes_host.argtypes = [_p, P(PlbWindowBatch), P(PlbOptions), C.c_int32, C.c_int32, _p, _p, _p]
+    lib.plb_best_score_genotypes_host.restype = C.c_int
     lib.plb_select_replay_host.argtypes = [P(PlbWindowBatch), P(PlbVariantSet), P(PlbSelectOptions), TRIAL_SCORE_FN, _p,
                                            P(PlbSelectOut)]
     lib.plb_select_replay_host.restype = C.c_int
@@ -218,7 +220,7 @@ EXPORTED_SYMBOLS = [
     "plb_align_flank_batch_host", "plb_gap_open_host",
     "plb_window_loglik_host", "plb_population_run_host", "plb_site_genotypes_host", "plb_batch_upload", "plb_batch_free",
     "plb_run_device", "plb_last_stats", "plb_set_timing", "plb_kernel_times",
-    "plb_build_haplotypes_host", "plb_select_haplotypes_host", "plb_select_replay_host", "plb_best_score_haplotypes_host",
+    "plb_build_haplotypes_host", "plb_select_haplotypes_host", "plb_select_replay_host", "plb_best_score_haplotypes_host", "plb_best_score_genotypes_host",
     "plb_select_stats", "plb_population_submit", "plb_population_wait", "plb_pack_bases_host", "plb_pack_nibbles_host", "plb_pack_quals_host",
     "plb_stage_reads_host", "plb_window_slices_host", "plb_batch_download", "plb_synth_fill_device",
 ]

@@ -21,6 +21,8 @@ Same method names, argument meaning and error behaviour as the reference's class
 * `Haplotype.alignReads / alignSingleRead` (src/cython/chaplotype.pxd:44-45, chaplotype.pyx:306-384): the
   likelihood array of one individual terminated by the reference's sentinel 999.
 * `BamReadBuffer.setWindowPointers` (src/cython/cwindow.pyx:655-689) over `reads.ReadBuffer`.
+* `getAllHLAHaplotypesInRegion` (src/cython/variantFilter.pyx:655-736): the --HLATyping haplotype selection, two batched
+  scoring calls + the reference's heap bookkeeping.
 
 Nothing here computes a likelihood: every number comes out of `Engine` (libplatypus_b200.so); without the library or a
 GPU construction fails loudly.
@@ -44,12 +46,13 @@ class Variant:
     """The fields of the reference's Variant (src/cython/variant.pyx:109-145) this path reads: refName, refPos, removed,
     added, nSupportingReads and the prior (Variant.calculatePrior, variant.pyx:219-259; candidate generation supplies it -
     the tandem-repeat error model behind it is out of scope).  Equality / hash / order as variant.pyx:282-353."""
-    __slots__ = ("refName", "refPos", "removed", "added", "nSupportingReads", "prior")
+    __slots__ = ("refName", "refPos", "removed", "added", "nSupportingReads", "prior", "varSource")
 
-    def __init__(self, refName, refPos, removed, added, nSupportingReads=1, prior=None):
+    def __init__(self, refName, refPos, removed, added, nSupportingReads=1, prior=None, varSource=1):
         self.refName, self.refPos = refName, int(refPos)
         self.removed, self.added = bytes(removed), bytes(added)
         self.nSupportingReads, self.prior = nSupportingReads, prior
+        self.varSource = varSource       # PLATYPUS_VAR 1, FILE_VAR 2, ASSEMBLER_VAR 4 (variant.pyx:43-45)
 
     def _key(self):
         return (self.refName, self.refPos, self.removed, self.added)
@@ -87,6 +90,7 @@ class Options:
         self.maxHaplotypes, self.maxVariants, self.maxReadLength, self.minPosterior = 50, 8, 150, 5
         self.useEMLikelihoods, self.calculateFlankScore, self.HLATyping, self.nInd, self.verbosity = 0, 0, 0, 1, 2
         self.rlen = 150
+        self.originalMaxHaplotypes, self.coverageSamplingLevel = 50, 30
         for k, v in kw.items():
             setattr(self, k, v)
 
@@ -206,6 +210,24 @@ class Haplotype:
     def __hash__(self):
         return hash(self.haplotypeSequence)
 
+    def _order(self):           # chaplotype.pyx:225-264: contig, window start, then the mutated sequence
+        return (self.refName, self.startPos, self.haplotypeSequence)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __lt__(self, other):
+        return self._order() < other._order()
+
+    def __gt__(self, other):
+        return self._order() > other._order()
+
+    def __le__(self, other):
+        return not self._order() > other._order()
+
+    def __ge__(self, other):
+        return not self._order() < other._order()
+
     # ---- scoring (seam S2) -------------------------------------------------------------------------------
     def alignReads(self, individualIndex, reads, badReads, brokenReads, useMapQualCap=0):
         """Haplotype.alignReads (chaplotype.pyx:306-377): log-likelihood of every read of one individual - good, then
@@ -231,6 +253,65 @@ class Haplotype:
             return float(self.alignReads(-2, [], [], [theRead], useMapQualCap)[0])
         finally:
             self.lastIndividualIndex, self.likelihoodCache = saved
+
+
+PLATYPUS_VAR, FILE_VAR, ASSEMBLER_VAR = 1, 2, 4      # variant.pyx:43-45
+
+
+def getAllHLAHaplotypesInRegion(chrom, windowStart, windowEnd, refFile, options, variants, refHaplotype, readBuffers,
+                                engine=None):
+    """getAllHLAHaplotypesInRegion (src/cython/variantFilter.pyx:655-736), the --HLATyping haplotype selection, with the
+    reference's argument list (+ the engine): one haplotype per FILE_VAR variant; up to 150 of them are returned as they
+    are.  Beyond that a heap keeps the originalMaxHaplotypes - 1 best (score, haplotype) tuples - first scored by
+    computeBestScoreForHaplotype, the best 75 of the heap are output, then every haplotype is scored once more as a genotype
+    with the best one (computeBestScoreForGenotype) and pushed onto the SAME heap, and the best 75 are output again (so the
+    list may name a haplotype twice, as the reference's does).  The scores come from the GPU in two calls for the whole
+    window (plb_best_score_haplotypes_host, plb_best_score_genotypes_host) instead of one alignSingleRead per read and
+    haplotype; the heap bookkeeping is the reference's own, on the same tuple order (ties by Haplotype comparison)."""
+    from heapq import heappush, heappushpop
+    engine = engine or refHaplotype.engine
+    maxReadLength = options.rlen
+    allHaps = [Haplotype(chrom, windowStart, windowEnd, (v,), refFile, maxReadLength, options, engine)
+               for v in variants if v.varSource == FILE_VAR]
+    nHaps = len(allHaps)
+    maxHaplotypes = 150                                # variantFilter.pyx:699
+    if nHaps <= maxHaplotypes:
+        return allHaps
+    if engine is None:
+        raise PlatypusError("getAllHLAHaplotypesInRegion needs an engine (there is no CPU path)")
+    originalMaxHaplotypes = options.originalMaxHaplotypes - 1
+    for k in range(0, nHaps, 64):                      # a variant mask holds 64 variants per build call
+        Haplotype.build_sequences(allHaps[k:k + 64], engine)
+    per_ind = [([_as_read(r) for r in rb.reads], [], []) for rb in readBuffers]
+    win = Window(int(windowStart), int(windowEnd), allHaps[0].hapStart, [h.haplotypeSequence for h in allHaps], per_ind)
+    batch = WindowBatch.from_windows([win], len(per_ind), dedupe_reads=False)
+    opt = options.plb_options()
+    hapsByBestScore, outputHaps = [], []
+
+    def push(item):
+        if len(hapsByBestScore) < originalMaxHaplotypes:
+            heappush(hapsByBestScore, item)
+        else:
+            heappushpop(hapsByBestScore, item)
+    scores = engine.best_score_haplotypes(batch, opt=opt)
+    for k in range(nHaps):
+        push((float(scores[k]), allHaps[k]))
+    for index, (score, thisHap) in enumerate(sorted(hapsByBestScore, reverse=True)):
+        if index < maxHaplotypes / 2:
+            outputHaps.append(thisHap)
+        else:
+            break
+    bestHap = sorted(hapsByBestScore, reverse=True)[0][1]
+    best = next(k for k, h in enumerate(allHaps) if h is bestHap)
+    scores = engine.best_score_genotypes(batch, [best] * nHaps, list(range(nHaps)), options.coverageSamplingLevel, opt=opt)
+    for k in range(nHaps):
+        push((float(scores[k]), allHaps[k]))
+    for index, (score, thisHap) in enumerate(sorted(hapsByBestScore, reverse=True)):
+        if index < maxHaplotypes / 2:
+            outputHaps.append(thisHap)
+        else:
+            break
+    return outputHaps
 
 
 def generateAllGenotypesFromHaplotypeList(haplotypes):

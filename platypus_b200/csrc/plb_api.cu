@@ -184,6 +184,11 @@ extern "C" int plb_context_create(int device, void* stream, PlbContext** out) {
                        e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     if (device < 0 || device >= n) return set_err(PLB_ERR_ARG, "device %d out of range (have %d)", device, n);
     CU(cudaSetDevice(device));
+    {   // log(1 - exp(mLTOT * mapq)) with the host's libm (see c_map_right); mapq 0 gives log(0) = -inf, as in the reference
+        double right[256];
+        for (int m = 0; m < 256; ++m) right[m] = log(1.0 - exp(kMLTOT * (double)m));
+        CU(cudaMemcpyToSymbol(c_map_right, right, sizeof right));
+    }
     PlbContext* c = new PlbContext();
     c->device = device;
     c->launches = 0;

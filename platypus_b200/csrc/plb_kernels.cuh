@@ -26,6 +26,11 @@ constexpr int kKmer = 7;
 constexpr int kHashSize = 16384;
 constexpr int kScoreNone = 1000000;
 constexpr double kMLTOT = -0.23025850929940459;
+// log(1 - exp(mLTOT * mapq)) for every mapping quality (chaplotype.pyx:622), filled by plb_context_create with the HOST's
+// libm - the reference's own values on that machine - so that a per-read log-likelihood mLTOT * score + this (two
+// separately rounded operations, as the reference's C code performs them: no FMA) is the reference's double bit for bit.
+// Sums of them taken in read order are then exact too, which is what keeps exactly tied haplotype scores tied.
+__constant__ double c_map_right[256];
 constexpr double kLog10E = 0.43429448190325182;
 constexpr double kLogHalf = -0.69314718055994529;
 constexpr int kRankWords = kHashSize / 32;            // one presence bit per possible 7-mer key
@@ -1270,7 +1275,7 @@ __global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScorePa
                 my_exact = 1;
             }
             ds.flags |= (int)b.read_mapq[r] << 8;
-            ds.ll_right = log(1.0 - exp(kMLTOT * (double)b.read_mapq[r]));
+            ds.ll_right = c_map_right[b.read_mapq[r]];
             ds.poff = 0;
             s_slot[s] = ds;
         }
@@ -1499,10 +1504,10 @@ __global__ void __launch_bounds__(NTHR, 3) k_dp(DevBatch b, DpPlan plan, ScorePa
                 // scores above 100 are flattened: mLTOT * (99 + (score - 99)^0.5 / 0.5)
                 const double cap = kMLTOT * (double)((ds.flags >> 8) & 0xFF);
                 const double v = sc > 100 ? kMLTOT * (99.0 + sqrt((double)sc - 99.0) / 0.5)
-                                          : kMLTOT * (double)sc + ds.ll_right;
+                                          : __dadd_rn(__dmul_rn(kMLTOT, (double)sc), ds.ll_right);
                 ll = v > cap ? v : cap;
             } else {
-                const double v = kMLTOT * (double)sc + ds.ll_right;
+                const double v = __dadd_rn(__dmul_rn(kMLTOT, (double)sc), ds.ll_right);   // not fused, see c_map_right
                 ll = v > -300.0 ? v : -300.0;
             }
             if (ll_out) ll_out[pair] = ll;

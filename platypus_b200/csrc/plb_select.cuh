@@ -182,6 +182,38 @@ __global__ void __launch_bounds__(128) k_hap_score(DevBatch b, const double* __r
     if (lane == 0) out[h] = best;
 }
 
+// computeBestScoreForGenotype (variantFilter.pyx:237-283) for arbitrary pairs of haplotypes of one window: one warp per
+// pair, the batch's slots are the sampled good reads.  Same arithmetic and order of additions as k_trial_score.
+__global__ void __launch_bounds__(128) k_pair_score(DevBatch b, const double* __restrict__ ll, int n_pairs,
+                                                    const int32_t* __restrict__ hap1, const int32_t* __restrict__ hap2,
+                                                    double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= n_pairs) return;
+    const int h1 = hap1[p], h2 = hap2[p];
+    const int w = b.hap_win[h1];
+    const int l1h = h1 - b.win_hap_off[w], l2h = h2 - b.win_hap_off[w];
+    const int nInd = b.n_individuals;
+    double best = -1e20;
+    for (int i = 0; i < nInd; ++i) {
+        const int64_t wi = (int64_t)w * nInd + i;
+        const int T = (int)(b.wi_slot_off[wi + 1] - b.wi_slot_off[wi]);
+        if (T == 0) continue;   // readBegin == readEnd
+        const double* l1 = ll + b.ll_off[wi] + (int64_t)l1h * T;
+        const double* l2 = ll + b.ll_off[wi] + (int64_t)l2h * T;
+        double tot = 0.0;
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int t = t0 + lane;
+            double term = 0.0;
+            if (t < T) term = log(0.5 * (exp(l1[t]) + exp(l2[t])));
+            const int n = min(32, T - t0);
+            for (int k = 0; k < n; ++k) tot += __shfl_sync(0xffffffffu, term, k);
+        }
+        if (tot > best) best = tot;
+    }
+    if (lane == 0) out[p] = best;
+}
+
 }  // namespace plb
 
 namespace {
@@ -1317,5 +1349,90 @@ extern "C" int plb_best_score_haplotypes_host(PlbContext* c, const PlbWindowBatc
     if (rc) return rc;
     if (e != cudaSuccess || e2 != cudaSuccess)
         return set_err(PLB_ERR_CUDA, "plb_best_score_haplotypes_host: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return PLB_OK;
+}
+
+extern "C" int plb_best_score_genotypes_host(PlbContext* c, const PlbWindowBatch* hb, const PlbOptions* opt_in,
+                                             int32_t target_coverage, int32_t n_pairs, const int32_t* hap1,
+                                             const int32_t* hap2, double* score_out) {
+    if (!c || !hb || !score_out || (n_pairs > 0 && (!hap1 || !hap2))) return set_err(PLB_ERR_ARG, "NULL argument");
+    if (target_coverage <= 0) return set_err(PLB_ERR_ARG, "target_coverage must be positive (variantFilter.pyx:251)");
+    int rc = check_options(opt_in);
+    if (rc) return rc;
+    if ((rc = require_idle(c, "plb_best_score_genotypes_host"))) return rc;
+    PlbOptions opt = *opt_in;
+    opt.use_mapq_cap = 0;   // alignSingleRead(read, False)
+    const int W = hb->n_windows, nInd = hb->n_individuals;
+    if (n_pairs <= 0) return PLB_OK;
+    if (W <= 0 || hb->n_haps <= 0) return set_err(PLB_ERR_ARG, "pairs given for an empty batch");
+    if (hb->seq_format != PLB_SEQ_ASCII || hb->qual_bits != 0)
+        return set_err(PLB_ERR_UNSUPPORTED, "plb_best_score_genotypes_host takes byte-per-base batches");
+    if ((rc = plb_validate(hb, &opt, 0))) return rc;
+    // a pair names two haplotypes of ONE window
+    std::vector<int32_t> hap_win((size_t)hb->n_haps);
+    for (int w = 0; w < W; ++w)
+        for (int h = hb->win_hap_off[w]; h < hb->win_hap_off[w + 1]; ++h) hap_win[(size_t)h] = w;
+    for (int p = 0; p < n_pairs; ++p) {
+        if (hap1[p] < 0 || hap1[p] >= hb->n_haps || hap2[p] < 0 || hap2[p] >= hb->n_haps)
+            return set_err(PLB_ERR_ARG, "pair %d: haplotype index out of range", p);
+        if (hap_win[(size_t)hap1[p]] != hap_win[(size_t)hap2[p]])
+            return set_err(PLB_ERR_ARG, "pair %d: the two haplotypes belong to different windows", p);
+    }
+    CU(cudaSetDevice(c->device));
+    // the sampled good reads of every (window, individual) (variantFilter.pyx:253-277: every sampleRate-th one), as
+    // broken mates: a bare alignReadToHaplotype per read
+    const int64_t nwi = (int64_t)W * nInd;
+    std::vector<int64_t> slot_off((size_t)nwi + 1, 0);
+    std::vector<int32_t> slots, zero((size_t)nwi, 0);
+    for (int w = 0; w < W; ++w) {
+        const int64_t size = (int64_t)hb->win_end[w] - hb->win_start[w];
+        if (size <= 0) return set_err(PLB_ERR_ARG, "window %d: empty interval", w);
+        for (int i = 0; i < nInd; ++i) {
+            const int64_t wi = (int64_t)w * nInd + i;
+            const int64_t b0 = hb->wi_slot_off[wi];
+            const int n_good = hb->wi_n_good[wi];
+            if (n_good > 0) {
+                const int r_first = hb->slot_read[b0];
+                const int64_t rlen = hb->read_seq_off[r_first + 1] - hb->read_seq_off[r_first];
+                const int rate = (int)std::max<int64_t>(1, rlen * n_good / size / target_coverage);
+                for (int t = 0; t < n_good; t += rate) slots.push_back(hb->slot_read[b0 + t]);
+            }
+            slot_off[(size_t)wi + 1] = (int64_t)slots.size();
+        }
+    }
+    PlbWindowBatch g = *hb;
+    g.n_slots = slot_off[(size_t)nwi];
+    g.wi_slot_off = slot_off.data();
+    g.slot_read = slots.data();
+    g.wi_n_good = zero.data();
+    g.wi_n_bad = zero.data();
+    g.max_variants = 0;
+    g.win_n_var = nullptr;
+    g.hap_var_mask = nullptr;
+    g.var_prior = nullptr;
+    PlbDeviceBatch* db = nullptr;
+    if ((rc = plb_batch_upload(c, &g, &db))) return rc;
+    cudaStream_t st = c->stream;
+    Block out{nullptr, 0};
+    const bool modes = opt.calc_flank_score != 0;
+    const size_t o_h1 = ((size_t)n_pairs * 8 + 255) & ~(size_t)255, o_h2 = o_h1 + (((size_t)n_pairs * 4 + 255) & ~(size_t)255);
+    rc = block_get(c, o_h2 + (size_t)n_pairs * 4 + 256, &out);
+    cudaError_t e = cudaSuccess;
+    if (!rc) e = cudaMemcpyAsync((uint8_t*)out.p + o_h1, hap1, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st);
+    if (!rc && e == cudaSuccess) e = cudaMemcpyAsync((uint8_t*)out.p + o_h2, hap2, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st);
+    if (!rc && modes) rc = mode_queues(c, db, false);
+    if (!rc) rc = launch_windows(c, db, db->chunks[0], &opt, nullptr, nullptr, st, false, modes ? db->mq : db->q);
+    if (!rc && e == cudaSuccess) {
+        k_pair_score<<<(n_pairs + 3) / 4, 128, 0, st>>>(db->d, db->ll_scratch, n_pairs, (const int32_t*)((uint8_t*)out.p + o_h1),
+                                                        (const int32_t*)((uint8_t*)out.p + o_h2), (double*)out.p);
+        rc = launch_check(c, "k_pair_score");
+    }
+    if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(score_out, out.p, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost, st);
+    const cudaError_t e2 = cudaStreamSynchronize(st);
+    if (out.p) block_put(c, out);
+    plb_batch_free(c, db);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess)
+        return set_err(PLB_ERR_CUDA, "plb_best_score_genotypes_host: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
     return PLB_OK;
 }

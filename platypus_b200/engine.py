@@ -334,6 +334,20 @@ class Engine:
         _check(self.lib, self.lib.plb_best_score_haplotypes_host(self.ctx, C.byref(s), C.byref(opt), _abi.ptr(out)))
         return out[:batch.n_haps]
 
+    def best_score_genotypes(self, batch: WindowBatch, hap1, hap2, target_coverage=30, opt=None):
+        """computeBestScoreForGenotype for pairs of haplotypes of the batch (reference: src/cython/variantFilter.pyx:237-283;
+        the second pass of getAllHLAHaplotypesInRegion, :723-733).  hap1 / hap2: haplotype indices, pairwise in one window.
+        Returns [n_pairs] float64."""
+        opt = opt or _abi.PlbOptions.default()
+        hap1 = np.ascontiguousarray(hap1, np.int32)
+        hap2 = np.ascontiguousarray(hap2, np.int32)
+        assert hap1.shape == hap2.shape and hap1.ndim == 1
+        out = np.zeros(max(len(hap1), 1), np.float64)
+        s = batch.as_struct()
+        _check(self.lib, self.lib.plb_best_score_genotypes_host(self.ctx, C.byref(s), C.byref(opt), int(target_coverage),
+                                                                len(hap1), _abi.ptr(hap1), _abi.ptr(hap2), _abi.ptr(out)))
+        return out[:len(hap1)]
+
     def call_windows(self, ref_batch: WindowBatch, variants, sel=None, opt=None, var_prior=None):
         """callVariantsInWindow for a batch of windows (reference: src/cython/variantcaller.pyx:74-141): haplotype
         selection (getHaplotypesInWindow), haplotype construction, then Population.setup + call on

@@ -384,12 +384,14 @@ def l3_golden_cases(golden_dir):
         yield b, {m: (g["c%d_m%d%d_ll" % (seed, m[0], m[1])], g["c%d_m%d%d_geno" % (seed, m[0], m[1])]) for m in L3_MODES}
 
 
-def check_l3(ll, pop, want_ll, want_geno, rtol=1e-9):
+def check_l3(ll, pop, want_ll, want_geno, rtol=1e-9, exact_ll=False):
     """Per-read log-likelihoods, genotype log-likelihoods (ours are stored rescaled: log(gl) + gl_log_max), GOF and
     hapLike of ONE single-individual window against the reference's values."""
     import numpy as np
     H, T = want_ll.shape
     np.testing.assert_allclose(np.asarray(ll).reshape(H, T), want_ll, rtol=1e-12, atol=0)
+    if exact_ll:   # mLTOT * score + log(1 - exp(mLTOT * mapq)): the same two roundings and the same libm value
+        assert np.array_equal(np.asarray(ll).reshape(H, T), want_ll)
     G = H * (H + 1) // 2
     logl = np.log(pop["gl"][0, 0, :G]) + pop["gl_log_max"][0, 0]
     np.testing.assert_allclose(logl, want_geno[:, 0], rtol=rtol, atol=1e-9)
@@ -622,6 +624,117 @@ def n1_batch(cases, ref_seqs, hap_starts):
         per += [([], [], [])] * (n_ind - len(per))
         wins.append(Window(c["win_start"], c["win_end"], hs, [ref], per))
     return WindowBatch.from_windows(wins, n_ind, dedupe_reads=False), VariantSet.from_lists([c["variants"] for c in cases])
+
+
+def hla_window_case(seed):
+    """One window for getAllHLAHaplotypesInRegion (variantFilter.pyx:655-736): a few hundred known alleles (varSource
+    FILE_VAR = 2; SNPs - up to three per position -, short insertions and deletions, pairs of insertions into a homopolymer
+    that spell the SAME haplotype, and some read-derived variants, varSource 1, which get no haplotype), 1-2 individuals
+    with 20-70 reads drawn from two true haplotypes.  Seeds divisible by 5 stay at or below the 150 haplotypes the
+    function returns unfiltered."""
+    rng = random.Random(7000003 * seed + 29)
+    genome = bytearray(_rand_seq(rng, 3000))
+    ws = 1300
+    we = ws + rng.randint(220, 420)
+    for _ in range(3):   # homopolymer runs: insertions of the run's base at two anchors give equal sequences
+        a = rng.randint(ws + 5, we - 20)
+        genome[a:a + rng.randint(4, 7)] = bytes([rng.choice(ACGT)]) * 7
+    genome = bytes(genome[:3000])
+    max_read_len = rng.choice([100, 150])
+    target = rng.randint(60, 150) if seed % 5 == 0 else rng.randint(151, 330)
+    var = set()
+    while len(var) < target:
+        p = rng.randint(ws, we - 4)
+        kind = rng.random()
+        if kind < 0.72:
+            alt = rng.choice([c for c in ACGT if c != genome[p]])
+            var.add((p, genome[p:p + 1], bytes([alt])))
+        elif kind < 0.84:
+            var.add((p, b"", _rand_seq(rng, rng.randint(1, 3))))
+        elif kind < 0.92:
+            var.add((p, b"", genome[p + 1:p + 2]))          # often inside a run: same sequence as its neighbour's insertion
+        else:
+            k = rng.randint(1, 4)
+            var.add((p, genome[p:p + k], b""))
+
+    def vtype(v):
+        nr, na = len(v[1]), len(v[2])
+        return (0 if na == 1 else 1) if nr == na else 2 if nr == 0 else 3 if na == 0 else 4
+    # (a set of tuples holding bytes iterates in hash order, which changes from process to process: sort on everything)
+    uniq = sorted(var, key=lambda v: (v[0], vtype(v), len(v[1]), v[1], v[2]))
+    variants = [(p, r, a, rng.choice([1, 2, 3, 5, 8]), 1 if rng.random() < 0.06 else 2) for (p, r, a) in uniq]
+    flank = min(2 * max_read_len, 500)
+    lo = max(0, ws - flank)
+
+    def apply(idxs):
+        out, cur = bytearray(), lo
+        for i in idxs:
+            p, rem, add = variants[i][:3]
+            if p < cur:
+                continue
+            if len(rem) == len(add):
+                out += genome[cur:p] + add
+                cur = p + len(rem)
+            elif not rem:
+                out += genome[cur:p + 1] + add
+                cur = p + 1
+            else:
+                out += genome[cur:p + 1]
+                cur = p + 1 + len(rem)
+        out += genome[cur:we + flank]
+        return bytes(out)
+    truth = [apply(sorted(rng.sample(range(len(variants)), rng.randint(1, 4)))) for _ in range(2)]
+    per_ind = []
+    for i in range(rng.choice([1, 2])):
+        reads = []
+        for _ in range(rng.choice([20, 40, 70])):
+            L = max_read_len if rng.random() < 0.8 else rng.choice([50, 75])
+            src = rng.choice(truth)
+            a = max(0, ws - lo - L + 10)
+            b = max(a, min(len(src) - L - 16, we - lo - 10))
+            idx = rng.randint(a, b)
+            seq = mutate(rng, src[idx:], L, n_rate=0.001)
+            qual = bytes(rng.randint(2, 41) for _ in range(L))
+            p = lo + idx + rng.choice([0, 0, 0, rng.randint(-4, 4)])
+            reads.append((seq, qual, p, p + L, rng.choice([60, 60, 60, 40, 23]), 512 if rng.random() < 0.02 else 0))
+        reads.sort(key=lambda t: t[2])
+        per_ind.append(reads)
+    return dict(genome=genome, win_start=ws, win_end=we, variants=variants, per_ind=per_ind, max_read_len=max_read_len,
+                opts=dict(original_max_haplotypes=rng.choice([20, 50, 50, 90]), coverage_sampling_level=rng.choice([5, 30])))
+
+
+def hla_golden_cases(golden_dir):
+    """The committed reference outputs for hla_window_case(seed) (tests/golden/make_n1_hla_fixture.py)."""
+    z = np.load(os.path.join(golden_dir, "n1_hla_ref.npz"), allow_pickle=False)
+    out = []
+    for k, seed in enumerate(z["seeds"]):
+        out.append(dict(seed=int(seed), haps=[int(i) for i in z["haps"][z["hap_off"][k]:z["hap_off"][k + 1]]],
+                        hap_score=z["hap_score"][z["fv_off"][k]:z["fv_off"][k + 1]],
+                        gt_score=z["gt_score"][z["fv_off"][k]:z["fv_off"][k + 1]],
+                        ref_seq=z["ref_seq"][z["ref_off"][k]:z["ref_off"][k + 1]].tobytes(), hap_start=int(z["hap_start"][k])))
+    return out
+
+
+class MemFasta:
+    """getSequence(refName, begin, end) over a bytes genome (half-open, clamped like fastafile.pyx:173-207)."""
+
+    def __init__(self, genome):
+        self.genome = genome
+
+    def getSequence(self, name, begin, end):
+        return self.genome[max(0, begin):min(len(self.genome), end)]
+
+
+def hla_compat_inputs(case, engine):
+    """(variants, refHaplotype, readBuffers, options) of an hla_window_case as platypus_b200.compat objects."""
+    from platypus_b200 import compat
+    opts = compat.Options(rlen=case["max_read_len"], HLATyping=0, originalMaxHaplotypes=case["opts"]["original_max_haplotypes"],
+                          coverageSamplingLevel=case["opts"]["coverage_sampling_level"])
+    fa = MemFasta(case["genome"])
+    variants = [compat.Variant(b"chr", p, rem, add, n, None, src) for (p, rem, add, n, src) in case["variants"]]
+    ref_hap = compat.Haplotype(b"chr", case["win_start"], case["win_end"], (), fa, case["max_read_len"], opts, engine)
+    bufs = [compat.WindowReads(reads=ind) for ind in case["per_ind"]]
+    return fa, variants, ref_hap, bufs, opts
 
 
 def masks_of(sets):

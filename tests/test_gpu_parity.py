@@ -483,7 +483,9 @@ def test_l3_golden_ref(engine, golden_dir):
     for b, want in cases.l3_golden_cases(golden_dir):
         for (hla, flank), (w_ll, w_geno) in want.items():
             got = engine.population_run(b, opt=_abi.PlbOptions.default(use_mapq_cap=hla, calc_flank_score=flank), want_ll=True)
-            cases.check_l3(got["ll"], got, w_ll, w_geno)
+            # without the map-quality cap a log-likelihood is two IEEE operations on the integer score and a per-mapq
+            # constant taken from the host's libm: bit-identical to the reference's double
+            cases.check_l3(got["ll"], got, w_ll, w_geno, exact_ll=(hla == 0))
             n += w_ll.size
     assert n > 9000
 
@@ -1043,6 +1045,47 @@ def test_device_generated_windows_roundtrip_and_parity(engine, oracle):
     assert np.array_equal(b2.read_seq[:2 * n], a.read_seq[2 * n:4 * n]) and np.array_equal(b2.read_qual[:2 * n], a.read_qual[2 * n:4 * n])
     assert np.array_equal(b2.hap_seq[:2 * 8 * 250], a.hap_seq[2 * 8 * 250:4 * 8 * 250])
     assert np.array_equal(b2.read_pos, a.read_pos[2 * 60:4 * 60]) and np.array_equal(b2.hap_var_mask, a.hap_var_mask[16:32])
+
+
+def test_n1_hla_selection_golden_ref(engine, golden_dir):
+    """The --HLATyping haplotype selection (getAllHLAHaplotypesInRegion, variantFilter.pyx:655-736) through
+    compat.getAllHLAHaplotypesInRegion: haplotype construction (plb_build_haplotypes_host), both scoring passes
+    (plb_best_score_haplotypes_host, plb_best_score_genotypes_host) on the GPU, the heap bookkeeping on the host.  The
+    returned list equals the one the REFERENCE'S OWN function returned for the same window (tests/golden/n1_hla_ref.npz:
+    57-311 known alleles per window, repeated haplotypes, equal-sequence haplotypes), and both score arrays are the
+    reference's to 1e-9."""
+    from platypus_b200 import compat
+    from platypus_b200.batch import Window
+    n_filtered = 0
+    for g in cases.hla_golden_cases(golden_dir):
+        c = cases.hla_window_case(g["seed"])
+        fa, variants, ref_hap, bufs, opts = cases.hla_compat_inputs(c, engine)
+        haps = compat.getAllHLAHaplotypesInRegion(b"chr", c["win_start"], c["win_end"], fa, opts, variants, ref_hap, bufs)
+        assert [variants.index(h.variants[0]) for h in haps] == g["haps"], g["seed"]
+        fv = [v for v in variants if v.varSource == compat.FILE_VAR]
+        n_filtered += len(fv) > 150
+        if g["seed"] % 4 == 1:      # the two score arrays themselves
+            hl = [compat.Haplotype(b"chr", c["win_start"], c["win_end"], (v,), fa, c["max_read_len"], opts, engine) for v in fv]
+            for k in range(0, len(hl), 64):
+                compat.Haplotype.build_sequences(hl[k:k + 64], engine)
+            per_ind = [([compat._as_read(r) for r in rb.reads], [], []) for rb in bufs]
+            b = WindowBatch.from_windows([Window(c["win_start"], c["win_end"], hl[0].hapStart, [h.haplotypeSequence for h in hl],
+                                                 per_ind)], len(per_ind), dedupe_reads=False)
+            hs = engine.best_score_haplotypes(b)
+            np.testing.assert_allclose(hs, g["hap_score"], rtol=1e-9, atol=0)
+            best = max(range(len(hl)), key=lambda k: (hs[k], hl[k].haplotypeSequence))
+            gs = engine.best_score_genotypes(b, [best] * len(hl), list(range(len(hl))), c["opts"]["coverage_sampling_level"])
+            np.testing.assert_allclose(gs, g["gt_score"], rtol=1e-9, atol=0)
+    assert n_filtered >= 15
+    # argument checks of the new entry point
+    from platypus_b200.engine import PlbError
+    b = cases.edge_batch(seed=3)
+    with pytest.raises(PlbError) as e:
+        engine.best_score_genotypes(b, [0], [b.n_haps - 1], 30)        # haplotypes of two windows
+    assert e.value.code == _abi.PLB_ERR_ARG
+    with pytest.raises(PlbError):
+        engine.best_score_genotypes(b, [0], [1], 0)                    # targetCoverage must be positive
+    assert len(engine.best_score_genotypes(b, [], [], 30)) == 0
 
 
 @pytest.mark.parametrize("n_windows", [2300, 1974])

@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_abi.EXPORTED_SYMBOLS), declared ^ set(_abi.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.plb_abi_version() == 5
+    assert lib.plb_abi_version() == 6
 
 
 def test_no_gpu_fails_loudly():

@@ -654,3 +654,78 @@ def test_golden_l3_population_many_samples(oracle, golden_dir):
         cases.check_l3_pop_many(arrs, want)
         n += b.n_individuals
     assert n == 4600
+
+
+# ---- the --HLATyping haplotype selection (variantFilter.pyx:655-736) ---------------------------------------------------
+def _hla_window(case, g):
+    c4 = dict(case)
+    c4["variants"] = [v[:4] for v in case["variants"]]
+    return cases.n1_select_window(c4, g["ref_seq"], g["hap_start"])
+
+
+def test_hla_selection_oracle_vs_reference_golden(golden_dir):
+    """The restated getAllHLAHaplotypesInRegion (oracle/select_oracle.hla_haplotypes: one haplotype per FILE_VAR variant,
+    the 150-haplotype short cut, the shared heap of (score, haplotype) tuples over both passes, repeated output) returns
+    the reference's own list on every fixture window, and its two scoring functions give the reference's numbers."""
+    from oracle import select_oracle as S
+    n_filtered = 0
+    for g in cases.hla_golden_cases(golden_dir):
+        c = cases.hla_window_case(g["seed"])
+        w = _hla_window(c, g)
+        src = [v[4] for v in c["variants"]]
+        got = S.hla_haplotypes(w, src, c["opts"]["original_max_haplotypes"], c["opts"]["coverage_sampling_level"])
+        assert got == g["haps"], g["seed"]
+        fv = [i for i, s_ in enumerate(src) if s_ == 2]
+        n_filtered += len(fv) > 150
+        if g["seed"] % 6 == 1:      # the scores themselves (a few windows: every one costs ~300 haplotypes x 100 reads)
+            sets = [(w.vars[i],) for i in fv]
+            hs = S.best_score_haplotypes(w, sets)
+            np.testing.assert_allclose(hs, g["hap_score"], rtol=1e-12, atol=0)
+            best = max(zip(hs, [S._HapKey(S.build_haplotype(w.ref_seq, w.win_start, w.win_end, w.hap_start, vs), i)
+                                for vs, i in zip(sets, fv)]), key=lambda t: (t[0], t[1].seq))[1]
+            pos = fv.index(best.idx)
+            gs = S.best_score_genotype_pairs(w, [sets[pos]] * len(sets), sets, c["opts"]["coverage_sampling_level"])
+            np.testing.assert_allclose(gs, g["gt_score"], rtol=1e-12, atol=0)
+    assert n_filtered >= 15
+
+
+class _OracleScoringEngine:
+    """Stands in for Engine in the CPU test of the HOST logic of compat.getAllHLAHaplotypesInRegion: sequences and scores
+    come from the fixture / the oracle, so what is tested is the bookkeeping above the C ABI (no product path uses it)."""
+
+    def __init__(self, window, fixture, file_vars):
+        self.w, self.g, self.fv = window, fixture, file_vars
+
+    def build_haplotypes(self, ref_batch, vset, hap_win, hap_mask):
+        from oracle import select_oracle as S
+        out = []
+        for m in hap_mask:
+            k = int(m).bit_length() - 1
+            p, nrem = int(vset.var_pos[k]), int(vset.var_n_removed[k])
+            add = bytes(vset.var_added[int(vset.var_added_off[k]):int(vset.var_added_off[k + 1])])
+            v = next(v for v in self.w.vars if v.pos == p and len(v.removed) == nrem and v.added == add)
+            out.append(S.build_haplotype(self.w.ref_seq, self.w.win_start, self.w.win_end, self.w.hap_start, (v,)))
+        return out
+
+    def best_score_haplotypes(self, batch, opt=None):
+        return np.asarray(self.g["hap_score"])
+
+    def best_score_genotypes(self, batch, hap1, hap2, target_coverage=30, opt=None):
+        self.best = int(hap1[0])
+        return np.asarray(self.g["gt_score"])
+
+
+def test_compat_hla_selection_host_logic(golden_dir):
+    """compat.getAllHLAHaplotypesInRegion - the reference's argument list, Haplotype ordering inside the (score, haplotype)
+    tuples, the heap shared by both passes - returns the reference's list when the scores are the reference's."""
+    from platypus_b200 import compat
+    for g in cases.hla_golden_cases(golden_dir):
+        c = cases.hla_window_case(g["seed"])
+        w = _hla_window(c, g)
+        fv = [i for i, v in enumerate(c["variants"]) if v[4] == 2]
+        eng = _OracleScoringEngine(w, g, fv)
+        fa, variants, ref_hap, bufs, opts = cases.hla_compat_inputs(c, eng)
+        haps = compat.getAllHLAHaplotypesInRegion(b"chr", c["win_start"], c["win_end"], fa, opts, variants, ref_hap, bufs)
+        got = [variants.index(h.variants[0]) for h in haps]
+        assert got == g["haps"], g["seed"]
+
